@@ -1,0 +1,208 @@
+/*
+ * nvo_b200 — C ABI of the B200-native (sm_100a) NeRF mapping hot path.
+ *
+ * Drop-in boundary for the operator surface that NeRF-VO's mapping thread reaches through
+ * nerfstudio -> tinycudann (reference paths relative to /root/reference):
+ *   - nerf_vo/thirdparty/tiny_cuda_nn/include/tiny-cuda-nn/cpp_api.h:86-111   (tcnn::cpp::Module:
+ *     inference / forward / backward on raw device pointers + cudaStream_t) and
+ *   - nerf_vo/thirdparty/tiny_cuda_nn/bindings/torch/tinycudann/bindings.cpp:282-336 (what pybind exposes),
+ * widened to the nerfstudio torch-path operators the field/sampler/renderer call
+ * (NS = nerf_vo/thirdparty/nerfstudio/nerfstudio): each entry point cites the function it replaces.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless its name starts with h_;
+ *   - the caller (PyTorch) owns every buffer; the library allocates nothing and keeps no state
+ *     except a thread-local error string;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - return value 0 = success; non-zero = failure, message via nvo_last_error()
+ *     (mirrors CHECK_THROW -> std::runtime_error of bindings.cpp:54-55; the Python shim raises RuntimeError);
+ *   - arithmetic follows the reference's *torch* implementation (the parity oracle): always-hashed levels,
+ *     floor/ceil corners, no +0.5 offset, biased Linear layers (SURVEY.md §8 a-notes);
+ *   - gradient outputs documented as "accumulate" are added into (atomics); the caller zero-fills.
+ */
+#ifndef NVO_B200_H
+#define NVO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NVO_MAX_LEVELS 32
+#define NVO_MAX_LAYERS 6
+
+/* dtype tags for the table / feature buffers */
+enum { NVO_F32 = 0, NVO_F16 = 1 };
+/* activations (tcnn network_config "activation"/"output_activation", NS/field_components/mlp.py:34-58) */
+/* NVO_ACT_TRUNC_EXP: exp forward, backward g*exp(clamp(x,-15,15)) (NS/field_components/activations.py:28-41) */
+enum { NVO_ACT_NONE = 0, NVO_ACT_RELU = 1, NVO_ACT_SIGMOID = 2, NVO_ACT_TANH = 3, NVO_ACT_EXP = 4, NVO_ACT_TRUNC_EXP = 5 };
+
+const char* nvo_last_error(void);
+int nvo_version(void);
+/* bindings.cpp:285 batch_size_granularity(); ours is the tcgen05 M tile */
+int nvo_batch_size_granularity(void);
+/* number of entry-point calls that enqueued GPU work since the library was loaded (bench.py's gpu_launches evidence) */
+int64_t nvo_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multiresolution hash grid — replaces NS/field_components/encodings.py:405-465 (HashEncoding.pytorch_fwd,
+ * hash_fn :405-422) and tcnn kernel_grid / kernel_grid_backward / kernel_grid_backward_input
+ * (tiny-cuda-nn/encodings/grid.h:48-349).  F (features per level) is 2.
+ * table: [n_levels * 2^log2_T, 2] row-major, level-major (encodings.py:351,381).
+ * scalings: the fp32 per-level scale computed by the caller exactly as encodings.py:347-349.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t n_levels;
+    int32_t log2_T;
+    int32_t table_dtype; /* NVO_F32 | NVO_F16 */
+    int32_t out_dtype;   /* NVO_F32 | NVO_F16 : dtype of y / dy */
+    float scalings[NVO_MAX_LEVELS];
+} nvo_grid_desc;
+
+/* y[n, 2L] = encode(x[n,3]) */
+int nvo_grid_forward(const nvo_grid_desc* d, void* stream, int64_t n, const float* x, const void* table, void* y);
+/* dtable[L*T,2] (fp32, accumulate) += scatter(dy[n,2L]) */
+int nvo_grid_backward(const nvo_grid_desc* d, void* stream, int64_t n, const float* x, const void* dy, float* dtable);
+/* dx[n,3] = d(sum(y*dy))/dx  (re-gathers the table instead of storing dy_dx, cf. grid.h:322-349) */
+int nvo_grid_backward_input(const nvo_grid_desc* d, void* stream, int64_t n, const float* x, const void* table, const void* dy, float* dx);
+/* idx[n, L, 8] int64: table row of every corner in the reference's corner order (encodings.py:435-442). Test hook. */
+int nvo_grid_indices(const nvo_grid_desc* d, void* stream, int64_t n, const float* x, int64_t* idx);
+
+/* ---------------------------------------------------------------------------------------------
+ * MLP — replaces NS/field_components/mlp.py:160-179 (MLP.pytorch_fwd) and tcnn FullyFusedMLP
+ * (tiny-cuda-nn/src/fully_fused_mlp.cu:499-557 forward, :150-258 backward, :760-830 weight gradients).
+ * params: torch layout, fp32: for each layer W[out,in] row-major then b[out], concatenated.
+ * acts[l] is the activation applied to the output of layer l (hidden layers: ReLU; last: the output activation).
+ * Per-layer activations let a trailing Linear head (e.g. PredNormalsFieldHead, NS/field_components/field_heads.py:189-204)
+ * run inside the same fused kernel.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t n_layers;
+    int32_t in_dim;
+    int32_t dims[NVO_MAX_LAYERS]; /* output width of each layer */
+    int32_t acts[NVO_MAX_LAYERS]; /* NVO_ACT_* per layer */
+} nvo_mlp_desc;
+
+int64_t nvo_mlp_n_params(const nvo_mlp_desc* d);
+/* floats of scratch per sample the training forward writes (post-activation outputs of every layer) */
+int64_t nvo_mlp_saved_per_sample(const nvo_mlp_desc* d);
+/* y[n, dims[last]]; saved (nullable => inference) [n, saved_per_sample];
+ * row_mask (nullable) [n] of 0/1: y is multiplied by it after the output activation (the `density * selector` of
+ * NS/fields/nerfacto_field.py:222, density_fields.py:115). */
+int nvo_mlp_forward(const nvo_mlp_desc* d, void* stream, int64_t n, const float* x, const float* params, const float* row_mask, float* y,
+                    float* saved);
+/* dx (nullable) [n,in_dim]; dparams (nullable, accumulate) [n_params] */
+int nvo_mlp_backward(const nvo_mlp_desc* d, void* stream, int64_t n, const float* x, const float* params, const float* saved,
+                     const float* y, const float* row_mask, const float* dy, float* dx, float* dparams);
+
+/* ---------------------------------------------------------------------------------------------
+ * Field element-wise operators.
+ * ------------------------------------------------------------------------------------------- */
+/* SceneContraction(order=inf) + (x+2)/4 + selector masking (NS/field_components/spatial_distortions.py:67-69,
+ * NS/fields/nerfacto_field.py:201-209): pos[n,3] -> x[n,3] (zeroed where outside (0,1)), selector[n] (0/1 as float).
+ * contract=0 skips the contraction and maps through the aabb instead: x = (pos - aabb_min)/(aabb_max-aabb_min). */
+int nvo_contract_forward(void* stream, int64_t n, const float* pos, float* x, float* selector);
+/* SHEncoding degree 4 on the vector as given (NS/utils/math.py:29-93): d[n,3] -> out[n,16] */
+int nvo_sh4_forward(void* stream, int64_t n, const float* d, float* out);
+/* NeRFEncoding torch path (NS/field_components/encodings.py:170-176): sin(cat[u, u+pi/2]), u = 2*pi*x_i*2^k;
+ * x[n,in_dim] -> out[n, in_dim*n_freq*2] */
+int nvo_frequency_forward(void* stream, int64_t n, int32_t in_dim, int32_t n_freq, const float* x, float* out);
+/* trunc_exp (NS/field_components/activations.py:28-41) */
+int nvo_trunc_exp_forward(void* stream, int64_t n, const float* x, float* y);
+int nvo_trunc_exp_backward(void* stream, int64_t n, const float* x, const float* dy, float* dx);
+/* out = scale * v / max(|v|, eps) on [n,3] (F.normalize; scale=-1 gives base_field.py:99 normals) and its backward */
+int nvo_normalize3_forward(void* stream, int64_t n, const float* v, float scale, float eps, float* out);
+int nvo_normalize3_backward(void* stream, int64_t n, const float* v, const float* dout, float scale, float eps, float* dv);
+/* Fused input assembly of NerfactoField.get_outputs (NS/fields/nerfacto_field.py:225-297) for B rays x S samples:
+ *   density[n]   = trunc_exp(h[:,0]) * selector                      (:214-222)
+ *   head_in[n,63]= [SH16((dir+1)/2) | h[:,1:16] | appearance32]      (:286-293, base_field.py:142)
+ *   pn_in[n,27]  = [posenc12(pos) | h[:,1:16]]                       (:278-281)
+ * appearance = embedding[cam_idx[ray]] (training) or the caller-provided mean vector when cam_idx is NULL (eval;
+ * embedding then points at ONE 32-vector).  h[n,16] is mlp_base's output.  pn_in may be NULL. */
+int nvo_field_assemble_forward(void* stream, int64_t B, int32_t S, const float* h, const float* selector, const float* directions, const float* pos,
+                               const int64_t* cam_idx, const float* embedding, float* density, float* head_in, float* pn_in);
+/* backward: dh[n,16] (overwritten) and dembedding[K,32] (accumulate, nullable) from ddensity[n] (nullable), dhead_in[n,63], dpn_in[n,27] (nullable) */
+int nvo_field_assemble_backward(void* stream, int64_t B, int32_t S, const float* h, const float* selector, const int64_t* cam_idx,
+                                const float* ddensity, const float* dhead_in, const float* dpn_in, float* dh, float* dembedding);
+
+/* ---------------------------------------------------------------------------------------------
+ * Per-ray operators.  B rays, S samples per ray.  Sample intervals are stored as bin EDGES:
+ *   sdist [B,S+1] spacing-space edges in [0,1] (RaySamples.spacing_starts/ends, NS/cameras/rays.py:113-116),
+ *   ebins [B,S+1] euclidean edges (Frustums.starts = ebins[:, :-1], ends = ebins[:, 1:]).
+ * Operators that read euclidean intervals take (starts, ends, stride): element (r,i) is starts[r*stride+i] /
+ * ends[r*stride+i]; for compact edges pass (ebins, ebins+1, S+1), for separate [B,S] arrays pass stride S.
+ * ------------------------------------------------------------------------------------------- */
+
+/* UniformLinDispPiecewiseSampler (NS/model_components/ray_samplers.py:78-128,225-248).
+ * base_bins[S+1] = torch.linspace(0,1,S+1) from the caller (bit-exact); jitter[B] in [0,1) or NULL (eval). */
+int nvo_sample_uniform(void* stream, int64_t B, int32_t S, const float* base_bins, const float* jitter, const float* nears, const float* fars,
+                       float* sdist, float* ebins);
+
+/* Frustums.get_positions (NS/cameras/rays.py:49-58): pos[B,S,3] = o + d*(start+end)/2 */
+int nvo_sample_positions(void* stream, int64_t B, int32_t S, const float* origins, const float* directions, const float* starts, const float* ends,
+                         int64_t stride, float* pos);
+
+/* RaySamples.get_weights (NS/cameras/rays.py:128-150) and its backward w.r.t. density */
+int nvo_weights_forward(void* stream, int64_t B, int32_t S, const float* starts, const float* ends, int64_t stride, const float* density,
+                        float* weights);
+int nvo_weights_backward(void* stream, int64_t B, int32_t S, const float* starts, const float* ends, int64_t stride, const float* density,
+                         const float* dweights, float* ddensity);
+
+/* PDFSampler.generate_ray_samples (ray_samplers.py:276-372) incl. the anneal pow of ProposalNetworkSampler (:602).
+ * u_base[S_out+1]: linspace(0, 1-1/n, n) (+1/(2n) already added by the caller in eval); jitter[B] or NULL.
+ * inds (nullable) int32 [B,S_out+1]: raw searchsorted(cdf,u,right) result (test hook; bit-exact contract). */
+int nvo_pdf_resample(void* stream, int64_t B, int32_t S_in, int32_t S_out, const float* weights, const float* sdist_in, const float* u_base,
+                     const float* jitter, float anneal, float histogram_padding, const float* nears, const float* fars, float* sdist_out,
+                     float* ebins_out, int32_t* inds);
+
+/* RGBRenderer('last_sample') + AccumulationRenderer + DepthRenderer(expected|median) + NormalsRenderer/NormalsShader
+ * (NS/model_components/renderers.py:70-117,199-230,287-315,333-381,427-447; shaders.py:56-77).
+ * Inputs nullable where noted; every output nullable.  eval_mode!=0 applies nan_to_num+clamp to rgb (:223-229).
+ * depth_expected is written UNCLIPPED; minmax[2] (initialised by the call) receives min/max of the mid-steps
+ * over the whole batch, nvo_clip_depth applies renderers.py:379 afterwards. */
+int nvo_render_forward(void* stream, int64_t B, int32_t S, int32_t eval_mode, const float* starts, const float* ends, int64_t stride,
+                       const float* weights, const float* rgb /*[B,S,3]*/,
+                       const float* normals /*nullable*/, const float* pred_normals /*nullable*/, float* out_rgb /*[B,3]*/, float* out_acc /*[B]*/,
+                       float* out_depth_expected /*[B]*/, float* minmax /*[2]*/, float* out_depth_median /*[B]*/, int32_t* out_median_idx /*[B]*/,
+                       float* out_normals /*[B,3]*/, float* out_pred_normals /*[B,3]*/);
+int nvo_clip_depth(void* stream, int64_t B, const float* minmax, float* depth);
+/* backward of nvo_render_forward (training mode). Any d_out_* may be NULL (= zero). dweights [B,S] is OVERWRITTEN
+ * unless accumulate_dweights!=0; drgb [B,S,3] and dpred_normals [B,S,3] (nullable) are overwritten. */
+int nvo_render_backward(void* stream, int64_t B, int32_t S, const float* starts, const float* ends, int64_t stride, const float* weights,
+                        const float* rgb, const float* normals,
+                        const float* pred_normals, const float* d_out_rgb, const float* d_out_acc, const float* d_out_depth_expected,
+                        const float* minmax, const float* d_out_normals, const float* d_out_pred_normals, int32_t accumulate_dweights,
+                        float* dweights, float* drgb, float* dpred_normals);
+
+/* ---------------------------------------------------------------------------------------------
+ * Losses (NS/model_components/losses.py). Each *_forward adds its per-batch MEAN (already divided by the element
+ * count the reference averages over) into loss[0] (accumulate, fp32); each *_backward ADDS scale * (*dscale) * dL/dweights
+ * into dweights: scale = host-side multiplier, dscale = nullable DEVICE scalar (the upstream autograd gradient), so
+ * no host synchronisation is needed to chain losses.
+ * ------------------------------------------------------------------------------------------- */
+/* distortion_loss / lossfun_distortion (losses.py:134-153) on weights [B,S], sdist [B,S+1] */
+int nvo_distortion_loss_forward(void* stream, int64_t B, int32_t S, const float* weights, const float* sdist, float* loss);
+int nvo_distortion_loss_backward(void* stream, int64_t B, int32_t S, const float* weights, const float* sdist, const float* dscale, float scale,
+                                 float* dweights);
+/* interlevel_loss for ONE proposal level (losses.py:52-130): c/w = final level (S), cp/wp = proposal level (Sp).
+ * idx_lo/idx_hi (nullable) int32 [B,S]: clamped searchsorted results (test hook). Gradient flows to wp only. */
+int nvo_interlevel_loss_forward(void* stream, int64_t B, int32_t S, int32_t Sp, const float* w, const float* c, const float* wp, const float* cp,
+                                float* loss, int32_t* idx_lo, int32_t* idx_hi);
+int nvo_interlevel_loss_backward(void* stream, int64_t B, int32_t S, int32_t Sp, const float* w, const float* c, const float* wp, const float* cp,
+                                 const float* dscale, float scale, float* dwp);
+/* ds_nerf_depth_loss through depth_loss(is_euclidean=False) (losses.py:224-246,288-324): depth_gt[B], directions_norm[B] */
+int nvo_depth_loss_forward(void* stream, int64_t B, int32_t S, const float* weights, const float* starts, const float* ends, int64_t stride,
+                           const float* depth_gt,
+                           const float* directions_norm, float sigma, float* loss);
+int nvo_depth_loss_backward(void* stream, int64_t B, int32_t S, const float* weights, const float* starts, const float* ends, int64_t stride,
+                            const float* depth_gt,
+                            const float* directions_norm, float sigma, const float* dscale, float scale, float* dweights);
+/* MSELoss on [B,3] (NS/models/nerfacto.py:362) and monosdf_normal_loss (losses.py:327-342); d_pred is overwritten with scale*grad */
+int nvo_mse_loss(void* stream, int64_t n, const float* pred, const float* target, float scale, float* loss, float* d_pred);
+int nvo_normal_loss(void* stream, int64_t B, const float* pred /*[B,3]*/, const float* gt /*[B,3]*/, float scale, float* loss, float* d_pred);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NVO_B200_H */

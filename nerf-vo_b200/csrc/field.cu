@@ -1,0 +1,279 @@
+// Element-wise field operators: scene contraction + normalisation, SH / frequency encodings, trunc_exp, 3-vector
+// normalisation, and the fused input assembly of NerfactoField.get_outputs (density activation, SH of the view
+// direction, position encoding, appearance-embedding gather, concatenation) with its backward.
+#include "nvo_common.cuh"
+
+// ---- contraction (spatial_distortions.py:67-69) + (x+2)/4 + selector (nerfacto_field.py:204-209) -----------------
+__global__ void __launch_bounds__(256) k_contract(int64_t n, const float* __restrict__ pos, float* __restrict__ x, float* __restrict__ selector) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    float p[3] = {__ldg(pos + 3 * t), __ldg(pos + 3 * t + 1), __ldg(pos + 3 * t + 2)};
+    const float mag = fmaxf(fabsf(p[0]), fmaxf(fabsf(p[1]), fabsf(p[2])));
+    bool sel = true;
+    float q[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float c = p[a];
+        if (!(mag < 1.f)) c = __fmul_rn(__fsub_rn(2.f, __fdiv_rn(1.f, mag)), __fdiv_rn(p[a], mag));
+        q[a] = __fdiv_rn(__fadd_rn(c, 2.f), 4.f);
+        sel = sel && (q[a] > 0.f) && (q[a] < 1.f);
+    }
+    const float m = sel ? 1.f : 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) x[3 * t + a] = __fmul_rn(q[a], m);
+    selector[t] = m;
+}
+
+// ---- SH degree 4 (NS/utils/math.py:45-78), constants rounded to fp32 as torch does for python-float * tensor ----
+__device__ __forceinline__ void sh16(float x, float y, float z, float* c) {
+    const float xx = __fmul_rn(x, x), yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+    c[0] = 0.28209479177387814f;
+    c[1] = __fmul_rn(0.4886025119029199f, y);
+    c[2] = __fmul_rn(0.4886025119029199f, z);
+    c[3] = __fmul_rn(0.4886025119029199f, x);
+    c[4] = __fmul_rn(__fmul_rn(1.0925484305920792f, x), y);
+    c[5] = __fmul_rn(__fmul_rn(1.0925484305920792f, y), z);
+    c[6] = __fsub_rn(__fmul_rn(0.9461746957575601f, zz), 0.31539156525251999f);
+    c[7] = __fmul_rn(__fmul_rn(1.0925484305920792f, x), z);
+    c[8] = __fmul_rn(0.5462742152960396f, __fsub_rn(xx, yy));
+    c[9] = __fmul_rn(__fmul_rn(0.5900435899266435f, y), __fsub_rn(__fmul_rn(3.f, xx), yy));
+    c[10] = __fmul_rn(__fmul_rn(__fmul_rn(2.890611442640554f, x), y), z);
+    c[11] = __fmul_rn(__fmul_rn(0.4570457994644658f, y), __fsub_rn(__fmul_rn(5.f, zz), 1.f));
+    c[12] = __fmul_rn(__fmul_rn(0.3731763325901154f, z), __fsub_rn(__fmul_rn(5.f, zz), 3.f));
+    c[13] = __fmul_rn(__fmul_rn(0.4570457994644658f, x), __fsub_rn(__fmul_rn(5.f, zz), 1.f));
+    c[14] = __fmul_rn(__fmul_rn(1.445305721320277f, z), __fsub_rn(xx, yy));
+    c[15] = __fmul_rn(__fmul_rn(0.5900435899266435f, x), __fsub_rn(xx, __fmul_rn(3.f, yy)));
+}
+
+__global__ void __launch_bounds__(256) k_sh4(int64_t n, const float* __restrict__ d, float* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    float c[16];
+    sh16(__ldg(d + 3 * t), __ldg(d + 3 * t + 1), __ldg(d + 3 * t + 2), c);
+#pragma unroll
+    for (int k = 0; k < 16; k += 4) reinterpret_cast<float4*>(out + 16 * t)[k >> 2] = make_float4(c[k], c[k + 1], c[k + 2], c[k + 3]);
+}
+
+// ---- frequency encoding, torch path (encodings.py:170-176) ------------------------------------------------------
+__device__ __forceinline__ float posenc_value(float xi, int k, bool cos_block) {
+    // u = (2*pi*x) * 2^k ; sin(u) or sin(u + pi/2)
+    const float u = __fmul_rn(__fmul_rn(6.283185307179586f, xi), (float)(1 << k));
+    return sinf(cos_block ? __fadd_rn(u, 1.5707963267948966f) : u);
+}
+
+__global__ void __launch_bounds__(256) k_frequency(int64_t n, int in_dim, int n_freq, const float* __restrict__ x, float* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int half = in_dim * n_freq, od = 2 * half;
+    if (t >= n * od) return;
+    const int64_t r = t / od;
+    int c = (int)(t - r * od);
+    const bool cosb = c >= half;
+    if (cosb) c -= half;
+    const int i = c / n_freq, k = c - i * n_freq;
+    out[t] = posenc_value(__ldg(x + r * in_dim + i), k, cosb);
+}
+
+// ---- trunc_exp -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_trunc_exp_fwd(int64_t n, const float* __restrict__ x, float* __restrict__ y) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) y[t] = expf(__ldg(x + t));
+}
+__global__ void __launch_bounds__(256) k_trunc_exp_bwd(int64_t n, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) dx[t] = __ldg(dy + t) * expf(fminf(fmaxf(__ldg(x + t), -15.f), 15.f));
+}
+
+// ---- normalize3 --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_normalize3_fwd(int64_t n, const float* __restrict__ v, float scale, float eps, float* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const float a = __ldg(v + 3 * t), b = __ldg(v + 3 * t + 1), c = __ldg(v + 3 * t + 2);
+    const float nrm = fmaxf(sqrtf(a * a + b * b + c * c), eps);
+    out[3 * t] = scale * (a / nrm);
+    out[3 * t + 1] = scale * (b / nrm);
+    out[3 * t + 2] = scale * (c / nrm);
+}
+__global__ void __launch_bounds__(256) k_normalize3_bwd(int64_t n, const float* __restrict__ v, const float* __restrict__ dout, float scale, float eps,
+                                                        float* __restrict__ dv) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const float a = __ldg(v + 3 * t), b = __ldg(v + 3 * t + 1), c = __ldg(v + 3 * t + 2);
+    const float g0 = scale * __ldg(dout + 3 * t), g1 = scale * __ldg(dout + 3 * t + 1), g2 = scale * __ldg(dout + 3 * t + 2);
+    const float r = sqrtf(a * a + b * b + c * c);
+    if (r > eps) {
+        const float dot = (a * g0 + b * g1 + c * g2) / (r * r * r);
+        dv[3 * t] = g0 / r - a * dot;
+        dv[3 * t + 1] = g1 / r - b * dot;
+        dv[3 * t + 2] = g2 / r - c * dot;
+    } else {  // clamped denominator is a constant
+        dv[3 * t] = g0 / eps;
+        dv[3 * t + 1] = g1 / eps;
+        dv[3 * t + 2] = g2 / eps;
+    }
+}
+
+// ---- fused head-input assembly --------------------------------------------------------------------------------
+#define GEO 15
+#define APP 32
+#define HEAD_IN 63
+#define PN_IN 27
+
+__global__ void __launch_bounds__(256)
+    k_assemble_fwd(int64_t B, int S, const float* __restrict__ h, const float* __restrict__ selector, const float* __restrict__ dirs,
+                   const float* __restrict__ pos, const int64_t* __restrict__ cam_idx, const float* __restrict__ embedding, float* __restrict__ density,
+                   float* __restrict__ head_in, float* __restrict__ pn_in) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * S) return;
+    const int64_t r = t / S;
+    float hv[16];
+#pragma unroll
+    for (int k = 0; k < 16; k += 4) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(h + 16 * t) + (k >> 2));
+        hv[k] = q.x, hv[k + 1] = q.y, hv[k + 2] = q.z, hv[k + 3] = q.w;
+    }
+    if (density) density[t] = __fmul_rn(expf(hv[0]), __ldg(selector + t));
+    float* o = head_in + HEAD_IN * t;
+    float c[16];
+    // get_normalized_directions (base_field.py:142): (d + 1) / 2
+    sh16(__fdiv_rn(__fadd_rn(__ldg(dirs + 3 * r), 1.f), 2.f), __fdiv_rn(__fadd_rn(__ldg(dirs + 3 * r + 1), 1.f), 2.f),
+         __fdiv_rn(__fadd_rn(__ldg(dirs + 3 * r + 2), 1.f), 2.f), c);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) o[k] = c[k];
+#pragma unroll
+    for (int k = 0; k < GEO; ++k) o[16 + k] = hv[1 + k];
+    const float* e = cam_idx ? embedding + APP * __ldg(cam_idx + r) : embedding;
+#pragma unroll 8
+    for (int k = 0; k < APP; ++k) o[16 + GEO + k] = __ldg(e + k);
+    if (pn_in) {
+        float* q = pn_in + PN_IN * t;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float xi = __ldg(pos + 3 * t + i);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                q[i * 2 + k] = posenc_value(xi, k, false);
+                q[6 + i * 2 + k] = posenc_value(xi, k, true);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < GEO; ++k) q[12 + k] = hv[1 + k];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    k_assemble_bwd(int64_t B, int S, const float* __restrict__ h, const float* __restrict__ selector, const int64_t* __restrict__ cam_idx,
+                   const float* __restrict__ ddensity, const float* __restrict__ dhead_in, const float* __restrict__ dpn_in, float* __restrict__ dh,
+                   float* __restrict__ dembedding) {
+    // one warp per ray when accumulating the appearance-embedding gradient: lanes stride over samples, then a warp
+    // reduction leaves ONE atomicAdd per (ray, channel) instead of S.
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= B) return;
+    float eacc = 0.f;  // lane k accumulates channel k of the embedding gradient
+    for (int s0 = 0; s0 < S; s0 += 32) {
+        const int s = s0 + lane;
+        const bool live = s < S;
+        const int64_t t = r * S + (live ? s : 0);
+        if (live) {
+            float g[16];
+            // trunc_exp backward (activations.py:38-41) with the selector product
+            const float h0 = __ldg(h + 16 * t);
+            g[0] = ddensity ? __ldg(ddensity + t) * __ldg(selector + t) * expf(fminf(fmaxf(h0, -15.f), 15.f)) : 0.f;
+#pragma unroll
+            for (int k = 0; k < GEO; ++k) {
+                float v = __ldg(dhead_in + HEAD_IN * t + 16 + k);
+                if (dpn_in) v += __ldg(dpn_in + PN_IN * t + 12 + k);
+                g[1 + k] = v;
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k += 4) reinterpret_cast<float4*>(dh + 16 * t)[k >> 2] = make_float4(g[k], g[k + 1], g[k + 2], g[k + 3]);
+        }
+        if (dembedding && cam_idx) {
+            // transpose-reduce: for each of the 32 samples of this chunk add its 32 appearance gradients; lane k keeps channel k
+            for (int j = 0; j < 32; ++j) {
+                if (s0 + j < S) eacc += __ldg(dhead_in + HEAD_IN * (r * S + s0 + j) + 16 + GEO + lane);
+            }
+        }
+    }
+    if (dembedding && cam_idx) atomicAdd(dembedding + APP * __ldg(cam_idx + r) + lane, eacc);
+}
+
+// ---- C ABI ----------------------------------------------------------------------------------------------------
+extern "C" int nvo_contract_forward(void* stream, int64_t n, const float* pos, float* x, float* selector) {
+    NVO_CHECK(n >= 0, "contract_forward: negative size");
+    if (n == 0) return 0;
+    NVO_CHECK(pos && x && selector, "contract_forward: null pointer");
+    k_contract<<<nvo_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(n, pos, x, selector);
+    NVO_CUDA_LAUNCH_CHECK("contract_forward");
+    return 0;
+}
+extern "C" int nvo_sh4_forward(void* stream, int64_t n, const float* d, float* out) {
+    NVO_CHECK(n >= 0, "sh4_forward: negative size");
+    if (n == 0) return 0;
+    NVO_CHECK(d && out, "sh4_forward: null pointer");
+    k_sh4<<<nvo_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(n, d, out);
+    NVO_CUDA_LAUNCH_CHECK("sh4_forward");
+    return 0;
+}
+extern "C" int nvo_frequency_forward(void* stream, int64_t n, int32_t in_dim, int32_t n_freq, const float* x, float* out) {
+    NVO_CHECK(n >= 0 && in_dim >= 1 && n_freq >= 1 && n_freq <= 24, "frequency_forward: bad shape");
+    if (n == 0) return 0;
+    NVO_CHECK(x && out, "frequency_forward: null pointer");
+    k_frequency<<<nvo_blocks(n * in_dim * n_freq * 2, 256), 256, 0, (cudaStream_t)stream>>>(n, in_dim, n_freq, x, out);
+    NVO_CUDA_LAUNCH_CHECK("frequency_forward");
+    return 0;
+}
+extern "C" int nvo_trunc_exp_forward(void* stream, int64_t n, const float* x, float* y) {
+    NVO_CHECK(n >= 0, "trunc_exp_forward: negative size");
+    if (n == 0) return 0;
+    NVO_CHECK(x && y, "trunc_exp_forward: null pointer");
+    k_trunc_exp_fwd<<<nvo_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(n, x, y);
+    NVO_CUDA_LAUNCH_CHECK("trunc_exp_forward");
+    return 0;
+}
+extern "C" int nvo_trunc_exp_backward(void* stream, int64_t n, const float* x, const float* dy, float* dx) {
+    NVO_CHECK(n >= 0, "trunc_exp_backward: negative size");
+    if (n == 0) return 0;
+    NVO_CHECK(x && dy && dx, "trunc_exp_backward: null pointer");
+    k_trunc_exp_bwd<<<nvo_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(n, x, dy, dx);
+    NVO_CUDA_LAUNCH_CHECK("trunc_exp_backward");
+    return 0;
+}
+extern "C" int nvo_normalize3_forward(void* stream, int64_t n, const float* v, float scale, float eps, float* out) {
+    NVO_CHECK(n >= 0, "normalize3_forward: negative size");
+    if (n == 0) return 0;
+    NVO_CHECK(v && out, "normalize3_forward: null pointer");
+    k_normalize3_fwd<<<nvo_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(n, v, scale, eps, out);
+    NVO_CUDA_LAUNCH_CHECK("normalize3_forward");
+    return 0;
+}
+extern "C" int nvo_normalize3_backward(void* stream, int64_t n, const float* v, const float* dout, float scale, float eps, float* dv) {
+    NVO_CHECK(n >= 0, "normalize3_backward: negative size");
+    if (n == 0) return 0;
+    NVO_CHECK(v && dout && dv, "normalize3_backward: null pointer");
+    k_normalize3_bwd<<<nvo_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(n, v, dout, scale, eps, dv);
+    NVO_CUDA_LAUNCH_CHECK("normalize3_backward");
+    return 0;
+}
+extern "C" int nvo_field_assemble_forward(void* stream, int64_t B, int32_t S, const float* h, const float* selector, const float* directions,
+                                          const float* pos, const int64_t* cam_idx, const float* embedding, float* density, float* head_in,
+                                          float* pn_in) {
+    NVO_CHECK(B >= 0 && S >= 1, "field_assemble_forward: bad shape");
+    if (B == 0) return 0;
+    NVO_CHECK(h && directions && embedding && head_in, "field_assemble_forward: null pointer");
+    NVO_CHECK(!density || selector, "field_assemble_forward: selector required for density");
+    NVO_CHECK(!pn_in || pos, "field_assemble_forward: positions required for pn_in");
+    k_assemble_fwd<<<nvo_blocks(B * S, 256), 256, 0, (cudaStream_t)stream>>>(B, S, h, selector, directions, pos, cam_idx, embedding, density, head_in, pn_in);
+    NVO_CUDA_LAUNCH_CHECK("field_assemble_forward");
+    return 0;
+}
+extern "C" int nvo_field_assemble_backward(void* stream, int64_t B, int32_t S, const float* h, const float* selector, const int64_t* cam_idx,
+                                           const float* ddensity, const float* dhead_in, const float* dpn_in, float* dh, float* dembedding) {
+    NVO_CHECK(B >= 0 && S >= 1, "field_assemble_backward: bad shape");
+    if (B == 0) return 0;
+    NVO_CHECK(h && dhead_in && dh, "field_assemble_backward: null pointer");
+    NVO_CHECK(!ddensity || selector, "field_assemble_backward: selector required for ddensity");
+    k_assemble_bwd<<<nvo_blocks(B * 32, 256), 256, 0, (cudaStream_t)stream>>>(B, S, h, selector, cam_idx, ddensity, dhead_in, dpn_in, dh, dembedding);
+    NVO_CUDA_LAUNCH_CHECK("field_assemble_backward");
+    return 0;
+}

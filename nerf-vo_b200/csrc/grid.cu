@@ -1,0 +1,275 @@
+// Multiresolution hash grid: gather / trilinear forward, atomic-scatter backward, input gradient.
+// Semantics = the reference's torch path (NS/field_components/encodings.py:405-465):
+//   scaled = x * scale_l (fp32), corners floor/ceil, hash (x*1 ^ y*2654435761 ^ z*805459861) mod 2^k + l*2^k,
+//   interpolation order x, y, z with separately-rounded mul/add (no FMA contraction) so that the fp32 path
+//   reproduces the reference bit for bit.
+// Work decomposition: one thread per (sample, level) with level fastest, so a warp's 32 threads cover
+// 32/L consecutive samples: x loads are near-broadcast, the y / dy accesses of a warp are one contiguous
+// 256-byte run (fp32) and every thread keeps 8 independent 8-byte (float2) or 4-byte (half2) gathers in flight.
+#include "nvo_common.cuh"
+
+struct GridP {
+    int L;
+    int log2T;
+    float scale[NVO_MAX_LEVELS];
+};
+
+#define PRIME_Y 2654435761u
+#define PRIME_Z 805459861u
+
+struct Corner {
+    float ox, oy, oz;       // fractional offsets
+    uint32_t hx[2], hy[2], hz[2];  // per-axis hash terms for floor (0) / ceil (1)
+};
+
+__device__ __forceinline__ Corner make_corner(float px, float py, float pz, float scale) {
+    Corner c;
+    const float sx = __fmul_rn(px, scale), sy = __fmul_rn(py, scale), sz = __fmul_rn(pz, scale);
+    const float fx = floorf(sx), fy = floorf(sy), fz = floorf(sz);
+    c.ox = __fsub_rn(sx, fx);
+    c.oy = __fsub_rn(sy, fy);
+    c.oz = __fsub_rn(sz, fz);
+    const int ifx = (int)fx, ify = (int)fy, ifz = (int)fz;
+    const int icx = (int)ceilf(sx), icy = (int)ceilf(sy), icz = (int)ceilf(sz);
+    c.hx[0] = (uint32_t)ifx;
+    c.hx[1] = (uint32_t)icx;
+    c.hy[0] = (uint32_t)ify * PRIME_Y;
+    c.hy[1] = (uint32_t)icy * PRIME_Y;
+    c.hz[0] = (uint32_t)ifz * PRIME_Z;
+    c.hz[1] = (uint32_t)icz * PRIME_Z;
+    return c;
+}
+
+// reference corner k -> (x,y,z) picks ceil(1)/floor(0): encodings.py:435-442
+//   k: 0=(c,c,c) 1=(c,f,c) 2=(f,f,c) 3=(f,c,c) 4=(c,c,f) 5=(c,f,f) 6=(f,f,f) 7=(f,c,f); bit k of each mask
+#define SEL_X(k) ((0x33 >> (k)) & 1)
+#define SEL_Y(k) ((0x99 >> (k)) & 1)
+#define SEL_Z(k) ((0x0F >> (k)) & 1)
+
+__device__ __forceinline__ uint32_t corner_index(const Corner& c, int sx, int sy, int sz, uint32_t mask) {
+    return (c.hx[sx] ^ c.hy[sy] ^ c.hz[sz]) & mask;
+}
+
+__device__ __forceinline__ float2 load_row(const float2* t, size_t i) { return __ldg(t + i); }
+__device__ __forceinline__ float2 load_row(const __half2* t, size_t i) { return __half22float2(__ldg(t + i)); }
+
+__device__ __forceinline__ void store_feat(float* y, int64_t t, float a, float b) { reinterpret_cast<float2*>(y)[t] = make_float2(a, b); }
+__device__ __forceinline__ void store_feat(__half* y, int64_t t, float a, float b) { reinterpret_cast<__half2*>(y)[t] = __floats2half2_rn(a, b); }
+__device__ __forceinline__ float2 load_feat(const float* y, int64_t t) { return __ldg(reinterpret_cast<const float2*>(y) + t); }
+__device__ __forceinline__ float2 load_feat(const __half* y, int64_t t) { return __half22float2(__ldg(reinterpret_cast<const __half2*>(y) + t)); }
+
+// a*w + b*(1-w) with the reference's rounding sequence (mul, mul, add)
+__device__ __forceinline__ float lerp_ref(float a, float b, float w, float omw) { return __fadd_rn(__fmul_rn(a, w), __fmul_rn(b, omw)); }
+
+template <typename RowT, typename OutT>
+__global__ void __launch_bounds__(256) k_grid_fwd(const __grid_constant__ GridP p, int64_t total, const float* __restrict__ x,
+                                                  const RowT* __restrict__ table, OutT* __restrict__ y) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int64_t s = t / p.L;
+    const int l = (int)(t - s * p.L);
+    const float px = __ldg(x + 3 * s), py = __ldg(x + 3 * s + 1), pz = __ldg(x + 3 * s + 2);
+    const Corner c = make_corner(px, py, pz, p.scale[l]);
+    const uint32_t mask = (1u << p.log2T) - 1u;
+    const RowT* slab = table + ((size_t)l << p.log2T);
+    // issue all 8 gathers before any use
+    float2 f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = load_row(slab, corner_index(c, SEL_X(k), SEL_Y(k), SEL_Z(k), mask));
+    const float mx = __fsub_rn(1.f, c.ox), my = __fsub_rn(1.f, c.oy), mz = __fsub_rn(1.f, c.oz);
+    float out[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+#define FJ(k) (j == 0 ? f[k].x : f[k].y)
+        const float f03 = lerp_ref(FJ(0), FJ(3), c.ox, mx);
+        const float f12 = lerp_ref(FJ(1), FJ(2), c.ox, mx);
+        const float f56 = lerp_ref(FJ(5), FJ(6), c.ox, mx);
+        const float f47 = lerp_ref(FJ(4), FJ(7), c.ox, mx);
+        const float f0312 = lerp_ref(f03, f12, c.oy, my);
+        const float f4756 = lerp_ref(f47, f56, c.oy, my);
+        out[j] = lerp_ref(f0312, f4756, c.oz, mz);
+#undef FJ
+    }
+    store_feat(y, t, out[0], out[1]);
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) k_grid_bwd(const __grid_constant__ GridP p, int64_t total, const float* __restrict__ x,
+                                                  const OutT* __restrict__ dy, float* __restrict__ dtable) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int64_t s = t / p.L;
+    const int l = (int)(t - s * p.L);
+    const float2 g = load_feat(dy, t);
+    if (g.x == 0.f && g.y == 0.f) return;  // adding zeros changes nothing (masked / padded samples)
+    const float px = __ldg(x + 3 * s), py = __ldg(x + 3 * s + 1), pz = __ldg(x + 3 * s + 2);
+    const Corner c = make_corner(px, py, pz, p.scale[l]);
+    const uint32_t mask = (1u << p.log2T) - 1u;
+    float* slab = dtable + (((size_t)l << p.log2T) << 1);
+    const float wx[2] = {1.f - c.ox, c.ox}, wy[2] = {1.f - c.oy, c.oy}, wz[2] = {1.f - c.oz, c.oz};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int sx = SEL_X(k), sy = SEL_Y(k), sz = SEL_Z(k);
+        const float w = wz[sz] * wy[sy] * wx[sx];
+        const uint32_t idx = corner_index(c, sx, sy, sz, mask);
+        nvo_red_add_v2(slab + 2 * (size_t)idx, g.x * w, g.y * w);
+    }
+}
+
+// dL/dx: one thread per (sample, level) computes its level's contribution, then the L lanes of a sample are
+// summed with warp shuffles when L divides 32 (main grid, L=16), else with atomics (L=5 proposals).
+template <typename RowT, typename OutT>
+__global__ void __launch_bounds__(256) k_grid_bwd_input(const __grid_constant__ GridP p, int64_t total, const float* __restrict__ x,
+                                                        const RowT* __restrict__ table, const OutT* __restrict__ dy, float* __restrict__ dx,
+                                                        int shuffle_reduce) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = t < total;
+    const int64_t tt = live ? t : total - 1;
+    const int64_t s = tt / p.L;
+    const int l = (int)(tt - s * p.L);
+    const float scale = p.scale[l];
+    const float px = __ldg(x + 3 * s), py = __ldg(x + 3 * s + 1), pz = __ldg(x + 3 * s + 2);
+    const Corner c = make_corner(px, py, pz, scale);
+    const uint32_t mask = (1u << p.log2T) - 1u;
+    const RowT* slab = table + ((size_t)l << p.log2T);
+    float2 f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = load_row(slab, corner_index(c, SEL_X(k), SEL_Y(k), SEL_Z(k), mask));
+    float2 g = load_feat(dy, tt);
+    if (!live) g = make_float2(0.f, 0.f);
+    const float mx = 1.f - c.ox, my = 1.f - c.oy, mz = 1.f - c.oz;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+#define FJ(k) (j == 0 ? f[k].x : f[k].y)
+        const float gj = j == 0 ? g.x : g.y;
+        const float f03 = FJ(0) * c.ox + FJ(3) * mx, f12 = FJ(1) * c.ox + FJ(2) * mx;
+        const float f56 = FJ(5) * c.ox + FJ(6) * mx, f47 = FJ(4) * c.ox + FJ(7) * mx;
+        const float f0312 = f03 * c.oy + f12 * my, f4756 = f47 * c.oy + f56 * my;
+        // d/d oz, d/d oy, d/d ox of the nested lerp
+        gz += gj * (f0312 - f4756);
+        gy += gj * (c.oz * (f03 - f12) + mz * (f47 - f56));
+        gx += gj * (c.oz * (c.oy * (FJ(0) - FJ(3)) + my * (FJ(1) - FJ(2))) + mz * (c.oy * (FJ(4) - FJ(7)) + my * (FJ(5) - FJ(6))));
+#undef FJ
+    }
+    gx *= scale;
+    gy *= scale;
+    gz *= scale;
+    if (shuffle_reduce) {
+        // L is a power of two dividing 32: lanes [k*L, (k+1)*L) hold one sample
+        for (int o = p.L >> 1; o > 0; o >>= 1) {
+            gx += __shfl_xor_sync(0xffffffffu, gx, o);
+            gy += __shfl_xor_sync(0xffffffffu, gy, o);
+            gz += __shfl_xor_sync(0xffffffffu, gz, o);
+        }
+        if (live && l == 0) {
+            dx[3 * s] = gx;
+            dx[3 * s + 1] = gy;
+            dx[3 * s + 2] = gz;
+        }
+    } else if (live) {
+        atomicAdd(dx + 3 * s, gx);
+        atomicAdd(dx + 3 * s + 1, gy);
+        atomicAdd(dx + 3 * s + 2, gz);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_grid_indices(const __grid_constant__ GridP p, int64_t total, const float* __restrict__ x, int64_t* __restrict__ idx) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int64_t s = t / p.L;
+    const int l = (int)(t - s * p.L);
+    const Corner c = make_corner(x[3 * s], x[3 * s + 1], x[3 * s + 2], p.scale[l]);
+    const uint32_t mask = (1u << p.log2T) - 1u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        idx[t * 8 + k] = (int64_t)corner_index(c, SEL_X(k), SEL_Y(k), SEL_Z(k), mask) + ((int64_t)l << p.log2T);
+}
+
+static int make_params(const nvo_grid_desc* d, GridP* p) {
+    NVO_CHECK(d != nullptr, "grid: null descriptor");
+    NVO_CHECK(d->n_levels >= 1 && d->n_levels <= NVO_MAX_LEVELS, "grid: n_levels=%d out of range [1,%d]", d->n_levels, NVO_MAX_LEVELS);
+    NVO_CHECK(d->log2_T >= 1 && d->log2_T <= 30, "grid: log2_T=%d out of range [1,30]", d->log2_T);
+    NVO_CHECK(d->table_dtype == NVO_F32 || d->table_dtype == NVO_F16, "grid: bad table_dtype %d", d->table_dtype);
+    NVO_CHECK(d->out_dtype == NVO_F32 || d->out_dtype == NVO_F16, "grid: bad out_dtype %d", d->out_dtype);
+    p->L = d->n_levels;
+    p->log2T = d->log2_T;
+    for (int i = 0; i < NVO_MAX_LEVELS; ++i) p->scale[i] = i < d->n_levels ? d->scalings[i] : 0.f;
+    return 0;
+}
+
+extern "C" int nvo_grid_forward(const nvo_grid_desc* d, void* stream, int64_t n, const float* x, const void* table, void* y) {
+    GridP p;
+    if (int e = make_params(d, &p)) return e;
+    NVO_CHECK(n >= 0, "grid_forward: negative batch");
+    if (n == 0) return 0;
+    NVO_CHECK(x && table && y, "grid_forward: null pointer");
+    const int64_t total = n * p.L;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned int g = nvo_blocks(total, 256);
+    if (d->table_dtype == NVO_F32 && d->out_dtype == NVO_F32)
+        k_grid_fwd<float2, float><<<g, 256, 0, st>>>(p, total, x, (const float2*)table, (float*)y);
+    else if (d->table_dtype == NVO_F32)
+        k_grid_fwd<float2, __half><<<g, 256, 0, st>>>(p, total, x, (const float2*)table, (__half*)y);
+    else if (d->out_dtype == NVO_F32)
+        k_grid_fwd<__half2, float><<<g, 256, 0, st>>>(p, total, x, (const __half2*)table, (float*)y);
+    else
+        k_grid_fwd<__half2, __half><<<g, 256, 0, st>>>(p, total, x, (const __half2*)table, (__half*)y);
+    NVO_CUDA_LAUNCH_CHECK("grid_forward");
+    return 0;
+}
+
+extern "C" int nvo_grid_backward(const nvo_grid_desc* d, void* stream, int64_t n, const float* x, const void* dy, float* dtable) {
+    GridP p;
+    if (int e = make_params(d, &p)) return e;
+    NVO_CHECK(n >= 0, "grid_backward: negative batch");
+    if (n == 0) return 0;
+    NVO_CHECK(x && dy && dtable, "grid_backward: null pointer");
+    const int64_t total = n * p.L;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned int g = nvo_blocks(total, 256);
+    if (d->out_dtype == NVO_F32)
+        k_grid_bwd<float><<<g, 256, 0, st>>>(p, total, x, (const float*)dy, dtable);
+    else
+        k_grid_bwd<__half><<<g, 256, 0, st>>>(p, total, x, (const __half*)dy, dtable);
+    NVO_CUDA_LAUNCH_CHECK("grid_backward");
+    return 0;
+}
+
+extern "C" int nvo_grid_backward_input(const nvo_grid_desc* d, void* stream, int64_t n, const float* x, const void* table, const void* dy, float* dx) {
+    GridP p;
+    if (int e = make_params(d, &p)) return e;
+    NVO_CHECK(n >= 0, "grid_backward_input: negative batch");
+    if (n == 0) return 0;
+    NVO_CHECK(x && table && dy && dx, "grid_backward_input: null pointer");
+    const int64_t total = n * p.L;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned int g = nvo_blocks(total, 256);
+    const int shuffle = (p.L <= 32 && (p.L & (p.L - 1)) == 0) ? 1 : 0;
+    if (!shuffle) {
+        cudaError_t e = cudaMemsetAsync(dx, 0, sizeof(float) * 3 * n, st);
+        NVO_CHECK(e == cudaSuccess, "grid_backward_input: memset failed: %s", cudaGetErrorString(e));
+    }
+    if (d->table_dtype == NVO_F32 && d->out_dtype == NVO_F32)
+        k_grid_bwd_input<float2, float><<<g, 256, 0, st>>>(p, total, x, (const float2*)table, (const float*)dy, dx, shuffle);
+    else if (d->table_dtype == NVO_F32)
+        k_grid_bwd_input<float2, __half><<<g, 256, 0, st>>>(p, total, x, (const float2*)table, (const __half*)dy, dx, shuffle);
+    else if (d->out_dtype == NVO_F32)
+        k_grid_bwd_input<__half2, float><<<g, 256, 0, st>>>(p, total, x, (const __half2*)table, (const float*)dy, dx, shuffle);
+    else
+        k_grid_bwd_input<__half2, __half><<<g, 256, 0, st>>>(p, total, x, (const __half2*)table, (const __half*)dy, dx, shuffle);
+    NVO_CUDA_LAUNCH_CHECK("grid_backward_input");
+    return 0;
+}
+
+extern "C" int nvo_grid_indices(const nvo_grid_desc* d, void* stream, int64_t n, const float* x, int64_t* idx) {
+    GridP p;
+    if (int e = make_params(d, &p)) return e;
+    NVO_CHECK(n >= 0, "grid_indices: negative batch");
+    if (n == 0) return 0;
+    NVO_CHECK(x && idx, "grid_indices: null pointer");
+    const int64_t total = n * p.L;
+    k_grid_indices<<<nvo_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(p, total, x, idx);
+    NVO_CUDA_LAUNCH_CHECK("grid_indices");
+    return 0;
+}

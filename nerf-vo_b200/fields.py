@@ -1,0 +1,205 @@
+"""NerfactoField and HashMLPDensityField with the reference's API
+(NS/fields/base_field.py:40-142, nerfacto_field.py:43-297, density_fields.py:34-119)."""
+from __future__ import annotations
+
+from enum import Enum
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import ops
+from .field_components import MLP, Embedding, HashEncoding, MLPWithHashEncoding, NeRFEncoding, SceneContraction, SHEncoding, repack
+from .rays import Frustums, RaySamples
+
+
+class FieldHeadNames(Enum):
+    """NS/field_components/field_heads.py:27-43 (the names the nerfacto path produces)."""
+
+    RGB = "rgb"
+    DENSITY = "density"
+    NORMALS = "normals"
+    PRED_NORMALS = "pred_normals"
+
+
+class PredNormalsFieldHead(nn.Module):
+    """Linear(in_dim, 3) + Tanh + normalize (NS/field_components/field_heads.py:189-204); keeps the `net` key."""
+
+    def __init__(self, in_dim: int) -> None:
+        super().__init__()
+        self.net = nn.Linear(in_dim, 3)
+
+
+class Field(nn.Module):
+    def __init__(self) -> None:
+        super().__init__()
+        self._sample_locations = None
+        self._density_before_activation = None
+
+    def density_fn(self, positions: torch.Tensor, times: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Density at explicit positions [..., 3] -> [..., 1] (NS/fields/base_field.py:48-68)."""
+        del times
+        density, _ = self._density_from_positions(positions)
+        return density
+
+    def get_density(self, ray_samples: RaySamples):
+        return self._density_from_positions(ray_samples.frustums.get_positions())
+
+    def forward(self, ray_samples: RaySamples, compute_normals: bool = False) -> Dict[FieldHeadNames, torch.Tensor]:
+        density, density_embedding = self.get_density(ray_samples)
+        field_outputs = self.get_outputs(ray_samples, density_embedding=density_embedding)
+        field_outputs[FieldHeadNames.DENSITY] = density
+        if compute_normals:
+            field_outputs[FieldHeadNames.NORMALS] = self.get_normals()
+        return field_outputs
+
+
+class HashMLPDensityField(Field):
+    """Proposal density field (NS/fields/density_fields.py:34-119)."""
+
+    def __init__(self, aabb: torch.Tensor, num_layers: int = 2, hidden_dim: int = 64, spatial_distortion: Optional[nn.Module] = None,
+                 use_linear: bool = False, num_levels: int = 8, max_res: int = 1024, base_res: int = 16, log2_hashmap_size: int = 18,
+                 features_per_level: int = 2, implementation: str = "nvo_b200") -> None:
+        super().__init__()
+        if spatial_distortion is None or not isinstance(spatial_distortion, SceneContraction):
+            raise NotImplementedError("nvo_b200 fields require SceneContraction(order=inf) (the NeRF-VO configuration)")
+        self.register_buffer("aabb", aabb)
+        self.spatial_distortion = spatial_distortion
+        self.use_linear = use_linear
+        self.register_buffer("max_res", torch.tensor(max_res))
+        self.register_buffer("num_levels", torch.tensor(num_levels))
+        self.register_buffer("log2_hashmap_size", torch.tensor(log2_hashmap_size))
+        self.encoding = HashEncoding(num_levels=num_levels, min_res=base_res, max_res=max_res, log2_hashmap_size=log2_hashmap_size,
+                                     features_per_level=features_per_level)
+        if not use_linear:
+            # density = trunc_exp(mlp(x)) * selector is evaluated inside the MLP kernel (output activation + row mask)
+            network = MLP(in_dim=self.encoding.get_out_dim(), num_layers=num_layers, layer_width=hidden_dim, out_dim=1, activation=nn.ReLU(),
+                          out_activation="trunc_exp")
+            self.mlp_base = nn.Sequential(self.encoding, network)
+        else:
+            self.linear = MLP(in_dim=self.encoding.get_out_dim(), num_layers=1, layer_width=1, out_dim=1, out_activation="trunc_exp")
+
+    def _density_from_positions(self, positions: torch.Tensor) -> Tuple[torch.Tensor, None]:
+        x, sel = ops.contract_normalize(positions)
+        feat = self.encoding(x)
+        net = self.mlp_base[1] if not self.use_linear else self.linear
+        density = net(feat, row_mask=sel)
+        return density.view(*positions.shape[:-1], 1), None
+
+    def get_outputs(self, ray_samples: RaySamples, density_embedding: Optional[torch.Tensor] = None) -> dict:
+        return {}
+
+
+class NerfactoField(Field):
+    """NS/fields/nerfacto_field.py:43-297 (no transient / semantic heads: NeRF-VO does not enable them)."""
+
+    def __init__(self, aabb: torch.Tensor, num_images: int, num_layers: int = 2, hidden_dim: int = 64, geo_feat_dim: int = 15, num_levels: int = 16,
+                 base_res: int = 16, max_res: int = 2048, log2_hashmap_size: int = 19, num_layers_color: int = 3, num_layers_transient: int = 2,
+                 features_per_level: int = 2, hidden_dim_color: int = 64, hidden_dim_transient: int = 64, appearance_embedding_dim: int = 32,
+                 transient_embedding_dim: int = 16, use_transient_embedding: bool = False, use_semantics: bool = False, num_semantic_classes: int = 100,
+                 pass_semantic_gradients: bool = False, use_pred_normals: bool = False, use_average_appearance_embedding: bool = False,
+                 spatial_distortion: Optional[nn.Module] = None, implementation: str = "nvo_b200") -> None:
+        super().__init__()
+        if use_transient_embedding or use_semantics:
+            raise NotImplementedError("transient / semantic heads are outside the NeRF-VO mapping path")
+        if spatial_distortion is None or not isinstance(spatial_distortion, SceneContraction):
+            raise NotImplementedError("nvo_b200 fields require SceneContraction(order=inf) (the NeRF-VO configuration)")
+        if geo_feat_dim != 15 or appearance_embedding_dim != 32:
+            raise NotImplementedError("fused input assembly is specialised for geo_feat_dim=15, appearance_embedding_dim=32 (nerfacto defaults)")
+        self.register_buffer("aabb", aabb)
+        self.geo_feat_dim = geo_feat_dim
+        self.register_buffer("max_res", torch.tensor(max_res))
+        self.register_buffer("num_levels", torch.tensor(num_levels))
+        self.register_buffer("log2_hashmap_size", torch.tensor(log2_hashmap_size))
+        self.spatial_distortion = spatial_distortion
+        self.num_images = num_images
+        self.appearance_embedding_dim = appearance_embedding_dim
+        self.embedding_appearance = Embedding(num_images, appearance_embedding_dim)
+        self.use_average_appearance_embedding = use_average_appearance_embedding
+        self.use_pred_normals = use_pred_normals
+        self.base_res = base_res
+        self.direction_encoding = SHEncoding(levels=4)
+        self.position_encoding = NeRFEncoding(in_dim=3, num_frequencies=2, min_freq_exp=0, max_freq_exp=1)
+        self.mlp_base = MLPWithHashEncoding(num_levels=num_levels, min_res=base_res, max_res=max_res, log2_hashmap_size=log2_hashmap_size,
+                                            features_per_level=features_per_level, num_layers=num_layers, layer_width=hidden_dim,
+                                            out_dim=1 + geo_feat_dim, activation=nn.ReLU(), out_activation=None)
+        if use_pred_normals:
+            self.mlp_pred_normals = MLP(in_dim=geo_feat_dim + self.position_encoding.get_out_dim(), num_layers=3, layer_width=64,
+                                        out_dim=hidden_dim_transient, activation=nn.ReLU(), out_activation=None)
+            self.field_head_pred_normals = PredNormalsFieldHead(in_dim=self.mlp_pred_normals.get_out_dim())
+            # mlp_pred_normals (3 layers) + Linear head + Tanh run as ONE 4-layer fused network
+            w = 64
+            self._pn_spec = ops.MlpSpec(self.mlp_pred_normals.in_dim, (w, w, hidden_dim_transient, 3), acts=("relu", "relu", "none", "tanh"))
+        self.mlp_head = MLP(in_dim=self.direction_encoding.get_out_dim() + geo_feat_dim + appearance_embedding_dim, num_layers=num_layers_color,
+                            layer_width=hidden_dim_color, out_dim=3, activation=nn.ReLU(), out_activation=nn.Sigmoid())
+        self._cache = None
+
+    # -- density -----------------------------------------------------------------------------------------
+    def _density_from_positions(self, positions: torch.Tensor):
+        shape = positions.shape[:-1]
+        x, sel = ops.contract_normalize(positions)
+        feat = self.mlp_base.encoder(x)
+        h = self.mlp_base.mlp(feat)  # [n,16]: raw density + geo features (nerfacto_field.py:213-215)
+        self._cache = {"x": x, "sel": sel, "h": h, "feat": feat, "shape": shape, "positions": positions}
+        self._sample_locations = x.view(*shape, 3)
+        self._density_before_activation = h[:, :1].view(*shape, 1)
+        density = (ops.trunc_exp(h[:, 0]) * sel).view(*shape, 1)
+        return density, h[:, 1:].view(*shape, self.geo_feat_dim)
+
+    def get_normals(self) -> torch.Tensor:
+        """-normalize(d raw_density / d x_normalised) (NS/fields/base_field.py:80-101), first order only, no graph."""
+        c = self._cache
+        assert c is not None, "Sample locations must be set before calling get_normals."
+        with torch.no_grad():
+            mlp = self.mlp_base.mlp
+            mlp._repack()
+            flat = ops.flat_alias([p.data for p in mlp._flat_param_list()])
+            n = c["x"].shape[0]
+            feat = c["feat"].detach()
+            y, saved = ops.mlp_forward(feat, flat, mlp.spec, save=True)
+            onehot = torch.zeros((n, mlp.out_dim), dtype=torch.float32, device=feat.device)
+            onehot[:, 0] = 1.0
+            dfeat, _ = ops.mlp_backward(feat, flat, saved, y, onehot, mlp.spec, need_dx=True, need_dparams=False)
+            enc = self.mlp_base.encoder
+            g = ops.grid_backward_input(c["x"], enc.hash_table.detach(), dfeat, enc.spec)
+            normals = ops.normalize3(g, scale=-1.0, eps=1e-12)
+        return normals.view(*c["shape"], 3)
+
+    # -- colour / predicted normals -------------------------------------------------------------------------
+    def get_outputs(self, ray_samples: RaySamples, density_embedding: Optional[torch.Tensor] = None) -> Dict[FieldHeadNames, torch.Tensor]:
+        raise NotImplementedError("use forward(): density, colour and normals are evaluated by one fused pipeline")
+
+    def forward(self, ray_samples: RaySamples, compute_normals: bool = False) -> Dict[FieldHeadNames, torch.Tensor]:
+        if ray_samples.camera_indices is None:
+            raise AttributeError("Camera indices are not provided.")
+        fr = ray_samples.frustums
+        B, S = fr.shape
+        positions = fr.get_positions()
+        x, sel = ops.contract_normalize(positions)
+        feat = self.mlp_base.encoder(x)
+        h = self.mlp_base.mlp(feat)
+        self._cache = {"x": x, "sel": sel, "h": h, "feat": feat, "shape": (B, S), "positions": positions}
+        self._sample_locations = x.view(B, S, 3)
+        self._density_before_activation = h[:, :1].view(B, S, 1)
+        dirs = fr.directions.reshape(B, 3).contiguous()
+        if self.training:
+            cam = ray_samples.camera_indices.reshape(B).long().contiguous()
+            emb = self.embedding_appearance.embedding.weight
+        else:
+            cam = None
+            if self.use_average_appearance_embedding:
+                emb = self.embedding_appearance.mean(dim=0)
+            else:
+                emb = torch.zeros(self.appearance_embedding_dim, device=dirs.device)
+        density, head_in, pn_in = ops.field_assemble(h, emb, sel, dirs, positions.reshape(-1, 3), cam, B, S, self.use_pred_normals)
+        out: Dict[FieldHeadNames, torch.Tensor] = {}
+        if self.use_pred_normals:
+            params = self.mlp_pred_normals._flat_param_list() + [self.field_head_pred_normals.net.weight, self.field_head_pred_normals.net.bias]
+            repack(params)
+            pn = ops.mlp_apply(pn_in, self._pn_spec, params)
+            out[FieldHeadNames.PRED_NORMALS] = ops.normalize3(pn, 1.0, 1e-12).view(B, S, 3)
+        out[FieldHeadNames.RGB] = self.mlp_head(head_in).view(B, S, 3)
+        out[FieldHeadNames.DENSITY] = density.view(B, S, 1)
+        if compute_normals:
+            out[FieldHeadNames.NORMALS] = self.get_normals()
+        return out

@@ -1,0 +1,657 @@
+"""Functional operators + autograd glue over the C-ABI kernels.  torch is used for memory, streams and the
+autograd graph only; every arithmetic step of the hot path runs in libnvo_b200.so.  No CPU fallback."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call, check
+
+# ------------------------------------------------------------------------------------------------
+# hash grid
+# ------------------------------------------------------------------------------------------------
+
+
+def torch_level_scalings(num_levels: int, min_res: int, max_res: int) -> torch.Tensor:
+    """The fp32 per-level scale exactly as the reference evaluates it (float32 pow then floor;
+    NS/field_components/encodings.py:346-349). Never recomputed on the device."""
+    levels = torch.arange(num_levels)
+    growth = np.exp((np.log(max_res) - np.log(min_res)) / (num_levels - 1)) if num_levels > 1 else 1
+    return torch.floor(min_res * growth**levels)
+
+
+def growth_level_scalings(num_levels: int, base_resolution: int, per_level_scale: float) -> torch.Tensor:
+    """Same, from the tcnn JSON keys (base_resolution, per_level_scale)."""
+    levels = torch.arange(num_levels)
+    return torch.floor(base_resolution * np.float64(per_level_scale) ** levels)
+
+
+@dataclass
+class GridSpec:
+    n_levels: int
+    log2_T: int
+    scalings: Tuple[float, ...]
+    features_per_level: int = 2
+
+    def __post_init__(self):
+        if self.features_per_level != 2:
+            raise RuntimeError("nvo_b200 hash grid supports n_features_per_level == 2 only")
+        self._desc = {}
+
+    @property
+    def n_rows(self) -> int:
+        return self.n_levels << self.log2_T
+
+    @property
+    def out_dim(self) -> int:
+        return self.n_levels * 2
+
+    def desc(self, table_dtype, out_dtype):
+        k = (table_dtype, out_dtype)
+        if k not in self._desc:
+            self._desc[k] = _lib.make_grid_desc(self.n_levels, self.log2_T, self.scalings, table_dtype, out_dtype)
+        return self._desc[k]
+
+
+def _check_grid_inputs(x, table, spec: GridSpec):
+    check(x, "grid input", torch.float32, (None, 3))
+    if table.dtype not in (torch.float32, torch.float16):
+        raise RuntimeError(f"hash table must be float32 or float16, got {table.dtype}")
+    check(table, "hash table", table.dtype)
+    if table.numel() != spec.n_rows * 2:
+        raise RuntimeError(f"hash table has {table.numel()} elements, expected {spec.n_rows * 2}")
+    if x.device != table.device:
+        raise RuntimeError("grid input and hash table must be on the same device")
+
+
+def grid_forward(x, table, spec: GridSpec, out_dtype=torch.float32):
+    _check_grid_inputs(x, table, spec)
+    y = torch.empty((x.shape[0], spec.out_dim), dtype=out_dtype, device=x.device)
+    call("nvo_grid_forward", spec.desc(table.dtype, out_dtype), x.shape[0], x, table, y)
+    return y
+
+
+def grid_backward(x, dy, spec: GridSpec, dtable=None, n_rows=None):
+    """Scatter dy into a fp32 gradient table (allocated zero-filled when not given)."""
+    check(x, "grid input", torch.float32, (None, 3))
+    check(dy, "grid dy", dy.dtype, (x.shape[0], spec.out_dim))
+    if dtable is None:
+        dtable = torch.zeros((spec.n_rows, 2), dtype=torch.float32, device=x.device)
+    call("nvo_grid_backward", spec.desc(torch.float32, dy.dtype), x.shape[0], x, dy, dtable)
+    return dtable
+
+
+def grid_backward_input(x, table, dy, spec: GridSpec):
+    _check_grid_inputs(x, table, spec)
+    check(dy, "grid dy", dy.dtype, (x.shape[0], spec.out_dim))
+    dx = torch.empty_like(x)
+    call("nvo_grid_backward_input", spec.desc(table.dtype, dy.dtype), x.shape[0], x, table, dy, dx)
+    return dx
+
+
+def grid_indices(x, spec: GridSpec):
+    check(x, "grid input", torch.float32, (None, 3))
+    idx = torch.empty((x.shape[0], spec.n_levels, 8), dtype=torch.int64, device=x.device)
+    call("nvo_grid_indices", spec.desc(torch.float32, torch.float32), x.shape[0], x, idx)
+    return idx
+
+
+class _GridEncode(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, table, spec, out_dtype):
+        x = x.contiguous()
+        y = grid_forward(x, table, spec, out_dtype)
+        ctx.save_for_backward(x, table)
+        ctx.spec = spec
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, table = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dtable = None
+        if ctx.needs_input_grad[1]:
+            dtable = grid_backward(x, dy, ctx.spec).view(table.shape)
+            if table.dtype != torch.float32:
+                dtable = dtable.to(table.dtype)
+        if ctx.needs_input_grad[0]:
+            dx = grid_backward_input(x, table, dy, ctx.spec)
+        return dx, dtable, None, None
+
+
+def grid_encode(x, table, spec: GridSpec, out_dtype=torch.float32):
+    return _GridEncode.apply(x, table, spec, out_dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# MLP
+# ------------------------------------------------------------------------------------------------
+
+
+@dataclass
+class MlpSpec:
+    in_dim: int
+    dims: Tuple[int, ...]
+    activation: str = "relu"
+    out_activation: str = "none"
+    acts: Optional[Tuple[str, ...]] = None  # per-layer override
+
+    def __post_init__(self):
+        if self.acts is None:
+            self.acts = tuple([self.activation] * (len(self.dims) - 1) + [self.out_activation])
+        self.desc = _lib.make_mlp_desc(self.in_dim, self.dims, self.acts)
+        ins = [self.in_dim] + list(self.dims[:-1])
+        self.shapes: List[Tuple[Tuple[int, int], Tuple[int]]] = [((o, i), (o,)) for i, o in zip(ins, self.dims)]
+        self.n_params = sum(o * i + o for i, o in zip(ins, self.dims))
+        self.saved_per_sample = sum(self.dims[:-1])
+
+    @property
+    def out_dim(self) -> int:
+        return self.dims[-1]
+
+    def offsets(self):
+        off, res = 0, []
+        for (w, b) in self.shapes:
+            res.append((off, off + w[0] * w[1]))
+            off += w[0] * w[1]
+            res.append((off, off + b[0]))
+            off += b[0]
+        return res
+
+
+def flat_alias(params: Sequence[torch.Tensor]) -> Optional[torch.Tensor]:
+    """If `params` are back-to-back views of one storage (our modules allocate them that way), return the flat
+    fp32 tensor aliasing them; otherwise None."""
+    p0 = params[0]
+    expect = p0.data_ptr()
+    for p in params:
+        if p.dtype != torch.float32 or not p.is_contiguous() or p.data_ptr() != expect or p.untyped_storage().data_ptr() != p0.untyped_storage().data_ptr():
+            return None
+        expect += p.numel() * 4
+    n = sum(p.numel() for p in params)
+    return torch.empty(0, dtype=torch.float32, device=p0.device).set_(p0.untyped_storage(), p0.storage_offset(), (n,), (1,))
+
+
+def mlp_forward(x, flat, spec: MlpSpec, save: bool, row_mask=None):
+    check(x, "mlp input", torch.float32, (None, spec.in_dim))
+    check(flat, "mlp params", torch.float32, (spec.n_params,))
+    n = x.shape[0]
+    if row_mask is not None:
+        check(row_mask, "row_mask", torch.float32, (n,))
+    y = torch.empty((n, spec.out_dim), dtype=torch.float32, device=x.device)
+    saved = torch.empty((n, spec.saved_per_sample), dtype=torch.float32, device=x.device) if (save and spec.saved_per_sample) else None
+    call("nvo_mlp_forward", spec.desc, n, x, flat, row_mask, y, saved)
+    return y, saved
+
+
+def mlp_backward(x, flat, saved, y, dy, spec: MlpSpec, need_dx: bool, need_dparams: bool, dflat=None, row_mask=None):
+    n = x.shape[0]
+    check(dy, "mlp dy", torch.float32, (n, spec.out_dim))
+    dx = torch.empty_like(x) if need_dx else None
+    if need_dparams and dflat is None:
+        dflat = torch.zeros(spec.n_params, dtype=torch.float32, device=x.device)
+    call("nvo_mlp_backward", spec.desc, n, x, flat, saved, y, row_mask, dy, dx, dflat if need_dparams else None)
+    return dx, dflat
+
+
+class _MlpApply(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, spec, row_mask, *params):
+        x = x.contiguous()
+        with torch.no_grad():
+            flat = flat_alias(params)
+            if flat is None:
+                flat = torch.cat([p.reshape(-1).float() for p in params])
+        need = x.requires_grad or any(p.requires_grad for p in params)
+        y, saved = mlp_forward(x, flat, spec, save=need, row_mask=row_mask)
+        ctx.save_for_backward(x, flat, saved, y, row_mask)
+        ctx.spec = spec
+        ctx.n_tensors = len(params)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, flat, saved, y, row_mask = ctx.saved_tensors
+        spec = ctx.spec
+        need_dx = ctx.needs_input_grad[0]
+        need_dp = any(ctx.needs_input_grad[3:])
+        dx, dflat = mlp_backward(x, flat, saved, y, dy.contiguous(), spec, need_dx, need_dp, row_mask=row_mask)
+        grads = [None] * ctx.n_tensors
+        if need_dp:
+            grads = []
+            for (a, b), (ws, bs) in zip(_pairs(spec.offsets()), spec.shapes):
+                grads.append(dflat[a[0]:a[1]].view(ws))
+                grads.append(dflat[b[0]:b[1]].view(bs))
+        return (dx, None, None, *grads)
+
+
+def _pairs(seq):
+    it = iter(seq)
+    return list(zip(it, it))
+
+
+def mlp_apply(x, spec: MlpSpec, params: Sequence[torch.Tensor], row_mask=None):
+    """params = [W0, b0, W1, b1, ...] in torch layout; row_mask [n] of 0/1 multiplies the output rows."""
+    return _MlpApply.apply(x, spec, row_mask, *params)
+
+
+# ------------------------------------------------------------------------------------------------
+# field element-wise operators
+# ------------------------------------------------------------------------------------------------
+
+
+def contract_normalize(positions):
+    """SceneContraction(L-inf) + (x+2)/4 + selector masking: positions [...,3] -> (x [n,3], selector [n])."""
+    p = check(positions.reshape(-1, 3).contiguous(), "positions", torch.float32)
+    x = torch.empty_like(p)
+    sel = torch.empty(p.shape[0], dtype=torch.float32, device=p.device)
+    call("nvo_contract_forward", p.shape[0], p, x, sel)
+    return x, sel
+
+
+def sh4(directions):
+    d = check(directions.reshape(-1, 3).contiguous(), "directions", torch.float32)
+    out = torch.empty((d.shape[0], 16), dtype=torch.float32, device=d.device)
+    call("nvo_sh4_forward", d.shape[0], d, out)
+    return out
+
+
+def frequency(x, n_freq: int):
+    x = check(x.contiguous(), "frequency input", torch.float32)
+    n, d = x.shape
+    out = torch.empty((n, d * n_freq * 2), dtype=torch.float32, device=x.device)
+    call("nvo_frequency_forward", n, d, n_freq, x, out)
+    return out
+
+
+class _TruncExp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = check(x.float().contiguous(), "trunc_exp input", torch.float32)
+        y = torch.empty_like(x)
+        call("nvo_trunc_exp_forward", x.numel(), x, y)
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        call("nvo_trunc_exp_backward", x.numel(), x, g.contiguous(), dx)
+        return dx
+
+
+trunc_exp = _TruncExp.apply
+
+
+class _Normalize3(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v, scale, eps):
+        shape = v.shape
+        v2 = check(v.reshape(-1, 3).contiguous(), "normalize input", torch.float32)
+        out = torch.empty_like(v2)
+        call("nvo_normalize3_forward", v2.shape[0], v2, scale, eps, out)
+        ctx.save_for_backward(v2)
+        ctx.scale, ctx.eps, ctx.shape = scale, eps, shape
+        return out.view(shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        (v2,) = ctx.saved_tensors
+        dv = torch.empty_like(v2)
+        call("nvo_normalize3_backward", v2.shape[0], v2, g.reshape(-1, 3).contiguous(), ctx.scale, ctx.eps, dv)
+        return dv.view(ctx.shape), None, None
+
+
+def normalize3(v, scale: float = 1.0, eps: float = 1e-12):
+    return _Normalize3.apply(v, float(scale), float(eps))
+
+
+class _FieldAssemble(torch.autograd.Function):
+    """h [n,16], selector [n], directions [B,3], positions [n,3], cam_idx [B] int64 | None, embedding [K,32] | mean [32]
+    -> density [n], head_in [n,63], pn_in [n,27] | None"""
+
+    @staticmethod
+    def forward(ctx, h, embedding, selector, directions, positions, cam_idx, B, S, want_pn):
+        n = B * S
+        h = check(h.contiguous(), "mlp_base output", torch.float32, (n, 16))
+        embedding = check(embedding.contiguous(), "appearance embedding", torch.float32)
+        dev = h.device
+        density = torch.empty(n, dtype=torch.float32, device=dev)
+        head_in = torch.empty((n, 63), dtype=torch.float32, device=dev)
+        pn_in = torch.empty((n, 27), dtype=torch.float32, device=dev) if want_pn else None
+        call("nvo_field_assemble_forward", B, S, h, selector, directions, positions, cam_idx, embedding, density, head_in, pn_in)
+        ctx.save_for_backward(h, selector, cam_idx)
+        ctx.B, ctx.S, ctx.emb_shape = B, S, embedding.shape
+        return density, head_in, pn_in
+
+    @staticmethod
+    def backward(ctx, ddensity, dhead_in, dpn_in):
+        h, selector, cam_idx = ctx.saved_tensors
+        dev = h.device
+        dh = torch.empty_like(h)
+        if dhead_in is None:
+            dhead_in = torch.zeros((h.shape[0], 63), dtype=torch.float32, device=dev)
+        demb = None
+        if ctx.needs_input_grad[1]:
+            demb = torch.zeros(ctx.emb_shape, dtype=torch.float32, device=dev)
+            if cam_idx is None:
+                # eval-style mean embedding: every sample contributes to the single vector
+                demb = dhead_in[:, 31:].sum(0).reshape(ctx.emb_shape)
+        c = lambda t: None if t is None else t.contiguous()
+        call("nvo_field_assemble_backward", ctx.B, ctx.S, h, selector, cam_idx, c(ddensity), dhead_in.contiguous(), c(dpn_in), dh,
+             demb if cam_idx is not None else None)
+        return dh, demb, None, None, None, None, None, None, None
+
+
+def field_assemble(h, embedding, selector, directions, positions, cam_idx, B: int, S: int, want_pn: bool):
+    return _FieldAssemble.apply(h, embedding, selector, directions, positions, cam_idx, B, S, want_pn)
+
+
+# ------------------------------------------------------------------------------------------------
+# intervals helper: (starts, ends, stride) triple the per-ray kernels take
+# ------------------------------------------------------------------------------------------------
+
+
+class Intervals:
+    """Euclidean sample intervals of B rays x S samples, either as compact edges ebins [B,S+1] or as separate
+    starts/ends [B,S]."""
+
+    def __init__(self, ebins: Optional[torch.Tensor] = None, starts: Optional[torch.Tensor] = None, ends: Optional[torch.Tensor] = None):
+        if ebins is not None:
+            self.ebins = check(ebins, "ebins", torch.float32)
+            self.B, self.S = ebins.shape[0], ebins.shape[1] - 1
+            self._starts = self._ends = None
+        else:
+            self.ebins = None
+            self._starts = check(starts.contiguous(), "starts", torch.float32)
+            self._ends = check(ends.contiguous(), "ends", torch.float32)
+            self.B, self.S = self._starts.shape
+
+    def triple(self):
+        if self.ebins is not None:
+            return self.ebins.data_ptr(), self.ebins.data_ptr() + 4, self.S + 1
+        return self._starts.data_ptr(), self._ends.data_ptr(), self.S
+
+    def keepalive(self):
+        return (self.ebins, self._starts, self._ends)
+
+    @property
+    def starts(self):
+        return self.ebins[:, :-1] if self.ebins is not None else self._starts
+
+    @property
+    def ends(self):
+        return self.ebins[:, 1:] if self.ebins is not None else self._ends
+
+    @property
+    def device(self):
+        return self.ebins.device if self.ebins is not None else self._starts.device
+
+
+def sample_uniform(num_samples: int, nears, fars, jitter=None):
+    """-> (sdist [B,S+1], ebins [B,S+1])"""
+    B = nears.shape[0]
+    dev = nears.device
+    nears = check(nears.reshape(-1).contiguous(), "nears", torch.float32, (B,))
+    fars = check(fars.reshape(-1).contiguous(), "fars", torch.float32, (B,))
+    base = torch.linspace(0.0, 1.0, num_samples + 1).to(dev)  # computed by torch (CPU) exactly as ray_samplers.py:100
+    if jitter is not None:
+        jitter = check(jitter.reshape(-1).contiguous(), "jitter", torch.float32, (B,))
+    sdist = torch.empty((B, num_samples + 1), dtype=torch.float32, device=dev)
+    ebins = torch.empty_like(sdist)
+    call("nvo_sample_uniform", B, num_samples, base, jitter, nears, fars, sdist, ebins)
+    return sdist, ebins
+
+
+def sample_positions(origins, directions, iv: Intervals):
+    check(origins, "origins", torch.float32, (iv.B, 3))
+    check(directions, "directions", torch.float32, (iv.B, 3))
+    pos = torch.empty((iv.B, iv.S, 3), dtype=torch.float32, device=origins.device)
+    s, e, stride = iv.triple()
+    call("nvo_sample_positions", iv.B, iv.S, origins, directions, s, e, stride, pos)
+    return pos
+
+
+class _Weights(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, density, iv: Intervals):
+        density = check(density.contiguous(), "density", torch.float32, (iv.B, iv.S))
+        w = torch.empty_like(density)
+        s, e, stride = iv.triple()
+        call("nvo_weights_forward", iv.B, iv.S, s, e, stride, density, w)
+        ctx.save_for_backward(density)
+        ctx.iv = iv
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        (density,) = ctx.saved_tensors
+        iv = ctx.iv
+        dd = torch.empty_like(density)
+        s, e, stride = iv.triple()
+        call("nvo_weights_backward", iv.B, iv.S, s, e, stride, density, dw.contiguous(), dd)
+        return dd, None
+
+
+def weights_from_density(density, iv: Intervals):
+    """density [B,S] -> weights [B,S] (RaySamples.get_weights)."""
+    return _Weights.apply(density, iv)
+
+
+def pdf_resample(weights, sdist_in, num_samples: int, nears, fars, jitter=None, anneal: float = 1.0, histogram_padding: float = 0.01,
+                 return_inds: bool = False):
+    """-> (sdist_out [B,S_out+1], ebins_out [B,S_out+1][, inds int32 [B,S_out+1]]); no gradient (the reference detaches)."""
+    B, S_in = weights.shape
+    dev = weights.device
+    weights = check(weights.detach().contiguous(), "weights", torch.float32, (B, S_in))
+    sdist_in = check(sdist_in.contiguous(), "sdist", torch.float32, (B, S_in + 1))
+    nears = check(nears.reshape(-1).contiguous(), "nears", torch.float32, (B,))
+    fars = check(fars.reshape(-1).contiguous(), "fars", torch.float32, (B,))
+    n = num_samples + 1
+    u = torch.linspace(0.0, 1.0 - (1.0 / n), steps=n)  # ray_samplers.py:317 / :327 evaluated by torch on the host
+    if jitter is None:
+        u = u + 1.0 / (2 * n)
+    else:
+        jitter = check(jitter.reshape(-1).contiguous(), "jitter", torch.float32, (B,))
+    u = u.to(dev)
+    sdist = torch.empty((B, n), dtype=torch.float32, device=dev)
+    ebins = torch.empty_like(sdist)
+    inds = torch.empty((B, n), dtype=torch.int32, device=dev) if return_inds else None
+    call("nvo_pdf_resample", B, S_in, num_samples, weights, sdist_in, u, jitter, float(anneal), float(histogram_padding), nears, fars, sdist, ebins, inds)
+    return (sdist, ebins, inds) if return_inds else (sdist, ebins)
+
+
+class _Render(torch.autograd.Function):
+    """All renderers in one pass.  Outputs: rgb[B,3], acc[B,1], depth_expected[B,1], depth_median[B,1], median_idx[B,1] (int),
+    normals[B,3], pred_normals[B,3] (None where the input is absent)."""
+
+    @staticmethod
+    def forward(ctx, weights, rgb, normals, pred_normals, iv: Intervals, eval_mode: bool, want_median: bool):
+        B, S = iv.B, iv.S
+        dev = weights.device
+        weights = check(weights.contiguous(), "weights", torch.float32, (B, S))
+        f = lambda t, name: None if t is None else check(t.contiguous(), name, torch.float32, (B, S, 3))
+        rgb, normals, pred_normals = f(rgb, "rgb"), f(normals, "normals"), f(pred_normals, "pred_normals")
+        new = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        o_rgb = new(B, 3) if rgb is not None else None
+        o_acc, o_dexp = new(B, 1), new(B, 1)
+        o_dmed = new(B, 1) if want_median else None
+        o_midx = torch.empty((B, 1), dtype=torch.int32, device=dev) if want_median else None
+        o_n = new(B, 3) if normals is not None else None
+        o_pn = new(B, 3) if pred_normals is not None else None
+        minmax = torch.empty(2, dtype=torch.float32, device=dev)  # initialised on the device by nvo_render_forward
+        s, e, stride = iv.triple()
+        call("nvo_render_forward", B, S, int(eval_mode), s, e, stride, weights, rgb, normals, pred_normals, o_rgb, o_acc, o_dexp, minmax, o_dmed, o_midx,
+             o_n, o_pn)
+        call("nvo_clip_depth", B, minmax, o_dexp)
+        ctx.save_for_backward(weights, rgb, normals, pred_normals, minmax)
+        ctx.iv = iv
+        outs = (o_rgb, o_acc, o_dexp, o_dmed, o_midx, o_n, o_pn)
+        ctx.mark_non_differentiable(*[t for t in (o_dmed, o_midx) if t is not None])
+        return outs
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_acc, d_dexp, d_dmed, d_midx, d_n, d_pn):
+        weights, rgb, normals, pred_normals, minmax = ctx.saved_tensors
+        iv = ctx.iv
+        B, S = iv.B, iv.S
+        c = lambda t: None if t is None else t.contiguous()
+        dw = torch.empty_like(weights)
+        drgb = torch.empty_like(rgb) if (rgb is not None and ctx.needs_input_grad[1]) else None
+        dpn = torch.empty_like(pred_normals) if (pred_normals is not None and ctx.needs_input_grad[3]) else None
+        s, e, stride = iv.triple()
+        call("nvo_render_backward", B, S, s, e, stride, weights, rgb, normals, pred_normals, c(d_rgb), c(d_acc), c(d_dexp), minmax, c(d_n), c(d_pn), 0, dw,
+             drgb, dpn)
+        return dw, drgb, None, dpn, None, None, None
+
+
+def render(weights, iv: Intervals, rgb=None, normals=None, pred_normals=None, eval_mode=False, want_median=True):
+    return _Render.apply(weights, rgb, normals, pred_normals, iv, eval_mode, want_median)
+
+
+# ------------------------------------------------------------------------------------------------
+# losses (scalar outputs are 0-dim tensors on the device; no host sync anywhere)
+# ------------------------------------------------------------------------------------------------
+
+
+def _scalar_like(t):
+    return torch.zeros(1, dtype=torch.float32, device=t.device)
+
+
+class _Distortion(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, weights, sdist):
+        B, S = weights.shape
+        weights = check(weights.contiguous(), "weights", torch.float32, (B, S))
+        sdist = check(sdist.contiguous(), "sdist", torch.float32, (B, S + 1))
+        loss = _scalar_like(weights)
+        call("nvo_distortion_loss_forward", B, S, weights, sdist, loss)
+        ctx.save_for_backward(weights, sdist)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        weights, sdist = ctx.saved_tensors
+        B, S = weights.shape
+        dw = torch.zeros_like(weights)
+        call("nvo_distortion_loss_backward", B, S, weights, sdist, g.reshape(1).float().contiguous(), 1.0, dw)
+        return dw, None
+
+
+class _Interlevel(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, w, c, wp, cp):
+        B, S = w.shape
+        Sp = wp.shape[1]
+        w = check(w.detach().contiguous(), "w", torch.float32, (B, S))
+        c = check(c.detach().contiguous(), "c", torch.float32, (B, S + 1))
+        wp = check(wp.contiguous(), "wp", torch.float32, (B, Sp))
+        cp = check(cp.contiguous(), "cp", torch.float32, (B, Sp + 1))
+        loss = _scalar_like(w)
+        call("nvo_interlevel_loss_forward", B, S, Sp, w, c, wp, cp, loss, None, None)
+        ctx.save_for_backward(w, c, wp, cp)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        w, c, wp, cp = ctx.saved_tensors
+        B, S = w.shape
+        Sp = wp.shape[1]
+        dwp = torch.zeros_like(wp)
+        call("nvo_interlevel_loss_backward", B, S, Sp, w, c, wp, cp, g.reshape(1).float().contiguous(), 1.0, dwp)
+        return None, None, dwp, None
+
+
+class _DepthLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, weights, iv: Intervals, depth_gt, dnorm, sigma: float):
+        B, S = iv.B, iv.S
+        weights = check(weights.contiguous(), "weights", torch.float32, (B, S))
+        depth_gt = check(depth_gt.reshape(-1).contiguous(), "termination_depth", torch.float32, (B,))
+        dnorm = check(dnorm.reshape(-1).contiguous(), "directions_norm", torch.float32, (B,))
+        loss = _scalar_like(weights)
+        s, e, stride = iv.triple()
+        call("nvo_depth_loss_forward", B, S, weights, s, e, stride, depth_gt, dnorm, float(sigma), loss)
+        ctx.save_for_backward(weights, depth_gt, dnorm)
+        ctx.iv, ctx.sigma = iv, float(sigma)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        weights, depth_gt, dnorm = ctx.saved_tensors
+        iv = ctx.iv
+        dw = torch.zeros_like(weights)
+        s, e, stride = iv.triple()
+        call("nvo_depth_loss_backward", iv.B, iv.S, weights, s, e, stride, depth_gt, dnorm, ctx.sigma, g.reshape(1).float().contiguous(), 1.0, dw)
+        return dw, None, None, None, None
+
+
+class _Mse(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target):
+        pred = check(pred.contiguous(), "pred", torch.float32)
+        target = check(target.contiguous(), "target", torch.float32, tuple(pred.shape))
+        loss = _scalar_like(pred)
+        d = torch.empty_like(pred)
+        call("nvo_mse_loss", pred.numel(), pred, target, 1.0, loss, d)
+        ctx.save_for_backward(d)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (d,) = ctx.saved_tensors
+        return d * g, None
+
+
+class _NormalLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, gt):
+        B = pred.shape[0]
+        pred = check(pred.contiguous(), "normal_pred", torch.float32, (B, 3))
+        gt = check(gt.contiguous(), "normal_gt", torch.float32, (B, 3))
+        loss = _scalar_like(pred)
+        d = torch.empty_like(pred)
+        call("nvo_normal_loss", B, pred, gt, 1.0, loss, d)
+        ctx.save_for_backward(d)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (d,) = ctx.saved_tensors
+        return d * g, None
+
+
+def distortion_loss_op(weights, sdist):
+    return _Distortion.apply(weights, sdist)
+
+
+def interlevel_loss_op(w, c, wp, cp):
+    return _Interlevel.apply(w, c, wp, cp)
+
+
+def interlevel_indices(w, c, wp, cp):
+    """Test hook: the clamped searchsorted indices (idx_lo, idx_hi) the interlevel loss uses."""
+    B, S = w.shape
+    Sp = wp.shape[1]
+    lo = torch.empty((B, S), dtype=torch.int32, device=w.device)
+    hi = torch.empty_like(lo)
+    loss = _scalar_like(w)
+    call("nvo_interlevel_loss_forward", B, S, Sp, w.contiguous(), c.contiguous(), wp.contiguous(), cp.contiguous(), loss, lo, hi)
+    return lo, hi
+
+
+def depth_loss_op(weights, iv: Intervals, depth_gt, directions_norm, sigma: float):
+    return _DepthLoss.apply(weights, iv, depth_gt, directions_norm, sigma)
+
+
+def mse_loss_op(pred, target):
+    return _Mse.apply(pred, target)
+
+
+def normal_loss_op(pred, gt):
+    return _NormalLoss.apply(pred, gt)
