@@ -202,6 +202,15 @@ int nvo_depth_loss_backward(void* stream, int64_t B, int32_t S, const float* wei
 int nvo_mse_loss(void* stream, int64_t n, const float* pred, const float* target, float scale, float* loss, float* d_pred);
 int nvo_normal_loss(void* stream, int64_t B, const float* pred /*[B,3]*/, const float* gt /*[B,3]*/, float scale, float* loss, float* d_pred);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused dense Adam over a flat fp32 buffer (torch.optim.Adam semantics; NS/engine/optimizers.py:138-150,
+ * nerf_vo/mapping/nerfstudio.py:84-100). step[1] is a DEVICE int32 counter (number of steps taken so far), read for the
+ * bias correction and incremented by the call, so the launch is CUDA-graph replayable. grad_scale multiplies the
+ * gradient first (1/world_size after a sum-allreduce).
+ * ------------------------------------------------------------------------------------------- */
+int nvo_adam_step(void* stream, int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int32_t* step, float lr,
+                  float beta1, float beta2, float eps, float grad_scale);
+
 #ifdef __cplusplus
 }
 #endif

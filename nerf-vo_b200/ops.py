@@ -107,6 +107,8 @@ class _GridEncode(torch.autograd.Function):
         y = grid_forward(x, table, spec, out_dtype)
         ctx.save_for_backward(x, table)
         ctx.spec = spec
+        # fused gradient accumulation: a trainer may attach a preallocated fp32 gradient buffer to the parameter
+        ctx.main_grad = getattr(table, "_nvo_main_grad", None)
         return y
 
     @staticmethod
@@ -114,7 +116,9 @@ class _GridEncode(torch.autograd.Function):
         x, table = ctx.saved_tensors
         dy = dy.contiguous()
         dx = dtable = None
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and ctx.main_grad is not None:
+            grid_backward(x, dy, ctx.spec, dtable=ctx.main_grad)  # scatter straight into the trainer's flat gradient
+        elif ctx.needs_input_grad[1]:
             dtable = grid_backward(x, dy, ctx.spec).view(table.shape)
             if table.dtype != torch.float32:
                 dtable = dtable.to(table.dtype)
@@ -211,6 +215,7 @@ class _MlpApply(torch.autograd.Function):
         ctx.save_for_backward(x, flat, saved, y, row_mask)
         ctx.spec = spec
         ctx.n_tensors = len(params)
+        ctx.main_grad = getattr(params[0], "_nvo_main_grad", None)  # flat fp32 gradient of all `params`, or None
         return y
 
     @staticmethod
@@ -219,9 +224,9 @@ class _MlpApply(torch.autograd.Function):
         spec = ctx.spec
         need_dx = ctx.needs_input_grad[0]
         need_dp = any(ctx.needs_input_grad[3:])
-        dx, dflat = mlp_backward(x, flat, saved, y, dy.contiguous(), spec, need_dx, need_dp, row_mask=row_mask)
+        dx, dflat = mlp_backward(x, flat, saved, y, dy.contiguous(), spec, need_dx, need_dp, dflat=ctx.main_grad, row_mask=row_mask)
         grads = [None] * ctx.n_tensors
-        if need_dp:
+        if need_dp and ctx.main_grad is None:
             grads = []
             for (a, b), (ws, bs) in zip(_pairs(spec.offsets()), spec.shapes):
                 grads.append(dflat[a[0]:a[1]].view(ws))
@@ -327,6 +332,7 @@ class _FieldAssemble(torch.autograd.Function):
         call("nvo_field_assemble_forward", B, S, h, selector, directions, positions, cam_idx, embedding, density, head_in, pn_in)
         ctx.save_for_backward(h, selector, cam_idx)
         ctx.B, ctx.S, ctx.emb_shape = B, S, embedding.shape
+        ctx.main_grad = getattr(embedding, "_nvo_main_grad", None)
         return density, head_in, pn_in
 
     @staticmethod
@@ -337,7 +343,9 @@ class _FieldAssemble(torch.autograd.Function):
         if dhead_in is None:
             dhead_in = torch.zeros((h.shape[0], 63), dtype=torch.float32, device=dev)
         demb = None
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and ctx.main_grad is not None and cam_idx is not None:
+            demb = ctx.main_grad
+        elif ctx.needs_input_grad[1]:
             demb = torch.zeros(ctx.emb_shape, dtype=torch.float32, device=dev)
             if cam_idx is None:
                 # eval-style mean embedding: every sample contributes to the single vector
@@ -345,6 +353,8 @@ class _FieldAssemble(torch.autograd.Function):
         c = lambda t: None if t is None else t.contiguous()
         call("nvo_field_assemble_backward", ctx.B, ctx.S, h, selector, cam_idx, c(ddensity), dhead_in.contiguous(), c(dpn_in), dh,
              demb if cam_idx is not None else None)
+        if demb is ctx.main_grad:
+            demb = None
         return dh, demb, None, None, None, None, None, None, None
 
 
@@ -393,13 +403,25 @@ class Intervals:
         return self.ebins.device if self.ebins is not None else self._starts.device
 
 
+_const_cache = {}
+
+
+def _cached_linspace(key, make, dev):
+    """Small host-evaluated constant tables (torch.linspace on the CPU, exactly as the reference computes them), uploaded
+    once per (shape, device) so that steady-state steps issue no H2D copies and stay CUDA-graph capturable."""
+    k = (key, str(dev))
+    if k not in _const_cache:
+        _const_cache[k] = make().to(dev)
+    return _const_cache[k]
+
+
 def sample_uniform(num_samples: int, nears, fars, jitter=None):
     """-> (sdist [B,S+1], ebins [B,S+1])"""
     B = nears.shape[0]
     dev = nears.device
     nears = check(nears.reshape(-1).contiguous(), "nears", torch.float32, (B,))
     fars = check(fars.reshape(-1).contiguous(), "fars", torch.float32, (B,))
-    base = torch.linspace(0.0, 1.0, num_samples + 1).to(dev)  # computed by torch (CPU) exactly as ray_samplers.py:100
+    base = _cached_linspace(("uniform", num_samples), lambda: torch.linspace(0.0, 1.0, num_samples + 1), dev)  # ray_samplers.py:100
     if jitter is not None:
         jitter = check(jitter.reshape(-1).contiguous(), "jitter", torch.float32, (B,))
     sdist = torch.empty((B, num_samples + 1), dtype=torch.float32, device=dev)
@@ -453,12 +475,14 @@ def pdf_resample(weights, sdist_in, num_samples: int, nears, fars, jitter=None, 
     nears = check(nears.reshape(-1).contiguous(), "nears", torch.float32, (B,))
     fars = check(fars.reshape(-1).contiguous(), "fars", torch.float32, (B,))
     n = num_samples + 1
-    u = torch.linspace(0.0, 1.0 - (1.0 / n), steps=n)  # ray_samplers.py:317 / :327 evaluated by torch on the host
-    if jitter is None:
-        u = u + 1.0 / (2 * n)
-    else:
+
+    def make_u():  # ray_samplers.py:317 / :327 evaluated by torch on the host
+        u = torch.linspace(0.0, 1.0 - (1.0 / n), steps=n)
+        return u + 1.0 / (2 * n) if jitter is None else u
+
+    u = _cached_linspace(("pdf_u", n, jitter is None), make_u, dev)
+    if jitter is not None:
         jitter = check(jitter.reshape(-1).contiguous(), "jitter", torch.float32, (B,))
-    u = u.to(dev)
     sdist = torch.empty((B, n), dtype=torch.float32, device=dev)
     ebins = torch.empty_like(sdist)
     inds = torch.empty((B, n), dtype=torch.int32, device=dev) if return_inds else None
@@ -655,3 +679,17 @@ def mse_loss_op(pred, target):
 
 def normal_loss_op(pred, gt):
     return _NormalLoss.apply(pred, gt)
+
+
+# ------------------------------------------------------------------------------------------------
+# optimizer
+# ------------------------------------------------------------------------------------------------
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, grad_scale: float = 1.0):
+    """Fused dense Adam over flat fp32 buffers; `step` is a device int32 [1] tensor, incremented by the call."""
+    n = params.numel()
+    for t, name in ((params, "params"), (grads, "grads"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        check(t, name, torch.float32, (n,))
+    check(step, "step", torch.int32, (1,))
+    call("nvo_adam_step", n, params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, grad_scale)

@@ -1,0 +1,192 @@
+"""Mapping-step engine: one call = zero grads, forward, losses, backward, (gradient all-reduce,) fused Adam — what
+`Nerfstudio.train()` drives through Trainer.train_iteration (nerf_vo/mapping/nerfstudio.py:142-173,
+NS/engine/trainer.py:455-494, NS/pipelines/base_pipeline.py:291-304), restated for the nvo_b200 kernels:
+
+  * every parameter lives in ONE flat fp32 buffer, gradients in another; backward kernels scatter straight into the flat
+    gradient (no per-tensor .grad, no AccumulateGrad pass), a single fused Adam launch updates everything;
+  * the whole step is captured in CUDA graphs (at 4096 rays the step is launch-bound) and replayed;
+  * data parallel: rays are sharded across ranks, parameters replicated, ONE NCCL sum-all-reduce of the flat gradient per
+    step, mean taken inside the Adam kernel (DDP semantics, NS/pipelines/base_pipeline.py:281-283).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .field_components import repack
+from .model import ExtendedNerfactoModel
+from .rays import RayBundle
+
+
+class MappingTrainer:
+    def __init__(self, model: ExtendedNerfactoModel, num_rays: int, lr: float = 1e-2, eps: float = 1e-15, betas=(0.9, 0.999),
+                 use_cuda_graph: bool = True, with_normals: bool = True, device: Optional[torch.device] = None):
+        self.model = model
+        self.device = device or next(model.parameters()).device
+        self.B = int(num_rays)
+        self.lr, self.eps, self.betas = lr, eps, betas
+        self.world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.use_cuda_graph = use_cuda_graph
+        self.with_normals = with_normals
+        model.train()
+        # ---- flat parameter / gradient / optimizer-state buffers ---------------------------------------------
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        uniq, seen = [], set()
+        for p in self.params:
+            if id(p) not in seen:
+                seen.add(id(p))
+                uniq.append(p)
+        self.params = uniq
+        # 16-byte alignment of every tensor start keeps float4 / float2 accesses legal: pad each to a multiple of 4 floats
+        sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]
+        total = sum(sizes)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.grad = torch.zeros_like(self.flat)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.step_count = torch.zeros(1, dtype=torch.int32, device=self.device)
+        off = 0
+        self._views = []
+        for p, n in zip(self.params, sizes):
+            self.flat[off:off + p.numel()].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + p.numel()].view(p.shape)
+            self._views.append((off, p.numel()))
+            off += n
+        self._attach_main_grads()
+        # ---- static inputs ---------------------------------------------------------------------------------------
+        B, dev = self.B, self.device
+        f = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
+        self.inputs = {"origins": f(B, 3), "directions": f(B, 3), "directions_norm": f(B, 1), "pixel_area": f(B, 1),
+                       "camera_indices": torch.zeros((B, 1), dtype=torch.int64, device=dev), "rgb": f(B, 3), "depth": f(B, 1), "normal": f(B, 3),
+                       "jitter0": f(B, 1), "jitter1": f(B, 1), "jitter2": f(B, 1)}
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self.loss_terms: Dict[str, torch.Tensor] = {}
+        self._graph_fb: Optional[torch.cuda.CUDAGraph] = None
+        self._graph_opt: Optional[torch.cuda.CUDAGraph] = None
+        self.launches_per_step = 0
+
+    # MLP groups whose parameters must be contiguous in the flat buffer get ONE main-grad view on their first tensor
+    def _attach_main_grads(self) -> None:
+        m = self.model
+        index = {id(p): v for p, v in zip(self.params, self._views)}
+
+        def span(ps):
+            a = index[id(ps[0])][0]
+            last = index[id(ps[-1])]
+            return self.grad[a:last[0] + last[1]]
+
+        def attach_mlp(ps):
+            # contiguity inside the flat buffer holds only when no padding was inserted between the group's tensors
+            flat = ops.flat_alias([p.data for p in ps])
+            if flat is None:
+                repack(ps)  # odd-sized tensors: give the group its own packed storage (falls out of the single flat buffer)
+                raise RuntimeError("internal: MLP group not contiguous in the flat buffer")
+            ps[0]._nvo_main_grad = span(ps)
+
+        f = m.field
+        for table in [f.mlp_base.encoder.hash_table] + [pn.encoding.hash_table for pn in m.proposal_networks]:
+            a, n = index[id(table)]
+            table._nvo_main_grad = self.grad[a:a + n].view(table.shape)
+        emb = f.embedding_appearance.embedding.weight
+        a, n = index[id(emb)]
+        emb._nvo_main_grad = self.grad[a:a + n].view(emb.shape)
+        groups = [f.mlp_base.mlp._flat_param_list(), f.mlp_head._flat_param_list()]
+        if f.use_pred_normals:
+            groups.append(f.mlp_pred_normals._flat_param_list() + [f.field_head_pred_normals.net.weight, f.field_head_pred_normals.net.bias])
+        for pn in m.proposal_networks:
+            groups.append((pn.mlp_base[1] if not pn.use_linear else pn.linear)._flat_param_list())
+        for ps in groups:
+            attach_mlp(ps)
+
+    # ---- one step --------------------------------------------------------------------------------------------------
+    def _bundle(self) -> RayBundle:
+        i = self.inputs
+        return RayBundle(origins=i["origins"], directions=i["directions"], pixel_area=i["pixel_area"], camera_indices=i["camera_indices"],
+                         metadata={"directions_norm": i["directions_norm"]})
+
+    def _forward_backward(self) -> None:
+        i = self.inputs
+        self.grad.zero_()
+        batch = {"image": i["rgb"], "depth_image": i["depth"]}
+        if self.with_normals:
+            batch["normal_image"] = i["normal"]
+        _, loss_dict, _ = self.model.get_train_loss_dict(self._bundle(), batch, [i["jitter0"], i["jitter1"], i["jitter2"]])
+        total = sum(loss_dict.values())
+        total.backward()
+        self.loss.copy_(total.detach())
+        self.loss_terms = {k: v.detach() for k, v in loss_dict.items()}
+
+    def _optimizer(self) -> None:
+        ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.betas[0], self.betas[1], self.eps,
+                      1.0 / self.world_size)
+
+    def set_inputs(self, rays: Dict[str, torch.Tensor], targets: Dict[str, torch.Tensor], jitters: Optional[List[torch.Tensor]] = None,
+                   non_blocking: bool = True) -> int:
+        """Copy one batch (host or device tensors) into the static input buffers; returns the bytes copied."""
+        n = 0
+        src = dict(rays)
+        src.update({"rgb": targets["rgb"], "depth": targets["depth"], "normal": targets["normal"]})
+        if jitters is None:
+            for k in range(3):
+                self.inputs[f"jitter{k}"].uniform_()
+        else:
+            for k in range(3):
+                src[f"jitter{k}"] = jitters[k]
+        for k, v in src.items():
+            if k in self.inputs:
+                self.inputs[k].copy_(v, non_blocking=non_blocking)
+                n += v.numel() * v.element_size()
+        return n
+
+    def capture(self, warmup: int = 3) -> None:
+        """Warm up on a side stream, then capture forward+backward (and the optimizer) into CUDA graphs."""
+        from . import _lib
+
+        self.model.proposal_sampler._step = 10 ** 6  # steady state: `updated` decided by steps_since_update
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self.model.proposal_sampler._steps_since_update = 10 ** 6  # always update the proposal networks (worst case)
+                self._forward_backward()
+                if self.world_size > 1:
+                    dist.all_reduce(self.grad)
+                self._optimizer()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        if not self.use_cuda_graph:
+            return
+        self.model.proposal_sampler._steps_since_update = 10 ** 6
+        n0 = _lib.launch_count()
+        self._graph_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph_fb):
+            self._forward_backward()
+            if self.world_size == 1:
+                self._optimizer()
+        if self.world_size > 1:
+            self._graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph_opt):
+                self._optimizer()
+        self.launches_per_step = _lib.launch_count() - n0
+
+    def train_step(self) -> torch.Tensor:
+        """Runs one step on the current contents of the static input buffers; returns the (device) loss scalar."""
+        if self._graph_fb is not None:
+            self._graph_fb.replay()
+            if self.world_size > 1:
+                dist.all_reduce(self.grad)
+                self._graph_opt.replay()
+        else:
+            from . import _lib
+
+            n0 = _lib.launch_count()
+            self.model.proposal_sampler._steps_since_update = 10 ** 6
+            self._forward_backward()
+            if self.world_size > 1:
+                dist.all_reduce(self.grad)
+            self._optimizer()
+            self.launches_per_step = _lib.launch_count() - n0
+        return self.loss
