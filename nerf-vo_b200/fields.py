@@ -134,15 +134,21 @@ class NerfactoField(Field):
                             layer_width=hidden_dim_color, out_dim=3, activation=nn.ReLU(), out_activation=nn.Sigmoid())
         self._cache = None
 
+    def _remember(self, x, feat, h, shape) -> None:
+        """State get_normals() needs (base_field.py:80-101 keeps _sample_locations / _density_before_activation).  Stored
+        DETACHED: normals are first-order and graph-free, and holding autograd nodes across steps would pin the previous
+        step's graph (and its stream) — which breaks CUDA-graph capture of the next step."""
+        self._cache = {"x": x.detach(), "feat": feat.detach(), "shape": tuple(shape)}
+        self._sample_locations = self._cache["x"].view(*shape, 3)
+        self._density_before_activation = h.detach()[:, :1].view(*shape, 1)
+
     # -- density -----------------------------------------------------------------------------------------
     def _density_from_positions(self, positions: torch.Tensor):
         shape = positions.shape[:-1]
         x, sel = ops.contract_normalize(positions)
         feat = self.mlp_base.encoder(x)
         h = self.mlp_base.mlp(feat)  # [n,16]: raw density + geo features (nerfacto_field.py:213-215)
-        self._cache = {"x": x, "sel": sel, "h": h, "feat": feat, "shape": shape, "positions": positions}
-        self._sample_locations = x.view(*shape, 3)
-        self._density_before_activation = h[:, :1].view(*shape, 1)
+        self._remember(x, feat, h, shape)
         density = (ops.trunc_exp(h[:, 0]) * sel).view(*shape, 1)
         return density, h[:, 1:].view(*shape, self.geo_feat_dim)
 
@@ -178,9 +184,7 @@ class NerfactoField(Field):
         x, sel = ops.contract_normalize(positions)
         feat = self.mlp_base.encoder(x)
         h = self.mlp_base.mlp(feat)
-        self._cache = {"x": x, "sel": sel, "h": h, "feat": feat, "shape": (B, S), "positions": positions}
-        self._sample_locations = x.view(B, S, 3)
-        self._density_before_activation = h[:, :1].view(B, S, 1)
+        self._remember(x, feat, h, (B, S))
         dirs = fr.directions.reshape(B, 3).contiguous()
         if self.training:
             cam = ray_samples.camera_indices.reshape(B).long().contiguous()

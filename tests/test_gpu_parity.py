@@ -166,8 +166,15 @@ def test_ray_ops_golden(nv, golden):
         # PDF resampling fed with the REFERENCE's weights: indices bit-exact, bins to 1e-6
         s1, inds = ps(rb, s0, T(g[f"{mode}.w0"])[..., None], num_samples=96, jitter=T(g["train.jitter1"]) if train else None, return_inds=True)
         ref_inds = torch.from_numpy(g[f"{mode}.pdf_inds"])
-        mism = (inds.cpu().long() != ref_inds).float().mean().item()
-        assert mism == 0.0, f"{mode}: {mism} of searchsorted indices differ"
+        bad = inds.cpu().long() != ref_inds
+        # Bit-exact except at exact floating-point TIES between u and a cdf entry (e.g. u = 48.5/97 = 0.5 = cdf[128] on a
+        # zero-density ray in eval mode): there the reference's own answer depends on the rounding of its vectorised fp32
+        # torch.sum (ISA-dependent); we accumulate the normaliser in fp64.  Every mismatch must be such a tie, and rare.
+        if bad.any():
+            cdf_ref, u_ref = torch.from_numpy(g[f"{mode}.pdf_cdf"]), torch.from_numpy(g[f"{mode}.pdf_u"])
+            rows, cols = bad.nonzero(as_tuple=True)
+            gap = (cdf_ref[rows] - u_ref[rows, cols][:, None]).abs().min(dim=1)[0]
+            assert float(gap.max()) <= 2.4e-7 and bad.float().mean().item() < 2e-3, (float(gap.max()), bad.float().mean().item())
         assert float((s1.sdist().cpu() - torch.from_numpy(g[f"{mode}.s1_sdist"])).abs().max()) < 1e-6
         # the spacing->euclidean map 1/(2-2s) amplifies 1-ulp spacing differences near the far plane: 1e-4 relative
         assert float(((s1.frustums.starts[..., 0].cpu() - torch.from_numpy(g[f"{mode}.s1_starts"])).abs() /
