@@ -96,6 +96,21 @@ int nvo_mlp_forward(const nvo_mlp_desc* d, void* stream, int64_t n, const float*
 int nvo_mlp_backward(const nvo_mlp_desc* d, void* stream, int64_t n, const float* x, const float* params, const float* saved,
                      const float* y, const float* row_mask, const float* dy, float* dx, float* dparams);
 
+/* Tensor-core path (tcgen05.mma, accumulators in TMEM) for networks whose widths are <= 64 and depth <= 4 — the three
+ * field MLPs.  Same semantics and parameter layout as nvo_mlp_forward/backward with fp16 operands and fp32 accumulation:
+ *   x16   [n, in_pad] fp16, in_pad = nvo_mlp_tc_in_pad(d) (in_dim rounded up to 16, zero padded);
+ *   saved opaque forward context of nvo_mlp_tc_saved_bytes(d, n) bytes (fp16 hidden activations, tile-major);
+ *   scratch one float the backward uses for its device-side gradient scale (max|dy| -> power-of-two loss scale, the
+ *   device analogue of tinycudann's loss_scale, modules.py:174);
+ *   y, dy, dx, dparams fp32 exactly as the SIMT entry points. */
+int nvo_mlp_tc_in_pad(const nvo_mlp_desc* d);
+int64_t nvo_mlp_tc_saved_bytes(const nvo_mlp_desc* d, int64_t n);
+int nvo_cast_pad_f16(void* stream, int64_t n, int32_t in_dim, int32_t kpad, const float* x, void* out);
+int nvo_mlp_tc_forward(const nvo_mlp_desc* d, void* stream, int64_t n, const void* x16, const float* params, const float* row_mask, float* y,
+                       void* saved);
+int nvo_mlp_tc_backward(const nvo_mlp_desc* d, void* stream, int64_t n, const void* x16, const float* params, const void* saved, const float* y,
+                        const float* row_mask, const float* dy, float* scratch, float* dx, float* dparams);
+
 /* ---------------------------------------------------------------------------------------------
  * Field element-wise operators.
  * ------------------------------------------------------------------------------------------- */
@@ -119,9 +134,10 @@ int nvo_normalize3_backward(void* stream, int64_t n, const float* v, const float
  *   head_in[n,63]= [SH16((dir+1)/2) | h[:,1:16] | appearance32]      (:286-293, base_field.py:142)
  *   pn_in[n,27]  = [posenc12(pos) | h[:,1:16]]                       (:278-281)
  * appearance = embedding[cam_idx[ray]] (training) or the caller-provided mean vector when cam_idx is NULL (eval;
- * embedding then points at ONE 32-vector).  h[n,16] is mlp_base's output.  pn_in may be NULL. */
+ * embedding then points at ONE 32-vector).  h[n,16] is mlp_base's output.  pn_in may be NULL.
+ * f16_padded != 0: head_in / pn_in are fp16 rows zero-padded to 64 / 32 columns (operand format of nvo_mlp_tc_forward). */
 int nvo_field_assemble_forward(void* stream, int64_t B, int32_t S, const float* h, const float* selector, const float* directions, const float* pos,
-                               const int64_t* cam_idx, const float* embedding, float* density, float* head_in, float* pn_in);
+                               const int64_t* cam_idx, const float* embedding, int32_t f16_padded, float* density, void* head_in, void* pn_in);
 /* backward: dh[n,16] (overwritten) and dembedding[K,32] (accumulate, nullable) from ddensity[n] (nullable), dhead_in[n,63], dpn_in[n,27] (nullable) */
 int nvo_field_assemble_backward(void* stream, int64_t B, int32_t S, const float* h, const float* selector, const int64_t* cam_idx,
                                 const float* ddensity, const float* dhead_in, const float* dpn_in, float* dh, float* dembedding);

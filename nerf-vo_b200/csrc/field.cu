@@ -118,10 +118,16 @@ __global__ void __launch_bounds__(256) k_normalize3_bwd(int64_t n, const float* 
 #define HEAD_IN 63
 #define PN_IN 27
 
+__device__ __forceinline__ void put(float* o, int k, float v) { o[k] = v; }
+__device__ __forceinline__ void put(__half* o, int k, float v) { o[k] = __float2half_rn(v); }
+
+// OutT = float: head_in [n,63], pn_in [n,27] (the reference's widths);  OutT = __half: zero-padded [n,64] / [n,32] rows that the
+// tensor-core MLP stages into shared memory with 16-byte copies.
+template <typename OutT, int HEAD_STRIDE, int PN_STRIDE>
 __global__ void __launch_bounds__(256)
     k_assemble_fwd(int64_t B, int S, const float* __restrict__ h, const float* __restrict__ selector, const float* __restrict__ dirs,
                    const float* __restrict__ pos, const int64_t* __restrict__ cam_idx, const float* __restrict__ embedding, float* __restrict__ density,
-                   float* __restrict__ head_in, float* __restrict__ pn_in) {
+                   OutT* __restrict__ head_in, OutT* __restrict__ pn_in) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B * S) return;
     const int64_t r = t / S;
@@ -132,31 +138,35 @@ __global__ void __launch_bounds__(256)
         hv[k] = q.x, hv[k + 1] = q.y, hv[k + 2] = q.z, hv[k + 3] = q.w;
     }
     if (density) density[t] = __fmul_rn(expf(hv[0]), __ldg(selector + t));
-    float* o = head_in + HEAD_IN * t;
+    OutT* o = head_in + (int64_t)HEAD_STRIDE * t;
     float c[16];
     // get_normalized_directions (base_field.py:142): (d + 1) / 2
     sh16(__fdiv_rn(__fadd_rn(__ldg(dirs + 3 * r), 1.f), 2.f), __fdiv_rn(__fadd_rn(__ldg(dirs + 3 * r + 1), 1.f), 2.f),
          __fdiv_rn(__fadd_rn(__ldg(dirs + 3 * r + 2), 1.f), 2.f), c);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) o[k] = c[k];
+    for (int k = 0; k < 16; ++k) put(o, k, c[k]);
 #pragma unroll
-    for (int k = 0; k < GEO; ++k) o[16 + k] = hv[1 + k];
+    for (int k = 0; k < GEO; ++k) put(o, 16 + k, hv[1 + k]);
     const float* e = cam_idx ? embedding + APP * __ldg(cam_idx + r) : embedding;
 #pragma unroll 8
-    for (int k = 0; k < APP; ++k) o[16 + GEO + k] = __ldg(e + k);
+    for (int k = 0; k < APP; ++k) put(o, 16 + GEO + k, __ldg(e + k));
+#pragma unroll
+    for (int k = HEAD_IN; k < HEAD_STRIDE; ++k) put(o, k, 0.f);
     if (pn_in) {
-        float* q = pn_in + PN_IN * t;
+        OutT* q = pn_in + (int64_t)PN_STRIDE * t;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const float xi = __ldg(pos + 3 * t + i);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                q[i * 2 + k] = posenc_value(xi, k, false);
-                q[6 + i * 2 + k] = posenc_value(xi, k, true);
+                put(q, i * 2 + k, posenc_value(xi, k, false));
+                put(q, 6 + i * 2 + k, posenc_value(xi, k, true));
             }
         }
 #pragma unroll
-        for (int k = 0; k < GEO; ++k) q[12 + k] = hv[1 + k];
+        for (int k = 0; k < GEO; ++k) put(q, 12 + k, hv[1 + k]);
+#pragma unroll
+        for (int k = PN_IN; k < PN_STRIDE; ++k) put(q, k, 0.f);
     }
 }
 
@@ -256,14 +266,19 @@ extern "C" int nvo_normalize3_backward(void* stream, int64_t n, const float* v, 
     return 0;
 }
 extern "C" int nvo_field_assemble_forward(void* stream, int64_t B, int32_t S, const float* h, const float* selector, const float* directions,
-                                          const float* pos, const int64_t* cam_idx, const float* embedding, float* density, float* head_in,
-                                          float* pn_in) {
+                                          const float* pos, const int64_t* cam_idx, const float* embedding, int32_t f16_padded, float* density,
+                                          void* head_in, void* pn_in) {
     NVO_CHECK(B >= 0 && S >= 1, "field_assemble_forward: bad shape");
     if (B == 0) return 0;
     NVO_CHECK(h && directions && embedding && head_in, "field_assemble_forward: null pointer");
     NVO_CHECK(!density || selector, "field_assemble_forward: selector required for density");
     NVO_CHECK(!pn_in || pos, "field_assemble_forward: positions required for pn_in");
-    k_assemble_fwd<<<nvo_blocks(B * S, 256), 256, 0, (cudaStream_t)stream>>>(B, S, h, selector, directions, pos, cam_idx, embedding, density, head_in, pn_in);
+    if (f16_padded)
+        k_assemble_fwd<__half, 64, 32><<<nvo_blocks(B * S, 256), 256, 0, (cudaStream_t)stream>>>(B, S, h, selector, directions, pos, cam_idx, embedding, density,
+                                                                                                (__half*)head_in, (__half*)pn_in);
+    else
+        k_assemble_fwd<float, HEAD_IN, PN_IN><<<nvo_blocks(B * S, 256), 256, 0, (cudaStream_t)stream>>>(B, S, h, selector, directions, pos, cam_idx, embedding,
+                                                                                                         density, (float*)head_in, (float*)pn_in);
     NVO_CUDA_LAUNCH_CHECK("field_assemble_forward");
     return 0;
 }

@@ -98,8 +98,13 @@ class NerfactoField(Field):
                  features_per_level: int = 2, hidden_dim_color: int = 64, hidden_dim_transient: int = 64, appearance_embedding_dim: int = 32,
                  transient_embedding_dim: int = 16, use_transient_embedding: bool = False, use_semantics: bool = False, num_semantic_classes: int = 100,
                  pass_semantic_gradients: bool = False, use_pred_normals: bool = False, use_average_appearance_embedding: bool = False,
-                 spatial_distortion: Optional[nn.Module] = None, implementation: str = "nvo_b200") -> None:
+                 spatial_distortion: Optional[nn.Module] = None, implementation: str = "nvo_b200", precision: str = "fp16") -> None:
+        """precision: "fp16" = hash features and the three MLPs on the tcgen05 tensor-core path (fp16 operands, fp32 accumulate,
+        fp32 master parameters — tinycudann's operating point); "fp32" = exact-arithmetic SIMT kernels (bit-level parity runs)."""
         super().__init__()
+        if precision not in ("fp16", "fp32"):
+            raise ValueError(f"precision must be 'fp16' or 'fp32', got {precision}")
+        self.precision = precision
         if use_transient_embedding or use_semantics:
             raise NotImplementedError("transient / semantic heads are outside the NeRF-VO mapping path")
         if spatial_distortion is None or not isinstance(spatial_distortion, SceneContraction):
@@ -134,21 +139,28 @@ class NerfactoField(Field):
                             layer_width=hidden_dim_color, out_dim=3, activation=nn.ReLU(), out_activation=nn.Sigmoid())
         self._cache = None
 
-    def _remember(self, x, feat, h, shape) -> None:
+    def _remember(self, x, h, shape) -> None:
         """State get_normals() needs (base_field.py:80-101 keeps _sample_locations / _density_before_activation).  Stored
         DETACHED: normals are first-order and graph-free, and holding autograd nodes across steps would pin the previous
         step's graph (and its stream) — which breaks CUDA-graph capture of the next step."""
-        self._cache = {"x": x.detach(), "feat": feat.detach(), "shape": tuple(shape)}
+        self._cache = {"x": x.detach(), "shape": tuple(shape)}
         self._sample_locations = self._cache["x"].view(*shape, 3)
         self._density_before_activation = h.detach()[:, :1].view(*shape, 1)
 
     # -- density -----------------------------------------------------------------------------------------
+    def _base(self, x: torch.Tensor) -> torch.Tensor:
+        """mlp_base(hash_grid(x)) -> h [n,16]: raw density + geo features (nerfacto_field.py:213-215)."""
+        enc, mlp = self.mlp_base.encoder, self.mlp_base.mlp
+        if self.precision == "fp16":
+            mlp._repack()
+            return ops.grid_mlp_tc(x, enc.hash_table, enc.spec, mlp.spec, mlp._flat_param_list())
+        return mlp(enc(x))
+
     def _density_from_positions(self, positions: torch.Tensor):
         shape = positions.shape[:-1]
         x, sel = ops.contract_normalize(positions)
-        feat = self.mlp_base.encoder(x)
-        h = self.mlp_base.mlp(feat)  # [n,16]: raw density + geo features (nerfacto_field.py:213-215)
-        self._remember(x, feat, h, shape)
+        h = self._base(x)
+        self._remember(x, h, shape)
         density = (ops.trunc_exp(h[:, 0]) * sel).view(*shape, 1)
         return density, h[:, 1:].view(*shape, self.geo_feat_dim)
 
@@ -157,17 +169,23 @@ class NerfactoField(Field):
         c = self._cache
         assert c is not None, "Sample locations must be set before calling get_normals."
         with torch.no_grad():
-            mlp = self.mlp_base.mlp
+            enc, mlp = self.mlp_base.encoder, self.mlp_base.mlp
             mlp._repack()
             flat = ops.flat_alias([p.data for p in mlp._flat_param_list()])
-            n = c["x"].shape[0]
-            feat = c["feat"].detach()
-            y, saved = ops.mlp_forward(feat, flat, mlp.spec, save=True)
-            onehot = torch.zeros((n, mlp.out_dim), dtype=torch.float32, device=feat.device)
+            x = c["x"]
+            n = x.shape[0]
+            table = enc.hash_table.detach()
+            onehot = torch.zeros((n, mlp.out_dim), dtype=torch.float32, device=x.device)
             onehot[:, 0] = 1.0
-            dfeat, _ = ops.mlp_backward(feat, flat, saved, y, onehot, mlp.spec, need_dx=True, need_dparams=False)
-            enc = self.mlp_base.encoder
-            g = ops.grid_backward_input(c["x"], enc.hash_table.detach(), dfeat, enc.spec)
+            if self.precision == "fp16":
+                feat = ops.grid_forward(x, table, enc.spec, torch.float16)
+                y, saved = ops.mlp_tc_forward(feat, flat, mlp.spec, True)
+                dfeat, _ = ops.mlp_tc_backward(feat, flat, saved, y, onehot, mlp.spec, True, False)
+            else:
+                feat = ops.grid_forward(x, table, enc.spec)
+                y, saved = ops.mlp_forward(feat, flat, mlp.spec, save=True)
+                dfeat, _ = ops.mlp_backward(feat, flat, saved, y, onehot, mlp.spec, need_dx=True, need_dparams=False)
+            g = ops.grid_backward_input(x, table, dfeat, enc.spec)
             normals = ops.normalize3(g, scale=-1.0, eps=1e-12)
         return normals.view(*c["shape"], 3)
 
@@ -182,9 +200,8 @@ class NerfactoField(Field):
         B, S = fr.shape
         positions = fr.get_positions()
         x, sel = ops.contract_normalize(positions)
-        feat = self.mlp_base.encoder(x)
-        h = self.mlp_base.mlp(feat)
-        self._remember(x, feat, h, (B, S))
+        h = self._base(x)
+        self._remember(x, h, (B, S))
         dirs = fr.directions.reshape(B, 3).contiguous()
         if self.training:
             cam = ray_samples.camera_indices.reshape(B).long().contiguous()
@@ -195,8 +212,24 @@ class NerfactoField(Field):
                 emb = self.embedding_appearance.mean(dim=0)
             else:
                 emb = torch.zeros(self.appearance_embedding_dim, device=dirs.device)
-        density, head_in, pn_in = ops.field_assemble(h, emb, sel, dirs, positions.reshape(-1, 3), cam, B, S, self.use_pred_normals)
         out: Dict[FieldHeadNames, torch.Tensor] = {}
+        if self.precision == "fp16":
+            self.mlp_head._repack()
+            pn_spec, pn_params = None, ()
+            if self.use_pred_normals:
+                pn_params = self.mlp_pred_normals._flat_param_list() + [self.field_head_pred_normals.net.weight, self.field_head_pred_normals.net.bias]
+                repack(pn_params)
+                pn_spec = self._pn_spec
+            density, rgb, pn = ops.field_heads_tc(h, emb, sel, dirs, positions.reshape(-1, 3), cam, B, S, self.mlp_head.spec,
+                                                  self.mlp_head._flat_param_list(), pn_spec, pn_params)
+            if pn is not None:
+                out[FieldHeadNames.PRED_NORMALS] = pn.view(B, S, 3)
+            out[FieldHeadNames.RGB] = rgb.view(B, S, 3)
+            out[FieldHeadNames.DENSITY] = density.view(B, S, 1)
+            if compute_normals:
+                out[FieldHeadNames.NORMALS] = self.get_normals()
+            return out
+        density, head_in, pn_in = ops.field_assemble(h, emb, sel, dirs, positions.reshape(-1, 3), cam, B, S, self.use_pred_normals)
         if self.use_pred_normals:
             params = self.mlp_pred_normals._flat_param_list() + [self.field_head_pred_normals.net.weight, self.field_head_pred_normals.net.bias]
             repack(params)

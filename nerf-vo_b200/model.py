@@ -61,6 +61,8 @@ class NerfactoModelConfig:
     depth_sigma: float = 0.001
     # ExtendedNerfactoModelConfig (nerf_vo/mapping/nerfstudio_utils.py:326-330)
     normal_loss_mult: float = 0.000005
+    # "fp16": field MLPs + hash features on the tcgen05 tensor-core path; "fp32": exact SIMT kernels (parity runs)
+    precision: str = "fp16"
 
 
 class NerfactoModel(nn.Module):
@@ -77,7 +79,7 @@ class NerfactoModel(nn.Module):
                                    features_per_level=c.features_per_level, log2_hashmap_size=c.log2_hashmap_size, hidden_dim_color=c.hidden_dim_color,
                                    hidden_dim_transient=c.hidden_dim_transient, spatial_distortion=contraction, num_images=num_train_data,
                                    use_pred_normals=c.predict_normals, use_average_appearance_embedding=c.use_average_appearance_embedding,
-                                   appearance_embedding_dim=c.appearance_embed_dim)
+                                   appearance_embedding_dim=c.appearance_embed_dim, precision=c.precision)
         self.proposal_networks = nn.ModuleList()
         for i in range(c.num_proposal_iterations):
             args = c.proposal_net_args_list[min(i, len(c.proposal_net_args_list) - 1)]

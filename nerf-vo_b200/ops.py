@@ -322,6 +322,7 @@ class _FieldAssemble(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, h, embedding, selector, directions, positions, cam_idx, B, S, want_pn):
+        ctx.set_materialize_grads(False)
         n = B * S
         h = check(h.contiguous(), "mlp_base output", torch.float32, (n, 16))
         embedding = check(embedding.contiguous(), "appearance embedding", torch.float32)
@@ -329,7 +330,7 @@ class _FieldAssemble(torch.autograd.Function):
         density = torch.empty(n, dtype=torch.float32, device=dev)
         head_in = torch.empty((n, 63), dtype=torch.float32, device=dev)
         pn_in = torch.empty((n, 27), dtype=torch.float32, device=dev) if want_pn else None
-        call("nvo_field_assemble_forward", B, S, h, selector, directions, positions, cam_idx, embedding, density, head_in, pn_in)
+        call("nvo_field_assemble_forward", B, S, h, selector, directions, positions, cam_idx, embedding, 0, density, head_in, pn_in)
         ctx.save_for_backward(h, selector, cam_idx)
         ctx.B, ctx.S, ctx.emb_shape = B, S, embedding.shape
         ctx.main_grad = getattr(embedding, "_nvo_main_grad", None)
@@ -496,6 +497,7 @@ class _Render(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, weights, rgb, normals, pred_normals, iv: Intervals, eval_mode: bool, want_median: bool):
+        ctx.set_materialize_grads(False)
         B, S = iv.B, iv.S
         dev = weights.device
         weights = check(weights.contiguous(), "weights", torch.float32, (B, S))
@@ -526,8 +528,10 @@ class _Render(torch.autograd.Function):
         B, S = iv.B, iv.S
         c = lambda t: None if t is None else t.contiguous()
         dw = torch.empty_like(weights)
-        drgb = torch.empty_like(rgb) if (rgb is not None and ctx.needs_input_grad[1]) else None
-        dpn = torch.empty_like(pred_normals) if (pred_normals is not None and ctx.needs_input_grad[3]) else None
+        drgb = torch.empty_like(rgb) if (rgb is not None and ctx.needs_input_grad[1] and d_rgb is not None) else None
+        # no upstream gradient on the rendered pred-normal map -> no gradient for the per-sample predictions (lets the
+        # producer skip the whole mlp_pred_normals backward, as when pred_normal_loss_mult == 0)
+        dpn = torch.empty_like(pred_normals) if (pred_normals is not None and ctx.needs_input_grad[3] and d_pn is not None) else None
         s, e, stride = iv.triple()
         call("nvo_render_backward", B, S, s, e, stride, weights, rgb, normals, pred_normals, c(d_rgb), c(d_acc), c(d_dexp), minmax, c(d_n), c(d_pn), 0, dw,
              drgb, dpn)
@@ -693,3 +697,213 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr: float, beta1: float 
         check(t, name, torch.float32, (n,))
     check(step, "step", torch.int32, (1,))
     call("nvo_adam_step", n, params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, grad_scale)
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core (tcgen05) MLP path: fp16 operands, fp32 accumulate, for widths <= 64 and depth <= 4
+# ------------------------------------------------------------------------------------------------
+
+
+def tc_eligible(spec: MlpSpec) -> bool:
+    return len(spec.dims) <= 4 and spec.in_dim <= 64 and all(d <= 64 for d in spec.dims)
+
+
+def tc_in_pad(spec: MlpSpec) -> int:
+    return (spec.in_dim + 15) // 16 * 16
+
+
+def cast_pad_f16(x, spec: MlpSpec):
+    """fp32 [n,in_dim] -> fp16 [n,in_pad] zero padded."""
+    check(x, "mlp input", torch.float32, (None, spec.in_dim))
+    out = torch.empty((x.shape[0], tc_in_pad(spec)), dtype=torch.float16, device=x.device)
+    call("nvo_cast_pad_f16", x.shape[0], spec.in_dim, tc_in_pad(spec), x, out)
+    return out
+
+
+def _tc_saved_bytes(spec: MlpSpec, n: int) -> int:
+    import ctypes
+
+    return int(_lib.load().nvo_mlp_tc_saved_bytes(ctypes.addressof(spec.desc), n))
+
+
+def mlp_tc_forward(x16, flat, spec: MlpSpec, save: bool, row_mask=None):
+    n = x16.shape[0]
+    check(x16, "mlp_tc input", torch.float16, (n, tc_in_pad(spec)))
+    check(flat, "mlp params", torch.float32, (spec.n_params,))
+    if row_mask is not None:
+        check(row_mask, "row_mask", torch.float32, (n,))
+    y = torch.empty((n, spec.out_dim), dtype=torch.float32, device=x16.device)
+    saved = None
+    if save and len(spec.dims) > 1:
+        saved = torch.empty(_tc_saved_bytes(spec, n), dtype=torch.uint8, device=x16.device)
+    call("nvo_mlp_tc_forward", spec.desc, n, x16, flat, row_mask, y, saved)
+    return y, saved
+
+
+def mlp_tc_backward(x16, flat, saved, y, dy, spec: MlpSpec, need_dx: bool, need_dparams: bool, dflat=None, row_mask=None):
+    n = x16.shape[0]
+    check(dy, "mlp dy", torch.float32, (n, spec.out_dim))
+    dx = torch.empty((n, spec.in_dim), dtype=torch.float32, device=x16.device) if need_dx else None
+    if need_dparams and dflat is None:
+        dflat = torch.zeros(spec.n_params, dtype=torch.float32, device=x16.device)
+    scratch = torch.empty(1, dtype=torch.float32, device=x16.device)
+    call("nvo_mlp_tc_backward", spec.desc, n, x16, flat, saved, y, row_mask, dy, scratch, dx, dflat if need_dparams else None)
+    return dx, dflat
+
+
+def _flat_of(params):
+    with torch.no_grad():
+        flat = flat_alias(params)
+        if flat is None:
+            flat = torch.cat([p.reshape(-1).float() for p in params])
+    return flat
+
+
+def _split_grads(dflat, spec: MlpSpec):
+    grads = []
+    for (a, b), (ws, bs) in zip(_pairs(spec.offsets()), spec.shapes):
+        grads.append(dflat[a[0]:a[1]].view(ws))
+        grads.append(dflat[b[0]:b[1]].view(bs))
+    return grads
+
+
+class _MlpApplyTC(torch.autograd.Function):
+    """fp32 [n,in_dim] input, cast + padded internally (tcnn.Network drop-in on the tensor-core path)."""
+
+    @staticmethod
+    def forward(ctx, x, spec, row_mask, *params):
+        x16 = cast_pad_f16(x.contiguous(), spec)
+        flat = _flat_of(params)
+        need = x.requires_grad or any(p.requires_grad for p in params)
+        y, saved = mlp_tc_forward(x16, flat, spec, need, row_mask)
+        ctx.save_for_backward(x16, flat, saved, y, row_mask)
+        ctx.spec, ctx.n_tensors = spec, len(params)
+        ctx.main_grad = getattr(params[0], "_nvo_main_grad", None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x16, flat, saved, y, row_mask = ctx.saved_tensors
+        need_dx, need_dp = ctx.needs_input_grad[0], any(ctx.needs_input_grad[3:])
+        dx, dflat = mlp_tc_backward(x16, flat, saved, y, dy.contiguous(), ctx.spec, need_dx, need_dp, ctx.main_grad, row_mask)
+        grads = [None] * ctx.n_tensors
+        if need_dp and ctx.main_grad is None:
+            grads = _split_grads(dflat, ctx.spec)
+        return (dx, None, None, *grads)
+
+
+def mlp_apply_tc(x, spec: MlpSpec, params, row_mask=None):
+    return _MlpApplyTC.apply(x, spec, row_mask, *params)
+
+
+class _GridMlpTC(torch.autograd.Function):
+    """MLPWithHashEncoding on the tensor-core path: hash-grid features are produced directly in fp16 and never cross
+    autograd; x [n,3] fp32 -> y [n,out] fp32."""
+
+    @staticmethod
+    def forward(ctx, x, table, gspec, mspec, *params):
+        x = x.contiguous()
+        feat16 = grid_forward(x, table, gspec, torch.float16)
+        flat = _flat_of(params)
+        need = x.requires_grad or table.requires_grad or any(p.requires_grad for p in params)
+        y, saved = mlp_tc_forward(feat16, flat, mspec, need)
+        ctx.save_for_backward(x, table, feat16, flat, saved, y)
+        ctx.gspec, ctx.mspec, ctx.n_tensors = gspec, mspec, len(params)
+        ctx.table_main_grad = getattr(table, "_nvo_main_grad", None)
+        ctx.mlp_main_grad = getattr(params[0], "_nvo_main_grad", None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, table, feat16, flat, saved, y = ctx.saved_tensors
+        need_dx, need_dt, need_dp = ctx.needs_input_grad[0], ctx.needs_input_grad[1], any(ctx.needs_input_grad[4:])
+        dfeat, dflat = mlp_tc_backward(feat16, flat, saved, y, dy.contiguous(), ctx.mspec, need_dx or need_dt, need_dp, ctx.mlp_main_grad)
+        dtable = dx = None
+        if need_dt:
+            if ctx.table_main_grad is not None:
+                grid_backward(x, dfeat, ctx.gspec, dtable=ctx.table_main_grad)
+            else:
+                dtable = grid_backward(x, dfeat, ctx.gspec).view(table.shape)
+        if need_dx:
+            dx = grid_backward_input(x, table, dfeat, ctx.gspec)
+        grads = [None] * ctx.n_tensors
+        if need_dp and ctx.mlp_main_grad is None:
+            grads = _split_grads(dflat, ctx.mspec)
+        return (dx, dtable, None, None, *grads)
+
+
+def grid_mlp_tc(x, table, gspec: GridSpec, mspec: MlpSpec, params):
+    return _GridMlpTC.apply(x, table, gspec, mspec, *params)
+
+
+class _FieldHeadsTC(torch.autograd.Function):
+    """NerfactoField.get_outputs on the tensor-core path: input assembly (fp16, padded) -> mlp_head -> rgb and
+    mlp_pred_normals(+head, tanh) -> normalize -> pred_normals, plus density = trunc_exp(h0)*selector.
+    Returns density [n], rgb [n,3], pred_normals [n,3] | None."""
+
+    @staticmethod
+    def forward(ctx, h, embedding, selector, directions, positions, cam_idx, B, S, head_spec, pn_spec, n_head, *params):
+        ctx.set_materialize_grads(False)
+        n = B * S
+        dev = h.device
+        h = check(h.contiguous(), "mlp_base output", torch.float32, (n, 16))
+        embedding = check(embedding.contiguous(), "appearance embedding", torch.float32)
+        head_params, pn_params = params[:n_head], params[n_head:]
+        want_pn = pn_spec is not None
+        density = torch.empty(n, dtype=torch.float32, device=dev)
+        head_in = torch.empty((n, 64), dtype=torch.float16, device=dev)
+        pn_in = torch.empty((n, 32), dtype=torch.float16, device=dev) if want_pn else None
+        call("nvo_field_assemble_forward", B, S, h, selector, directions, positions, cam_idx, embedding, 1, density, head_in, pn_in)
+        need = h.requires_grad or embedding.requires_grad or any(p.requires_grad for p in params)
+        head_flat = _flat_of(head_params)
+        rgb, head_saved = mlp_tc_forward(head_in, head_flat, head_spec, need)
+        pn_flat = pn_saved = pn_raw = pn = None
+        if want_pn:
+            pn_flat = _flat_of(pn_params)
+            pn_raw, pn_saved = mlp_tc_forward(pn_in, pn_flat, pn_spec, need)
+            pn = torch.empty_like(pn_raw)
+            call("nvo_normalize3_forward", n, pn_raw, 1.0, 1e-12, pn)
+        ctx.save_for_backward(h, selector, cam_idx, head_in, head_flat, head_saved, rgb, pn_in, pn_flat, pn_saved, pn_raw)
+        ctx.B, ctx.S, ctx.emb_shape, ctx.head_spec, ctx.pn_spec = B, S, embedding.shape, head_spec, pn_spec
+        ctx.n_head, ctx.n_pn = len(head_params), len(pn_params)
+        ctx.emb_main_grad = getattr(embedding, "_nvo_main_grad", None)
+        ctx.head_main_grad = getattr(head_params[0], "_nvo_main_grad", None)
+        ctx.pn_main_grad = getattr(pn_params[0], "_nvo_main_grad", None) if want_pn else None
+        return density, rgb, pn
+
+    @staticmethod
+    def backward(ctx, ddensity, drgb, dpn):
+        h, selector, cam_idx, head_in, head_flat, head_saved, rgb, pn_in, pn_flat, pn_saved, pn_raw = ctx.saved_tensors
+        n, dev = h.shape[0], h.device
+        c = lambda t: None if t is None else t.contiguous()
+        if drgb is None:
+            drgb = torch.zeros((n, 3), dtype=torch.float32, device=dev)
+        dhead_in, dhead_flat = mlp_tc_backward(head_in, head_flat, head_saved, rgb, drgb.contiguous(), ctx.head_spec, True, True, ctx.head_main_grad)
+        dpn_in = dpn_flat = None
+        if ctx.pn_spec is not None and dpn is not None:
+            dpn_raw = torch.empty_like(pn_raw)
+            call("nvo_normalize3_backward", n, pn_raw, dpn.contiguous(), 1.0, 1e-12, dpn_raw)
+            dpn_in, dpn_flat = mlp_tc_backward(pn_in, pn_flat, pn_saved, pn_raw, dpn_raw, ctx.pn_spec, True, True, ctx.pn_main_grad)
+        dh = torch.empty_like(h)
+        demb = None
+        if ctx.needs_input_grad[1]:
+            if ctx.emb_main_grad is not None and cam_idx is not None:
+                demb = ctx.emb_main_grad
+            elif cam_idx is not None:
+                demb = torch.zeros(ctx.emb_shape, dtype=torch.float32, device=dev)
+            else:
+                demb = dhead_in[:, 31:].sum(0).reshape(ctx.emb_shape)
+        call("nvo_field_assemble_backward", ctx.B, ctx.S, h, selector, cam_idx, c(ddensity), dhead_in, dpn_in, dh, demb if cam_idx is not None else None)
+        if demb is ctx.emb_main_grad:
+            demb = None
+        head_grads = [None] * ctx.n_head
+        if ctx.head_main_grad is None:
+            head_grads = _split_grads(dhead_flat, ctx.head_spec)
+        pn_grads = [None] * ctx.n_pn
+        if ctx.pn_spec is not None and ctx.pn_main_grad is None:
+            pn_grads = _split_grads(dpn_flat, ctx.pn_spec) if dpn_flat is not None else [None] * ctx.n_pn
+        return (dh, demb, None, None, None, None, None, None, None, None, None, *head_grads, *pn_grads)
+
+
+def field_heads_tc(h, embedding, selector, directions, positions, cam_idx, B, S, head_spec, head_params, pn_spec=None, pn_params=()):
+    return _FieldHeadsTC.apply(h, embedding, selector, directions, positions, cam_idx, B, S, head_spec, pn_spec, len(head_params), *head_params, *pn_params)

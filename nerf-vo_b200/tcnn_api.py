@@ -127,7 +127,9 @@ class _MlpPart:
         for (a, b), (ws, bs) in zip(ops._pairs(self.spec.offsets()), self.spec.shapes):
             views.append(flat[a[0]:a[1]].view(ws))
             views.append(flat[b[0]:b[1]].view(bs))
-        return ops.mlp_apply(x, self.spec, views)
+        if ops.tc_eligible(self.spec) and min(self.spec.dims[:-1] or (64,)) >= 32:
+            return ops.mlp_apply_tc(x, self.spec, views)  # FullyFusedMLP on tcgen05 (fp16 operands, fp32 accumulate)
+        return ops.mlp_apply(x, self.spec, views)  # narrow networks: exact fp32 SIMT kernel
 
 
 class Encoding(Module):
