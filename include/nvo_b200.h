@@ -112,6 +112,26 @@ int nvo_mlp_tc_backward(const nvo_mlp_desc* d, void* stream, int64_t n, const vo
                         const float* row_mask, const float* dy, float* scratch, float* dx, float* dparams);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused proposal density field — replaces HashMLPDensityField.density_fn / get_density
+ * (NS/fields/density_fields.py:93-116, NS/fields/base_field.py:48-68) as ProposalNetworkSampler calls it
+ * (NS/model_components/ray_samplers.py:604-610): position -> SceneContraction -> (x+2)/4 -> selector -> hash grid (5 levels)
+ * -> Linear(10,16)+ReLU -> Linear(16,1) -> trunc_exp * selector in one kernel; nothing but the density (and, for
+ * training, the 2L interpolated features) is written to HBM.
+ * Sample points: `positions` [B*S,3] when non-NULL, else o + d*(start+end)/2 from (origins, directions, starts, ends, stride).
+ * params: the MLP in torch layout (W0[16,10], b0[16], W1[1,16], b1[1]), fp32.
+ * feat (nullable => inference): [L][B*S][2] fp32 saved for the backward.  nvo_prop_density_supported tells the host
+ * whether a (levels, hidden width, layers) combination has a fused kernel; others use the unfused operators.
+ * backward: dtable (fp32, accumulate, nullable), dparams (accumulate, nullable) from ddensity [B*S].
+ * ------------------------------------------------------------------------------------------- */
+int nvo_prop_density_supported(int32_t n_levels, int32_t hidden, int32_t n_layers);
+int nvo_prop_density_forward(const nvo_grid_desc* g, int32_t hidden, void* stream, int64_t B, int32_t S, const float* origins, const float* directions,
+                             const float* starts, const float* ends, int64_t stride, const float* positions, const void* table, const float* params,
+                             float* density, float* feat);
+int nvo_prop_density_backward(const nvo_grid_desc* g, int32_t hidden, void* stream, int64_t B, int32_t S, const float* origins, const float* directions,
+                              const float* starts, const float* ends, int64_t stride, const float* positions, const float* params, const float* feat,
+                              const float* ddensity, float* dtable, float* dparams);
+
+/* ---------------------------------------------------------------------------------------------
  * Field element-wise operators.
  * ------------------------------------------------------------------------------------------- */
 /* SceneContraction(order=inf) + (x+2)/4 + selector masking (NS/field_components/spatial_distortions.py:67-69,

@@ -6,60 +6,12 @@
 // Work decomposition: one thread per (sample, level) with level fastest, so a warp's 32 threads cover
 // 32/L consecutive samples: x loads are near-broadcast, the y / dy accesses of a warp are one contiguous
 // 256-byte run (fp32) and every thread keeps 8 independent 8-byte (float2) or 4-byte (half2) gathers in flight.
-#include "nvo_common.cuh"
-
-struct GridP {
-    int L;
-    int log2T;
-    float scale[NVO_MAX_LEVELS];
-};
-
-#define PRIME_Y 2654435761u
-#define PRIME_Z 805459861u
-
-struct Corner {
-    float ox, oy, oz;       // fractional offsets
-    uint32_t hx[2], hy[2], hz[2];  // per-axis hash terms for floor (0) / ceil (1)
-};
-
-__device__ __forceinline__ Corner make_corner(float px, float py, float pz, float scale) {
-    Corner c;
-    const float sx = __fmul_rn(px, scale), sy = __fmul_rn(py, scale), sz = __fmul_rn(pz, scale);
-    const float fx = floorf(sx), fy = floorf(sy), fz = floorf(sz);
-    c.ox = __fsub_rn(sx, fx);
-    c.oy = __fsub_rn(sy, fy);
-    c.oz = __fsub_rn(sz, fz);
-    const int ifx = (int)fx, ify = (int)fy, ifz = (int)fz;
-    const int icx = (int)ceilf(sx), icy = (int)ceilf(sy), icz = (int)ceilf(sz);
-    c.hx[0] = (uint32_t)ifx;
-    c.hx[1] = (uint32_t)icx;
-    c.hy[0] = (uint32_t)ify * PRIME_Y;
-    c.hy[1] = (uint32_t)icy * PRIME_Y;
-    c.hz[0] = (uint32_t)ifz * PRIME_Z;
-    c.hz[1] = (uint32_t)icz * PRIME_Z;
-    return c;
-}
-
-// reference corner k -> (x,y,z) picks ceil(1)/floor(0): encodings.py:435-442
-//   k: 0=(c,c,c) 1=(c,f,c) 2=(f,f,c) 3=(f,c,c) 4=(c,c,f) 5=(c,f,f) 6=(f,f,f) 7=(f,c,f); bit k of each mask
-#define SEL_X(k) ((0x33 >> (k)) & 1)
-#define SEL_Y(k) ((0x99 >> (k)) & 1)
-#define SEL_Z(k) ((0x0F >> (k)) & 1)
-
-__device__ __forceinline__ uint32_t corner_index(const Corner& c, int sx, int sy, int sz, uint32_t mask) {
-    return (c.hx[sx] ^ c.hy[sy] ^ c.hz[sz]) & mask;
-}
-
-__device__ __forceinline__ float2 load_row(const float2* t, size_t i) { return __ldg(t + i); }
-__device__ __forceinline__ float2 load_row(const __half2* t, size_t i) { return __half22float2(__ldg(t + i)); }
+#include "grid_common.cuh"
 
 __device__ __forceinline__ void store_feat(float* y, int64_t t, float a, float b) { reinterpret_cast<float2*>(y)[t] = make_float2(a, b); }
 __device__ __forceinline__ void store_feat(__half* y, int64_t t, float a, float b) { reinterpret_cast<__half2*>(y)[t] = __floats2half2_rn(a, b); }
 __device__ __forceinline__ float2 load_feat(const float* y, int64_t t) { return __ldg(reinterpret_cast<const float2*>(y) + t); }
 __device__ __forceinline__ float2 load_feat(const __half* y, int64_t t) { return __half22float2(__ldg(reinterpret_cast<const __half2*>(y) + t)); }
-
-// a*w + b*(1-w) with the reference's rounding sequence (mul, mul, add)
-__device__ __forceinline__ float lerp_ref(float a, float b, float w, float omw) { return __fadd_rn(__fmul_rn(a, w), __fmul_rn(b, omw)); }
 
 template <typename RowT, typename OutT>
 __global__ void __launch_bounds__(256) k_grid_fwd(const __grid_constant__ GridP p, int64_t total, const float* __restrict__ x,
@@ -93,26 +45,23 @@ __global__ void __launch_bounds__(256) k_grid_fwd(const __grid_constant__ GridP 
     store_feat(y, t, out[0], out[1]);
 }
 
+// Backward scatter: one thread per SAMPLE looping over the levels, so that the 32 lanes of a warp are 32 consecutive samples
+// (neighbours along a ray) and equal target rows form runs that seg_red_add_v2 collapses before touching L2.
 template <typename OutT>
-__global__ void __launch_bounds__(256) k_grid_bwd(const __grid_constant__ GridP p, int64_t total, const float* __restrict__ x,
+__global__ void __launch_bounds__(256) k_grid_bwd(const __grid_constant__ GridP p, int64_t n, const float* __restrict__ x,
                                                   const OutT* __restrict__ dy, float* __restrict__ dtable) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const int64_t s = t / p.L;
-    const int l = (int)(t - s * p.L);
-    const float2 g = load_feat(dy, t);
-    if (g.x == 0.f && g.y == 0.f) return;  // adding zeros changes nothing (masked / padded samples)
-    const float px = __ldg(x + 3 * s), py = __ldg(x + 3 * s + 1), pz = __ldg(x + 3 * s + 2);
-    const Corner c = make_corner(px, py, pz, p.scale[l]);
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool valid = s < n;
+    const int64_t ss = valid ? s : n - 1;
+    const float px = __ldg(x + 3 * ss), py = __ldg(x + 3 * ss + 1), pz = __ldg(x + 3 * ss + 2);
     const uint32_t mask = (1u << p.log2T) - 1u;
-    float* slab = dtable + (((size_t)l << p.log2T) << 1);
-    const float wx[2] = {1.f - c.ox, c.ox}, wy[2] = {1.f - c.oy, c.oy}, wz[2] = {1.f - c.oz, c.oz};
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int sx = SEL_X(k), sy = SEL_Y(k), sz = SEL_Z(k);
-        const float w = wz[sz] * wy[sy] * wx[sx];
-        const uint32_t idx = corner_index(c, sx, sy, sz, mask);
-        nvo_red_add_v2(slab + 2 * (size_t)idx, g.x * w, g.y * w);
+    for (int l = 0; l < p.L; ++l) {
+        float2 g = load_feat(dy, ss * p.L + l);
+        if (!valid) g = make_float2(0.f, 0.f);
+        if (__ballot_sync(0xffffffffu, g.x != 0.f || g.y != 0.f) == 0u) continue;  // whole warp masked / padded at this level
+        const Corner c = make_corner(px, py, pz, p.scale[l]);
+        grid_level_scatter(dtable + (((size_t)l << p.log2T) << 1), c, mask, g.x, g.y, valid, lane);
     }
 }
 
@@ -225,13 +174,12 @@ extern "C" int nvo_grid_backward(const nvo_grid_desc* d, void* stream, int64_t n
     NVO_CHECK(n >= 0, "grid_backward: negative batch");
     if (n == 0) return 0;
     NVO_CHECK(x && dy && dtable, "grid_backward: null pointer");
-    const int64_t total = n * p.L;
     cudaStream_t st = (cudaStream_t)stream;
-    const unsigned int g = nvo_blocks(total, 256);
+    const unsigned int g = nvo_blocks(n, 256);
     if (d->out_dtype == NVO_F32)
-        k_grid_bwd<float><<<g, 256, 0, st>>>(p, total, x, (const float*)dy, dtable);
+        k_grid_bwd<float><<<g, 256, 0, st>>>(p, n, x, (const float*)dy, dtable);
     else
-        k_grid_bwd<__half><<<g, 256, 0, st>>>(p, total, x, (const __half*)dy, dtable);
+        k_grid_bwd<__half><<<g, 256, 0, st>>>(p, n, x, (const __half*)dy, dtable);
     NVO_CUDA_LAUNCH_CHECK("grid_backward");
     return 0;
 }

@@ -78,13 +78,42 @@ class HashMLPDensityField(Field):
             self.mlp_base = nn.Sequential(self.encoding, network)
         else:
             self.linear = MLP(in_dim=self.encoding.get_out_dim(), num_layers=1, layer_width=1, out_dim=1, out_activation="trunc_exp")
+        self._fused_ok = None
+
+    def _net(self) -> MLP:
+        return self.mlp_base[1] if not self.use_linear else self.linear
+
+    def _fused(self) -> bool:
+        if self._fused_ok is None:
+            self._fused_ok = (not self.use_linear) and ops.prop_density_supported(self.encoding.spec, self._net().spec)
+        return self._fused_ok
 
     def _density_from_positions(self, positions: torch.Tensor) -> Tuple[torch.Tensor, None]:
+        net = self._net()
+        if self._fused():
+            # one kernel: contraction, hash grid, MLP, trunc_exp * selector (csrc/prop.cu)
+            net._repack()
+            n = positions.numel() // 3
+            density = ops.prop_density(self.encoding.hash_table, self.encoding.spec, net.spec, net._flat_param_list(), n, 1, positions=positions)
+            return density.view(*positions.shape[:-1], 1), None
         x, sel = ops.contract_normalize(positions)
         feat = self.encoding(x)
-        net = self.mlp_base[1] if not self.use_linear else self.linear
         density = net(feat, row_mask=sel)
         return density.view(*positions.shape[:-1], 1), None
+
+    def density_from_ray_samples(self, ray_samples: RaySamples) -> torch.Tensor:
+        """density_fn(ray_samples.frustums.get_positions()) without materialising the positions: the fused kernel derives
+        each sample point from the ray and its interval (same arithmetic as Frustums.get_positions)."""
+        fr = ray_samples.frustums
+        iv = fr.intervals()
+        if not self._fused() or fr.offsets is not None or fr.origins.shape[-2] != 1:
+            return self.density_fn(fr.get_positions())
+        net = self._net()
+        net._repack()
+        o = fr.origins.reshape(-1, 3).contiguous()
+        d = fr.directions.reshape(-1, 3).contiguous()
+        density = ops.prop_density(self.encoding.hash_table, self.encoding.spec, net.spec, net._flat_param_list(), iv.B, iv.S, origins=o, directions=d, iv=iv)
+        return density.view(iv.B, iv.S, 1)
 
     def get_outputs(self, ray_samples: RaySamples, density_embedding: Optional[torch.Tensor] = None) -> dict:
         return {}

@@ -245,6 +245,81 @@ def mlp_apply(x, spec: MlpSpec, params: Sequence[torch.Tensor], row_mask=None):
 
 
 # ------------------------------------------------------------------------------------------------
+# fused proposal density field (grid + 16-wide MLP + trunc_exp * selector in one kernel each way)
+# ------------------------------------------------------------------------------------------------
+
+
+def prop_density_supported(gspec: GridSpec, mspec: MlpSpec) -> bool:
+    if len(mspec.dims) != 2 or mspec.dims[1] != 1 or mspec.acts[0] != "relu" or mspec.acts[1] != "trunc_exp" or mspec.in_dim != gspec.out_dim:
+        return False
+    return bool(_lib.load().nvo_prop_density_supported(gspec.n_levels, mspec.dims[0], 2))
+
+
+class _PropDensity(torch.autograd.Function):
+    """density [B,S] at the samples of `iv` on rays (origins, directions), or at explicit `positions` [B*S,3]."""
+
+    @staticmethod
+    def forward(ctx, table, gspec, hidden, origins, directions, iv, positions, B, S, *params):
+        flat = _flat_of(params)
+        dev = table.device
+        need = any(ctx.needs_input_grad)  # False under no_grad (eval, frozen proposal steps): no features saved
+        n = B * S
+        density = torch.empty((B, S), dtype=torch.float32, device=dev)
+        feat = torch.empty((gspec.n_levels, n, 2), dtype=torch.float32, device=dev) if need else None
+        if positions is not None:
+            positions = check(positions.reshape(-1, 3).contiguous(), "positions", torch.float32, (n, 3))
+            s = e = None
+            stride = 0
+        else:
+            check(origins, "origins", torch.float32, (B, 3))
+            check(directions, "directions", torch.float32, (B, 3))
+            s, e, stride = iv.triple()
+        call("nvo_prop_density_forward", gspec.desc(table.dtype, torch.float32), hidden, B, S, origins, directions, s, e, stride, positions, table, flat,
+             density, feat)
+        ctx.save_for_backward(table, flat, feat, origins, directions, positions)
+        ctx.iv, ctx.gspec, ctx.hidden, ctx.B, ctx.S, ctx.n_tensors = iv, gspec, hidden, B, S, len(params)
+        ctx.table_main_grad = getattr(table, "_nvo_main_grad", None)
+        ctx.mlp_main_grad = getattr(params[0], "_nvo_main_grad", None)
+        ctx.mspec_shapes = [tuple(p.shape) for p in params]
+        return density
+
+    @staticmethod
+    def backward(ctx, ddensity):
+        table, flat, feat, origins, directions, positions = ctx.saved_tensors
+        need_dt, need_dp = ctx.needs_input_grad[0], any(ctx.needs_input_grad[9:])
+        dev = table.device
+        dtable = dflat = None
+        if need_dt:
+            dtable = ctx.table_main_grad if ctx.table_main_grad is not None else torch.zeros(table.shape, dtype=torch.float32, device=dev)
+        if need_dp:
+            dflat = ctx.mlp_main_grad if ctx.mlp_main_grad is not None else torch.zeros(flat.numel(), dtype=torch.float32, device=dev)
+        if positions is not None:
+            s = e = None
+            stride = 0
+        else:
+            s, e, stride = ctx.iv.triple()
+        call("nvo_prop_density_backward", ctx.gspec.desc(table.dtype, torch.float32), ctx.hidden, ctx.B, ctx.S, origins, directions, s, e, stride, positions,
+             flat, feat, ddensity.contiguous(), dtable, dflat)
+        if dtable is ctx.table_main_grad:
+            dtable = None
+        elif dtable is not None and table.dtype != torch.float32:
+            dtable = dtable.to(table.dtype)
+        grads = [None] * ctx.n_tensors
+        if need_dp and ctx.mlp_main_grad is None:
+            off = 0
+            grads = []
+            for shp in ctx.mspec_shapes:
+                k = int(np.prod(shp))
+                grads.append(dflat[off:off + k].view(shp))
+                off += k
+        return (dtable, None, None, None, None, None, None, None, None, *grads)
+
+
+def prop_density(table, gspec: GridSpec, mspec: MlpSpec, params, B: int, S: int, origins=None, directions=None, iv=None, positions=None):
+    return _PropDensity.apply(table, gspec, mspec.dims[0], origins, directions, iv, positions, B, S, *params)
+
+
+# ------------------------------------------------------------------------------------------------
 # field element-wise operators
 # ------------------------------------------------------------------------------------------------
 

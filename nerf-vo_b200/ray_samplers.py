@@ -127,11 +127,13 @@ class ProposalNetworkSampler(Sampler):
                 # the anneal pow (ray_samplers.py:602) is applied inside the resampling kernel
                 ray_samples = self.pdf_sampler(ray_bundle, ray_samples, weights, num_samples=num_samples, jitter=jit, anneal=self._anneal)
             if is_prop:
-                if updated:
-                    density = density_fns[i_level](ray_samples.frustums.get_positions())
-                else:
-                    with torch.no_grad():
-                        density = density_fns[i_level](ray_samples.frustums.get_positions())
+                fn = density_fns[i_level]
+                owner = getattr(fn, "__self__", None)
+                # our proposal fields evaluate straight from the ray samples (no positions tensor); any other callable
+                # gets the reference's density_fn(positions) call
+                fused = getattr(owner, "density_from_ray_samples", None) if getattr(fn, "__name__", "") == "density_fn" else None
+                with torch.enable_grad() if updated else torch.no_grad():
+                    density = fused(ray_samples) if fused is not None else fn(ray_samples.frustums.get_positions())
                 weights = ray_samples.get_weights(density)
                 weights_list.append(weights)
                 ray_samples_list.append(ray_samples)
