@@ -33,7 +33,8 @@ extern "C" {
 #define NVO_MAX_LAYERS 6
 
 /* dtype tags for the table / feature buffers */
-enum { NVO_F32 = 0, NVO_F16 = 1 };
+/* NVO_F16_TMH (grid forward output only): fp16 in the tensor-core MLP's tile-major operand layout, see nvo_mlp_tc_forward */
+enum { NVO_F32 = 0, NVO_F16 = 1, NVO_F16_TMH = 2 };
 /* activations (tcnn network_config "activation"/"output_activation", NS/field_components/mlp.py:34-58) */
 /* NVO_ACT_TRUNC_EXP: exp forward, backward g*exp(clamp(x,-15,15)) (NS/field_components/activations.py:28-41) */
 enum { NVO_ACT_NONE = 0, NVO_ACT_RELU = 1, NVO_ACT_SIGMOID = 2, NVO_ACT_TANH = 3, NVO_ACT_EXP = 4, NVO_ACT_TRUNC_EXP = 5 };
@@ -56,7 +57,7 @@ typedef struct {
     int32_t n_levels;
     int32_t log2_T;
     int32_t table_dtype; /* NVO_F32 | NVO_F16 */
-    int32_t out_dtype;   /* NVO_F32 | NVO_F16 : dtype of y / dy */
+    int32_t out_dtype;   /* NVO_F32 | NVO_F16 : dtype of y / dy (row-major [n,2L]); NVO_F16_TMH: y as TMH tiles, forward only */
     float scalings[NVO_MAX_LEVELS];
 } nvo_grid_desc;
 
@@ -97,18 +98,25 @@ int nvo_mlp_backward(const nvo_mlp_desc* d, void* stream, int64_t n, const float
                      const float* y, const float* row_mask, const float* dy, float* dx, float* dparams);
 
 /* Tensor-core path (tcgen05.mma, accumulators in TMEM) for networks whose widths are <= 64 and depth <= 4 — the three
- * field MLPs.  Same semantics and parameter layout as nvo_mlp_forward/backward with fp16 operands and fp32 accumulation:
- *   x16   [n, in_pad] fp16, in_pad = nvo_mlp_tc_in_pad(d) (in_dim rounded up to 16, zero padded);
- *   saved opaque forward context of nvo_mlp_tc_saved_bytes(d, n) bytes (fp16 hidden activations, tile-major);
+ * field MLPs.  Same semantics and parameter layout as nvo_mlp_forward/backward with fp16 operands and fp32 accumulation.
+ *   x16     the input in TMH layout ("tile-major half"): tiles of 128 rows, each a contiguous in_pad*256-byte block
+ *           [chunk = col/8][row][8 halfs] (the UMMA canonical operand layout, moved to shared memory by one bulk copy);
+ *           in_pad = nvo_mlp_tc_in_pad(d) (in_dim rounded up to 16); ceil(n/128) tiles, padding columns / rows ZERO.
+ *           nvo_cast_pad_f16 produces it from fp32 [n,in_dim] row-major; the hash grid and the field assembly write it directly.
+ *   wimage  the packed fp16 weight image of nvo_mlp_tc_wimage_bytes(d) bytes, refreshed with nvo_mlp_tc_pack_weights
+ *           whenever `params` (torch layout, fp32, as nvo_mlp_forward) change;
+ *   saved   opaque forward context of nvo_mlp_tc_saved_bytes(d, n) bytes (fp16 hidden activations, TMH layout);
  *   scratch one float the backward uses for its device-side gradient scale (max|dy| -> power-of-two loss scale, the
- *   device analogue of tinycudann's loss_scale, modules.py:174);
- *   y, dy, dx, dparams fp32 exactly as the SIMT entry points. */
+ *           device analogue of tinycudann's loss_scale, modules.py:174);
+ *   y, dy, dx, dparams fp32 row-major exactly as the SIMT entry points. */
 int nvo_mlp_tc_in_pad(const nvo_mlp_desc* d);
 int64_t nvo_mlp_tc_saved_bytes(const nvo_mlp_desc* d, int64_t n);
+int64_t nvo_mlp_tc_wimage_bytes(const nvo_mlp_desc* d);
 int nvo_cast_pad_f16(void* stream, int64_t n, int32_t in_dim, int32_t kpad, const float* x, void* out);
-int nvo_mlp_tc_forward(const nvo_mlp_desc* d, void* stream, int64_t n, const void* x16, const float* params, const float* row_mask, float* y,
+int nvo_mlp_tc_pack_weights(const nvo_mlp_desc* d, void* stream, const float* params, void* wimage);
+int nvo_mlp_tc_forward(const nvo_mlp_desc* d, void* stream, int64_t n, const void* x16, const void* wimage, const float* row_mask, float* y,
                        void* saved);
-int nvo_mlp_tc_backward(const nvo_mlp_desc* d, void* stream, int64_t n, const void* x16, const float* params, const void* saved, const float* y,
+int nvo_mlp_tc_backward(const nvo_mlp_desc* d, void* stream, int64_t n, const void* x16, const void* wimage, const void* saved, const float* y,
                         const float* row_mask, const float* dy, float* scratch, float* dx, float* dparams);
 
 /* ---------------------------------------------------------------------------------------------
@@ -155,7 +163,8 @@ int nvo_normalize3_backward(void* stream, int64_t n, const float* v, const float
  *   pn_in[n,27]  = [posenc12(pos) | h[:,1:16]]                       (:278-281)
  * appearance = embedding[cam_idx[ray]] (training) or the caller-provided mean vector when cam_idx is NULL (eval;
  * embedding then points at ONE 32-vector).  h[n,16] is mlp_base's output.  pn_in may be NULL.
- * f16_padded != 0: head_in / pn_in are fp16 rows zero-padded to 64 / 32 columns (operand format of nvo_mlp_tc_forward). */
+ * f16_padded != 0: head_in / pn_in are fp16 TMH tiles zero-padded to 64 / 32 columns and to ceil(B*S/128) whole tiles (the
+ * operand format of nvo_mlp_tc_forward). */
 int nvo_field_assemble_forward(void* stream, int64_t B, int32_t S, const float* h, const float* selector, const float* directions, const float* pos,
                                const int64_t* cam_idx, const float* embedding, int32_t f16_padded, float* density, void* head_in, void* pn_in);
 /* backward: dh[n,16] (overwritten) and dembedding[K,32] (accumulate, nullable) from ddensity[n] (nullable), dhead_in[n,63], dpn_in[n,27] (nullable) */

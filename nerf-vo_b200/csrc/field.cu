@@ -118,55 +118,97 @@ __global__ void __launch_bounds__(256) k_normalize3_bwd(int64_t n, const float* 
 #define HEAD_IN 63
 #define PN_IN 27
 
-__device__ __forceinline__ void put(float* o, int k, float v) { o[k] = v; }
-__device__ __forceinline__ void put(__half* o, int k, float v) { o[k] = __float2half_rn(v); }
-
-// OutT = float: head_in [n,63], pn_in [n,27] (the reference's widths);  OutT = __half: zero-padded [n,64] / [n,32] rows that the
-// tensor-core MLP stages into shared memory with 16-byte copies.
-template <typename OutT, int HEAD_STRIDE, int PN_STRIDE>
-__global__ void __launch_bounds__(256)
-    k_assemble_fwd(int64_t B, int S, const float* __restrict__ h, const float* __restrict__ selector, const float* __restrict__ dirs,
-                   const float* __restrict__ pos, const int64_t* __restrict__ cam_idx, const float* __restrict__ embedding, float* __restrict__ density,
-                   OutT* __restrict__ head_in, OutT* __restrict__ pn_in) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= B * S) return;
-    const int64_t r = t / S;
-    float hv[16];
+// head_in [n,63] = [SH16((dir+1)/2) | h[1:16] | appearance32], pn_in [n,27] = [posenc12(pos) | h[1:16]] for one sample
+__device__ __forceinline__ void assemble_rows(int64_t t, int64_t r, const float* __restrict__ h, const float* __restrict__ dirs,
+                                              const float* __restrict__ pos, const int64_t* __restrict__ cam_idx, const float* __restrict__ embedding,
+                                              float* hv, float* head, float* pn, bool want_pn) {
 #pragma unroll
     for (int k = 0; k < 16; k += 4) {
         const float4 q = __ldg(reinterpret_cast<const float4*>(h + 16 * t) + (k >> 2));
         hv[k] = q.x, hv[k + 1] = q.y, hv[k + 2] = q.z, hv[k + 3] = q.w;
     }
-    if (density) density[t] = __fmul_rn(expf(hv[0]), __ldg(selector + t));
-    OutT* o = head_in + (int64_t)HEAD_STRIDE * t;
-    float c[16];
     // get_normalized_directions (base_field.py:142): (d + 1) / 2
     sh16(__fdiv_rn(__fadd_rn(__ldg(dirs + 3 * r), 1.f), 2.f), __fdiv_rn(__fadd_rn(__ldg(dirs + 3 * r + 1), 1.f), 2.f),
-         __fdiv_rn(__fadd_rn(__ldg(dirs + 3 * r + 2), 1.f), 2.f), c);
+         __fdiv_rn(__fadd_rn(__ldg(dirs + 3 * r + 2), 1.f), 2.f), head);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) put(o, k, c[k]);
-#pragma unroll
-    for (int k = 0; k < GEO; ++k) put(o, 16 + k, hv[1 + k]);
+    for (int k = 0; k < GEO; ++k) head[16 + k] = hv[1 + k];
     const float* e = cam_idx ? embedding + APP * __ldg(cam_idx + r) : embedding;
-#pragma unroll 8
-    for (int k = 0; k < APP; ++k) put(o, 16 + GEO + k, __ldg(e + k));
 #pragma unroll
-    for (int k = HEAD_IN; k < HEAD_STRIDE; ++k) put(o, k, 0.f);
-    if (pn_in) {
-        OutT* q = pn_in + (int64_t)PN_STRIDE * t;
+    for (int k = 0; k < APP; k += 4) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(e + k));
+        head[16 + GEO + k] = q.x, head[16 + GEO + k + 1] = q.y, head[16 + GEO + k + 2] = q.z, head[16 + GEO + k + 3] = q.w;
+    }
+    head[HEAD_IN] = 0.f;
+    if (want_pn) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const float xi = __ldg(pos + 3 * t + i);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                put(q, i * 2 + k, posenc_value(xi, k, false));
-                put(q, 6 + i * 2 + k, posenc_value(xi, k, true));
+                pn[i * 2 + k] = posenc_value(xi, k, false);
+                pn[6 + i * 2 + k] = posenc_value(xi, k, true);
             }
         }
 #pragma unroll
-        for (int k = 0; k < GEO; ++k) put(q, 12 + k, hv[1 + k]);
+        for (int k = 0; k < GEO; ++k) pn[12 + k] = hv[1 + k];
 #pragma unroll
-        for (int k = PN_IN; k < PN_STRIDE; ++k) put(q, k, 0.f);
+        for (int k = PN_IN; k < 32; ++k) pn[k] = 0.f;
+    }
+}
+
+// fp32 outputs: head_in [n,63], pn_in [n,27] row-major (the reference's widths)
+__global__ void __launch_bounds__(256)
+    k_assemble_fwd(int64_t B, int S, const float* __restrict__ h, const float* __restrict__ selector, const float* __restrict__ dirs,
+                   const float* __restrict__ pos, const int64_t* __restrict__ cam_idx, const float* __restrict__ embedding, float* __restrict__ density,
+                   float* __restrict__ head_in, float* __restrict__ pn_in) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * S) return;
+    const int64_t r = t / S;
+    float hv[16], head[64], pn[32];
+    assemble_rows(t, r, h, dirs, pos, cam_idx, embedding, hv, head, pn, pn_in != nullptr);
+    if (density) density[t] = __fmul_rn(expf(hv[0]), __ldg(selector + t));
+#pragma unroll
+    for (int k = 0; k < HEAD_IN; ++k) head_in[(int64_t)HEAD_IN * t + k] = head[k];
+    if (pn_in) {
+#pragma unroll
+        for (int k = 0; k < PN_IN; ++k) pn_in[(int64_t)PN_IN * t + k] = pn[k];
+    }
+}
+
+__device__ __forceinline__ uint4 pack8h(const float* v) {
+    __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]), c = __floats2half2_rn(v[4], v[5]), d = __floats2half2_rn(v[6], v[7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    u.z = *reinterpret_cast<uint32_t*>(&c);
+    u.w = *reinterpret_cast<uint32_t*>(&d);
+    return u;
+}
+
+// fp16 outputs in the tensor-core MLP's operand layout (TMH tiles of 128 rows, zero padded to 64 / 32 columns and to whole
+// tiles): thread == row, every 8-feature chunk is one 16-byte store, a warp writes 512 contiguous bytes per chunk.
+__global__ void __launch_bounds__(128)
+    k_assemble_fwd_tmh(int64_t B, int S, const float* __restrict__ h, const float* __restrict__ selector, const float* __restrict__ dirs,
+                       const float* __restrict__ pos, const int64_t* __restrict__ cam_idx, const float* __restrict__ embedding, float* __restrict__ density,
+                       uint4* __restrict__ head_in, uint4* __restrict__ pn_in) {
+    const int64_t tile = blockIdx.x;
+    const int rr = threadIdx.x;
+    const int64_t t = tile * 128 + rr;
+    float hv[16], head[64], pn[32];
+    if (t < B * S) {
+        assemble_rows(t, t / S, h, dirs, pos, cam_idx, embedding, hv, head, pn, pn_in != nullptr);
+        if (density) density[t] = __fmul_rn(expf(hv[0]), __ldg(selector + t));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 64; ++k) head[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) pn[k] = 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) head_in[(tile * 8 + c) * 128 + rr] = pack8h(head + 8 * c);
+    if (pn_in) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) pn_in[(tile * 4 + c) * 128 + rr] = pack8h(pn + 8 * c);
     }
 }
 
@@ -274,11 +316,11 @@ extern "C" int nvo_field_assemble_forward(void* stream, int64_t B, int32_t S, co
     NVO_CHECK(!density || selector, "field_assemble_forward: selector required for density");
     NVO_CHECK(!pn_in || pos, "field_assemble_forward: positions required for pn_in");
     if (f16_padded)
-        k_assemble_fwd<__half, 64, 32><<<nvo_blocks(B * S, 256), 256, 0, (cudaStream_t)stream>>>(B, S, h, selector, directions, pos, cam_idx, embedding, density,
-                                                                                                (__half*)head_in, (__half*)pn_in);
+        k_assemble_fwd_tmh<<<(unsigned int)((B * S + 127) / 128), 128, 0, (cudaStream_t)stream>>>(B, S, h, selector, directions, pos, cam_idx, embedding, density,
+                                                                                                 (uint4*)head_in, (uint4*)pn_in);
     else
-        k_assemble_fwd<float, HEAD_IN, PN_IN><<<nvo_blocks(B * S, 256), 256, 0, (cudaStream_t)stream>>>(B, S, h, selector, directions, pos, cam_idx, embedding,
-                                                                                                         density, (float*)head_in, (float*)pn_in);
+        k_assemble_fwd<<<nvo_blocks(B * S, 256), 256, 0, (cudaStream_t)stream>>>(B, S, h, selector, directions, pos, cam_idx, embedding, density,
+                                                                                  (float*)head_in, (float*)pn_in);
     NVO_CUDA_LAUNCH_CHECK("field_assemble_forward");
     return 0;
 }

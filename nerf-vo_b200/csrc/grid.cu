@@ -45,6 +45,56 @@ __global__ void __launch_bounds__(256) k_grid_fwd(const __grid_constant__ GridP 
     store_feat(y, t, out[0], out[1]);
 }
 
+// Forward straight into the tensor-core MLP's operand layout (TMH: tiles of 128 rows, [chunk = col/8][row][8 halfs], see
+// mlp_tc.cu): one thread per (row, chunk) computes the chunk's 4 levels (32 independent gathers in flight) and writes ONE
+// 16-byte vector; consecutive lanes are consecutive rows of the same chunk, so a warp stores 512 contiguous bytes and the
+// coarse-level gathers of neighbouring samples coalesce in L1.  Rows >= n and levels >= L are written as zeros (the MLP's
+// zero padding), so the buffer needs no separate initialisation.
+template <typename RowT>
+__global__ void __launch_bounds__(256) k_grid_fwd_tmh(const __grid_constant__ GridP p, int64_t n, int nch, const float* __restrict__ x,
+                                                      const RowT* __restrict__ table, uint4* __restrict__ y) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= ((n + 127) >> 7 << 7)) return;  // beyond the last (padded) tile
+    const int c = blockIdx.y;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (row < n) {
+        const float px = __ldg(x + 3 * row), py = __ldg(x + 3 * row + 1), pz = __ldg(x + 3 * row + 2);
+        const uint32_t mask = (1u << p.log2T) - 1u;
+        float2 f[4][8];
+        Corner cs[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int l = c * 4 + q;
+            if (l < p.L) {
+                cs[q] = make_corner(px, py, pz, p.scale[l]);
+                const RowT* slab = table + ((size_t)l << p.log2T);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[q][k] = load_row(slab, corner_index(cs[q], SEL_X(k), SEL_Y(k), SEL_Z(k), mask));
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int l = c * 4 + q;
+            if (l < p.L) {
+                const float2 o = trilerp_ref(f[q], cs[q]);
+                v[2 * q] = o.x;
+                v[2 * q + 1] = o.y;
+            }
+        }
+    }
+    const int64_t tile = row >> 7;
+    const int r = (int)(row & 127);
+    __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]), h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    u.z = *reinterpret_cast<uint32_t*>(&h2);
+    u.w = *reinterpret_cast<uint32_t*>(&h3);
+    y[(tile * nch + c) * 128 + r] = u;
+}
+
 // Backward scatter: one thread per SAMPLE looping over the levels, so that the 32 lanes of a warp are 32 consecutive samples
 // (neighbours along a ray) and equal target rows form runs that seg_red_add_v2 collapses before touching L2.
 template <typename OutT>
@@ -140,7 +190,7 @@ static int make_params(const nvo_grid_desc* d, GridP* p) {
     NVO_CHECK(d->n_levels >= 1 && d->n_levels <= NVO_MAX_LEVELS, "grid: n_levels=%d out of range [1,%d]", d->n_levels, NVO_MAX_LEVELS);
     NVO_CHECK(d->log2_T >= 1 && d->log2_T <= 30, "grid: log2_T=%d out of range [1,30]", d->log2_T);
     NVO_CHECK(d->table_dtype == NVO_F32 || d->table_dtype == NVO_F16, "grid: bad table_dtype %d", d->table_dtype);
-    NVO_CHECK(d->out_dtype == NVO_F32 || d->out_dtype == NVO_F16, "grid: bad out_dtype %d", d->out_dtype);
+    NVO_CHECK(d->out_dtype == NVO_F32 || d->out_dtype == NVO_F16 || d->out_dtype == NVO_F16_TMH, "grid: bad out_dtype %d", d->out_dtype);
     p->L = d->n_levels;
     p->log2T = d->log2_T;
     for (int i = 0; i < NVO_MAX_LEVELS; ++i) p->scale[i] = i < d->n_levels ? d->scalings[i] : 0.f;
@@ -155,6 +205,16 @@ extern "C" int nvo_grid_forward(const nvo_grid_desc* d, void* stream, int64_t n,
     NVO_CHECK(x && table && y, "grid_forward: null pointer");
     const int64_t total = n * p.L;
     cudaStream_t st = (cudaStream_t)stream;
+    if (d->out_dtype == NVO_F16_TMH) {
+        const int nch = ((2 * p.L + 15) & ~15) >> 3;  // feature columns padded to the MMA K granularity (16)
+        const dim3 grid((unsigned int)(((n + 127) / 128 * 128 + 255) / 256), (unsigned int)nch);
+        if (d->table_dtype == NVO_F32)
+            k_grid_fwd_tmh<float2><<<grid, 256, 0, st>>>(p, n, nch, x, (const float2*)table, (uint4*)y);
+        else
+            k_grid_fwd_tmh<__half2><<<grid, 256, 0, st>>>(p, n, nch, x, (const __half2*)table, (uint4*)y);
+        NVO_CUDA_LAUNCH_CHECK("grid_forward(tmh)");
+        return 0;
+    }
     const unsigned int g = nvo_blocks(total, 256);
     if (d->table_dtype == NVO_F32 && d->out_dtype == NVO_F32)
         k_grid_fwd<float2, float><<<g, 256, 0, st>>>(p, total, x, (const float2*)table, (float*)y);

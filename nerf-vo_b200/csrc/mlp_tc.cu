@@ -1,19 +1,31 @@
 // Fully fused MLP on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM) for the 64-wide field networks.
-// One CTA processes 128-sample tiles; per layer ONE elected thread issues K/16 tcgen05.mma (M=128 samples, N = layer
-// width, fp16 operands, fp32 accumulate), commits to an mbarrier, and the 4 warps (thread == sample row) pull the
-// accumulator out of TMEM with tcgen05.ld, add bias, apply the activation, convert to fp16 and write the row straight back
-// into shared memory in the UMMA canonical (no-swizzle) layout as the next layer's A operand.
 //
-// Shared-memory operand layout ("natural tile"): T[chunk = col/8][row][8 halfs], i.e. 16-byte vectors of 8 consecutive
-// features of one row, rows adjacent at 16 B, 8-feature chunks at stride rows*16 B.  Verified on B200 (tools/umma_probe.cu):
+// Data layout ("TMH", tile-major half): an activation matrix [n, K] lives in HBM as tiles of 128 rows, each tile a
+// contiguous K*256-byte block [chunk = col/8][row][8 halfs] — exactly the UMMA canonical no-swizzle operand layout.  A tile
+// therefore moves HBM -> shared memory with ONE bulk async copy (cp.async.bulk, the TMA engine's 1-D mode) that signals an
+// mbarrier, producers (hash-grid gather, input assembly) write it with fully coalesced 16-byte stores, and neither
+// transposed weights nor transposed activations are ever materialised:
 //   * as a K-major operand (forward: A = activations, B = W[out][in]):       LBO = chunk stride, SBO = 128 B
 //   * as an MN-major operand (dgrad: B = the SAME W tile; wgrad: A = dZ, B = activations, K = the 128 samples):
 //                                                                             LBO = 128 B, SBO = chunk stride
-// so neither transposed weight copies nor transposed activation tiles are ever materialised.
+// (descriptor conventions pinned on B200 by tools/umma_probe.cu).
 //
-// Backward per layer: wgrad dW_l (+ db_l via an appended ones-column) accumulates in TMEM ACROSS all tiles of the CTA and
-// is flushed once with atomics; dgrad goes TMEM -> registers -> (x relu') -> fp16 -> shared as the next dZ.  Gradients are
-// scaled by a device-side power-of-two (2^8 / max|dy|) before the fp16 conversion and unscaled in fp32 on the way out.
+// Weights: packed once per parameter update (k_tc_pack) into an fp16 image in the same tile layout + fp32 biases; every CTA
+// pulls the image into shared memory with one bulk copy.
+//
+// Forward (k_mlp_tc_fwd): persistent CTAs of 128 threads (thread == sample row), 3-5 CTAs per SM.  The next tile's input is
+// prefetched into the second input buffer while the current tile runs its layer chain: per layer ONE thread issues K/16
+// tcgen05.mma (M = 128 samples, N = layer width) and commits to an mbarrier; the 4 warps pull the accumulator out of TMEM
+// (tcgen05.ld), add bias, activate, convert to fp16 and write the row back to shared memory as the next layer's A operand
+// (and to the saved-activation buffer, TMH layout, for the backward).
+//
+// Backward (k_mlp_tc_bwd): one CTA per SM (the weight-gradient accumulators of ALL layers stay resident in TMEM across every
+// tile of the CTA: dW_l += dZ_l^T A_{l-1}, bias gradient through an appended ones-column, flushed once at the end).  All
+// activations a tile needs (input + every saved hidden layer) are prefetched for the NEXT tile by bulk copies into the
+// second stage while the current tile computes.  Per layer the dgrad MMAs are issued first and committed; the wgrad MMAs
+// are issued right behind them and run on the tensor pipe while the 4 warps do the dgrad epilogue (TMEM -> x act' -> fp16
+// -> the other dZ buffer), so the tensor pipe and the epilogue overlap.  Gradients are scaled by a device-side power of
+// two (2^8 / max|dy|) before the fp16 conversion and unscaled in fp32 on the way out.
 #include <cuda_fp16.h>
 #include "nvo_common.cuh"
 
@@ -26,10 +38,13 @@
 struct TcP {
     int n_layers, in_dim, k0pad;
     int dims[TC_MAX_LAYERS], npad[TC_MAX_LAYERS], kpad[TC_MAX_LAYERS], acts[TC_MAX_LAYERS];
-    int w_off[TC_MAX_LAYERS], b_off[TC_MAX_LAYERS];      // float offsets into params
-    int sw_off[TC_MAX_LAYERS], sb_off[TC_MAX_LAYERS];    // byte offsets into dynamic smem
+    int w_off[TC_MAX_LAYERS], b_off[TC_MAX_LAYERS];      // float offsets into params (torch layout)
+    int iw_off[TC_MAX_LAYERS], ib_off[TC_MAX_LAYERS];    // byte offsets into the packed weight image
+    int img_bytes;
     int saved_chunk_off[TC_MAX_LAYERS];                  // chunk offset of layer l's output inside a saved tile
     int saved_chunks;                                    // chunks per saved tile
+    int a_off[TC_MAX_LAYERS];                            // backward: byte offset of layer l's INPUT tile inside a stage
+    int stage_bytes;                                     // backward: bytes of one prefetch stage
     int n_params;
 };
 
@@ -56,6 +71,9 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint64_t* mbar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
 }
+__device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
     uint32_t done = 0;
     while (!done) {
@@ -66,11 +84,35 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
             : "memory");
     }
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA engine), completion counted in bytes on `mbar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(mbar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// 16 consecutive accumulator columns of this thread's row (lane) -> registers
+// 32 consecutive accumulator columns of this thread's row (lane) -> registers (one wait for the whole batch)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     uint32_t r[16];
     asm volatile(
@@ -114,102 +156,207 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
     return u;
 }
 
-// stage W_l (fp32 torch layout) as an fp16 natural tile with npad rows, zero padded; bias as fp32
-__device__ __forceinline__ void stage_weights(const TcP& p, const float* __restrict__ params, unsigned char* smem) {
+
+// ---- epilogue building blocks, specialised on the activation so the per-element code is branch-free ---------------
+template <int ACT>
+__device__ __forceinline__ float act_fwd_t(float v) {
+    if (ACT == NVO_ACT_RELU) return fmaxf(v, 0.f);
+    if (ACT == NVO_ACT_NONE) return v;
+    return tc_act_fwd(v, ACT);
+}
+template <int ACT>
+__device__ __forceinline__ float act_bwd_t(float a) {
+    if (ACT == NVO_ACT_RELU) return a > 0.f ? 1.f : 0.f;
+    if (ACT == NVO_ACT_NONE) return 1.f;
+    return tc_act_bwd(a, ACT);
+}
+
+// hidden layer of the forward: NC (16 | 32) accumulator columns -> + bias -> activation -> fp16 -> next layer's A tile (+ saved)
+template <int ACT, int NC>
+__device__ __forceinline__ void fwd_hidden_cols(uint32_t taddr, const float* __restrict__ sb, unsigned char* __restrict__ sAct, uint4* __restrict__ saved_tile,
+                                                int c8_0, int tid) {
+    float v[NC];
+    if (NC == 32)
+        tmem_ld32(taddr, v);
+    else
+        tmem_ld16(taddr, v);
+#pragma unroll
+    for (int q = 0; q < NC / 4; ++q) {
+        const float4 b = *reinterpret_cast<const float4*>(sb + 4 * q);  // warp-broadcast
+        v[4 * q] = act_fwd_t<ACT>(v[4 * q] + b.x);
+        v[4 * q + 1] = act_fwd_t<ACT>(v[4 * q + 1] + b.y);
+        v[4 * q + 2] = act_fwd_t<ACT>(v[4 * q + 2] + b.z);
+        v[4 * q + 3] = act_fwd_t<ACT>(v[4 * q + 3] + b.w);
+    }
+#pragma unroll
+    for (int q = 0; q < NC / 8; ++q) {
+        const uint4 u = pack8(v + q * 8);
+        *reinterpret_cast<uint4*>(sAct + (c8_0 + q) * CHUNK_B + tid * 16) = u;
+        if (saved_tile) saved_tile[(c8_0 + q) * TM + tid] = u;  // TMH: coalesced 16-byte stores
+    }
+}
+template <int ACT>
+__device__ __forceinline__ void fwd_hidden_layer(uint32_t trow, int np, const float* __restrict__ sb, unsigned char* __restrict__ sAct,
+                                                 uint4* __restrict__ saved_tile, int tid) {
+    int c = 0;
+    for (; c + 32 <= np; c += 32) fwd_hidden_cols<ACT, 32>(trow + c, sb + c, sAct, saved_tile, c >> 3, tid);
+    if (c < np) fwd_hidden_cols<ACT, 16>(trow + c, sb + c, sAct, saved_tile, c >> 3, tid);
+}
+
+// hidden layer of the backward: NC dgrad columns -> x act'(a) -> fp16 -> the next dZ tile
+template <int ACT, int NC>
+__device__ __forceinline__ void bwd_hidden_cols(uint32_t taddr, const unsigned char* __restrict__ sA, unsigned char* __restrict__ sGn, int c8_0, int tid) {
+    float v[NC];
+    if (NC == 32)
+        tmem_ld32(taddr, v);
+    else
+        tmem_ld16(taddr, v);
+#pragma unroll
+    for (int q = 0; q < NC / 8; ++q) {
+        if (ACT != NVO_ACT_NONE) {
+            const uint4 a = *reinterpret_cast<const uint4*>(sA + (c8_0 + q) * CHUNK_B + tid * 16);
+            const __half2* h = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(h[j]);
+                v[q * 8 + 2 * j] *= act_bwd_t<ACT>(f.x);
+                v[q * 8 + 2 * j + 1] *= act_bwd_t<ACT>(f.y);
+            }
+        }
+        *reinterpret_cast<uint4*>(sGn + (c8_0 + q) * CHUNK_B + tid * 16) = pack8(v + q * 8);
+    }
+}
+template <int ACT>
+__device__ __forceinline__ void bwd_hidden_layer(uint32_t trow, int kp, const unsigned char* __restrict__ sA, unsigned char* __restrict__ sGn, int tid) {
+    int c = 0;
+    for (; c + 32 <= kp; c += 32) bwd_hidden_cols<ACT, 32>(trow + c, sA, sGn, c >> 3, tid);
+    if (c < kp) bwd_hidden_cols<ACT, 16>(trow + c, sA, sGn, c >> 3, tid);
+}
+
+// ================================================================================================================
+// weight image: per layer W_l as an fp16 natural tile with npad rows (zero padded) followed by the fp32 bias [npad]
+// ================================================================================================================
+__global__ void __launch_bounds__(256) k_tc_pack(const __grid_constant__ TcP p, const float* __restrict__ params, unsigned char* __restrict__ img) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
     for (int l = 0; l < p.n_layers; ++l) {
         const int K = l == 0 ? p.in_dim : p.dims[l - 1], N = p.dims[l], kp = p.kpad[l], np = p.npad[l];
-        __half* sw = reinterpret_cast<__half*>(smem + p.sw_off[l]);
-        float* sb = reinterpret_cast<float*>(smem + p.sb_off[l]);
-        for (int e = threadIdx.x; e < np * kp; e += TM) {
+        __half* iw = reinterpret_cast<__half*>(img + p.iw_off[l]);
+        float* ib = reinterpret_cast<float*>(img + p.ib_off[l]);
+        for (int e = t; e < np * kp; e += stride) {
             const int o = e / kp, i = e - o * kp;
             const float w = (o < N && i < K) ? __ldg(params + p.w_off[l] + o * K + i) : 0.f;
-            sw[((i >> 3) * np + o) * 8 + (i & 7)] = __float2half_rn(w);
+            iw[((i >> 3) * np + o) * 8 + (i & 7)] = __float2half_rn(w);
         }
-        for (int o = threadIdx.x; o < np; o += TM) sb[o] = o < N ? __ldg(params + p.b_off[l] + o) : 0.f;
+        for (int o = t; o < np; o += stride) ib[o] = o < N ? __ldg(params + p.b_off[l] + o) : 0.f;
     }
 }
 
 // ================================================================================================================
-// forward
-// smem: [A tile 16 KB][W_l, b_l ...][mbar][tmem ptr]
+// forward.  smem: [in0 16 KB][in1 16 KB][act 16 KB][weight image][mbar_mma, mbar_w, mbar_in0, mbar_in1, tmem ptr]
 // ================================================================================================================
-__global__ void __launch_bounds__(TM) k_mlp_tc_fwd(const __grid_constant__ TcP p, int64_t n, const __half* __restrict__ x16,
-                                                   const float* __restrict__ params, const float* __restrict__ row_mask, float* __restrict__ y,
-                                                   __half* __restrict__ saved, int smem_ctrl_off) {
+#define FWD_IN0 0
+#define FWD_IN1 (8 * CHUNK_B)
+#define FWD_ACT (16 * CHUNK_B)
+#define FWD_W (24 * CHUNK_B)
+
+__global__ void __launch_bounds__(TM) k_mlp_tc_fwd(const __grid_constant__ TcP p, int64_t n, const unsigned char* __restrict__ x16,
+                                                   const unsigned char* __restrict__ wimg, const float* __restrict__ row_mask, float* __restrict__ y,
+                                                   uint4* __restrict__ saved, int smem_ctrl_off) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* sA = smem;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + smem_ctrl_off);
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + smem_ctrl_off + 8);
+    unsigned char* sAct = smem + FWD_ACT;
+    unsigned char* sW = smem + FWD_W;
+    uint64_t* mbar_mma = reinterpret_cast<uint64_t*>(smem + smem_ctrl_off);
+    uint64_t* mbar_w = mbar_mma + 1;
+    uint64_t* mbar_in = mbar_mma + 2;  // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mbar_mma + 4);
     const int tid = threadIdx.x, warp = tid >> 5;
-    stage_weights(p, params, smem);
+    const int64_t n_tiles = (n + TM - 1) / TM;
+    const uint32_t in_bytes = (uint32_t)p.k0pad * 256u;
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(tmem_ptr)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)) : "memory");
-    fence_async_smem();
+    if (tid == 0) {
+        mbar_init(mbar_mma, 1);
+        mbar_init(mbar_w, 1);
+        mbar_init(mbar_in, 1);
+        mbar_init(mbar_in + 1, 1);
+        fence_mbar_init();
+        fence_async_smem();
+        mbar_expect_tx(mbar_w, (uint32_t)p.img_bytes);
+        bulk_g2s(sW, wimg, (uint32_t)p.img_bytes, mbar_w);
+        mbar_expect_tx(mbar_in, in_bytes);
+        bulk_g2s(smem + FWD_IN0, x16 + (int64_t)blockIdx.x * in_bytes, in_bytes, mbar_in);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    mbar_wait(mbar_w, 0);
     uint32_t phase = 0;
-    const int64_t n_tiles = (n + TM - 1) / TM;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
         const int64_t row = tile * TM + tid;
         const bool live = row < n;
-        // ---- stage the input rows (fp16, K0pad wide) as the layer-0 A operand --------------------------------
-        {
-            const int nch = p.k0pad >> 3;
-            const uint4* src = reinterpret_cast<const uint4*>(x16 + row * p.k0pad);
-            for (int c = 0; c < nch; ++c) {
-                uint4 v = make_uint4(0, 0, 0, 0);
-                if (live) v = __ldg(src + c);
-                *reinterpret_cast<uint4*>(sA + c * CHUNK_B + tid * 16) = v;
-            }
+        unsigned char* sIn = smem + (buf ? FWD_IN1 : FWD_IN0);
+        // prefetch the next tile's input: the other buffer was last read by layer-0 MMAs of the previous tile (completed)
+        if (tid == 0 && tile + gridDim.x < n_tiles) {
+            mbar_expect_tx(mbar_in + (buf ^ 1), in_bytes);
+            bulk_g2s(smem + (buf ? FWD_IN0 : FWD_IN1), x16 + (tile + gridDim.x) * in_bytes, in_bytes, mbar_in + (buf ^ 1));
         }
-        fence_async_smem();
-        __syncthreads();
+        mbar_wait(mbar_in + buf, (uint32_t)((it >> 1) & 1));
         for (int l = 0; l < p.n_layers; ++l) {
             const int kp = p.kpad[l], np = p.npad[l];
             if (tid == 0) {
                 tc_fence_after();
                 const uint32_t idesc = umma_idesc(TM, np, 0, 0);
-                const uint32_t a0 = smem_u32(sA), b0 = smem_u32(smem + p.sw_off[l]);
+                const uint32_t a0 = smem_u32(l == 0 ? sIn : sAct), b0 = smem_u32(sW + p.iw_off[l]);
                 for (int k = 0; k < (kp >> 4); ++k)
                     umma_f16(tmem, umma_desc(a0 + k * 2 * CHUNK_B, CHUNK_B, 128), umma_desc(b0 + k * 2 * np * 16, np * 16, 128), idesc, k > 0);
-                umma_commit(mbar);
+                umma_commit(mbar_mma);
             }
-            mbar_wait(mbar, phase);
+            mbar_wait(mbar_mma, phase);
             phase ^= 1;
             tc_fence_after();
-            const float* sb = reinterpret_cast<const float*>(smem + p.sb_off[l]);
+            const float* sb = reinterpret_cast<const float*>(sW + p.ib_off[l]);
             const bool last = l == p.n_layers - 1;
             const int act = p.acts[l];
-            for (int c16 = 0; c16 < np; c16 += 16) {
-                float v[16];
-                tmem_ld16(trow + c16, v);
+            if (!last) {
+                uint4* saved_tile = saved ? saved + (tile * p.saved_chunks + p.saved_chunk_off[l]) * TM : nullptr;
+                if (act == NVO_ACT_RELU)
+                    fwd_hidden_layer<NVO_ACT_RELU>(trow, np, sb, sAct, saved_tile, tid);
+                else if (act == NVO_ACT_NONE)
+                    fwd_hidden_layer<NVO_ACT_NONE>(trow, np, sb, sAct, saved_tile, tid);
+                else if (act == NVO_ACT_SIGMOID)
+                    fwd_hidden_layer<NVO_ACT_SIGMOID>(trow, np, sb, sAct, saved_tile, tid);
+                else if (act == NVO_ACT_TANH)
+                    fwd_hidden_layer<NVO_ACT_TANH>(trow, np, sb, sAct, saved_tile, tid);
+                else
+                    fwd_hidden_layer<NVO_ACT_EXP>(trow, np, sb, sAct, saved_tile, tid);
+            } else {
+                const int N = p.dims[l];
+                const float m = (live && row_mask) ? __ldg(row_mask + row) : 1.f;
+                for (int c16 = 0; c16 < N; c16 += 16) {
+                    float v[16];
+                    tmem_ld16(trow + c16, v);
+                    if (live) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = tc_act_fwd(v[j] + sb[c16 + j], act);
-                if (!last) {
-                    const uint4 lo = pack8(v), hi = pack8(v + 8);
-                    const int c8 = c16 >> 3;
-                    *reinterpret_cast<uint4*>(sA + c8 * CHUNK_B + tid * 16) = lo;
-                    *reinterpret_cast<uint4*>(sA + (c8 + 1) * CHUNK_B + tid * 16) = hi;
-                    if (saved) {  // tile-major natural layout: fully coalesced 16-byte stores
-                        uint4* dst = reinterpret_cast<uint4*>(saved) + ((tile * p.saved_chunks + p.saved_chunk_off[l] + c8) * TM + tid);
-                        dst[0] = lo;
-                        dst[TM] = hi;
+                        for (int j = 0; j < 16; ++j) v[j] = tc_act_fwd(v[j] + sb[c16 + j], act) * m;
+                        float* dst = y + row * N + c16;
+                        if (N - c16 >= 16 && (N & 3) == 0) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (c16 + j < N) dst[j] = v[j];
+                        }
                     }
-                } else if (live) {
-                    const float m = row_mask ? __ldg(row_mask + row) : 1.f;
-                    const int N = p.dims[l];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c16 + j < N) y[row * N + c16 + j] = v[j] * m;
                 }
             }
-            // the next MMA (next layer or next tile) overwrites TMEM and reads the freshly written A tile
+            // the next MMA (next layer or next tile) overwrites TMEM and reads the freshly written activation tile
             tc_fence_before();
             fence_async_smem();
             __syncthreads();
@@ -222,7 +369,8 @@ __global__ void __launch_bounds__(TM) k_mlp_tc_fwd(const __grid_constant__ TcP p
 
 // ================================================================================================================
 // backward
-// smem: [G tile 16 KB][A tile 20 KB (8 chunks + ones chunk + zero chunk)][W_l, b_l ...][mbar][tmem ptr]
+// smem: [G0 16 KB][G1 16 KB][stage0][stage1][weight image][mbar_mma, mbar_w, mbar_st0, mbar_st1, tmem ptr]
+//   stage = for every layer l: its input tile (kpad_l/8 chunks) + ones chunk + zero chunk (the bias-gradient columns)
 // TMEM (512 cols): [0,64) dgrad accumulator, [64 + 80*l, ...) dW_l (+ db_l in column kpad_l)
 // ================================================================================================================
 __global__ void k_absmax_scale(int64_t count, const float* __restrict__ dy, float* __restrict__ scale_bits) {
@@ -241,25 +389,58 @@ __device__ __forceinline__ float grad_scale_from_max(float mx) {
     return ldexpf(1.f, 8 - e);      // max|dy| * scale in [128, 256)
 }
 
-__global__ void __launch_bounds__(TM) k_mlp_tc_bwd(const __grid_constant__ TcP p, int64_t n, const __half* __restrict__ x16,
-                                                   const float* __restrict__ params, const __half* __restrict__ saved, const float* __restrict__ y,
-                                                   const float* __restrict__ row_mask, const float* __restrict__ dy, const float* __restrict__ dy_absmax,
-                                                   float* __restrict__ dx, float* __restrict__ dparams, int smem_w_off, int smem_ctrl_off) {
+#define BWD_G0 0
+#define BWD_G1 (8 * CHUNK_B)
+#define BWD_STAGE (16 * CHUNK_B)
+
+__device__ __forceinline__ void bwd_prefetch(const TcP& p, unsigned char* stage, int64_t tile, const unsigned char* __restrict__ x16,
+                                             const unsigned char* __restrict__ saved, uint64_t* mbar) {
+    uint32_t total = (uint32_t)p.k0pad * 256u;
+    for (int l = 1; l < p.n_layers; ++l) total += (uint32_t)p.kpad[l] * 256u;
+    mbar_expect_tx(mbar, total);
+    bulk_g2s(stage + p.a_off[0], x16 + tile * ((int64_t)p.k0pad * 256), (uint32_t)p.k0pad * 256u, mbar);
+    for (int l = 1; l < p.n_layers; ++l)
+        bulk_g2s(stage + p.a_off[l], saved + (tile * p.saved_chunks + p.saved_chunk_off[l - 1]) * (int64_t)CHUNK_B, (uint32_t)p.kpad[l] * 256u, mbar);
+}
+
+__global__ void __launch_bounds__(TM) k_mlp_tc_bwd(const __grid_constant__ TcP p, int64_t n, const unsigned char* __restrict__ x16,
+                                                   const unsigned char* __restrict__ wimg, const unsigned char* __restrict__ saved,
+                                                   const float* __restrict__ y, const float* __restrict__ row_mask, const float* __restrict__ dy,
+                                                   const float* __restrict__ dy_absmax, float* __restrict__ dx, float* __restrict__ dparams, int smem_w_off,
+                                                   int smem_ctrl_off) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* sG = smem;
-    unsigned char* sA = smem + 8 * CHUNK_B;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + smem_ctrl_off);
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + smem_ctrl_off + 8);
+    unsigned char* sW = smem + smem_w_off;
+    uint64_t* mbar_mma = reinterpret_cast<uint64_t*>(smem + smem_ctrl_off);
+    uint64_t* mbar_w = mbar_mma + 1;
+    uint64_t* mbar_st = mbar_mma + 2;  // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mbar_mma + 4);
     const int tid = threadIdx.x, warp = tid >> 5;
-    stage_weights(p, params, smem);
-    // zero the G / A tiles once: padded chunks must hold finite values (they feed unused accumulator rows/cols)
-    for (int e = tid; e < (18 * CHUNK_B) / 16; e += TM) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0, 0, 0, 0);
+    const int64_t n_tiles = (n + TM - 1) / TM;
+    // zero both dZ buffers and both stages once: padded chunks must hold finite values (they feed unused accumulator rows /
+    // columns), then write the constant ones / zero chunks behind every layer's input tile
+    for (int e = tid; e < (BWD_STAGE + 2 * p.stage_bytes) / 16; e += TM) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    for (int s = 0; s < 2; ++s)
+        for (int l = 0; l < p.n_layers; ++l)  // ones chunk: feature kpad_l == 1.0 for every row -> dW column kpad_l accumulates sum_s dZ = db
+            *reinterpret_cast<uint4*>(smem + BWD_STAGE + s * p.stage_bytes + p.a_off[l] + (p.kpad[l] >> 3) * CHUNK_B + tid * 16) =
+                make_uint4(0x00003C00u, 0, 0, 0);
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)) : "memory");
-    fence_async_smem();
+    fence_async_smem();  // generic-proxy initialisation above ordered before the async-proxy (bulk copy / MMA) accesses
+    __syncthreads();
+    if (tid == 0) {
+        mbar_init(mbar_mma, 1);
+        mbar_init(mbar_w, 1);
+        mbar_init(mbar_st, 1);
+        mbar_init(mbar_st + 1, 1);
+        fence_mbar_init();
+        fence_async_smem();
+        mbar_expect_tx(mbar_w, (uint32_t)p.img_bytes);
+        bulk_g2s(sW, wimg, (uint32_t)p.img_bytes, mbar_w);
+        if ((int64_t)blockIdx.x < n_tiles) bwd_prefetch(p, smem + BWD_STAGE, blockIdx.x, x16, saved, mbar_st);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -267,15 +448,22 @@ __global__ void __launch_bounds__(TM) k_mlp_tc_bwd(const __grid_constant__ TcP p
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
     const float gscale = grad_scale_from_max(__ldg(dy_absmax));
     const float inv_gscale = 1.f / gscale;
+    mbar_wait(mbar_w, 0);
     uint32_t phase = 0;
     const int last = p.n_layers - 1;
-    const int64_t n_tiles = (n + TM - 1) / TM;
-    int tiles_done = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tiles_done) {
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
         const int64_t row = tile * TM + tid;
         const bool live = row < n;
-        // ---- dZ of the last layer: dy * mask * act'(y) * scale -> fp16 G tile ----------------------------------
+        unsigned char* stage = smem + BWD_STAGE + buf * p.stage_bytes;
+        // every MMA of the previous tile has completed (its layer-0 commit sits behind the wgrad MMAs and was waited on), so
+        // the other stage and both dZ buffers are free: prefetch the next tile's activations while this one computes
+        if (tid == 0 && tile + gridDim.x < n_tiles)
+            bwd_prefetch(p, smem + BWD_STAGE + (buf ^ 1) * p.stage_bytes, tile + gridDim.x, x16, saved, mbar_st + (buf ^ 1));
+        // ---- dZ of the last layer: dy * mask * act'(y) * scale -> fp16 G tile (buffer parity of `last`) -------------
         {
+            unsigned char* sG = smem + ((last & 1) ? BWD_G1 : BWD_G0);
             const int N = p.dims[last], np = p.npad[last], act = p.acts[last];
             const float m = (live && row_mask) ? __ldg(row_mask + row) : 1.f;
             for (int c8 = 0; c8 < (np >> 3); ++c8) {
@@ -286,92 +474,84 @@ __global__ void __launch_bounds__(TM) k_mlp_tc_bwd(const __grid_constant__ TcP p
                     float g = 0.f;
                     if (live && o < N) {
                         g = __ldg(dy + row * N + o) * m;
-                        if (act != NVO_ACT_NONE) {
-                            float a = __ldg(y + row * N + o);
-                            g *= tc_act_bwd(a, act);
-                        }
+                        if (act != NVO_ACT_NONE) g *= tc_act_bwd(__ldg(y + row * N + o), act);
                     }
                     v[j] = g * gscale;
                 }
                 *reinterpret_cast<uint4*>(sG + c8 * CHUNK_B + tid * 16) = pack8(v);
             }
         }
+        mbar_wait(mbar_st + buf, (uint32_t)((it >> 1) & 1));  // this tile's activations have landed
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
         for (int l = last; l >= 0; --l) {
             const int kp = p.kpad[l], np = p.npad[l];
-            // ---- stage the layer's input activations A_{l-1} (+ ones / zero chunks for the bias gradient) -------
-            {
-                const int nch = kp >> 3;
-                if (l == 0) {
-                    const uint4* src = reinterpret_cast<const uint4*>(x16 + row * p.k0pad);
-                    for (int c = 0; c < nch; ++c) {
-                        uint4 v = make_uint4(0, 0, 0, 0);
-                        if (live) v = __ldg(src + c);
-                        *reinterpret_cast<uint4*>(sA + c * CHUNK_B + tid * 16) = v;
-                    }
-                } else {
-                    const uint4* src = reinterpret_cast<const uint4*>(saved) + ((tile * p.saved_chunks + p.saved_chunk_off[l - 1]) * TM + tid);
-                    for (int c = 0; c < nch; ++c) {
-                        uint4 v = __ldg(src + c * TM);
-                        if (!live) v = make_uint4(0, 0, 0, 0);
-                        *reinterpret_cast<uint4*>(sA + c * CHUNK_B + tid * 16) = v;
-                    }
-                }
-                // ones chunk: feature kp == 1.0 for every row  ->  dW column kp accumulates sum_s dZ = db
-                *reinterpret_cast<uint4*>(sA + nch * CHUNK_B + tid * 16) = make_uint4(0x00003C00u, 0, 0, 0);
-                *reinterpret_cast<uint4*>(sA + (nch + 1) * CHUNK_B + tid * 16) = make_uint4(0, 0, 0, 0);
-            }
-            fence_async_smem();
-            tc_fence_before();
-            __syncthreads();
+            unsigned char* sG = smem + ((l & 1) ? BWD_G1 : BWD_G0);    // dZ_l
+            unsigned char* sGn = smem + ((l & 1) ? BWD_G0 : BWD_G1);   // dZ_{l-1}
+            unsigned char* sA = stage + p.a_off[l];                    // input activations of layer l (+ ones / zero chunks)
             const bool need_dgrad = l > 0 || dx != nullptr;
             if (tid == 0) {
                 tc_fence_after();
-                const uint32_t g0 = smem_u32(sG), a0 = smem_u32(sA), w0 = smem_u32(smem + p.sw_off[l]);
-                if (dparams) {
-                    // wgrad: D[feature o (M=128 padded)][input i (N = kp+16)] += sum_s dZ[s][o] * A[s][i]; both operands MN-major, K = samples
-                    const uint32_t idesc = umma_idesc(TM, kp + 16, 1, 1);
-                    const uint32_t dcol = tmem + 64 + DW_COLS * l;
-                    for (int k = 0; k < TM / 16; ++k)
-                        umma_f16(dcol, umma_desc(g0 + k * 256, 128, CHUNK_B), umma_desc(a0 + k * 256, 128, CHUNK_B), idesc, (tiles_done > 0 || k > 0) ? 1u : 0u);
-                }
+                const uint32_t g0 = smem_u32(sG), a0 = smem_u32(sA), w0 = smem_u32(sW + p.iw_off[l]);
                 if (need_dgrad) {
                     // dgrad: D[s][i] = sum_o dZ[s][o] * W[o][i]; A = G tile K-major, B = W tile MN-major
                     const uint32_t idesc = umma_idesc(TM, kp, 0, 1);
                     for (int k = 0; k < (np >> 4); ++k)
                         umma_f16(tmem, umma_desc(g0 + k * 2 * CHUNK_B, CHUNK_B, 128), umma_desc(w0 + k * 256, 128, np * 16), idesc, k > 0);
+                    if (l > 0) umma_commit(mbar_mma);  // the epilogue below only needs the dgrad accumulator
                 }
-                umma_commit(mbar);
+                if (dparams) {
+                    // wgrad: D[feature o (M=128 padded)][input i (N = kp+16)] += sum_s dZ[s][o] * A[s][i]; both operands MN-major, K = samples.
+                    // Issued behind the dgrad commit: runs on the tensor pipe while the warps do the dgrad epilogue.
+                    const uint32_t idesc = umma_idesc(TM, kp + 16, 1, 1);
+                    const uint32_t dcol = tmem + 64 + DW_COLS * l;
+                    for (int k = 0; k < TM / 16; ++k)
+                        umma_f16(dcol, umma_desc(g0 + k * 256, 128, CHUNK_B), umma_desc(a0 + k * 256, 128, CHUNK_B), idesc, (it > 0 || k > 0) ? 1u : 0u);
+                }
+                if (l == 0) umma_commit(mbar_mma);  // layer 0: the commit covers the wgrad MMAs too => the tile is fully retired
             }
-            mbar_wait(mbar, phase);
+            mbar_wait(mbar_mma, phase);
             phase ^= 1;
             tc_fence_after();
             if (need_dgrad) {
                 const int K = l == 0 ? p.in_dim : p.dims[l - 1];
-                for (int c16 = 0; c16 < kp; c16 += 16) {
-                    float v[16];
-                    tmem_ld16(trow + c16, v);
-                    if (l > 0) {
-                        // dZ_{l-1} = dA_{l-1} * act'(a_{l-1}); a_{l-1} is this row's entry of the A tile
-                        const int act = p.acts[l - 1];
-                        const int c8 = c16 >> 3;
-                        const uint4 a_lo = *reinterpret_cast<const uint4*>(sA + c8 * CHUNK_B + tid * 16);
-                        const uint4 a_hi = *reinterpret_cast<const uint4*>(sA + (c8 + 1) * CHUNK_B + tid * 16);
-                        const __half2* h_lo = reinterpret_cast<const __half2*>(&a_lo);
-                        const __half2* h_hi = reinterpret_cast<const __half2*>(&a_hi);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float2 f0 = __half22float2(h_lo[j]), f1 = __half22float2(h_hi[j]);
-                            v[2 * j] *= tc_act_bwd(f0.x, act);
-                            v[2 * j + 1] *= tc_act_bwd(f0.y, act);
-                            v[8 + 2 * j] *= tc_act_bwd(f1.x, act);
-                            v[8 + 2 * j + 1] *= tc_act_bwd(f1.y, act);
+                if (l > 0) {
+                    // dZ_{l-1} = dA_{l-1} * act'(a_{l-1}); a_{l-1} is this row's entry of layer l's input tile
+                    const int act = p.acts[l - 1];
+                    if (act == NVO_ACT_RELU)
+                        bwd_hidden_layer<NVO_ACT_RELU>(trow, kp, sA, sGn, tid);
+                    else if (act == NVO_ACT_NONE)
+                        bwd_hidden_layer<NVO_ACT_NONE>(trow, kp, sA, sGn, tid);
+                    else if (act == NVO_ACT_SIGMOID)
+                        bwd_hidden_layer<NVO_ACT_SIGMOID>(trow, kp, sA, sGn, tid);
+                    else if (act == NVO_ACT_TANH)
+                        bwd_hidden_layer<NVO_ACT_TANH>(trow, kp, sA, sGn, tid);
+                    else
+                        bwd_hidden_layer<NVO_ACT_EXP>(trow, kp, sA, sGn, tid);
+                } else {
+                    for (int c32 = 0; c32 < kp; c32 += 32) {
+                        float v[32];
+                        if (kp - c32 >= 32) {
+                            tmem_ld32(trow + c32, v);
+                        } else {
+                            tmem_ld16(trow + c32, v);
                         }
-                        *reinterpret_cast<uint4*>(sG + c8 * CHUNK_B + tid * 16) = pack8(v);
-                        *reinterpret_cast<uint4*>(sG + (c8 + 1) * CHUNK_B + tid * 16) = pack8(v + 8);
-                    } else if (live) {
+                        const int ncol = min(32, kp - c32);
+                        if (live) {
+                            float* dst = dx + row * K + c32;
+                            if ((K & 3) == 0 && K - c32 >= ncol) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (c16 + j < K) dx[row * K + c16 + j] = v[j] * inv_gscale;
+                                for (int q = 0; q < 8; ++q)
+                                    if (q * 4 < ncol)
+                                        reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q] * inv_gscale, v[4 * q + 1] * inv_gscale,
+                                                                                        v[4 * q + 2] * inv_gscale, v[4 * q + 3] * inv_gscale);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (j < ncol && c32 + j < K) dst[j] = v[j] * inv_gscale;
+                            }
+                        }
                     }
                 }
             }
@@ -381,7 +561,7 @@ __global__ void __launch_bounds__(TM) k_mlp_tc_bwd(const __grid_constant__ TcP p
         }
     }
     // ---- flush dW / db: thread o holds row o of every layer's accumulator ------------------------------------------
-    if (dparams && tiles_done > 0) {
+    if (dparams && it > 0) {
         tc_fence_after();
         for (int l = 0; l < p.n_layers; ++l) {
             const int K = l == 0 ? p.in_dim : p.dims[l - 1], N = p.dims[l], kp = p.kpad[l];
@@ -406,24 +586,34 @@ __global__ void __launch_bounds__(TM) k_mlp_tc_bwd(const __grid_constant__ TcP p
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
-// fp32 [n, in_dim] -> fp16 [n, kpad] zero padded (generic entry for tcnn.Network inputs)
-__global__ void __launch_bounds__(256) k_cast_pad(int64_t n, int in_dim, int kpad, const float* __restrict__ x, __half* __restrict__ out) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n * kpad) return;
-    const int64_t r = t / kpad;
-    const int c = (int)(t - r * kpad);
-    out[t] = __float2half_rn(c < in_dim ? __ldg(x + r * in_dim + c) : 0.f);
+// fp32 [n, in_dim] row-major -> fp16 TMH tiles [ceil(n/128)][kpad/8][128][8], zero padded (columns >= in_dim, rows >= n)
+__global__ void __launch_bounds__(256) k_cast_tmh(int64_t n, int in_dim, int kpad, const float* __restrict__ x, uint4* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one (tile, chunk, row) item per thread
+    const int nch = kpad >> 3;
+    const int64_t n_tiles = (n + TM - 1) / TM;
+    if (t >= n_tiles * nch * TM) return;
+    const int r = (int)(t & (TM - 1));
+    const int64_t tc = t >> 7;
+    const int c = (int)(tc % nch);
+    const int64_t row = (tc / nch) * TM + r;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int col = c * 8 + j;
+        v[j] = (row < n && col < in_dim) ? __ldg(x + row * in_dim + col) : 0.f;
+    }
+    out[t] = pack8(v);
 }
 
 // ================================================================================================================
-static int make_tc_params(const nvo_mlp_desc* d, TcP* p, int base_off, int* w_region_end) {
+static int make_tc_params(const nvo_mlp_desc* d, TcP* p) {
     NVO_CHECK(d != nullptr, "mlp_tc: null descriptor");
     NVO_CHECK(d->n_layers >= 1 && d->n_layers <= TC_MAX_LAYERS, "mlp_tc: n_layers=%d out of range [1,%d]", d->n_layers, TC_MAX_LAYERS);
     NVO_CHECK(d->in_dim >= 1 && d->in_dim <= MAXW, "mlp_tc: in_dim=%d out of range [1,%d]", d->in_dim, MAXW);
     p->n_layers = d->n_layers;
     p->in_dim = d->in_dim;
     p->k0pad = (d->in_dim + 15) & ~15;
-    int off = 0, soff = base_off, chunks = 0, in = d->in_dim;
+    int off = 0, ioff = 0, chunks = 0, in = d->in_dim, aoff = 0;
     for (int l = 0; l < TC_MAX_LAYERS; ++l) {
         if (l < d->n_layers) {
             NVO_CHECK(d->dims[l] >= 1 && d->dims[l] <= MAXW, "mlp_tc: layer %d width %d out of range [1,%d]", l, d->dims[l], MAXW);
@@ -436,69 +626,86 @@ static int make_tc_params(const nvo_mlp_desc* d, TcP* p, int base_off, int* w_re
             off += d->dims[l] * in;
             p->b_off[l] = off;
             off += d->dims[l];
-            p->sw_off[l] = soff;
-            soff += p->npad[l] * p->kpad[l] * 2;
-            p->sb_off[l] = soff;
-            soff += p->npad[l] * 4;
+            p->iw_off[l] = ioff;
+            ioff += p->npad[l] * p->kpad[l] * 2;
+            p->ib_off[l] = ioff;
+            ioff += p->npad[l] * 4;
             p->saved_chunk_off[l] = chunks;
             if (l < d->n_layers - 1) chunks += p->npad[l] >> 3;
+            p->a_off[l] = aoff;
+            aoff += ((p->kpad[l] >> 3) + 2) * CHUNK_B;
             in = d->dims[l];
         } else {
-            p->dims[l] = p->acts[l] = p->npad[l] = p->kpad[l] = p->w_off[l] = p->b_off[l] = p->sw_off[l] = p->sb_off[l] = p->saved_chunk_off[l] = 0;
+            p->dims[l] = p->acts[l] = p->npad[l] = p->kpad[l] = p->w_off[l] = p->b_off[l] = p->iw_off[l] = p->ib_off[l] = p->saved_chunk_off[l] = p->a_off[l] = 0;
         }
     }
     p->n_params = off;
     p->saved_chunks = chunks;
-    *w_region_end = (soff + 15) & ~15;
+    p->img_bytes = (ioff + 15) & ~15;
+    p->stage_bytes = aoff;
     return 0;
 }
 
 extern "C" int64_t nvo_mlp_tc_saved_bytes(const nvo_mlp_desc* d, int64_t n) {
     TcP p;
-    int e;
-    if (make_tc_params(d, &p, 0, &e)) return -1;
+    if (make_tc_params(d, &p)) return -1;
     const int64_t tiles = (n + TM - 1) / TM;
     return tiles * p.saved_chunks * CHUNK_B;
+}
+
+extern "C" int64_t nvo_mlp_tc_wimage_bytes(const nvo_mlp_desc* d) {
+    TcP p;
+    if (make_tc_params(d, &p)) return -1;
+    return p.img_bytes;
 }
 
 extern "C" int nvo_mlp_tc_in_pad(const nvo_mlp_desc* d) { return d ? ((d->in_dim + 15) & ~15) : -1; }
 
 extern "C" int nvo_cast_pad_f16(void* stream, int64_t n, int32_t in_dim, int32_t kpad, const float* x, void* out) {
-    NVO_CHECK(n >= 0 && in_dim >= 1 && kpad >= in_dim, "cast_pad_f16: bad shape");
+    NVO_CHECK(n >= 0 && in_dim >= 1 && kpad >= in_dim && (kpad & 7) == 0, "cast_pad_f16: bad shape");
     if (n == 0) return 0;
     NVO_CHECK(x && out, "cast_pad_f16: null pointer");
-    k_cast_pad<<<nvo_blocks(n * kpad, 256), 256, 0, (cudaStream_t)stream>>>(n, in_dim, kpad, x, (__half*)out);
+    const int64_t items = ((n + TM - 1) / TM) * (kpad >> 3) * TM;
+    k_cast_tmh<<<nvo_blocks(items, 256), 256, 0, (cudaStream_t)stream>>>(n, in_dim, kpad, x, (uint4*)out);
     NVO_CUDA_LAUNCH_CHECK("cast_pad_f16");
     return 0;
 }
 
-extern "C" int nvo_mlp_tc_forward(const nvo_mlp_desc* d, void* stream, int64_t n, const void* x16, const float* params, const float* row_mask, float* y,
+extern "C" int nvo_mlp_tc_pack_weights(const nvo_mlp_desc* d, void* stream, const float* params, void* wimage) {
+    TcP p;
+    if (int e = make_tc_params(d, &p)) return e;
+    NVO_CHECK(params && wimage, "mlp_tc_pack_weights: null pointer");
+    k_tc_pack<<<8, 256, 0, (cudaStream_t)stream>>>(p, params, (unsigned char*)wimage);
+    NVO_CUDA_LAUNCH_CHECK("mlp_tc_pack_weights");
+    return 0;
+}
+
+extern "C" int nvo_mlp_tc_forward(const nvo_mlp_desc* d, void* stream, int64_t n, const void* x16, const void* wimage, const float* row_mask, float* y,
                                   void* saved) {
     TcP p;
-    int wend;
-    if (int e = make_tc_params(d, &p, 8 * CHUNK_B, &wend)) return e;
+    if (int e = make_tc_params(d, &p)) return e;
     NVO_CHECK(n >= 0, "mlp_tc_forward: negative batch");
     if (n == 0) return 0;
-    NVO_CHECK(x16 && params && y, "mlp_tc_forward: null pointer");
-    const int ctrl = wend;
-    const size_t smem = (size_t)ctrl + 16;
+    NVO_CHECK(x16 && wimage && y, "mlp_tc_forward: null pointer");
+    const int ctrl = FWD_W + p.img_bytes;
+    const size_t smem = (size_t)ctrl + 48;
     cudaError_t e = cudaFuncSetAttribute(k_mlp_tc_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     NVO_CHECK(e == cudaSuccess, "mlp_tc_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     const int64_t tiles = (n + TM - 1) / TM;
-    const unsigned int grid = (unsigned int)min(tiles, (int64_t)nvo_sm_count() * 4);
-    k_mlp_tc_fwd<<<grid, TM, smem, (cudaStream_t)stream>>>(p, n, (const __half*)x16, params, row_mask, y, (__half*)saved, ctrl);
+    const int ctas_per_sm = (int)max((size_t)1, min((size_t)4, (size_t)(227 * 1024) / (smem + 1024)));
+    const unsigned int grid = (unsigned int)min(tiles, (int64_t)nvo_sm_count() * ctas_per_sm);
+    k_mlp_tc_fwd<<<grid, TM, smem, (cudaStream_t)stream>>>(p, n, (const unsigned char*)x16, (const unsigned char*)wimage, row_mask, y, (uint4*)saved, ctrl);
     NVO_CUDA_LAUNCH_CHECK("mlp_tc_forward");
     return 0;
 }
 
-extern "C" int nvo_mlp_tc_backward(const nvo_mlp_desc* d, void* stream, int64_t n, const void* x16, const float* params, const void* saved, const float* y,
+extern "C" int nvo_mlp_tc_backward(const nvo_mlp_desc* d, void* stream, int64_t n, const void* x16, const void* wimage, const void* saved, const float* y,
                                    const float* row_mask, const float* dy, float* scratch, float* dx, float* dparams) {
     TcP p;
-    int wend;
-    if (int e = make_tc_params(d, &p, 18 * CHUNK_B, &wend)) return e;
+    if (int e = make_tc_params(d, &p)) return e;
     NVO_CHECK(n >= 0, "mlp_tc_backward: negative batch");
     if (n == 0) return 0;
-    NVO_CHECK(x16 && params && dy && scratch, "mlp_tc_backward: null pointer");
+    NVO_CHECK(x16 && wimage && dy && scratch, "mlp_tc_backward: null pointer");
     NVO_CHECK(p.n_layers == 1 || saved, "mlp_tc_backward: saved activations required for multi-layer networks");
     NVO_CHECK(p.acts[p.n_layers - 1] == NVO_ACT_NONE || y, "mlp_tc_backward: y required for an output activation");
     cudaStream_t st = (cudaStream_t)stream;
@@ -507,13 +714,16 @@ extern "C" int nvo_mlp_tc_backward(const nvo_mlp_desc* d, void* stream, int64_t 
     const int64_t count = n * p.dims[p.n_layers - 1];
     k_absmax_scale<<<(unsigned int)min((int64_t)nvo_sm_count() * 4, (count + 255) / 256), 256, 0, st>>>(count, dy, scratch);
     NVO_CUDA_LAUNCH_CHECK("mlp_tc_backward(absmax)");
-    const int ctrl = wend;
-    const size_t smem = (size_t)ctrl + 16;
+    const int w_off = BWD_STAGE + 2 * p.stage_bytes;
+    const int ctrl = w_off + p.img_bytes;
+    const size_t smem = (size_t)ctrl + 48;
+    NVO_CHECK(smem <= 227 * 1024, "mlp_tc_backward: network needs %zu B of shared memory (> 227 KB)", smem);
     e = cudaFuncSetAttribute(k_mlp_tc_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     NVO_CHECK(e == cudaSuccess, "mlp_tc_backward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     const int64_t tiles = (n + TM - 1) / TM;
     const unsigned int grid = (unsigned int)min(tiles, (int64_t)nvo_sm_count());
-    k_mlp_tc_bwd<<<grid, TM, smem, st>>>(p, n, (const __half*)x16, params, (const __half*)saved, y, row_mask, dy, scratch, dx, dparams, 18 * CHUNK_B, ctrl);
+    k_mlp_tc_bwd<<<grid, TM, smem, st>>>(p, n, (const unsigned char*)x16, (const unsigned char*)wimage, (const unsigned char*)saved, y, row_mask, dy, scratch,
+                                         dx, dparams, w_off, ctrl);
     NVO_CUDA_LAUNCH_CHECK("mlp_tc_backward");
     return 0;
 }

@@ -168,28 +168,30 @@ class NerfactoField(Field):
                             layer_width=hidden_dim_color, out_dim=3, activation=nn.ReLU(), out_activation=nn.Sigmoid())
         self._cache = None
 
-    def _remember(self, x, h, shape) -> None:
+    def _remember(self, x, h, shape, tc=None) -> None:
         """State get_normals() needs (base_field.py:80-101 keeps _sample_locations / _density_before_activation).  Stored
         DETACHED: normals are first-order and graph-free, and holding autograd nodes across steps would pin the previous
-        step's graph (and its stream) — which breaks CUDA-graph capture of the next step."""
-        self._cache = {"x": x.detach(), "shape": tuple(shape)}
+        step's graph (and its stream) — which breaks CUDA-graph capture of the next step.  `tc` = the tensor-core forward's
+        internal buffers (features, weight image, saved activations), reused by the input-gradient pass."""
+        self._cache = {"x": x.detach(), "shape": tuple(shape), "tc": tc}
         self._sample_locations = self._cache["x"].view(*shape, 3)
         self._density_before_activation = h.detach()[:, :1].view(*shape, 1)
 
     # -- density -----------------------------------------------------------------------------------------
-    def _base(self, x: torch.Tensor) -> torch.Tensor:
+    def _base(self, x: torch.Tensor):
         """mlp_base(hash_grid(x)) -> h [n,16]: raw density + geo features (nerfacto_field.py:213-215)."""
         enc, mlp = self.mlp_base.encoder, self.mlp_base.mlp
         if self.precision == "fp16":
             mlp._repack()
-            return ops.grid_mlp_tc(x, enc.hash_table, enc.spec, mlp.spec, mlp._flat_param_list())
-        return mlp(enc(x))
+            tc = {}
+            return ops.grid_mlp_tc(x, enc.hash_table, enc.spec, mlp.spec, mlp._flat_param_list(), cache=tc), tc
+        return mlp(enc(x)), None
 
     def _density_from_positions(self, positions: torch.Tensor):
         shape = positions.shape[:-1]
         x, sel = ops.contract_normalize(positions)
-        h = self._base(x)
-        self._remember(x, h, shape)
+        h, tc = self._base(x)
+        self._remember(x, h, shape, tc)
         density = (ops.trunc_exp(h[:, 0]) * sel).view(*shape, 1)
         return density, h[:, 1:].view(*shape, self.geo_feat_dim)
 
@@ -200,17 +202,16 @@ class NerfactoField(Field):
         with torch.no_grad():
             enc, mlp = self.mlp_base.encoder, self.mlp_base.mlp
             mlp._repack()
-            flat = ops.flat_alias([p.data for p in mlp._flat_param_list()])
             x = c["x"]
             n = x.shape[0]
             table = enc.hash_table.detach()
             onehot = torch.zeros((n, mlp.out_dim), dtype=torch.float32, device=x.device)
             onehot[:, 0] = 1.0
             if self.precision == "fp16":
-                feat = ops.grid_forward(x, table, enc.spec, torch.float16)
-                y, saved = ops.mlp_tc_forward(feat, flat, mlp.spec, True)
-                dfeat, _ = ops.mlp_tc_backward(feat, flat, saved, y, onehot, mlp.spec, True, False)
+                tc = c["tc"]  # forward buffers of this very evaluation: only the dgrad chain runs here
+                dfeat, _ = ops.mlp_tc_backward(tc["feat16"], tc["wimage"], tc["saved"], tc["y"], onehot, mlp.spec, True, False)
             else:
+                flat = ops.flat_alias([p.data for p in mlp._flat_param_list()])
                 feat = ops.grid_forward(x, table, enc.spec)
                 y, saved = ops.mlp_forward(feat, flat, mlp.spec, save=True)
                 dfeat, _ = ops.mlp_backward(feat, flat, saved, y, onehot, mlp.spec, need_dx=True, need_dparams=False)
@@ -229,8 +230,8 @@ class NerfactoField(Field):
         B, S = fr.shape
         positions = fr.get_positions()
         x, sel = ops.contract_normalize(positions)
-        h = self._base(x)
-        self._remember(x, h, (B, S))
+        h, tc = self._base(x)
+        self._remember(x, h, (B, S), tc)
         dirs = fr.directions.reshape(B, 3).contiguous()
         if self.training:
             cam = ray_samples.camera_indices.reshape(B).long().contiguous()

@@ -68,9 +68,18 @@ def _check_grid_inputs(x, table, spec: GridSpec):
         raise RuntimeError("grid input and hash table must be on the same device")
 
 
+def tmh_numel(n: int, kpad: int) -> int:
+    """fp16 elements of a TMH buffer ("tile-major half", the tensor-core MLP's operand layout): ceil(n/128) tiles of 128 x kpad."""
+    return (n + 127) // 128 * 128 * kpad
+
+
 def grid_forward(x, table, spec: GridSpec, out_dtype=torch.float32):
+    """out_dtype: torch.float32 / torch.float16 -> [n, 2L] row-major; "tmh" -> fp16 TMH tiles (columns padded to 16, zero filled)."""
     _check_grid_inputs(x, table, spec)
-    y = torch.empty((x.shape[0], spec.out_dim), dtype=out_dtype, device=x.device)
+    if out_dtype == "tmh":
+        y = torch.empty(tmh_numel(x.shape[0], (spec.out_dim + 15) // 16 * 16), dtype=torch.float16, device=x.device)
+    else:
+        y = torch.empty((x.shape[0], spec.out_dim), dtype=out_dtype, device=x.device)
     call("nvo_grid_forward", spec.desc(table.dtype, out_dtype), x.shape[0], x, table, y)
     return y
 
@@ -788,9 +797,9 @@ def tc_in_pad(spec: MlpSpec) -> int:
 
 
 def cast_pad_f16(x, spec: MlpSpec):
-    """fp32 [n,in_dim] -> fp16 [n,in_pad] zero padded."""
+    """fp32 [n,in_dim] row-major -> fp16 TMH tiles (in_pad columns, whole tiles, zero padded)."""
     check(x, "mlp input", torch.float32, (None, spec.in_dim))
-    out = torch.empty((x.shape[0], tc_in_pad(spec)), dtype=torch.float16, device=x.device)
+    out = torch.empty(tmh_numel(x.shape[0], tc_in_pad(spec)), dtype=torch.float16, device=x.device)
     call("nvo_cast_pad_f16", x.shape[0], spec.in_dim, tc_in_pad(spec), x, out)
     return out
 
@@ -801,28 +810,41 @@ def _tc_saved_bytes(spec: MlpSpec, n: int) -> int:
     return int(_lib.load().nvo_mlp_tc_saved_bytes(ctypes.addressof(spec.desc), n))
 
 
-def mlp_tc_forward(x16, flat, spec: MlpSpec, save: bool, row_mask=None):
-    n = x16.shape[0]
-    check(x16, "mlp_tc input", torch.float16, (n, tc_in_pad(spec)))
+def tc_pack_weights(flat, spec: MlpSpec):
+    """fp32 torch-layout parameters -> the packed fp16 weight image the tensor-core kernels bulk-copy into shared memory."""
+    import ctypes
+
     check(flat, "mlp params", torch.float32, (spec.n_params,))
+    nbytes = getattr(spec, "_wimage_bytes", None)
+    if nbytes is None:
+        nbytes = spec._wimage_bytes = int(_lib.load().nvo_mlp_tc_wimage_bytes(ctypes.addressof(spec.desc)))
+    img = torch.empty(nbytes, dtype=torch.uint8, device=flat.device)
+    call("nvo_mlp_tc_pack_weights", spec.desc, flat, img)
+    return img
+
+
+def mlp_tc_forward(x16, wimage, spec: MlpSpec, n: int, save: bool, row_mask=None):
+    """x16: TMH fp16 buffer of n rows; wimage from tc_pack_weights."""
+    check(x16, "mlp_tc input", torch.float16, (tmh_numel(n, tc_in_pad(spec)),))
+    check(wimage, "mlp_tc weight image", torch.uint8)
     if row_mask is not None:
         check(row_mask, "row_mask", torch.float32, (n,))
     y = torch.empty((n, spec.out_dim), dtype=torch.float32, device=x16.device)
     saved = None
     if save and len(spec.dims) > 1:
         saved = torch.empty(_tc_saved_bytes(spec, n), dtype=torch.uint8, device=x16.device)
-    call("nvo_mlp_tc_forward", spec.desc, n, x16, flat, row_mask, y, saved)
+    call("nvo_mlp_tc_forward", spec.desc, n, x16, wimage, row_mask, y, saved)
     return y, saved
 
 
-def mlp_tc_backward(x16, flat, saved, y, dy, spec: MlpSpec, need_dx: bool, need_dparams: bool, dflat=None, row_mask=None):
-    n = x16.shape[0]
+def mlp_tc_backward(x16, wimage, saved, y, dy, spec: MlpSpec, need_dx: bool, need_dparams: bool, dflat=None, row_mask=None):
+    n = dy.shape[0]
     check(dy, "mlp dy", torch.float32, (n, spec.out_dim))
     dx = torch.empty((n, spec.in_dim), dtype=torch.float32, device=x16.device) if need_dx else None
     if need_dparams and dflat is None:
         dflat = torch.zeros(spec.n_params, dtype=torch.float32, device=x16.device)
     scratch = torch.empty(1, dtype=torch.float32, device=x16.device)
-    call("nvo_mlp_tc_backward", spec.desc, n, x16, flat, saved, y, row_mask, dy, scratch, dx, dflat if need_dparams else None)
+    call("nvo_mlp_tc_backward", spec.desc, n, x16, wimage, saved, y, row_mask, dy, scratch, dx, dflat if need_dparams else None)
     return dx, dflat
 
 
@@ -847,20 +869,20 @@ class _MlpApplyTC(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, spec, row_mask, *params):
+        n = x.shape[0]
         x16 = cast_pad_f16(x.contiguous(), spec)
-        flat = _flat_of(params)
-        need = x.requires_grad or any(p.requires_grad for p in params)
-        y, saved = mlp_tc_forward(x16, flat, spec, need, row_mask)
-        ctx.save_for_backward(x16, flat, saved, y, row_mask)
+        wimage = tc_pack_weights(_flat_of(params), spec)
+        y, saved = mlp_tc_forward(x16, wimage, spec, n, any(ctx.needs_input_grad), row_mask)
+        ctx.save_for_backward(x16, wimage, saved, y, row_mask)
         ctx.spec, ctx.n_tensors = spec, len(params)
         ctx.main_grad = getattr(params[0], "_nvo_main_grad", None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x16, flat, saved, y, row_mask = ctx.saved_tensors
+        x16, wimage, saved, y, row_mask = ctx.saved_tensors
         need_dx, need_dp = ctx.needs_input_grad[0], any(ctx.needs_input_grad[3:])
-        dx, dflat = mlp_tc_backward(x16, flat, saved, y, dy.contiguous(), ctx.spec, need_dx, need_dp, ctx.main_grad, row_mask)
+        dx, dflat = mlp_tc_backward(x16, wimage, saved, y, dy.contiguous(), ctx.spec, need_dx, need_dp, ctx.main_grad, row_mask)
         grads = [None] * ctx.n_tensors
         if need_dp and ctx.main_grad is None:
             grads = _split_grads(dflat, ctx.spec)
@@ -872,17 +894,22 @@ def mlp_apply_tc(x, spec: MlpSpec, params, row_mask=None):
 
 
 class _GridMlpTC(torch.autograd.Function):
-    """MLPWithHashEncoding on the tensor-core path: hash-grid features are produced directly in fp16 and never cross
-    autograd; x [n,3] fp32 -> y [n,out] fp32."""
+    """MLPWithHashEncoding on the tensor-core path: hash-grid features are produced directly in the MLP's fp16 operand
+    layout and never cross autograd; x [n,3] fp32 -> y [n,out] fp32.  `cache` (a dict) receives the internal buffers
+    (feat16, wimage, saved, y) so get_normals can run the input-gradient pass without recomputing the forward."""
 
     @staticmethod
-    def forward(ctx, x, table, gspec, mspec, *params):
+    def forward(ctx, x, table, gspec, mspec, cache, *params):
         x = x.contiguous()
-        feat16 = grid_forward(x, table, gspec, torch.float16)
-        flat = _flat_of(params)
-        need = x.requires_grad or table.requires_grad or any(p.requires_grad for p in params)
-        y, saved = mlp_tc_forward(feat16, flat, mspec, need)
-        ctx.save_for_backward(x, table, feat16, flat, saved, y)
+        n = x.shape[0]
+        feat16 = grid_forward(x, table, gspec, "tmh")
+        wimage = tc_pack_weights(_flat_of(params), mspec)
+        y, saved = mlp_tc_forward(feat16, wimage, mspec, n, any(ctx.needs_input_grad) or cache is not None)
+        if cache is not None:
+            # y.detach(): a separate tensor object — the returned `y` gets a grad_fn attached, and caching it would pin this step's
+            # autograd graph (and its stream) into the next step, which breaks CUDA-graph capture
+            cache.update(feat16=feat16, wimage=wimage, saved=saved, y=y.detach())
+        ctx.save_for_backward(x, table, feat16, wimage, saved, y)
         ctx.gspec, ctx.mspec, ctx.n_tensors = gspec, mspec, len(params)
         ctx.table_main_grad = getattr(table, "_nvo_main_grad", None)
         ctx.mlp_main_grad = getattr(params[0], "_nvo_main_grad", None)
@@ -890,9 +917,9 @@ class _GridMlpTC(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        x, table, feat16, flat, saved, y = ctx.saved_tensors
-        need_dx, need_dt, need_dp = ctx.needs_input_grad[0], ctx.needs_input_grad[1], any(ctx.needs_input_grad[4:])
-        dfeat, dflat = mlp_tc_backward(feat16, flat, saved, y, dy.contiguous(), ctx.mspec, need_dx or need_dt, need_dp, ctx.mlp_main_grad)
+        x, table, feat16, wimage, saved, y = ctx.saved_tensors
+        need_dx, need_dt, need_dp = ctx.needs_input_grad[0], ctx.needs_input_grad[1], any(ctx.needs_input_grad[5:])
+        dfeat, dflat = mlp_tc_backward(feat16, wimage, saved, y, dy.contiguous(), ctx.mspec, need_dx or need_dt, need_dp, ctx.mlp_main_grad)
         dtable = dx = None
         if need_dt:
             if ctx.table_main_grad is not None:
@@ -904,11 +931,11 @@ class _GridMlpTC(torch.autograd.Function):
         grads = [None] * ctx.n_tensors
         if need_dp and ctx.mlp_main_grad is None:
             grads = _split_grads(dflat, ctx.mspec)
-        return (dx, dtable, None, None, *grads)
+        return (dx, dtable, None, None, None, *grads)
 
 
-def grid_mlp_tc(x, table, gspec: GridSpec, mspec: MlpSpec, params):
-    return _GridMlpTC.apply(x, table, gspec, mspec, *params)
+def grid_mlp_tc(x, table, gspec: GridSpec, mspec: MlpSpec, params, cache=None):
+    return _GridMlpTC.apply(x, table, gspec, mspec, cache, *params)
 
 
 class _FieldHeadsTC(torch.autograd.Function):
@@ -926,16 +953,16 @@ class _FieldHeadsTC(torch.autograd.Function):
         head_params, pn_params = params[:n_head], params[n_head:]
         want_pn = pn_spec is not None
         density = torch.empty(n, dtype=torch.float32, device=dev)
-        head_in = torch.empty((n, 64), dtype=torch.float16, device=dev)
-        pn_in = torch.empty((n, 32), dtype=torch.float16, device=dev) if want_pn else None
+        head_in = torch.empty(tmh_numel(n, 64), dtype=torch.float16, device=dev)
+        pn_in = torch.empty(tmh_numel(n, 32), dtype=torch.float16, device=dev) if want_pn else None
         call("nvo_field_assemble_forward", B, S, h, selector, directions, positions, cam_idx, embedding, 1, density, head_in, pn_in)
-        need = h.requires_grad or embedding.requires_grad or any(p.requires_grad for p in params)
-        head_flat = _flat_of(head_params)
-        rgb, head_saved = mlp_tc_forward(head_in, head_flat, head_spec, need)
+        need = any(ctx.needs_input_grad)
+        head_flat = tc_pack_weights(_flat_of(head_params), head_spec)
+        rgb, head_saved = mlp_tc_forward(head_in, head_flat, head_spec, n, need)
         pn_flat = pn_saved = pn_raw = pn = None
         if want_pn:
-            pn_flat = _flat_of(pn_params)
-            pn_raw, pn_saved = mlp_tc_forward(pn_in, pn_flat, pn_spec, need)
+            pn_flat = tc_pack_weights(_flat_of(pn_params), pn_spec)
+            pn_raw, pn_saved = mlp_tc_forward(pn_in, pn_flat, pn_spec, n, need)
             pn = torch.empty_like(pn_raw)
             call("nvo_normalize3_forward", n, pn_raw, 1.0, 1e-12, pn)
         ctx.save_for_backward(h, selector, cam_idx, head_in, head_flat, head_saved, rgb, pn_in, pn_flat, pn_saved, pn_raw)
