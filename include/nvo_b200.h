@@ -34,7 +34,8 @@ extern "C" {
 
 /* dtype tags for the table / feature buffers */
 /* NVO_F16_TMH (grid forward output only): fp16 in the tensor-core MLP's tile-major operand layout, see nvo_mlp_tc_forward */
-enum { NVO_F32 = 0, NVO_F16 = 1, NVO_F16_TMH = 2 };
+/* NVO_F32_TMF (dy of nvo_grid_backward / nvo_grid_backward_input only): fp32 tile-major, see nvo_mlp_tc_backward's dx */
+enum { NVO_F32 = 0, NVO_F16 = 1, NVO_F16_TMH = 2, NVO_F32_TMF = 3 };
 /* activations (tcnn network_config "activation"/"output_activation", NS/field_components/mlp.py:34-58) */
 /* NVO_ACT_TRUNC_EXP: exp forward, backward g*exp(clamp(x,-15,15)) (NS/field_components/activations.py:28-41) */
 enum { NVO_ACT_NONE = 0, NVO_ACT_RELU = 1, NVO_ACT_SIGMOID = 2, NVO_ACT_TANH = 3, NVO_ACT_EXP = 4, NVO_ACT_TRUNC_EXP = 5 };
@@ -108,12 +109,16 @@ int nvo_mlp_backward(const nvo_mlp_desc* d, void* stream, int64_t n, const float
  *   saved   opaque forward context of nvo_mlp_tc_saved_bytes(d, n) bytes (fp16 hidden activations, TMH layout);
  *   scratch one float the backward uses for its device-side gradient scale (max|dy| -> power-of-two loss scale, the
  *           device analogue of tinycudann's loss_scale, modules.py:174);
- *   y, dy, dx, dparams fp32 row-major exactly as the SIMT entry points. */
+ *   y, dy, dparams fp32 row-major exactly as the SIMT entry points;
+ *   dx      fp32 in TMF layout ("tile-major float"): [ceil(n/128)][in_dim][128], i.e. column-major inside each 128-row tile, so
+ *           the kernel's row-per-thread epilogue stores coalesced and the per-sample consumers (nvo_grid_backward with
+ *           out_dtype NVO_F32_TMF, nvo_field_assemble_backward with tmf != 0) read coalesced; nvo_tmf_to_rows converts to [n,in_dim]. */
 int nvo_mlp_tc_in_pad(const nvo_mlp_desc* d);
 int64_t nvo_mlp_tc_saved_bytes(const nvo_mlp_desc* d, int64_t n);
 int64_t nvo_mlp_tc_wimage_bytes(const nvo_mlp_desc* d);
 int nvo_cast_pad_f16(void* stream, int64_t n, int32_t in_dim, int32_t kpad, const float* x, void* out);
 int nvo_mlp_tc_pack_weights(const nvo_mlp_desc* d, void* stream, const float* params, void* wimage);
+int nvo_tmf_to_rows(void* stream, int64_t n, int32_t K, const float* src, float* dst);
 int nvo_mlp_tc_forward(const nvo_mlp_desc* d, void* stream, int64_t n, const void* x16, const void* wimage, const float* row_mask, float* y,
                        void* saved);
 int nvo_mlp_tc_backward(const nvo_mlp_desc* d, void* stream, int64_t n, const void* x16, const void* wimage, const void* saved, const float* y,
@@ -168,8 +173,9 @@ int nvo_normalize3_backward(void* stream, int64_t n, const float* v, const float
 int nvo_field_assemble_forward(void* stream, int64_t B, int32_t S, const float* h, const float* selector, const float* directions, const float* pos,
                                const int64_t* cam_idx, const float* embedding, int32_t f16_padded, float* density, void* head_in, void* pn_in);
 /* backward: dh[n,16] (overwritten) and dembedding[K,32] (accumulate, nullable) from ddensity[n] (nullable), dhead_in[n,63], dpn_in[n,27] (nullable) */
+/* tmf != 0: dhead_in / dpn_in are in the TMF layout nvo_mlp_tc_backward writes ([tile][63 | 27][128]) instead of row-major */
 int nvo_field_assemble_backward(void* stream, int64_t B, int32_t S, const float* h, const float* selector, const int64_t* cam_idx,
-                                const float* ddensity, const float* dhead_in, const float* dpn_in, float* dh, float* dembedding);
+                                const float* ddensity, const float* dhead_in, const float* dpn_in, int32_t tmf, float* dh, float* dembedding);
 
 /* ---------------------------------------------------------------------------------------------
  * Per-ray operators.  B rays, S samples per ray.  Sample intervals are stored as bin EDGES:

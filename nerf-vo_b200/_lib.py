@@ -19,7 +19,7 @@ HEADER = os.path.join(os.path.dirname(HERE), "include", "nvo_b200.h")
 
 NVO_MAX_LEVELS = 32
 NVO_MAX_LAYERS = 6
-NVO_F32, NVO_F16, NVO_F16_TMH = 0, 1, 2
+NVO_F32, NVO_F16, NVO_F16_TMH, NVO_F32_TMF = 0, 1, 2, 3
 ACT = {"none": 0, "relu": 1, "sigmoid": 2, "tanh": 3, "exponential": 4, "exp": 4, "trunc_exp": 5}
 
 
@@ -156,7 +156,7 @@ def make_grid_desc(n_levels: int, log2_T: int, scalings, table_dtype=torch.float
     d = GridDesc()
     d.n_levels, d.log2_T = int(n_levels), int(log2_T)
     d.table_dtype = NVO_F16 if table_dtype == torch.float16 else NVO_F32
-    d.out_dtype = NVO_F16_TMH if out_dtype == "tmh" else (NVO_F16 if out_dtype == torch.float16 else NVO_F32)
+    d.out_dtype = {"tmh": NVO_F16_TMH, "tmf": NVO_F32_TMF}.get(out_dtype) if isinstance(out_dtype, str) else (NVO_F16 if out_dtype == torch.float16 else NVO_F32)
     sc = [float(s) for s in scalings]
     for i in range(NVO_MAX_LEVELS):
         d.scalings[i] = sc[i] if i < n_levels else 0.0

@@ -214,8 +214,10 @@ __global__ void __launch_bounds__(128)
 
 __global__ void __launch_bounds__(256)
     k_assemble_bwd(int64_t B, int S, const float* __restrict__ h, const float* __restrict__ selector, const int64_t* __restrict__ cam_idx,
-                   const float* __restrict__ ddensity, const float* __restrict__ dhead_in, const float* __restrict__ dpn_in, float* __restrict__ dh,
-                   float* __restrict__ dembedding) {
+                   const float* __restrict__ ddensity, const float* __restrict__ dhead_in, const float* __restrict__ dpn_in, int tmf,
+                   float* __restrict__ dh, float* __restrict__ dembedding) {
+    // element (sample t, column c) of a [n, K] gradient: row-major, or TMF [tile][K][128] (mlp_tc.cu's dx layout)
+    auto at = [tmf](const float* g, int K, int64_t t, int c) { return tmf ? __ldg(g + (((t >> 7) * K + c) << 7) + (t & 127)) : __ldg(g + K * t + c); };
     // one warp per ray when accumulating the appearance-embedding gradient: lanes stride over samples, then a warp
     // reduction leaves ONE atomicAdd per (ray, channel) instead of S.
     const int lane = threadIdx.x & 31;
@@ -233,8 +235,8 @@ __global__ void __launch_bounds__(256)
             g[0] = ddensity ? __ldg(ddensity + t) * __ldg(selector + t) * expf(fminf(fmaxf(h0, -15.f), 15.f)) : 0.f;
 #pragma unroll
             for (int k = 0; k < GEO; ++k) {
-                float v = __ldg(dhead_in + HEAD_IN * t + 16 + k);
-                if (dpn_in) v += __ldg(dpn_in + PN_IN * t + 12 + k);
+                float v = at(dhead_in, HEAD_IN, t, 16 + k);
+                if (dpn_in) v += at(dpn_in, PN_IN, t, 12 + k);
                 g[1 + k] = v;
             }
 #pragma unroll
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(256)
         if (dembedding && cam_idx) {
             // transpose-reduce: for each of the 32 samples of this chunk add its 32 appearance gradients; lane k keeps channel k
             for (int j = 0; j < 32; ++j) {
-                if (s0 + j < S) eacc += __ldg(dhead_in + HEAD_IN * (r * S + s0 + j) + 16 + GEO + lane);
+                if (s0 + j < S) eacc += at(dhead_in, HEAD_IN, r * S + s0 + j, 16 + GEO + lane);
             }
         }
     }
@@ -325,12 +327,12 @@ extern "C" int nvo_field_assemble_forward(void* stream, int64_t B, int32_t S, co
     return 0;
 }
 extern "C" int nvo_field_assemble_backward(void* stream, int64_t B, int32_t S, const float* h, const float* selector, const int64_t* cam_idx,
-                                           const float* ddensity, const float* dhead_in, const float* dpn_in, float* dh, float* dembedding) {
+                                           const float* ddensity, const float* dhead_in, const float* dpn_in, int32_t tmf, float* dh, float* dembedding) {
     NVO_CHECK(B >= 0 && S >= 1, "field_assemble_backward: bad shape");
     if (B == 0) return 0;
     NVO_CHECK(h && dhead_in && dh, "field_assemble_backward: null pointer");
     NVO_CHECK(!ddensity || selector, "field_assemble_backward: selector required for ddensity");
-    k_assemble_bwd<<<nvo_blocks(B * 32, 256), 256, 0, (cudaStream_t)stream>>>(B, S, h, selector, cam_idx, ddensity, dhead_in, dpn_in, dh, dembedding);
+    k_assemble_bwd<<<nvo_blocks(B * 32, 256), 256, 0, (cudaStream_t)stream>>>(B, S, h, selector, cam_idx, ddensity, dhead_in, dpn_in, tmf, dh, dembedding);
     NVO_CUDA_LAUNCH_CHECK("field_assemble_backward");
     return 0;
 }

@@ -12,6 +12,17 @@ __device__ __forceinline__ void store_feat(float* y, int64_t t, float a, float b
 __device__ __forceinline__ void store_feat(__half* y, int64_t t, float a, float b) { reinterpret_cast<__half2*>(y)[t] = __floats2half2_rn(a, b); }
 __device__ __forceinline__ float2 load_feat(const float* y, int64_t t) { return __ldg(reinterpret_cast<const float2*>(y) + t); }
 __device__ __forceinline__ float2 load_feat(const __half* y, int64_t t) { return __half22float2(__ldg(reinterpret_cast<const __half2*>(y) + t)); }
+// dy of (sample s, level l): row-major [n, 2L] (t = s*L + l) or, tmf != 0, fp32 tile-major [tile][2L][128] (mlp_tc.cu's dx)
+template <typename OutT>
+__device__ __forceinline__ float2 load_dy(const OutT* dy, int64_t s, int l, int L, int tmf) {
+    return load_feat(dy, s * L + l);
+}
+template <>
+__device__ __forceinline__ float2 load_dy<float>(const float* dy, int64_t s, int l, int L, int tmf) {
+    if (!tmf) return load_feat(dy, s * L + l);
+    const float* b = dy + (((s >> 7) * (2 * L) + 2 * l) << 7) + (s & 127);
+    return make_float2(__ldg(b), __ldg(b + 128));
+}
 
 template <typename RowT, typename OutT>
 __global__ void __launch_bounds__(256) k_grid_fwd(const __grid_constant__ GridP p, int64_t total, const float* __restrict__ x,
@@ -99,7 +110,7 @@ __global__ void __launch_bounds__(256) k_grid_fwd_tmh(const __grid_constant__ Gr
 // (neighbours along a ray) and equal target rows form runs that seg_red_add_v2 collapses before touching L2.
 template <typename OutT>
 __global__ void __launch_bounds__(256) k_grid_bwd(const __grid_constant__ GridP p, int64_t n, const float* __restrict__ x,
-                                                  const OutT* __restrict__ dy, float* __restrict__ dtable) {
+                                                  const OutT* __restrict__ dy, float* __restrict__ dtable, int tmf) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool valid = s < n;
@@ -107,7 +118,7 @@ __global__ void __launch_bounds__(256) k_grid_bwd(const __grid_constant__ GridP 
     const float px = __ldg(x + 3 * ss), py = __ldg(x + 3 * ss + 1), pz = __ldg(x + 3 * ss + 2);
     const uint32_t mask = (1u << p.log2T) - 1u;
     for (int l = 0; l < p.L; ++l) {
-        float2 g = load_feat(dy, ss * p.L + l);
+        float2 g = load_dy(dy, ss, l, p.L, tmf);
         if (!valid) g = make_float2(0.f, 0.f);
         if (__ballot_sync(0xffffffffu, g.x != 0.f || g.y != 0.f) == 0u) continue;  // whole warp masked / padded at this level
         const Corner c = make_corner(px, py, pz, p.scale[l]);
@@ -120,7 +131,7 @@ __global__ void __launch_bounds__(256) k_grid_bwd(const __grid_constant__ GridP 
 template <typename RowT, typename OutT>
 __global__ void __launch_bounds__(256) k_grid_bwd_input(const __grid_constant__ GridP p, int64_t total, const float* __restrict__ x,
                                                         const RowT* __restrict__ table, const OutT* __restrict__ dy, float* __restrict__ dx,
-                                                        int shuffle_reduce) {
+                                                        int shuffle_reduce, int tmf) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = t < total;
     const int64_t tt = live ? t : total - 1;
@@ -134,7 +145,7 @@ __global__ void __launch_bounds__(256) k_grid_bwd_input(const __grid_constant__ 
     float2 f[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = load_row(slab, corner_index(c, SEL_X(k), SEL_Y(k), SEL_Z(k), mask));
-    float2 g = load_feat(dy, tt);
+    float2 g = load_dy(dy, s, l, p.L, tmf);
     if (!live) g = make_float2(0.f, 0.f);
     const float mx = 1.f - c.ox, my = 1.f - c.oy, mz = 1.f - c.oz;
     float gx = 0.f, gy = 0.f, gz = 0.f;
@@ -190,7 +201,7 @@ static int make_params(const nvo_grid_desc* d, GridP* p) {
     NVO_CHECK(d->n_levels >= 1 && d->n_levels <= NVO_MAX_LEVELS, "grid: n_levels=%d out of range [1,%d]", d->n_levels, NVO_MAX_LEVELS);
     NVO_CHECK(d->log2_T >= 1 && d->log2_T <= 30, "grid: log2_T=%d out of range [1,30]", d->log2_T);
     NVO_CHECK(d->table_dtype == NVO_F32 || d->table_dtype == NVO_F16, "grid: bad table_dtype %d", d->table_dtype);
-    NVO_CHECK(d->out_dtype == NVO_F32 || d->out_dtype == NVO_F16 || d->out_dtype == NVO_F16_TMH, "grid: bad out_dtype %d", d->out_dtype);
+    NVO_CHECK(d->out_dtype >= NVO_F32 && d->out_dtype <= NVO_F32_TMF, "grid: bad out_dtype %d", d->out_dtype);
     p->L = d->n_levels;
     p->log2T = d->log2_T;
     for (int i = 0; i < NVO_MAX_LEVELS; ++i) p->scale[i] = i < d->n_levels ? d->scalings[i] : 0.f;
@@ -236,10 +247,10 @@ extern "C" int nvo_grid_backward(const nvo_grid_desc* d, void* stream, int64_t n
     NVO_CHECK(x && dy && dtable, "grid_backward: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned int g = nvo_blocks(n, 256);
-    if (d->out_dtype == NVO_F32)
-        k_grid_bwd<float><<<g, 256, 0, st>>>(p, n, x, (const float*)dy, dtable);
+    if (d->out_dtype == NVO_F32 || d->out_dtype == NVO_F32_TMF)
+        k_grid_bwd<float><<<g, 256, 0, st>>>(p, n, x, (const float*)dy, dtable, d->out_dtype == NVO_F32_TMF);
     else
-        k_grid_bwd<__half><<<g, 256, 0, st>>>(p, n, x, (const __half*)dy, dtable);
+        k_grid_bwd<__half><<<g, 256, 0, st>>>(p, n, x, (const __half*)dy, dtable, 0);
     NVO_CUDA_LAUNCH_CHECK("grid_backward");
     return 0;
 }
@@ -258,14 +269,16 @@ extern "C" int nvo_grid_backward_input(const nvo_grid_desc* d, void* stream, int
         cudaError_t e = cudaMemsetAsync(dx, 0, sizeof(float) * 3 * n, st);
         NVO_CHECK(e == cudaSuccess, "grid_backward_input: memset failed: %s", cudaGetErrorString(e));
     }
-    if (d->table_dtype == NVO_F32 && d->out_dtype == NVO_F32)
-        k_grid_bwd_input<float2, float><<<g, 256, 0, st>>>(p, total, x, (const float2*)table, (const float*)dy, dx, shuffle);
+    const int tmf = d->out_dtype == NVO_F32_TMF;
+    const bool f32 = d->out_dtype == NVO_F32 || tmf;
+    if (d->table_dtype == NVO_F32 && f32)
+        k_grid_bwd_input<float2, float><<<g, 256, 0, st>>>(p, total, x, (const float2*)table, (const float*)dy, dx, shuffle, tmf);
     else if (d->table_dtype == NVO_F32)
-        k_grid_bwd_input<float2, __half><<<g, 256, 0, st>>>(p, total, x, (const float2*)table, (const __half*)dy, dx, shuffle);
-    else if (d->out_dtype == NVO_F32)
-        k_grid_bwd_input<__half2, float><<<g, 256, 0, st>>>(p, total, x, (const __half2*)table, (const float*)dy, dx, shuffle);
+        k_grid_bwd_input<float2, __half><<<g, 256, 0, st>>>(p, total, x, (const float2*)table, (const __half*)dy, dx, shuffle, 0);
+    else if (f32)
+        k_grid_bwd_input<__half2, float><<<g, 256, 0, st>>>(p, total, x, (const __half2*)table, (const float*)dy, dx, shuffle, tmf);
     else
-        k_grid_bwd_input<__half2, __half><<<g, 256, 0, st>>>(p, total, x, (const __half2*)table, (const __half*)dy, dx, shuffle);
+        k_grid_bwd_input<__half2, __half><<<g, 256, 0, st>>>(p, total, x, (const __half2*)table, (const __half*)dy, dx, shuffle, 0);
     NVO_CUDA_LAUNCH_CHECK("grid_backward_input");
     return 0;
 }

@@ -403,6 +403,43 @@ __device__ __forceinline__ void bwd_prefetch(const TcP& p, unsigned char* stage,
         bulk_g2s(stage + p.a_off[l], saved + (tile * p.saved_chunks + p.saved_chunk_off[l - 1]) * (int64_t)CHUNK_B, (uint32_t)p.kpad[l] * 256u, mbar);
 }
 
+// dL/dz of the last layer for one (row, output o): dy * mask * act'(y)
+__device__ __forceinline__ float dz_last_direct(const TcP& p, int64_t n, int64_t row, int o, const float* __restrict__ dy, const float* __restrict__ y,
+                                                const float* __restrict__ row_mask) {
+    const int last = p.n_layers - 1, N = p.dims[last], act = p.acts[last];
+    if (row >= n || o >= N) return 0.f;
+    float g = __ldg(dy + row * N + o);
+    if (row_mask) g *= __ldg(row_mask + row);
+    if (act != NVO_ACT_NONE) g *= tc_act_bwd(__ldg(y + row * N + o), act);
+    return g;
+}
+// the first 16 outputs of a tile's row into registers (every field network has <= 16 real outputs); loads are issued one
+// tile ahead so their latency hides behind the previous tile's layer chain
+__device__ __forceinline__ void load_dz_last(const TcP& p, int64_t n, int64_t tile, int tid, int64_t n_tiles, const float* __restrict__ dy,
+                                             const float* __restrict__ y, const float* __restrict__ row_mask, float* pre) {
+    const int last = p.n_layers - 1, N = p.dims[last], act = p.acts[last];
+    const int64_t row = tile * TM + tid;
+    const bool live = tile < n_tiles && row < n;
+    const float m = (live && row_mask) ? __ldg(row_mask + row) : 1.f;
+    if (live && N == 16 && act == NVO_ACT_NONE) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(dy + row * 16) + q);
+            pre[4 * q] = g.x * m, pre[4 * q + 1] = g.y * m, pre[4 * q + 2] = g.z * m, pre[4 * q + 3] = g.w * m;
+        }
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        float g = 0.f;
+        if (live && j < N) {
+            g = __ldg(dy + row * N + j) * m;
+            if (act != NVO_ACT_NONE) g *= tc_act_bwd(__ldg(y + row * N + j), act);
+        }
+        pre[j] = g;
+    }
+}
+
 __global__ void __launch_bounds__(TM) k_mlp_tc_bwd(const __grid_constant__ TcP p, int64_t n, const unsigned char* __restrict__ x16,
                                                    const unsigned char* __restrict__ wimg, const unsigned char* __restrict__ saved,
                                                    const float* __restrict__ y, const float* __restrict__ row_mask, const float* __restrict__ dy,
@@ -452,6 +489,8 @@ __global__ void __launch_bounds__(TM) k_mlp_tc_bwd(const __grid_constant__ TcP p
     uint32_t phase = 0;
     const int last = p.n_layers - 1;
     int it = 0;
+    float pre[16];
+    load_dz_last(p, n, blockIdx.x, tid, n_tiles, dy, y, row_mask, pre);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
         const int64_t row = tile * TM + tid;
@@ -462,22 +501,25 @@ __global__ void __launch_bounds__(TM) k_mlp_tc_bwd(const __grid_constant__ TcP p
         if (tid == 0 && tile + gridDim.x < n_tiles)
             bwd_prefetch(p, smem + BWD_STAGE + (buf ^ 1) * p.stage_bytes, tile + gridDim.x, x16, saved, mbar_st + (buf ^ 1));
         // ---- dZ of the last layer: dy * mask * act'(y) * scale -> fp16 G tile (buffer parity of `last`) -------------
+        // (dy, y, mask of THIS tile were loaded into registers during the previous tile; issue the next tile's loads now)
         {
             unsigned char* sG = smem + ((last & 1) ? BWD_G1 : BWD_G0);
-            const int N = p.dims[last], np = p.npad[last], act = p.acts[last];
-            const float m = (live && row_mask) ? __ldg(row_mask + row) : 1.f;
-            for (int c8 = 0; c8 < (np >> 3); ++c8) {
+            const int np = p.npad[last];
+            float cur[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) cur[j] = pre[j];
+            load_dz_last(p, n, tile + gridDim.x, tid, n_tiles, dy, y, row_mask, pre);
+#pragma unroll
+            for (int c8 = 0; c8 < 2; ++c8) {  // np >= 16: the two register-resident chunks
                 float v[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int o = c8 * 8 + j;
-                    float g = 0.f;
-                    if (live && o < N) {
-                        g = __ldg(dy + row * N + o) * m;
-                        if (act != NVO_ACT_NONE) g *= tc_act_bwd(__ldg(y + row * N + o), act);
-                    }
-                    v[j] = g * gscale;
-                }
+                for (int j = 0; j < 8; ++j) v[j] = cur[c8 * 8 + j] * gscale;
+                *reinterpret_cast<uint4*>(sG + c8 * CHUNK_B + tid * 16) = pack8(v);
+            }
+            for (int c8 = 2; c8 < (np >> 3); ++c8) {  // wider output layers (not on the nerfacto path): direct loads
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = dz_last_direct(p, n, row, c8 * 8 + j, dy, y, row_mask) * gscale;
                 *reinterpret_cast<uint4*>(sG + c8 * CHUNK_B + tid * 16) = pack8(v);
             }
         }
@@ -539,18 +581,11 @@ __global__ void __launch_bounds__(TM) k_mlp_tc_bwd(const __grid_constant__ TcP p
                         }
                         const int ncol = min(32, kp - c32);
                         if (live) {
-                            float* dst = dx + row * K + c32;
-                            if ((K & 3) == 0 && K - c32 >= ncol) {
+                            // TMF ("tile-major float"): dx[tile][col][row] — a warp stores 128 contiguous bytes per column
+                            float* dst = dx + (tile * K + c32) * TM + tid;
 #pragma unroll
-                                for (int q = 0; q < 8; ++q)
-                                    if (q * 4 < ncol)
-                                        reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q] * inv_gscale, v[4 * q + 1] * inv_gscale,
-                                                                                        v[4 * q + 2] * inv_gscale, v[4 * q + 3] * inv_gscale);
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (j < ncol && c32 + j < K) dst[j] = v[j] * inv_gscale;
-                            }
+                            for (int j = 0; j < 32; ++j)
+                                if (j < ncol && c32 + j < K) dst[j * TM] = v[j] * inv_gscale;
                         }
                     }
                 }
@@ -584,6 +619,15 @@ __global__ void __launch_bounds__(TM) k_mlp_tc_bwd(const __grid_constant__ TcP p
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// fp32 TMF [ceil(n/128)][K][128] -> row-major [n, K] (only the generic tcnn.Network wrapper needs row-major input gradients)
+__global__ void __launch_bounds__(256) k_tmf_to_rows(int64_t n, int K, const float* __restrict__ src, float* __restrict__ dst) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * K) return;
+    const int64_t row = t / K;
+    const int c = (int)(t - row * K);
+    dst[t] = __ldg(src + ((row >> 7) * K + c) * TM + (row & 127));
 }
 
 // fp32 [n, in_dim] row-major -> fp16 TMH tiles [ceil(n/128)][kpad/8][128][8], zero padded (columns >= in_dim, rows >= n)
@@ -668,6 +712,15 @@ extern "C" int nvo_cast_pad_f16(void* stream, int64_t n, int32_t in_dim, int32_t
     const int64_t items = ((n + TM - 1) / TM) * (kpad >> 3) * TM;
     k_cast_tmh<<<nvo_blocks(items, 256), 256, 0, (cudaStream_t)stream>>>(n, in_dim, kpad, x, (uint4*)out);
     NVO_CUDA_LAUNCH_CHECK("cast_pad_f16");
+    return 0;
+}
+
+extern "C" int nvo_tmf_to_rows(void* stream, int64_t n, int32_t K, const float* src, float* dst) {
+    NVO_CHECK(n >= 0 && K >= 1, "tmf_to_rows: bad shape");
+    if (n == 0) return 0;
+    NVO_CHECK(src && dst, "tmf_to_rows: null pointer");
+    k_tmf_to_rows<<<nvo_blocks(n * K, 256), 256, 0, (cudaStream_t)stream>>>(n, K, src, dst);
+    NVO_CUDA_LAUNCH_CHECK("tmf_to_rows");
     return 0;
 }
 

@@ -215,7 +215,7 @@ class NerfactoField(Field):
                 feat = ops.grid_forward(x, table, enc.spec)
                 y, saved = ops.mlp_forward(feat, flat, mlp.spec, save=True)
                 dfeat, _ = ops.mlp_backward(feat, flat, saved, y, onehot, mlp.spec, need_dx=True, need_dparams=False)
-            g = ops.grid_backward_input(x, table, dfeat, enc.spec)
+            g = ops.grid_backward_input(x, table, dfeat, enc.spec, tmf=self.precision == "fp16")
             normals = ops.normalize3(g, scale=-1.0, eps=1e-12)
         return normals.view(*c["shape"], 3)
 

@@ -84,21 +84,28 @@ def grid_forward(x, table, spec: GridSpec, out_dtype=torch.float32):
     return y
 
 
-def grid_backward(x, dy, spec: GridSpec, dtable=None, n_rows=None):
-    """Scatter dy into a fp32 gradient table (allocated zero-filled when not given)."""
+def grid_backward(x, dy, spec: GridSpec, dtable=None, n_rows=None, tmf: bool = False):
+    """Scatter dy into a fp32 gradient table (allocated zero-filled when not given).  tmf: dy is the fp32 tile-major buffer
+    the tensor-core MLP backward writes ([tile][2L][128]) instead of [n, 2L] row-major."""
     check(x, "grid input", torch.float32, (None, 3))
-    check(dy, "grid dy", dy.dtype, (x.shape[0], spec.out_dim))
+    if tmf:
+        check(dy, "grid dy (tmf)", torch.float32, (tmh_numel(x.shape[0], spec.out_dim),))
+    else:
+        check(dy, "grid dy", dy.dtype, (x.shape[0], spec.out_dim))
     if dtable is None:
         dtable = torch.zeros((spec.n_rows, 2), dtype=torch.float32, device=x.device)
-    call("nvo_grid_backward", spec.desc(torch.float32, dy.dtype), x.shape[0], x, dy, dtable)
+    call("nvo_grid_backward", spec.desc(torch.float32, "tmf" if tmf else dy.dtype), x.shape[0], x, dy, dtable)
     return dtable
 
 
-def grid_backward_input(x, table, dy, spec: GridSpec):
+def grid_backward_input(x, table, dy, spec: GridSpec, tmf: bool = False):
     _check_grid_inputs(x, table, spec)
-    check(dy, "grid dy", dy.dtype, (x.shape[0], spec.out_dim))
+    if tmf:
+        check(dy, "grid dy (tmf)", torch.float32, (tmh_numel(x.shape[0], spec.out_dim),))
+    else:
+        check(dy, "grid dy", dy.dtype, (x.shape[0], spec.out_dim))
     dx = torch.empty_like(x)
-    call("nvo_grid_backward_input", spec.desc(table.dtype, dy.dtype), x.shape[0], x, table, dy, dx)
+    call("nvo_grid_backward_input", spec.desc(table.dtype, "tmf" if tmf else dy.dtype), x.shape[0], x, table, dy, dx)
     return dx
 
 
@@ -436,7 +443,7 @@ class _FieldAssemble(torch.autograd.Function):
                 # eval-style mean embedding: every sample contributes to the single vector
                 demb = dhead_in[:, 31:].sum(0).reshape(ctx.emb_shape)
         c = lambda t: None if t is None else t.contiguous()
-        call("nvo_field_assemble_backward", ctx.B, ctx.S, h, selector, cam_idx, c(ddensity), dhead_in.contiguous(), c(dpn_in), dh,
+        call("nvo_field_assemble_backward", ctx.B, ctx.S, h, selector, cam_idx, c(ddensity), dhead_in.contiguous(), c(dpn_in), 0, dh,
              demb if cam_idx is not None else None)
         if demb is ctx.main_grad:
             demb = None
@@ -840,12 +847,20 @@ def mlp_tc_forward(x16, wimage, spec: MlpSpec, n: int, save: bool, row_mask=None
 def mlp_tc_backward(x16, wimage, saved, y, dy, spec: MlpSpec, need_dx: bool, need_dparams: bool, dflat=None, row_mask=None):
     n = dy.shape[0]
     check(dy, "mlp dy", torch.float32, (n, spec.out_dim))
-    dx = torch.empty((n, spec.in_dim), dtype=torch.float32, device=x16.device) if need_dx else None
+    # dx comes back in TMF layout ([tile][in_dim][128] fp32, see include/nvo_b200.h); tmf_to_rows() converts when needed
+    dx = torch.empty(tmh_numel(n, spec.in_dim), dtype=torch.float32, device=x16.device) if need_dx else None
     if need_dparams and dflat is None:
         dflat = torch.zeros(spec.n_params, dtype=torch.float32, device=x16.device)
     scratch = torch.empty(1, dtype=torch.float32, device=x16.device)
     call("nvo_mlp_tc_backward", spec.desc, n, x16, wimage, saved, y, row_mask, dy, scratch, dx, dflat if need_dparams else None)
     return dx, dflat
+
+
+def tmf_to_rows(src, n: int, k: int):
+    check(src, "tmf buffer", torch.float32, (tmh_numel(n, k),))
+    dst = torch.empty((n, k), dtype=torch.float32, device=src.device)
+    call("nvo_tmf_to_rows", n, k, src, dst)
+    return dst
 
 
 def _flat_of(params):
@@ -883,6 +898,8 @@ class _MlpApplyTC(torch.autograd.Function):
         x16, wimage, saved, y, row_mask = ctx.saved_tensors
         need_dx, need_dp = ctx.needs_input_grad[0], any(ctx.needs_input_grad[3:])
         dx, dflat = mlp_tc_backward(x16, wimage, saved, y, dy.contiguous(), ctx.spec, need_dx, need_dp, ctx.main_grad, row_mask)
+        if dx is not None:
+            dx = tmf_to_rows(dx, dy.shape[0], ctx.spec.in_dim)
         grads = [None] * ctx.n_tensors
         if need_dp and ctx.main_grad is None:
             grads = _split_grads(dflat, ctx.spec)
@@ -923,11 +940,11 @@ class _GridMlpTC(torch.autograd.Function):
         dtable = dx = None
         if need_dt:
             if ctx.table_main_grad is not None:
-                grid_backward(x, dfeat, ctx.gspec, dtable=ctx.table_main_grad)
+                grid_backward(x, dfeat, ctx.gspec, dtable=ctx.table_main_grad, tmf=True)
             else:
-                dtable = grid_backward(x, dfeat, ctx.gspec).view(table.shape)
+                dtable = grid_backward(x, dfeat, ctx.gspec, tmf=True).view(table.shape)
         if need_dx:
-            dx = grid_backward_input(x, table, dfeat, ctx.gspec)
+            dx = grid_backward_input(x, table, dfeat, ctx.gspec, tmf=True)
         grads = [None] * ctx.n_tensors
         if need_dp and ctx.mlp_main_grad is None:
             grads = _split_grads(dflat, ctx.mspec)
@@ -994,8 +1011,8 @@ class _FieldHeadsTC(torch.autograd.Function):
             elif cam_idx is not None:
                 demb = torch.zeros(ctx.emb_shape, dtype=torch.float32, device=dev)
             else:
-                demb = dhead_in[:, 31:].sum(0).reshape(ctx.emb_shape)
-        call("nvo_field_assemble_backward", ctx.B, ctx.S, h, selector, cam_idx, c(ddensity), dhead_in, dpn_in, dh, demb if cam_idx is not None else None)
+                demb = tmf_to_rows(dhead_in, n, 63)[:, 31:].sum(0).reshape(ctx.emb_shape)
+        call("nvo_field_assemble_backward", ctx.B, ctx.S, h, selector, cam_idx, c(ddensity), dhead_in, dpn_in, 1, dh, demb if cam_idx is not None else None)
         if demb is ctx.emb_main_grad:
             demb = None
         head_grads = [None] * ctx.n_head
