@@ -12,6 +12,51 @@ from . import _lib
 from ._lib import call, check
 
 # ------------------------------------------------------------------------------------------------
+# side streams for gradient-leaf kernels
+# ------------------------------------------------------------------------------------------------
+
+
+class _LeafStreams:
+    """Kernels that only scatter into the trainer's flat gradient buffer (hash-table scatter, fused proposal backward) have no
+    consumer inside the backward pass, so they may run on side streams next to the remaining (latency-bound) backward chain.
+    The trainer enables this, and joins the streams before the optimizer / all-reduce.  Tensors such a kernel reads are kept
+    alive until the join, so the caching allocator cannot hand their blocks to main-stream work that would race with it."""
+
+    def __init__(self):
+        self.enabled = False
+        self.streams: List[torch.cuda.Stream] = []
+        self.used: List[torch.cuda.Stream] = []
+        self.refs: list = []
+        self.next = 0
+
+    def enable(self, n: int = 3):
+        self.streams = [torch.cuda.Stream() for _ in range(n)]
+        self.enabled = True
+
+    def fork(self, *keepalive):
+        """Returns a context manager running its body on the next side stream, ordered after the current stream."""
+        cur = torch.cuda.current_stream()
+        st = self.streams[self.next % len(self.streams)]
+        self.next += 1
+        st.wait_stream(cur)
+        if st not in self.used:
+            self.used.append(st)
+        self.refs.append(keepalive)
+        return torch.cuda.stream(st)
+
+    def join(self):
+        cur = torch.cuda.current_stream()
+        for st in self.used:
+            cur.wait_stream(st)
+        self.used.clear()
+        self.refs.clear()
+        self.next = 0
+
+
+leaf_streams = _LeafStreams()
+
+
+# ------------------------------------------------------------------------------------------------
 # hash grid
 # ------------------------------------------------------------------------------------------------
 
@@ -314,8 +359,14 @@ class _PropDensity(torch.autograd.Function):
             stride = 0
         else:
             s, e, stride = ctx.iv.triple()
-        call("nvo_prop_density_backward", ctx.gspec.desc(table.dtype, torch.float32), ctx.hidden, ctx.B, ctx.S, origins, directions, s, e, stride, positions,
-             flat, feat, ddensity.contiguous(), dtable, dflat)
+        ddensity = ddensity.contiguous()
+        args = ("nvo_prop_density_backward", ctx.gspec.desc(table.dtype, torch.float32), ctx.hidden, ctx.B, ctx.S, origins, directions, s, e, stride, positions,
+                flat, feat, ddensity, dtable, dflat)
+        if leaf_streams.enabled and (not need_dt or dtable is ctx.table_main_grad) and (not need_dp or dflat is ctx.mlp_main_grad):
+            with leaf_streams.fork(table, flat, feat, origins, directions, positions, ddensity, ctx.iv):
+                call(*args)
+        else:
+            call(*args)
         if dtable is ctx.table_main_grad:
             dtable = None
         elif dtable is not None and table.dtype != torch.float32:
@@ -939,7 +990,10 @@ class _GridMlpTC(torch.autograd.Function):
         dfeat, dflat = mlp_tc_backward(feat16, wimage, saved, y, dy.contiguous(), ctx.mspec, need_dx or need_dt, need_dp, ctx.mlp_main_grad)
         dtable = dx = None
         if need_dt:
-            if ctx.table_main_grad is not None:
+            if ctx.table_main_grad is not None and leaf_streams.enabled:
+                with leaf_streams.fork(x, dfeat):
+                    grid_backward(x, dfeat, ctx.gspec, dtable=ctx.table_main_grad, tmf=True)
+            elif ctx.table_main_grad is not None:
                 grid_backward(x, dfeat, ctx.gspec, dtable=ctx.table_main_grad, tmf=True)
             else:
                 dtable = grid_backward(x, dfeat, ctx.gspec, tmf=True).view(table.shape)

@@ -64,6 +64,9 @@ class MappingTrainer:
                        "jitter0": f(B, 1), "jitter1": f(B, 1), "jitter2": f(B, 1)}
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
         self.loss_terms: Dict[str, torch.Tensor] = {}
+        if self.device.type == "cuda" and not ops.leaf_streams.enabled:
+            with torch.cuda.device(self.device):
+                ops.leaf_streams.enable(3)
         self._graph_fb: Optional[torch.cuda.CUDAGraph] = None
         self._graph_opt: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_step = 0
@@ -116,6 +119,7 @@ class MappingTrainer:
         _, loss_dict, _ = self.model.get_train_loss_dict(self._bundle(), batch, [i["jitter0"], i["jitter1"], i["jitter2"]])
         total = sum(loss_dict.values())
         total.backward()
+        ops.leaf_streams.join()  # scatter kernels running on side streams must land before the all-reduce / optimizer
         self.loss.copy_(total.detach())
         self.loss_terms = {k: v.detach() for k, v in loss_dict.items()}
 
