@@ -132,17 +132,21 @@ int nvo_mlp_tc_backward(const nvo_mlp_desc* d, void* stream, int64_t n, const vo
  * training, the 2L interpolated features) is written to HBM.
  * Sample points: `positions` [B*S,3] when non-NULL, else o + d*(start+end)/2 from (origins, directions, starts, ends, stride).
  * params: the MLP in torch layout (W0[16,10], b0[16], W1[1,16], b1[1]), fp32.
- * feat (nullable => inference): [L][B*S][2] fp32 saved for the backward.  nvo_prop_density_supported tells the host
+ * feat (nullable => inference): opaque buffer of nvo_prop_density_feat_floats(L, B*S) floats saved for the backward.  nvo_prop_density_supported tells the host
  * whether a (levels, hidden width, layers) combination has a fused kernel; others use the unfused operators.
  * backward: dtable (fp32, accumulate, nullable), dparams (accumulate, nullable) from ddensity [B*S].
  * ------------------------------------------------------------------------------------------- */
 int nvo_prop_density_supported(int32_t n_levels, int32_t hidden, int32_t n_layers);
-int nvo_prop_density_forward(const nvo_grid_desc* g, int32_t hidden, void* stream, int64_t B, int32_t S, const float* origins, const float* directions,
-                             const float* starts, const float* ends, int64_t stride, const float* positions, const void* table, const float* params,
-                             float* density, float* feat);
-int nvo_prop_density_backward(const nvo_grid_desc* g, int32_t hidden, void* stream, int64_t B, int32_t S, const float* origins, const float* directions,
-                              const float* starts, const float* ends, int64_t stride, const float* positions, const float* params, const float* feat,
-                              const float* ddensity, float* dtable, float* dparams);
+/* floats of the saved-feature buffer for n samples (level-major, padded to 128-sample blocks, permuted inside a block) */
+int64_t nvo_prop_density_feat_floats(int32_t n_levels, int64_t n);
+/* slot in [0,4): which constant-memory bank holds this network's MLP parameters while its kernels run (the call copies
+ * `params` there first, device to device, on `stream`); networks evaluated concurrently on different streams need distinct slots. */
+int nvo_prop_density_forward(const nvo_grid_desc* g, int32_t hidden, int32_t slot, void* stream, int64_t B, int32_t S, const float* origins,
+                             const float* directions, const float* starts, const float* ends, int64_t stride, const float* positions, const void* table,
+                             const float* params, float* density, float* feat);
+int nvo_prop_density_backward(const nvo_grid_desc* g, int32_t hidden, int32_t slot, void* stream, int64_t B, int32_t S, const float* origins,
+                              const float* directions, const float* starts, const float* ends, int64_t stride, const float* positions,
+                              const float* params, const float* feat, const float* ddensity, float* dtable, float* dparams);
 
 /* ---------------------------------------------------------------------------------------------
  * Field element-wise operators.

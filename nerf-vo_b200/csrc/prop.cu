@@ -47,32 +47,41 @@ __device__ __forceinline__ void sample_point(int64_t t, int S, const float* __re
     for (int a = 0; a < 3; ++a) p[a] = __fadd_rn(__ldg(o + 3 * r + a), __fdiv_rn(__fmul_rn(__ldg(d + 3 * r + a), se), 2.f));
 }
 
+// MLP parameters live in constant memory (one slot per proposal network, refreshed from the fp32 parameter buffer by a
+// device-to-device copy in front of every launch): every multiply-accumulate is then ONE FFMA with a constant-bank operand
+// instead of a shared-memory load + FFMA — these kernels are issue-bound, not bandwidth-bound.
+#define PROP_SLOTS 4
+#define PROP_SLOT_FLOATS 256
+__constant__ float c_prop[PROP_SLOTS][PROP_SLOT_FLOATS];
+
 // hidden layer + output pre-activation, accumulation order of the SIMT reference kernel (bias first, inputs ascending)
-template <int L>
-__device__ __forceinline__ float prop_mlp(const float* __restrict__ sp, const float* f, float* h) {
+template <int L, int SLOT>
+__device__ __forceinline__ float prop_mlp(const float* f, float* h) {
     using PL = PropLayout<L>;
-    float z = sp[PL::B1];
+    float z = c_prop[SLOT][PL::B1];
 #pragma unroll
     for (int j = 0; j < PH; ++j) {
-        float acc = sp[PL::B0 + j];
+        float acc = c_prop[SLOT][PL::B0 + j];
 #pragma unroll
-        for (int i = 0; i < PL::IN; ++i) acc = fmaf(sp[PL::W0 + j * PL::IN + i], f[i], acc);
+        for (int i = 0; i < PL::IN; ++i) acc = fmaf(c_prop[SLOT][PL::W0 + j * PL::IN + i], f[i], acc);
         h[j] = fmaxf(acc, 0.f);
     }
 #pragma unroll
-    for (int j = 0; j < PH; ++j) z = fmaf(sp[PL::W1 + j], h[j], z);
+    for (int j = 0; j < PH; ++j) z = fmaf(c_prop[SLOT][PL::W1 + j], h[j], z);
     return z;
 }
 
-template <int L, typename RowT>
-__global__ void __launch_bounds__(256) k_prop_fwd(const __grid_constant__ GridP p, int64_t N, int S, const float* __restrict__ o, const float* __restrict__ d,
-                                                  const float* __restrict__ starts, const float* __restrict__ ends, int64_t stride,
-                                                  const float* __restrict__ positions, const RowT* __restrict__ table, const float* __restrict__ params,
+// Saved-feature layout: level-major [L][Npad], and inside every block of 128 samples the sample j = 4*lane + g sits at
+// g*32 + lane, so the backward (one thread = 4 consecutive samples) reads 256 contiguous bytes per warp and level while
+// the forward (one thread = one sample) still writes whole 32-byte sectors.
+__device__ __forceinline__ int64_t feat_slot(int64_t t) { return (t & ~(int64_t)127) + ((t & 3) << 5) + ((t & 127) >> 2); }
+
+template <int L, int SLOT, typename RowT>
+__global__ void __launch_bounds__(256) k_prop_fwd(const __grid_constant__ GridP p, int64_t N, int64_t Npad, int S, const float* __restrict__ o,
+                                                  const float* __restrict__ d, const float* __restrict__ starts, const float* __restrict__ ends,
+                                                  int64_t stride, const float* __restrict__ positions, const RowT* __restrict__ table,
                                                   float* __restrict__ density, float2* __restrict__ feat) {
     using PL = PropLayout<L>;
-    __shared__ float sp[PL::NP];
-    for (int e = threadIdx.x; e < PL::NP; e += blockDim.x) sp[e] = __ldg(params + e);
-    __syncthreads();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= N) return;
     float pos[3], q[3];
@@ -80,34 +89,59 @@ __global__ void __launch_bounds__(256) k_prop_fwd(const __grid_constant__ GridP 
     const float m = contract_point(pos, q);
     const uint32_t mask = (1u << p.log2T) - 1u;
     float f[PL::IN];
+    const int64_t slot = feat_slot(t);
 #pragma unroll
     for (int l = 0; l < L; ++l) {
         const Corner c = make_corner(q[0], q[1], q[2], p.scale[l]);
         const float2 v = grid_level_forward(table + ((size_t)l << p.log2T), c, mask);
         f[2 * l] = v.x;
         f[2 * l + 1] = v.y;
-        if (feat) feat[(int64_t)l * N + t] = v;  // level-major: a warp stores 256 contiguous bytes per level
+        if (feat) feat[(int64_t)l * Npad + slot] = v;
     }
     float h[PH];
-    const float z = prop_mlp<L>(sp, f, h);
+    const float z = prop_mlp<L, SLOT>(f, h);
     density[t] = expf(z) * m;  // trunc_exp forward (activations.py:33) * selector (density_fields.py:115)
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// backward: one warp = 128 consecutive samples, one thread = G = 4 consecutive samples of a ray.
+//   pass A (per g): recompute the MLP from the saved features, dz -> dh -> df; park df and the normalised position in shared
+//                   memory; weight gradients by the staged outer-product reduction over the warp's 32 samples.
+//   pass B (per level): walk the thread's 4 samples in order, accumulating corner contributions in registers while the
+//                   target row stays the same and issuing ONE red.global.add.v2.f32 per run (samples along a ray stay in a
+//                   coarse cell for many steps; this costs ~10 instructions per corner where a warp-wide segmented scan
+//                   costs ~60).
+// ---------------------------------------------------------------------------------------------------------------------
 #define PROP_BWD_THREADS 128
+#define PROP_G 4
+
 template <int L>
-__global__ void __launch_bounds__(PROP_BWD_THREADS, 4) k_prop_bwd(const __grid_constant__ GridP p, int64_t N, int S, const float* __restrict__ o,
-                                                               const float* __restrict__ d, const float* __restrict__ starts, const float* __restrict__ ends,
-                                                               int64_t stride, const float* __restrict__ positions, const float* __restrict__ params,
-                                                               const float2* __restrict__ feat, const float* __restrict__ ddensity,
-                                                               float* __restrict__ dtable, float* __restrict__ dparams) {
+struct PropSmem {
     using PL = PropLayout<L>;
+    static constexpr int RS = 50;                               // staging row stride (floats), rows 8-byte aligned
+    static constexpr int S_DH = 0, S_F = 16, S_DZ = 16 + 2 * PL::CH, S_H = S_DZ + 2;  // dh[16] | fext[2CH] | dz,pad | hext[17]
+    static constexpr int DF = 0;                                // [G][IN][32]
+    static constexpr int Q = DF + PROP_G * PL::IN * 32;         // [G][3][32]
+    static constexpr int STAGE = Q + PROP_G * 3 * 32;           // [32][RS]
+    static constexpr int PER_WARP = STAGE + 32 * RS;
+    static_assert(S_H + PH + 1 <= RS, "staging row too small");
+};
+
+template <int L, int SLOT>
+__global__ void __launch_bounds__(PROP_BWD_THREADS, 3) k_prop_bwd(const __grid_constant__ GridP p, int64_t N, int64_t Npad, int S, const float* __restrict__ o,
+                                                                  const float* __restrict__ d, const float* __restrict__ starts,
+                                                                  const float* __restrict__ ends, int64_t stride, const float* __restrict__ positions,
+                                                                  const float2* __restrict__ feat, const float* __restrict__ ddensity,
+                                                                  float* __restrict__ dtable, float* __restrict__ dparams) {
+    using PL = PropLayout<L>;
+    using SM = PropSmem<L>;
     constexpr int NW = PROP_BWD_THREADS / 32;
-    __shared__ float sp[PL::NP];
-    __shared__ float stage_all[NW * 32 * PL::RS];
-    for (int e = threadIdx.x; e < PL::NP; e += blockDim.x) sp[e] = __ldg(params + e);
-    __syncthreads();
+    extern __shared__ __align__(16) float smem_f[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* stage = stage_all + warp * 32 * PL::RS;
+    float* ws = smem_f + warp * SM::PER_WARP;
+    float* dfs = ws + SM::DF;
+    float* qs = ws + SM::Q;
+    float* stage = ws + SM::STAGE;
     const uint32_t mask = (1u << p.log2T) - 1u;
     // wgrad roles: dW0ext[j][half*CH + c], c < CH  (column IN is the bias); lanes 0..PH: dW1ext[lane]
     const int wj = lane & (PH - 1), whalf = lane >> 4;
@@ -115,72 +149,114 @@ __global__ void __launch_bounds__(PROP_BWD_THREADS, 4) k_prop_bwd(const __grid_c
 #pragma unroll
     for (int c = 0; c < PL::CH; ++c) acc0[c] = 0.f;
     float acc1 = 0.f;
-
-    for (int64_t base = ((int64_t)blockIdx.x * NW + warp) * 32; base < N; base += (int64_t)gridDim.x * PROP_BWD_THREADS) {
-        const int64_t t = base + lane;
-        const bool valid = t < N;
-        const int64_t tt = valid ? t : N - 1;
-        float pos[3], q[3];
-        sample_point(tt, S, o, d, starts, ends, stride, positions, pos);
-        const float m = contract_point(pos, q);
-        float f[PL::IN];
+    const int64_t n_st = (N + 127) >> 7;
+    for (int64_t st = (int64_t)blockIdx.x * NW + warp; st < n_st; st += (int64_t)gridDim.x * NW) {
+        const int64_t base = st << 7;
+        unsigned any = 0u;
+        // ---------------- pass A ----------------
+#pragma unroll 1
+        for (int g = 0; g < PROP_G; ++g) {
+            const int64_t t = base + lane * PROP_G + g;
+            const bool valid = t < N;
+            const int64_t tt = valid ? t : N - 1;
+            float pos[3], q[3];
+            sample_point(tt, S, o, d, starts, ends, stride, positions, pos);
+            const float m = contract_point(pos, q);
 #pragma unroll
-        for (int l = 0; l < L; ++l) {
-            const float2 v = __ldg(feat + (int64_t)l * N + tt);
-            f[2 * l] = v.x;
-            f[2 * l + 1] = v.y;
-        }
-        float h[PH];
-        const float z = prop_mlp<L>(sp, f, h);
-        // d density / d z = selector * exp(clamp(z, -15, 15))   (activations.py:37-41)
-        const float dz = valid ? __ldg(ddensity + tt) * m * expf(fminf(fmaxf(z, -15.f), 15.f)) : 0.f;
-        if (__ballot_sync(0xffffffffu, dz != 0.f) == 0u) continue;  // nothing flows back from these 32 samples
-        float dh[PH];
-        float* row = stage + lane * PL::RS;
+            for (int a = 0; a < 3; ++a) qs[(g * 3 + a) * 32 + lane] = q[a];
+            float f[PL::IN];
 #pragma unroll
-        for (int j = 0; j < PH; ++j) dh[j] = h[j] > 0.f ? dz * sp[PL::W1 + j] : 0.f;
-#pragma unroll
-        for (int i = 0; i < PL::IN; ++i) {  // dL/df, parked in this lane's staging row until the scatter
-            float a = 0.f;
-#pragma unroll
-            for (int j = 0; j < PH; ++j) a = fmaf(sp[PL::W0 + j * PL::IN + i], dh[j], a);
-            row[PL::S_DF + i] = a;
-        }
-        // ---- weight gradients: stage this warp's 32 samples, reduce the outer products over them -----------------
-        if (dparams) {
-#pragma unroll
-            for (int j = 0; j < PH; ++j) row[PL::S_DH + j] = dh[j];
-#pragma unroll
-            for (int i = 0; i < 2 * PL::CH; ++i) row[PL::S_F + i] = i < PL::IN ? f[i < PL::IN ? i : 0] : (i == PL::IN ? 1.f : 0.f);  // [f | 1 | 0-pad]
-            row[PL::S_DZ] = dz;
-#pragma unroll
-            for (int j = 0; j < PH; ++j) row[PL::S_H + j] = h[j];
-            row[PL::S_H + PH] = 1.f;
-            __syncwarp();
-#pragma unroll 4
-            for (int s = 0; s < 32; ++s) {
-                const float* r = stage + s * PL::RS;
-                const float g = r[PL::S_DH + wj];
-#pragma unroll
-                for (int c = 0; c < PL::CH; ++c) acc0[c] = fmaf(g, r[PL::S_F + whalf * PL::CH + c], acc0[c]);
-                if (lane <= PH) acc1 = fmaf(r[PL::S_DZ], r[PL::S_H + lane], acc1);
+            for (int l = 0; l < L; ++l) {
+                const float2 v = __ldg(feat + (int64_t)l * Npad + base + g * 32 + lane);  // == feat_slot(t)
+                f[2 * l] = v.x;
+                f[2 * l + 1] = v.y;
             }
-            __syncwarp();
+            float h[PH];
+            const float z = prop_mlp<L, SLOT>(f, h);
+            // d density / d z = selector * exp(clamp(z, -15, 15))   (activations.py:37-41)
+            const float dz = valid ? __ldg(ddensity + tt) * m * expf(fminf(fmaxf(z, -15.f), 15.f)) : 0.f;
+            const unsigned nz = __ballot_sync(0xffffffffu, dz != 0.f);
+            any |= nz;
+            float dh[PH];
+#pragma unroll
+            for (int j = 0; j < PH; ++j) dh[j] = h[j] > 0.f ? dz * c_prop[SLOT][PL::W1 + j] : 0.f;
+#pragma unroll
+            for (int i = 0; i < PL::IN; ++i) {
+                float a = 0.f;
+#pragma unroll
+                for (int j = 0; j < PH; ++j) a = fmaf(c_prop[SLOT][PL::W0 + j * PL::IN + i], dh[j], a);
+                dfs[(g * PL::IN + i) * 32 + lane] = a;
+            }
+            if (dparams && nz != 0u) {
+                float* row = stage + lane * SM::RS;
+#pragma unroll
+                for (int j = 0; j < PH; ++j) row[SM::S_DH + j] = dh[j];
+#pragma unroll
+                for (int i = 0; i < 2 * PL::CH; ++i) row[SM::S_F + i] = i < PL::IN ? f[i < PL::IN ? i : 0] : (i == PL::IN ? 1.f : 0.f);  // [f | 1 | 0-pad]
+                row[SM::S_DZ] = dz;
+#pragma unroll
+                for (int j = 0; j < PH; ++j) row[SM::S_H + j] = h[j];
+                row[SM::S_H + PH] = 1.f;
+                __syncwarp();
+#pragma unroll 4
+                for (int s = 0; s < 32; ++s) {
+                    const float* r = stage + s * SM::RS;
+                    const float gj = r[SM::S_DH + wj];
+                    const float2* fe = reinterpret_cast<const float2*>(r + SM::S_F + whalf * PL::CH);
+#pragma unroll
+                    for (int c = 0; c < PL::CH / 2; ++c) {
+                        const float2 v = fe[c];
+                        acc0[2 * c] = fmaf(gj, v.x, acc0[2 * c]);
+                        acc0[2 * c + 1] = fmaf(gj, v.y, acc0[2 * c + 1]);
+                    }
+                    if (lane <= PH) acc1 = fmaf(r[SM::S_DZ], r[SM::S_H + lane], acc1);
+                }
+                __syncwarp();
+            }
         }
-        // ---- hash-table gradient: per level, warp-deduplicated scatter ------------------------------------------
-        if (dtable) {
+        // ---------------- pass B ----------------
+        if (dtable && any != 0u) {
 #pragma unroll 1
             for (int l = 0; l < L; ++l) {
-                const Corner c = make_corner(q[0], q[1], q[2], p.scale[l]);
-                grid_level_scatter(dtable + (((size_t)l << p.log2T) << 1), c, mask, row[PL::S_DF + 2 * l], row[PL::S_DF + 2 * l + 1], valid, lane);
+                float* slab = dtable + (((size_t)l << p.log2T) << 1);
+                const float scale = p.scale[l];
+                uint32_t pidx[8];
+                float a0[8], a1[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) pidx[k] = 0xffffffffu, a0[k] = 0.f, a1[k] = 0.f;
+#pragma unroll
+                for (int g = 0; g < PROP_G; ++g) {
+                    const float g0 = dfs[(g * PL::IN + 2 * l) * 32 + lane], g1 = dfs[(g * PL::IN + 2 * l + 1) * 32 + lane];
+                    const Corner c = make_corner(qs[(g * 3) * 32 + lane], qs[(g * 3 + 1) * 32 + lane], qs[(g * 3 + 2) * 32 + lane], scale);
+                    const float wx[2] = {1.f - c.ox, c.ox}, wy[2] = {1.f - c.oy, c.oy}, wz[2] = {1.f - c.oz, c.oz};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int sx = SEL_X(k), sy = SEL_Y(k), sz = SEL_Z(k);
+                        const float w = wz[sz] * wy[sy] * wx[sx];
+                        const uint32_t idx = corner_index(c, sx, sy, sz, mask);
+                        if (idx != pidx[k]) {
+                            if (a0[k] != 0.f || a1[k] != 0.f) nvo_red_add_v2(slab + 2 * (size_t)pidx[k], a0[k], a1[k]);
+                            pidx[k] = idx;
+                            a0[k] = 0.f;
+                            a1[k] = 0.f;
+                        }
+                        a0[k] = fmaf(g0, w, a0[k]);
+                        a1[k] = fmaf(g1, w, a1[k]);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (a0[k] != 0.f || a1[k] != 0.f) nvo_red_add_v2(slab + 2 * (size_t)pidx[k], a0[k], a1[k]);
             }
         }
+        __syncwarp();
     }
     if (!dparams) return;
     // ---- CTA reduction of the register accumulators, one atomicAdd per parameter -----------------------------------
     __syncthreads();
-    float* red = stage_all;  // [NW][NP]
+    float* red = smem_f;  // [NW][NP]
     float* mine = red + warp * PL::NP;
+    __syncthreads();
 #pragma unroll
     for (int c = 0; c < PL::CH; ++c) {
         const int col = whalf * PL::CH + c;
@@ -217,7 +293,27 @@ static int prop_params(const nvo_grid_desc* g, int32_t hidden, GridP* p) {
 
 extern "C" int nvo_prop_density_supported(int32_t n_levels, int32_t hidden, int32_t n_layers) { return n_levels == 5 && hidden == PH && n_layers == 2; }
 
-extern "C" int nvo_prop_density_forward(const nvo_grid_desc* g, int32_t hidden, void* stream, int64_t B, int32_t S, const float* origins,
+extern "C" int64_t nvo_prop_density_feat_floats(int32_t n_levels, int64_t n) { return (int64_t)n_levels * ((n + 127) / 128 * 128) * 2; }
+
+static int upload_params(int slot, const float* params, cudaStream_t st) {
+    NVO_CHECK(slot >= 0 && slot < PROP_SLOTS, "prop_density: slot %d out of range [0,%d)", slot, PROP_SLOTS);
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_prop, params, sizeof(float) * PropLayout<5>::NP, sizeof(float) * PROP_SLOT_FLOATS * slot,
+                                            cudaMemcpyDeviceToDevice, st);
+    NVO_CHECK(e == cudaSuccess, "prop_density: parameter upload failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+template <int SLOT>
+static void launch_fwd(const nvo_grid_desc* g, const GridP& p, cudaStream_t st, int64_t N, int64_t Npad, int S, const float* o, const float* d, const float* s,
+                       const float* e, int64_t stride, const float* positions, const void* table, float* density, float* feat) {
+    const unsigned int grid = nvo_blocks(N, 256);
+    if (g->table_dtype == NVO_F32)
+        k_prop_fwd<5, SLOT, float2><<<grid, 256, 0, st>>>(p, N, Npad, S, o, d, s, e, stride, positions, (const float2*)table, density, (float2*)feat);
+    else
+        k_prop_fwd<5, SLOT, __half2><<<grid, 256, 0, st>>>(p, N, Npad, S, o, d, s, e, stride, positions, (const __half2*)table, density, (float2*)feat);
+}
+
+extern "C" int nvo_prop_density_forward(const nvo_grid_desc* g, int32_t hidden, int32_t slot, void* stream, int64_t B, int32_t S, const float* origins,
                                         const float* directions, const float* starts, const float* ends, int64_t stride, const float* positions,
                                         const void* table, const float* params, float* density, float* feat) {
     GridP p;
@@ -226,20 +322,32 @@ extern "C" int nvo_prop_density_forward(const nvo_grid_desc* g, int32_t hidden, 
     if (B == 0) return 0;
     NVO_CHECK(table && params && density, "prop_density_forward: null pointer");
     NVO_CHECK(positions || (origins && directions && starts && ends), "prop_density_forward: need positions or rays + intervals");
-    const int64_t N = B * S;
+    const int64_t N = B * S, Npad = (N + 127) / 128 * 128;
     cudaStream_t st = (cudaStream_t)stream;
-    const unsigned int grid = nvo_blocks(N, 256);
-    if (g->table_dtype == NVO_F32)
-        k_prop_fwd<5, float2><<<grid, 256, 0, st>>>(p, N, S, origins, directions, starts, ends, stride, positions, (const float2*)table, params, density,
-                                                   (float2*)feat);
-    else
-        k_prop_fwd<5, __half2><<<grid, 256, 0, st>>>(p, N, S, origins, directions, starts, ends, stride, positions, (const __half2*)table, params, density,
-                                                    (float2*)feat);
+    if (int e = upload_params(slot, params, st)) return e;
+    switch (slot) {
+        case 0: launch_fwd<0>(g, p, st, N, Npad, S, origins, directions, starts, ends, stride, positions, table, density, feat); break;
+        case 1: launch_fwd<1>(g, p, st, N, Npad, S, origins, directions, starts, ends, stride, positions, table, density, feat); break;
+        case 2: launch_fwd<2>(g, p, st, N, Npad, S, origins, directions, starts, ends, stride, positions, table, density, feat); break;
+        default: launch_fwd<3>(g, p, st, N, Npad, S, origins, directions, starts, ends, stride, positions, table, density, feat); break;
+    }
     NVO_CUDA_LAUNCH_CHECK("prop_density_forward");
     return 0;
 }
 
-extern "C" int nvo_prop_density_backward(const nvo_grid_desc* g, int32_t hidden, void* stream, int64_t B, int32_t S, const float* origins,
+template <int SLOT>
+static int launch_bwd(const GridP& p, cudaStream_t st, int64_t N, int64_t Npad, int S, const float* o, const float* d, const float* s, const float* e,
+                      int64_t stride, const float* positions, const float* feat, const float* ddensity, float* dtable, float* dparams) {
+    const size_t smem = sizeof(float) * PropSmem<5>::PER_WARP * (PROP_BWD_THREADS / 32);
+    cudaError_t err = cudaFuncSetAttribute(k_prop_bwd<5, SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    NVO_CHECK(err == cudaSuccess, "prop_density_backward: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+    const int64_t blocks = ((N + 127) / 128 + PROP_BWD_THREADS / 32 - 1) / (PROP_BWD_THREADS / 32);
+    const unsigned int grid = (unsigned int)min(blocks, (int64_t)nvo_sm_count() * 8);
+    k_prop_bwd<5, SLOT><<<grid, PROP_BWD_THREADS, smem, st>>>(p, N, Npad, S, o, d, s, e, stride, positions, (const float2*)feat, ddensity, dtable, dparams);
+    return 0;
+}
+
+extern "C" int nvo_prop_density_backward(const nvo_grid_desc* g, int32_t hidden, int32_t slot, void* stream, int64_t B, int32_t S, const float* origins,
                                          const float* directions, const float* starts, const float* ends, int64_t stride, const float* positions,
                                          const float* params, const float* feat, const float* ddensity, float* dtable, float* dparams) {
     GridP p;
@@ -248,11 +356,17 @@ extern "C" int nvo_prop_density_backward(const nvo_grid_desc* g, int32_t hidden,
     if (B == 0) return 0;
     NVO_CHECK(params && feat && ddensity, "prop_density_backward: null pointer");
     NVO_CHECK(positions || (origins && directions && starts && ends), "prop_density_backward: need positions or rays + intervals");
-    const int64_t N = B * S;
-    const int64_t warps = (N + 31) / 32;
-    const unsigned int grid = (unsigned int)min((warps + PROP_BWD_THREADS / 32 - 1) / (PROP_BWD_THREADS / 32), (int64_t)nvo_sm_count() * 12);
-    k_prop_bwd<5><<<grid, PROP_BWD_THREADS, 0, (cudaStream_t)stream>>>(p, N, S, origins, directions, starts, ends, stride, positions, params,
-                                                                      (const float2*)feat, ddensity, dtable, dparams);
+    const int64_t N = B * S, Npad = (N + 127) / 128 * 128;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int e = upload_params(slot, params, st)) return e;  // re-uploaded: another network may have used the slot since the forward
+    int rc;
+    switch (slot) {
+        case 0: rc = launch_bwd<0>(p, st, N, Npad, S, origins, directions, starts, ends, stride, positions, feat, ddensity, dtable, dparams); break;
+        case 1: rc = launch_bwd<1>(p, st, N, Npad, S, origins, directions, starts, ends, stride, positions, feat, ddensity, dtable, dparams); break;
+        case 2: rc = launch_bwd<2>(p, st, N, Npad, S, origins, directions, starts, ends, stride, positions, feat, ddensity, dtable, dparams); break;
+        default: rc = launch_bwd<3>(p, st, N, Npad, S, origins, directions, starts, ends, stride, positions, feat, ddensity, dtable, dparams); break;
+    }
+    if (rc) return rc;
     NVO_CUDA_LAUNCH_CHECK("prop_density_backward");
     return 0;
 }

@@ -57,6 +57,8 @@ class Field(nn.Module):
 class HashMLPDensityField(Field):
     """Proposal density field (NS/fields/density_fields.py:34-119)."""
 
+    _next_slot = 0
+
     def __init__(self, aabb: torch.Tensor, num_layers: int = 2, hidden_dim: int = 64, spatial_distortion: Optional[nn.Module] = None,
                  use_linear: bool = False, num_levels: int = 8, max_res: int = 1024, base_res: int = 16, log2_hashmap_size: int = 18,
                  features_per_level: int = 2, implementation: str = "nvo_b200") -> None:
@@ -79,6 +81,9 @@ class HashMLPDensityField(Field):
         else:
             self.linear = MLP(in_dim=self.encoding.get_out_dim(), num_layers=1, layer_width=1, out_dim=1, out_activation="trunc_exp")
         self._fused_ok = None
+        # constant-memory bank of the fused kernels: consecutive fields get different banks (proposal network 0 / 1)
+        self._slot = HashMLPDensityField._next_slot % 4
+        HashMLPDensityField._next_slot += 1
 
     def _net(self) -> MLP:
         return self.mlp_base[1] if not self.use_linear else self.linear
@@ -94,7 +99,7 @@ class HashMLPDensityField(Field):
             # one kernel: contraction, hash grid, MLP, trunc_exp * selector (csrc/prop.cu)
             net._repack()
             n = positions.numel() // 3
-            density = ops.prop_density(self.encoding.hash_table, self.encoding.spec, net.spec, net._flat_param_list(), n, 1, positions=positions)
+            density = ops.prop_density(self.encoding.hash_table, self.encoding.spec, net.spec, net._flat_param_list(), n, 1, positions=positions, slot=self._slot)
             return density.view(*positions.shape[:-1], 1), None
         x, sel = ops.contract_normalize(positions)
         feat = self.encoding(x)
@@ -112,7 +117,7 @@ class HashMLPDensityField(Field):
         net._repack()
         o = fr.origins.reshape(-1, 3).contiguous()
         d = fr.directions.reshape(-1, 3).contiguous()
-        density = ops.prop_density(self.encoding.hash_table, self.encoding.spec, net.spec, net._flat_param_list(), iv.B, iv.S, origins=o, directions=d, iv=iv)
+        density = ops.prop_density(self.encoding.hash_table, self.encoding.spec, net.spec, net._flat_param_list(), iv.B, iv.S, origins=o, directions=d, iv=iv, slot=self._slot)
         return density.view(iv.B, iv.S, 1)
 
     def get_outputs(self, ray_samples: RaySamples, density_embedding: Optional[torch.Tensor] = None) -> dict:

@@ -320,13 +320,13 @@ class _PropDensity(torch.autograd.Function):
     """density [B,S] at the samples of `iv` on rays (origins, directions), or at explicit `positions` [B*S,3]."""
 
     @staticmethod
-    def forward(ctx, table, gspec, hidden, origins, directions, iv, positions, B, S, *params):
+    def forward(ctx, table, gspec, hidden, slot, origins, directions, iv, positions, B, S, *params):
         flat = _flat_of(params)
         dev = table.device
         need = any(ctx.needs_input_grad)  # False under no_grad (eval, frozen proposal steps): no features saved
         n = B * S
         density = torch.empty((B, S), dtype=torch.float32, device=dev)
-        feat = torch.empty((gspec.n_levels, n, 2), dtype=torch.float32, device=dev) if need else None
+        feat = torch.empty(int(_lib.load().nvo_prop_density_feat_floats(gspec.n_levels, n)), dtype=torch.float32, device=dev) if need else None
         if positions is not None:
             positions = check(positions.reshape(-1, 3).contiguous(), "positions", torch.float32, (n, 3))
             s = e = None
@@ -335,10 +335,10 @@ class _PropDensity(torch.autograd.Function):
             check(origins, "origins", torch.float32, (B, 3))
             check(directions, "directions", torch.float32, (B, 3))
             s, e, stride = iv.triple()
-        call("nvo_prop_density_forward", gspec.desc(table.dtype, torch.float32), hidden, B, S, origins, directions, s, e, stride, positions, table, flat,
+        call("nvo_prop_density_forward", gspec.desc(table.dtype, torch.float32), hidden, slot, B, S, origins, directions, s, e, stride, positions, table, flat,
              density, feat)
         ctx.save_for_backward(table, flat, feat, origins, directions, positions)
-        ctx.iv, ctx.gspec, ctx.hidden, ctx.B, ctx.S, ctx.n_tensors = iv, gspec, hidden, B, S, len(params)
+        ctx.iv, ctx.gspec, ctx.hidden, ctx.slot, ctx.B, ctx.S, ctx.n_tensors = iv, gspec, hidden, slot, B, S, len(params)
         ctx.table_main_grad = getattr(table, "_nvo_main_grad", None)
         ctx.mlp_main_grad = getattr(params[0], "_nvo_main_grad", None)
         ctx.mspec_shapes = [tuple(p.shape) for p in params]
@@ -347,7 +347,7 @@ class _PropDensity(torch.autograd.Function):
     @staticmethod
     def backward(ctx, ddensity):
         table, flat, feat, origins, directions, positions = ctx.saved_tensors
-        need_dt, need_dp = ctx.needs_input_grad[0], any(ctx.needs_input_grad[9:])
+        need_dt, need_dp = ctx.needs_input_grad[0], any(ctx.needs_input_grad[10:])
         dev = table.device
         dtable = dflat = None
         if need_dt:
@@ -360,7 +360,7 @@ class _PropDensity(torch.autograd.Function):
         else:
             s, e, stride = ctx.iv.triple()
         ddensity = ddensity.contiguous()
-        args = ("nvo_prop_density_backward", ctx.gspec.desc(table.dtype, torch.float32), ctx.hidden, ctx.B, ctx.S, origins, directions, s, e, stride, positions,
+        args = ("nvo_prop_density_backward", ctx.gspec.desc(table.dtype, torch.float32), ctx.hidden, ctx.slot, ctx.B, ctx.S, origins, directions, s, e, stride, positions,
                 flat, feat, ddensity, dtable, dflat)
         if leaf_streams.enabled and (not need_dt or dtable is ctx.table_main_grad) and (not need_dp or dflat is ctx.mlp_main_grad):
             with leaf_streams.fork(table, flat, feat, origins, directions, positions, ddensity, ctx.iv):
@@ -379,11 +379,12 @@ class _PropDensity(torch.autograd.Function):
                 k = int(np.prod(shp))
                 grads.append(dflat[off:off + k].view(shp))
                 off += k
-        return (dtable, None, None, None, None, None, None, None, None, *grads)
+        return (dtable, None, None, None, None, None, None, None, None, None, *grads)
 
 
-def prop_density(table, gspec: GridSpec, mspec: MlpSpec, params, B: int, S: int, origins=None, directions=None, iv=None, positions=None):
-    return _PropDensity.apply(table, gspec, mspec.dims[0], origins, directions, iv, positions, B, S, *params)
+def prop_density(table, gspec: GridSpec, mspec: MlpSpec, params, B: int, S: int, origins=None, directions=None, iv=None, positions=None, slot: int = 0):
+    """slot: constant-memory bank (0..3) for the MLP parameters; give networks that may run concurrently distinct slots."""
+    return _PropDensity.apply(table, gspec, mspec.dims[0], int(slot) % 4, origins, directions, iv, positions, B, S, *params)
 
 
 # ------------------------------------------------------------------------------------------------
