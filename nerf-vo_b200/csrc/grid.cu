@@ -106,23 +106,36 @@ __global__ void __launch_bounds__(256) k_grid_fwd_tmh(const __grid_constant__ Gr
     y[(tile * nch + c) * 128 + r] = u;
 }
 
-// Backward scatter: one thread per SAMPLE looping over the levels, so that the 32 lanes of a warp are 32 consecutive samples
-// (neighbours along a ray) and equal target rows form runs that seg_red_add_v2 collapses before touching L2.
+// Backward scatter: one thread walks GB = 4 consecutive samples (neighbours along a ray) through a group of 4 levels, merging
+// equal-cell runs in registers and pairing the x-floor / x-ceil rows into 16-byte reductions (ScatterRun, grid_common.cuh).
+// blockIdx.y = level group, so all 16 levels of a sample quad are in flight on different CTAs.
+#define GB 4
 template <typename OutT>
-__global__ void __launch_bounds__(256) k_grid_bwd(const __grid_constant__ GridP p, int64_t n, const float* __restrict__ x,
+__global__ void __launch_bounds__(128) k_grid_bwd(const __grid_constant__ GridP p, int64_t n, const float* __restrict__ x,
                                                   const OutT* __restrict__ dy, float* __restrict__ dtable, int tmf) {
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const bool valid = s < n;
-    const int64_t ss = valid ? s : n - 1;
-    const float px = __ldg(x + 3 * ss), py = __ldg(x + 3 * ss + 1), pz = __ldg(x + 3 * ss + 2);
+    const int64_t t0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * GB;
+    if (t0 >= n) return;
+    float q[GB][3];
+#pragma unroll
+    for (int g = 0; g < GB; ++g) {
+        const int64_t t = min(t0 + g, n - 1);
+        q[g][0] = __ldg(x + 3 * t), q[g][1] = __ldg(x + 3 * t + 1), q[g][2] = __ldg(x + 3 * t + 2);
+    }
     const uint32_t mask = (1u << p.log2T) - 1u;
-    for (int l = 0; l < p.L; ++l) {
-        float2 g = load_dy(dy, ss, l, p.L, tmf);
-        if (!valid) g = make_float2(0.f, 0.f);
-        if (__ballot_sync(0xffffffffu, g.x != 0.f || g.y != 0.f) == 0u) continue;  // whole warp masked / padded at this level
-        const Corner c = make_corner(px, py, pz, p.scale[l]);
-        grid_level_scatter(dtable + (((size_t)l << p.log2T) << 1), c, mask, g.x, g.y, valid, lane);
+    const int l_end = min(p.L, (int)(blockIdx.y + 1) * 4);
+    for (int l = blockIdx.y * 4; l < l_end; ++l) {
+        float* slab = dtable + (((size_t)l << p.log2T) << 1);
+        const float scale = p.scale[l];
+        ScatterRun run;
+        run.reset();
+#pragma unroll
+        for (int g = 0; g < GB; ++g) {
+            if (t0 + g >= n) break;
+            const float2 gr = load_dy(dy, t0 + g, l, p.L, tmf);
+            if (gr.x == 0.f && gr.y == 0.f) continue;  // adding zeros changes nothing (masked / padded samples)
+            run.add(slab, make_corner(q[g][0], q[g][1], q[g][2], scale), mask, gr.x, gr.y);
+        }
+        run.finish(slab);
     }
 }
 
@@ -246,11 +259,11 @@ extern "C" int nvo_grid_backward(const nvo_grid_desc* d, void* stream, int64_t n
     if (n == 0) return 0;
     NVO_CHECK(x && dy && dtable, "grid_backward: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    const unsigned int g = nvo_blocks(n, 256);
+    const dim3 g(nvo_blocks((n + GB - 1) / GB, 128), (unsigned int)((p.L + 3) / 4));
     if (d->out_dtype == NVO_F32 || d->out_dtype == NVO_F32_TMF)
-        k_grid_bwd<float><<<g, 256, 0, st>>>(p, n, x, (const float*)dy, dtable, d->out_dtype == NVO_F32_TMF);
+        k_grid_bwd<float><<<g, 128, 0, st>>>(p, n, x, (const float*)dy, dtable, d->out_dtype == NVO_F32_TMF);
     else
-        k_grid_bwd<__half><<<g, 256, 0, st>>>(p, n, x, (const __half*)dy, dtable, 0);
+        k_grid_bwd<__half><<<g, 128, 0, st>>>(p, n, x, (const __half*)dy, dtable, 0);
     NVO_CUDA_LAUNCH_CHECK("grid_backward");
     return 0;
 }

@@ -100,41 +100,63 @@ __device__ __forceinline__ float contract_point(const float* p, float* q) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Warp-level pre-reduction of the gradient scatter.  The 32 lanes of a warp hold 32 CONSECUTIVE samples (along a ray),
-// which at coarse levels fall into the same grid cell in long runs; one `red` per run instead of one per lane removes
-// most of the same-address serialisation in the L2 atomic units.  Runs = maximal stretches of adjacent lanes whose
-// target row index is equal; a segmented Hillis-Steele scan sums each run into its last lane, which issues the
-// reduction.  The scan depth adapts to the longest run in the warp (0 steps when every lane hits a different row).
-// All 32 lanes must call this (lanes without work pass valid = false and a = b = 0).
+// Sequential run-merging scatter (measured on B200, tools/atomics_probe.cu: L2 reductions retire at ~200 G requests/s whatever
+// their width — f32, v2.f32, v4.f32 cost the same — lanes of one instruction hitting the SAME row are NOT merged by the
+// hardware, while one red.v4.f32 updates two adjacent rows for the price of one).  So:
+//   * a thread walks G consecutive samples of a ray and keeps, per (y,z) corner combination, the pending sum for the x-floor and
+//     x-ceil rows in registers while the cell does not change (consecutive samples share coarse cells);
+//   * on a change (and at the end) the pair is flushed: rows r and r^1 (x-floor even) go out as ONE 16-byte red.v4.f32,
+//     otherwise as two red.v2.f32.
 // ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void seg_red_add_v2(float* __restrict__ slab, uint32_t idx, float a, float b, bool valid, int lane) {
-    const uint32_t key = valid ? idx : (0x80000000u | (uint32_t)lane);  // invalid lanes never merge with anything
-    const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
-    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != key);
-    const unsigned cont = ~heads;  // bit i set: lane i continues the run of lane i-1
-    if (cont != 0u) {
-        const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
-        const unsigned r1 = cont & (cont << 1), r2 = r1 & (r1 << 2), r3 = r2 & (r2 << 4), r4 = r3 & (r3 << 8);
-        const int nsteps = 1 + (r1 != 0u) + (r2 != 0u) + (r3 != 0u) + (r4 != 0u);
-        for (int k = 0, o = 1; k < nsteps; ++k, o <<= 1) {
-            const float ta = __shfl_up_sync(0xffffffffu, a, o), tb = __shfl_up_sync(0xffffffffu, b, o);
-            if (lane - o >= start) {
-                a += ta;
-                b += tb;
-            }
-        }
-    }
-    const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
-    if (tail && valid && (a != 0.f || b != 0.f)) nvo_red_add_v2(slab + 2 * (size_t)idx, a, b);
+__device__ __forceinline__ void nvo_red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// scatter of one (sample, level): dL/dy = (g0, g1) into the 8 corner rows with the trilinear weights
-__device__ __forceinline__ void grid_level_scatter(float* __restrict__ slab, const Corner& c, uint32_t mask, float g0, float g1, bool valid, int lane) {
-    const float wx[2] = {1.f - c.ox, c.ox}, wy[2] = {1.f - c.oy, c.oy}, wz[2] = {1.f - c.oz, c.oz};
+struct ScatterRun {
+    uint32_t pf[4], pc[4];  // pending x-floor / x-ceil rows per (y,z) combination
+    float af0[4], af1[4], ac0[4], ac1[4];
+    __device__ __forceinline__ void reset() {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int sx = SEL_X(k), sy = SEL_Y(k), sz = SEL_Z(k);
-        const float w = wz[sz] * wy[sy] * wx[sx];
-        seg_red_add_v2(slab, corner_index(c, sx, sy, sz, mask), g0 * w, g1 * w, valid, lane);
+        for (int j = 0; j < 4; ++j) pf[j] = pc[j] = 0xffffffffu, af0[j] = af1[j] = ac0[j] = ac1[j] = 0.f;
     }
-}
+    __device__ __forceinline__ void flush(float* __restrict__ slab, int j) {
+        const bool nf = af0[j] != 0.f || af1[j] != 0.f, nc = ac0[j] != 0.f || ac1[j] != 0.f;
+        if (!nf && !nc) return;
+        if ((pf[j] ^ pc[j]) == 1u) {  // adjacent rows of one aligned 16-byte pair
+            if (pf[j] < pc[j])
+                nvo_red_add_v4(slab + 2 * (size_t)pf[j], af0[j], af1[j], ac0[j], ac1[j]);
+            else
+                nvo_red_add_v4(slab + 2 * (size_t)pc[j], ac0[j], ac1[j], af0[j], af1[j]);
+        } else {
+            if (nf) nvo_red_add_v2(slab + 2 * (size_t)pf[j], af0[j], af1[j]);
+            if (nc) nvo_red_add_v2(slab + 2 * (size_t)pc[j], ac0[j], ac1[j]);
+        }
+    }
+    // add one sample's (g0, g1) at corner geometry c
+    __device__ __forceinline__ void add(float* __restrict__ slab, const Corner& c, uint32_t mask, float g0, float g1) {
+        const float wx0 = 1.f - c.ox, wx1 = c.ox;
+        const float wy[2] = {1.f - c.oy, c.oy}, wz[2] = {1.f - c.oz, c.oz};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int sy = j & 1, sz = j >> 1;
+            const uint32_t hyz = c.hy[sy] ^ c.hz[sz];
+            const uint32_t idf = (c.hx[0] ^ hyz) & mask, idc = (c.hx[1] ^ hyz) & mask;
+            if (idf != pf[j] || idc != pc[j]) {
+                flush(slab, j);
+                pf[j] = idf;
+                pc[j] = idc;
+                af0[j] = af1[j] = ac0[j] = ac1[j] = 0.f;
+            }
+            const float wyz = wz[sz] * wy[sy];
+            const float wf = wyz * wx0, wc = wyz * wx1;
+            af0[j] = fmaf(g0, wf, af0[j]);
+            af1[j] = fmaf(g1, wf, af1[j]);
+            ac0[j] = fmaf(g0, wc, ac0[j]);
+            ac1[j] = fmaf(g1, wc, ac1[j]);
+        }
+    }
+    __device__ __forceinline__ void finish(float* __restrict__ slab) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) flush(slab, j);
+    }
+};

@@ -7,12 +7,12 @@
 // registers removes every intermediate tensor (positions, normalised x, selector, features, hidden activations) from HBM.
 // The 64-wide field networks are the tensor-core path (mlp_tc.cu).
 //
-// Decomposition: one thread per sample; the 32 lanes of a warp are 32 consecutive samples of a ray, so gathers of the
-// coarse levels hit the same sectors (L1) and the backward scatter collapses equal-row runs in the warp before issuing
-// `red.global.add.v2.f32` (grid_common.cuh).  Weight gradients: every warp stages (dh, [f,1], dz, [h,1]) of its 32 samples in
-// shared memory and the lanes reduce the outer products over the 32 samples into registers (lane = (hidden unit, half of
-// the input columns)); registers are summed across the CTA's warps at the end and flushed with one atomicAdd per
-// parameter per CTA.
+// Decomposition: forward one thread per sample (the 32 lanes of a warp are 32 consecutive samples of a ray, so gathers of the
+// coarse levels hit the same sectors in L1); backward one thread per 4 consecutive samples, which merges equal-cell runs in
+// registers before issuing paired 16-byte reductions (ScatterRun, grid_common.cuh).  Weight gradients: every warp stages
+// (dh, [f,1], dz, [h,1]) of 32 samples in shared memory and the lanes reduce the outer products over them into registers
+// (lane = (hidden unit, half of the input columns)); registers are summed across the CTA's warps at the end and flushed with
+// one atomicAdd per parameter per CTA.
 #include "grid_common.cuh"
 
 #define PH 16  // hidden width (nerfacto proposal networks, NS/models/nerfacto.py:93-97)
@@ -220,33 +220,16 @@ __global__ void __launch_bounds__(PROP_BWD_THREADS, 3) k_prop_bwd(const __grid_c
             for (int l = 0; l < L; ++l) {
                 float* slab = dtable + (((size_t)l << p.log2T) << 1);
                 const float scale = p.scale[l];
-                uint32_t pidx[8];
-                float a0[8], a1[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) pidx[k] = 0xffffffffu, a0[k] = 0.f, a1[k] = 0.f;
+                ScatterRun run;
+                run.reset();
 #pragma unroll
                 for (int g = 0; g < PROP_G; ++g) {
                     const float g0 = dfs[(g * PL::IN + 2 * l) * 32 + lane], g1 = dfs[(g * PL::IN + 2 * l + 1) * 32 + lane];
+                    if (g0 == 0.f && g1 == 0.f) continue;  // masked / invalid sample: contributes nothing, must not break a run either
                     const Corner c = make_corner(qs[(g * 3) * 32 + lane], qs[(g * 3 + 1) * 32 + lane], qs[(g * 3 + 2) * 32 + lane], scale);
-                    const float wx[2] = {1.f - c.ox, c.ox}, wy[2] = {1.f - c.oy, c.oy}, wz[2] = {1.f - c.oz, c.oz};
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int sx = SEL_X(k), sy = SEL_Y(k), sz = SEL_Z(k);
-                        const float w = wz[sz] * wy[sy] * wx[sx];
-                        const uint32_t idx = corner_index(c, sx, sy, sz, mask);
-                        if (idx != pidx[k]) {
-                            if (a0[k] != 0.f || a1[k] != 0.f) nvo_red_add_v2(slab + 2 * (size_t)pidx[k], a0[k], a1[k]);
-                            pidx[k] = idx;
-                            a0[k] = 0.f;
-                            a1[k] = 0.f;
-                        }
-                        a0[k] = fmaf(g0, w, a0[k]);
-                        a1[k] = fmaf(g1, w, a1[k]);
-                    }
+                    run.add(slab, c, mask, g0, g1);
                 }
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (a0[k] != 0.f || a1[k] != 0.f) nvo_red_add_v2(slab + 2 * (size_t)pidx[k], a0[k], a1[k]);
+                run.finish(slab);
             }
         }
         __syncwarp();
