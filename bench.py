@@ -27,6 +27,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the same kernel/shape
+# (profiles/r01_ncu_grid_fwd_tmh.md); None until a capture exists
+RECORDED_TRAFFIC = {"k_grid_fwd_tmh": None}
+
 METRIC = "nerf_mapping_train_rays_per_s"
 UNIT = "rays/s"
 RAYS_PER_GPU = 4096
@@ -200,27 +204,31 @@ def run_ours(args):
 
     roofline = cpu = None
     if rank == 0:
-        # dominant-kernel roofline: the main hash-grid forward (16 levels, fp32 table) on this workload's final-level sample count
+        # roofline kernel: the main hash-grid forward of this step (16 levels, fp32 table of 2^19 rows, fp16 TMH output feeding the
+        # tensor-core MLP) on the step's final-level sample count, L2 flushed between launches, CUDA events on the launching stream
         peak, peak_src = load_peaks()
         N = B * 48
         enc = model.field.mlp_base.encoder
         x = torch.rand(N, 3, device=dev)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+        table = enc.hash_table.detach()
         evs = []
         for i in range(3 + 20):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            nv.ops.grid_forward(x, enc.hash_table.detach(), enc.spec)
+            nv.ops.grid_forward(x, table, enc.spec, "tmh")
             e1.record()
             evs.append((e0, e1))
         torch.cuda.synchronize()
         t_ms = sum(a.elapsed_time(b) for a, b in evs[3:]) / 20
-        alg_bytes = (12 + 16 * 8 * 2 * 4 + 16 * 2 * 4) * N  # 1164 B/sample for the fp32 main grid
+        per_sample = 12 + 16 * 8 * 2 * 4 + 16 * 2 * 2  # xyz + 16 levels x 8 corners x 2 fp32 features + 32 fp16 outputs
+        alg_bytes = per_sample * N
         ach = alg_bytes / (t_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_grid_fwd<float2,float> (main grid forward, L2 flushed between launches)", "achieved": ach, "peak": peak,
-                    "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src, "launch_us": t_ms * 1e3,
-                    "algorithmic_bytes_per_launch": alg_bytes}
+        roofline = {"bound": "hbm", "kernel": "k_grid_fwd_tmh<float2> (main hash grid forward, fp32 table -> fp16 TMH tiles; L2 flushed between launches)",
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": RECORDED_TRAFFIC.get("k_grid_fwd_tmh"),
+                    "peak_source": peak_src, "launch_us": t_ms * 1e3, "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_per_sample": per_sample,
+                    "samples_per_launch": N}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             v, sec = cpu_port_rays_per_s(1024, 2, 1, threads)
@@ -230,8 +238,9 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": rays_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_gpu": B, "global_rays": world * B, "parallelism": f"dp{world} (ray sharding, flat-gradient NCCL all-reduce)",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "precision": "fp16 tensor-core operands (hash features, field MLPs) with fp32 accumulation; fp32 tables, proposal networks, per-ray ops, optimizer",
+                       "rays_per_gpu": B, "global_rays": world * B, "parallelism": f"dp{world} (ray sharding, flat-gradient NCCL all-reduce)",
                        "step": "zero-grad + forward + losses + backward + fused Adam, proposal networks updated every step",
                        "l2": "no explicit flush: parameters+gradients+Adam state = 290 MB per step exceed the 126 MB L2",
                        "cuda_graph": not args.no_graph},

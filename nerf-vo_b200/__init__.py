@@ -1,6 +1,6 @@
 """nvo_b200 — B200-native (sm_100a) kernels for NeRF-VO's NeRF mapping hot path, behind the reference's own operator
 API (tinycudann modules; nerfstudio fields / samplers / renderers / losses).  See DESIGN.md and include/nvo_b200.h."""
-from . import _lib, ops  # noqa: F401
+from . import _lib, ops, sharding  # noqa: F401
 from . import tcnn_api  # noqa: F401
 from .field_components import MLP, Embedding, HashEncoding, MLPWithHashEncoding, NeRFEncoding, SceneContraction, SHEncoding, trunc_exp  # noqa: F401
 from .fields import FieldHeadNames, HashMLPDensityField, NerfactoField  # noqa: F401

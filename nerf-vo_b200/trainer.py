@@ -15,7 +15,7 @@ from typing import Dict, List, Optional
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import ops, sharding
 from .field_components import repack
 from .model import ExtendedNerfactoModel
 from .rays import RayBundle
@@ -156,8 +156,7 @@ class MappingTrainer:
             for _ in range(warmup):
                 self.model.proposal_sampler._steps_since_update = 10 ** 6  # always update the proposal networks (worst case)
                 self._forward_backward()
-                if self.world_size > 1:
-                    dist.all_reduce(self.grad)
+                sharding.allreduce_gradient_(self.grad)
                 self._optimizer()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
@@ -181,7 +180,7 @@ class MappingTrainer:
         if self._graph_fb is not None:
             self._graph_fb.replay()
             if self.world_size > 1:
-                dist.all_reduce(self.grad)
+                sharding.allreduce_gradient_(self.grad)
                 self._graph_opt.replay()
         else:
             from . import _lib
@@ -189,8 +188,7 @@ class MappingTrainer:
             n0 = _lib.launch_count()
             self.model.proposal_sampler._steps_since_update = 10 ** 6
             self._forward_backward()
-            if self.world_size > 1:
-                dist.all_reduce(self.grad)
+            sharding.allreduce_gradient_(self.grad)
             self._optimizer()
             self.launches_per_step = _lib.launch_count() - n0
         return self.loss
