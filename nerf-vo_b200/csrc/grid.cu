@@ -35,10 +35,9 @@ __global__ void __launch_bounds__(256) k_grid_fwd(const __grid_constant__ GridP 
     const Corner c = make_corner(px, py, pz, p.scale[l]);
     const uint32_t mask = (1u << p.log2T) - 1u;
     const RowT* slab = table + ((size_t)l << p.log2T);
-    // issue all 8 gathers before any use
+    // issue all gathers before any use
     float2 f[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = load_row(slab, corner_index(c, SEL_X(k), SEL_Y(k), SEL_Z(k), mask));
+    gather_level(slab, c, mask, f);
     const float mx = __fsub_rn(1.f, c.ox), my = __fsub_rn(1.f, c.oy), mz = __fsub_rn(1.f, c.oz);
     float out[2];
 #pragma unroll
@@ -80,9 +79,7 @@ __global__ void __launch_bounds__(256) k_grid_fwd_tmh(const __grid_constant__ Gr
             const int l = c * 4 + q;
             if (l < p.L) {
                 cs[q] = make_corner(px, py, pz, p.scale[l]);
-                const RowT* slab = table + ((size_t)l << p.log2T);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) f[q][k] = load_row(slab, corner_index(cs[q], SEL_X(k), SEL_Y(k), SEL_Z(k), mask));
+                gather_level(table + ((size_t)l << p.log2T), cs[q], mask, f[q]);
             }
         }
 #pragma unroll
@@ -156,8 +153,7 @@ __global__ void __launch_bounds__(256) k_grid_bwd_input(const __grid_constant__ 
     const uint32_t mask = (1u << p.log2T) - 1u;
     const RowT* slab = table + ((size_t)l << p.log2T);
     float2 f[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = load_row(slab, corner_index(c, SEL_X(k), SEL_Y(k), SEL_Z(k), mask));
+    gather_level(slab, c, mask, f);
     float2 g = load_dy(dy, s, l, p.L, tmf);
     if (!live) g = make_float2(0.f, 0.f);
     const float mx = 1.f - c.ox, my = 1.f - c.oy, mz = 1.f - c.oz;

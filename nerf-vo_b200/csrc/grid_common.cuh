@@ -72,12 +72,47 @@ __device__ __forceinline__ float2 trilerp_ref(const float2* f, const Corner& c) 
     return make_float2(out[0], out[1]);
 }
 
-// one level of the encoding for one sample: 8 gathers issued back to back, then the interpolation
+// Gather of the 8 corner rows of one (sample, level) into f[k] (reference corner numbering).  The hash is linear in x
+// (prime 1), so for an even x-floor the x-floor / x-ceil rows of each (y,z) combination are r and r^1: ONE aligned double-width
+// load fetches both.  Scattered gathers are bound by L1 tag lookups (one per distinct 32-byte sector per instruction), so this
+// removes a quarter of them on average; the values are bit-identical to eight separate loads.
+__device__ __forceinline__ void load_row_pair(const float2* t, uint32_t lo, float2& a, float2& b) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(t + lo));
+    a = make_float2(v.x, v.y);
+    b = make_float2(v.z, v.w);
+}
+__device__ __forceinline__ void load_row_pair(const __half2* t, uint32_t lo, float2& a, float2& b) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(t + lo));
+    a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+    b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+}
+template <typename RowT>
+__device__ __forceinline__ void gather_level(const RowT* __restrict__ slab, const Corner& c, uint32_t mask, float2* f) {
+    // reference corner k -> (x,y,z): 0=ccc 1=cfc 2=ffc 3=fcc 4=ccf 5=cff 6=fff 7=fcf.  For the (y,z) combination j = sy + 2*sz the
+    // x-ceil member is corner kc[j] and the x-floor member corner kf[j]:  (f,f): 5,6   (c,f): 4,7   (f,c): 1,2   (c,c): 0,3
+    const int kc[4] = {5, 4, 1, 0}, kf[4] = {6, 7, 2, 3};  // indexed by j = sy + 2*sz
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int sy = j & 1, sz = j >> 1;
+        const uint32_t hyz = c.hy[sy] ^ c.hz[sz];
+        const uint32_t idf = (c.hx[0] ^ hyz) & mask, idc = (c.hx[1] ^ hyz) & mask;
+        if ((idf ^ idc) == 1u) {
+            float2 lo, hi;
+            load_row_pair(slab, idf & idc, lo, hi);  // idf & idc == min(idf, idc): the even row of the pair
+            f[kf[j]] = (idf & 1u) ? hi : lo;
+            f[kc[j]] = (idf & 1u) ? lo : hi;
+        } else {
+            f[kf[j]] = load_row(slab, idf);
+            f[kc[j]] = load_row(slab, idc);
+        }
+    }
+}
+
+// one level of the encoding for one sample: all gathers issued back to back, then the interpolation
 template <typename RowT>
 __device__ __forceinline__ float2 grid_level_forward(const RowT* __restrict__ slab, const Corner& c, uint32_t mask) {
     float2 f[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = load_row(slab, corner_index(c, SEL_X(k), SEL_Y(k), SEL_Z(k), mask));
+    gather_level(slab, c, mask, f);
     return trilerp_ref(f, c);
 }
 
