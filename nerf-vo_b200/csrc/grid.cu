@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256) k_grid_fwd(const __grid_constant__ GridP 
 // coarse-level gathers of neighbouring samples coalesce in L1.  Rows >= n and levels >= L are written as zeros (the MLP's
 // zero padding), so the buffer needs no separate initialisation.
 template <typename RowT>
-__global__ void __launch_bounds__(256) k_grid_fwd_tmh(const __grid_constant__ GridP p, int64_t n, int nch, const float* __restrict__ x,
+__global__ void __launch_bounds__(256, 3) k_grid_fwd_tmh(const __grid_constant__ GridP p, int64_t n, int nch, const float* __restrict__ x,
                                                       const RowT* __restrict__ table, uint4* __restrict__ y) {
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= ((n + 127) >> 7 << 7)) return;  // beyond the last (padded) tile

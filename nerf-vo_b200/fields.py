@@ -172,6 +172,7 @@ class NerfactoField(Field):
         self.mlp_head = MLP(in_dim=self.direction_encoding.get_out_dim() + geo_feat_dim + appearance_embedding_dim, num_layers=num_layers_color,
                             layer_width=hidden_dim_color, out_dim=3, activation=nn.ReLU(), out_activation=nn.Sigmoid())
         self._cache = None
+        self._onehot = None
 
     def _remember(self, x, h, shape, tc=None) -> None:
         """State get_normals() needs (base_field.py:80-101 keeps _sample_locations / _density_before_activation).  Stored
@@ -210,8 +211,12 @@ class NerfactoField(Field):
             x = c["x"]
             n = x.shape[0]
             table = enc.hash_table.detach()
-            onehot = torch.zeros((n, mlp.out_dim), dtype=torch.float32, device=x.device)
-            onehot[:, 0] = 1.0
+            key = (n, mlp.out_dim, str(x.device))
+            if self._onehot is None or self._onehot[0] != key:  # constant d(out)/d(out_0) seed, built once per batch shape
+                oh = torch.zeros((n, mlp.out_dim), dtype=torch.float32, device=x.device)
+                oh[:, 0] = 1.0
+                self._onehot = (key, oh)
+            onehot = self._onehot[1]
             if self.precision == "fp16":
                 tc = c["tc"]  # forward buffers of this very evaluation: only the dgrad chain runs here
                 dfeat, _ = ops.mlp_tc_backward(tc["feat16"], tc["wimage"], tc["saved"], tc["y"], onehot, mlp.spec, True, False)

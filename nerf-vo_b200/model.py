@@ -94,6 +94,7 @@ class NerfactoModel(nn.Module):
                                                        num_proposal_network_iterations=c.num_proposal_iterations, single_jitter=c.use_single_jitter,
                                                        update_sched=update_schedule)
         self.step = 0
+        self._near_far_cache: Dict = {}
 
     # ---- bookkeeping the reference does through training callbacks (nerfacto.py:244-286) ------------------
     def get_param_groups(self) -> Dict[str, List[nn.Parameter]]:
@@ -113,10 +114,14 @@ class NerfactoModel(nn.Module):
     # ---- forward -------------------------------------------------------------------------------------------------
     def set_nears_and_fars(self, ray_bundle: RayBundle) -> RayBundle:
         """NearFarCollider (NS/model_components/scene_colliders.py:186-191)."""
-        ones = torch.ones_like(ray_bundle.origins[..., 0:1])
         near = self.config.near_plane if self.training else 0.0
-        ray_bundle.nears = ones * near
-        ray_bundle.fars = ones * self.config.far_plane
+        shape, dev = tuple(ray_bundle.origins[..., 0:1].shape), ray_bundle.origins.device
+        key = (shape, str(dev), near, self.config.far_plane)
+        if self._near_far_cache.get("key") != key:  # constants: built once per (batch shape, mode), not two kernels per step
+            self._near_far_cache = {"key": key, "nears": torch.full(shape, near, dtype=torch.float32, device=dev),
+                                    "fars": torch.full(shape, self.config.far_plane, dtype=torch.float32, device=dev)}
+        ray_bundle.nears = self._near_far_cache["nears"]
+        ray_bundle.fars = self._near_far_cache["fars"]
         return ray_bundle
 
     def forward(self, ray_bundle: RayBundle, jitters: Optional[List[torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
@@ -224,6 +229,29 @@ class ExtendedNerfactoModel(DepthNerfactoModel):
         if metrics_dict is not None and "normal_loss" in metrics_dict:
             loss["normal_loss"] = self.config.normal_loss_mult * metrics_dict["normal_loss"]
         return loss
+
+    def get_train_loss_fused(self, ray_bundle: RayBundle, batch, jitters=None):
+        """Same step as get_train_loss_dict with every loss evaluated by ONE autograd node (ops.fused_step_losses): returns
+        (outputs, total_loss, terms, weights): `total_loss` carries the graph; terms[name] * weights[name] are the entries
+        get_loss_dict would produce (`terms` = ONE detached device vector viewed per name, so logging costs no kernels unless
+        asked for).  Used by MappingTrainer; values and gradients equal the unfused path (tests/test_gpu_parity.py)."""
+        from . import ops
+
+        c = self.config
+        assert self.training and c.num_proposal_iterations == 2, "fused losses cover the NeRF-VO training configuration"
+        outputs = self(ray_bundle, jitters)
+        wl, rl = outputs["weights_list"], outputs["ray_samples_list"]
+        use_n = "normal_image" in batch and c.normal_loss_mult > 0.0 and c.predict_normals
+        use_d = "depth_image" in batch
+        mults = (1.0, c.interlevel_loss_mult, c.distortion_loss_mult, c.depth_loss_mult / len(wl) if use_d else 0.0, c.normal_loss_mult if use_n else 0.0)
+        dnorm = outputs["directions_norm"] if not c.is_euclidean_depth else torch.ones_like(batch["depth_image"])
+        total, terms = ops.fused_step_losses(
+            wl, [r.sdist() for r in rl], [r.frustums.intervals() for r in rl], outputs["rgb"], batch["image"],
+            normals_img=outputs["normals"] if use_n else None, normal_gt=batch["normal_image"] if use_n else None,
+            depth_gt=batch["depth_image"] if use_d else None, directions_norm=dnorm if use_d else None, sigma=c.depth_sigma, mults=mults)
+        names = ("rgb_loss", "interlevel_loss", "distortion_loss", "depth_loss", "normal_loss")
+        # depth: `terms` holds the SUM over the weight sets, its weight the multiplier / number of sets (depth_nerfacto.py:93-103)
+        return outputs, total, {n: terms[i] for i, n in enumerate(names) if mults[i] != 0.0}, {n: mults[i] for i, n in enumerate(names) if mults[i] != 0.0}
 
     def get_train_loss_dict(self, ray_bundle: RayBundle, batch, jitters=None):
         """VanillaPipeline.get_train_loss_dict (NS/pipelines/base_pipeline.py:291-304) for this model."""

@@ -828,6 +828,82 @@ def normal_loss_op(pred, gt):
     return _NormalLoss.apply(pred, gt)
 
 
+class _FusedStepLosses(torch.autograd.Function):
+    """Every loss of the NeRF-VO mapping step (nerf_vo/mapping/nerfstudio.py:71-82: rgb MSE, interlevel, distortion, DS-NeRF depth
+    over the three weight sets, MonoSDF normal) in ONE autograd node: the forward kernels add their batch means into a 5-vector,
+    the backward kernels accumulate multiplier * dL/dweights straight into one zero-filled buffer per level.  Same kernels and
+    arithmetic as the individual loss ops; what disappears is the ~40 scalar torch kernels that glue them together
+    (multiplier products, zero fills, gradient accumulation adds, their backward twins).
+    terms = [rgb, interlevel, distortion, depth (sum over levels), normal] (unweighted); total = sum(mults * terms)."""
+
+    @staticmethod
+    def forward(ctx, w0, w1, w2, rgb, normals_img, spec):
+        ctx.set_materialize_grads(False)
+        ws = [check(w.reshape(w.shape[0], -1).contiguous(), "weights", torch.float32) for w in (w0, w1, w2)]
+        B = ws[0].shape[0]
+        dev = ws[0].device
+        rgb = check(rgb.contiguous(), "rgb", torch.float32, (B, 3))
+        terms = torch.zeros(5, dtype=torch.float32, device=dev)
+        d_rgb = torch.empty_like(rgb)
+        call("nvo_mse_loss", rgb.numel(), rgb, spec["rgb_gt"], spec["mults"][0], terms, d_rgb)
+        wf, cf = ws[2], spec["sdist"][2]
+        for i in range(2):
+            call("nvo_interlevel_loss_forward", B, wf.shape[1], ws[i].shape[1], wf, cf, ws[i], spec["sdist"][i], terms[1:], None, None)
+        call("nvo_distortion_loss_forward", B, wf.shape[1], wf, cf, terms[2:])
+        if spec["depth_gt"] is not None:
+            for i in range(3):
+                s, e, stride = spec["iv"][i].triple()
+                call("nvo_depth_loss_forward", B, ws[i].shape[1], ws[i], s, e, stride, spec["depth_gt"], spec["dnorm"], spec["sigma"], terms[3:])
+        d_n = None
+        if spec["normal_gt"] is not None and normals_img is not None:
+            normals_img = check(normals_img.contiguous(), "normals", torch.float32, (B, 3))
+            d_n = torch.empty_like(normals_img)
+            call("nvo_normal_loss", B, normals_img, spec["normal_gt"], spec["mults"][4], terms[4:], d_n)
+        total = torch.dot(terms, spec["mults_dev"])
+        ctx.save_for_backward(*ws, d_rgb, d_n)
+        ctx.spec = spec
+        ctx.mark_non_differentiable(terms)
+        return total, terms
+
+    @staticmethod
+    def backward(ctx, g, _g_terms):
+        w0, w1, w2, d_rgb, d_n = ctx.saved_tensors
+        ws, spec = [w0, w1, w2], ctx.spec
+        B = w0.shape[0]
+        sizes = [w.shape[1] for w in ws]
+        g = g.reshape(1).float().contiguous()
+        flat = torch.zeros(B * sum(sizes), dtype=torch.float32, device=w0.device)
+        dws, off = [], 0
+        for n_s in sizes:
+            dws.append(flat[off:off + B * n_s].view(B, n_s))
+            off += B * n_s
+        m = spec["mults"]
+        wf, cf = ws[2], spec["sdist"][2]
+        for i in range(2):
+            call("nvo_interlevel_loss_backward", B, wf.shape[1], sizes[i], wf, cf, ws[i], spec["sdist"][i], g, m[1], dws[i])
+        call("nvo_distortion_loss_backward", B, wf.shape[1], wf, cf, g, m[2], dws[2])
+        if spec["depth_gt"] is not None:
+            for i in range(3):
+                s, e, stride = spec["iv"][i].triple()
+                call("nvo_depth_loss_backward", B, sizes[i], ws[i], s, e, stride, spec["depth_gt"], spec["dnorm"], spec["sigma"], g, m[3], dws[i])
+        shp = spec["w_shapes"]
+        return (dws[0].view(shp[0]), dws[1].view(shp[1]), dws[2].view(shp[2]), d_rgb * g, None if d_n is None else d_n * g, None)
+
+
+def fused_step_losses(weights_list, sdist_list, iv_list, rgb, rgb_gt, normals_img=None, normal_gt=None, depth_gt=None, directions_norm=None,
+                      sigma: float = 0.001, mults=(1.0, 1.0, 0.002, 0.001 / 3, 5e-6)):
+    """mults = multipliers of [rgb, interlevel, distortion, depth (already divided by the number of levels), normal]."""
+    dev = rgb.device
+    f = lambda t, shape: None if t is None else check(t.reshape(shape).contiguous(), "target", torch.float32)
+    B = rgb.shape[0]
+    key = ("loss_mults", tuple(float(x) for x in mults))
+    mults_dev = _cached_linspace(key, lambda: torch.tensor([float(x) for x in mults], dtype=torch.float32), dev)
+    spec = {"sdist": [check(s.contiguous(), "sdist", torch.float32) for s in sdist_list], "iv": list(iv_list), "rgb_gt": f(rgb_gt, (B, 3)),
+            "normal_gt": f(normal_gt, (B, 3)), "depth_gt": f(depth_gt, (B,)), "dnorm": f(directions_norm, (B,)), "sigma": float(sigma),
+            "mults": [float(x) for x in mults], "mults_dev": mults_dev, "w_shapes": [tuple(w.shape) for w in weights_list]}
+    return _FusedStepLosses.apply(weights_list[0], weights_list[1], weights_list[2], rgb, normals_img, spec)
+
+
 # ------------------------------------------------------------------------------------------------
 # optimizer
 # ------------------------------------------------------------------------------------------------

@@ -63,7 +63,8 @@ class MappingTrainer:
                        "camera_indices": torch.zeros((B, 1), dtype=torch.int64, device=dev), "rgb": f(B, 3), "depth": f(B, 1), "normal": f(B, 3),
                        "jitter0": f(B, 1), "jitter1": f(B, 1), "jitter2": f(B, 1)}
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
-        self.loss_terms: Dict[str, torch.Tensor] = {}
+        self._terms: Dict[str, torch.Tensor] = {}
+        self._term_weights: Dict[str, float] = {}
         if self.device.type == "cuda" and not ops.leaf_streams.enabled:
             with torch.cuda.device(self.device):
                 ops.leaf_streams.enable(3)
@@ -104,6 +105,11 @@ class MappingTrainer:
         for ps in groups:
             attach_mlp(ps)
 
+    @property
+    def loss_terms(self) -> Dict[str, torch.Tensor]:
+        """The weighted loss_dict entries of the last step (device scalars), built on demand."""
+        return {k: v * self._term_weights[k] for k, v in self._terms.items()}
+
     # ---- one step --------------------------------------------------------------------------------------------------
     def _bundle(self) -> RayBundle:
         i = self.inputs
@@ -116,12 +122,11 @@ class MappingTrainer:
         batch = {"image": i["rgb"], "depth_image": i["depth"]}
         if self.with_normals:
             batch["normal_image"] = i["normal"]
-        _, loss_dict, _ = self.model.get_train_loss_dict(self._bundle(), batch, [i["jitter0"], i["jitter1"], i["jitter2"]])
-        total = sum(loss_dict.values())
+        _, total, terms, weights = self.model.get_train_loss_fused(self._bundle(), batch, [i["jitter0"], i["jitter1"], i["jitter2"]])
         total.backward()
         ops.leaf_streams.join()  # scatter kernels running on side streams must land before the all-reduce / optimizer
         self.loss.copy_(total.detach())
-        self.loss_terms = {k: v.detach() for k, v in loss_dict.items()}
+        self._terms, self._term_weights = terms, weights
 
     def _optimizer(self) -> None:
         ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.betas[0], self.betas[1], self.eps,

@@ -550,3 +550,29 @@ def test_fused_proposal_density_vs_oracle(nv, S, B):
     # frozen proposal step (ray_samplers.py:608-610): no saved features, same values
     with torch.no_grad():
         assert torch.equal(field.density_from_ray_samples(rs), dens)
+
+
+def test_fused_step_losses_match_unfused(nv, golden):
+    """The single-node loss evaluation the trainer uses (ops.fused_step_losses) against the per-loss path that the golden
+    test pins to the reference: total and every weighted term 1e-6 relative, every parameter gradient 1e-5 of max-abs."""
+    g = golden("model_step_small")
+    res = []
+    for fused in (False, True):
+        m, rb, batch, jit = _build_model(nv, g)
+        m.proposal_sampler.set_anneal(float(g["anneal"]))
+        if fused:
+            _, total, terms, weights = m.get_train_loss_fused(rb, batch, jit)
+            ld = {k: v * weights[k] for k, v in terms.items()}
+        else:
+            _, ld, _ = m.get_train_loss_dict(rb, batch, jit)
+            total = sum(ld.values())
+        total.backward()
+        res.append((float(total), {k: float(v) for k, v in ld.items()}, {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}))
+    (t0, l0, g0), (t1, l1, g1) = res
+    assert abs(t0 - t1) <= 1e-6 * abs(t0)
+    assert set(l0) == set(l1)
+    for k in l0:
+        assert abs(l0[k] - l1[k]) <= 1e-6 * abs(l0[k]) + 1e-12, (k, l0[k], l1[k])
+    assert set(g0) == set(g1)
+    for k in g0:
+        assert rel_err(g1[k], g0[k]) < 1e-5, (k, rel_err(g1[k], g0[k]))
