@@ -108,7 +108,8 @@ int nvo_mlp_backward(const nvo_mlp_desc* d, void* stream, int64_t n, const float
  *           whenever `params` (torch layout, fp32, as nvo_mlp_forward) change;
  *   saved   opaque forward context of nvo_mlp_tc_saved_bytes(d, n) bytes (fp16 hidden activations, TMH layout);
  *   scratch one float the backward uses for its device-side gradient scale (max|dy| -> power-of-two loss scale, the
- *           device analogue of tinycudann's loss_scale, modules.py:174);
+ *           device analogue of tinycudann's loss_scale, modules.py:174); dy_absmax_hint > 0 supplies max|dy| from the
+ *           caller instead (e.g. 1 for a one-hot seed) and skips the reduction pass;
  *   y, dy, dparams fp32 row-major exactly as the SIMT entry points;
  *   dx      fp32 in TMF layout ("tile-major float"): [ceil(n/128)][in_dim][128], i.e. column-major inside each 128-row tile, so
  *           the kernel's row-per-thread epilogue stores coalesced and the per-sample consumers (nvo_grid_backward with
@@ -122,7 +123,7 @@ int nvo_tmf_to_rows(void* stream, int64_t n, int32_t K, const float* src, float*
 int nvo_mlp_tc_forward(const nvo_mlp_desc* d, void* stream, int64_t n, const void* x16, const void* wimage, const float* row_mask, float* y,
                        void* saved);
 int nvo_mlp_tc_backward(const nvo_mlp_desc* d, void* stream, int64_t n, const void* x16, const void* wimage, const void* saved, const float* y,
-                        const float* row_mask, const float* dy, float* scratch, float* dx, float* dparams);
+                        const float* row_mask, const float* dy, float dy_absmax_hint, float* scratch, float* dx, float* dparams);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused proposal density field — replaces HashMLPDensityField.density_fn / get_density

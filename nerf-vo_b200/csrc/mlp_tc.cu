@@ -443,8 +443,8 @@ __device__ __forceinline__ void load_dz_last(const TcP& p, int64_t n, int64_t ti
 __global__ void __launch_bounds__(TM) k_mlp_tc_bwd(const __grid_constant__ TcP p, int64_t n, const unsigned char* __restrict__ x16,
                                                    const unsigned char* __restrict__ wimg, const unsigned char* __restrict__ saved,
                                                    const float* __restrict__ y, const float* __restrict__ row_mask, const float* __restrict__ dy,
-                                                   const float* __restrict__ dy_absmax, float* __restrict__ dx, float* __restrict__ dparams, int smem_w_off,
-                                                   int smem_ctrl_off) {
+                                                   const float* __restrict__ dy_absmax, float absmax_hint, float* __restrict__ dx, float* __restrict__ dparams,
+                                                   int smem_w_off, int smem_ctrl_off) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sW = smem + smem_w_off;
     uint64_t* mbar_mma = reinterpret_cast<uint64_t*>(smem + smem_ctrl_off);
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(TM) k_mlp_tc_bwd(const __grid_constant__ TcP p
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    const float gscale = grad_scale_from_max(__ldg(dy_absmax));
+    const float gscale = grad_scale_from_max(absmax_hint > 0.f ? absmax_hint : __ldg(dy_absmax));
     const float inv_gscale = 1.f / gscale;
     mbar_wait(mbar_w, 0);
     uint32_t phase = 0;
@@ -753,7 +753,7 @@ extern "C" int nvo_mlp_tc_forward(const nvo_mlp_desc* d, void* stream, int64_t n
 }
 
 extern "C" int nvo_mlp_tc_backward(const nvo_mlp_desc* d, void* stream, int64_t n, const void* x16, const void* wimage, const void* saved, const float* y,
-                                   const float* row_mask, const float* dy, float* scratch, float* dx, float* dparams) {
+                                   const float* row_mask, const float* dy, float dy_absmax_hint, float* scratch, float* dx, float* dparams) {
     TcP p;
     if (int e = make_tc_params(d, &p)) return e;
     NVO_CHECK(n >= 0, "mlp_tc_backward: negative batch");
@@ -762,11 +762,14 @@ extern "C" int nvo_mlp_tc_backward(const nvo_mlp_desc* d, void* stream, int64_t 
     NVO_CHECK(p.n_layers == 1 || saved, "mlp_tc_backward: saved activations required for multi-layer networks");
     NVO_CHECK(p.acts[p.n_layers - 1] == NVO_ACT_NONE || y, "mlp_tc_backward: y required for an output activation");
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(float), st);
-    NVO_CHECK(e == cudaSuccess, "mlp_tc_backward: memset: %s", cudaGetErrorString(e));
-    const int64_t count = n * p.dims[p.n_layers - 1];
-    k_absmax_scale<<<(unsigned int)min((int64_t)nvo_sm_count() * 4, (count + 255) / 256), 256, 0, st>>>(count, dy, scratch);
-    NVO_CUDA_LAUNCH_CHECK("mlp_tc_backward(absmax)");
+    cudaError_t e = cudaSuccess;
+    if (!(dy_absmax_hint > 0.f)) {  // the caller does not know max|dy|: one reduction pass over dy
+        e = cudaMemsetAsync(scratch, 0, sizeof(float), st);
+        NVO_CHECK(e == cudaSuccess, "mlp_tc_backward: memset: %s", cudaGetErrorString(e));
+        const int64_t count = n * p.dims[p.n_layers - 1];
+        k_absmax_scale<<<(unsigned int)min((int64_t)nvo_sm_count() * 4, (count + 255) / 256), 256, 0, st>>>(count, dy, scratch);
+        NVO_CUDA_LAUNCH_CHECK("mlp_tc_backward(absmax)");
+    }
     const int w_off = BWD_STAGE + 2 * p.stage_bytes;
     const int ctrl = w_off + p.img_bytes;
     const size_t smem = (size_t)ctrl + 48;
@@ -776,7 +779,7 @@ extern "C" int nvo_mlp_tc_backward(const nvo_mlp_desc* d, void* stream, int64_t 
     const int64_t tiles = (n + TM - 1) / TM;
     const unsigned int grid = (unsigned int)min(tiles, (int64_t)nvo_sm_count());
     k_mlp_tc_bwd<<<grid, TM, smem, st>>>(p, n, (const unsigned char*)x16, (const unsigned char*)wimage, (const unsigned char*)saved, y, row_mask, dy, scratch,
-                                         dx, dparams, w_off, ctrl);
+                                         dy_absmax_hint, dx, dparams, w_off, ctrl);
     NVO_CUDA_LAUNCH_CHECK("mlp_tc_backward");
     return 0;
 }

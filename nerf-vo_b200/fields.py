@@ -219,7 +219,7 @@ class NerfactoField(Field):
             onehot = self._onehot[1]
             if self.precision == "fp16":
                 tc = c["tc"]  # forward buffers of this very evaluation: only the dgrad chain runs here
-                dfeat, _ = ops.mlp_tc_backward(tc["feat16"], tc["wimage"], tc["saved"], tc["y"], onehot, mlp.spec, True, False)
+                dfeat, _ = ops.mlp_tc_backward(tc["feat16"], tc["wimage"], tc["saved"], tc["y"], onehot, mlp.spec, True, False, dy_absmax=1.0)
             else:
                 flat = ops.flat_alias([p.data for p in mlp._flat_param_list()])
                 feat = ops.grid_forward(x, table, enc.spec)

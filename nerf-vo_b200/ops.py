@@ -29,9 +29,16 @@ class _LeafStreams:
         self.refs: list = []
         self.next = 0
 
-    def enable(self, n: int = 3):
+    def enable(self, n: int = 3, n_levels: int = 2):
         self.streams = [torch.cuda.Stream() for _ in range(n)]
+        # one stream per proposal level: the level's forward (density + weights) is issued there, so autograd runs the level's
+        # BACKWARD there too, ordered only after the gradients it consumes — i.e. concurrently with the main field's backward
+        self.level_streams = [torch.cuda.Stream() for _ in range(n_levels)]
         self.enabled = True
+
+    def on_level_stream(self) -> bool:
+        cur = torch.cuda.current_stream()
+        return any(cur == st for st in getattr(self, "level_streams", []))
 
     def fork(self, *keepalive):
         """Returns a context manager running its body on the next side stream, ordered after the current stream."""
@@ -362,7 +369,8 @@ class _PropDensity(torch.autograd.Function):
         ddensity = ddensity.contiguous()
         args = ("nvo_prop_density_backward", ctx.gspec.desc(table.dtype, torch.float32), ctx.hidden, ctx.slot, ctx.B, ctx.S, origins, directions, s, e, stride, positions,
                 flat, feat, ddensity, dtable, dflat)
-        if leaf_streams.enabled and (not need_dt or dtable is ctx.table_main_grad) and (not need_dp or dflat is ctx.mlp_main_grad):
+        if (leaf_streams.enabled and not leaf_streams.on_level_stream() and (not need_dt or dtable is ctx.table_main_grad)
+                and (not need_dp or dflat is ctx.mlp_main_grad)):
             with leaf_streams.fork(table, flat, feat, origins, directions, positions, ddensity, ctx.iv):
                 call(*args)
         else:
@@ -828,6 +836,24 @@ def normal_loss_op(pred, gt):
     return _NormalLoss.apply(pred, gt)
 
 
+def _run_levels(level) -> None:
+    """level(0), level(1) on two helper streams, level(2) on the current one, joined before returning (plain sequential calls when
+    side streams are not enabled).  Every tensor involved outlives the call, so no allocator hazards arise."""
+    if not leaf_streams.enabled:
+        for i in range(3):
+            level(i)
+        return
+    main = torch.cuda.current_stream()
+    helpers = leaf_streams.streams[:2]
+    for i, st in enumerate(helpers):
+        st.wait_stream(main)
+        with torch.cuda.stream(st):
+            level(i)
+    level(2)
+    for st in helpers:
+        main.wait_stream(st)
+
+
 class _FusedStepLosses(torch.autograd.Function):
     """Every loss of the NeRF-VO mapping step (nerf_vo/mapping/nerfstudio.py:71-82: rgb MSE, interlevel, distortion, DS-NeRF depth
     over the three weight sets, MonoSDF normal) in ONE autograd node: the forward kernels add their batch means into a 5-vector,
@@ -845,20 +871,25 @@ class _FusedStepLosses(torch.autograd.Function):
         rgb = check(rgb.contiguous(), "rgb", torch.float32, (B, 3))
         terms = torch.zeros(5, dtype=torch.float32, device=dev)
         d_rgb = torch.empty_like(rgb)
-        call("nvo_mse_loss", rgb.numel(), rgb, spec["rgb_gt"], spec["mults"][0], terms, d_rgb)
-        wf, cf = ws[2], spec["sdist"][2]
-        for i in range(2):
-            call("nvo_interlevel_loss_forward", B, wf.shape[1], ws[i].shape[1], wf, cf, ws[i], spec["sdist"][i], terms[1:], None, None)
-        call("nvo_distortion_loss_forward", B, wf.shape[1], wf, cf, terms[2:])
-        if spec["depth_gt"] is not None:
-            for i in range(3):
-                s, e, stride = spec["iv"][i].triple()
-                call("nvo_depth_loss_forward", B, ws[i].shape[1], ws[i], s, e, stride, spec["depth_gt"], spec["dnorm"], spec["sigma"], terms[3:])
         d_n = None
         if spec["normal_gt"] is not None and normals_img is not None:
             normals_img = check(normals_img.contiguous(), "normals", torch.float32, (B, 3))
             d_n = torch.empty_like(normals_img)
-            call("nvo_normal_loss", B, normals_img, spec["normal_gt"], spec["mults"][4], terms[4:], d_n)
+        wf, cf = ws[2], spec["sdist"][2]
+
+        def level(i):  # everything that reads weight set i: the kernels are tiny (4096 warps), so the three levels run side by side
+            if i < 2:
+                call("nvo_interlevel_loss_forward", B, wf.shape[1], ws[i].shape[1], wf, cf, ws[i], spec["sdist"][i], terms[1:], None, None)
+            else:
+                call("nvo_mse_loss", rgb.numel(), rgb, spec["rgb_gt"], spec["mults"][0], terms, d_rgb)
+                call("nvo_distortion_loss_forward", B, wf.shape[1], wf, cf, terms[2:])
+                if d_n is not None:
+                    call("nvo_normal_loss", B, normals_img, spec["normal_gt"], spec["mults"][4], terms[4:], d_n)
+            if spec["depth_gt"] is not None:
+                s, e, stride = spec["iv"][i].triple()
+                call("nvo_depth_loss_forward", B, ws[i].shape[1], ws[i], s, e, stride, spec["depth_gt"], spec["dnorm"], spec["sigma"], terms[3:])
+
+        _run_levels(level)
         total = torch.dot(terms, spec["mults_dev"])
         ctx.save_for_backward(*ws, d_rgb, d_n)
         ctx.spec = spec
@@ -879,13 +910,17 @@ class _FusedStepLosses(torch.autograd.Function):
             off += B * n_s
         m = spec["mults"]
         wf, cf = ws[2], spec["sdist"][2]
-        for i in range(2):
-            call("nvo_interlevel_loss_backward", B, wf.shape[1], sizes[i], wf, cf, ws[i], spec["sdist"][i], g, m[1], dws[i])
-        call("nvo_distortion_loss_backward", B, wf.shape[1], wf, cf, g, m[2], dws[2])
-        if spec["depth_gt"] is not None:
-            for i in range(3):
+
+        def level(i):  # each level owns its gradient buffer: no two streams touch the same one
+            if i < 2:
+                call("nvo_interlevel_loss_backward", B, wf.shape[1], sizes[i], wf, cf, ws[i], spec["sdist"][i], g, m[1], dws[i])
+            else:
+                call("nvo_distortion_loss_backward", B, wf.shape[1], wf, cf, g, m[2], dws[2])
+            if spec["depth_gt"] is not None:
                 s, e, stride = spec["iv"][i].triple()
                 call("nvo_depth_loss_backward", B, sizes[i], ws[i], s, e, stride, spec["depth_gt"], spec["dnorm"], spec["sigma"], g, m[3], dws[i])
+
+        _run_levels(level)
         shp = spec["w_shapes"]
         return (dws[0].view(shp[0]), dws[1].view(shp[1]), dws[2].view(shp[2]), d_rgb * g, None if d_n is None else d_n * g, None)
 
@@ -972,7 +1007,7 @@ def mlp_tc_forward(x16, wimage, spec: MlpSpec, n: int, save: bool, row_mask=None
     return y, saved
 
 
-def mlp_tc_backward(x16, wimage, saved, y, dy, spec: MlpSpec, need_dx: bool, need_dparams: bool, dflat=None, row_mask=None):
+def mlp_tc_backward(x16, wimage, saved, y, dy, spec: MlpSpec, need_dx: bool, need_dparams: bool, dflat=None, row_mask=None, dy_absmax: float = 0.0):
     n = dy.shape[0]
     check(dy, "mlp dy", torch.float32, (n, spec.out_dim))
     # dx comes back in TMF layout ([tile][in_dim][128] fp32, see include/nvo_b200.h); tmf_to_rows() converts when needed
@@ -980,7 +1015,7 @@ def mlp_tc_backward(x16, wimage, saved, y, dy, spec: MlpSpec, need_dx: bool, nee
     if need_dparams and dflat is None:
         dflat = torch.zeros(spec.n_params, dtype=torch.float32, device=x16.device)
     scratch = torch.empty(1, dtype=torch.float32, device=x16.device)
-    call("nvo_mlp_tc_backward", spec.desc, n, x16, wimage, saved, y, row_mask, dy, scratch, dx, dflat if need_dparams else None)
+    call("nvo_mlp_tc_backward", spec.desc, n, x16, wimage, saved, y, row_mask, dy, float(dy_absmax), scratch, dx, dflat if need_dparams else None)
     return dx, dflat
 
 

@@ -20,11 +20,16 @@ class Sampler(nn.Module):
 
 
 def _piecewise_spacing_to_euclidean(nears, fars) -> Callable:
-    """Host-visible closure equivalent to ray_samplers.py:112-117 (kept for API parity; kernels evaluate it on the device)."""
+    """Host-visible closure equivalent to ray_samplers.py:112-117 (kept for API parity; kernels evaluate it on the device).
+    Lazy: s_near / s_far are only computed if somebody calls it."""
     f = lambda x: torch.where(x < 1, x / 2, 1 - 1 / (2 * x))
     finv = lambda x: torch.where(x < 0.5, 2 * x, 1 / (2 - 2 * x))
-    s_near, s_far = f(nears), f(fars)
-    return lambda x: finv(x * s_far + (1 - x) * s_near)
+
+    def fn(x):
+        s_near, s_far = f(nears), f(fars)
+        return finv(x * s_far + (1 - x) * s_near)
+
+    return fn
 
 
 class UniformLinDispPiecewiseSampler(Sampler):
@@ -132,9 +137,24 @@ class ProposalNetworkSampler(Sampler):
                 # our proposal fields evaluate straight from the ray samples (no positions tensor); any other callable
                 # gets the reference's density_fn(positions) call
                 fused = getattr(owner, "density_from_ray_samples", None) if getattr(fn, "__name__", "") == "density_fn" else None
-                with torch.enable_grad() if updated else torch.no_grad():
-                    density = fused(ray_samples) if fused is not None else fn(ray_samples.frustums.get_positions())
-                weights = ray_samples.get_weights(density)
+                side = None
+                if updated and ops.leaf_streams.enabled and i_level < len(ops.leaf_streams.level_streams) and ray_samples.frustums.starts.is_cuda:
+                    side = ops.leaf_streams.level_streams[i_level]
+                if side is not None:
+                    # forward of this level on its own stream (still strictly ordered: fork after, join before, the main stream);
+                    # its backward then runs there as well, next to the main field's backward instead of behind it
+                    main = torch.cuda.current_stream()
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        density = fused(ray_samples) if fused is not None else fn(ray_samples.frustums.get_positions())
+                        weights = ray_samples.get_weights(density)
+                    main.wait_stream(side)
+                    for t in (density, weights):
+                        t.record_stream(main)
+                else:
+                    with torch.enable_grad() if updated else torch.no_grad():
+                        density = fused(ray_samples) if fused is not None else fn(ray_samples.frustums.get_positions())
+                    weights = ray_samples.get_weights(density)
                 weights_list.append(weights)
                 ray_samples_list.append(ray_samples)
         if updated:

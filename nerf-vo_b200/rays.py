@@ -64,7 +64,7 @@ class Frustums:
 class RaySamples:
     frustums: Frustums
     camera_indices: Optional[torch.Tensor] = None
-    deltas: Optional[torch.Tensor] = None
+    _deltas: Optional[torch.Tensor] = None
     spacing_starts: Optional[torch.Tensor] = None
     spacing_ends: Optional[torch.Tensor] = None
     spacing_to_euclidean_fn: Optional[Callable] = None
@@ -77,6 +77,13 @@ class RaySamples:
     @property
     def shape(self):
         return self.frustums.shape
+
+    @property
+    def deltas(self) -> torch.Tensor:
+        """ends - starts [B,S,1] (rays.py:291), evaluated on first use: no kernel on the hot path reads it."""
+        if self._deltas is None:
+            self._deltas = self.frustums.ends - self.frustums.starts
+        return self._deltas
 
     def sdist(self) -> torch.Tensor:
         """[B,S+1] spacing edges = cat[spacing_starts, spacing_ends[-1]] (NS/model_components/losses.py:84-90)."""
@@ -131,7 +138,6 @@ class RayBundle:
         return RaySamples(
             frustums=fr,
             camera_indices=None if self.camera_indices is None else self.camera_indices[:, None, :],
-            deltas=ends - starts,
             spacing_starts=sdist[:, :-1, None],
             spacing_ends=sdist[:, 1:, None],
             spacing_to_euclidean_fn=spacing_to_euclidean_fn,
