@@ -28,8 +28,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the same kernel/shape
-# (profiles/r01_ncu_grid_fwd_tmh.md); None until a capture exists
-RECORDED_TRAFFIC = {"k_grid_fwd_tmh": None}
+# (profiles/r01_ncu_full_step_kernels.md: 48.92 MB read + 7.37 MB written — far below the algorithmic bytes because the 64 MiB table
+# is served from the 126 MB L2)
+RECORDED_TRAFFIC = {"k_grid_fwd_tmh": 56.29e6}
 
 METRIC = "nerf_mapping_train_rays_per_s"
 UNIT = "rays/s"
@@ -152,7 +153,7 @@ def run_ours(args):
     torch.manual_seed(0)  # identical parameters on every rank (replicated), rays differ per rank
     model = nv.ExtendedNerfactoModel(nv.NerfactoModelConfig(), num_train_data=NUM_IMAGES).to(dev)
     B = RAYS_PER_GPU
-    trainer = MappingTrainer(model, num_rays=B, lr=1e-2, eps=1e-15, use_cuda_graph=not args.no_graph)
+    trainer = MappingTrainer(model, num_rays=B, lr=1e-2, eps=1e-15, use_cuda_graph=not args.no_graph, exchange=args.exchange)
 
     n_pool = 8
     host_batches, dev_batches = [], []
@@ -202,6 +203,32 @@ def run_ours(args):
     rays_per_s = world * B * args.steps / (ms * 1e-3)
     e2e_rays_per_s = world * B * args.steps / (ms_e2e * 1e-3)
 
+    # N > 1: the exchange step alone (fused arm: barrier + reduce-scatter + Adam + all-gather in one kernel; every rank launches it the
+    # same number of times), against the measured NVLink peer-copy bandwidth (B200_PROFILING.md: 770 GB/s per direction per GPU)
+    exchange = None
+    if world > 1:
+        reps = 20
+        for _ in range(3):
+            trainer._exchange(); trainer._optimizer()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            trainer._exchange(); trainer._optimizer()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cs = torch.stack([trainer.flat.double().sum(), trainer.flat.double().abs().sum()])
+        allcs = [torch.zeros_like(cs) for _ in range(world)]
+        dist.all_gather(allcs, cs)
+        consistent = all(torch.equal(allcs[0], c) for c in allcs)  # every replica holds bit-identical parameters after the run
+        nbytes = trainer.flat.numel() * 4
+        link = (world - 1) / world * nbytes
+        exchange = {"arm": trainer.exchange, "us_per_step": float(t) * 1e3, "flat_bytes": nbytes, "nvlink_bytes_per_direction_per_gpu": link,
+                    "achieved_GBs_per_direction": link / (float(t) * 1e-3) / 1e9, "peer_copy_peak_GBs": 770.0,
+                    "replicas_bit_identical": bool(consistent), "error_word": trainer.peer.error_word() if trainer.peer is not None else 0}
+
     roofline = cpu = None
     if rank == 0:
         # roofline kernel: the main hash-grid forward of this step (16 levels, fp32 table of 2^19 rows, fp16 TMH output feeding the
@@ -242,7 +269,7 @@ def run_ours(args):
             "metric": METRIC, "value": rays_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "precision": "fp16 tensor-core operands (hash features, field MLPs) with fp32 accumulation; fp32 tables, proposal networks, per-ray ops, optimizer",
-                       "rays_per_gpu": B, "global_rays": world * B, "parallelism": f"dp{world} (ray sharding, flat-gradient NCCL all-reduce)",
+                       "rays_per_gpu": B, "global_rays": world * B, "parallelism": f"dp{world} (ray sharding; gradient exchange: {trainer.exchange})",
                        "step": "zero-grad + forward + losses + backward + fused Adam, proposal networks updated every step",
                        "l2": "no explicit flush: parameters+gradients+Adam state = 290 MB per step exceed the 126 MB L2",
                        "cuda_graph": not args.no_graph},
@@ -252,6 +279,7 @@ def run_ours(args):
             "clocks": clk.summary(),
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "exchange": exchange,
             "final_loss": final_loss,
         }
         print(json.dumps(line), flush=True)
@@ -268,6 +296,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N>1 gradient exchange: 'fused' = peer-memory reduce-scatter+Adam+all-gather kernel, 'nccl' = all-reduce + replicated Adam")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -267,6 +267,29 @@ int nvo_normal_loss(void* stream, int64_t B, const float* pred /*[B,3]*/, const 
 int nvo_adam_step(void* stream, int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int32_t* step, float lr,
                   float beta1, float beta2, float eps, float grad_scale);
 
+/* ---------------------------------------------------------------------------------------------
+ * Data-parallel exchange fused with the optimizer over NVLink peer memory (csrc/exchange.cu) — replaces the
+ * DistributedDataParallel gradient all-reduce + dense Adam the reference would run for world_size > 1
+ * (NS/pipelines/base_pipeline.py:281-283, NS/engine/optimizers.py:138-150).
+ * One launch per rank and step: barrier(gradients ready) -> reduce-scatter by peer loads -> Adam on the rank's own
+ * slice (moments exist only there) -> all-gather by peer stores -> barrier(replicas written).
+ * h_peer_params / h_peer_grads / h_peer_flags: HOST arrays of `world` device pointers (entry k = rank k's buffer as
+ * mapped into THIS process; entry `rank` = the local allocation). Flag pads are nvo_exchange_flag_words() int32, zeroed.
+ * n (floats, multiple of 4) is the flat buffer length; exp_avg_slice / exp_avg_sq_slice hold nvo_exchange_slice() floats.
+ * step[1]: device int32 step counter, identical on every rank, incremented by the call (epoch of the barriers).
+ * Spin waits are bounded; on timeout flag word 33 of the local pad becomes non-zero (1: ready barrier, 2: done barrier).
+ * ------------------------------------------------------------------------------------------- */
+int nvo_exchange_flag_words(void);
+int64_t nvo_exchange_slice(int64_t n, int32_t rank, int32_t world, int64_t* lo, int64_t* hi);
+int nvo_adam_exchange_step(void* stream, int64_t n, int32_t rank, int32_t world, const void* h_peer_params, const void* h_peer_grads,
+                           const void* h_peer_flags, float* exp_avg_slice, float* exp_avg_sq_slice, int32_t* step, float lr, float beta1,
+                           float beta2, float eps, float grad_scale);
+/* peer-visible allocations: cudaMalloc (zero-filled) + CUDA IPC export / import; handles are 64 opaque bytes */
+int nvo_peer_alloc(int64_t bytes, void* h_ptr_out, void* h_handle64_out);
+int nvo_peer_open(const void* h_handle64, void* h_ptr_out);
+int nvo_peer_close(void* ptr);
+int nvo_peer_free(void* ptr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,7 +89,7 @@ def load() -> ctypes.CDLL:
         fn.argtypes = [_CT[k] for k in sig]
         if name == "nvo_last_error":
             fn.restype = ctypes.c_char_p
-        elif name in ("nvo_mlp_n_params", "nvo_mlp_saved_per_sample", "nvo_launch_count", "nvo_mlp_tc_saved_bytes", "nvo_mlp_tc_wimage_bytes", "nvo_prop_density_feat_floats"):
+        elif name in ("nvo_mlp_n_params", "nvo_mlp_saved_per_sample", "nvo_launch_count", "nvo_mlp_tc_saved_bytes", "nvo_mlp_tc_wimage_bytes", "nvo_prop_density_feat_floats", "nvo_exchange_slice"):
             fn.restype = ctypes.c_int64
         else:
             fn.restype = ctypes.c_int

@@ -1,0 +1,219 @@
+// Data-parallel gradient exchange fused with the optimizer, over NVLink / NVSwitch peer memory (SURVEY §8e + §8f row 1).
+//
+// The reference would wrap the model in DistributedDataParallel (NS/pipelines/base_pipeline.py:281-283: bucketed NCCL
+// all-reduce of every gradient, then a dense torch Adam on every rank).  Here the exchange and the optimizer are ONE kernel:
+//
+//   rank r owns the slice [r*chunk, (r+1)*chunk) of the flat parameter buffer (ZeRO-1 style: its Adam moments exist only on r)
+//     1. barrier "gradients ready": release-store of the step epoch into every peer's flag pad, acquire-poll of the own pad;
+//     2. reduce-scatter by direct peer LOADS: g = sum over ranks of grad_k[i] for i in the own slice (16-byte loads through NVLink);
+//     3. Adam on the slice (moments local, 1/W of the optimizer traffic of a replicated Adam);
+//     4. all-gather by direct peer STORES: the new parameter values are written into every rank's replica;
+//     5. barrier "replicas written": system fence, the last CTA signals every peer and waits for theirs — after the kernel a rank
+//        may zero its gradient buffer and read its parameters.
+//
+// Per step and GPU, (W-1)/W of the flat buffer crosses NVLink once in each direction (the minimum for an all-reduce), no
+// staging copies, no separate optimizer pass; the whole mapping step stays one CUDA graph (no host-side collective call).
+//
+// Buffers that peers touch (parameters, gradients, flag pads) are plain cudaMalloc allocations exported with CUDA IPC
+// (nvo_peer_alloc / nvo_peer_open); PyTorch wraps them as tensors.  Spin waits are bounded (~4 s): on timeout the kernel
+// raises the error word instead of hanging the GPU.
+#include "nvo_common.cuh"
+
+#define NVO_MAX_PEERS 16
+#define FLAG_READY 0                 // flags[FLAG_READY + k]: rank k's gradients of epoch e are complete
+#define FLAG_DONE NVO_MAX_PEERS      // flags[FLAG_DONE + k]:  rank k has finished reading / writing peers for epoch e
+#define FLAG_COUNT (2 * NVO_MAX_PEERS)   // flags[FLAG_COUNT]: local CTA completion counter; [FLAG_COUNT+1]: error word
+#define FLAG_WORDS 64
+
+struct PeerSet {
+    float* params[NVO_MAX_PEERS];
+    const float* grads[NVO_MAX_PEERS];
+    int* flags[NVO_MAX_PEERS];
+};
+
+__device__ __forceinline__ void st_release_sys(int* p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) {
+    float4 v;  // system-scope relaxed load: never served from a stale L1 line of a previous step
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_peer_f4(float* p, const float4 v) {
+    asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// waits until flags[base + k] >= epoch for every k != rank (thread k polls flag k); false on timeout
+__device__ __forceinline__ bool wait_all(const int* flags, int base, int world, int rank, int epoch) {
+    bool ok = true;
+    const int k = threadIdx.x;
+    if (k < world && k != rank) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys(flags + base + k) < epoch) {
+            if (clock64() - t0 > 8000000000LL) {  // ~4 s at 2 GHz
+                ok = false;
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    return __syncthreads_and(ok);
+}
+
+template <int W>
+__global__ void __launch_bounds__(512) k_exchange_adam(const __grid_constant__ PeerSet ps, int rank, int64_t lo4, int64_t hi4, float* __restrict__ m,
+                                                       float* __restrict__ v, const int* __restrict__ step_ptr, float lr, float b1, float b2, float eps,
+                                                       float grad_scale) {
+    int* my_flags = ps.flags[rank];
+    const int epoch = *step_ptr + 1;
+    // ---- 1. every rank's backward has landed -----------------------------------------------------------------------
+    if (blockIdx.x == 0 && threadIdx.x < W && threadIdx.x != rank) {
+        __threadfence_system();
+        st_release_sys(ps.flags[threadIdx.x] + FLAG_READY + rank, epoch);
+    }
+    if (!wait_all(my_flags, FLAG_READY, W, rank, epoch)) {
+        if (threadIdx.x == 0) atomicExch(my_flags + FLAG_COUNT + 1, 1);
+    }
+    const float t = (float)epoch;
+    const float step_size = lr / (1.f - powf(b1, t)), inv_bc2 = 1.f / sqrtf(1.f - powf(b2, t));
+    // ---- 2-4. reduce-scatter (peer loads) -> Adam -> all-gather (peer stores) on the own slice -------------------------
+    for (int64_t i = lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 g[W];
+#pragma unroll
+        for (int k = 0; k < W; ++k) g[k] = ld_peer_f4(ps.grads[k] + 4 * i);  // W independent 16-byte loads in flight
+        float4 gs = g[0];
+#pragma unroll
+        for (int k = 1; k < W; ++k) gs.x += g[k].x, gs.y += g[k].y, gs.z += g[k].z, gs.w += g[k].w;
+        const int64_t j = i - lo4;
+        float4 pp = reinterpret_cast<const float4*>(ps.params[rank])[i];
+        float4 mm = reinterpret_cast<float4*>(m)[j];
+        float4 vv = reinterpret_cast<float4*>(v)[j];
+#define UPD(c)                                                        \
+    {                                                                 \
+        const float gr = gs.c * grad_scale;                           \
+        mm.c = b1 * mm.c + (1.f - b1) * gr;                           \
+        vv.c = b2 * vv.c + (1.f - b2) * gr * gr;                      \
+        pp.c -= step_size * mm.c / (sqrtf(vv.c) * inv_bc2 + eps);     \
+    }
+        UPD(x) UPD(y) UPD(z) UPD(w)
+#undef UPD
+        reinterpret_cast<float4*>(m)[j] = mm;
+        reinterpret_cast<float4*>(v)[j] = vv;
+#pragma unroll
+        for (int k = 0; k < W; ++k) st_peer_f4(ps.params[k] + 4 * i, pp);
+    }
+    // ---- 5. replicas written: last CTA signals the peers and waits for theirs -----------------------------------------------
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int s_last;
+    if (threadIdx.x == 0) s_last = atomicAdd(my_flags + FLAG_COUNT, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) my_flags[FLAG_COUNT] = 0;  // re-armed for the next step
+    __threadfence_system();
+    if (threadIdx.x < W && threadIdx.x != rank) st_release_sys(ps.flags[threadIdx.x] + FLAG_DONE + rank, epoch);
+    if (!wait_all(my_flags, FLAG_DONE, W, rank, epoch)) {
+        if (threadIdx.x == 0) atomicExch(my_flags + FLAG_COUNT + 1, 2);
+    }
+}
+
+__global__ void k_tick_step(int* step) { *step += 1; }
+
+typedef void (*exchange_fn)(const PeerSet, int, int64_t, int64_t, float*, float*, const int*, float, float, float, float, float);
+
+extern "C" int nvo_exchange_flag_words(void) { return FLAG_WORDS; }
+
+extern "C" int64_t nvo_exchange_slice(int64_t n, int32_t rank, int32_t world, int64_t* lo, int64_t* hi) {
+    // slice of rank in floats: [lo, hi), cut on float4 boundaries; returns its length
+    const int64_t n4 = (n + 3) / 4, chunk = (n4 + world - 1) / world;
+    int64_t a = (int64_t)rank * chunk, b = a + chunk;
+    if (a > n4) a = n4;
+    if (b > n4) b = n4;
+    if (lo) *lo = a * 4;
+    if (hi) *hi = b * 4;
+    return (b - a) * 4;
+}
+
+extern "C" int nvo_adam_exchange_step(void* stream, int64_t n, int32_t rank, int32_t world, const void* h_peer_params, const void* h_peer_grads,
+                                      const void* h_peer_flags, float* exp_avg_slice, float* exp_avg_sq_slice, int32_t* step, float lr, float beta1,
+                                      float beta2, float eps, float grad_scale) {
+    NVO_CHECK(n > 0 && (n & 3) == 0, "adam_exchange_step: flat size %lld must be a positive multiple of 4 floats", (long long)n);
+    NVO_CHECK(world >= 1 && world <= NVO_MAX_PEERS && rank >= 0 && rank < world, "adam_exchange_step: bad rank/world %d/%d", rank, world);
+    NVO_CHECK(h_peer_params && h_peer_grads && h_peer_flags && exp_avg_slice && exp_avg_sq_slice && step, "adam_exchange_step: null pointer");
+    PeerSet ps;
+    for (int k = 0; k < NVO_MAX_PEERS; ++k) {
+        ps.params[k] = k < world ? ((float* const*)h_peer_params)[k] : nullptr;
+        ps.grads[k] = k < world ? ((const float* const*)h_peer_grads)[k] : nullptr;
+        ps.flags[k] = k < world ? ((int* const*)h_peer_flags)[k] : nullptr;
+        if (k < world) NVO_CHECK(ps.params[k] && ps.grads[k] && ps.flags[k], "adam_exchange_step: null peer pointer for rank %d", k);
+    }
+    int64_t lo, hi;
+    nvo_exchange_slice(n, rank, world, &lo, &hi);
+    exchange_fn fn = nullptr;
+    switch (world) {
+        case 1: fn = k_exchange_adam<1>; break;
+        case 2: fn = k_exchange_adam<2>; break;
+        case 4: fn = k_exchange_adam<4>; break;
+        case 8: fn = k_exchange_adam<8>; break;
+        default: NVO_CHECK(false, "adam_exchange_step: world size %d unsupported (1, 2, 4 or 8 GPUs of one NVSwitch domain)", world);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    // persistent grid: as many 512-thread CTAs as are co-resident, each thread keeps `world` 16-byte peer loads in flight per trip
+    const int64_t items = (hi - lo) / 4;
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 512, 0);
+    const unsigned int grid = (unsigned int)max((int64_t)1, min((int64_t)nvo_sm_count() * max(per_sm, 1), (items + 511) / 512));
+    fn<<<grid, 512, 0, st>>>(ps, rank, lo / 4, hi / 4, exp_avg_slice, exp_avg_sq_slice, step, lr, beta1, beta2, eps, grad_scale);
+    NVO_CUDA_LAUNCH_CHECK("adam_exchange_step");
+    k_tick_step<<<1, 1, 0, st>>>(step);
+    NVO_CUDA_LAUNCH_CHECK("adam_exchange_step(tick)");
+    return 0;
+}
+
+// ---- peer-visible allocations (CUDA IPC) ----------------------------------------------------------------------------------
+extern "C" int nvo_peer_alloc(int64_t bytes, void* h_ptr_out, void* h_handle64_out) {
+    NVO_CHECK(bytes > 0 && h_ptr_out && h_handle64_out, "peer_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+    NVO_CHECK(e == cudaSuccess, "peer_alloc: cudaMalloc(%lld): %s", (long long)bytes, cudaGetErrorString(e));
+    e = cudaMemset(p, 0, (size_t)bytes);
+    NVO_CHECK(e == cudaSuccess, "peer_alloc: cudaMemset: %s", cudaGetErrorString(e));
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        NVO_CHECK(false, "peer_alloc: cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    }
+    memcpy(h_handle64_out, &h, 64);
+    *(void**)h_ptr_out = p;
+    return 0;
+}
+
+extern "C" int nvo_peer_open(const void* h_handle64, void* h_ptr_out) {
+    NVO_CHECK(h_handle64 && h_ptr_out, "peer_open: null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, h_handle64, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    NVO_CHECK(e == cudaSuccess, "peer_open: cudaIpcOpenMemHandle: %s (peer access over NVLink is required for the fused exchange)", cudaGetErrorString(e));
+    *(void**)h_ptr_out = p;
+    return 0;
+}
+
+extern "C" int nvo_peer_close(void* ptr) {
+    if (!ptr) return 0;
+    cudaError_t e = cudaIpcCloseMemHandle(ptr);
+    NVO_CHECK(e == cudaSuccess, "peer_close: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int nvo_peer_free(void* ptr) {
+    if (!ptr) return 0;
+    cudaError_t e = cudaFree(ptr);
+    NVO_CHECK(e == cudaSuccess, "peer_free: %s", cudaGetErrorString(e));
+    return 0;
+}

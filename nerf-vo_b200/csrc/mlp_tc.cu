@@ -342,8 +342,10 @@ __global__ void __launch_bounds__(TM) k_mlp_tc_fwd(const __grid_constant__ TcP p
                     float v[16];
                     tmem_ld16(trow + c16, v);
                     if (live) {
+                        // only the real outputs go through the activation (a 3-wide sigmoid / tanh head must not pay for 16 columns)
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = tc_act_fwd(v[j] + sb[c16 + j], act) * m;
+                        for (int j = 0; j < 16; ++j)
+                            if (c16 + j < N) v[j] = tc_act_fwd(v[j] + sb[c16 + j], act) * m;
                         float* dst = y + row * N + c16;
                         if (N - c16 >= 16 && (N & 3) == 0) {
 #pragma unroll

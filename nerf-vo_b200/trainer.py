@@ -5,8 +5,11 @@ NS/engine/trainer.py:455-494, NS/pipelines/base_pipeline.py:291-304), restated f
   * every parameter lives in ONE flat fp32 buffer, gradients in another; backward kernels scatter straight into the flat
     gradient (no per-tensor .grad, no AccumulateGrad pass), a single fused Adam launch updates everything;
   * the whole step is captured in CUDA graphs (at 4096 rays the step is launch-bound, SURVEY §7) and replayed;
-  * data parallel: rays are sharded across ranks, parameters replicated, ONE NCCL sum-all-reduce of the flat gradient per
-    step, mean taken inside the Adam kernel (DDP semantics, NS/pipelines/base_pipeline.py:281-283).
+  * data parallel: rays are sharded across ranks, parameters replicated; the gradient exchange is fused with the optimizer
+    (`exchange="fused"`, csrc/exchange.cu: reduce-scatter by NVLink peer loads -> Adam on the rank's slice -> all-gather by
+    peer stores, one kernel, the step stays a single CUDA graph) or, as the library arm, ONE NCCL sum-all-reduce of the flat
+    gradient followed by the replicated Adam (`exchange="nccl"`); both give DDP's mean-gradient semantics
+    (NS/pipelines/base_pipeline.py:281-283).
 """
 from __future__ import annotations
 
@@ -23,12 +26,16 @@ from .rays import RayBundle
 
 class MappingTrainer:
     def __init__(self, model: ExtendedNerfactoModel, num_rays: int, lr: float = 1e-2, eps: float = 1e-15, betas=(0.9, 0.999),
-                 use_cuda_graph: bool = True, with_normals: bool = True, device: Optional[torch.device] = None):
+                 use_cuda_graph: bool = True, with_normals: bool = True, device: Optional[torch.device] = None, exchange: str = "fused"):
         self.model = model
         self.device = device or next(model.parameters()).device
         self.B = int(num_rays)
         self.lr, self.eps, self.betas = lr, eps, betas
         self.world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if exchange not in ("fused", "nccl"):
+            raise ValueError(f"exchange must be 'fused' (peer-memory reduce-scatter + Adam + all-gather kernel) or 'nccl', got {exchange!r}")
+        self.exchange = exchange if self.world_size > 1 else "local"
+        self.peer = None
         self.use_cuda_graph = use_cuda_graph
         self.with_normals = with_normals
         model.train()
@@ -43,10 +50,18 @@ class MappingTrainer:
         # 16-byte alignment of every tensor start keeps float4 / float2 accesses legal: pad each to a multiple of 4 floats
         sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]
         total = sum(sizes)
-        self.flat = torch.zeros(total, dtype=torch.float32, device=self.device)
-        self.grad = torch.zeros_like(self.flat)
-        self.exp_avg = torch.zeros_like(self.flat)
-        self.exp_avg_sq = torch.zeros_like(self.flat)
+        if self.exchange == "fused":
+            # parameters and gradients live in peer-mapped (CUDA IPC) allocations; Adam moments only for the slice this rank owns
+            from .peer import PeerBuffers
+
+            self.peer = PeerBuffers(total, self.device)
+            self.flat, self.grad = self.peer.params, self.peer.grads
+            self.exp_avg, self.exp_avg_sq = self.peer.exp_avg, self.peer.exp_avg_sq
+        else:
+            self.flat = torch.zeros(total, dtype=torch.float32, device=self.device)
+            self.grad = torch.zeros_like(self.flat)
+            self.exp_avg = torch.zeros_like(self.flat)
+            self.exp_avg_sq = torch.zeros_like(self.flat)
         self.step_count = torch.zeros(1, dtype=torch.int32, device=self.device)
         off = 0
         self._views = []
@@ -129,8 +144,16 @@ class MappingTrainer:
         self._terms, self._term_weights = terms, weights
 
     def _optimizer(self) -> None:
+        if self.peer is not None:
+            self.peer.adam_exchange_step(self.step_count, self.lr, self.betas[0], self.betas[1], self.eps)
+            return
         ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.betas[0], self.betas[1], self.eps,
                       1.0 / self.world_size)
+
+    def _exchange(self) -> None:
+        """NCCL arm: sum-all-reduce of the flat gradient (the fused arm exchanges inside the optimizer kernel)."""
+        if self.exchange == "nccl":
+            sharding.allreduce_gradient_(self.grad)
 
     def set_inputs(self, rays: Dict[str, torch.Tensor], targets: Dict[str, torch.Tensor], jitters: Optional[List[torch.Tensor]] = None,
                    non_blocking: bool = True) -> int:
@@ -161,7 +184,7 @@ class MappingTrainer:
             for _ in range(warmup):
                 self.model.proposal_sampler._steps_since_update = 10 ** 6  # always update the proposal networks (worst case)
                 self._forward_backward()
-                sharding.allreduce_gradient_(self.grad)
+                self._exchange()
                 self._optimizer()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
@@ -172,9 +195,9 @@ class MappingTrainer:
         self._graph_fb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph_fb):
             self._forward_backward()
-            if self.world_size == 1:
+            if self.exchange != "nccl":
                 self._optimizer()
-        if self.world_size > 1:
+        if self.exchange == "nccl":
             self._graph_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph_opt):
                 self._optimizer()
@@ -184,7 +207,7 @@ class MappingTrainer:
         """Runs one step on the current contents of the static input buffers; returns the (device) loss scalar."""
         if self._graph_fb is not None:
             self._graph_fb.replay()
-            if self.world_size > 1:
+            if self.exchange == "nccl":
                 sharding.allreduce_gradient_(self.grad)
                 self._graph_opt.replay()
         else:
@@ -193,7 +216,7 @@ class MappingTrainer:
             n0 = _lib.launch_count()
             self.model.proposal_sampler._steps_since_update = 10 ** 6
             self._forward_backward()
-            sharding.allreduce_gradient_(self.grad)
+            self._exchange()
             self._optimizer()
             self.launches_per_step = _lib.launch_count() - n0
         return self.loss

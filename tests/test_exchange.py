@@ -1,0 +1,109 @@
+"""Fused gradient exchange + Adam (csrc/exchange.cu, nerf-vo_b200/peer.py).
+
+CPU: the slice arithmetic (host mirror vs the library).  GPU: the kernel at world_size 1 against torch.optim.Adam, and —
+when the box has two GPUs — two ranks exchanging through NVLink peer memory against the NCCL all-reduce + replicated Adam arm."""
+import ctypes
+import os
+import socket
+
+import pytest
+import torch
+
+
+def test_slice_ranges_cover_the_flat_buffer_cpu():
+    import nerf_vo_b200 as nv
+    from nerf_vo_b200 import peer
+
+    lib = nv._lib.load()
+    for n in (4, 8, 1000, 18_432_516, 73_000_000):
+        for world in (1, 2, 4, 8):
+            prev = 0
+            for r in range(world):
+                lo, hi = ctypes.c_int64(), ctypes.c_int64()
+                length = lib.nvo_exchange_slice(n, r, world, ctypes.addressof(lo), ctypes.addressof(hi))
+                assert (lo.value, hi.value) == peer.slice_range(n, r, world)
+                assert length == hi.value - lo.value and lo.value % 4 == 0
+                assert lo.value == prev or lo.value == hi.value
+                prev = max(prev, hi.value)
+            assert prev == (n + 3) // 4 * 4
+
+
+@pytest.mark.gpu
+def test_exchange_world1_matches_torch_adam():
+    import nerf_vo_b200 as nv
+    from nerf_vo_b200.peer import PeerBuffers
+
+    dev = torch.device("cuda", 0)
+    n = 1 << 20
+    bufs = PeerBuffers(n, dev)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    p0 = torch.randn(n, generator=g)
+    bufs.params.copy_(p0)
+    ref = p0.clone().to(dev).requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-2, eps=1e-15)
+    step = torch.zeros(1, dtype=torch.int32, device=dev)
+    for it in range(4):
+        grad = torch.randn(n, generator=g).to(dev) * 10.0 ** (-it)
+        bufs.grads.copy_(grad)
+        bufs.adam_exchange_step(step, 1e-2, 0.9, 0.999, 1e-15)
+        ref.grad = grad.clone()
+        opt.step()
+    torch.cuda.synchronize()
+    assert int(step) == 4 and bufs.error_word() == 0
+    # fp32 Adam, same formula; torch's foreach kernels may contract differently: tolerance 2e-6 absolute on O(1) parameters
+    assert float((bufs.params - ref.detach()).abs().max()) < 2e-6
+
+
+def _two_rank_worker(rank, world, port, tmp):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import nerf_vo_b200 as nv
+    from nerf_vo_b200 import ops
+    from nerf_vo_b200.peer import PeerBuffers
+
+    n = 4 * 1_000_003  # odd number of float4s: ragged last slice
+    bufs = PeerBuffers(n, dev)
+    g = torch.Generator(device="cpu").manual_seed(7)
+    p0 = torch.randn(n, generator=g)
+    bufs.params.copy_(p0)
+    # library arm: NCCL sum-all-reduce + replicated nvo_adam_step
+    flat, m, v = p0.clone().to(dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    step_a = torch.zeros(1, dtype=torch.int32, device=dev)
+    step_b = torch.zeros(1, dtype=torch.int32, device=dev)
+    worst = 0.0
+    for it in range(5):
+        gr = torch.Generator(device="cpu").manual_seed(100 * it + rank)
+        grad = torch.randn(n, generator=gr).to(dev)
+        bufs.grads.copy_(grad)
+        bufs.adam_exchange_step(step_a, 1e-2, 0.9, 0.999, 1e-15)
+        red = grad.clone()
+        dist.all_reduce(red)
+        ops.adam_step(flat, red, m, v, step_b, 1e-2, 0.9, 0.999, 1e-15, 1.0 / world)
+        torch.cuda.synchronize()
+        worst = max(worst, float((bufs.params - flat).abs().max()))
+    ok = worst == 0.0 if world == 2 else worst < 1e-6  # a + b is order-independent: two ranks are bit-exact
+    ok = ok and bufs.error_word() == 0
+    torch.save({"ok": bool(ok), "worst": worst}, os.path.join(tmp, f"r{rank}.pt"))
+    dist.barrier()
+    bufs.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_exchange_two_ranks_matches_nccl_arm(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_two_rank_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        out = torch.load(os.path.join(str(tmp_path), f"r{r}.pt"))
+        assert out["ok"], (r, out)

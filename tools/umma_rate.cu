@@ -1,0 +1,93 @@
+// Standalone probe (not product code): issue rate of tcgen05.mma kind::f16, cta_group::1, M=128 with the no-swizzle canonical
+// shared-memory layout the MLP kernels use, for the three operand arrangements (forward K-major/K-major, dgrad K-major/MN-major,
+// wgrad MN-major/MN-major) and several N.  One CTA per SM, R back-to-back MMAs into one accumulator, clock64 around issue..commit.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o umma_rate umma_rate.cu
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t swz) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)swz << 61;
+    return d;
+}
+__device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(adesc),
+                 "l"(bdesc), "r"(idesc), "r"(acc)
+                 : "memory");
+}
+
+// mode 0: fwd (A K-major lbo 2048/sbo 128, B K-major lbo N*16/sbo 128); 1: dgrad (B MN-major lbo 128/sbo N*16); 2: wgrad (both MN-major lbo 128/sbo 2048)
+// mode 3: fwd with 128B-swizzle descriptors (K-major, sbo 1024) — data is garbage, only the rate matters
+__global__ void __launch_bounds__(128) rate(int mode, int N, int R, int two_acc, long long* out) {
+    extern __shared__ __align__(1024) unsigned char dyn[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 65536 / 4; i += 128) reinterpret_cast<uint32_t*>(dyn)[i] = 0x3C003C00u;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base;
+    long long t0 = 0, t1 = 0;
+    if (tid == 0) {
+        const uint32_t a0 = smem_u32(dyn), b0 = smem_u32(dyn + 32768);
+        uint32_t idesc;
+        uint64_t ad, bd;
+        if (mode == 0) { idesc = make_idesc(128, N, 0, 0); ad = make_desc(a0, 2048, 128, 0); bd = make_desc(b0, N * 16, 128, 0); }
+        else if (mode == 1) { idesc = make_idesc(128, N, 0, 1); ad = make_desc(a0, 2048, 128, 0); bd = make_desc(b0, 128, N * 16, 0); }
+        else if (mode == 2) { idesc = make_idesc(128, N, 1, 1); ad = make_desc(a0, 128, 2048, 0); bd = make_desc(b0, 128, 2048, 0); }
+        else { idesc = make_idesc(128, N, 0, 0); ad = make_desc(a0, 16, 1024, 2); bd = make_desc(b0, 16, 1024, 2); }
+        t0 = clock64();
+        for (int r = 0; r < R; ++r) mma_f16(tmem + (two_acc ? (r & 1) * 256 : 0), ad, bd, idesc, r > 1);
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+    }
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0) : "memory");
+    if (tid == 0) {
+        t1 = clock64();
+        out[blockIdx.x] = t1 - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+int main() {
+    long long* d;
+    cudaMalloc(&d, 148 * 8);
+    long long h[148];
+    cudaFuncSetAttribute(rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    const int R = 4096;
+    const char* names[] = {"fwd  K/K  no-swizzle", "dgrad K/MN no-swizzle", "wgrad MN/MN no-swizzle", "fwd  K/K  128B-swizzle"};
+    for (int mode = 0; mode < 4; ++mode)
+        for (int N : {16, 32, 64, 80, 128, 256})
+            for (int two = 0; two < 2; ++two) {
+                if (mode == 2 && N > 128) continue;
+                rate<<<148, 128, 65536>>>(mode, N, R, two, d);
+                cudaError_t e = cudaDeviceSynchronize();
+                if (e != cudaSuccess) { printf("%s N=%d: %s\n", names[mode], N, cudaGetErrorString(e)); return 1; }
+                cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+                double s = 0;
+                for (int i = 0; i < 148; ++i) s += h[i];
+                printf("%-24s N=%3d acc=%d : %.1f cycles/MMA (M=128,K=16)  floor=%.0f\n", names[mode], N, two + 1, s / 148 / R, 128.0 * N / 256);
+            }
+    return 0;
+}
