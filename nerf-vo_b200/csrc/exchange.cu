@@ -63,8 +63,10 @@ __device__ __forceinline__ bool wait_all(const int* flags, int base, int world, 
     return __syncthreads_and(ok);
 }
 
-template <int W>
-__global__ void __launch_bounds__(512) k_exchange_adam(const __grid_constant__ PeerSet ps, int rank, int64_t lo4, int64_t hi4, float* __restrict__ m,
+// U float4 items per thread and trip: U*W independent 16-byte peer loads in flight per thread (NVLink round trips are ~2 us; the
+// kernel is latency-bound unless every SM keeps tens of KB outstanding)
+template <int W, int U>
+__global__ void __launch_bounds__(256) k_exchange_adam(const __grid_constant__ PeerSet ps, int rank, int64_t lo4, int64_t hi4, float* __restrict__ m,
                                                        float* __restrict__ v, const int* __restrict__ step_ptr, float lr, float b1, float b2, float eps,
                                                        float grad_scale) {
     int* my_flags = ps.flags[rank];
@@ -80,17 +82,28 @@ __global__ void __launch_bounds__(512) k_exchange_adam(const __grid_constant__ P
     const float t = (float)epoch;
     const float step_size = lr / (1.f - powf(b1, t)), inv_bc2 = 1.f / sqrtf(1.f - powf(b2, t));
     // ---- 2-4. reduce-scatter (peer loads) -> Adam -> all-gather (peer stores) on the own slice -------------------------
-    for (int64_t i = lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi4; i += (int64_t)gridDim.x * blockDim.x) {
-        float4 g[W];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi4; i0 += stride * U) {
+        float4 g[U][W];
 #pragma unroll
-        for (int k = 0; k < W; ++k) g[k] = ld_peer_f4(ps.grads[k] + 4 * i);  // W independent 16-byte loads in flight
-        float4 gs = g[0];
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < hi4) {
 #pragma unroll
-        for (int k = 1; k < W; ++k) gs.x += g[k].x, gs.y += g[k].y, gs.z += g[k].z, gs.w += g[k].w;
-        const int64_t j = i - lo4;
-        float4 pp = reinterpret_cast<const float4*>(ps.params[rank])[i];
-        float4 mm = reinterpret_cast<float4*>(m)[j];
-        float4 vv = reinterpret_cast<float4*>(v)[j];
+                for (int k = 0; k < W; ++k) g[u][k] = ld_peer_f4(ps.grads[k] + 4 * i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i >= hi4) break;
+            float4 gs = g[u][0];
+#pragma unroll
+            for (int k = 1; k < W; ++k) gs.x += g[u][k].x, gs.y += g[u][k].y, gs.z += g[u][k].z, gs.w += g[u][k].w;
+            const int64_t j = i - lo4;
+            float4 pp = reinterpret_cast<const float4*>(ps.params[rank])[i];
+            float4 mm = reinterpret_cast<float4*>(m)[j];
+            float4 vv = reinterpret_cast<float4*>(v)[j];
 #define UPD(c)                                                        \
     {                                                                 \
         const float gr = gs.c * grad_scale;                           \
@@ -98,12 +111,13 @@ __global__ void __launch_bounds__(512) k_exchange_adam(const __grid_constant__ P
         vv.c = b2 * vv.c + (1.f - b2) * gr * gr;                      \
         pp.c -= step_size * mm.c / (sqrtf(vv.c) * inv_bc2 + eps);     \
     }
-        UPD(x) UPD(y) UPD(z) UPD(w)
+            UPD(x) UPD(y) UPD(z) UPD(w)
 #undef UPD
-        reinterpret_cast<float4*>(m)[j] = mm;
-        reinterpret_cast<float4*>(v)[j] = vv;
+            reinterpret_cast<float4*>(m)[j] = mm;
+            reinterpret_cast<float4*>(v)[j] = vv;
 #pragma unroll
-        for (int k = 0; k < W; ++k) st_peer_f4(ps.params[k] + 4 * i, pp);
+            for (int k = 0; k < W; ++k) st_peer_f4(ps.params[k] + 4 * i, pp);
+        }
     }
     // ---- 5. replicas written: last CTA signals the peers and waits for theirs -----------------------------------------------
     __threadfence_system();
@@ -154,19 +168,19 @@ extern "C" int nvo_adam_exchange_step(void* stream, int64_t n, int32_t rank, int
     nvo_exchange_slice(n, rank, world, &lo, &hi);
     exchange_fn fn = nullptr;
     switch (world) {
-        case 1: fn = k_exchange_adam<1>; break;
-        case 2: fn = k_exchange_adam<2>; break;
-        case 4: fn = k_exchange_adam<4>; break;
-        case 8: fn = k_exchange_adam<8>; break;
+        case 1: fn = k_exchange_adam<1, 4>; break;
+        case 2: fn = k_exchange_adam<2, 4>; break;
+        case 4: fn = k_exchange_adam<4, 2>; break;
+        case 8: fn = k_exchange_adam<8, 1>; break;
         default: NVO_CHECK(false, "adam_exchange_step: world size %d unsupported (1, 2, 4 or 8 GPUs of one NVSwitch domain)", world);
     }
     cudaStream_t st = (cudaStream_t)stream;
-    // persistent grid: as many 512-thread CTAs as are co-resident, each thread keeps `world` 16-byte peer loads in flight per trip
+    // persistent grid: as many 256-thread CTAs as are co-resident (every CTA takes part in the flag waits, so none may queue)
     const int64_t items = (hi - lo) / 4;
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 512, 0);
-    const unsigned int grid = (unsigned int)max((int64_t)1, min((int64_t)nvo_sm_count() * max(per_sm, 1), (items + 511) / 512));
-    fn<<<grid, 512, 0, st>>>(ps, rank, lo / 4, hi / 4, exp_avg_slice, exp_avg_sq_slice, step, lr, beta1, beta2, eps, grad_scale);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0);
+    const unsigned int grid = (unsigned int)max((int64_t)1, min((int64_t)nvo_sm_count() * max(per_sm, 1), (items + 255) / 256));
+    fn<<<grid, 256, 0, st>>>(ps, rank, lo / 4, hi / 4, exp_avg_slice, exp_avg_sq_slice, step, lr, beta1, beta2, eps, grad_scale);
     NVO_CUDA_LAUNCH_CHECK("adam_exchange_step");
     k_tick_step<<<1, 1, 0, st>>>(step);
     NVO_CUDA_LAUNCH_CHECK("adam_exchange_step(tick)");

@@ -29,7 +29,8 @@
 #include <cuda_fp16.h>
 #include "nvo_common.cuh"
 
-#define TM 128           // samples per tile == threads per CTA
+#define TM 128           // samples per tile
+#define NT 256           // threads per CTA: warp w owns TMEM lanes 32*(w&3).. (rows of the tile) and the column half (w>>2)
 #define CHUNK_B 2048     // bytes of one 8-feature chunk of a 128-row tile
 #define MAXW 64
 #define TC_MAX_LAYERS 4
@@ -43,8 +44,11 @@ struct TcP {
     int img_bytes;
     int saved_chunk_off[TC_MAX_LAYERS];                  // chunk offset of layer l's output inside a saved tile
     int saved_chunks;                                    // chunks per saved tile
-    int a_off[TC_MAX_LAYERS];                            // backward: byte offset of layer l's INPUT tile inside a stage
-    int stage_bytes;                                     // backward: bytes of one prefetch stage
+    int a_off[TC_MAX_LAYERS];                            // backward: byte offset of layer l's INPUT tile inside the stage
+    int stage_bytes;                                     // backward: bytes of the activation stage (every layer's input tile + ones/zero chunks)
+    int wg_t[TC_MAX_LAYERS];                             // backward: 1 = weight gradient accumulated transposed (D[in][out], N = 16 columns)
+    int dw_col[TC_MAX_LAYERS];                           // backward: first TMEM column of layer l's weight-gradient accumulator
+    int tmem_cols;                                       // backward: TMEM columns to allocate (256 or 512)
     int n_params;
 };
 
@@ -171,10 +175,17 @@ __device__ __forceinline__ float act_bwd_t(float a) {
     return tc_act_bwd(a, ACT);
 }
 
+// column range of a K- or N-wide accumulator that column-half `half` (warps 0-3 / 4-7) of the CTA handles
+__device__ __forceinline__ void half_range(int width, int half, int& c0, int& c1) {
+    const int split = width > 32 ? 32 : (width == 32 ? 16 : width);
+    c0 = half ? split : 0;
+    c1 = half ? width : split;
+}
+
 // hidden layer of the forward: NC (16 | 32) accumulator columns -> + bias -> activation -> fp16 -> next layer's A tile (+ saved)
 template <int ACT, int NC>
 __device__ __forceinline__ void fwd_hidden_cols(uint32_t taddr, const float* __restrict__ sb, unsigned char* __restrict__ sAct, uint4* __restrict__ saved_tile,
-                                                int c8_0, int tid) {
+                                                int c8_0, int r) {
     float v[NC];
     if (NC == 32)
         tmem_ld32(taddr, v);
@@ -191,21 +202,22 @@ __device__ __forceinline__ void fwd_hidden_cols(uint32_t taddr, const float* __r
 #pragma unroll
     for (int q = 0; q < NC / 8; ++q) {
         const uint4 u = pack8(v + q * 8);
-        *reinterpret_cast<uint4*>(sAct + (c8_0 + q) * CHUNK_B + tid * 16) = u;
-        if (saved_tile) saved_tile[(c8_0 + q) * TM + tid] = u;  // TMH: coalesced 16-byte stores
+        *reinterpret_cast<uint4*>(sAct + (c8_0 + q) * CHUNK_B + r * 16) = u;
+        if (saved_tile) saved_tile[(c8_0 + q) * TM + r] = u;  // TMH: coalesced 16-byte stores
     }
 }
 template <int ACT>
-__device__ __forceinline__ void fwd_hidden_layer(uint32_t trow, int np, const float* __restrict__ sb, unsigned char* __restrict__ sAct,
-                                                 uint4* __restrict__ saved_tile, int tid) {
-    int c = 0;
-    for (; c + 32 <= np; c += 32) fwd_hidden_cols<ACT, 32>(trow + c, sb + c, sAct, saved_tile, c >> 3, tid);
-    if (c < np) fwd_hidden_cols<ACT, 16>(trow + c, sb + c, sAct, saved_tile, c >> 3, tid);
+__device__ __forceinline__ void fwd_hidden_layer(uint32_t trow, int np, int half, const float* __restrict__ sb, unsigned char* __restrict__ sAct,
+                                                 uint4* __restrict__ saved_tile, int r) {
+    int c, c1;
+    half_range(np, half, c, c1);
+    for (; c + 32 <= c1; c += 32) fwd_hidden_cols<ACT, 32>(trow + c, sb + c, sAct, saved_tile, c >> 3, r);
+    if (c < c1) fwd_hidden_cols<ACT, 16>(trow + c, sb + c, sAct, saved_tile, c >> 3, r);
 }
 
 // hidden layer of the backward: NC dgrad columns -> x act'(a) -> fp16 -> the next dZ tile
 template <int ACT, int NC>
-__device__ __forceinline__ void bwd_hidden_cols(uint32_t taddr, const unsigned char* __restrict__ sA, unsigned char* __restrict__ sGn, int c8_0, int tid) {
+__device__ __forceinline__ void bwd_hidden_cols(uint32_t taddr, const unsigned char* __restrict__ sA, unsigned char* __restrict__ sGn, int c8_0, int r) {
     float v[NC];
     if (NC == 32)
         tmem_ld32(taddr, v);
@@ -214,7 +226,7 @@ __device__ __forceinline__ void bwd_hidden_cols(uint32_t taddr, const unsigned c
 #pragma unroll
     for (int q = 0; q < NC / 8; ++q) {
         if (ACT != NVO_ACT_NONE) {
-            const uint4 a = *reinterpret_cast<const uint4*>(sA + (c8_0 + q) * CHUNK_B + tid * 16);
+            const uint4 a = *reinterpret_cast<const uint4*>(sA + (c8_0 + q) * CHUNK_B + r * 16);
             const __half2* h = reinterpret_cast<const __half2*>(&a);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -223,14 +235,15 @@ __device__ __forceinline__ void bwd_hidden_cols(uint32_t taddr, const unsigned c
                 v[q * 8 + 2 * j + 1] *= act_bwd_t<ACT>(f.y);
             }
         }
-        *reinterpret_cast<uint4*>(sGn + (c8_0 + q) * CHUNK_B + tid * 16) = pack8(v + q * 8);
+        *reinterpret_cast<uint4*>(sGn + (c8_0 + q) * CHUNK_B + r * 16) = pack8(v + q * 8);
     }
 }
 template <int ACT>
-__device__ __forceinline__ void bwd_hidden_layer(uint32_t trow, int kp, const unsigned char* __restrict__ sA, unsigned char* __restrict__ sGn, int tid) {
-    int c = 0;
-    for (; c + 32 <= kp; c += 32) bwd_hidden_cols<ACT, 32>(trow + c, sA, sGn, c >> 3, tid);
-    if (c < kp) bwd_hidden_cols<ACT, 16>(trow + c, sA, sGn, c >> 3, tid);
+__device__ __forceinline__ void bwd_hidden_layer(uint32_t trow, int kp, int half, const unsigned char* __restrict__ sA, unsigned char* __restrict__ sGn, int r) {
+    int c, c1;
+    half_range(kp, half, c, c1);
+    for (; c + 32 <= c1; c += 32) bwd_hidden_cols<ACT, 32>(trow + c, sA, sGn, c >> 3, r);
+    if (c < c1) bwd_hidden_cols<ACT, 16>(trow + c, sA, sGn, c >> 3, r);
 }
 
 // ================================================================================================================
@@ -253,13 +266,15 @@ __global__ void __launch_bounds__(256) k_tc_pack(const __grid_constant__ TcP p, 
 
 // ================================================================================================================
 // forward.  smem: [in0 16 KB][in1 16 KB][act 16 KB][weight image][mbar_mma, mbar_w, mbar_in0, mbar_in1, tmem ptr]
+// 256 threads: warp w reads TMEM lanes 32*(w&3).. (tile rows) and handles the column half (w>>2) of every epilogue, so a
+// layer's TMEM -> bias -> activation -> fp16 -> shared chain is half as long per warp and twice as many warps hide it.
 // ================================================================================================================
 #define FWD_IN0 0
 #define FWD_IN1 (8 * CHUNK_B)
 #define FWD_ACT (16 * CHUNK_B)
 #define FWD_W (24 * CHUNK_B)
 
-__global__ void __launch_bounds__(TM) k_mlp_tc_fwd(const __grid_constant__ TcP p, int64_t n, const unsigned char* __restrict__ x16,
+__global__ void __launch_bounds__(NT) k_mlp_tc_fwd(const __grid_constant__ TcP p, int64_t n, const unsigned char* __restrict__ x16,
                                                    const unsigned char* __restrict__ wimg, const float* __restrict__ row_mask, float* __restrict__ y,
                                                    uint4* __restrict__ saved, int smem_ctrl_off) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -269,7 +284,8 @@ __global__ void __launch_bounds__(TM) k_mlp_tc_fwd(const __grid_constant__ TcP p
     uint64_t* mbar_w = mbar_mma + 1;
     uint64_t* mbar_in = mbar_mma + 2;  // [2]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mbar_mma + 4);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, half = warp >> 2;
+    const int r = ((warp & 3) << 5) | (tid & 31);  // row of the tile == TMEM lane
     const int64_t n_tiles = (n + TM - 1) / TM;
     const uint32_t in_bytes = (uint32_t)p.k0pad * 256u;
     if (warp == 0) {
@@ -292,13 +308,13 @@ __global__ void __launch_bounds__(TM) k_mlp_tc_fwd(const __grid_constant__ TcP p
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     mbar_wait(mbar_w, 0);
     uint32_t phase = 0;
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
-        const int64_t row = tile * TM + tid;
+        const int64_t row = tile * TM + r;
         const bool live = row < n;
         unsigned char* sIn = smem + (buf ? FWD_IN1 : FWD_IN0);
         // prefetch the next tile's input: the other buffer was last read by layer-0 MMAs of the previous tile (completed)
@@ -326,23 +342,23 @@ __global__ void __launch_bounds__(TM) k_mlp_tc_fwd(const __grid_constant__ TcP p
             if (!last) {
                 uint4* saved_tile = saved ? saved + (tile * p.saved_chunks + p.saved_chunk_off[l]) * TM : nullptr;
                 if (act == NVO_ACT_RELU)
-                    fwd_hidden_layer<NVO_ACT_RELU>(trow, np, sb, sAct, saved_tile, tid);
+                    fwd_hidden_layer<NVO_ACT_RELU>(trow, np, half, sb, sAct, saved_tile, r);
                 else if (act == NVO_ACT_NONE)
-                    fwd_hidden_layer<NVO_ACT_NONE>(trow, np, sb, sAct, saved_tile, tid);
+                    fwd_hidden_layer<NVO_ACT_NONE>(trow, np, half, sb, sAct, saved_tile, r);
                 else if (act == NVO_ACT_SIGMOID)
-                    fwd_hidden_layer<NVO_ACT_SIGMOID>(trow, np, sb, sAct, saved_tile, tid);
+                    fwd_hidden_layer<NVO_ACT_SIGMOID>(trow, np, half, sb, sAct, saved_tile, r);
                 else if (act == NVO_ACT_TANH)
-                    fwd_hidden_layer<NVO_ACT_TANH>(trow, np, sb, sAct, saved_tile, tid);
+                    fwd_hidden_layer<NVO_ACT_TANH>(trow, np, half, sb, sAct, saved_tile, r);
                 else
-                    fwd_hidden_layer<NVO_ACT_EXP>(trow, np, sb, sAct, saved_tile, tid);
+                    fwd_hidden_layer<NVO_ACT_EXP>(trow, np, half, sb, sAct, saved_tile, r);
             } else {
                 const int N = p.dims[l];
-                const float m = (live && row_mask) ? __ldg(row_mask + row) : 1.f;
-                for (int c16 = 0; c16 < N; c16 += 16) {
+                // 16-column groups alternate between the two column halves; only the real outputs go through the activation
+                for (int c16 = half * 16; c16 < N; c16 += 32) {
                     float v[16];
                     tmem_ld16(trow + c16, v);
                     if (live) {
-                        // only the real outputs go through the activation (a 3-wide sigmoid / tanh head must not pay for 16 columns)
+                        const float m = row_mask ? __ldg(row_mask + row) : 1.f;
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
                             if (c16 + j < N) v[j] = tc_act_fwd(v[j] + sb[c16 + j], act) * m;
@@ -371,9 +387,16 @@ __global__ void __launch_bounds__(TM) k_mlp_tc_fwd(const __grid_constant__ TcP p
 
 // ================================================================================================================
 // backward
-// smem: [G0 16 KB][G1 16 KB][stage0][stage1][weight image][mbar_mma, mbar_w, mbar_st0, mbar_st1, tmem ptr]
-//   stage = for every layer l: its input tile (kpad_l/8 chunks) + ones chunk + zero chunk (the bias-gradient columns)
-// TMEM (512 cols): [0,64) dgrad accumulator, [64 + 80*l, ...) dW_l (+ db_l in column kpad_l)
+// smem: [G0 16 KB][G1 16 KB][stage][weight image][mbar_mma, mbar_w, mbar_a[4], tmem ptr]
+//   stage = for every layer l: its input tile (kpad_l/8 chunks) + ones chunk + zero chunk (the bias-gradient columns); layers whose
+//           weight gradient is accumulated transposed come first (their M = 128 operand read runs 16 chunks past a_off[l])
+// TMEM: [0,64) dgrad accumulator, then per layer dW_l (+ db_l): kpad_l + 16 columns (rows = output features), or, for layers with
+//   <= 16 outputs, the TRANSPOSED product D[input i][output o] in 16 columns (rows = input features, row kpad_l = db).  The
+//   three-layer colour head then needs 64 + 80 + 80 + 16 = 240 columns, so TWO CTAs fit one SM (256 columns each) and one CTA's
+//   MMAs / bulk copies overlap the other's epilogue.
+// The stage is single-buffered per layer with one mbarrier each: as soon as the commit of layer l-1's dgrad shows that layer l's
+// wgrad MMAs have retired, the NEXT tile's input tile of layer l is fetched into the same buffer (bulk copy), i.e. the stage is
+// refilled progressively behind the backward sweep instead of holding two whole copies.
 // ================================================================================================================
 __global__ void k_absmax_scale(int64_t count, const float* __restrict__ dy, float* __restrict__ scale_bits) {
     // scale_bits[0] accumulates max|dy| as an int-ordered float (non-negative)
@@ -395,14 +418,15 @@ __device__ __forceinline__ float grad_scale_from_max(float mx) {
 #define BWD_G1 (8 * CHUNK_B)
 #define BWD_STAGE (16 * CHUNK_B)
 
-__device__ __forceinline__ void bwd_prefetch(const TcP& p, unsigned char* stage, int64_t tile, const unsigned char* __restrict__ x16,
-                                             const unsigned char* __restrict__ saved, uint64_t* mbar) {
-    uint32_t total = (uint32_t)p.k0pad * 256u;
-    for (int l = 1; l < p.n_layers; ++l) total += (uint32_t)p.kpad[l] * 256u;
-    mbar_expect_tx(mbar, total);
-    bulk_g2s(stage + p.a_off[0], x16 + tile * ((int64_t)p.k0pad * 256), (uint32_t)p.k0pad * 256u, mbar);
-    for (int l = 1; l < p.n_layers; ++l)
-        bulk_g2s(stage + p.a_off[l], saved + (tile * p.saved_chunks + p.saved_chunk_off[l - 1]) * (int64_t)CHUNK_B, (uint32_t)p.kpad[l] * 256u, mbar);
+// bulk copy of layer l's input tile of `tile` (l == 0: the network input, else the saved activations of layer l-1)
+__device__ __forceinline__ void bwd_fetch(const TcP& p, unsigned char* stage, int l, int64_t tile, const unsigned char* __restrict__ x16,
+                                          const unsigned char* __restrict__ saved, uint64_t* mbar) {
+    const uint32_t bytes = (uint32_t)p.kpad[l] * 256u;
+    mbar_expect_tx(mbar, bytes);
+    if (l == 0)
+        bulk_g2s(stage + p.a_off[0], x16 + tile * ((int64_t)p.k0pad * 256), bytes, mbar);
+    else
+        bulk_g2s(stage + p.a_off[l], saved + (tile * p.saved_chunks + p.saved_chunk_off[l - 1]) * (int64_t)CHUNK_B, bytes, mbar);
 }
 
 // dL/dz of the last layer for one (row, output o): dy * mask * act'(y)
@@ -417,10 +441,10 @@ __device__ __forceinline__ float dz_last_direct(const TcP& p, int64_t n, int64_t
 }
 // the first 16 outputs of a tile's row into registers (every field network has <= 16 real outputs); loads are issued one
 // tile ahead so their latency hides behind the previous tile's layer chain
-__device__ __forceinline__ void load_dz_last(const TcP& p, int64_t n, int64_t tile, int tid, int64_t n_tiles, const float* __restrict__ dy,
+__device__ __forceinline__ void load_dz_last(const TcP& p, int64_t n, int64_t tile, int r, int64_t n_tiles, const float* __restrict__ dy,
                                              const float* __restrict__ y, const float* __restrict__ row_mask, float* pre) {
     const int last = p.n_layers - 1, N = p.dims[last], act = p.acts[last];
-    const int64_t row = tile * TM + tid;
+    const int64_t row = tile * TM + r;
     const bool live = tile < n_tiles && row < n;
     const float m = (live && row_mask) ? __ldg(row_mask + row) : 1.f;
     if (live && N == 16 && act == NVO_ACT_NONE) {
@@ -442,29 +466,34 @@ __device__ __forceinline__ void load_dz_last(const TcP& p, int64_t n, int64_t ti
     }
 }
 
-__global__ void __launch_bounds__(TM) k_mlp_tc_bwd(const __grid_constant__ TcP p, int64_t n, const unsigned char* __restrict__ x16,
+__global__ void __launch_bounds__(NT) k_mlp_tc_bwd(const __grid_constant__ TcP p, int64_t n, const unsigned char* __restrict__ x16,
                                                    const unsigned char* __restrict__ wimg, const unsigned char* __restrict__ saved,
                                                    const float* __restrict__ y, const float* __restrict__ row_mask, const float* __restrict__ dy,
                                                    const float* __restrict__ dy_absmax, float absmax_hint, float* __restrict__ dx, float* __restrict__ dparams,
                                                    int smem_w_off, int smem_ctrl_off) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sW = smem + smem_w_off;
+    unsigned char* stage = smem + BWD_STAGE;
     uint64_t* mbar_mma = reinterpret_cast<uint64_t*>(smem + smem_ctrl_off);
     uint64_t* mbar_w = mbar_mma + 1;
-    uint64_t* mbar_st = mbar_mma + 2;  // [2]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mbar_mma + 4);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    uint64_t* mbar_a = mbar_mma + 2;  // [TC_MAX_LAYERS]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mbar_mma + 2 + TC_MAX_LAYERS);
+    const int tid = threadIdx.x, warp = tid >> 5, half = warp >> 2;
+    const int r = ((warp & 3) << 5) | (tid & 31);  // row of the tile == TMEM lane
     const int64_t n_tiles = (n + TM - 1) / TM;
-    // zero both dZ buffers and both stages once: padded chunks must hold finite values (they feed unused accumulator rows /
-    // columns), then write the constant ones / zero chunks behind every layer's input tile
-    for (int e = tid; e < (BWD_STAGE + 2 * p.stage_bytes) / 16; e += TM) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0, 0, 0, 0);
+    const int last = p.n_layers - 1;
+    // zero both dZ buffers and the stage once: padded chunks must hold finite values (they feed unused accumulator rows /
+    // columns), then write the constant ones chunk behind every layer's input tile (the zero chunk behind it stays zero)
+    for (int e = tid; e < (BWD_STAGE + p.stage_bytes) / 16; e += NT) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    for (int s = 0; s < 2; ++s)
-        for (int l = 0; l < p.n_layers; ++l)  // ones chunk: feature kpad_l == 1.0 for every row -> dW column kpad_l accumulates sum_s dZ = db
-            *reinterpret_cast<uint4*>(smem + BWD_STAGE + s * p.stage_bytes + p.a_off[l] + (p.kpad[l] >> 3) * CHUNK_B + tid * 16) =
-                make_uint4(0x00003C00u, 0, 0, 0);
+    if (tid < TM)
+        for (int l = 0; l < p.n_layers; ++l)  // ones chunk: feature kpad_l == 1.0 for every row -> the dW entry of feature kpad_l accumulates sum_s dZ = db
+            *reinterpret_cast<uint4*>(stage + p.a_off[l] + (p.kpad[l] >> 3) * CHUNK_B + tid * 16) = make_uint4(0x00003C00u, 0, 0, 0);
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr)) : "memory");
+        if (p.tmem_cols == 256)
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_ptr)) : "memory");
+        else
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     fence_async_smem();  // generic-proxy initialisation above ordered before the async-proxy (bulk copy / MMA) accesses
@@ -472,60 +501,58 @@ __global__ void __launch_bounds__(TM) k_mlp_tc_bwd(const __grid_constant__ TcP p
     if (tid == 0) {
         mbar_init(mbar_mma, 1);
         mbar_init(mbar_w, 1);
-        mbar_init(mbar_st, 1);
-        mbar_init(mbar_st + 1, 1);
+        for (int l = 0; l < TC_MAX_LAYERS; ++l) mbar_init(mbar_a + l, 1);
         fence_mbar_init();
         fence_async_smem();
         mbar_expect_tx(mbar_w, (uint32_t)p.img_bytes);
         bulk_g2s(sW, wimg, (uint32_t)p.img_bytes, mbar_w);
-        if ((int64_t)blockIdx.x < n_tiles) bwd_prefetch(p, smem + BWD_STAGE, blockIdx.x, x16, saved, mbar_st);
+        if ((int64_t)blockIdx.x < n_tiles)
+            for (int l = last; l >= 0; --l) bwd_fetch(p, stage, l, blockIdx.x, x16, saved, mbar_a + l);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const float gscale = grad_scale_from_max(absmax_hint > 0.f ? absmax_hint : __ldg(dy_absmax));
     const float inv_gscale = 1.f / gscale;
     mbar_wait(mbar_w, 0);
     uint32_t phase = 0;
-    const int last = p.n_layers - 1;
     int it = 0;
     float pre[16];
-    load_dz_last(p, n, blockIdx.x, tid, n_tiles, dy, y, row_mask, pre);
+    if (half == 0) load_dz_last(p, n, blockIdx.x, r, n_tiles, dy, y, row_mask, pre);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const int64_t row = tile * TM + tid;
+        const int64_t row = tile * TM + r;
         const bool live = row < n;
-        unsigned char* stage = smem + BWD_STAGE + buf * p.stage_bytes;
-        // every MMA of the previous tile has completed (its layer-0 commit sits behind the wgrad MMAs and was waited on), so
-        // the other stage and both dZ buffers are free: prefetch the next tile's activations while this one computes
-        if (tid == 0 && tile + gridDim.x < n_tiles)
-            bwd_prefetch(p, smem + BWD_STAGE + (buf ^ 1) * p.stage_bytes, tile + gridDim.x, x16, saved, mbar_st + (buf ^ 1));
+        const int64_t next_tile = tile + gridDim.x;
+        const uint32_t a_parity = (uint32_t)(it & 1);
         // ---- dZ of the last layer: dy * mask * act'(y) * scale -> fp16 G tile (buffer parity of `last`) -------------
-        // (dy, y, mask of THIS tile were loaded into registers during the previous tile; issue the next tile's loads now)
+        // (every MMA of the previous tile has retired: its layer-0 commit sits behind the wgrad MMAs and was waited on, so both dZ
+        // buffers are free.  dy, y, mask of THIS tile were loaded into registers during the previous tile; issue the next tile's now)
         {
             unsigned char* sG = smem + ((last & 1) ? BWD_G1 : BWD_G0);
             const int np = p.npad[last];
-            float cur[16];
+            if (half == 0) {
+                float cur[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) cur[j] = pre[j];
-            load_dz_last(p, n, tile + gridDim.x, tid, n_tiles, dy, y, row_mask, pre);
+                for (int j = 0; j < 16; ++j) cur[j] = pre[j];
+                load_dz_last(p, n, next_tile, r, n_tiles, dy, y, row_mask, pre);
 #pragma unroll
-            for (int c8 = 0; c8 < 2; ++c8) {  // np >= 16: the two register-resident chunks
-                float v[8];
+                for (int c8 = 0; c8 < 2; ++c8) {  // np >= 16: the two register-resident chunks
+                    float v[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = cur[c8 * 8 + j] * gscale;
-                *reinterpret_cast<uint4*>(sG + c8 * CHUNK_B + tid * 16) = pack8(v);
-            }
-            for (int c8 = 2; c8 < (np >> 3); ++c8) {  // wider output layers (not on the nerfacto path): direct loads
-                float v[8];
+                    for (int j = 0; j < 8; ++j) v[j] = cur[c8 * 8 + j] * gscale;
+                    *reinterpret_cast<uint4*>(sG + c8 * CHUNK_B + r * 16) = pack8(v);
+                }
+            } else {
+                for (int c8 = 2; c8 < (np >> 3); ++c8) {  // wider output layers (not on the nerfacto path): direct loads
+                    float v[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = dz_last_direct(p, n, row, c8 * 8 + j, dy, y, row_mask) * gscale;
-                *reinterpret_cast<uint4*>(sG + c8 * CHUNK_B + tid * 16) = pack8(v);
+                    for (int j = 0; j < 8; ++j) v[j] = dz_last_direct(p, n, row, c8 * 8 + j, dy, y, row_mask) * gscale;
+                    *reinterpret_cast<uint4*>(sG + c8 * CHUNK_B + r * 16) = pack8(v);
+                }
             }
         }
-        mbar_wait(mbar_st + buf, (uint32_t)((it >> 1) & 1));  // this tile's activations have landed
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -535,6 +562,7 @@ __global__ void __launch_bounds__(TM) k_mlp_tc_bwd(const __grid_constant__ TcP p
             unsigned char* sGn = smem + ((l & 1) ? BWD_G0 : BWD_G1);   // dZ_{l-1}
             unsigned char* sA = stage + p.a_off[l];                    // input activations of layer l (+ ones / zero chunks)
             const bool need_dgrad = l > 0 || dx != nullptr;
+            mbar_wait(mbar_a + l, a_parity);  // this tile's input activations of layer l have landed (read by the wgrad MMAs and by the epilogue)
             if (tid == 0) {
                 tc_fence_after();
                 const uint32_t g0 = smem_u32(sG), a0 = smem_u32(sA), w0 = smem_u32(sW + p.iw_off[l]);
@@ -546,49 +574,66 @@ __global__ void __launch_bounds__(TM) k_mlp_tc_bwd(const __grid_constant__ TcP p
                     if (l > 0) umma_commit(mbar_mma);  // the epilogue below only needs the dgrad accumulator
                 }
                 if (dparams) {
-                    // wgrad: D[feature o (M=128 padded)][input i (N = kp+16)] += sum_s dZ[s][o] * A[s][i]; both operands MN-major, K = samples.
-                    // Issued behind the dgrad commit: runs on the tensor pipe while the warps do the dgrad epilogue.
-                    const uint32_t idesc = umma_idesc(TM, kp + 16, 1, 1);
-                    const uint32_t dcol = tmem + 64 + DW_COLS * l;
-                    for (int k = 0; k < TM / 16; ++k)
-                        umma_f16(dcol, umma_desc(g0 + k * 256, 128, CHUNK_B), umma_desc(a0 + k * 256, 128, CHUNK_B), idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    // wgrad, both operands MN-major, K = the tile's 128 samples.  Issued behind the dgrad commit: runs on the tensor pipe
+                    // while the warps do the dgrad epilogue.
+                    const uint32_t dcol = tmem + (uint32_t)p.dw_col[l];
+                    const uint32_t acc0 = it > 0 ? 1u : 0u;
+                    if (p.wg_t[l]) {
+                        // narrow output layer: D[input i (M = 128, rows >= kp+16 unused)][output o (N = 16)] += sum_s Aext[s][i] * dZ[s][o]
+                        const uint32_t idesc = umma_idesc(TM, 16, 1, 1);
+                        for (int k = 0; k < TM / 16; ++k)
+                            umma_f16(dcol, umma_desc(a0 + k * 256, 128, CHUNK_B), umma_desc(g0 + k * 256, 128, CHUNK_B), idesc, (k > 0) ? 1u : acc0);
+                    } else {
+                        // D[output o (M = 128 padded)][input i (N = kp+16, column kp = ones)] += sum_s dZ[s][o] * Aext[s][i]
+                        const uint32_t idesc = umma_idesc(TM, kp + 16, 1, 1);
+                        for (int k = 0; k < TM / 16; ++k)
+                            umma_f16(dcol, umma_desc(g0 + k * 256, 128, CHUNK_B), umma_desc(a0 + k * 256, 128, CHUNK_B), idesc, (k > 0) ? 1u : acc0);
+                    }
                 }
                 if (l == 0) umma_commit(mbar_mma);  // layer 0: the commit covers the wgrad MMAs too => the tile is fully retired
             }
             mbar_wait(mbar_mma, phase);
             phase ^= 1;
             tc_fence_after();
+            // MMAs retire in order: this commit also covers layer l+1's wgrad (and, for l == 0, layer 0's), the last readers of those
+            // input tiles -> refill them with the next tile's activations
+            if (tid == 0 && next_tile < n_tiles) {
+                if (l < last) bwd_fetch(p, stage, l + 1, next_tile, x16, saved, mbar_a + l + 1);
+                if (l == 0) bwd_fetch(p, stage, 0, next_tile, x16, saved, mbar_a);
+            }
             if (need_dgrad) {
                 const int K = l == 0 ? p.in_dim : p.dims[l - 1];
                 if (l > 0) {
                     // dZ_{l-1} = dA_{l-1} * act'(a_{l-1}); a_{l-1} is this row's entry of layer l's input tile
                     const int act = p.acts[l - 1];
                     if (act == NVO_ACT_RELU)
-                        bwd_hidden_layer<NVO_ACT_RELU>(trow, kp, sA, sGn, tid);
+                        bwd_hidden_layer<NVO_ACT_RELU>(trow, kp, half, sA, sGn, r);
                     else if (act == NVO_ACT_NONE)
-                        bwd_hidden_layer<NVO_ACT_NONE>(trow, kp, sA, sGn, tid);
+                        bwd_hidden_layer<NVO_ACT_NONE>(trow, kp, half, sA, sGn, r);
                     else if (act == NVO_ACT_SIGMOID)
-                        bwd_hidden_layer<NVO_ACT_SIGMOID>(trow, kp, sA, sGn, tid);
+                        bwd_hidden_layer<NVO_ACT_SIGMOID>(trow, kp, half, sA, sGn, r);
                     else if (act == NVO_ACT_TANH)
-                        bwd_hidden_layer<NVO_ACT_TANH>(trow, kp, sA, sGn, tid);
+                        bwd_hidden_layer<NVO_ACT_TANH>(trow, kp, half, sA, sGn, r);
                     else
-                        bwd_hidden_layer<NVO_ACT_EXP>(trow, kp, sA, sGn, tid);
+                        bwd_hidden_layer<NVO_ACT_EXP>(trow, kp, half, sA, sGn, r);
                 } else {
-                    for (int c32 = 0; c32 < kp; c32 += 32) {
+                    int c, c1;
+                    half_range(kp, half, c, c1);
+                    while (c < c1) {
                         float v[32];
-                        if (kp - c32 >= 32) {
-                            tmem_ld32(trow + c32, v);
-                        } else {
-                            tmem_ld16(trow + c32, v);
-                        }
-                        const int ncol = min(32, kp - c32);
+                        const int ncol = (c1 - c >= 32) ? 32 : 16;
+                        if (ncol == 32)
+                            tmem_ld32(trow + c, v);
+                        else
+                            tmem_ld16(trow + c, v);
                         if (live) {
                             // TMF ("tile-major float"): dx[tile][col][row] — a warp stores 128 contiguous bytes per column
-                            float* dst = dx + (tile * K + c32) * TM + tid;
+                            float* dst = dx + (tile * K + c) * TM + r;
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
-                                if (j < ncol && c32 + j < K) dst[j * TM] = v[j] * inv_gscale;
+                                if (j < ncol && c + j < K) dst[j * TM] = v[j] * inv_gscale;
                         }
+                        c += ncol;
                     }
                 }
             }
@@ -597,22 +642,37 @@ __global__ void __launch_bounds__(TM) k_mlp_tc_bwd(const __grid_constant__ TcP p
             __syncthreads();
         }
     }
-    // ---- flush dW / db: thread o holds row o of every layer's accumulator ------------------------------------------
+    // ---- flush dW / db ------------------------------------------------------------------------------------------------------
     if (dparams && it > 0) {
         tc_fence_after();
         for (int l = 0; l < p.n_layers; ++l) {
             const int K = l == 0 ? p.in_dim : p.dims[l - 1], N = p.dims[l], kp = p.kpad[l];
-            for (int c16 = 0; c16 < kp + 16; c16 += 16) {
-                float v[16];
-                tmem_ld16(trow + 64 + DW_COLS * l + c16, v);
-                if (tid < N) {
+            const uint32_t dcol = trow + (uint32_t)p.dw_col[l];
+            if (p.wg_t[l]) {
+                // lane r holds input feature r: columns = outputs (N <= 16); row kp = the ones feature = bias gradient
+                if (half == 0) {
+                    float v[16];
+                    tmem_ld16(dcol, v);
+                    if (r < K || r == kp) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int i = c16 + j;
-                        if (i < K)
-                            atomicAdd(dparams + p.w_off[l] + tid * K + i, v[j] * inv_gscale);
-                        else if (i == kp)
-                            atomicAdd(dparams + p.b_off[l] + tid, v[j] * inv_gscale);
+                        for (int o = 0; o < 16; ++o)
+                            if (o < N) atomicAdd(r < K ? dparams + p.w_off[l] + o * K + r : dparams + p.b_off[l] + o, v[o] * inv_gscale);
+                    }
+                }
+            } else {
+                // lane r holds output feature r: columns = inputs, column kp = bias gradient; 16-column groups alternate between the halves
+                for (int c16 = half * 16; c16 < kp + 16; c16 += 32) {
+                    float v[16];
+                    tmem_ld16(dcol + c16, v);
+                    if (r < N) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int i = c16 + j;
+                            if (i < K)
+                                atomicAdd(dparams + p.w_off[l] + r * K + i, v[j] * inv_gscale);
+                            else if (i == kp)
+                                atomicAdd(dparams + p.b_off[l] + r, v[j] * inv_gscale);
+                        }
                     }
                 }
             }
@@ -620,7 +680,12 @@ __global__ void __launch_bounds__(TM) k_mlp_tc_bwd(const __grid_constant__ TcP p
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    if (warp == 0) {
+        if (p.tmem_cols == 256)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
 }
 
 // fp32 TMF [ceil(n/128)][K][128] -> row-major [n, K] (only the generic tcnn.Network wrapper needs row-major input gradients)
@@ -678,17 +743,49 @@ static int make_tc_params(const nvo_mlp_desc* d, TcP* p) {
             ioff += p->npad[l] * 4;
             p->saved_chunk_off[l] = chunks;
             if (l < d->n_layers - 1) chunks += p->npad[l] >> 3;
-            p->a_off[l] = aoff;
-            aoff += ((p->kpad[l] >> 3) + 2) * CHUNK_B;
             in = d->dims[l];
         } else {
-            p->dims[l] = p->acts[l] = p->npad[l] = p->kpad[l] = p->w_off[l] = p->b_off[l] = p->iw_off[l] = p->ib_off[l] = p->saved_chunk_off[l] = p->a_off[l] = 0;
+            p->dims[l] = p->acts[l] = p->npad[l] = p->kpad[l] = p->w_off[l] = p->b_off[l] = p->iw_off[l] = p->ib_off[l] = p->saved_chunk_off[l] = 0;
+            p->a_off[l] = 0;
         }
     }
     p->n_params = off;
     p->saved_chunks = chunks;
     p->img_bytes = (ioff + 15) & ~15;
+    // backward: weight-gradient orientation, TMEM columns and stage layout (transposed layers first, see k_mlp_tc_bwd)
+    int col = MAXW;
+    for (int l = 0; l < TC_MAX_LAYERS; ++l) {
+        p->wg_t[l] = (l < d->n_layers && p->npad[l] == 16) ? 1 : 0;
+        p->dw_col[l] = col;
+        if (l < d->n_layers) col += p->wg_t[l] ? 16 : p->kpad[l] + 16;
+    }
+    NVO_CHECK(col <= 512, "mlp_tc: network needs %d TMEM columns (> 512)", col);
+    p->tmem_cols = col <= 256 ? 256 : 512;
+    aoff = 0;
+    for (int pass = 0; pass < 2; ++pass)
+        for (int l = 0; l < d->n_layers; ++l)
+            if ((pass == 0) == (p->wg_t[l] != 0)) {
+                p->a_off[l] = aoff;
+                aoff += ((p->kpad[l] >> 3) + 2) * CHUNK_B;
+            }
     p->stage_bytes = aoff;
+    // a transposed layer's M = 128 operand read covers 16 chunks from a_off[l]: it must stay inside stage + weight image, else that
+    // layer goes back to the row = output orientation (the stage order then no longer matters for it)
+    bool relayout = false;
+    for (int l = 0; l < d->n_layers; ++l)
+        if (p->wg_t[l] && p->a_off[l] + 16 * CHUNK_B > p->stage_bytes + p->img_bytes) {
+            p->wg_t[l] = 0;
+            relayout = true;
+        }
+    if (relayout) {
+        col = MAXW;
+        for (int l = 0; l < d->n_layers; ++l) {
+            p->dw_col[l] = col;
+            col += p->wg_t[l] ? 16 : p->kpad[l] + 16;
+        }
+        NVO_CHECK(col <= 512, "mlp_tc: network needs %d TMEM columns (> 512)", col);
+        p->tmem_cols = col <= 256 ? 256 : 512;
+    }
     return 0;
 }
 
@@ -749,7 +846,7 @@ extern "C" int nvo_mlp_tc_forward(const nvo_mlp_desc* d, void* stream, int64_t n
     const int64_t tiles = (n + TM - 1) / TM;
     const int ctas_per_sm = (int)max((size_t)1, min((size_t)4, (size_t)(227 * 1024) / (smem + 1024)));
     const unsigned int grid = (unsigned int)min(tiles, (int64_t)nvo_sm_count() * ctas_per_sm);
-    k_mlp_tc_fwd<<<grid, TM, smem, (cudaStream_t)stream>>>(p, n, (const unsigned char*)x16, (const unsigned char*)wimage, row_mask, y, (uint4*)saved, ctrl);
+    k_mlp_tc_fwd<<<grid, NT, smem, (cudaStream_t)stream>>>(p, n, (const unsigned char*)x16, (const unsigned char*)wimage, row_mask, y, (uint4*)saved, ctrl);
     NVO_CUDA_LAUNCH_CHECK("mlp_tc_forward");
     return 0;
 }
@@ -772,15 +869,17 @@ extern "C" int nvo_mlp_tc_backward(const nvo_mlp_desc* d, void* stream, int64_t 
         k_absmax_scale<<<(unsigned int)min((int64_t)nvo_sm_count() * 4, (count + 255) / 256), 256, 0, st>>>(count, dy, scratch);
         NVO_CUDA_LAUNCH_CHECK("mlp_tc_backward(absmax)");
     }
-    const int w_off = BWD_STAGE + 2 * p.stage_bytes;
+    const int w_off = BWD_STAGE + p.stage_bytes;
     const int ctrl = w_off + p.img_bytes;
-    const size_t smem = (size_t)ctrl + 48;
+    const size_t smem = (size_t)ctrl + 64;
     NVO_CHECK(smem <= 227 * 1024, "mlp_tc_backward: network needs %zu B of shared memory (> 227 KB)", smem);
     e = cudaFuncSetAttribute(k_mlp_tc_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     NVO_CHECK(e == cudaSuccess, "mlp_tc_backward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     const int64_t tiles = (n + TM - 1) / TM;
-    const unsigned int grid = (unsigned int)min(tiles, (int64_t)nvo_sm_count());
-    k_mlp_tc_bwd<<<grid, TM, smem, st>>>(p, n, (const unsigned char*)x16, (const unsigned char*)wimage, (const unsigned char*)saved, y, row_mask, dy, scratch,
+    // co-resident CTAs per SM: bounded by TMEM (512 columns) and shared memory; their MMAs / copies / epilogues overlap
+    const int ctas_per_sm = (int)max((size_t)1, min((size_t)(512 / p.tmem_cols), (size_t)(227 * 1024) / (smem + 1024)));
+    const unsigned int grid = (unsigned int)min(tiles, (int64_t)nvo_sm_count() * ctas_per_sm);
+    k_mlp_tc_bwd<<<grid, NT, smem, st>>>(p, n, (const unsigned char*)x16, (const unsigned char*)wimage, (const unsigned char*)saved, y, row_mask, dy, scratch,
                                          dy_absmax_hint, dx, dparams, w_off, ctrl);
     NVO_CUDA_LAUNCH_CHECK("mlp_tc_backward");
     return 0;

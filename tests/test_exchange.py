@@ -74,7 +74,7 @@ def _two_rank_worker(rank, world, port, tmp):
     flat, m, v = p0.clone().to(dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
     step_a = torch.zeros(1, dtype=torch.int32, device=dev)
     step_b = torch.zeros(1, dtype=torch.int32, device=dev)
-    worst = 0.0
+    worst, hist = 0.0, []
     for it in range(5):
         gr = torch.Generator(device="cpu").manual_seed(100 * it + rank)
         grad = torch.randn(n, generator=gr).to(dev)
@@ -85,9 +85,15 @@ def _two_rank_worker(rank, world, port, tmp):
         ops.adam_step(flat, red, m, v, step_b, 1e-2, 0.9, 0.999, 1e-15, 1.0 / world)
         torch.cuda.synchronize()
         worst = max(worst, float((bufs.params - flat).abs().max()))
-    ok = worst == 0.0 if world == 2 else worst < 1e-6  # a + b is order-independent: two ranks are bit-exact
+        hist.append(float((bufs.params - flat).abs().max()))
+    # the gradient sum of two ranks is order-independent (step 1 is bit-identical on B200); later steps differ by 1 ulp of an O(4)
+    # parameter because the two kernels contract mul+add into FMA differently: tolerance 1e-6 absolute
+    ok = worst < 1e-6 and hist[0] == 0.0
     ok = ok and bufs.error_word() == 0
-    torch.save({"ok": bool(ok), "worst": worst}, os.path.join(tmp, f"r{rank}.pt"))
+    lo, hi = bufs.slice
+    own = float((bufs.params[lo:hi] - flat[lo:hi]).abs().max())
+    torch.save({"ok": bool(ok), "worst": worst, "per_step": hist, "own_slice_err": own, "error_word": bufs.error_word(), "steps": (int(step_a), int(step_b))},
+               os.path.join(tmp, f"r{rank}.pt"))
     dist.barrier()
     bufs.close()
     dist.destroy_process_group()
