@@ -264,6 +264,45 @@ def run_ours(args):
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": "2 timed steps (1 warm-up) x 1024 rays of the same workload, full-size tables, oracle port of the reference torch path"}
 
+    # row f2: the same step fed by the device-resident keyframe store through the fused prologue kernel (pixel sampling +
+    # gather + ray generation inside the CUDA graph) — what Nerfstudio.train() does per iteration; 192 keyframes at NeRF-VO's 640x360
+    dataset_fed = None
+    if world == 1 and not args.no_dataset_leg:
+        from nerf_vo_b200.data import DynamicDataManager, DynamicDataManagerConfig
+        from nerf_vo_b200.synthetic import synthetic_keyframes
+
+        dm = DynamicDataManager(DynamicDataManagerConfig(train_num_rays_per_batch=B, num_frames=NUM_IMAGES, frame_height=360, frame_width=640), device=dev)
+        synthetic_keyframes(dm.train_dataset, seed=4321)
+        trainer.datamanager = dm
+        trainer.capture(warmup=3)
+        for _ in range(max(3, args.warmup)):
+            trainer.train_step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            loss_host = float(trainer.train_step())
+        e1.record()
+        torch.cuda.synchronize()
+        ms_ds = e0.elapsed_time(e1)
+        # the prologue launch alone (L2 flushed between launches)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        evs = []
+        for i in range(3 + 20):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            dm.next_train(0)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        dataset_fed = {"value": B * args.steps / (ms_ds * 1e-3), "unit": UNIT, "ms_per_step": ms_ds / args.steps, "loss_read_back_each_step": True,
+                       "keyframes": NUM_IMAGES, "frame": "360x640", "resident_bytes": int(sum(t.numel() * 4 for t in (dm.train_dataset.frames_color, dm.train_dataset.frames_depth, dm.train_dataset.frames_normal))),
+                       "prologue_us": sum(a.elapsed_time(b) for a, b in evs[3:]) / 20 * 1e3,
+                       "prologue_note": "torch uniform_ draw + k_batch_prologue (one thread per ray: 3 pixel gathers, pinhole ray, normal rotation); latency-bound at 4096 rays",
+                       "final_loss": loss_host}
+        trainer.datamanager = None
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": rays_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -280,6 +319,7 @@ def run_ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "exchange": exchange,
+            "dataset_fed": dataset_fed,
             "final_loss": final_loss,
         }
         print(json.dumps(line), flush=True)
@@ -296,6 +336,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dataset-leg", action="store_true", help="skip the extra leg that feeds the step from a resident keyframe store (row f2)")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="N>1 gradient exchange: 'fused' = peer-memory reduce-scatter+Adam+all-gather kernel, 'nccl' = all-reduce + replicated Adam")
     args = ap.parse_args()

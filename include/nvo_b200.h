@@ -259,6 +259,38 @@ int nvo_mse_loss(void* stream, int64_t n, const float* pred, const float* target
 int nvo_normal_loss(void* stream, int64_t B, const float* pred /*[B,3]*/, const float* gt /*[B,3]*/, float scale, float* loss, float* d_pred);
 
 /* ---------------------------------------------------------------------------------------------
+ * Step prologue: pixel sampling + pixel gather + ray generation + camera-pose correction in ONE launch —
+ * replaces DynamicDataManager.next_train (nerf_vo/mapping/nerfstudio_utils.py:295-300): DynamicDataset.get_dataset (:133-155,
+ * which re-solves R^-1 n over EVERY frame each step), PixelSampler.collate_image_dataset_batch (NS/data/pixel_samplers.py:103-106,
+ * 170-219, including its c/y/x `.cpu()` sync), RayGenerator.forward (NS/model_components/ray_generators.py:40-57),
+ * Cameras.generate_rays perspective branch (NS/cameras/cameras.py:596-654,780-785,865-912) and
+ * CameraOptimizer.apply_to_raybundle (NS/cameras/camera_optimizers.py:108-147).
+ *   u[B,3]            uniform [0,1) draws (torch.rand); indices = trunc(u * [K,H,W]) in fp32, bit-exact
+ *   intrinsics[*,4]   fx fy cx cy per frame; extrinsics[*,4,4] camera-to-world (row-major; only rows 0..2 are read)
+ *   frames_color[K,H,W,3], frames_depth[K,H,W,1], frames_normal[K,H,W,3] (camera-frame normals; NULL = no normal target)
+ *   pose_adjustment[*,6] (translation, rotation tangent) or NULL; pose_mode NVO_POSE_OFF / SO3XR3 / SE3
+ * outputs: indices[B,3] int64 (camera,row,col), camera_indices[B,1] int64, origins/directions[B,3] (pose-corrected),
+ *   directions_norm[B,1], pixel_area[B,1], rgb[B,3], depth[B,1], normal[B,3] = (R^-1 n + 1)/2 (nullable with frames_normal),
+ *   directions_raw[B,3] (nullable): the uncorrected unit directions, the saved input of nvo_pose_correction_backward.
+ * ------------------------------------------------------------------------------------------- */
+enum { NVO_POSE_OFF = 0, NVO_POSE_SO3XR3 = 1, NVO_POSE_SE3 = 2 };
+int nvo_batch_prologue(void* stream, int64_t B, int32_t K, int32_t H, int32_t W, const float* u, const float* intrinsics, const float* extrinsics,
+                       const float* frames_color, const float* frames_depth, const float* frames_normal, const float* pose_adjustment,
+                       int32_t pose_mode, int64_t* indices, int64_t* camera_indices, float* origins, float* directions, float* directions_norm,
+                       float* pixel_area, float* rgb, float* depth, float* normal, float* directions_raw);
+/* Cameras.generate_rays for given pixels (indices[n,3] int64) or, with indices == NULL, for every pixel of frame `cam` in row-major
+ * order (n = H*W; the evaluation bundle of Cameras.generate_rays(camera_indices=cam, keep_shape=True), evaluation/nerf_renderer.py:140-147).
+ * No pose correction (eval mode, NS/models/nerfacto.py:290). */
+int nvo_generate_rays(void* stream, int64_t n, int32_t cam, int32_t W, const int64_t* indices, const float* intrinsics, const float* extrinsics,
+                      int64_t* camera_indices, float* origins, float* directions, float* directions_norm, float* pixel_area);
+/* exp_map_SO3xR3 / exp_map_SE3 (NS/cameras/lie_groups.py:25-60,63-120): tangent[n,6] -> matrices[n,3,4] (CameraOptimizer.forward) */
+int nvo_pose_exp_map(void* stream, int64_t n, int32_t pose_mode, const float* tangent, float* matrices);
+/* backward of the pose correction: d_pose[K,6] += d(origins, directions)/d(pose_adjustment) applied to (d_origins, d_directions)[B,3].
+ * scratch[K,12] must be zero on entry (per-camera cotangent of [R|t], accumulated by reductions). */
+int nvo_pose_correction_backward(void* stream, int64_t B, int32_t K, int32_t pose_mode, const int64_t* camera_indices, const float* directions_raw,
+                                 const float* d_origins, const float* d_directions, const float* pose_adjustment, float* scratch, float* d_pose);
+
+/* ---------------------------------------------------------------------------------------------
  * Fused dense Adam over a flat fp32 buffer (torch.optim.Adam semantics; NS/engine/optimizers.py:138-150,
  * nerf_vo/mapping/nerfstudio.py:84-100). step[1] is a DEVICE int32 counter (number of steps taken so far), read for the
  * bias correction and incremented by the call, so the launch is CUDA-graph replayable. grad_scale multiplies the

@@ -1192,3 +1192,132 @@ class _FieldHeadsTC(torch.autograd.Function):
 
 def field_heads_tc(h, embedding, selector, directions, positions, cam_idx, B, S, head_spec, head_params, pn_spec=None, pn_params=()):
     return _FieldHeadsTC.apply(h, embedding, selector, directions, positions, cam_idx, B, S, head_spec, pn_spec, len(head_params), *head_params, *pn_params)
+
+
+# ------------------------------------------------------------------------------------------------
+# step prologue (csrc/batch.cu): pixel sampling + gather + ray generation + camera-pose correction
+# ------------------------------------------------------------------------------------------------
+
+
+def _check_cameras(intrinsics, extrinsics):
+    check(intrinsics, "camera intrinsics", torch.float32, (None, 4))
+    check(extrinsics, "camera extrinsics", torch.float32, (None, 4, 4))
+
+
+def batch_prologue(u, num_active: int, intrinsics, extrinsics, frames_color, frames_depth, frames_normal=None, pose_adjustment=None, pose_mode: int = 0,
+                   want_raw_directions: bool = False):
+    """One launch of nvo_batch_prologue (include/nvo_b200.h): returns a dict with indices / camera_indices (int64), origins, directions,
+    directions_norm, pixel_area, image, depth_image, normal_image (when frames_normal is given) [, directions_raw]."""
+    check(u, "uniform draws", torch.float32, (None, 3))
+    _check_cameras(intrinsics, extrinsics)
+    K_alloc, H, W, _ = frames_color.shape
+    check(frames_color, "frames_color", torch.float32, (K_alloc, H, W, 3))
+    check(frames_depth, "frames_depth", torch.float32, (K_alloc, H, W, 1))
+    if frames_normal is not None:
+        check(frames_normal, "frames_normal", torch.float32, (K_alloc, H, W, 3))
+    if not (0 < num_active <= K_alloc and num_active <= intrinsics.shape[0] and num_active <= extrinsics.shape[0]):
+        raise RuntimeError(f"num_active={num_active} out of range for {K_alloc} frame slots / {intrinsics.shape[0]} cameras")
+    if pose_mode != 0:
+        check(pose_adjustment, "pose_adjustment", torch.float32, (None, 6))
+        if pose_adjustment.shape[0] < num_active:
+            raise RuntimeError("pose_adjustment has fewer rows than active cameras")
+    B, dev = u.shape[0], u.device
+    f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+    out = {"indices": torch.empty((B, 3), dtype=torch.int64, device=dev), "camera_indices": torch.empty((B, 1), dtype=torch.int64, device=dev),
+           "origins": f(B, 3), "directions": f(B, 3), "directions_norm": f(B, 1), "pixel_area": f(B, 1), "image": f(B, 3), "depth_image": f(B, 1)}
+    if frames_normal is not None:
+        out["normal_image"] = f(B, 3)
+    if want_raw_directions:
+        out["directions_raw"] = f(B, 3)
+    call("nvo_batch_prologue", B, num_active, H, W, u, intrinsics, extrinsics, frames_color, frames_depth, frames_normal,
+         pose_adjustment.detach() if pose_mode != 0 else None, pose_mode, out["indices"], out["camera_indices"], out["origins"], out["directions"],
+         out["directions_norm"], out["pixel_area"], out["image"], out["depth_image"], out.get("normal_image"), out.get("directions_raw"))
+    return out
+
+
+def generate_rays(intrinsics, extrinsics, indices=None, cam: int = 0, height: int = 0, width: int = 0):
+    """Pinhole rays for indices [n,3] (camera,row,col) or every pixel of frame `cam`: (origins, directions, directions_norm, pixel_area, camera_indices)."""
+    _check_cameras(intrinsics, extrinsics)
+    dev = intrinsics.device
+    if indices is not None:
+        check(indices, "ray indices", torch.int64, (None, 3))
+        n = indices.shape[0]
+    else:
+        if not (0 <= cam < extrinsics.shape[0]) or height <= 0 or width <= 0:
+            raise RuntimeError(f"generate_rays: camera {cam} / image size {height}x{width} invalid")
+        n = height * width
+    f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+    o, d, dn, pa, ci = f(n, 3), f(n, 3), f(n, 1), f(n, 1), torch.empty((n, 1), dtype=torch.int64, device=dev)
+    call("nvo_generate_rays", n, cam, width, indices, intrinsics, extrinsics, ci, o, d, dn, pa)
+    return o, d, dn, pa, ci
+
+
+class _PoseExpMap(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tangent, mode):
+        out = torch.empty((tangent.shape[0], 3, 4), dtype=torch.float32, device=tangent.device)
+        call("nvo_pose_exp_map", tangent.shape[0], mode, tangent, out)
+        ctx.save_for_backward(tangent)
+        ctx.mode = mode
+        return out
+
+    @staticmethod
+    def backward(ctx, dM):
+        (tangent,) = ctx.saved_tensors
+        n = tangent.shape[0]
+        d = torch.zeros_like(tangent)
+        # the per-camera cotangent IS dM here: k_pose_grad alone (B = 0 rays), scratch = dM
+        empty_i = torch.empty(0, dtype=torch.int64, device=tangent.device)
+        empty_f = torch.empty(0, dtype=torch.float32, device=tangent.device)
+        call("nvo_pose_correction_backward", 0, n, ctx.mode, empty_i, empty_f, empty_f, empty_f, tangent, dM.contiguous().view(n, 12), d)
+        return d, None
+
+
+def pose_exp_map(tangent, mode: int):
+    check(tangent, "pose tangent", torch.float32, (None, 6))
+    return _PoseExpMap.apply(tangent, mode)
+
+
+class _PoseCorrection(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, origins, directions, cam_idx, pose, mode):
+        B = origins.shape[0]
+        M = torch.empty((pose.shape[0], 3, 4), dtype=torch.float32, device=pose.device)
+        call("nvo_pose_exp_map", pose.shape[0], mode, pose, M)
+        Mi = M[cam_idx]
+        o = origins + Mi[:, :, 3]
+        d = torch.bmm(Mi[:, :, :3], directions[..., None]).squeeze(-1)
+        ctx.save_for_backward(directions, cam_idx, pose, Mi)
+        ctx.mode = mode
+        return o, d
+
+    @staticmethod
+    def backward(ctx, do, dd):
+        directions, cam_idx, pose, Mi = ctx.saved_tensors
+        K = pose.shape[0]
+        dpose = torch.zeros_like(pose)
+        scratch = torch.zeros((K, 12), dtype=torch.float32, device=pose.device)
+        do, dd = do.contiguous(), dd.contiguous()
+        call("nvo_pose_correction_backward", directions.shape[0], K, ctx.mode, cam_idx, directions, do, dd, pose, scratch, dpose)
+        d_dir = torch.bmm(Mi[:, :, :3].transpose(1, 2), dd[..., None]).squeeze(-1) if ctx.needs_input_grad[1] else None
+        return (do if ctx.needs_input_grad[0] else None), d_dir, None, dpose, None
+
+
+def pose_correction(origins, directions, cam_idx, pose_adjustment, mode: int):
+    """CameraOptimizer.apply_to_raybundle on an existing bundle (the fused prologue applies it in-kernel): origins + t, R @ directions,
+    with the gradient w.r.t. pose_adjustment from nvo_pose_correction_backward."""
+    check(origins, "origins", torch.float32, (None, 3))
+    check(directions, "directions", torch.float32, (origins.shape[0], 3))
+    check(cam_idx, "camera indices", torch.int64, (origins.shape[0],))
+    check(pose_adjustment, "pose_adjustment", torch.float32, (None, 6))
+    return _PoseCorrection.apply(origins, directions, cam_idx, pose_adjustment, mode)
+
+
+def pose_correction_backward(cam_idx, directions_raw, d_origins, d_directions, pose_adjustment, mode: int, d_pose=None):
+    """Gradient of the fused prologue's pose correction: d_pose[K,6] (+)= from dL/d(origins, directions) [B,3]."""
+    K = pose_adjustment.shape[0]
+    if d_pose is None:
+        d_pose = torch.zeros_like(pose_adjustment)
+    scratch = torch.zeros((K, 12), dtype=torch.float32, device=pose_adjustment.device)
+    call("nvo_pose_correction_backward", directions_raw.shape[0], K, mode, cam_idx.reshape(-1), directions_raw, d_origins, d_directions, pose_adjustment, scratch, d_pose)
+    return d_pose

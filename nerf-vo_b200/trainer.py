@@ -26,8 +26,12 @@ from .rays import RayBundle
 
 class MappingTrainer:
     def __init__(self, model: ExtendedNerfactoModel, num_rays: int, lr: float = 1e-2, eps: float = 1e-15, betas=(0.9, 0.999),
-                 use_cuda_graph: bool = True, with_normals: bool = True, device: Optional[torch.device] = None, exchange: str = "fused"):
+                 use_cuda_graph: bool = True, with_normals: bool = True, device: Optional[torch.device] = None, exchange: str = "fused",
+                 datamanager=None):
         self.model = model
+        # optional: a DynamicDataManager (data.py). The step then starts with the fused prologue kernel (pixel sampling + gather + ray
+        # generation, drawn on the device like the reference's torch.rand) instead of reading the static input buffers.
+        self.datamanager = datamanager
         self.device = device or next(model.parameters()).device
         self.B = int(num_rays)
         self.lr, self.eps, self.betas = lr, eps, betas
@@ -134,10 +138,18 @@ class MappingTrainer:
     def _forward_backward(self) -> None:
         i = self.inputs
         self.grad.zero_()
-        batch = {"image": i["rgb"], "depth_image": i["depth"]}
-        if self.with_normals:
-            batch["normal_image"] = i["normal"]
-        _, total, terms, weights = self.model.get_train_loss_fused(self._bundle(), batch, [i["jitter0"], i["jitter1"], i["jitter2"]])
+        if self.datamanager is not None:
+            bundle, batch = self.datamanager.next_train(0)  # DynamicDataManager.next_train (nerfstudio_utils.py:295-300)
+            if not self.with_normals:
+                batch.pop("normal_image", None)
+            for k in range(3):
+                i[f"jitter{k}"].uniform_()  # the samplers' torch.rand (ray_samplers.py:115,330), on the device
+        else:
+            bundle = self._bundle()
+            batch = {"image": i["rgb"], "depth_image": i["depth"]}
+            if self.with_normals:
+                batch["normal_image"] = i["normal"]
+        _, total, terms, weights = self.model.get_train_loss_fused(bundle, batch, [i["jitter0"], i["jitter1"], i["jitter2"]])
         total.backward()
         ops.leaf_streams.join()  # scatter kernels running on side streams must land before the all-reduce / optimizer
         self.loss.copy_(total.detach())

@@ -276,6 +276,68 @@ def gen_field_enc():
     np.savez_compressed(os.path.join(OUT, "field_enc.npz"), **_np(G))
 
 
+def gen_batch_prologue(B=193, K=7, H=24, W=40):
+    """Pixel sampling + pixel gather + ray generation + camera-pose correction, through the reference's own
+    PixelSampler.sample (NS/data/pixel_samplers.py:170-219,300-317), RayGenerator.forward
+    (NS/model_components/ray_generators.py:40-57 -> Cameras.generate_rays, NS/cameras/cameras.py:503-912) and
+    CameraOptimizer.apply_to_raybundle (NS/cameras/camera_optimizers.py:108-147, mode SO3xR3).  The dataset dict is
+    built exactly as DynamicDataset.get_dataset does (nerf_vo/mapping/nerfstudio_utils.py:133-155: the per-frame
+    `linalg.solve(R, n)` normal transform over the whole frames); that module itself does not import here (its
+    datamanager base pulls in the dataparser registry), so those 12 lines are executed verbatim on the same tensors."""
+    rh.install()
+    from nerfstudio.cameras import camera_utils
+    from nerfstudio.cameras.camera_optimizers import CameraOptimizerConfig
+    from nerfstudio.cameras.cameras import Cameras, CameraType
+    from nerfstudio.data.pixel_samplers import PixelSamplerConfig
+    from nerfstudio.model_components.ray_generators import RayGenerator
+
+    g = torch.Generator().manual_seed(77)
+    intr = torch.stack([torch.rand(K, generator=g) * 10 + 20, torch.rand(K, generator=g) * 10 + 22, W / 2 - 0.5 + torch.rand(K, generator=g),
+                        H / 2 - 0.5 + torch.rand(K, generator=g)], dim=-1)
+    q = torch.nn.functional.normalize(torch.randn(K, 4, generator=g), dim=-1)
+    w, x, y, z = q.unbind(-1)
+    R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w), 2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                     2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], dim=-1).reshape(K, 3, 3)
+    ext = torch.eye(4).repeat(K, 1, 1)
+    ext[:, :3, :3] = R * (0.5 + torch.rand(K, 1, 1, generator=g))  # scaled rotations: the scene normalisation scales poses
+    ext[:, :3, 3] = torch.rand(K, 3, generator=g) - 0.5
+    color = torch.rand(K, H, W, 3, generator=g)
+    depth = torch.rand(K, H, W, 1, generator=g) * 4
+    normal = torch.nn.functional.normalize(torch.randn(K, H, W, 3, generator=g), dim=-1)
+    # DynamicDataset.get_dataset (nerfstudio_utils.py:133-155)
+    frames_normal = (torch.linalg.solve(ext[:, :3, :3], normal.permute(0, 3, 1, 2).reshape(K, 3, H * W)).reshape(K, 3, H, W).permute(0, 2, 3, 1) + 1) / 2
+    dataset = {"image_idx": torch.arange(0, K, dtype=torch.long), "image": color, "depth_image": depth, "normal_image": frames_normal}
+    cameras = Cameras(fx=intr[:, 0], fy=intr[:, 1], cx=intr[:, 2], cy=intr[:, 3],
+                      distortion_params=camera_utils.get_distortion_params(k1=0, k2=0, k3=0, k4=0, p1=0, p2=0), height=H, width=W,
+                      camera_to_worlds=ext[:, :3], camera_type=CameraType.PERSPECTIVE)
+    sampler = PixelSamplerConfig().setup(num_rays_per_batch=B)
+    torch.manual_seed(5)
+    with rh.record_rand() as rec:
+        batch = sampler.sample(dataset)
+    assert len(rec.values) == 1 and rec.values[0].shape == (B, 3)
+    rb = RayGenerator(cameras)(batch["indices"])
+    G = {"intrinsics": intr, "extrinsics": ext, "frames_color": color, "frames_depth": depth, "frames_normal": normal, "u": rec.values[0],
+         "indices": batch["indices"], "image": batch["image"], "depth_image": batch["depth_image"], "normal_image": batch["normal_image"],
+         "origins": rb.origins, "directions": rb.directions, "pixel_area": rb.pixel_area, "camera_indices": rb.camera_indices,
+         "directions_norm": rb.metadata["directions_norm"]}
+    opt = CameraOptimizerConfig(mode="SO3xR3").setup(num_cameras=K, device="cpu")
+    adj = torch.randn(K, 6, generator=g) * torch.tensor([0.05, 0.05, 0.05, 0.2, 0.2, 0.2])
+    adj[0] = 0.0  # zero tangent: the clamp(nrms, 1e-4) branch
+    adj[1, 3:] = torch.tensor([1e-3, -2e-3, 5e-4])  # below the clamp
+    with torch.no_grad():
+        opt.pose_adjustment.copy_(adj)
+    G["pose_adjustment"] = adj
+    G["pose_matrices_so3xr3"] = opt(torch.arange(K)).detach()
+    o0, d0 = rb.origins.clone(), rb.directions.clone()
+    opt.apply_to_raybundle(rb)
+    G["origins_so3xr3"], G["directions_so3xr3"] = rb.origins.detach(), rb.directions.detach()
+    # gradient of a fixed linear functional of the corrected rays w.r.t. the pose parameters (autograd through the reference code)
+    co, cd = torch.randn(B, 3, generator=g), torch.randn(B, 3, generator=g)
+    ((rb.origins * co).sum() + (rb.directions * cd).sum()).backward()
+    G["cot_origins"], G["cot_directions"], G["pose_adjustment_grad"] = co, cd, opt.pose_adjustment.grad.clone()
+    np.savez_compressed(os.path.join(OUT, "batch_prologue.npz"), **_np(G))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_hash_indices()
@@ -284,5 +346,6 @@ if __name__ == "__main__":
     gen_field_enc()
     gen_ray_ops()
     gen_model_step()
+    gen_batch_prologue()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

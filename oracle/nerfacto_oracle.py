@@ -713,3 +713,92 @@ def synthetic_rays(num_rays: int, num_images: int = 192, seed: int = 1234, H: in
 def synthetic_jitters(num_rays: int, n_levels: int = 3, seed: int = 99) -> List[Tensor]:
     g = torch.Generator().manual_seed(seed)
     return [torch.rand(num_rays, 1, generator=g) for _ in range(n_levels)]
+
+
+# ----------------------------------------------------------------------------------------
+# step prologue: pixel sampling, pixel gather, ray generation, camera-pose correction
+# ----------------------------------------------------------------------------------------
+
+
+def pixel_indices(u: Tensor, num_images: int, height: int, width: int) -> Tensor:
+    """(rand(B,3) * [K,H,W]).long()  (NS/data/pixel_samplers.py:103-106): fp32 product, truncation toward zero."""
+    return (u * torch.tensor([num_images, height, width], dtype=torch.float32)).long()
+
+
+def generate_rays(indices: Tensor, intrinsics: Tensor, c2w: Tensor) -> Dict[str, Tensor]:
+    """Perspective branch of Cameras.generate_rays (NS/cameras/cameras.py:596-633 image coordinates, :654 OpenCV->OpenGL
+    flip, :780-785 directions, :865-892 rotation, normalisation, pixel area) on pixel centres `index + 0.5`
+    (RayGenerator, NS/model_components/ray_generators.py:51-54; Cameras.get_image_coords :307-311).
+    indices: [B,3] int64 (camera, row, col); intrinsics: [K,4] fx fy cx cy; c2w: [K,3|4,4]."""
+    c, yi, xi = indices.unbind(-1)
+    y, x = yi.float() + 0.5, xi.float() + 0.5
+    fx, fy, cx, cy = intrinsics[c].unbind(-1)
+    cs = torch.stack([torch.stack([(x - cx) / fx, (y - cy) / fy], -1), torch.stack([(x - cx + 1) / fx, (y - cy) / fy], -1),
+                      torch.stack([(x - cx) / fx, (y - cy + 1) / fy], -1)], dim=0)  # [3,B,2]
+    d = torch.stack([cs[..., 0], -cs[..., 1], -torch.ones_like(cs[..., 0])], dim=-1)  # [3,B,3]
+    R = c2w[c][:, :3, :3]
+    d = torch.sum(d[..., None, :] * R, dim=-1)
+    norm = torch.maximum(torch.linalg.vector_norm(d, dim=-1, keepdim=True), torch.tensor([1e-8]))  # camera_utils.py:286-298, _EPS
+    d = d / norm
+    dx = torch.sqrt(torch.sum((d[0] - d[1]) ** 2, dim=-1))
+    dy = torch.sqrt(torch.sum((d[0] - d[2]) ** 2, dim=-1))
+    return {"origins": c2w[c][:, :3, 3], "directions": d[0], "pixel_area": (dx * dy)[..., None], "camera_indices": c[:, None],
+            "directions_norm": norm[0]}
+
+
+def exp_map_so3xr3(t: Tensor) -> Tensor:
+    """[R|t] of SO(3) x R^3 (NS/cameras/lie_groups.py:25-60): Rodrigues with the squared angle clamped at 1e-4."""
+    w = t[:, 3:]
+    ang = torch.clamp((w * w).sum(1), 1e-4).sqrt()
+    f1 = ang.sin() / ang
+    f2 = (1.0 - ang.cos()) / (ang * ang)
+    z = torch.zeros_like(w[:, 0])
+    K = torch.stack([z, -w[:, 2], w[:, 1], w[:, 2], z, -w[:, 0], -w[:, 1], w[:, 0], z], -1).reshape(-1, 3, 3)
+    Rm = f1[:, None, None] * K + f2[:, None, None] * torch.bmm(K, K) + torch.eye(3)[None]
+    return torch.cat([Rm, t[:, :3, None]], dim=-1)
+
+
+def exp_map_se3(t: Tensor) -> Tensor:
+    """se(3) -> SE(3), tangent ordered (translation, rotation) like lietorch.SE3.exp (NS/cameras/lie_groups.py:63-120:
+    the reference calls lietorch, absent here — PARITY UNPINNED for this mode; the closed form below is the one the
+    reference keeps in comments :70-117 and is cross-checked against torch.linalg.matrix_exp in the tests)."""
+    v, w = t[:, :3].double(), t[:, 3:].double()
+    th2 = (w * w).sum(1)
+    small = th2 < 1e-8
+    ths = torch.where(small, torch.ones_like(th2), th2).sqrt()  # sqrt only where it is differentiable
+    A = torch.where(small, 1 - th2 / 6, ths.sin() / ths)
+    Bc = torch.where(small, 0.5 - th2 / 24, (1 - ths.cos()) / (ths * ths))
+    C = torch.where(small, 1.0 / 6 - th2 / 120, (ths - ths.sin()) / (ths * ths * ths))
+    z = torch.zeros_like(th2)
+    K = torch.stack([z, -w[:, 2], w[:, 1], w[:, 2], z, -w[:, 0], -w[:, 1], w[:, 0], z], -1).reshape(-1, 3, 3)
+    K2 = torch.bmm(K, K)
+    eye = torch.eye(3, dtype=torch.float64)[None]
+    Rm = eye + A[:, None, None] * K + Bc[:, None, None] * K2
+    V = eye + Bc[:, None, None] * K + C[:, None, None] * K2
+    return torch.cat([Rm, torch.bmm(V, v[:, :, None])], dim=-1).float()
+
+
+def apply_pose_correction(origins: Tensor, directions: Tensor, camera_indices: Tensor, pose_adjustment: Optional[Tensor], mode: str):
+    """CameraOptimizer.apply_to_raybundle (NS/cameras/camera_optimizers.py:138-147): origins + t, R @ directions."""
+    if mode == "off" or pose_adjustment is None:
+        return origins, directions
+    M = (exp_map_so3xr3 if mode == "SO3xR3" else exp_map_se3)(pose_adjustment[camera_indices.reshape(-1)])
+    return origins + M[:, :3, 3], torch.bmm(M[:, :3, :3], directions[..., None]).squeeze(-1)
+
+
+def next_train_batch(u: Tensor, intrinsics: Tensor, extrinsics: Tensor, frames_color: Tensor, frames_depth: Tensor,
+                     frames_normal: Optional[Tensor] = None, pose_adjustment: Optional[Tensor] = None, mode: str = "off"):
+    """DynamicDataManager.next_train (nerf_vo/mapping/nerfstudio_utils.py:295-300) + the pose correction NerfactoModel.get_outputs
+    applies in training (NS/models/nerfacto.py:290-291): dataset dict (:133-155, normals (R^-1 n + 1)/2 — evaluated at the sampled
+    pixels only, the per-pixel solve is independent of the rest of the frame), PixelSampler.collate_image_dataset_batch
+    (NS/data/pixel_samplers.py:170-219), RayGenerator.  Returns (rays, batch)."""
+    K, H, W, _ = frames_color.shape
+    idx = pixel_indices(u, K, H, W)
+    c, y, x = idx.unbind(-1)
+    batch = {"indices": idx, "image": frames_color[c, y, x], "depth_image": frames_depth[c, y, x]}
+    if frames_normal is not None:
+        n = torch.linalg.solve(extrinsics[c, :3, :3], frames_normal[c, y, x][..., None]).squeeze(-1)
+        batch["normal_image"] = (n + 1) / 2
+    rays = generate_rays(idx, intrinsics, extrinsics[:, :3])
+    rays["origins"], rays["directions"] = apply_pose_correction(rays["origins"], rays["directions"], rays["camera_indices"], pose_adjustment, mode)
+    return rays, batch
