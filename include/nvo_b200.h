@@ -291,6 +291,18 @@ int nvo_pose_correction_backward(void* stream, int64_t B, int32_t K, int32_t pos
                                  const float* d_origins, const float* d_directions, const float* pose_adjustment, float* scratch, float* d_pose);
 
 /* ---------------------------------------------------------------------------------------------
+ * Evaluation frame output — replaces the host-side numpy of NerfstudioRenderer.render_frame
+ * (evaluation/nerf_renderer.py:160-167) and NeRFRenderer-driven passes of evaluation/renderer.py:79-97,113-121.
+ * ------------------------------------------------------------------------------------------- */
+/* color[n,3] uint8 = (uint8)(rgb*255) (numpy astype: truncation); depth_out[n] = depth[n] / directions_norm[n] (directions_norm
+ * NULL = plain copy, the non-depth-supervised branch); depth16[n] uint16 = (uint16)((depth_out*scale_a)*scale_b) in fp32, nullable. */
+int nvo_frame_finalize(void* stream, int64_t n, const float* rgb, const float* depth, const float* directions_norm, float scale_a, float scale_b,
+                       void* color, float* depth_out, void* depth16);
+/* sums[3] (double, accumulate; caller zero-fills) += { sum depth_gt, sum depth_pred, count } over pixels with
+ * 0 < depth_gt < 5 and 0 < depth_pred < 5 (evaluation/renderer.py:88-93: the per-keyframe depth-scale alignment). */
+int nvo_depth_scale_sums(void* stream, int64_t n, const float* depth_gt, const float* depth_pred, void* sums);
+
+/* ---------------------------------------------------------------------------------------------
  * Fused dense Adam over a flat fp32 buffer (torch.optim.Adam semantics; NS/engine/optimizers.py:138-150,
  * nerf_vo/mapping/nerfstudio.py:84-100). step[1] is a DEVICE int32 counter (number of steps taken so far), read for the
  * bias correction and incremented by the call, so the launch is CUDA-graph replayable. grad_scale multiplies the

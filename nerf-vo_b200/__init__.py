@@ -7,6 +7,7 @@ from .data import (CameraOptimizer, CameraOptimizerConfig, Cameras, DynamicDataM
 from .field_components import MLP, Embedding, HashEncoding, MLPWithHashEncoding, NeRFEncoding, SceneContraction, SHEncoding, trunc_exp  # noqa: F401
 from .fields import FieldHeadNames, HashMLPDensityField, NerfactoField  # noqa: F401
 from .model import DepthNerfactoModel, ExtendedNerfactoModel, NerfactoModel, NerfactoModelConfig  # noqa: F401
+from .nerf_renderer import NerfstudioRenderer  # noqa: F401
 from .ray_samplers import PDFSampler, ProposalNetworkSampler, UniformLinDispPiecewiseSampler  # noqa: F401
 from .rays import Frustums, RayBundle, RaySamples  # noqa: F401
 from .renderers import AccumulationRenderer, DepthRenderer, NormalsRenderer, NormalsShader, RGBRenderer, render_all  # noqa: F401

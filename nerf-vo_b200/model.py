@@ -181,17 +181,25 @@ class NerfactoModel(nn.Module):
     # ---- evaluation (NS/models/base_model.py:164-192) ----------------------------------------------------------------
     @torch.no_grad()
     def get_outputs_for_camera_ray_bundle(self, camera_ray_bundle: RayBundle, num_rays_per_chunk: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        """Chunked evaluation of a whole-image bundle (NS/models/base_model.py:164-192).  Each output is allocated once at image size
+        and every chunk writes its slice (the reference appends 200 chunk tensors per key and concatenates).  Rays are independent,
+        so the result does not depend on the chunk size — except `expected_depth`, which the reference clips to the min / max sample
+        distance of each CALL (renderers.py:379), i.e. per chunk there too.  evaluation/nerf_renderer.py renders with the config's
+        4096-ray chunks; `NerfstudioRenderer` here passes a larger chunk (same pixels, fewer launches)."""
         chunk = num_rays_per_chunk or self.config.eval_num_rays_per_chunk
         image_shape = camera_ray_bundle.origins.shape[:-1]
         flat = camera_ray_bundle.flatten()
         n = len(flat)
-        outs: Dict[str, List[torch.Tensor]] = {}
+        outs: Dict[str, torch.Tensor] = {}
         for i in range(0, n, chunk):
             o = self.forward(flat[i:i + chunk])
             for k, v in o.items():
-                if torch.is_tensor(v):
-                    outs.setdefault(k, []).append(v)
-        return {k: torch.cat(v).view(*image_shape, -1) for k, v in outs.items()}
+                if not torch.is_tensor(v):
+                    continue
+                if k not in outs:
+                    outs[k] = torch.empty((n,) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)
+                outs[k][i:i + v.shape[0]] = v
+        return {k: v.view(*image_shape, -1) for k, v in outs.items()}
 
 
 class DepthNerfactoModel(NerfactoModel):

@@ -53,3 +53,27 @@ def proposal_update_due(step: int, steps_since_update: int, warmup: int = 5000, 
 
     sched = float(np.clip(np.interp(step, [0, warmup], [0, update_every]), 1, update_every))
     return steps_since_update > sched or step < 10
+
+
+# ---- evaluation frames (config 5): image rows are independent units -----------------------------------------------------
+
+
+def row_shard(height: int, rank: int, world: int) -> Tuple[int, int]:
+    """Half-open row range of `rank` for an image of `height` rows: ceil(H/W) rows per rank, the last ranks may be short / empty
+    (a frame height need not divide: 680 rows over 8 ranks = 85 each, 360 over 7 = 52 x 6 + 48)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world: {rank}/{world}")
+    per = (height + world - 1) // world
+    lo = min(rank * per, height)
+    return lo, min(lo + per, height)
+
+
+def gather_rows(local_rows: torch.Tensor, height: int, world: int, group=None) -> torch.Tensor:
+    """All-gather of the per-rank row blocks [h_r, W, ...] into the full [H, W, ...] frame (every rank gets it).  Blocks are padded to
+    ceil(H/world) rows so one fixed-size all_gather_into_tensor serves ragged shards."""
+    per = (height + world - 1) // world
+    pad = torch.zeros((per,) + tuple(local_rows.shape[1:]), dtype=local_rows.dtype, device=local_rows.device)
+    pad[:local_rows.shape[0]] = local_rows
+    out = torch.empty((world * per,) + tuple(local_rows.shape[1:]), dtype=local_rows.dtype, device=local_rows.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    return out[:height]

@@ -338,6 +338,56 @@ def gen_batch_prologue(B=193, K=7, H=24, W=40):
     np.savez_compressed(os.path.join(OUT, "batch_prologue.npz"), **_np(G))
 
 
+def gen_frame_render(H=10, W=14, K=8, main_log2=12, prop_log2=10):
+    """Evaluation frame render through the reference: the body of NerfstudioRenderer.render_frame
+    (evaluation/nerf_renderer.py:132-168 — that module imports open3d / the instant-ngp build, so its lines are executed here on the
+    reference's own Cameras.generate_rays(camera_indices=0, keep_shape=True) and Model.get_outputs_for_camera_ray_bundle,
+    NS/models/base_model.py:164-192), plus the depth-scale alignment arithmetic of evaluation/renderer.py:79-97 and the uint16
+    depth conversion of :113-121.  Model parameters are those of model_step_small.npz (same seeds), so they are not stored again."""
+    rh.install()
+    from nerfstudio.cameras import camera_utils
+    from nerfstudio.cameras.cameras import Cameras, CameraType
+
+    m = rh.build_reference_model(main_log2=main_log2, prop_log2=prop_log2, num_images=K, seed=0)
+    torch.manual_seed(1)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "hash_table" in n:
+                p.normal_(0, 0.1)
+    m.eval()
+    m.config.eval_num_rays_per_chunk = 48  # ragged chunks: 140 rays = 48 + 48 + 44
+    intr = {"fx": 9.0, "fy": 9.5, "cx": 6.4, "cy": 5.2, "height": H, "width": W}
+    g = torch.Generator().manual_seed(21)
+    q = torch.nn.functional.normalize(torch.randn(4, generator=g), dim=-1)
+    w, x, y, z = q.tolist()
+    ext = np.eye(4)
+    ext[:3, :3] = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                            [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    ext[:3, 3] = [0.1, -0.2, 0.05]
+    camera_extrinsics = ext.copy()
+    # ---- evaluation/nerf_renderer.py:134-168 ----
+    camera_extrinsics[0:3, 1:3] *= -1
+    cameras = Cameras(fx=intr["fx"], fy=intr["fy"], cx=intr["cx"], cy=intr["cy"],
+                      distortion_params=camera_utils.get_distortion_params(k1=0, k2=0, k3=0, k4=0, p1=0, p2=0), height=intr["height"], width=intr["width"],
+                      camera_to_worlds=torch.Tensor(camera_extrinsics).unsqueeze(0)[:, :3], camera_type=CameraType.PERSPECTIVE)
+    camera_ray_bundle = cameras.generate_rays(camera_indices=0, keep_shape=True)
+    with torch.no_grad():
+        outputs = m.get_outputs_for_camera_ray_bundle(camera_ray_bundle)
+    color = (outputs["rgb"].cpu().numpy() * 255).astype(np.uint8)
+    depth = (outputs["depth"] / camera_ray_bundle.metadata["directions_norm"]).cpu().numpy()[..., 0]
+    # ---- evaluation/renderer.py:79-97 (one keyframe) and :113-121 ----
+    frame_depth_gt = (torch.rand(H, W, generator=g) * 6).numpy()
+    frame_depth_gt[0, :3] = 0
+    mask = (frame_depth_gt > 0) * (depth > 0) * (frame_depth_gt < 5) * (depth < 5)
+    scale = frame_depth_gt[mask].mean() / depth[mask].mean()
+    depth16 = (depth.copy() * np.float32(scale) * np.float32(6553.5)).astype(np.uint16)
+    G = {"intrinsics": np.array([intr["fx"], intr["fy"], intr["cx"], intr["cy"]], dtype=np.float32), "extrinsics": ext, "color": color, "depth": depth,
+         "out.rgb": outputs["rgb"], "out.depth": outputs["depth"], "out.accumulation": outputs["accumulation"],
+         "directions_norm": camera_ray_bundle.metadata["directions_norm"], "origins": camera_ray_bundle.origins, "directions": camera_ray_bundle.directions,
+         "depth_gt": frame_depth_gt, "mask_count": int(mask.sum()), "scale": np.float64(scale), "depth16": depth16}
+    np.savez_compressed(os.path.join(OUT, "frame_render_small.npz"), **_np(G))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_hash_indices()
@@ -347,5 +397,6 @@ if __name__ == "__main__":
     gen_ray_ops()
     gen_model_step()
     gen_batch_prologue()
+    gen_frame_render()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -802,3 +802,50 @@ def next_train_batch(u: Tensor, intrinsics: Tensor, extrinsics: Tensor, frames_c
     rays = generate_rays(idx, intrinsics, extrinsics[:, :3])
     rays["origins"], rays["directions"] = apply_pose_correction(rays["origins"], rays["directions"], rays["camera_indices"], pose_adjustment, mode)
     return rays, batch
+
+
+# ----------------------------------------------------------------------------------------
+# evaluation frame render
+# ----------------------------------------------------------------------------------------
+
+
+def frame_rays(intrinsics: Tensor, extrinsics_std: np.ndarray, height: int, width: int) -> Dict[str, Tensor]:
+    """Full-frame bundle of NerfstudioRenderer.render_frame (evaluation/nerf_renderer.py:134-158): standard -> NeRF axis convention
+    (columns 1:3 negated), then Cameras.generate_rays(camera_indices=0, keep_shape=True) on every pixel centre, row-major."""
+    ext = np.array(extrinsics_std, dtype=np.float64, copy=True)
+    ext[0:3, 1:3] *= -1
+    c2w = torch.tensor(ext, dtype=torch.float32)[None, :3]
+    ys, xs = torch.meshgrid(torch.arange(height), torch.arange(width), indexing="ij")
+    idx = torch.stack([torch.zeros_like(ys), ys, xs], dim=-1).reshape(-1, 3)
+    return generate_rays(idx, intrinsics.reshape(1, 4), c2w)
+
+
+def finalize_frame(rgb: Tensor, depth: Tensor, directions_norm: Tensor) -> Tuple[np.ndarray, np.ndarray]:
+    """(rgb * 255).astype(uint8) and depth / directions_norm (evaluation/nerf_renderer.py:160-167; DepthNerfacto branch)."""
+    color = (rgb.numpy() * 255).astype(np.uint8)
+    return color, (depth / directions_norm).numpy()[..., 0]
+
+
+def depth_scale_sums(depth_gt: np.ndarray, depth_pred: np.ndarray) -> Tuple[float, float, int]:
+    """Masked sums behind depth_gt[mask].mean() / depth_pred[mask].mean() (evaluation/renderer.py:88-93)."""
+    mask = (depth_gt > 0) * (depth_pred > 0) * (depth_gt < 5) * (depth_pred < 5)
+    return float(depth_gt[mask].astype(np.float64).sum()), float(depth_pred[mask].astype(np.float64).sum()), int(mask.sum())
+
+
+def depth_to_uint16(depth: np.ndarray, scale_pred2gt: float, depth_scale: float) -> np.ndarray:
+    """(raw_depth * scale_pred2gt * depth_scale).astype(uint16) in fp32 (evaluation/renderer.py:116-119)."""
+    return (depth.astype(np.float32) * np.float32(scale_pred2gt) * np.float32(depth_scale)).astype(np.uint16)
+
+
+def render_frame(P: Dict[str, Tensor], cfg: ModelCfg, intrinsics: Tensor, extrinsics_std: np.ndarray, height: int, width: int, chunk: int = 4096):
+    """NerfstudioRenderer.render_frame: eval-mode forward in `chunk`-ray slices (NS/models/base_model.py:164-192) -> (uint8 colour, depth)."""
+    rays = frame_rays(intrinsics, extrinsics_std, height, width)
+    n = height * width
+    rgb, depth = [], []
+    with torch.no_grad():
+        for i in range(0, n, chunk):
+            o = mapping_forward(P, cfg, rays["origins"][i:i + chunk], rays["directions"][i:i + chunk], rays["camera_indices"][i:i + chunk], None, 1.0, training=False)
+            rgb.append(o["rgb"])
+            depth.append(o["depth"])
+    color, d = finalize_frame(torch.cat(rgb), torch.cat(depth), rays["directions_norm"])
+    return color.reshape(height, width, 3), d.reshape(height, width)

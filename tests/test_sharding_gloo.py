@@ -72,3 +72,48 @@ def test_shard_range_errors():
         nv.sharding.shard_range(10, 0, 3)
     with pytest.raises(ValueError):
         nv.sharding.shard_range(8, 2, 2)
+
+
+# ---- evaluation frames: row sharding + gather (config 5) ---------------------------------------------------------------
+def _row_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import nerf_vo_b200 as nv
+
+    sh = nv.sharding
+    H, W = 37, 5  # 37 rows over 2 ranks: 19 + 18 (ragged)
+    full_c = (torch.arange(H * W * 3) % 251).to(torch.uint8).view(H, W, 3)
+    full_d = torch.arange(H * W, dtype=torch.float32).view(H, W)
+    lo, hi = sh.row_shard(H, rank, world)
+    c = sh.gather_rows(full_c[lo:hi].clone(), H, world)
+    d = sh.gather_rows(full_d[lo:hi].clone(), H, world)
+    torch.save({"ok": bool(torch.equal(c, full_c) and torch.equal(d, full_d)), "rows": (lo, hi)}, os.path.join(tmp, f"row{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_row_sharded_frame(tmp_path):
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_row_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    rows = []
+    for r in range(2):
+        out = torch.load(os.path.join(str(tmp_path), f"row{r}.pt"))
+        assert out["ok"], r
+        rows.append(out["rows"])
+    assert rows == [(0, 19), (19, 37)]
+
+
+def test_row_shard_covers_every_row_once():
+    import nerf_vo_b200 as nv
+
+    for H in (1, 7, 360, 680, 681):
+        for world in (1, 2, 3, 4, 8):
+            spans = [nv.sharding.row_shard(H, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == H
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:])) and all(lo <= hi for lo, hi in spans)
+    assert nv.sharding.row_shard(680, 3, 8) == (255, 340)
