@@ -152,7 +152,7 @@ def run_ours(args):
 
     torch.manual_seed(0)  # identical parameters on every rank (replicated), rays differ per rank
     model = nv.ExtendedNerfactoModel(nv.NerfactoModelConfig(), num_train_data=NUM_IMAGES).to(dev)
-    B = RAYS_PER_GPU
+    B = args.rays
     trainer = MappingTrainer(model, num_rays=B, lr=1e-2, eps=1e-15, use_cuda_graph=not args.no_graph, exchange=args.exchange)
 
     n_pool = 8
@@ -307,7 +307,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": rays_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "precision": "fp16 tensor-core operands (hash features, field MLPs) with fp32 accumulation; fp32 tables, proposal networks, per-ray ops, optimizer",
+            "config": {"workload": WORKLOAD if B == RAYS_PER_GPU else WORKLOAD.replace("4096 rays/GPU", f"{B} rays/GPU"), "precision": "fp16 tensor-core operands (hash features, field MLPs) with fp32 accumulation; fp32 tables, proposal networks, per-ray ops, optimizer",
                        "rays_per_gpu": B, "global_rays": world * B, "parallelism": f"dp{world} (ray sharding; gradient exchange: {trainer.exchange})",
                        "step": "zero-grad + forward + losses + backward + fused Adam, proposal networks updated every step",
                        "l2": "no explicit flush: parameters+gradients+Adam state = 290 MB per step exceed the 126 MB L2",
@@ -334,6 +334,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rays", type=int, default=RAYS_PER_GPU, help="rays per GPU per step (default: configs[1]'s 4096; 65536 = configs[2]'s batch)")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dataset-leg", action="store_true", help="skip the extra leg that feeds the step from a resident keyframe store (row f2)")

@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(256) k_contract(int64_t n, const float* __rest
     for (int a = 0; a < 3; ++a) {
         float c = p[a];
         if (!(mag < 1.f)) c = __fmul_rn(__fsub_rn(2.f, __fdiv_rn(1.f, mag)), __fdiv_rn(p[a], mag));
-        q[a] = __fdiv_rn(__fadd_rn(c, 2.f), 4.f);
+        q[a] = __fmul_rn(__fadd_rn(c, 2.f), 0.25f);
         sel = sel && (q[a] > 0.f) && (q[a] < 1.f);
     }
     const float m = sel ? 1.f : 0.f;
@@ -128,8 +128,8 @@ __device__ __forceinline__ void assemble_rows(int64_t t, int64_t r, const float*
         hv[k] = q.x, hv[k + 1] = q.y, hv[k + 2] = q.z, hv[k + 3] = q.w;
     }
     // get_normalized_directions (base_field.py:142): (d + 1) / 2
-    sh16(__fdiv_rn(__fadd_rn(__ldg(dirs + 3 * r), 1.f), 2.f), __fdiv_rn(__fadd_rn(__ldg(dirs + 3 * r + 1), 1.f), 2.f),
-         __fdiv_rn(__fadd_rn(__ldg(dirs + 3 * r + 2), 1.f), 2.f), head);
+    sh16(__fmul_rn(__fadd_rn(__ldg(dirs + 3 * r), 1.f), 0.5f), __fmul_rn(__fadd_rn(__ldg(dirs + 3 * r + 1), 1.f), 0.5f),
+         __fmul_rn(__fadd_rn(__ldg(dirs + 3 * r + 2), 1.f), 0.5f), head);
 #pragma unroll
     for (int k = 0; k < GEO; ++k) head[16 + k] = hv[1 + k];
     const float* e = cam_idx ? embedding + APP * __ldg(cam_idx + r) : embedding;

@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256, 3) k_grid_fwd_tmh(const __grid_constant__
 }
 
 // Backward scatter: one thread walks GB = 4 consecutive samples (neighbours along a ray) through a group of 4 levels, merging
-// equal-cell runs in registers and pairing the x-floor / x-ceil rows into 16-byte reductions (ScatterRun, grid_common.cuh).
+// equal-cell runs in registers and pairing the x-floor / x-ceil rows into 16-byte reductions (CellRun, grid_common.cuh).
 // blockIdx.y = level group, so all 16 levels of a sample quad are in flight on different CTAs.
 #define GB 4
 template <typename OutT>
@@ -113,26 +113,47 @@ __global__ void __launch_bounds__(128) k_grid_bwd(const __grid_constant__ GridP 
     const int64_t t0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * GB;
     if (t0 >= n) return;
     float q[GB][3];
+    if (t0 + GB <= n && (reinterpret_cast<size_t>(x) & 15) == 0) {  // 12 contiguous floats, 48-byte aligned
+        const float4* xv = reinterpret_cast<const float4*>(x + 3 * t0);
+        const float4 a = __ldg(xv), b = __ldg(xv + 1), c = __ldg(xv + 2);
+        q[0][0] = a.x, q[0][1] = a.y, q[0][2] = a.z, q[1][0] = a.w, q[1][1] = b.x, q[1][2] = b.y;
+        q[2][0] = b.z, q[2][1] = b.w, q[2][2] = c.x, q[3][0] = c.y, q[3][1] = c.z, q[3][2] = c.w;
+    } else {
 #pragma unroll
-    for (int g = 0; g < GB; ++g) {
-        const int64_t t = min(t0 + g, n - 1);
-        q[g][0] = __ldg(x + 3 * t), q[g][1] = __ldg(x + 3 * t + 1), q[g][2] = __ldg(x + 3 * t + 2);
+        for (int g = 0; g < GB; ++g) {
+            const int64_t t = min(t0 + g, n - 1);
+            q[g][0] = __ldg(x + 3 * t), q[g][1] = __ldg(x + 3 * t + 1), q[g][2] = __ldg(x + 3 * t + 2);
+        }
     }
     const uint32_t mask = (1u << p.log2T) - 1u;
+    const bool tmf_vec = tmf && sizeof(OutT) == 4 && (reinterpret_cast<size_t>(dy) & 15) == 0;
     const int l_end = min(p.L, (int)(blockIdx.y + 1) * 4);
     for (int l = blockIdx.y * 4; l < l_end; ++l) {
         float* slab = dtable + (((size_t)l << p.log2T) << 1);
         const float scale = p.scale[l];
-        ScatterRun run;
+        CellRun run;
         run.reset();
+        float g0[GB], g1[GB];
+        if (tmf_vec) {
+            // fp32 tile-major dy: the quad's four samples are 16 contiguous bytes per feature column (t0 is a multiple of 4, tiles are 128 rows)
+            const float* b = reinterpret_cast<const float*>(dy) + (((t0 >> 7) * (2 * p.L) + 2 * l) << 7) + (t0 & 127);
+            const float4 a = __ldg(reinterpret_cast<const float4*>(b)), c = __ldg(reinterpret_cast<const float4*>(b + 128));
+            g0[0] = a.x, g0[1] = a.y, g0[2] = a.z, g0[3] = a.w;
+            g1[0] = c.x, g1[1] = c.y, g1[2] = c.z, g1[3] = c.w;
+        } else {
+#pragma unroll
+            for (int g = 0; g < GB; ++g) {
+                const float2 gr = load_dy(dy, min(t0 + g, n - 1), l, p.L, tmf);
+                g0[g] = gr.x, g1[g] = gr.y;
+            }
+        }
 #pragma unroll
         for (int g = 0; g < GB; ++g) {
             if (t0 + g >= n) break;
-            const float2 gr = load_dy(dy, t0 + g, l, p.L, tmf);
-            if (gr.x == 0.f && gr.y == 0.f) continue;  // adding zeros changes nothing (masked / padded samples)
-            run.add(slab, make_corner(q[g][0], q[g][1], q[g][2], scale), mask, gr.x, gr.y);
+            if (g0[g] == 0.f && g1[g] == 0.f) continue;  // adding zeros changes nothing (masked / padded samples)
+            run.add(slab, q[g][0], q[g][1], q[g][2], scale, mask, g0[g], g1[g]);
         }
-        run.finish(slab);
+        run.flush(slab);
     }
 }
 

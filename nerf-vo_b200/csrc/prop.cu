@@ -44,15 +44,18 @@ __device__ __forceinline__ void sample_point(int64_t t, int S, const float* __re
     const int k = (int)(t - r * S);
     const float se = __fadd_rn(__ldg(starts + r * stride + k), __ldg(ends + r * stride + k));
 #pragma unroll
-    for (int a = 0; a < 3; ++a) p[a] = __fadd_rn(__ldg(o + 3 * r + a), __fdiv_rn(__fmul_rn(__ldg(d + 3 * r + a), se), 2.f));
+    for (int a = 0; a < 3; ++a) p[a] = __fadd_rn(__ldg(o + 3 * r + a), __fmul_rn(__fmul_rn(__ldg(d + 3 * r + a), se), 0.5f));
 }
 
 // MLP parameters live in constant memory (one slot per proposal network, refreshed from the fp32 parameter buffer by a
-// device-to-device copy in front of every launch): every multiply-accumulate is then ONE FFMA with a constant-bank operand
-// instead of a shared-memory load + FFMA — these kernels are issue-bound, not bandwidth-bound.
+// device-to-device copy in front of every launch): every multiply-accumulate is then ONE FFMA with a uniform-register operand
+// (LDCU.128 fetches four weights) instead of a shared-memory load + FFMA — these kernels are issue-bound, not bandwidth-bound.
+// The backward keeps a SECOND copy (c_propb) for its dgrad: with one symbol ptxas sees every weight used twice (recompute + dgrad),
+// hoists all 193 of them into vector registers and spills (168 registers, 300 B of spills before; 100 registers now).
 #define PROP_SLOTS 4
 #define PROP_SLOT_FLOATS 256
 __constant__ float c_prop[PROP_SLOTS][PROP_SLOT_FLOATS];
+__constant__ float c_propb[PROP_SLOTS][PROP_SLOT_FLOATS];
 
 // hidden layer + output pre-activation, accumulation order of the SIMT reference kernel (bias first, inputs ascending)
 template <int L, int SLOT>
@@ -71,9 +74,9 @@ __device__ __forceinline__ float prop_mlp(const float* f, float* h) {
     return z;
 }
 
-// Saved-feature layout: level-major [L][Npad], and inside every block of 128 samples the sample j = 4*lane + g sits at
-// g*32 + lane, so the backward (one thread = 4 consecutive samples) reads 256 contiguous bytes per warp and level while
-// the forward (one thread = one sample) still writes whole 32-byte sectors.
+// Saved-for-backward layout (opaque `feat` buffer): features level-major [L][Npad] float2, then [Npad] float4 = (normalised position,
+// selector).  Inside every block of 128 samples the sample j = 4*lane + g sits at g*32 + lane, so the backward (one thread = 4
+// consecutive samples) reads 256 / 512 contiguous bytes per warp while the forward (one thread = one sample) still writes whole sectors.
 __device__ __forceinline__ int64_t feat_slot(int64_t t) { return (t & ~(int64_t)127) + ((t & 3) << 5) + ((t & 127) >> 2); }
 
 template <int L, int SLOT, typename RowT>
@@ -98,6 +101,7 @@ __global__ void __launch_bounds__(256) k_prop_fwd(const __grid_constant__ GridP 
         f[2 * l + 1] = v.y;
         if (feat) feat[(int64_t)l * Npad + slot] = v;
     }
+    if (feat) reinterpret_cast<float4*>(feat + (int64_t)L * Npad)[slot] = make_float4(q[0], q[1], q[2], m);
     float h[PH];
     const float z = prop_mlp<L, SLOT>(f, h);
     density[t] = expf(z) * m;  // trunc_exp forward (activations.py:33) * selector (density_fields.py:115)
@@ -105,12 +109,14 @@ __global__ void __launch_bounds__(256) k_prop_fwd(const __grid_constant__ GridP 
 
 // ---------------------------------------------------------------------------------------------------------------------
 // backward: one warp = 128 consecutive samples, one thread = G = 4 consecutive samples of a ray.
-//   pass A (per g): recompute the MLP from the saved features, dz -> dh -> df; park df and the normalised position in shared
-//                   memory; weight gradients by the staged outer-product reduction over the warp's 32 samples.
-//   pass B (per level): walk the thread's 4 samples in order, accumulating corner contributions in registers while the
-//                   target row stays the same and issuing ONE red.global.add.v2.f32 per run (samples along a ray stay in a
-//                   coarse cell for many steps; this costs ~10 instructions per corner where a warp-wide segmented scan
-//                   costs ~60).
+//   pass A (per g): recompute the MLP from the saved features, dz -> dh -> df; park df and the saved normalised position in shared
+//                   memory.  Weight gradients: dW1 / db1 accumulate in the thread's own registers (17 FFMA per sample, reduced over
+//                   the warp once at the end of the kernel); dW0 / db0 = sum_s dh[s] (x) [f[s], 1] goes through a 32-row staging
+//                   tile: lane = (half-warp, pair of hidden units, half of the 12 columns) owns a 2 x 6 register tile and walks 16 of the
+//                   32 staged rows (4 shared-memory loads per 12 FFMA).
+//   pass B (per level): walk the thread's 4 samples in order with a CellRun (grid_common.cuh): partial sums stay in registers while
+//                   the integer cell does not change (samples along a ray stay in a coarse cell for many steps), one 16-byte
+//                   red.global.add.v4.f32 per (y,z) corner pair per run.
 // ---------------------------------------------------------------------------------------------------------------------
 #define PROP_BWD_THREADS 128
 #define PROP_G 4
@@ -118,19 +124,18 @@ __global__ void __launch_bounds__(256) k_prop_fwd(const __grid_constant__ GridP 
 template <int L>
 struct PropSmem {
     using PL = PropLayout<L>;
-    static constexpr int RS = 50;                               // staging row stride (floats), rows 8-byte aligned
-    static constexpr int S_DH = 0, S_F = 16, S_DZ = 16 + 2 * PL::CH, S_H = S_DZ + 2;  // dh[16] | fext[2CH] | dz,pad | hext[17]
+    static constexpr int RS = 28;                               // staging row: dh[16] | f[IN] 1 0-pad to 12 ; 112 B rows (16-byte aligned,
+                                                                // 16-byte chunks of 8 consecutive rows fall in distinct banks)
+    static constexpr int S_DH = 0, S_F = 16;
     static constexpr int DF = 0;                                // [G][IN][32]
     static constexpr int Q = DF + PROP_G * PL::IN * 32;         // [G][3][32]
     static constexpr int STAGE = Q + PROP_G * 3 * 32;           // [32][RS]
     static constexpr int PER_WARP = STAGE + 32 * RS;
-    static_assert(S_H + PH + 1 <= RS, "staging row too small");
+    static_assert(PL::IN + 1 <= 12 && PH == 16, "staging tile is laid out for 16 hidden units and <= 11 extended input columns");
 };
 
 template <int L, int SLOT>
-__global__ void __launch_bounds__(PROP_BWD_THREADS, 3) k_prop_bwd(const __grid_constant__ GridP p, int64_t N, int64_t Npad, int S, const float* __restrict__ o,
-                                                                  const float* __restrict__ d, const float* __restrict__ starts,
-                                                                  const float* __restrict__ ends, int64_t stride, const float* __restrict__ positions,
+__global__ void __launch_bounds__(PROP_BWD_THREADS, 4) k_prop_bwd(const __grid_constant__ GridP p, int64_t N, int64_t Npad, int S,
                                                                   const float2* __restrict__ feat, const float* __restrict__ ddensity,
                                                                   float* __restrict__ dtable, float* __restrict__ dparams) {
     using PL = PropLayout<L>;
@@ -143,12 +148,15 @@ __global__ void __launch_bounds__(PROP_BWD_THREADS, 3) k_prop_bwd(const __grid_c
     float* qs = ws + SM::Q;
     float* stage = ws + SM::STAGE;
     const uint32_t mask = (1u << p.log2T) - 1u;
-    // wgrad roles: dW0ext[j][half*CH + c], c < CH  (column IN is the bias); lanes 0..PH: dW1ext[lane]
-    const int wj = lane & (PH - 1), whalf = lane >> 4;
-    float acc0[PL::CH];
+    const float4* qsaved = reinterpret_cast<const float4*>(feat + (int64_t)L * Npad);
+    // dW0ext roles: half-warp hw walks rows {8a + 4hw + b}, hidden units 2jp, 2jp+1, columns 6ch .. 6ch+5 of [f | 1 | 0]
+    const int hw = lane >> 4, jp = (lane & 15) >> 1, ch = lane & 1;
+    float acc0[2][6];
 #pragma unroll
-    for (int c = 0; c < PL::CH; ++c) acc0[c] = 0.f;
-    float acc1 = 0.f;
+    for (int c = 0; c < 6; ++c) acc0[0][c] = acc0[1][c] = 0.f;
+    float accw1[PH], accb1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < PH; ++j) accw1[j] = 0.f;
     const int64_t n_st = (N + 127) >> 7;
     for (int64_t st = (int64_t)blockIdx.x * NW + warp; st < n_st; st += (int64_t)gridDim.x * NW) {
         const int64_t base = st << 7;
@@ -158,100 +166,120 @@ __global__ void __launch_bounds__(PROP_BWD_THREADS, 3) k_prop_bwd(const __grid_c
         for (int g = 0; g < PROP_G; ++g) {
             const int64_t t = base + lane * PROP_G + g;
             const bool valid = t < N;
-            const int64_t tt = valid ? t : N - 1;
-            float pos[3], q[3];
-            sample_point(tt, S, o, d, starts, ends, stride, positions, pos);
-            const float m = contract_point(pos, q);
-#pragma unroll
-            for (int a = 0; a < 3; ++a) qs[(g * 3 + a) * 32 + lane] = q[a];
+            const int64_t sl = base + g * 32 + lane;  // == feat_slot(t)
+            float4 q4 = __ldg(qsaved + sl);
             float f[PL::IN];
 #pragma unroll
             for (int l = 0; l < L; ++l) {
-                const float2 v = __ldg(feat + (int64_t)l * Npad + base + g * 32 + lane);  // == feat_slot(t)
-                f[2 * l] = v.x;
-                f[2 * l + 1] = v.y;
+                const float2 v = __ldg(feat + (int64_t)l * Npad + sl);
+                f[2 * l] = valid ? v.x : 0.f;
+                f[2 * l + 1] = valid ? v.y : 0.f;
             }
+            if (!valid) q4 = make_float4(0.f, 0.f, 0.f, 0.f);  // rows past N were never written by the forward
+            qs[(g * 3 + 0) * 32 + lane] = q4.x;
+            qs[(g * 3 + 1) * 32 + lane] = q4.y;
+            qs[(g * 3 + 2) * 32 + lane] = q4.z;
             float h[PH];
             const float z = prop_mlp<L, SLOT>(f, h);
             // d density / d z = selector * exp(clamp(z, -15, 15))   (activations.py:37-41)
-            const float dz = valid ? __ldg(ddensity + tt) * m * expf(fminf(fmaxf(z, -15.f), 15.f)) : 0.f;
+            const float dz = valid ? __ldg(ddensity + t) * q4.w * expf(fminf(fmaxf(z, -15.f), 15.f)) : 0.f;
             const unsigned nz = __ballot_sync(0xffffffffu, dz != 0.f);
             any |= nz;
             float dh[PH];
 #pragma unroll
-            for (int j = 0; j < PH; ++j) dh[j] = h[j] > 0.f ? dz * c_prop[SLOT][PL::W1 + j] : 0.f;
+            for (int j = 0; j < PH; ++j) dh[j] = h[j] > 0.f ? dz * c_propb[SLOT][PL::W1 + j] : 0.f;
+            {
+                float df[PL::IN];
 #pragma unroll
-            for (int i = 0; i < PL::IN; ++i) {
-                float a = 0.f;
+                for (int i = 0; i < PL::IN; ++i) df[i] = 0.f;
 #pragma unroll
-                for (int j = 0; j < PH; ++j) a = fmaf(c_prop[SLOT][PL::W0 + j * PL::IN + i], dh[j], a);
-                dfs[(g * PL::IN + i) * 32 + lane] = a;
+                for (int j = 0; j < PH; ++j) {
+#pragma unroll
+                    for (int i = 0; i < PL::IN; ++i) df[i] = fmaf(c_propb[SLOT][PL::W0 + j * PL::IN + i], dh[j], df[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < PL::IN; ++i) dfs[(g * PL::IN + i) * 32 + lane] = df[i];
             }
             if (dparams && nz != 0u) {
-                float* row = stage + lane * SM::RS;
 #pragma unroll
-                for (int j = 0; j < PH; ++j) row[SM::S_DH + j] = dh[j];
+                for (int j = 0; j < PH; ++j) accw1[j] = fmaf(dz, h[j], accw1[j]);
+                accb1 += dz;
+                float4* row = reinterpret_cast<float4*>(stage + lane * SM::RS);
 #pragma unroll
-                for (int i = 0; i < 2 * PL::CH; ++i) row[SM::S_F + i] = i < PL::IN ? f[i < PL::IN ? i : 0] : (i == PL::IN ? 1.f : 0.f);  // [f | 1 | 0-pad]
-                row[SM::S_DZ] = dz;
-#pragma unroll
-                for (int j = 0; j < PH; ++j) row[SM::S_H + j] = h[j];
-                row[SM::S_H + PH] = 1.f;
+                for (int k = 0; k < 4; ++k) row[k] = make_float4(dh[4 * k], dh[4 * k + 1], dh[4 * k + 2], dh[4 * k + 3]);
+                row[4] = make_float4(f[0], f[1], f[2], f[3]);
+                row[5] = make_float4(f[4], f[5], f[6], f[7]);
+                row[6] = make_float4(f[8], f[9], 1.f, 0.f);
                 __syncwarp();
 #pragma unroll 4
-                for (int s = 0; s < 32; ++s) {
-                    const float* r = stage + s * SM::RS;
-                    const float gj = r[SM::S_DH + wj];
-                    const float2* fe = reinterpret_cast<const float2*>(r + SM::S_F + whalf * PL::CH);
+                for (int k = 0; k < 16; ++k) {
+                    const float* r = stage + ((k >> 2) * 8 + hw * 4 + (k & 3)) * SM::RS;
+                    const float2 gj = *reinterpret_cast<const float2*>(r + SM::S_DH + 2 * jp);
+                    const float2* fe = reinterpret_cast<const float2*>(r + SM::S_F + 6 * ch);
 #pragma unroll
-                    for (int c = 0; c < PL::CH / 2; ++c) {
+                    for (int c = 0; c < 3; ++c) {
                         const float2 v = fe[c];
-                        acc0[2 * c] = fmaf(gj, v.x, acc0[2 * c]);
-                        acc0[2 * c + 1] = fmaf(gj, v.y, acc0[2 * c + 1]);
+                        acc0[0][2 * c] = fmaf(gj.x, v.x, acc0[0][2 * c]);
+                        acc0[0][2 * c + 1] = fmaf(gj.x, v.y, acc0[0][2 * c + 1]);
+                        acc0[1][2 * c] = fmaf(gj.y, v.x, acc0[1][2 * c]);
+                        acc0[1][2 * c + 1] = fmaf(gj.y, v.y, acc0[1][2 * c + 1]);
                     }
-                    if (lane <= PH) acc1 = fmaf(r[SM::S_DZ], r[SM::S_H + lane], acc1);
                 }
                 __syncwarp();
             }
         }
         // ---------------- pass B ----------------
         if (dtable && any != 0u) {
+            __syncwarp();
 #pragma unroll 1
             for (int l = 0; l < L; ++l) {
                 float* slab = dtable + (((size_t)l << p.log2T) << 1);
                 const float scale = p.scale[l];
-                ScatterRun run;
+                CellRun run;
                 run.reset();
 #pragma unroll
                 for (int g = 0; g < PROP_G; ++g) {
                     const float g0 = dfs[(g * PL::IN + 2 * l) * 32 + lane], g1 = dfs[(g * PL::IN + 2 * l + 1) * 32 + lane];
                     if (g0 == 0.f && g1 == 0.f) continue;  // masked / invalid sample: contributes nothing, must not break a run either
-                    const Corner c = make_corner(qs[(g * 3) * 32 + lane], qs[(g * 3 + 1) * 32 + lane], qs[(g * 3 + 2) * 32 + lane], scale);
-                    run.add(slab, c, mask, g0, g1);
+                    run.add(slab, qs[(g * 3) * 32 + lane], qs[(g * 3 + 1) * 32 + lane], qs[(g * 3 + 2) * 32 + lane], scale, mask, g0, g1);
                 }
-                run.finish(slab);
+                run.flush(slab);
             }
         }
         __syncwarp();
     }
     if (!dparams) return;
-    // ---- CTA reduction of the register accumulators, one atomicAdd per parameter -----------------------------------
+    // ---- warp reduction of the thread-local accumulators, CTA reduction through shared memory, one atomicAdd per parameter ----
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        acc0[0][c] += __shfl_xor_sync(0xffffffffu, acc0[0][c], 16);
+        acc0[1][c] += __shfl_xor_sync(0xffffffffu, acc0[1][c], 16);
+    }
+#pragma unroll
+    for (int j = 0; j < PH; ++j) accw1[j] = nvo_warp_sum(accw1[j]);
+    accb1 = nvo_warp_sum(accb1);
     __syncthreads();
     float* red = smem_f;  // [NW][NP]
     float* mine = red + warp * PL::NP;
-    __syncthreads();
+    if (hw == 0) {
 #pragma unroll
-    for (int c = 0; c < PL::CH; ++c) {
-        const int col = whalf * PL::CH + c;
-        if (col < PL::IN)
-            mine[PL::W0 + wj * PL::IN + col] = acc0[c];
-        else if (col == PL::IN)
-            mine[PL::B0 + wj] = acc0[c];
+        for (int u = 0; u < 2; ++u) {
+            const int j = 2 * jp + u;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const int col = 6 * ch + c;
+                if (col < PL::IN)
+                    mine[PL::W0 + j * PL::IN + col] = acc0[u][c];
+                else if (col == PL::IN)
+                    mine[PL::B0 + j] = acc0[u][c];
+            }
+        }
     }
-    if (lane < PH)
-        mine[PL::W1 + lane] = acc1;
-    else if (lane == PH)
-        mine[PL::B1] = acc1;
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < PH; ++j) mine[PL::W1 + j] = accw1[j];
+        mine[PL::B1] = accb1;
+    }
     __syncthreads();
     for (int e = threadIdx.x; e < PL::NP; e += blockDim.x) {
         float v = 0.f;
@@ -276,12 +304,14 @@ static int prop_params(const nvo_grid_desc* g, int32_t hidden, GridP* p) {
 
 extern "C" int nvo_prop_density_supported(int32_t n_levels, int32_t hidden, int32_t n_layers) { return n_levels == 5 && hidden == PH && n_layers == 2; }
 
-extern "C" int64_t nvo_prop_density_feat_floats(int32_t n_levels, int64_t n) { return (int64_t)n_levels * ((n + 127) / 128 * 128) * 2; }
+extern "C" int64_t nvo_prop_density_feat_floats(int32_t n_levels, int64_t n) { return ((int64_t)n_levels * 2 + 4) * ((n + 127) / 128 * 128); }
 
-static int upload_params(int slot, const float* params, cudaStream_t st) {
+static int upload_params(int slot, const float* params, cudaStream_t st, bool backward_copy = false) {
     NVO_CHECK(slot >= 0 && slot < PROP_SLOTS, "prop_density: slot %d out of range [0,%d)", slot, PROP_SLOTS);
     cudaError_t e = cudaMemcpyToSymbolAsync(c_prop, params, sizeof(float) * PropLayout<5>::NP, sizeof(float) * PROP_SLOT_FLOATS * slot,
                                             cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess && backward_copy)
+        e = cudaMemcpyToSymbolAsync(c_propb, params, sizeof(float) * PropLayout<5>::NP, sizeof(float) * PROP_SLOT_FLOATS * slot, cudaMemcpyDeviceToDevice, st);
     NVO_CHECK(e == cudaSuccess, "prop_density: parameter upload failed: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -319,14 +349,13 @@ extern "C" int nvo_prop_density_forward(const nvo_grid_desc* g, int32_t hidden, 
 }
 
 template <int SLOT>
-static int launch_bwd(const GridP& p, cudaStream_t st, int64_t N, int64_t Npad, int S, const float* o, const float* d, const float* s, const float* e,
-                      int64_t stride, const float* positions, const float* feat, const float* ddensity, float* dtable, float* dparams) {
+static int launch_bwd(const GridP& p, cudaStream_t st, int64_t N, int64_t Npad, int S, const float* feat, const float* ddensity, float* dtable, float* dparams) {
     const size_t smem = sizeof(float) * PropSmem<5>::PER_WARP * (PROP_BWD_THREADS / 32);
     cudaError_t err = cudaFuncSetAttribute(k_prop_bwd<5, SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     NVO_CHECK(err == cudaSuccess, "prop_density_backward: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
     const int64_t blocks = ((N + 127) / 128 + PROP_BWD_THREADS / 32 - 1) / (PROP_BWD_THREADS / 32);
     const unsigned int grid = (unsigned int)min(blocks, (int64_t)nvo_sm_count() * 8);
-    k_prop_bwd<5, SLOT><<<grid, PROP_BWD_THREADS, smem, st>>>(p, N, Npad, S, o, d, s, e, stride, positions, (const float2*)feat, ddensity, dtable, dparams);
+    k_prop_bwd<5, SLOT><<<grid, PROP_BWD_THREADS, smem, st>>>(p, N, Npad, S, (const float2*)feat, ddensity, dtable, dparams);
     return 0;
 }
 
@@ -341,13 +370,13 @@ extern "C" int nvo_prop_density_backward(const nvo_grid_desc* g, int32_t hidden,
     NVO_CHECK(positions || (origins && directions && starts && ends), "prop_density_backward: need positions or rays + intervals");
     const int64_t N = B * S, Npad = (N + 127) / 128 * 128;
     cudaStream_t st = (cudaStream_t)stream;
-    if (int e = upload_params(slot, params, st)) return e;  // re-uploaded: another network may have used the slot since the forward
+    if (int e = upload_params(slot, params, st, true)) return e;  // re-uploaded: another network may have used the slot since the forward
     int rc;
     switch (slot) {
-        case 0: rc = launch_bwd<0>(p, st, N, Npad, S, origins, directions, starts, ends, stride, positions, feat, ddensity, dtable, dparams); break;
-        case 1: rc = launch_bwd<1>(p, st, N, Npad, S, origins, directions, starts, ends, stride, positions, feat, ddensity, dtable, dparams); break;
-        case 2: rc = launch_bwd<2>(p, st, N, Npad, S, origins, directions, starts, ends, stride, positions, feat, ddensity, dtable, dparams); break;
-        default: rc = launch_bwd<3>(p, st, N, Npad, S, origins, directions, starts, ends, stride, positions, feat, ddensity, dtable, dparams); break;
+        case 0: rc = launch_bwd<0>(p, st, N, Npad, S, feat, ddensity, dtable, dparams); break;
+        case 1: rc = launch_bwd<1>(p, st, N, Npad, S, feat, ddensity, dtable, dparams); break;
+        case 2: rc = launch_bwd<2>(p, st, N, Npad, S, feat, ddensity, dtable, dparams); break;
+        default: rc = launch_bwd<3>(p, st, N, Npad, S, feat, ddensity, dtable, dparams); break;
     }
     if (rc) return rc;
     NVO_CUDA_LAUNCH_CHECK("prop_density_backward");

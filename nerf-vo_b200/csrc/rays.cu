@@ -10,7 +10,7 @@
 #define MAX_S 1024
 
 // ---- spacing functions of UniformLinDispPiecewiseSampler (ray_samplers.py:244-245) -------------------------
-__device__ __forceinline__ float spacing_fn(float t) { return t < 1.f ? __fdiv_rn(t, 2.f) : __fsub_rn(1.f, __fdiv_rn(1.f, __fmul_rn(2.f, t))); }
+__device__ __forceinline__ float spacing_fn(float t) { return t < 1.f ? __fmul_rn(t, 0.5f) : __fsub_rn(1.f, __fdiv_rn(1.f, __fmul_rn(2.f, t))); }
 __device__ __forceinline__ float spacing_fn_inv(float s) {
     return s < 0.5f ? __fmul_rn(2.f, s) : __fdiv_rn(1.f, __fsub_rn(2.f, __fmul_rn(2.f, s)));
 }
@@ -29,8 +29,8 @@ __global__ void k_sample_uniform(int64_t B, int S, const float* __restrict__ bas
     float b = __ldg(base + k);
     if (jitter) {
         // ray_samplers.py:105-109: lower + (upper - lower) * t_rand with centres (b[k+1]+b[k])/2
-        const float lo = k == 0 ? b : __fdiv_rn(__fadd_rn(b, __ldg(base + k - 1)), 2.f);
-        const float hi = k == S ? b : __fdiv_rn(__fadd_rn(__ldg(base + k + 1), b), 2.f);
+        const float lo = k == 0 ? b : __fmul_rn(__fadd_rn(b, __ldg(base + k - 1)), 0.5f);
+        const float hi = k == S ? b : __fmul_rn(__fadd_rn(__ldg(base + k + 1), b), 0.5f);
         b = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), __ldg(jitter + r)));
     }
     sdist[t] = b;
@@ -46,7 +46,7 @@ __global__ void k_sample_positions(int64_t B, int S, const float* __restrict__ o
     const float se = __fadd_rn(__ldg(starts + r * stride + k), __ldg(ends + r * stride + k));
 #pragma unroll
     for (int a = 0; a < 3; ++a)  // rays.py:55: origins + directions * (starts + ends) / 2
-        pos[3 * t + a] = __fadd_rn(__ldg(o + 3 * r + a), __fdiv_rn(__fmul_rn(__ldg(d + 3 * r + a), se), 2.f));
+        pos[3 * t + a] = __fadd_rn(__ldg(o + 3 * r + a), __fmul_rn(__fmul_rn(__ldg(d + 3 * r + a), se), 0.5f));
 }
 
 __device__ __forceinline__ float nan_to_num(float v) {
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(32 * RAYS_PER_BLOCK)
         const int i = c0 + lane;
         const bool live = i < S;
         const float w = live ? __ldg(w_ + i) : 0.f;
-        const float t = live ? __fdiv_rn(__fadd_rn(__ldg(st + i), __ldg(en + i)), 2.f) : 0.f;
+        const float t = live ? __fmul_rn(__fadd_rn(__ldg(st + i), __ldg(en + i)), 0.5f) : 0.f;
         if (live) {
             acc += w;
             wt += w * t;
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(32 * RAYS_PER_BLOCK)
         if (out_dmed || out_midx) {
             const int idx = min(max(below_half, 0), S - 1);
             if (out_midx) out_midx[r] = idx;
-            if (out_dmed) out_dmed[r] = __fdiv_rn(__fadd_rn(__ldg(st + idx), __ldg(en + idx)), 2.f);
+            if (out_dmed) out_dmed[r] = __fmul_rn(__fadd_rn(__ldg(st + idx), __ldg(en + idx)), 0.5f);
         }
         if (out_n && normals) {
             const float inv = 1.f / (sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]) + 1e-10f);
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(32 * RAYS_PER_BLOCK)
     for (int i = lane; i < S; i += 32) {
         const float w = __ldg(w_ + i);
         acc += w;
-        if (d_dexp) wt += w * __fdiv_rn(__fadd_rn(__ldg(st + i), __ldg(en + i)), 2.f);
+        if (d_dexp) wt += w * __fmul_rn(__fadd_rn(__ldg(st + i), __ldg(en + i)), 0.5f);
         if (d_n && normals)
 #pragma unroll
             for (int a = 0; a < 3; ++a) N[a] += w * __ldg(normals + (r * S + i) * 3 + a);
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(32 * RAYS_PER_BLOCK)
             for (int a = 0; a < 3; ++a) drgb[(r * S + i) * 3 + a] = 0.f;
         }
         if (d_dexp) {
-            const float t = __fdiv_rn(__fadd_rn(__ldg(st + i), __ldg(en + i)), 2.f);
+            const float t = __fmul_rn(__fadd_rn(__ldg(st + i), __ldg(en + i)), 0.5f);
             dw += g_dexp * (t - dexp) / (acc + 1e-10f);
         }
         if (d_n && normals)

@@ -13,6 +13,7 @@ NS/engine/trainer.py:455-494, NS/pipelines/base_pipeline.py:291-304), restated f
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -190,7 +191,11 @@ class MappingTrainer:
         from . import _lib
 
         self.model.proposal_sampler._step = 10 ** 6  # steady state: `updated` decided by steps_since_update
-        s = torch.cuda.Stream()
+        # the capture stream gets HIGH priority, the gradient-leaf side streams (proposal backward, table scatter) keep the default (lowest):
+        # kernel nodes inherit it, so when a main-chain kernel and a leaf kernel both have CTAs pending the block scheduler places the
+        # main chain first and the leaf kernels fill what is left instead of pushing the chain's start back
+        prio = -1 if os.environ.get("NVO_MAIN_PRIORITY", "1") == "1" else 0
+        s = torch.cuda.Stream(priority=prio)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):
@@ -205,13 +210,13 @@ class MappingTrainer:
         self.model.proposal_sampler._steps_since_update = 10 ** 6
         n0 = _lib.launch_count()
         self._graph_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph_fb):
+        with torch.cuda.graph(self._graph_fb, stream=s):
             self._forward_backward()
             if self.exchange != "nccl":
                 self._optimizer()
         if self.exchange == "nccl":
             self._graph_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph_opt):
+            with torch.cuda.graph(self._graph_opt, stream=s):
                 self._optimizer()
         self.launches_per_step = _lib.launch_count() - n0
 

@@ -1,0 +1,47 @@
+#!/usr/bin/env python
+"""Kernel timeline of the mapping step (CUDA-graph replay) through torch.profiler/CUPTI: per kernel stream, start, duration.
+Writes gpurun_out/timeline_<tag>.csv (one replay) and prints the per-stream busy time and the gaps on the capture stream.
+usage: python tools/timeline.py [--rays 4096] [--tag s6]"""
+import argparse, os, sys, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import nerf_vo_b200 as nv
+from nerf_vo_b200.synthetic import synthetic_jitters, synthetic_rays
+from nerf_vo_b200.trainer import MappingTrainer
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--rays", type=int, default=4096)
+ap.add_argument("--tag", default="step")
+a = ap.parse_args()
+dev = torch.device("cuda", 0)
+torch.manual_seed(0)
+model = nv.ExtendedNerfactoModel(nv.NerfactoModelConfig(), num_train_data=192).to(dev)
+tr = MappingTrainer(model, num_rays=a.rays)
+rays, targets = synthetic_rays(a.rays, num_images=192, seed=1234)
+jit = synthetic_jitters(a.rays, seed=99)
+tr.set_inputs({k: v.to(dev) for k, v in rays.items()}, {k: v.to(dev) for k, v in targets.items()}, [j.to(dev) for j in jit])
+tr.capture(warmup=3)
+for _ in range(5):
+    tr.train_step()
+torch.cuda.synchronize()
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    for _ in range(3):
+        tr.train_step()
+    torch.cuda.synchronize()
+path = os.path.join(ROOT, "gpurun_out", f"trace_{a.tag}.json")
+prof.export_chrome_trace(path)
+ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
+os.remove(path)
+ev.sort(key=lambda e: e["ts"])
+# split into replays by the largest gaps: take the LAST replay
+n = len(ev) // 3
+last = ev[-n:]
+t0 = last[0]["ts"]
+with open(os.path.join(ROOT, "gpurun_out", f"timeline_{a.tag}.csv"), "w") as f:
+    f.write("start_us,dur_us,stream,name\n")
+    for e in last:
+        f.write(f"{e['ts'] - t0:.2f},{e['dur']:.2f},{e['args'].get('stream')},\"{e['name'][:60]}\"\n")
+end = max(e["ts"] + e["dur"] for e in last) - t0
+print(f"replay: {len(last)} activities, span {end:.1f} us")
