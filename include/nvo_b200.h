@@ -68,6 +68,13 @@ int nvo_grid_forward(const nvo_grid_desc* d, void* stream, int64_t n, const floa
 int nvo_grid_backward(const nvo_grid_desc* d, void* stream, int64_t n, const float* x, const void* dy, float* dtable);
 /* dx[n,3] = d(sum(y*dy))/dx  (re-gathers the table instead of storing dy_dx, cf. grid.h:322-349) */
 int nvo_grid_backward_input(const nvo_grid_desc* d, void* stream, int64_t n, const float* x, const void* table, const void* dy, float* dx);
+/* nvo_grid_forward with out_dtype NVO_F16_TMH that also saves d(feature)/d(x) (tcnn's `dy_dx`, grid.h:160-211, stored when input
+ * gradients are prepared): jac = fp16 [tile][chunk][axis 0..2][row 0..127][8], the derivative of the chunk's 8 features w.r.t. the
+ * level-scaled coordinate (NOT yet multiplied by scale_l); 3 x the TMH feature buffer's size. */
+int nvo_grid_forward_jac(const nvo_grid_desc* d, void* stream, int64_t n, const float* x, const void* table, void* y, void* jac);
+/* dx[n,3] = sum_l scale_l * jac_l^T dy_l from the saved derivatives; dy = fp32 tile-major [tile][2L][128] (NVO_F32_TMF).
+ * normalize_scale != 0: dx is written as normalize_scale * v / max(|v|, eps) (density-gradient normals, NS/fields/base_field.py:97-99). */
+int nvo_grid_jac_dx(const nvo_grid_desc* d, void* stream, int64_t n, const void* jac, const float* dy, float normalize_scale, float eps, float* dx);
 /* idx[n, L, 8] int64: table row of every corner in the reference's corner order (encodings.py:435-442). Test hook. */
 int nvo_grid_indices(const nvo_grid_desc* d, void* stream, int64_t n, const float* x, int64_t* idx);
 

@@ -218,17 +218,20 @@ __global__ void __launch_bounds__(256)
                    float* __restrict__ dh, float* __restrict__ dembedding) {
     // element (sample t, column c) of a [n, K] gradient: row-major, or TMF [tile][K][128] (mlp_tc.cu's dx layout)
     auto at = [tmf](const float* g, int K, int64_t t, int c) { return tmf ? __ldg(g + (((t >> 7) * K + c) << 7) + (t & 127)) : __ldg(g + K * t + c); };
-    // one warp per ray when accumulating the appearance-embedding gradient: lanes stride over samples, then a warp
-    // reduction leaves ONE atomicAdd per (ray, channel) instead of S.
+    // one warp per ray: lanes stride over the ray's samples (every global access of the warp is a contiguous run in the tile-major
+    // layout); each lane sums the 32 appearance-gradient channels of ITS samples in registers, a butterfly transpose-reduce (31 shuffles)
+    // then leaves channel k in lane k: ONE atomicAdd per (ray, channel) instead of S.
     const int lane = threadIdx.x & 31;
     const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (r >= B) return;
-    float eacc = 0.f;  // lane k accumulates channel k of the embedding gradient
+    const bool want_emb = dembedding && cam_idx;
+    float e[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) e[k] = 0.f;
     for (int s0 = 0; s0 < S; s0 += 32) {
         const int s = s0 + lane;
-        const bool live = s < S;
-        const int64_t t = r * S + (live ? s : 0);
-        if (live) {
+        if (s < S) {
+            const int64_t t = r * S + s;
             float g[16];
             // trunc_exp backward (activations.py:38-41) with the selector product
             const float h0 = __ldg(h + 16 * t);
@@ -241,15 +244,25 @@ __global__ void __launch_bounds__(256)
             }
 #pragma unroll
             for (int k = 0; k < 16; k += 4) reinterpret_cast<float4*>(dh + 16 * t)[k >> 2] = make_float4(g[k], g[k + 1], g[k + 2], g[k + 3]);
-        }
-        if (dembedding && cam_idx) {
-            // transpose-reduce: for each of the 32 samples of this chunk add its 32 appearance gradients; lane k keeps channel k
-            for (int j = 0; j < 32; ++j) {
-                if (s0 + j < S) eacc += at(dhead_in, HEAD_IN, r * S + s0 + j, 16 + GEO + lane);
+            if (want_emb) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) e[k] += at(dhead_in, HEAD_IN, t, 16 + GEO + k);
             }
         }
     }
-    if (dembedding && cam_idx) atomicAdd(dembedding + APP * __ldg(cam_idx + r) + lane, eacc);
+    if (want_emb) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int i = 0; i < o; ++i) {
+                const float send = up ? e[i] : e[i + o];
+                const float keep = up ? e[i + o] : e[i];
+                e[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+        }
+        atomicAdd(dembedding + APP * __ldg(cam_idx + r) + lane, e[0]);
+    }
 }
 
 // ---- C ABI ----------------------------------------------------------------------------------------------------

@@ -103,6 +103,109 @@ __global__ void __launch_bounds__(256, 3) k_grid_fwd_tmh(const __grid_constant__
     y[(tile * nch + c) * 128 + r] = u;
 }
 
+// The same forward, additionally saving d(feature)/d(x) so that dL/dx later costs no second gather pass (what tcnn's forward does
+// with `dy_dx` when input gradients are prepared, TCNN/.../encodings/grid.h:160-211; nerfstudio needs dL/dx every step for the
+// density-gradient normals, NS/fields/base_field.py:80-101).  Per (row, chunk) three more 16-byte vectors: the x / y / z derivatives
+// of the chunk's 8 features in UNSCALED form (derivative w.r.t. the level's scaled coordinate; the consumer multiplies by scale_l,
+// which keeps the fp16 range independent of the level resolution).  Layout: [tile][chunk][axis][row 0..127][8 halfs].
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+template <typename RowT>
+__global__ void __launch_bounds__(256, 2) k_grid_fwd_tmh_jac(const __grid_constant__ GridP p, int64_t n, int nch, const float* __restrict__ x,
+                                                          const RowT* __restrict__ table, uint4* __restrict__ y, uint4* __restrict__ jac) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= ((n + 127) >> 7 << 7)) return;  // beyond the last (padded) tile
+    const int c = blockIdx.y;
+    uint32_t v[4] = {0u, 0u, 0u, 0u}, jx[4] = {0u, 0u, 0u, 0u}, jy[4] = {0u, 0u, 0u, 0u}, jz[4] = {0u, 0u, 0u, 0u};
+    if (row < n) {
+        const float px = __ldg(x + 3 * row), py = __ldg(x + 3 * row + 1), pz = __ldg(x + 3 * row + 2);
+        const uint32_t mask = (1u << p.log2T) - 1u;
+        float2 f[4][8];
+        Corner cs[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int l = c * 4 + q;
+            if (l < p.L) {
+                cs[q] = make_corner(px, py, pz, p.scale[l]);
+                gather_level(table + ((size_t)l << p.log2T), cs[q], mask, f[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int l = c * 4 + q;
+            if (l < p.L) {
+                const float2 o = trilerp_ref(f[q], cs[q]);  // the feature itself: the reference's rounding sequence, as k_grid_fwd_tmh
+                v[q] = pack_h2(o.x, o.y);
+                const float ox = cs[q].ox, oy = cs[q].oy, oz = cs[q].oz;
+                const float mx = 1.f - ox, my = 1.f - oy, mz = 1.f - oz;
+                float d[2][3];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+#define FJ(k) (j == 0 ? f[q][k].x : f[q][k].y)
+                    const float f03 = FJ(0) * ox + FJ(3) * mx, f12 = FJ(1) * ox + FJ(2) * mx;
+                    const float f56 = FJ(5) * ox + FJ(6) * mx, f47 = FJ(4) * ox + FJ(7) * mx;
+                    d[j][2] = (f03 * oy + f12 * my) - (f47 * oy + f56 * my);
+                    d[j][1] = oz * (f03 - f12) + mz * (f47 - f56);
+                    d[j][0] = oz * (oy * (FJ(0) - FJ(3)) + my * (FJ(1) - FJ(2))) + mz * (oy * (FJ(4) - FJ(7)) + my * (FJ(5) - FJ(6)));
+#undef FJ
+                }
+                jx[q] = pack_h2(d[0][0], d[1][0]);
+                jy[q] = pack_h2(d[0][1], d[1][1]);
+                jz[q] = pack_h2(d[0][2], d[1][2]);
+            }
+        }
+    }
+    const int64_t tile = row >> 7;
+    const int r = (int)(row & 127);
+    y[(tile * nch + c) * 128 + r] = make_uint4(v[0], v[1], v[2], v[3]);
+    uint4* jb = jac + ((tile * nch + c) * 3) * 128 + r;
+    jb[0] = make_uint4(jx[0], jx[1], jx[2], jx[3]);
+    jb[128] = make_uint4(jy[0], jy[1], jy[2], jy[3]);
+    jb[256] = make_uint4(jz[0], jz[1], jz[2], jz[3]);
+}
+
+// dL/dx from the saved derivatives: dx[row][axis] = sum_l scale_l * (J[l,0,axis] * dy[2l] + J[l,1,axis] * dy[2l+1]); dy is the fp32
+// tile-major buffer of the tensor-core MLP backward ([tile][2L][128]).  One thread per row: every access of a warp is contiguous.
+// normalize_scale != 0: the result is written as normalize_scale * v / max(|v|, eps) (the normals epilogue, base_field.py:97-99).
+__global__ void __launch_bounds__(128) k_grid_jac_dx(const __grid_constant__ GridP p, int64_t n, int nch, const uint4* __restrict__ jac,
+                                                     const float* __restrict__ dy, float normalize_scale, float eps, float* __restrict__ dx) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const int64_t tile = row >> 7;
+    const int r = (int)(row & 127);
+    float acc[3] = {0.f, 0.f, 0.f};
+    const int nreal = (p.L + 3) >> 2;
+    for (int c = 0; c < nreal; ++c) {
+        const uint4* jb = jac + ((tile * nch + c) * 3) * 128 + r;
+        const uint4 J[3] = {__ldg(jb), __ldg(jb + 128), __ldg(jb + 256)};
+        const float* db = dy + (((tile * (2 * p.L)) + 8 * c) << 7) + r;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int l = c * 4 + q;
+            if (l < p.L) {
+                const float s = p.scale[l];
+                const float g0 = __ldg(db + ((2 * q) << 7)) * s, g1 = __ldg(db + ((2 * q + 1) << 7)) * s;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const uint32_t w = q == 0 ? J[a].x : q == 1 ? J[a].y : q == 2 ? J[a].z : J[a].w;
+                    const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&w));
+                    acc[a] = fmaf(d.x, g0, fmaf(d.y, g1, acc[a]));
+                }
+            }
+        }
+    }
+    if (normalize_scale != 0.f) {
+        const float nrm = fmaxf(sqrtf(acc[0] * acc[0] + acc[1] * acc[1] + acc[2] * acc[2]), eps);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) acc[a] = normalize_scale * (acc[a] / nrm);
+    }
+    dx[3 * row] = acc[0];
+    dx[3 * row + 1] = acc[1];
+    dx[3 * row + 2] = acc[2];
+}
+
 // Backward scatter: one thread walks GB = 4 consecutive samples (neighbours along a ray) through a group of 4 levels, merging
 // equal-cell runs in registers and pairing the x-floor / x-ceil rows into 16-byte reductions (CellRun, grid_common.cuh).
 // blockIdx.y = level group, so all 16 levels of a sample quad are in flight on different CTAs.
@@ -266,6 +369,37 @@ extern "C" int nvo_grid_forward(const nvo_grid_desc* d, void* stream, int64_t n,
     else
         k_grid_fwd<__half2, __half><<<g, 256, 0, st>>>(p, total, x, (const __half2*)table, (__half*)y);
     NVO_CUDA_LAUNCH_CHECK("grid_forward");
+    return 0;
+}
+
+extern "C" int nvo_grid_forward_jac(const nvo_grid_desc* d, void* stream, int64_t n, const float* x, const void* table, void* y, void* jac) {
+    GridP p;
+    if (int e = make_params(d, &p)) return e;
+    NVO_CHECK(n >= 0, "grid_forward_jac: negative batch");
+    NVO_CHECK(d->out_dtype == NVO_F16_TMH, "grid_forward_jac: output layout must be NVO_F16_TMH");
+    if (n == 0) return 0;
+    NVO_CHECK(x && table && y && jac, "grid_forward_jac: null pointer");
+    const int nch = ((2 * p.L + 15) & ~15) >> 3;
+    const dim3 grid((unsigned int)(((n + 127) / 128 * 128 + 255) / 256), (unsigned int)nch);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d->table_dtype == NVO_F32)
+        k_grid_fwd_tmh_jac<float2><<<grid, 256, 0, st>>>(p, n, nch, x, (const float2*)table, (uint4*)y, (uint4*)jac);
+    else
+        k_grid_fwd_tmh_jac<__half2><<<grid, 256, 0, st>>>(p, n, nch, x, (const __half2*)table, (uint4*)y, (uint4*)jac);
+    NVO_CUDA_LAUNCH_CHECK("grid_forward_jac");
+    return 0;
+}
+
+extern "C" int nvo_grid_jac_dx(const nvo_grid_desc* d, void* stream, int64_t n, const void* jac, const float* dy, float normalize_scale, float eps,
+                               float* dx) {
+    GridP p;
+    if (int e = make_params(d, &p)) return e;
+    NVO_CHECK(n >= 0, "grid_jac_dx: negative batch");
+    if (n == 0) return 0;
+    NVO_CHECK(jac && dy && dx, "grid_jac_dx: null pointer");
+    const int nch = ((2 * p.L + 15) & ~15) >> 3;
+    k_grid_jac_dx<<<nvo_blocks(n, 128), 128, 0, (cudaStream_t)stream>>>(p, n, nch, (const uint4*)jac, dy, normalize_scale, eps, dx);
+    NVO_CUDA_LAUNCH_CHECK("grid_jac_dx");
     return 0;
 }
 

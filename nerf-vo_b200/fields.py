@@ -174,6 +174,14 @@ class NerfactoField(Field):
         self._cache = None
         self._onehot = None
 
+    def tc_networks(self):
+        """(parameter list, MlpSpec) of every network the tensor-core path evaluates, in forward order (ops.prepack_weights)."""
+        nets = [(self.mlp_base.mlp._flat_param_list(), self.mlp_base.mlp.spec), (self.mlp_head._flat_param_list(), self.mlp_head.spec)]
+        if self.use_pred_normals:
+            nets.append((self.mlp_pred_normals._flat_param_list() + [self.field_head_pred_normals.net.weight, self.field_head_pred_normals.net.bias],
+                         self._pn_spec))
+        return nets
+
     def _remember(self, x, h, shape, tc=None) -> None:
         """State get_normals() needs (base_field.py:80-101 keeps _sample_locations / _density_before_activation).  Stored
         DETACHED: normals are first-order and graph-free, and holding autograd nodes across steps would pin the previous
@@ -184,12 +192,13 @@ class NerfactoField(Field):
         self._density_before_activation = h.detach()[:, :1].view(*shape, 1)
 
     # -- density -----------------------------------------------------------------------------------------
-    def _base(self, x: torch.Tensor):
-        """mlp_base(hash_grid(x)) -> h [n,16]: raw density + geo features (nerfacto_field.py:213-215)."""
+    def _base(self, x: torch.Tensor, want_normals: bool = False):
+        """mlp_base(hash_grid(x)) -> h [n,16]: raw density + geo features (nerfacto_field.py:213-215).  want_normals: the
+        grid forward also saves d(feature)/dx (tcnn's dy_dx) so get_normals() needs no second gather pass."""
         enc, mlp = self.mlp_base.encoder, self.mlp_base.mlp
         if self.precision == "fp16":
             mlp._repack()
-            tc = {}
+            tc = {"want_jac": bool(want_normals)}
             return ops.grid_mlp_tc(x, enc.hash_table, enc.spec, mlp.spec, mlp._flat_param_list(), cache=tc), tc
         return mlp(enc(x)), None
 
@@ -225,8 +234,11 @@ class NerfactoField(Field):
                 feat = ops.grid_forward(x, table, enc.spec)
                 y, saved = ops.mlp_forward(feat, flat, mlp.spec, save=True)
                 dfeat, _ = ops.mlp_backward(feat, flat, saved, y, onehot, mlp.spec, need_dx=True, need_dparams=False)
-            g = ops.grid_backward_input(x, table, dfeat, enc.spec, tmf=self.precision == "fp16")
-            normals = ops.normalize3(g, scale=-1.0, eps=1e-12)
+            if self.precision == "fp16" and c["tc"].get("jac") is not None:
+                normals = ops.grid_jac_dx(c["tc"]["jac"], dfeat, enc.spec, n, normalize_scale=-1.0, eps=1e-12)
+            else:
+                g = ops.grid_backward_input(x, table, dfeat, enc.spec, tmf=self.precision == "fp16")
+                normals = ops.normalize3(g, scale=-1.0, eps=1e-12)
         return normals.view(*c["shape"], 3)
 
     # -- colour / predicted normals -------------------------------------------------------------------------
@@ -240,7 +252,7 @@ class NerfactoField(Field):
         B, S = fr.shape
         positions = fr.get_positions()
         x, sel = ops.contract_normalize(positions)
-        h, tc = self._base(x)
+        h, tc = self._base(x, want_normals=compute_normals)
         self._remember(x, h, (B, S), tc)
         dirs = fr.directions.reshape(B, 3).contiguous()
         if self.training:

@@ -151,8 +151,16 @@ class NerfactoModel(nn.Module):
                     outputs["rendered_pred_normal_loss"] = L.pred_normal_loss(weights.detach(), fo[FieldHeadNames.NORMALS].detach(),
                                                                             fo[FieldHeadNames.PRED_NORMALS])
         with torch.no_grad():
+            from . import ops
+
             for i in range(self.config.num_proposal_iterations):
-                outputs[f"prop_depth_{i}"] = render_all(weights_list[i].detach(), ray_samples_list[i])[3]
+                if getattr(self, "_leaf_renders", False) and ops.leaf_streams.enabled:
+                    # nothing inside the step consumes the proposal depth maps: under the trainer (which joins the side streams before
+                    # the optimizer) they are rendered next to the loss kernels instead of in front of them
+                    with ops.leaf_streams.fork(weights_list[i], ray_samples_list[i]):
+                        outputs[f"prop_depth_{i}"] = render_all(weights_list[i].detach(), ray_samples_list[i])[3]
+                else:
+                    outputs[f"prop_depth_{i}"] = render_all(weights_list[i].detach(), ray_samples_list[i])[3]
         if ray_bundle.metadata is not None and "directions_norm" in ray_bundle.metadata:
             outputs["directions_norm"] = ray_bundle.metadata["directions_norm"]
         return outputs

@@ -161,6 +161,25 @@ def grid_backward_input(x, table, dy, spec: GridSpec, tmf: bool = False):
     return dx
 
 
+def grid_forward_jac(x, table, spec: GridSpec):
+    """TMH features plus the saved d(feature)/d(x) (fp16, 3 x the feature buffer; include/nvo_b200.h: nvo_grid_forward_jac)."""
+    _check_grid_inputs(x, table, spec)
+    numel = tmh_numel(x.shape[0], (spec.out_dim + 15) // 16 * 16)
+    y = torch.empty(numel, dtype=torch.float16, device=x.device)
+    jac = torch.empty(3 * numel, dtype=torch.float16, device=x.device)
+    call("nvo_grid_forward_jac", spec.desc(table.dtype, "tmh"), x.shape[0], x, table, y, jac)
+    return y, jac
+
+
+def grid_jac_dx(jac, dy, spec: GridSpec, n: int, normalize_scale: float = 0.0, eps: float = 1e-12):
+    """dx [n,3] from the saved derivatives and the tile-major fp32 dy; normalize_scale != 0 fuses scale * v / max(|v|, eps)."""
+    check(jac, "grid jacobian", torch.float16, (3 * tmh_numel(n, (spec.out_dim + 15) // 16 * 16),))
+    check(dy, "grid dy (tmf)", torch.float32, (tmh_numel(n, spec.out_dim),))
+    dx = torch.empty((n, 3), dtype=torch.float32, device=dy.device)
+    call("nvo_grid_jac_dx", spec.desc(torch.float32, "tmf"), n, jac, dy, normalize_scale, eps, dx)
+    return dx
+
+
 def grid_indices(x, spec: GridSpec):
     check(x, "grid input", torch.float32, (None, 3))
     idx = torch.empty((x.shape[0], spec.n_levels, 8), dtype=torch.int64, device=x.device)
@@ -985,12 +1004,49 @@ def tc_pack_weights(flat, spec: MlpSpec):
     import ctypes
 
     check(flat, "mlp params", torch.float32, (spec.n_params,))
+    hit = _prepacked.get((flat.data_ptr(), id(spec)))
+    if hit is not None:
+        torch.cuda.current_stream().wait_event(hit[1])  # packed ahead on a side stream (prepack_weights)
+        return hit[0]
     nbytes = getattr(spec, "_wimage_bytes", None)
     if nbytes is None:
         nbytes = spec._wimage_bytes = int(_lib.load().nvo_mlp_tc_wimage_bytes(ctypes.addressof(spec.desc)))
     img = torch.empty(nbytes, dtype=torch.uint8, device=flat.device)
     call("nvo_mlp_tc_pack_weights", spec.desc, flat, img)
     return img
+
+
+# weight images packed ahead of their use: (parameter pointer, spec) -> (image, ready event).  The trainer fills it at the start of a
+# step on a side stream (the parameters only change in the optimizer), so the three repack launches leave the forward's critical chain;
+# it is cleared before the optimizer runs.
+_prepacked: dict = {}
+
+
+def prepack_weights(nets) -> None:
+    """nets: iterable of (params list, MlpSpec).  Images are allocated on the CURRENT stream (their consumers' stream) and written on a
+    side stream; tc_pack_weights() hands them out after waiting for the ready event."""
+    import ctypes
+
+    jobs = []
+    for params, spec in nets:
+        flat = _flat_of(params)
+        nbytes = getattr(spec, "_wimage_bytes", None)
+        if nbytes is None:
+            nbytes = spec._wimage_bytes = int(_lib.load().nvo_mlp_tc_wimage_bytes(ctypes.addressof(spec.desc)))
+        jobs.append((flat, spec, torch.empty(nbytes, dtype=torch.uint8, device=flat.device)))
+    if not jobs:
+        return
+    with leaf_streams.fork(*[j[2] for j in jobs]):
+        for flat, spec, img in jobs:
+            call("nvo_mlp_tc_pack_weights", spec.desc, flat, img)
+        ev = torch.cuda.Event()
+        ev.record()
+    for flat, spec, img in jobs:
+        _prepacked[(flat.data_ptr(), id(spec))] = (img, ev)
+
+
+def clear_prepacked() -> None:
+    _prepacked.clear()
 
 
 def mlp_tc_forward(x16, wimage, spec: MlpSpec, n: int, save: bool, row_mask=None):
@@ -1082,10 +1138,15 @@ class _GridMlpTC(torch.autograd.Function):
     def forward(ctx, x, table, gspec, mspec, cache, *params):
         x = x.contiguous()
         n = x.shape[0]
-        feat16 = grid_forward(x, table, gspec, "tmh")
+        jac = None
+        if cache is not None and cache.get("want_jac"):
+            feat16, jac = grid_forward_jac(x, table, gspec)  # normals follow: keep d(feature)/dx instead of re-gathering the table
+        else:
+            feat16 = grid_forward(x, table, gspec, "tmh")
         wimage = tc_pack_weights(_flat_of(params), mspec)
         y, saved = mlp_tc_forward(feat16, wimage, mspec, n, any(ctx.needs_input_grad) or cache is not None)
         if cache is not None:
+            cache["jac"] = jac
             # y.detach(): a separate tensor object — the returned `y` gets a grad_fn attached, and caching it would pin this step's
             # autograd graph (and its stream) into the next step, which breaks CUDA-graph capture
             cache.update(feat16=feat16, wimage=wimage, saved=saved, y=y.detach())

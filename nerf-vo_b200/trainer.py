@@ -138,7 +138,16 @@ class MappingTrainer:
 
     def _forward_backward(self) -> None:
         i = self.inputs
-        self.grad.zero_()
+        side = self.device.type == "cuda" and ops.leaf_streams.enabled
+        if side:
+            # off the critical chain: the 74 MB zero fill of the flat gradient and the fp16 weight images of the three field networks
+            # run on side streams next to the proposal sampling; both are joined before their first consumer
+            with ops.leaf_streams.fork(self.grad):
+                self.grad.zero_()
+            if self.model.field.precision == "fp16":
+                ops.prepack_weights(self.model.field.tc_networks())
+        else:
+            self.grad.zero_()
         if self.datamanager is not None:
             bundle, batch = self.datamanager.next_train(0)  # DynamicDataManager.next_train (nerfstudio_utils.py:295-300)
             if not self.with_normals:
@@ -150,8 +159,15 @@ class MappingTrainer:
             batch = {"image": i["rgb"], "depth_image": i["depth"]}
             if self.with_normals:
                 batch["normal_image"] = i["normal"]
-        _, total, terms, weights = self.model.get_train_loss_fused(bundle, batch, [i["jitter0"], i["jitter1"], i["jitter2"]])
+        self.model._leaf_renders = side  # proposal depth maps rendered on side streams (joined below), only inside this step
+        try:
+            _, total, terms, weights = self.model.get_train_loss_fused(bundle, batch, [i["jitter0"], i["jitter1"], i["jitter2"]])
+        finally:
+            self.model._leaf_renders = False
+        if side:
+            ops.leaf_streams.join()  # the zero fill must have landed before the first backward kernel accumulates into the gradient
         total.backward()
+        ops.clear_prepacked()
         ops.leaf_streams.join()  # scatter kernels running on side streams must land before the all-reduce / optimizer
         self.loss.copy_(total.detach())
         self._terms, self._term_weights = terms, weights

@@ -85,6 +85,45 @@ def test_grid_empty_and_ragged(nv):
         assert torch.equal(nv.ops.grid_forward(x, table, spec).cpu(), ref)
 
 
+def _rows_to_tmf(a):
+    """[n, K] row-major -> the tensor-core MLP backward's fp32 tile-major layout [tile][K][128] (rows zero padded to whole tiles)."""
+    n, k = a.shape
+    tiles = (n + 127) // 128
+    pad = torch.zeros(tiles * 128, k, dtype=a.dtype, device=a.device)
+    pad[:n] = a
+    return pad.view(tiles, 128, k).permute(0, 2, 1).contiguous().view(-1)
+
+
+@pytest.mark.parametrize("L,log2,n", [(16, 12, 1000), (16, 19, 128 * 40 + 17), (5, 10, 333)])
+def test_grid_saved_jacobian_input_gradient(nv, L, log2, n):
+    """nvo_grid_forward_jac + nvo_grid_jac_dx (saved d feature / dx, tcnn's dy_dx) against the exact fp32 oracle gradient and against the
+    re-gathering kernel; the features written next to the Jacobian are bit-identical to nvo_grid_forward's."""
+    gc = O.GridCfg(num_levels=L, log2_hashmap_size=log2, max_res=2048 if L == 16 else 128)
+    sc = O.level_scalings(gc)
+    spec = nv.ops.GridSpec(L, log2, tuple(float(s) for s in sc))
+    gen = torch.Generator().manual_seed(L * 100 + log2)
+    x = torch.rand(n, 3, generator=gen)
+    x[0] = torch.tensor([0.25, 0.5, 0.75])  # on grid planes of the coarse levels: floor == ceil, zero derivative there
+    table = torch.randn(L << log2, 2, generator=gen) * 0.1
+    dy = torch.randn(n, 2 * L, generator=gen)
+    xg = x.clone().requires_grad_(True)
+    (O.hash_encode(xg, table, sc, log2) * dy).sum().backward()
+    xd, td = x.to(DEV), table.to(DEV)
+    feat, jac = nv.ops.grid_forward_jac(xd, td, spec)
+    assert torch.equal(feat, nv.ops.grid_forward(xd, td, spec, "tmh"))
+    dy_tmf = _rows_to_tmf(dy.to(DEV))
+    dx = nv.ops.grid_jac_dx(jac, dy_tmf, spec, n)
+    exact = nv.ops.grid_backward_input(xd, td, dy_tmf, spec, tmf=True)
+    assert rel_err(exact, xg.grad) < 1e-5
+    # derivatives are stored in fp16 (unscaled, so the range does not depend on the level resolution): 11-bit mantissa
+    assert rel_err(dx, xg.grad) < 2e-3
+    # fused normals epilogue: -v / max(|v|, eps)
+    nrm = nv.ops.grid_jac_dx(jac, dy_tmf, spec, n, normalize_scale=-1.0, eps=1e-12)
+    ref = -torch.nn.functional.normalize(dx, dim=-1, eps=1e-12)
+    assert float((nrm - ref).abs().max()) < 1e-6
+    assert nv.ops.grid_jac_dx(jac[:0], dy_tmf[:0], spec, 0).shape == (0, 3)
+
+
 def test_grid_errors(nv):
     spec = nv.ops.GridSpec(16, 12, tuple(float(s) for s in O.level_scalings(O.GridCfg(log2_hashmap_size=12))))
     table = torch.randn(16 << 12, 2, device=DEV)
