@@ -18,12 +18,17 @@
 // (nvo_peer_alloc / nvo_peer_open); PyTorch wraps them as tensors.  Spin waits are bounded (~4 s): on timeout the kernel
 // raises the error word instead of hanging the GPU.
 #include "nvo_common.cuh"
+#include <stdlib.h>
 
 #define NVO_MAX_PEERS 16
 #define FLAG_READY 0                 // flags[FLAG_READY + k]: rank k's gradients of epoch e are complete
 #define FLAG_DONE NVO_MAX_PEERS      // flags[FLAG_DONE + k]:  rank k has finished reading / writing peers for epoch e
 #define FLAG_COUNT (2 * NVO_MAX_PEERS)   // flags[FLAG_COUNT]: local CTA completion counter; [FLAG_COUNT+1]: error word
-#define FLAG_WORDS 64
+// one block of flags per exchange PHASE (parameter group): the groups' exchanges of one step run as separate launches that may be in
+// flight at the same time (the fields group is exchanged while the proposal networks' backward still runs)
+#define FLAG_PHASE_STRIDE 40
+#define NVO_MAX_PHASES 3
+#define FLAG_WORDS 128
 
 struct PeerSet {
     float* params[NVO_MAX_PEERS];
@@ -68,13 +73,13 @@ __device__ __forceinline__ bool wait_all(const int* flags, int base, int world, 
 template <int W, int U>
 __global__ void __launch_bounds__(256) k_exchange_adam(const __grid_constant__ PeerSet ps, int rank, int64_t lo4, int64_t hi4, float* __restrict__ m,
                                                        float* __restrict__ v, const int* __restrict__ step_ptr, float lr, float b1, float b2, float eps,
-                                                       float grad_scale) {
-    int* my_flags = ps.flags[rank];
+                                                       float grad_scale, int flag_base) {
+    int* my_flags = ps.flags[rank] + flag_base;
     const int epoch = *step_ptr + 1;
     // ---- 1. every rank's backward has landed -----------------------------------------------------------------------
     if (blockIdx.x == 0 && threadIdx.x < W && threadIdx.x != rank) {
         __threadfence_system();
-        st_release_sys(ps.flags[threadIdx.x] + FLAG_READY + rank, epoch);
+        st_release_sys(ps.flags[threadIdx.x] + flag_base + FLAG_READY + rank, epoch);
     }
     if (!wait_all(my_flags, FLAG_READY, W, rank, epoch)) {
         if (threadIdx.x == 0) atomicExch(my_flags + FLAG_COUNT + 1, 1);
@@ -128,7 +133,7 @@ __global__ void __launch_bounds__(256) k_exchange_adam(const __grid_constant__ P
     if (!s_last) return;
     if (threadIdx.x == 0) my_flags[FLAG_COUNT] = 0;  // re-armed for the next step
     __threadfence_system();
-    if (threadIdx.x < W && threadIdx.x != rank) st_release_sys(ps.flags[threadIdx.x] + FLAG_DONE + rank, epoch);
+    if (threadIdx.x < W && threadIdx.x != rank) st_release_sys(ps.flags[threadIdx.x] + flag_base + FLAG_DONE + rank, epoch);
     if (!wait_all(my_flags, FLAG_DONE, W, rank, epoch)) {
         if (threadIdx.x == 0) atomicExch(my_flags + FLAG_COUNT + 1, 2);
     }
@@ -136,7 +141,7 @@ __global__ void __launch_bounds__(256) k_exchange_adam(const __grid_constant__ P
 
 __global__ void k_tick_step(int* step) { *step += 1; }
 
-typedef void (*exchange_fn)(const PeerSet, int, int64_t, int64_t, float*, float*, const int*, float, float, float, float, float);
+typedef void (*exchange_fn)(const PeerSet, int, int64_t, int64_t, float*, float*, const int*, float, float, float, float, float, int);
 
 extern "C" int nvo_exchange_flag_words(void) { return FLAG_WORDS; }
 
@@ -151,18 +156,25 @@ extern "C" int64_t nvo_exchange_slice(int64_t n, int32_t rank, int32_t world, in
     return (b - a) * 4;
 }
 
-extern "C" int nvo_adam_exchange_step(void* stream, int64_t n, int32_t rank, int32_t world, const void* h_peer_params, const void* h_peer_grads,
-                                      const void* h_peer_flags, float* exp_avg_slice, float* exp_avg_sq_slice, int32_t* step, float lr, float beta1,
-                                      float beta2, float eps, float grad_scale) {
-    NVO_CHECK(n > 0 && (n & 3) == 0, "adam_exchange_step: flat size %lld must be a positive multiple of 4 floats", (long long)n);
-    NVO_CHECK(world >= 1 && world <= NVO_MAX_PEERS && rank >= 0 && rank < world, "adam_exchange_step: bad rank/world %d/%d", rank, world);
-    NVO_CHECK(h_peer_params && h_peer_grads && h_peer_flags && exp_avg_slice && exp_avg_sq_slice && step, "adam_exchange_step: null pointer");
+// Exchange + Adam of the flat range [offset, offset + n) (one parameter group); `phase` selects the group's block of flags.
+extern "C" int nvo_adam_exchange_group(void* stream, int64_t offset, int64_t n, int32_t phase, int32_t rank, int32_t world, const void* h_peer_params,
+                                       const void* h_peer_grads, const void* h_peer_flags, float* exp_avg_slice, float* exp_avg_sq_slice, int32_t* step,
+                                       float lr, float beta1, float beta2, float eps, float grad_scale) {
+    NVO_CHECK(n > 0 && (n & 3) == 0 && offset >= 0 && (offset & 3) == 0, "adam_exchange: range [%lld, +%lld) must be float4-aligned and non-empty",
+              (long long)offset, (long long)n);
+    NVO_CHECK(phase >= 0 && phase < NVO_MAX_PHASES, "adam_exchange: phase %d out of range [0,%d)", phase, NVO_MAX_PHASES);
+    NVO_CHECK(world >= 1 && world <= NVO_MAX_PEERS && rank >= 0 && rank < world, "adam_exchange: bad rank/world %d/%d", rank, world);
+    NVO_CHECK(h_peer_params && h_peer_grads && h_peer_flags && exp_avg_slice && exp_avg_sq_slice && step, "adam_exchange: null pointer");
     PeerSet ps;
     for (int k = 0; k < NVO_MAX_PEERS; ++k) {
         ps.params[k] = k < world ? ((float* const*)h_peer_params)[k] : nullptr;
         ps.grads[k] = k < world ? ((const float* const*)h_peer_grads)[k] : nullptr;
         ps.flags[k] = k < world ? ((int* const*)h_peer_flags)[k] : nullptr;
-        if (k < world) NVO_CHECK(ps.params[k] && ps.grads[k] && ps.flags[k], "adam_exchange_step: null peer pointer for rank %d", k);
+        if (k < world) {
+            NVO_CHECK(ps.params[k] && ps.grads[k] && ps.flags[k], "adam_exchange: null peer pointer for rank %d", k);
+            ps.params[k] += offset;
+            ps.grads[k] += offset;
+        }
     }
     int64_t lo, hi;
     nvo_exchange_slice(n, rank, world, &lo, &hi);
@@ -172,19 +184,34 @@ extern "C" int nvo_adam_exchange_step(void* stream, int64_t n, int32_t rank, int
         case 2: fn = k_exchange_adam<2, 4>; break;
         case 4: fn = k_exchange_adam<4, 2>; break;
         case 8: fn = k_exchange_adam<8, 1>; break;
-        default: NVO_CHECK(false, "adam_exchange_step: world size %d unsupported (1, 2, 4 or 8 GPUs of one NVSwitch domain)", world);
+        default: NVO_CHECK(false, "adam_exchange: world size %d unsupported (1, 2, 4 or 8 GPUs of one NVSwitch domain)", world);
     }
     cudaStream_t st = (cudaStream_t)stream;
-    // persistent grid: as many 256-thread CTAs as are co-resident (every CTA takes part in the flag waits, so none may queue)
+    // persistent grid: as many 256-thread CTAs as are co-resident (measured at 2 GPUs: 151 us for the whole flat buffer against 175 us
+    // with two CTAs per SM).  NVO_EXCHANGE_CTAS_PER_SM=k caps it, for runs that overlap the exchange with other kernels.
     const int64_t items = (hi - lo) / 4;
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0);
-    const unsigned int grid = (unsigned int)max((int64_t)1, min((int64_t)nvo_sm_count() * max(per_sm, 1), (items + 255) / 256));
-    fn<<<grid, 256, 0, st>>>(ps, rank, lo / 4, hi / 4, exp_avg_slice, exp_avg_sq_slice, step, lr, beta1, beta2, eps, grad_scale);
-    NVO_CUDA_LAUNCH_CHECK("adam_exchange_step");
+    per_sm = max(per_sm, 1);
+    if (const char* cap = getenv("NVO_EXCHANGE_CTAS_PER_SM")) per_sm = max(1, min(per_sm, atoi(cap)));
+    const unsigned int grid = (unsigned int)max((int64_t)1, min((int64_t)nvo_sm_count() * per_sm, (items + 255) / 256));
+    // An SM's L1 / shared-memory split is fixed while any CTA is resident.  This kernel uses no shared memory, so by default it would
+    // configure its SMs with the smallest carve-out and the proposal backward (40 KB of dynamic shared memory per CTA) could not become
+    // co-resident until the exchange had drained (observed: profiles/r01_timeline_n2_s9_early_no_carveout.csv).  Ask for the largest
+    // carve-out instead.
+    cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    fn<<<grid, 256, 0, st>>>(ps, rank, lo / 4, hi / 4, exp_avg_slice, exp_avg_sq_slice, step, lr, beta1, beta2, eps, grad_scale, phase * FLAG_PHASE_STRIDE);
+    NVO_CUDA_LAUNCH_CHECK("adam_exchange");
     k_tick_step<<<1, 1, 0, st>>>(step);
-    NVO_CUDA_LAUNCH_CHECK("adam_exchange_step(tick)");
+    NVO_CUDA_LAUNCH_CHECK("adam_exchange(tick)");
     return 0;
+}
+
+extern "C" int nvo_adam_exchange_step(void* stream, int64_t n, int32_t rank, int32_t world, const void* h_peer_params, const void* h_peer_grads,
+                                      const void* h_peer_flags, float* exp_avg_slice, float* exp_avg_sq_slice, int32_t* step, float lr, float beta1,
+                                      float beta2, float eps, float grad_scale) {
+    return nvo_adam_exchange_group(stream, 0, n, 0, rank, world, h_peer_params, h_peer_grads, h_peer_flags, exp_avg_slice, exp_avg_sq_slice, step, lr,
+                                   beta1, beta2, eps, grad_scale);
 }
 
 // ---- peer-visible allocations (CUDA IPC) ----------------------------------------------------------------------------------

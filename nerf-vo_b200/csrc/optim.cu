@@ -59,6 +59,9 @@ extern "C" int nvo_adam_step(void* stream, int64_t n, float* params, const float
               "adam_step: buffers must be 16-byte aligned");
     const int64_t n4 = n / 4;
     cudaStream_t st = (cudaStream_t)stream;
+    // largest shared-memory carve-out: kernels with dynamic shared memory (proposal backward) can then share an SM with this one
+    // (the L1 / shared split of an SM cannot change while CTAs are resident); Adam streams and has no use for L1
+    cudaFuncSetAttribute(k_adam, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     k_adam<<<nvo_blocks(n4 > 0 ? n4 : 1, 256), 256, 0, st>>>(n4, n, params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, grad_scale);
     NVO_CUDA_LAUNCH_CHECK("adam_step");
     k_tick<<<1, 1, 0, st>>>(step);

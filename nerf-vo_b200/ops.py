@@ -28,6 +28,11 @@ class _LeafStreams:
         self.used: List[torch.cuda.Stream] = []
         self.refs: list = []
         self.next = 0
+        # set by the trainer for the duration of one backward pass:
+        #   after_field_backward(): called on the side stream that carries the main hash-table scatter, right after its launch;
+        #   defer_event: the fused proposal backward waits for it (keeps those long kernels out of the field's backward chain)
+        self.after_field_backward = None
+        self.defer_event = None
 
     def enable(self, n: int = 3, n_levels: int = 2):
         self.streams = [torch.cuda.Stream() for _ in range(n)]
@@ -388,6 +393,8 @@ class _PropDensity(torch.autograd.Function):
         ddensity = ddensity.contiguous()
         args = ("nvo_prop_density_backward", ctx.gspec.desc(table.dtype, torch.float32), ctx.hidden, ctx.slot, ctx.B, ctx.S, origins, directions, s, e, stride, positions,
                 flat, feat, ddensity, dtable, dflat)
+        if leaf_streams.defer_event is not None:
+            torch.cuda.current_stream().wait_event(leaf_streams.defer_event)
         if (leaf_streams.enabled and not leaf_streams.on_level_stream() and (not need_dt or dtable is ctx.table_main_grad)
                 and (not need_dp or dflat is ctx.mlp_main_grad)):
             with leaf_streams.fork(table, flat, feat, origins, directions, positions, ddensity, ctx.iv):
@@ -1166,6 +1173,8 @@ class _GridMlpTC(torch.autograd.Function):
             if ctx.table_main_grad is not None and leaf_streams.enabled:
                 with leaf_streams.fork(x, dfeat):
                     grid_backward(x, dfeat, ctx.gspec, dtable=ctx.table_main_grad, tmf=True)
+                    if leaf_streams.after_field_backward is not None and not need_dx:
+                        leaf_streams.after_field_backward()
             elif ctx.table_main_grad is not None:
                 grid_backward(x, dfeat, ctx.gspec, dtable=ctx.table_main_grad, tmf=True)
             else:

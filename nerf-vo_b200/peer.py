@@ -101,10 +101,35 @@ class PeerBuffers:
         _lib.call("nvo_adam_exchange_step", self.n, self.rank, self.world, ctypes.addressof(self._h_params), ctypes.addressof(self._h_grads),
                   ctypes.addressof(self._h_flags), self.exp_avg, self.exp_avg_sq, step, lr, beta1, beta2, eps, 1.0 / self.world)
 
+    def add_group(self, offset: int, n: int) -> int:
+        """Registers the flat range [offset, offset + n) as one optimizer parameter group: its own Adam moments (only this rank's slice of
+        the range) and its own block of flags (exchange phase).  Returns the group id for adam_exchange_group."""
+        if offset % 4 or n % 4 or n <= 0 or offset < 0 or offset + n > self.n:
+            raise RuntimeError(f"parameter group [{offset}, +{n}) must be float4-aligned and inside the flat buffer of {self.n} floats")
+        if not hasattr(self, "_groups"):
+            self._groups = []
+        if len(self._groups) >= 3:
+            raise RuntimeError("at most 3 exchange groups (flag phases)")
+        chunk = slice_range(n, 0, self.world)[1]
+        with torch.cuda.device(self.device):
+            m = torch.zeros(max(chunk, 4), dtype=torch.float32, device=self.device)
+            self._groups.append((int(offset), int(n), m, torch.zeros_like(m)))
+        return len(self._groups) - 1
+
+    def group_moments(self, gid: int):
+        return self._groups[gid][2], self._groups[gid][3]
+
+    def adam_exchange_group(self, gid: int, step: torch.Tensor, lr: float, beta1: float, beta2: float, eps: float) -> None:
+        """adam_exchange_step restricted to one registered group; `step` is the GROUP's device counter (incremented here)."""
+        off, n, m, v = self._groups[gid]
+        _lib.call("nvo_adam_exchange_group", off, n, gid, self.rank, self.world, ctypes.addressof(self._h_params), ctypes.addressof(self._h_grads),
+                  ctypes.addressof(self._h_flags), m, v, step, lr, beta1, beta2, eps, 1.0 / self.world)
+
     def error_word(self) -> int:
-        """0 = healthy; 1 / 2 = a peer never signalled 'gradients ready' / 'replicas written' (bounded spin timed out)."""
+        """0 = healthy; 1 / 2 = a peer never signalled 'gradients ready' / 'replicas written' (bounded spin timed out) in any phase."""
         words = int(_lib.load().nvo_exchange_flag_words())
-        return int(self.flags[33].item()) if words > 33 else 0
+        f = self.flags.cpu()
+        return max([int(f[40 * ph + 33]) for ph in range(3) if 40 * ph + 33 < words] or [0])
 
     def close(self) -> None:
         lib = _lib.load()

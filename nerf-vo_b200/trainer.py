@@ -9,7 +9,13 @@ NS/engine/trainer.py:455-494, NS/pipelines/base_pipeline.py:291-304), restated f
     (`exchange="fused"`, csrc/exchange.cu: reduce-scatter by NVLink peer loads -> Adam on the rank's slice -> all-gather by
     peer stores, one kernel, the step stays a single CUDA graph) or, as the library arm, ONE NCCL sum-all-reduce of the flat
     gradient followed by the replicated Adam (`exchange="nccl"`); both give DDP's mean-gradient semantics
-    (NS/pipelines/base_pipeline.py:281-283).
+    (NS/pipelines/base_pipeline.py:281-283);
+  * two optimizer parameter groups like the reference's ("fields", "proposal_networks": NS/models/nerfacto.py:244-249, one Adam each,
+    NS/engine/optimizers.py:138-150), each with its own step counter.  The fields group is stepped (and exchanged) as soon as the main
+    hash-table scatter has landed — on a high-priority stream, next to the proposal networks' backward, which is ordered behind the
+    field's backward chain; the proposal group follows.  `proposal_update="reference"` follows ProposalNetworkSampler's update schedule
+    (NS/model_components/ray_samplers.py:596-610): on steps where the proposal networks receive no gradient their backward is not run
+    and their Adam group is not stepped (torch skips parameters whose .grad is None); "always" updates them every step.
 """
 from __future__ import annotations
 
@@ -28,7 +34,7 @@ from .rays import RayBundle
 class MappingTrainer:
     def __init__(self, model: ExtendedNerfactoModel, num_rays: int, lr: float = 1e-2, eps: float = 1e-15, betas=(0.9, 0.999),
                  use_cuda_graph: bool = True, with_normals: bool = True, device: Optional[torch.device] = None, exchange: str = "fused",
-                 datamanager=None):
+                 datamanager=None, proposal_update: str = "always"):
         self.model = model
         # optional: a DynamicDataManager (data.py). The step then starts with the fused prologue kernel (pixel sampling + gather + ray
         # generation, drawn on the device like the reference's torch.rand) instead of reading the static input buffers.
@@ -43,6 +49,10 @@ class MappingTrainer:
         self.peer = None
         self.use_cuda_graph = use_cuda_graph
         self.with_normals = with_normals
+        if proposal_update not in ("always", "reference"):
+            raise ValueError(f"proposal_update must be 'always' or 'reference', got {proposal_update!r}")
+        self.proposal_update = proposal_update
+        self.iteration = 0  # host-side step number (drives the proposal update schedule)
         model.train()
         # ---- flat parameter / gradient / optimizer-state buffers ---------------------------------------------
         self.params = [p for p in model.parameters() if p.requires_grad]
@@ -55,19 +65,33 @@ class MappingTrainer:
         # 16-byte alignment of every tensor start keeps float4 / float2 accesses legal: pad each to a multiple of 4 floats
         sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]
         total = sum(sizes)
+        # parameter groups = contiguous ranges of the flat buffer: "fields" first, "proposal_networks" behind it (registration order)
+        names = {id(p): n for n, p in model.named_parameters()}
+        is_prop = [names[id(p)].startswith("proposal_networks.") for p in self.params]
+        n_fields = sum(sz for sz, pr in zip(sizes, is_prop) if not pr)
+        contiguous = all(not pr for pr in is_prop[:is_prop.index(True)]) and all(is_prop[is_prop.index(True):]) if any(is_prop) else True
+        if any(is_prop) and contiguous and 0 < n_fields < total:
+            self.groups = [("fields", 0, n_fields), ("proposal_networks", n_fields, total - n_fields)]
+        else:
+            self.groups = [("fields", 0, total)]
         if self.exchange == "fused":
-            # parameters and gradients live in peer-mapped (CUDA IPC) allocations; Adam moments only for the slice this rank owns
+            # parameters and gradients live in peer-mapped (CUDA IPC) allocations; Adam moments only for the slices this rank owns
             from .peer import PeerBuffers
 
             self.peer = PeerBuffers(total, self.device)
             self.flat, self.grad = self.peer.params, self.peer.grads
-            self.exp_avg, self.exp_avg_sq = self.peer.exp_avg, self.peer.exp_avg_sq
+            self._peer_groups = [self.peer.add_group(off, n) for _, off, n in self.groups]
+            self.exp_avg = self.exp_avg_sq = None
         else:
             self.flat = torch.zeros(total, dtype=torch.float32, device=self.device)
             self.grad = torch.zeros_like(self.flat)
             self.exp_avg = torch.zeros_like(self.flat)
             self.exp_avg_sq = torch.zeros_like(self.flat)
-        self.step_count = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # one device step counter per group (torch keeps `step` per parameter; a group that got no gradient is not stepped)
+        self.step_counts = [torch.zeros(1, dtype=torch.int32, device=self.device) for _ in self.groups]
+        self.step_count = self.step_counts[0]
+        self._opt_stream: Optional[torch.cuda.Stream] = None
+        self._fields_done = False
         off = 0
         self._views = []
         for p, n in zip(self.params, sizes):
@@ -137,8 +161,13 @@ class MappingTrainer:
                          metadata={"directions_norm": i["directions_norm"]})
 
     def _forward_backward(self) -> None:
+        """zero-grad, forward, losses, backward.  On the fused / local arms the optimizer of the "fields" group is launched from
+        INSIDE the backward (ops.leaf_streams.after_field_backward), right behind the main hash-table scatter, on a high-priority
+        stream; the proposal networks' backward is ordered behind the field's chain, so both run side by side (one is HBM / NVLink
+        bound, the other issue / reduction bound).  _optimizer() then steps whatever has not been stepped yet."""
         i = self.inputs
         side = self.device.type == "cuda" and ops.leaf_streams.enabled
+        self._fields_done = False
         if side:
             # off the critical chain: the 74 MB zero fill of the flat gradient and the fp16 weight images of the three field networks
             # run on side streams next to the proposal sampling; both are joined before their first consumer
@@ -166,18 +195,56 @@ class MappingTrainer:
             self.model._leaf_renders = False
         if side:
             ops.leaf_streams.join()  # the zero fill must have landed before the first backward kernel accumulates into the gradient
-        total.backward()
+        # Early launch of the fields group's optimizer / exchange next to the (deferred) proposal backward: measured on one and two B200s
+        # (profiles/r01_timeline_*s9*.csv) it does not pay — both sides want the same registers (the exchange keeps 128 B of peer loads in
+        # flight per thread), so the proposal backward crawls while the exchange runs, and the field chain loses the proposal backward
+        # that used to fill its idle issue slots.  Kept behind NVO_EARLY_FIELDS_OPT=1 for boxes with more ranks.
+        early = side and len(self.groups) == 2 and self.exchange != "nccl" and os.environ.get("NVO_EARLY_FIELDS_OPT", "0") == "1"
+        if early:
+            ops.leaf_streams.after_field_backward = self._fields_optimizer_hook
+        try:
+            total.backward()
+        finally:
+            ops.leaf_streams.after_field_backward = None
+            ops.leaf_streams.defer_event = None
         ops.clear_prepacked()
         ops.leaf_streams.join()  # scatter kernels running on side streams must land before the all-reduce / optimizer
+        if self._fields_done:
+            torch.cuda.current_stream().wait_stream(self._opt_stream)
         self.loss.copy_(total.detach())
         self._terms, self._term_weights = terms, weights
 
-    def _optimizer(self) -> None:
+    def _fields_optimizer_hook(self) -> None:
+        """Called by the main grid's backward on the side stream that carries the table scatter, after the scatter was launched: every
+        gradient of the "fields" group is complete once that stream reaches this point."""
+        cur = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        ops.leaf_streams.defer_event = ev  # the proposal networks' backward starts here, not next to the field's backward chain
+        if self._opt_stream is None:
+            self._opt_stream = torch.cuda.Stream(priority=-1)
+        self._opt_stream.wait_event(ev)
+        with torch.cuda.stream(self._opt_stream):
+            self._optimizer_group(0)
+        self._fields_done = True
+
+    def _optimizer_group(self, gi: int) -> None:
+        _, off, n = self.groups[gi]
         if self.peer is not None:
-            self.peer.adam_exchange_step(self.step_count, self.lr, self.betas[0], self.betas[1], self.eps)
+            self.peer.adam_exchange_group(self._peer_groups[gi], self.step_counts[gi], self.lr, self.betas[0], self.betas[1], self.eps)
             return
-        ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.betas[0], self.betas[1], self.eps,
-                      1.0 / self.world_size)
+        ops.adam_step(self.flat[off:off + n], self.grad[off:off + n], self.exp_avg[off:off + n], self.exp_avg_sq[off:off + n], self.step_counts[gi],
+                      self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / self.world_size)
+
+    def _optimizer(self, updated: bool = True) -> None:
+        """Steps every group that has not been stepped inside the backward; the proposal group only when it received gradients."""
+        for gi, (name, _, _) in enumerate(self.groups):
+            if gi == 0 and self._fields_done:
+                continue
+            if name == "proposal_networks" and not updated:
+                continue
+            self._optimizer_group(gi)
+        self._fields_done = False
 
     def _exchange(self) -> None:
         """NCCL arm: sum-all-reduce of the flat gradient (the fused arm exchanges inside the optimizer kernel)."""
@@ -202,54 +269,83 @@ class MappingTrainer:
                 n += v.numel() * v.element_size()
         return n
 
+    def _set_sampler_state(self, updated: bool) -> None:
+        """Pins ProposalNetworkSampler's `updated` predicate (ray_samplers.py:596: steps_since_update > sched(step) or step < 10)."""
+        ps = self.model.proposal_sampler
+        ps._step = 10 ** 6
+        ps._steps_since_update = 10 ** 6 if updated else 0
+
+    def _updated_now(self) -> bool:
+        """The reference's predicate for THIS iteration; rank-invariant (depends on step counters only)."""
+        if self.proposal_update == "always":
+            return True
+        ps = self.model.proposal_sampler
+        seen = max(self.iteration - 1, 0)  # the sampler's _step is set by the AFTER_TRAIN_ITERATION callback of the previous iteration
+        return bool(self._ssu > ps.update_sched(seen) or seen < 10)
+
     def capture(self, warmup: int = 3) -> None:
-        """Warm up on a side stream, then capture forward+backward (and the optimizer) into CUDA graphs."""
+        """Warm up on a side stream, then capture forward+backward (and the optimizer) into CUDA graphs: one graph for steps that update
+        the proposal networks and, with proposal_update="reference", one for steps that do not."""
         from . import _lib
 
-        self.model.proposal_sampler._step = 10 ** 6  # steady state: `updated` decided by steps_since_update
         # the capture stream gets HIGH priority, the gradient-leaf side streams (proposal backward, table scatter) keep the default (lowest):
         # kernel nodes inherit it, so when a main-chain kernel and a leaf kernel both have CTAs pending the block scheduler places the
         # main chain first and the leaf kernels fill what is left instead of pushing the chain's start back
         prio = -1 if os.environ.get("NVO_MAIN_PRIORITY", "1") == "1" else 0
         s = torch.cuda.Stream(priority=prio)
         s.wait_stream(torch.cuda.current_stream())
+        self._ssu = 0
+        modes = [True] if self.proposal_update == "always" else [True, False]
         with torch.cuda.stream(s):
             for _ in range(warmup):
-                self.model.proposal_sampler._steps_since_update = 10 ** 6  # always update the proposal networks (worst case)
-                self._forward_backward()
-                self._exchange()
-                self._optimizer()
+                for upd in modes:
+                    self._set_sampler_state(upd)
+                    self._forward_backward()
+                    self._exchange()
+                    self._optimizer(upd)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         if not self.use_cuda_graph:
             return
-        self.model.proposal_sampler._steps_since_update = 10 ** 6
-        n0 = _lib.launch_count()
-        self._graph_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph_fb, stream=s):
-            self._forward_backward()
-            if self.exchange != "nccl":
-                self._optimizer()
-        if self.exchange == "nccl":
-            self._graph_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph_opt, stream=s):
-                self._optimizer()
-        self.launches_per_step = _lib.launch_count() - n0
+        self._graphs = {}
+        for upd in modes:
+            self._set_sampler_state(upd)
+            n0 = _lib.launch_count()
+            g_fb = torch.cuda.CUDAGraph()
+            g_opt = None
+            with torch.cuda.graph(g_fb, stream=s):
+                self._forward_backward()
+                if self.exchange != "nccl":
+                    self._optimizer(upd)
+            if self.exchange == "nccl":
+                g_opt = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_opt, stream=s):
+                    self._optimizer(upd)
+            self._graphs[upd] = (g_fb, g_opt)
+            if upd:
+                self.launches_per_step = _lib.launch_count() - n0
+        self._graph_fb, self._graph_opt = self._graphs[True]
 
     def train_step(self) -> torch.Tensor:
         """Runs one step on the current contents of the static input buffers; returns the (device) loss scalar."""
+        upd = self._updated_now() if hasattr(self, "_ssu") else True
         if self._graph_fb is not None:
-            self._graph_fb.replay()
+            g_fb, g_opt = self._graphs[upd]
+            g_fb.replay()
             if self.exchange == "nccl":
                 sharding.allreduce_gradient_(self.grad)
-                self._graph_opt.replay()
+                g_opt.replay()
         else:
             from . import _lib
 
             n0 = _lib.launch_count()
-            self.model.proposal_sampler._steps_since_update = 10 ** 6
+            self._set_sampler_state(upd)
             self._forward_backward()
             self._exchange()
-            self._optimizer()
+            self._optimizer(upd)
             self.launches_per_step = _lib.launch_count() - n0
+        # ProposalNetworkSampler.step_cb + the reset in generate_ray_samples (ray_samplers.py:591-594,611-612)
+        if hasattr(self, "_ssu"):
+            self._ssu = 1 if upd else self._ssu + 1
+        self.iteration += 1
         return self.loss

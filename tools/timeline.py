@@ -14,12 +14,17 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--rays", type=int, default=4096)
 ap.add_argument("--tag", default="step")
 a = ap.parse_args()
-dev = torch.device("cuda", 0)
+world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+torch.cuda.set_device(dev)
+if world > 1:  # under torchrun: every rank steps (fused exchange), rank 0 writes its own timeline
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
 torch.manual_seed(0)
 model = nv.ExtendedNerfactoModel(nv.NerfactoModelConfig(), num_train_data=192).to(dev)
 tr = MappingTrainer(model, num_rays=a.rays)
-rays, targets = synthetic_rays(a.rays, num_images=192, seed=1234)
-jit = synthetic_jitters(a.rays, seed=99)
+rays, targets = synthetic_rays(a.rays, num_images=192, seed=1234 + 1000 * rank)
+jit = synthetic_jitters(a.rays, seed=99 + 1000 * rank)
 tr.set_inputs({k: v.to(dev) for k, v in rays.items()}, {k: v.to(dev) for k, v in targets.items()}, [j.to(dev) for j in jit])
 tr.capture(warmup=3)
 for _ in range(5):
@@ -30,6 +35,11 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(3):
         tr.train_step()
     torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
+    if rank != 0:
+        dist.destroy_process_group()
+        sys.exit(0)
 path = os.path.join(ROOT, "gpurun_out", f"trace_{a.tag}.json")
 prof.export_chrome_trace(path)
 ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
