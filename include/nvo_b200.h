@@ -155,6 +155,11 @@ int nvo_prop_density_forward(const nvo_grid_desc* g, int32_t hidden, int32_t slo
 int nvo_prop_density_backward(const nvo_grid_desc* g, int32_t hidden, int32_t slot, void* stream, int64_t B, int32_t S, const float* origins,
                               const float* directions, const float* starts, const float* ends, int64_t stride, const float* positions,
                               const float* params, const float* feat, const float* ddensity, float* dtable, float* dparams);
+/* The same backward split in two: this call runs the MLP part only (weight gradients into dparams) and writes the feature gradients as
+ * fp32 tile-major [tile][2L][128] (NVO_F32_TMF) plus the normalised, selector-masked positions xq [ceil(n/128)*128, 3]; the caller then
+ * scatters them with nvo_grid_backward(out_dtype = NVO_F32_TMF), whose long-run kernel merges equal-cell runs over 16 samples of a ray. */
+int nvo_prop_density_backward_split(const nvo_grid_desc* g, int32_t hidden, int32_t slot, void* stream, int64_t B, int32_t S, const float* params,
+                                    const float* feat, const float* ddensity, float* dparams, float* dfeat_tmf, float* xq);
 
 /* ---------------------------------------------------------------------------------------------
  * Field element-wise operators.

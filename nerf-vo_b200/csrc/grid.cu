@@ -7,6 +7,7 @@
 // 32/L consecutive samples: x loads are near-broadcast, the y / dy accesses of a warp are one contiguous
 // 256-byte run (fp32) and every thread keeps 8 independent 8-byte (float2) or 4-byte (half2) gathers in flight.
 #include "grid_common.cuh"
+#include <stdlib.h>
 
 __device__ __forceinline__ void store_feat(float* y, int64_t t, float a, float b) { reinterpret_cast<float2*>(y)[t] = make_float2(a, b); }
 __device__ __forceinline__ void store_feat(__half* y, int64_t t, float a, float b) { reinterpret_cast<__half2*>(y)[t] = __floats2half2_rn(a, b); }
@@ -260,6 +261,55 @@ __global__ void __launch_bounds__(128) k_grid_bwd(const __grid_constant__ GridP 
     }
 }
 
+// Long-run variant for the tile-major fp32 dy of the tensor-core path: one thread walks G consecutive samples (G = 8 or 16: a third of
+// a 48-sample ray) through ONE level (blockIdx.y), so equal-cell runs of the coarse levels — a ray's samples cluster around a surface —
+// are merged over 2-4 times more samples before a reduction is issued.  Same thread count as k_grid_bwd's (quad, 4-level group).
+template <int G>
+__global__ void __launch_bounds__(128) k_grid_bwd_run(const __grid_constant__ GridP p, int64_t n, const float* __restrict__ x,
+                                                      const float* __restrict__ dy, float* __restrict__ dtable) {
+    const int64_t t0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * G;
+    if (t0 >= n) return;
+    const int l = blockIdx.y;
+    float* slab = dtable + (((size_t)l << p.log2T) << 1);
+    const float scale = p.scale[l];
+    const uint32_t mask = (1u << p.log2T) - 1u;
+    // the G samples sit in one 128-row tile (G divides 128): G contiguous floats per feature column
+    const float* b = dy + (((t0 >> 7) * (2 * p.L) + 2 * l) << 7) + (t0 & 127);
+    float g0[G], g1[G];
+#pragma unroll
+    for (int k = 0; k < G; k += 4) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(b + k)), c = __ldg(reinterpret_cast<const float4*>(b + 128 + k));
+        g0[k] = a.x, g0[k + 1] = a.y, g0[k + 2] = a.z, g0[k + 3] = a.w;
+        g1[k] = c.x, g1[k + 1] = c.y, g1[k + 2] = c.z, g1[k + 3] = c.w;
+    }
+    CellRun run;
+    run.reset();
+    const bool full = t0 + G <= n;
+#pragma unroll
+    for (int k = 0; k < G; k += 4) {
+        float q[4][3];
+        if (full) {  // x + 3*t0 is 16-byte aligned: t0 is a multiple of 4 and the caller checked the base pointer
+            const float4* xv = reinterpret_cast<const float4*>(x + 3 * (t0 + k));
+            const float4 a = __ldg(xv), bb = __ldg(xv + 1), c = __ldg(xv + 2);
+            q[0][0] = a.x, q[0][1] = a.y, q[0][2] = a.z, q[1][0] = a.w, q[1][1] = bb.x, q[1][2] = bb.y;
+            q[2][0] = bb.z, q[2][1] = bb.w, q[2][2] = c.x, q[3][0] = c.y, q[3][1] = c.z, q[3][2] = c.w;
+        } else {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int64_t t = min(t0 + k + g, n - 1);
+                q[g][0] = __ldg(x + 3 * t), q[g][1] = __ldg(x + 3 * t + 1), q[g][2] = __ldg(x + 3 * t + 2);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            if (t0 + k + g >= n) break;
+            if (g0[k + g] == 0.f && g1[k + g] == 0.f) continue;
+            run.add(slab, q[g][0], q[g][1], q[g][2], scale, mask, g0[k + g], g1[k + g]);
+        }
+    }
+    run.flush(slab);
+}
+
 // dL/dx: one thread per (sample, level) computes its level's contribution, then the L lanes of a sample are
 // summed with warp shuffles when L divides 32 (main grid, L=16), else with atomics (L=5 proposals).
 template <typename RowT, typename OutT>
@@ -410,6 +460,20 @@ extern "C" int nvo_grid_backward(const nvo_grid_desc* d, void* stream, int64_t n
     if (n == 0) return 0;
     NVO_CHECK(x && dy && dtable, "grid_backward: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    if (d->out_dtype == NVO_F32_TMF && (reinterpret_cast<size_t>(dy) & 15) == 0 && (reinterpret_cast<size_t>(x) & 15) == 0) {
+        // samples per thread and level: 16 (default; measured on a step's own sample positions: 146 -> 121 us), 8, or 0 = the quad kernel
+        const char* e = getenv("NVO_GRID_BWD_RUN");
+        const int run_g = e ? atoi(e) : 16;
+        if (run_g == 8 || run_g == 16) {
+            const dim3 gr(nvo_blocks((n + run_g - 1) / run_g, 128), (unsigned int)p.L);
+            if (run_g == 8)
+                k_grid_bwd_run<8><<<gr, 128, 0, st>>>(p, n, x, (const float*)dy, dtable);
+            else
+                k_grid_bwd_run<16><<<gr, 128, 0, st>>>(p, n, x, (const float*)dy, dtable);
+            NVO_CUDA_LAUNCH_CHECK("grid_backward(run)");
+            return 0;
+        }
+    }
     const dim3 g(nvo_blocks((n + GB - 1) / GB, 128), (unsigned int)((p.L + 3) / 4));
     if (d->out_dtype == NVO_F32 || d->out_dtype == NVO_F32_TMF)
         k_grid_bwd<float><<<g, 128, 0, st>>>(p, n, x, (const float*)dy, dtable, d->out_dtype == NVO_F32_TMF);

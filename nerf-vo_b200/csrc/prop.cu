@@ -134,10 +134,15 @@ struct PropSmem {
     static_assert(PL::IN + 1 <= 12 && PH == 16, "staging tile is laid out for 16 hidden units and <= 11 extended input columns");
 };
 
-template <int L, int SLOT>
-__global__ void __launch_bounds__(PROP_BWD_THREADS, 4) k_prop_bwd(const __grid_constant__ GridP p, int64_t N, int64_t Npad, int S,
+// SPLIT: the kernel stops after pass A and hands the feature gradients (fp32 tile-major [tile][2L][128], the layout of the tensor-core
+// MLP's input gradient) and the normalised positions ([Npad,3]) to the long-run table scatter of grid.cu (k_grid_bwd_run: 16 consecutive
+// samples of a ray per thread and level).  Measured (profiles/r01_ncu_step_kernels_s10.md): the fused kernel runs 16 warps per SM at
+// 126 registers and issues ~2000 instructions per sample, most of them in pass B's divergent flushes; two lean kernels are faster.
+template <int L, int SLOT, bool SPLIT>
+__global__ void __launch_bounds__(PROP_BWD_THREADS, SPLIT ? 5 : 4) k_prop_bwd(const __grid_constant__ GridP p, int64_t N, int64_t Npad, int S,
                                                                   const float2* __restrict__ feat, const float* __restrict__ ddensity,
-                                                                  float* __restrict__ dtable, float* __restrict__ dparams) {
+                                                                  float* __restrict__ dtable, float* __restrict__ dparams,
+                                                                  float* __restrict__ df_tmf, float* __restrict__ xq) {
     using PL = PropLayout<L>;
     using SM = PropSmem<L>;
     constexpr int NW = PROP_BWD_THREADS / 32;
@@ -228,8 +233,22 @@ __global__ void __launch_bounds__(PROP_BWD_THREADS, 4) k_prop_bwd(const __grid_c
                 __syncwarp();
             }
         }
+        if (SPLIT) {
+            // coalesced hand-over: lane owns rows 4*lane .. 4*lane+3 of the tile = its four samples (g = 0..3)
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < PL::IN; ++i) {
+                const float4 v = make_float4(dfs[(0 * PL::IN + i) * 32 + lane], dfs[(1 * PL::IN + i) * 32 + lane], dfs[(2 * PL::IN + i) * 32 + lane],
+                                             dfs[(3 * PL::IN + i) * 32 + lane]);
+                *reinterpret_cast<float4*>(df_tmf + (((st * PL::IN) + i) << 7) + 4 * lane) = v;
+            }
+            float4* xo = reinterpret_cast<float4*>(xq + 3 * (base + 4 * lane));
+            xo[0] = make_float4(qs[0 * 32 + lane], qs[1 * 32 + lane], qs[2 * 32 + lane], qs[3 * 32 + lane]);
+            xo[1] = make_float4(qs[4 * 32 + lane], qs[5 * 32 + lane], qs[6 * 32 + lane], qs[7 * 32 + lane]);
+            xo[2] = make_float4(qs[8 * 32 + lane], qs[9 * 32 + lane], qs[10 * 32 + lane], qs[11 * 32 + lane]);
+        }
         // ---------------- pass B ----------------
-        if (dtable && any != 0u) {
+        if (!SPLIT && dtable && any != 0u) {
             __syncwarp();
 #pragma unroll 1
             for (int l = 0; l < L; ++l) {
@@ -349,19 +368,47 @@ extern "C" int nvo_prop_density_forward(const nvo_grid_desc* g, int32_t hidden, 
 }
 
 template <int SLOT>
-static int launch_bwd(const GridP& p, cudaStream_t st, int64_t N, int64_t Npad, int S, const float* feat, const float* ddensity, float* dtable, float* dparams) {
+static int launch_bwd(const GridP& p, cudaStream_t st, int64_t N, int64_t Npad, int S, const float* feat, const float* ddensity, float* dtable, float* dparams,
+                      float* df_tmf, float* xq) {
     const size_t smem = sizeof(float) * PropSmem<5>::PER_WARP * (PROP_BWD_THREADS / 32);
-    cudaError_t err = cudaFuncSetAttribute(k_prop_bwd<5, SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    NVO_CHECK(err == cudaSuccess, "prop_density_backward: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
     const int64_t blocks = ((N + 127) / 128 + PROP_BWD_THREADS / 32 - 1) / (PROP_BWD_THREADS / 32);
+    if (df_tmf) {
+        cudaError_t err = cudaFuncSetAttribute(k_prop_bwd<5, SLOT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        NVO_CHECK(err == cudaSuccess, "prop_density_backward: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+        const unsigned int grid = (unsigned int)min(blocks, (int64_t)nvo_sm_count() * 10);
+        k_prop_bwd<5, SLOT, true><<<grid, PROP_BWD_THREADS, smem, st>>>(p, N, Npad, S, (const float2*)feat, ddensity, nullptr, dparams, df_tmf, xq);
+        return 0;
+    }
+    cudaError_t err = cudaFuncSetAttribute(k_prop_bwd<5, SLOT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    NVO_CHECK(err == cudaSuccess, "prop_density_backward: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
     const unsigned int grid = (unsigned int)min(blocks, (int64_t)nvo_sm_count() * 8);
-    k_prop_bwd<5, SLOT><<<grid, PROP_BWD_THREADS, smem, st>>>(p, N, Npad, S, (const float2*)feat, ddensity, dtable, dparams);
+    k_prop_bwd<5, SLOT, false><<<grid, PROP_BWD_THREADS, smem, st>>>(p, N, Npad, S, (const float2*)feat, ddensity, dtable, dparams, nullptr, nullptr);
     return 0;
 }
+
+static int prop_backward_impl(const nvo_grid_desc* g, int32_t hidden, int32_t slot, void* stream, int64_t B, int32_t S, const float* origins,
+                              const float* directions, const float* starts, const float* ends, int64_t stride, const float* positions,
+                              const float* params, const float* feat, const float* ddensity, float* dtable, float* dparams, float* df_tmf, float* xq);
 
 extern "C" int nvo_prop_density_backward(const nvo_grid_desc* g, int32_t hidden, int32_t slot, void* stream, int64_t B, int32_t S, const float* origins,
                                          const float* directions, const float* starts, const float* ends, int64_t stride, const float* positions,
                                          const float* params, const float* feat, const float* ddensity, float* dtable, float* dparams) {
+    return prop_backward_impl(g, hidden, slot, stream, B, S, origins, directions, starts, ends, stride, positions, params, feat, ddensity, dtable, dparams,
+                              nullptr, nullptr);
+}
+
+extern "C" int nvo_prop_density_backward_split(const nvo_grid_desc* g, int32_t hidden, int32_t slot, void* stream, int64_t B, int32_t S,
+                                               const float* params, const float* feat, const float* ddensity, float* dparams, float* dfeat_tmf,
+                                               float* xq) {
+    NVO_CHECK(dfeat_tmf && xq, "prop_density_backward_split: null output pointer");
+    // any non-null `positions` stands for "no ray arguments needed": the backward works from the saved features only
+    return prop_backward_impl(g, hidden, slot, stream, B, S, nullptr, nullptr, nullptr, nullptr, 0, feat, params, feat, ddensity, nullptr, dparams, dfeat_tmf,
+                              xq);
+}
+
+static int prop_backward_impl(const nvo_grid_desc* g, int32_t hidden, int32_t slot, void* stream, int64_t B, int32_t S, const float* origins,
+                              const float* directions, const float* starts, const float* ends, int64_t stride, const float* positions,
+                              const float* params, const float* feat, const float* ddensity, float* dtable, float* dparams, float* df_tmf, float* xq) {
     GridP p;
     if (int e = prop_params(g, hidden, &p)) return e;
     NVO_CHECK(B >= 0 && S >= 1, "prop_density_backward: bad shape");
@@ -373,10 +420,10 @@ extern "C" int nvo_prop_density_backward(const nvo_grid_desc* g, int32_t hidden,
     if (int e = upload_params(slot, params, st, true)) return e;  // re-uploaded: another network may have used the slot since the forward
     int rc;
     switch (slot) {
-        case 0: rc = launch_bwd<0>(p, st, N, Npad, S, feat, ddensity, dtable, dparams); break;
-        case 1: rc = launch_bwd<1>(p, st, N, Npad, S, feat, ddensity, dtable, dparams); break;
-        case 2: rc = launch_bwd<2>(p, st, N, Npad, S, feat, ddensity, dtable, dparams); break;
-        default: rc = launch_bwd<3>(p, st, N, Npad, S, feat, ddensity, dtable, dparams); break;
+        case 0: rc = launch_bwd<0>(p, st, N, Npad, S, feat, ddensity, dtable, dparams, df_tmf, xq); break;
+        case 1: rc = launch_bwd<1>(p, st, N, Npad, S, feat, ddensity, dtable, dparams, df_tmf, xq); break;
+        case 2: rc = launch_bwd<2>(p, st, N, Npad, S, feat, ddensity, dtable, dparams, df_tmf, xq); break;
+        default: rc = launch_bwd<3>(p, st, N, Npad, S, feat, ddensity, dtable, dparams, df_tmf, xq); break;
     }
     if (rc) return rc;
     NVO_CUDA_LAUNCH_CHECK("prop_density_backward");

@@ -2,6 +2,8 @@
 autograd graph only; every arithmetic step of the hot path runs in libnvo_b200.so.  No CPU fallback."""
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -393,14 +395,28 @@ class _PropDensity(torch.autograd.Function):
         ddensity = ddensity.contiguous()
         args = ("nvo_prop_density_backward", ctx.gspec.desc(table.dtype, torch.float32), ctx.hidden, ctx.slot, ctx.B, ctx.S, origins, directions, s, e, stride, positions,
                 flat, feat, ddensity, dtable, dflat)
+        split = need_dt and os.environ.get("NVO_PROP_BWD_SPLIT", "1") == "1"
+
+        def run():
+            if not split:
+                call(*args)
+                return
+            # two lean kernels instead of the fused one: MLP part -> tile-major feature gradients + positions, then the long-run scatter
+            n = ctx.B * ctx.S
+            dft = torch.empty(tmh_numel(n, ctx.gspec.out_dim), dtype=torch.float32, device=dev)
+            xq = torch.empty(((n + 127) // 128 * 128, 3), dtype=torch.float32, device=dev)
+            call("nvo_prop_density_backward_split", ctx.gspec.desc(table.dtype, torch.float32), ctx.hidden, ctx.slot, ctx.B, ctx.S, flat, feat, ddensity, dflat,
+                 dft, xq)
+            grid_backward(xq[:n], dft, ctx.gspec, dtable=dtable.view(-1, 2), tmf=True)
+
         if leaf_streams.defer_event is not None:
             torch.cuda.current_stream().wait_event(leaf_streams.defer_event)
         if (leaf_streams.enabled and not leaf_streams.on_level_stream() and (not need_dt or dtable is ctx.table_main_grad)
                 and (not need_dp or dflat is ctx.mlp_main_grad)):
             with leaf_streams.fork(table, flat, feat, origins, directions, positions, ddensity, ctx.iv):
-                call(*args)
+                run()
         else:
-            call(*args)
+            run()
         if dtable is ctx.table_main_grad:
             dtable = None
         elif dtable is not None and table.dtype != torch.float32:

@@ -124,6 +124,29 @@ def test_grid_saved_jacobian_input_gradient(nv, L, log2, n):
     assert nv.ops.grid_jac_dx(jac[:0], dy_tmf[:0], spec, 0).shape == (0, 3)
 
 
+@pytest.mark.parametrize("n", [16, 1000, 128 * 30 + 77])
+def test_grid_scatter_tile_major_variants(nv, n, monkeypatch):
+    """The tile-major (tensor-core path) scatter — long-run kernel (16 or 8 samples per thread and level) and quad kernel — against the
+    row-major scatter and the oracle's index_put gradient, ragged sizes included; positions along 'rays' so equal-cell runs occur."""
+    L, log2 = 16, 14
+    sc = O.level_scalings(O.GridCfg(log2_hashmap_size=log2))
+    spec = nv.ops.GridSpec(L, log2, tuple(float(s) for s in sc))
+    gen = torch.Generator().manual_seed(n)
+    o, d = torch.rand(n // 16 + 1, 3, generator=gen), torch.randn(n // 16 + 1, 3, generator=gen) * 0.02
+    x = (o[:, None] + d[:, None] * torch.linspace(0, 1, 16)[None, :, None]).reshape(-1, 3)[:n].clamp(0.001, 0.999).contiguous()
+    dy = torch.randn(n, 2 * L, generator=gen)
+    dy[n // 2] = 0.0  # a masked sample inside a run
+    table = torch.zeros(L << log2, 2, requires_grad=True)
+    (O.hash_encode(x, table, sc, log2) * dy).sum().backward()
+    xd, dyd = x.to(DEV), dy.to(DEV)
+    rows = nv.ops.grid_backward(xd, dyd, spec)
+    assert rel_err(rows, table.grad) < 1e-5
+    for run in ("16", "8", "0"):
+        monkeypatch.setenv("NVO_GRID_BWD_RUN", run)
+        tm = nv.ops.grid_backward(xd, _rows_to_tmf(dyd), spec, tmf=True)
+        assert rel_err(tm, table.grad) < 1e-5, run
+
+
 def test_grid_errors(nv):
     spec = nv.ops.GridSpec(16, 12, tuple(float(s) for s in O.level_scalings(O.GridCfg(log2_hashmap_size=12))))
     table = torch.randn(16 << 12, 2, device=DEV)

@@ -10,12 +10,31 @@ import nerf_vo_b200 as nv
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=196608)
 ap.add_argument("--log2", type=int, default=19)
+ap.add_argument("--step-positions", action="store_true")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
 L = 16
 spec = nv.ops.GridSpec(L, a.log2, tuple(float(s) for s in nv.ops.torch_level_scalings(L, 16, 2048)))
 x = torch.rand(a.n, 3, device=dev)
+if a.step_positions:
+    # the final-level sample positions of a real mapping step (48 PDF-resampled samples per ray: clustered, unlike uniform noise)
+    from nerf_vo_b200.synthetic import synthetic_jitters, synthetic_rays
+    from nerf_vo_b200.trainer import MappingTrainer
+    B = a.n // 48
+    model = nv.ExtendedNerfactoModel(nv.NerfactoModelConfig(), num_train_data=192).to(dev)
+    with torch.no_grad():
+        for nme, prm in model.named_parameters():
+            if "hash_table" in nme:
+                prm.normal_(0, 0.1)  # "trained-like" tables: densities are not ~1 everywhere, so the PDF samples cluster
+    tr = MappingTrainer(model, num_rays=B, use_cuda_graph=False)
+    rays, targets = synthetic_rays(B, num_images=192, seed=1234)
+    tr.set_inputs({k: v.to(dev) for k, v in rays.items()}, {k: v.to(dev) for k, v in targets.items()}, [j.to(dev) for j in synthetic_jitters(B, seed=99)])
+    for _ in range(3):
+        tr.train_step()
+    x = model.field._cache["x"].detach().clone()
+    a.n = x.shape[0]
+    del tr, model
 table = (torch.rand(L << a.log2, 2, device=dev) * 2 - 1) * 1e-3
 dtable = torch.zeros_like(table)
 dy = torch.randn(nv.ops.tmh_numel(a.n, 2 * L), device=dev)
@@ -41,4 +60,14 @@ timed("grid_forward (tmh)", lambda: nv.ops.grid_forward(x, table, spec, "tmh"), 
 timed("grid_forward_jac (tmh + fp16 dy_dx)", lambda: nv.ops.grid_forward_jac(x, table, spec), alg_bytes=n * (12 + 16 * 64 + 64 + 192))
 timed("grid_backward_input (re-gather)", lambda: nv.ops.grid_backward_input(x, table, dy, spec, tmf=True), alg_bytes=n * (12 + 16 * 64 + 128 + 12))
 timed("grid_jac_dx", lambda: nv.ops.grid_jac_dx(jac, dy, spec, n, -1.0), alg_bytes=n * (192 + 128 + 12))
-timed("grid_backward (scatter)", lambda: nv.ops.grid_backward(x, dy, spec, dtable=dtable, tmf=True), alg_bytes=n * (12 + 128 + 16 * 64))
+ref = None
+for run in ("0", "8", "16"):
+    os.environ["NVO_GRID_BWD_RUN"] = run
+    dtable.zero_()
+    nv.ops.grid_backward(x, dy, spec, dtable=dtable, tmf=True)
+    if ref is None:
+        ref = dtable.clone()
+    else:
+        print(f"  run={run}: max |d - d_ref| / max|d_ref| = {float((dtable - ref).abs().max() / ref.abs().max()):.2e}")
+    timed(f"grid_backward (scatter) NVO_GRID_BWD_RUN={run}", lambda: nv.ops.grid_backward(x, dy, spec, dtable=dtable, tmf=True), alg_bytes=n * (12 + 128 + 16 * 64))
+os.environ.pop("NVO_GRID_BWD_RUN")
