@@ -47,6 +47,16 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_tensor_peak():
+    """Dense bf16/fp16 tensor peak in TFLOP/s: the burst figure (kernels timed alone)."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        if "bf16_tflops" in d:
+            return float(d["bf16_tflops"]), "measured burst (MEASURED_PEAKS.json)"
+    return 1636.0, "fallback (B200_PROFILING.md)"
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
 
@@ -258,6 +268,45 @@ def run_ours(args):
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": RECORDED_TRAFFIC.get("k_grid_fwd_tmh"),
                     "peak_source": peak_src, "launch_us": t_ms * 1e3, "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_per_sample": per_sample,
                     "samples_per_launch": N, "inputs": "sample positions of the last timed step"}
+        # secondary kernels, timed the same way (L2 flushed, CUDA events): the main-table scatter against HBM, the three field networks'
+        # tensor-core kernels against the dense fp16/bf16 tensor peak (SURVEY 8d FLOP counts, unpadded)
+        def timed_us(fn, reps=20):
+            ev = []
+            for i in range(3 + reps):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record()
+                ev.append((a, b))
+            torch.cuda.synchronize()
+            return sum(a.elapsed_time(b) for a, b in ev[3:]) / reps * 1e3
+
+        tpeak, tpeak_src = load_tensor_peak()
+        extras = []
+        dy_tmf = torch.randn(nv.ops.tmh_numel(N, enc.spec.out_dim), device=dev)
+        scratch = torch.zeros_like(table)
+        us = timed_us(lambda: nv.ops.grid_backward(x, dy_tmf, enc.spec, dtable=scratch, tmf=True))
+        b_s = 12 + 16 * 2 * 4 + 16 * 8 * 2 * 4  # xyz + dL/dy (32 fp32) + 16 levels x 8 corners x 2 fp32 scattered once
+        extras.append({"kernel": "k_grid_bwd_run<16> (main hash grid scatter, fp32 reductions)", "bound": "hbm", "launch_us": us, "achieved": b_s * N / us / 1e3,
+                       "peak": peak, "unit": "GB/s", "frac": b_s * N / us / 1e3 / peak, "algorithmic_bytes_per_sample": b_s})
+        fld = model.field
+        nets = {"mlp_base 32-64-16": (fld.mlp_base.mlp.spec, fld.mlp_base.mlp._flat_param_list(), 6144),
+                "mlp_head 63-64-64-3": (fld.mlp_head.spec, fld.mlp_head._flat_param_list(), 16640)}
+        for name, (spec, params, flop) in nets.items():
+            with torch.no_grad():
+                xin = torch.randn(N, spec.in_dim, device=dev)
+                x16 = nv.ops.cast_pad_f16(xin, spec)
+                wimg = nv.ops.tc_pack_weights(nv.ops._flat_of(params), spec)
+                y, saved = nv.ops.mlp_tc_forward(x16, wimg, spec, N, True)
+                dy = torch.randn_like(y)
+                dflat = torch.zeros(spec.n_params, dtype=torch.float32, device=dev)
+                us_f = timed_us(lambda: nv.ops.mlp_tc_forward(x16, wimg, spec, N, True))
+                us_b = timed_us(lambda: nv.ops.mlp_tc_backward(x16, wimg, saved, y, dy, spec, True, True, dflat, dy_absmax=8.0))
+            for tag, t_us, fl in (("fwd", us_f, flop), ("bwd (dgrad + wgrad)", us_b, 2 * flop)):
+                tf = fl * N / t_us / 1e6
+                extras.append({"kernel": f"k_mlp_tc_{tag}: {name}", "bound": "tensor", "launch_us": t_us, "achieved": tf, "peak": tpeak, "unit": "TFLOP/s",
+                               "frac": tf / tpeak, "flop_per_sample": fl, "peak_source": tpeak_src})
+        roofline["others"] = extras
+        del dy_tmf, scratch
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             v, sec = cpu_port_rays_per_s(1024, 2, 1, threads)
@@ -303,6 +352,34 @@ def run_ours(args):
                        "final_loss": loss_host}
         trainer.datamanager = None
 
+    # the reference's own proposal update schedule (NS/model_components/ray_samplers.py:596-610 with NeRF-VO's update_every = 5,
+    # warm-up 5000 of 8192 mapping iterations): past the warm-up only every 6th step sends gradients to the proposal networks; the other
+    # steps run neither their backward nor their Adam group.  `value` above is the every-step worst case.
+    ref_sched = None
+    if world == 1 and not args.no_schedule_leg:
+        trainer2 = MappingTrainer(model, num_rays=B, lr=1e-2, eps=1e-15, use_cuda_graph=not args.no_graph, proposal_update="reference")
+        trainer2.set_inputs(*dev_batches[0])
+        trainer2.capture(warmup=3)
+        trainer2.iteration, trainer2._ssu = 6000, 1
+        for s_ in range(12):
+            trainer2.set_inputs(*dev_batches[s_ % n_pool])
+            trainer2.train_step()
+        k = (args.steps + 5) // 6 * 6
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        first = trainer2.iteration
+        e0.record()
+        for s_ in range(k):
+            trainer2.set_inputs(*dev_batches[s_ % n_pool])
+            trainer2.train_step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_rs = e0.elapsed_time(e1)
+        ref_sched = {"value": B * k / (ms_rs * 1e-3), "unit": UNIT, "ms_per_step": ms_rs / k, "steps": k,
+                     "proposal_updates": int(trainer2.step_counts[1]) if len(trainer2.step_counts) > 1 else None,
+                     "note": "iterations 6000.. of NeRF-VO's 8192: proposal networks receive gradients every 6th step (reference schedule); inputs resident"}
+        del trainer2
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": rays_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -320,6 +397,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "exchange": exchange,
             "dataset_fed": dataset_fed,
+            "reference_schedule": ref_sched,
             "final_loss": final_loss,
         }
         print(json.dumps(line), flush=True)
@@ -337,6 +415,7 @@ def main():
     ap.add_argument("--rays", type=int, default=RAYS_PER_GPU, help="rays per GPU per step (default: configs[1]'s 4096; 65536 = configs[2]'s batch)")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-schedule-leg", action="store_true", help="skip the extra leg that follows the reference's proposal update schedule")
     ap.add_argument("--no-dataset-leg", action="store_true", help="skip the extra leg that feeds the step from a resident keyframe store (row f2)")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="N>1 gradient exchange: 'fused' = peer-memory reduce-scatter+Adam+all-gather kernel, 'nccl' = all-reduce + replicated Adam")
