@@ -388,6 +388,32 @@ def gen_frame_render(H=10, W=14, K=8, main_log2=12, prop_log2=10):
     np.savez_compressed(os.path.join(OUT, "frame_render_small.npz"), **_np(G))
 
 
+def gen_checkpoint(K=8, main_log2=12, prop_log2=10, B=64):
+    """A checkpoint dict exactly as NS/engine/trainer.py:436-447 writes it, from the UNMODIFIED reference model after two real optimizer
+    steps (one torch.optim.Adam per parameter group, NS/engine/optimizers.py:138-150): keys / shapes / dtypes as JSON, tensors as .pt."""
+    import json
+
+    model = rh.build_reference_model(main_log2=main_log2, prop_log2=prop_log2, num_images=K, seed=0)
+    groups = model.get_param_groups()
+    groups = {k: v for k, v in groups.items() if len(v) > 0}
+    opts = {k: torch.optim.Adam(v, lr=1e-2, eps=1e-15) for k, v in groups.items()}
+    rays, targets = O.synthetic_rays(B, num_images=K, seed=11)
+    for it in range(2):
+        for o in opts.values():
+            o.zero_grad(set_to_none=True)
+        out, ld, jit, _ = rh.reference_step(model, rays, targets, step=it)
+        for o in opts.values():
+            o.step()
+    ckpt = {"step": 1, "pipeline": {"_model." + k: v.detach().clone() for k, v in model.state_dict().items()},
+            "optimizers": {k: o.state_dict() for k, o in opts.items()}, "schedulers": {}, "scalers": {}}
+    torch.save(ckpt, os.path.join(OUT, "reference_checkpoint_small.pt"))
+    meta = {"keys": [[k, list(v.shape), str(v.dtype)] for k, v in ckpt["pipeline"].items()],
+            "groups": {k: [len(o.state_dict()["param_groups"][0]["params"]), sorted(int(i) for i in o.state_dict()["state"].keys())] for k, o in opts.items()}}
+    with open(os.path.join(OUT, "reference_checkpoint_keys.json"), "w") as f:
+        json.dump(meta, f, indent=0)
+    print("checkpoint:", len(meta["keys"]), "keys,", {k: v[0] for k, v in meta["groups"].items()})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_hash_indices()
@@ -398,5 +424,6 @@ if __name__ == "__main__":
     gen_model_step()
     gen_batch_prologue()
     gen_frame_render()
+    gen_checkpoint()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
