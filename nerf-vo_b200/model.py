@@ -157,7 +157,7 @@ class NerfactoModel(nn.Module):
                 if getattr(self, "_leaf_renders", False) and ops.leaf_streams.enabled:
                     # nothing inside the step consumes the proposal depth maps: under the trainer (which joins the side streams before
                     # the optimizer) they are rendered next to the loss kernels instead of in front of them
-                    with ops.leaf_streams.fork(weights_list[i], ray_samples_list[i]):
+                    with ops.leaf_streams.fork(weights_list[i], ray_samples_list[i], aux=True):
                         outputs[f"prop_depth_{i}"] = render_all(weights_list[i].detach(), ray_samples_list[i])[3]
                 else:
                     outputs[f"prop_depth_{i}"] = render_all(weights_list[i].detach(), ray_samples_list[i])[3]
@@ -246,7 +246,7 @@ class ExtendedNerfactoModel(DepthNerfactoModel):
             loss["normal_loss"] = self.config.normal_loss_mult * metrics_dict["normal_loss"]
         return loss
 
-    def get_train_loss_fused(self, ray_bundle: RayBundle, batch, jitters=None):
+    def get_train_loss_fused(self, ray_bundle: RayBundle, batch, jitters=None, eager_grads: bool = False):
         """Same step as get_train_loss_dict with every loss evaluated by ONE autograd node (ops.fused_step_losses): returns
         (outputs, total_loss, terms, weights): `total_loss` carries the graph; terms[name] * weights[name] are the entries
         get_loss_dict would produce (`terms` = ONE detached device vector viewed per name, so logging costs no kernels unless
@@ -264,7 +264,8 @@ class ExtendedNerfactoModel(DepthNerfactoModel):
         total, terms = ops.fused_step_losses(
             wl, [r.sdist() for r in rl], [r.frustums.intervals() for r in rl], outputs["rgb"], batch["image"],
             normals_img=outputs["normals"] if use_n else None, normal_gt=batch["normal_image"] if use_n else None,
-            depth_gt=batch["depth_image"] if use_d else None, directions_norm=dnorm if use_d else None, sigma=c.depth_sigma, mults=mults)
+            depth_gt=batch["depth_image"] if use_d else None, directions_norm=dnorm if use_d else None, sigma=c.depth_sigma, mults=mults,
+            eager_grads=eager_grads)
         names = ("rgb_loss", "interlevel_loss", "distortion_loss", "depth_loss", "normal_loss")
         # depth: `terms` holds the SUM over the weight sets, its weight the multiplier / number of sets (depth_nerfacto.py:93-103)
         return outputs, total, {n: terms[i] for i, n in enumerate(names) if mults[i] != 0.0}, {n: mults[i] for i, n in enumerate(names) if mults[i] != 0.0}

@@ -41,17 +41,24 @@ class _LeafStreams:
         # one stream per proposal level: the level's forward (density + weights) is issued there, so autograd runs the level's
         # BACKWARD there too, ordered only after the gradients it consumes — i.e. concurrently with the main field's backward
         self.level_streams = [torch.cuda.Stream() for _ in range(n_levels)]
+        # outputs nothing inside the step consumes (proposal depth maps): their own streams, so they never queue in front of a loss kernel
+        self.aux_streams = [torch.cuda.Stream() for _ in range(2)]
+        self.next_aux = 0
         self.enabled = True
 
     def on_level_stream(self) -> bool:
         cur = torch.cuda.current_stream()
         return any(cur == st for st in getattr(self, "level_streams", []))
 
-    def fork(self, *keepalive):
+    def fork(self, *keepalive, aux: bool = False):
         """Returns a context manager running its body on the next side stream, ordered after the current stream."""
         cur = torch.cuda.current_stream()
-        st = self.streams[self.next % len(self.streams)]
-        self.next += 1
+        if aux:
+            st = self.aux_streams[self.next_aux % len(self.aux_streams)]
+            self.next_aux += 1
+        else:
+            st = self.streams[self.next % len(self.streams)]
+            self.next += 1
         st.wait_stream(cur)
         if st not in self.used:
             self.used.append(st)
@@ -65,6 +72,7 @@ class _LeafStreams:
         self.used.clear()
         self.refs.clear()
         self.next = 0
+        self.next_aux = 0
 
 
 leaf_streams = _LeafStreams()
@@ -919,21 +927,46 @@ class _FusedStepLosses(torch.autograd.Function):
             d_n = torch.empty_like(normals_img)
         wf, cf = ws[2], spec["sdist"][2]
 
+        # eager_grads (the trainer's promise that `total` is differentiated with grad_output == 1, i.e. total.backward()): the gradient
+        # kernels are launched right behind their forward twins, on the same per-level streams, instead of as a second wave after the
+        # autograd engine has turned around — they only read the weights, so nothing orders them behind the scalar total.
+        eager = bool(spec.get("eager_grads")) and any(ctx.needs_input_grad[:3])
+        dws = None
+        if eager:
+            sizes = [w.shape[1] for w in ws]
+            flat = torch.zeros(B * sum(sizes), dtype=torch.float32, device=dev)
+            dws, off = [], 0
+            for n_s in sizes:
+                dws.append(flat[off:off + B * n_s].view(B, n_s))
+                off += B * n_s
+            one = _cached_linspace(("unit_grad",), lambda: torch.ones(1, dtype=torch.float32), dev)
+        m = spec["mults"]
+
         def level(i):  # everything that reads weight set i: the kernels are tiny (4096 warps), so the three levels run side by side
             if i < 2:
                 call("nvo_interlevel_loss_forward", B, wf.shape[1], ws[i].shape[1], wf, cf, ws[i], spec["sdist"][i], terms[1:], None, None)
+                if eager:
+                    call("nvo_interlevel_loss_backward", B, wf.shape[1], sizes[i], wf, cf, ws[i], spec["sdist"][i], one, m[1], dws[i])
             else:
                 call("nvo_mse_loss", rgb.numel(), rgb, spec["rgb_gt"], spec["mults"][0], terms, d_rgb)
                 call("nvo_distortion_loss_forward", B, wf.shape[1], wf, cf, terms[2:])
+                if eager:
+                    call("nvo_distortion_loss_backward", B, wf.shape[1], wf, cf, one, m[2], dws[2])
                 if d_n is not None:
                     call("nvo_normal_loss", B, normals_img, spec["normal_gt"], spec["mults"][4], terms[4:], d_n)
             if spec["depth_gt"] is not None:
                 s, e, stride = spec["iv"][i].triple()
                 call("nvo_depth_loss_forward", B, ws[i].shape[1], ws[i], s, e, stride, spec["depth_gt"], spec["dnorm"], spec["sigma"], terms[3:])
+                if eager:
+                    call("nvo_depth_loss_backward", B, sizes[i], ws[i], s, e, stride, spec["depth_gt"], spec["dnorm"], spec["sigma"], one, m[3], dws[i])
 
         _run_levels(level)
         total = torch.dot(terms, spec["mults_dev"])
-        ctx.save_for_backward(*ws, d_rgb, d_n)
+        if eager:
+            ctx.save_for_backward(dws[0], dws[1], dws[2], d_rgb, d_n)
+        else:
+            ctx.save_for_backward(*ws, d_rgb, d_n)
+        ctx.eager = eager
         ctx.spec = spec
         ctx.mark_non_differentiable(terms)
         return total, terms
@@ -942,6 +975,9 @@ class _FusedStepLosses(torch.autograd.Function):
     def backward(ctx, g, _g_terms):
         w0, w1, w2, d_rgb, d_n = ctx.saved_tensors
         ws, spec = [w0, w1, w2], ctx.spec
+        if ctx.eager:  # gradients were produced next to the forward, for grad_output == 1
+            shp = spec["w_shapes"]
+            return (w0.view(shp[0]), w1.view(shp[1]), w2.view(shp[2]), d_rgb, d_n, None)
         B = w0.shape[0]
         sizes = [w.shape[1] for w in ws]
         g = g.reshape(1).float().contiguous()
@@ -968,8 +1004,9 @@ class _FusedStepLosses(torch.autograd.Function):
 
 
 def fused_step_losses(weights_list, sdist_list, iv_list, rgb, rgb_gt, normals_img=None, normal_gt=None, depth_gt=None, directions_norm=None,
-                      sigma: float = 0.001, mults=(1.0, 1.0, 0.002, 0.001 / 3, 5e-6)):
-    """mults = multipliers of [rgb, interlevel, distortion, depth (already divided by the number of levels), normal]."""
+                      sigma: float = 0.001, mults=(1.0, 1.0, 0.002, 0.001 / 3, 5e-6), eager_grads: bool = False):
+    """mults = multipliers of [rgb, interlevel, distortion, depth (already divided by the number of levels), normal].
+    eager_grads=True: the caller will call total.backward() (grad_output exactly 1): gradients are computed alongside the forward."""
     dev = rgb.device
     f = lambda t, shape: None if t is None else check(t.reshape(shape).contiguous(), "target", torch.float32)
     B = rgb.shape[0]
@@ -977,7 +1014,7 @@ def fused_step_losses(weights_list, sdist_list, iv_list, rgb, rgb_gt, normals_im
     mults_dev = _cached_linspace(key, lambda: torch.tensor([float(x) for x in mults], dtype=torch.float32), dev)
     spec = {"sdist": [check(s.contiguous(), "sdist", torch.float32) for s in sdist_list], "iv": list(iv_list), "rgb_gt": f(rgb_gt, (B, 3)),
             "normal_gt": f(normal_gt, (B, 3)), "depth_gt": f(depth_gt, (B,)), "dnorm": f(directions_norm, (B,)), "sigma": float(sigma),
-            "mults": [float(x) for x in mults], "mults_dev": mults_dev, "w_shapes": [tuple(w.shape) for w in weights_list]}
+            "mults": [float(x) for x in mults], "mults_dev": mults_dev, "w_shapes": [tuple(w.shape) for w in weights_list], "eager_grads": bool(eager_grads)}
     return _FusedStepLosses.apply(weights_list[0], weights_list[1], weights_list[2], rgb, normals_img, spec)
 
 

@@ -190,7 +190,8 @@ class MappingTrainer:
                 batch["normal_image"] = i["normal"]
         self.model._leaf_renders = side  # proposal depth maps rendered on side streams (joined below), only inside this step
         try:
-            _, total, terms, weights = self.model.get_train_loss_fused(bundle, batch, [i["jitter0"], i["jitter1"], i["jitter2"]])
+            # eager_grads: this step differentiates `total` with total.backward() below, i.e. with grad_output == 1
+            _, total, terms, weights = self.model.get_train_loss_fused(bundle, batch, [i["jitter0"], i["jitter1"], i["jitter2"]], eager_grads=True)
         finally:
             self.model._leaf_renders = False
         if side:
