@@ -116,7 +116,8 @@ int nvo_mlp_backward(const nvo_mlp_desc* d, void* stream, int64_t n, const float
  *   saved   opaque forward context of nvo_mlp_tc_saved_bytes(d, n) bytes (fp16 hidden activations, TMH layout);
  *   scratch one float the backward uses for its device-side gradient scale (max|dy| -> power-of-two loss scale, the
  *           device analogue of tinycudann's loss_scale, modules.py:174); dy_absmax_hint > 0 supplies max|dy| from the
- *           caller instead (e.g. 1 for a one-hot seed) and skips the reduction pass;
+ *           caller instead (e.g. 1 for a one-hot seed) and skips the reduction pass; dy_absmax_hint < 0: `scratch` already holds
+ *           max|dy| as a float bit pattern, written by the kernel that produced dy (nvo_field_assemble_backward);
  *   y, dy, dparams fp32 row-major exactly as the SIMT entry points;
  *   dx      fp32 in TMF layout ("tile-major float"): [ceil(n/128)][in_dim][128], i.e. column-major inside each 128-row tile, so
  *           the kernel's row-per-thread epilogue stores coalesced and the per-sample consumers (nvo_grid_backward with
@@ -191,8 +192,11 @@ int nvo_field_assemble_forward(void* stream, int64_t B, int32_t S, const float* 
                                const int64_t* cam_idx, const float* embedding, int32_t f16_padded, float* density, void* head_in, void* pn_in);
 /* backward: dh[n,16] (overwritten) and dembedding[K,32] (accumulate, nullable) from ddensity[n] (nullable), dhead_in[n,63], dpn_in[n,27] (nullable) */
 /* tmf != 0: dhead_in / dpn_in are in the TMF layout nvo_mlp_tc_backward writes ([tile][63 | 27][128]) instead of row-major */
+/* dh_absmax (nullable, one float, zero-filled by the caller): receives max|dh| (atomic max on the bit pattern), which nvo_mlp_tc_backward
+ * accepts in `scratch` with dy_absmax_hint < 0 — the gradient-scale reduction pass over dh then disappears from the backward chain */
 int nvo_field_assemble_backward(void* stream, int64_t B, int32_t S, const float* h, const float* selector, const int64_t* cam_idx,
-                                const float* ddensity, const float* dhead_in, const float* dpn_in, int32_t tmf, float* dh, float* dembedding);
+                                const float* ddensity, const float* dhead_in, const float* dpn_in, int32_t tmf, float* dh, float* dembedding,
+                                float* dh_absmax);
 
 /* ---------------------------------------------------------------------------------------------
  * Per-ray operators.  B rays, S samples per ray.  Sample intervals are stored as bin EDGES:

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(128)
 __global__ void __launch_bounds__(256)
     k_assemble_bwd(int64_t B, int S, const float* __restrict__ h, const float* __restrict__ selector, const int64_t* __restrict__ cam_idx,
                    const float* __restrict__ ddensity, const float* __restrict__ dhead_in, const float* __restrict__ dpn_in, int tmf,
-                   float* __restrict__ dh, float* __restrict__ dembedding) {
+                   float* __restrict__ dh, float* __restrict__ dembedding, int* __restrict__ dh_absmax_bits) {
     // element (sample t, column c) of a [n, K] gradient: row-major, or TMF [tile][K][128] (mlp_tc.cu's dx layout)
     auto at = [tmf](const float* g, int K, int64_t t, int c) { return tmf ? __ldg(g + (((t >> 7) * K + c) << 7) + (t & 127)) : __ldg(g + K * t + c); };
     // one warp per ray: lanes stride over the ray's samples (every global access of the warp is a contiguous run in the tile-major
@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(256)
     float e[32];
 #pragma unroll
     for (int k = 0; k < 32; ++k) e[k] = 0.f;
+    float amax = 0.f;  // max |dh| of this lane's samples: the consumer (tensor-core MLP backward) derives its gradient scale from it
     for (int s0 = 0; s0 < S; s0 += 32) {
         const int s = s0 + lane;
         if (s < S) {
@@ -244,11 +245,21 @@ __global__ void __launch_bounds__(256)
             }
 #pragma unroll
             for (int k = 0; k < 16; k += 4) reinterpret_cast<float4*>(dh + 16 * t)[k >> 2] = make_float4(g[k], g[k + 1], g[k + 2], g[k + 3]);
+            if (dh_absmax_bits) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) amax = fmaxf(amax, fabsf(g[k]));
+            }
             if (want_emb) {
 #pragma unroll
                 for (int k = 0; k < 32; ++k) e[k] += at(dhead_in, HEAD_IN, t, 16 + GEO + k);
             }
         }
+    }
+    if (dh_absmax_bits) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        // non-negative floats order like their bit patterns (k_absmax_scale's convention); NaN / Inf are left to the consumer's guard
+        if (lane == 0 && amax > 0.f) atomicMax(dh_absmax_bits, __float_as_int(amax));
     }
     if (want_emb) {
 #pragma unroll
@@ -340,12 +351,14 @@ extern "C" int nvo_field_assemble_forward(void* stream, int64_t B, int32_t S, co
     return 0;
 }
 extern "C" int nvo_field_assemble_backward(void* stream, int64_t B, int32_t S, const float* h, const float* selector, const int64_t* cam_idx,
-                                           const float* ddensity, const float* dhead_in, const float* dpn_in, int32_t tmf, float* dh, float* dembedding) {
+                                           const float* ddensity, const float* dhead_in, const float* dpn_in, int32_t tmf, float* dh, float* dembedding,
+                                           float* dh_absmax) {
     NVO_CHECK(B >= 0 && S >= 1, "field_assemble_backward: bad shape");
     if (B == 0) return 0;
     NVO_CHECK(h && dhead_in && dh, "field_assemble_backward: null pointer");
     NVO_CHECK(!ddensity || selector, "field_assemble_backward: selector required for ddensity");
-    k_assemble_bwd<<<nvo_blocks(B * 32, 256), 256, 0, (cudaStream_t)stream>>>(B, S, h, selector, cam_idx, ddensity, dhead_in, dpn_in, tmf, dh, dembedding);
+    k_assemble_bwd<<<nvo_blocks(B * 32, 256), 256, 0, (cudaStream_t)stream>>>(B, S, h, selector, cam_idx, ddensity, dhead_in, dpn_in, tmf, dh, dembedding,
+                                                                              reinterpret_cast<int*>(dh_absmax));
     NVO_CUDA_LAUNCH_CHECK("field_assemble_backward");
     return 0;
 }

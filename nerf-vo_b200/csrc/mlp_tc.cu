@@ -862,7 +862,7 @@ extern "C" int nvo_mlp_tc_backward(const nvo_mlp_desc* d, void* stream, int64_t 
     NVO_CHECK(p.acts[p.n_layers - 1] == NVO_ACT_NONE || y, "mlp_tc_backward: y required for an output activation");
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaSuccess;
-    if (!(dy_absmax_hint > 0.f)) {  // the caller does not know max|dy|: one reduction pass over dy
+    if (dy_absmax_hint == 0.f) {  // the caller does not know max|dy| (> 0: given; < 0: already in scratch): one reduction pass over dy
         e = cudaMemsetAsync(scratch, 0, sizeof(float), st);
         NVO_CHECK(e == cudaSuccess, "mlp_tc_backward: memset: %s", cudaGetErrorString(e));
         const int64_t count = n * p.dims[p.n_layers - 1];

@@ -40,7 +40,11 @@ class _LeafStreams:
         self.streams = [torch.cuda.Stream() for _ in range(n)]
         # one stream per proposal level: the level's forward (density + weights) is issued there, so autograd runs the level's
         # BACKWARD there too, ordered only after the gradients it consumes — i.e. concurrently with the main field's backward
-        self.level_streams = [torch.cuda.Stream() for _ in range(n_levels)]
+        if os.environ.get("NVO_ONE_LEVEL_STREAM", "0") == "1":
+            one = torch.cuda.Stream(priority=int(os.environ.get("NVO_LEVEL_PRIORITY", "0")))
+            self.level_streams = [one for _ in range(n_levels)]
+        else:
+            self.level_streams = [torch.cuda.Stream(priority=int(os.environ.get("NVO_LEVEL_PRIORITY", "0"))) for _ in range(n_levels)]
         # outputs nothing inside the step consumes (proposal depth maps): their own streams, so they never queue in front of a loss kernel
         self.aux_streams = [torch.cuda.Stream() for _ in range(2)]
         self.next_aux = 0
@@ -554,7 +558,7 @@ class _FieldAssemble(torch.autograd.Function):
                 demb = dhead_in[:, 31:].sum(0).reshape(ctx.emb_shape)
         c = lambda t: None if t is None else t.contiguous()
         call("nvo_field_assemble_backward", ctx.B, ctx.S, h, selector, cam_idx, c(ddensity), dhead_in.contiguous(), c(dpn_in), 0, dh,
-             demb if cam_idx is not None else None)
+             demb if cam_idx is not None else None, None)
         if demb is ctx.main_grad:
             demb = None
         return dh, demb, None, None, None, None, None, None, None
@@ -1123,6 +1127,11 @@ def mlp_tc_forward(x16, wimage, spec: MlpSpec, n: int, save: bool, row_mask=None
     return y, saved
 
 
+# max|dy| handed from the kernel that produced a gradient to the tensor-core backward that consumes it: (data_ptr, numel) -> device float
+# (bit pattern).  One entry at most, written by _FieldHeadsTC.backward and popped by the next mlp_tc_backward on that very tensor.
+_dy_absmax: dict = {}
+
+
 def mlp_tc_backward(x16, wimage, saved, y, dy, spec: MlpSpec, need_dx: bool, need_dparams: bool, dflat=None, row_mask=None, dy_absmax: float = 0.0):
     n = dy.shape[0]
     check(dy, "mlp dy", torch.float32, (n, spec.out_dim))
@@ -1130,7 +1139,11 @@ def mlp_tc_backward(x16, wimage, saved, y, dy, spec: MlpSpec, need_dx: bool, nee
     dx = torch.empty(tmh_numel(n, spec.in_dim), dtype=torch.float32, device=x16.device) if need_dx else None
     if need_dparams and dflat is None:
         dflat = torch.zeros(spec.n_params, dtype=torch.float32, device=x16.device)
-    scratch = torch.empty(1, dtype=torch.float32, device=x16.device)
+    scratch = _dy_absmax.pop((dy.data_ptr(), dy.numel()), None) if dy_absmax == 0.0 else None
+    if scratch is not None:
+        dy_absmax = -1.0  # `scratch` already holds max|dy|
+    else:
+        scratch = torch.empty(1, dtype=torch.float32, device=x16.device)
     call("nvo_mlp_tc_backward", spec.desc, n, x16, wimage, saved, y, row_mask, dy, float(dy_absmax), scratch, dx, dflat if need_dparams else None)
     return dx, dflat
 
@@ -1301,7 +1314,11 @@ class _FieldHeadsTC(torch.autograd.Function):
                 demb = torch.zeros(ctx.emb_shape, dtype=torch.float32, device=dev)
             else:
                 demb = tmf_to_rows(dhead_in, n, 63)[:, 31:].sum(0).reshape(ctx.emb_shape)
-        call("nvo_field_assemble_backward", ctx.B, ctx.S, h, selector, cam_idx, c(ddensity), dhead_in, dpn_in, 1, dh, demb if cam_idx is not None else None)
+        # max|dh| is reduced inside this kernel and handed to the base network's backward (its gradient-scale pass disappears)
+        amax = torch.zeros(1, dtype=torch.float32, device=dev)
+        call("nvo_field_assemble_backward", ctx.B, ctx.S, h, selector, cam_idx, c(ddensity), dhead_in, dpn_in, 1, dh, demb if cam_idx is not None else None, amax)
+        _dy_absmax.clear()
+        _dy_absmax[(dh.data_ptr(), dh.numel())] = amax
         if demb is ctx.emb_main_grad:
             demb = None
         head_grads = [None] * ctx.n_head

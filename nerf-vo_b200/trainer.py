@@ -239,12 +239,21 @@ class MappingTrainer:
 
     def _optimizer(self, updated: bool = True) -> None:
         """Steps every group that has not been stepped inside the backward; the proposal group only when it received gradients."""
-        for gi, (name, _, _) in enumerate(self.groups):
+        side = self.device.type == "cuda" and ops.leaf_streams.enabled and self.peer is None
+        forked = False
+        for gi, (name, _, _) in reversed(list(enumerate(self.groups))):  # the small group first: it slips in next to the big one's CTAs
             if gi == 0 and self._fields_done:
                 continue
             if name == "proposal_networks" and not updated:
                 continue
-            self._optimizer_group(gi)
+            if side and gi > 0:
+                with ops.leaf_streams.fork():  # disjoint ranges of the flat buffers: the small group's Adam runs next to the big one's
+                    self._optimizer_group(gi)
+                forked = True
+            else:
+                self._optimizer_group(gi)
+        if forked:
+            ops.leaf_streams.join()
         self._fields_done = False
 
     def _exchange(self) -> None:
