@@ -266,6 +266,17 @@ class NerfactoField(Field):
                 emb = torch.zeros(self.appearance_embedding_dim, device=dirs.device)
         out: Dict[FieldHeadNames, torch.Tensor] = {}
         if self.precision == "fp16":
+            import os
+
+            normals = side_n = None
+            if compute_normals and ops.leaf_streams.enabled and x.is_cuda and os.environ.get("NVO_FIELD_BRANCHES", "1") == "1":
+                # density-gradient normals (base network's input-gradient chain + saved-Jacobian product) depend on the base network only:
+                # they run on their own stream next to the colour / predicted-normals heads and are joined before the renderer reads them
+                main = torch.cuda.current_stream()
+                side_n = ops.leaf_streams.branch_streams[0]
+                side_n.wait_stream(main)
+                with torch.cuda.stream(side_n):
+                    normals = self.get_normals()
             self.mlp_head._repack()
             pn_spec, pn_params = None, ()
             if self.use_pred_normals:
@@ -278,7 +289,11 @@ class NerfactoField(Field):
                 out[FieldHeadNames.PRED_NORMALS] = pn.view(B, S, 3)
             out[FieldHeadNames.RGB] = rgb.view(B, S, 3)
             out[FieldHeadNames.DENSITY] = density.view(B, S, 1)
-            if compute_normals:
+            if side_n is not None:
+                main.wait_stream(side_n)
+                normals.record_stream(main)
+                out[FieldHeadNames.NORMALS] = normals
+            elif compute_normals:
                 out[FieldHeadNames.NORMALS] = self.get_normals()
             return out
         density, head_in, pn_in = ops.field_assemble(h, emb, sel, dirs, positions.reshape(-1, 3), cam, B, S, self.use_pred_normals)

@@ -48,6 +48,9 @@ class _LeafStreams:
         # outputs nothing inside the step consumes (proposal depth maps): their own streams, so they never queue in front of a loss kernel
         self.aux_streams = [torch.cuda.Stream() for _ in range(2)]
         self.next_aux = 0
+        # independent branches of the field's forward (density-gradient normals, predicted-normals network) next to the colour head:
+        # each is a chain of latency-bound launches that leaves most of the SMs idle
+        self.branch_streams = [torch.cuda.Stream(priority=-1) for _ in range(2)]
         self.enabled = True
 
     def on_level_stream(self) -> bool:
@@ -1276,14 +1279,32 @@ class _FieldHeadsTC(torch.autograd.Function):
         pn_in = torch.empty(tmh_numel(n, 32), dtype=torch.float16, device=dev) if want_pn else None
         call("nvo_field_assemble_forward", B, S, h, selector, directions, positions, cam_idx, embedding, 1, density, head_in, pn_in)
         need = any(ctx.needs_input_grad)
-        head_flat = tc_pack_weights(_flat_of(head_params), head_spec)
-        rgb, head_saved = mlp_tc_forward(head_in, head_flat, head_spec, n, need)
         pn_flat = pn_saved = pn_raw = pn = None
-        if want_pn:
-            pn_flat = tc_pack_weights(_flat_of(pn_params), pn_spec)
-            pn_raw, pn_saved = mlp_tc_forward(pn_in, pn_flat, pn_spec, n, need)
-            pn = torch.empty_like(pn_raw)
-            call("nvo_normalize3_forward", n, pn_raw, 1.0, 1e-12, pn)
+
+        def pn_branch():
+            flat = tc_pack_weights(_flat_of(pn_params), pn_spec)
+            raw, sv = mlp_tc_forward(pn_in, flat, pn_spec, n, need)
+            out = torch.empty_like(raw)
+            call("nvo_normalize3_forward", n, raw, 1.0, 1e-12, out)
+            return flat, raw, sv, out
+
+        head_flat = tc_pack_weights(_flat_of(head_params), head_spec)
+        if want_pn and leaf_streams.enabled and os.environ.get("NVO_FIELD_BRANCHES", "1") == "1":
+            # the predicted-normals network only shares its input assembly with the colour head: issue it on its own stream
+            main = torch.cuda.current_stream()
+            side = leaf_streams.branch_streams[1]
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                pn_flat, pn_raw, pn_saved, pn = pn_branch()
+            rgb, head_saved = mlp_tc_forward(head_in, head_flat, head_spec, n, need)
+            main.wait_stream(side)
+            for t in (pn_flat, pn_raw, pn_saved, pn):
+                if t is not None:
+                    t.record_stream(main)  # allocated on the side stream, consumed (render, backward) on the main one
+        else:
+            rgb, head_saved = mlp_tc_forward(head_in, head_flat, head_spec, n, need)
+            if want_pn:
+                pn_flat, pn_raw, pn_saved, pn = pn_branch()
         ctx.save_for_backward(h, selector, cam_idx, head_in, head_flat, head_saved, rgb, pn_in, pn_flat, pn_saved, pn_raw)
         ctx.B, ctx.S, ctx.emb_shape, ctx.head_spec, ctx.pn_spec = B, S, embedding.shape, head_spec, pn_spec
         ctx.n_head, ctx.n_pn = len(head_params), len(pn_params)
