@@ -10,7 +10,8 @@ MonoSDF normal losses, predicted normals on — synthetic Replica-shaped rays, r
 
 Prints ONE JSON line (rank 0).  `value` = rays/s with inputs resident in HBM, timed with CUDA events over K CUDA-graph replays
 of the whole step; `e2e` = the same through the public trainer API from pinned HOST buffers (H2D of the batch + D2H of the loss
-inside the timed region); `roofline` = the main hash-grid forward kernel against the measured HBM peak; `cpu_baseline` = the CPU
+inside the timed region); `roofline` = the hash-table scatter kernel (largest share of the step) against the measured HBM peak, other
+kernels under `roofline.others`; `cpu_baseline` = the CPU
 oracle port timed on this box's host cores on a bounded sample (N=1 only).  `--impl reference` times the reference's own CPU
 algorithm (oracle port; the Python reference cannot travel to the GPU box) on all host threads.
 """
@@ -27,10 +28,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the same kernel/shape
-# (profiles/r01_ncu_full_step_kernels.md: 48.92 MB read + 7.37 MB written — far below the algorithmic bytes because the 64 MiB table
-# is served from the 126 MB L2)
-RECORDED_TRAFFIC = {"k_grid_fwd_tmh": 56.29e6}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the same kernels / shapes
+# (profiles/r01_ncu_step_kernels_s10.md: scatter launches 74.8 + 23.9 + 58.0 MB -> 52.2 MB on average; profiles/r01_ncu_full_step_kernels.md:
+# grid forward 48.92 MB read + 7.37 MB written; with the saved Jacobian 49.1 + 24.7 MB) — far below the algorithmic bytes because the tables are served from the 126 MB L2
+RECORDED_TRAFFIC = {"k_grid_fwd_tmh": 56.29e6, "k_grid_bwd_run": 52.2e6, "k_grid_fwd_tmh_jac": 73.8e6}
 
 METRIC = "nerf_mapping_train_rays_per_s"
 UNIT = "rays/s"
@@ -241,35 +242,18 @@ def run_ours(args):
 
     roofline = cpu = None
     if rank == 0:
-        # roofline kernel: the main hash-grid forward of this step (16 levels, fp32 table of 2^19 rows, fp16 TMH output feeding the
-        # tensor-core MLP) on the step's final-level sample count, L2 flushed between launches, CUDA events on the launching stream
+        # Roofline kernel = the one with the largest share of the step in the ncu launch list (profiles/r01_launches_s10.md: 19 %):
+        # k_grid_bwd_run<16>, the hash-table scatter, launched three times per step (main 16-level grid, two 5-level proposal grids).
+        # Each launch is repeated here on the LAST TIMED STEP's own sample positions (contracted, normalised), L2 flushed between launches,
+        # CUDA events on the launching stream.  achieved = algorithmic bytes of the three launches / their summed duration.
         peak, peak_src = load_peaks()
         N = B * 48
         enc = model.field.mlp_base.encoder
-        # the launch is repeated on the LAST TIMED STEP's own sample positions (contracted, normalised; 48 PDF-resampled samples per ray)
         x = model.field._cache["x"].detach().clone()
         assert x.shape == (N, 3)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
         table = enc.hash_table.detach()
-        evs = []
-        for i in range(3 + 20):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            nv.ops.grid_forward(x, table, enc.spec, "tmh")
-            e1.record()
-            evs.append((e0, e1))
-        torch.cuda.synchronize()
-        t_ms = sum(a.elapsed_time(b) for a, b in evs[3:]) / 20
-        per_sample = 12 + 16 * 8 * 2 * 4 + 16 * 2 * 2  # xyz + 16 levels x 8 corners x 2 fp32 features + 32 fp16 outputs
-        alg_bytes = per_sample * N
-        ach = alg_bytes / (t_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_grid_fwd_tmh<float2> (main hash grid forward, fp32 table -> fp16 TMH tiles; L2 flushed between launches)",
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": RECORDED_TRAFFIC.get("k_grid_fwd_tmh"),
-                    "peak_source": peak_src, "launch_us": t_ms * 1e3, "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_per_sample": per_sample,
-                    "samples_per_launch": N, "inputs": "sample positions of the last timed step"}
-        # secondary kernels, timed the same way (L2 flushed, CUDA events): the main-table scatter against HBM, the three field networks'
-        # tensor-core kernels against the dense fp16/bf16 tensor peak (SURVEY 8d FLOP counts, unpadded)
+
         def timed_us(fn, reps=20):
             ev = []
             for i in range(3 + reps):
@@ -280,14 +264,49 @@ def run_ours(args):
             torch.cuda.synchronize()
             return sum(a.elapsed_time(b) for a, b in ev[3:]) / reps * 1e3
 
+        # sample positions of the two proposal levels: the sampler run once more on the last batch (no gradients)
+        with torch.no_grad():
+            model.proposal_sampler._steps_since_update = 0
+            bundle = model.set_nears_and_fars(trainer._bundle())
+            _, _, rs_list = model.proposal_sampler(bundle, density_fns=model.density_fns, jitters=[trainer.inputs[f"jitter{k}"] for k in range(3)])
+            xs = [nv.ops.contract_normalize(rs.frustums.get_positions().reshape(-1, 3).contiguous())[0] for rs in rs_list[:2]]
+        torch.cuda.synchronize()
+        launches = [("main grid 16 x 2^19", x, enc.spec, torch.zeros_like(table))]
+        for i, pn in enumerate(model.proposal_networks):
+            launches.append((f"proposal grid {i} 5 x 2^17", xs[i], pn.encoding.spec, torch.zeros_like(pn.encoding.hash_table.detach())))
+        parts, tot_bytes, tot_us = [], 0, 0.0
+        for name, xl, spec, scratch in launches:
+            n_l, L_l = xl.shape[0], spec.n_levels
+            dy_l = torch.randn(nv.ops.tmh_numel(n_l, spec.out_dim), device=dev)
+            us = timed_us(lambda: nv.ops.grid_backward(xl, dy_l, spec, dtable=scratch, tmf=True))
+            b_s = 12 + L_l * 2 * 4 + L_l * 8 * 2 * 4  # xyz + dL/dy (2L fp32) + L levels x 8 corners x 2 fp32 scattered once
+            parts.append({"launch": name, "samples": n_l, "launch_us": us, "algorithmic_bytes_per_sample": b_s, "achieved_GBs": b_s * n_l / us / 1e3})
+            tot_bytes += b_s * n_l
+            tot_us += us
+            del dy_l
+        ach = tot_bytes / tot_us / 1e3
+        roofline = {"bound": "hbm", "kernel": "k_grid_bwd_run<16> (hash-table scatter: fp32 red.global.add, 16 consecutive samples of a ray per thread and level; "
+                                               "3 launches per step, L2 flushed between launches)",
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": RECORDED_TRAFFIC.get("k_grid_bwd_run"),
+                    "peak_source": peak_src, "launch_us": tot_us / len(parts), "algorithmic_bytes_per_launch": tot_bytes / len(parts),
+                    "launches_per_step": len(parts), "per_launch": parts, "inputs": "sample positions of the last timed step (all three levels)"}
+        del launches
+        # secondary kernels, timed the same way: the main grid's forward (+ saved Jacobian) against HBM, the field networks' tensor-core kernels
+        # against the dense fp16/bf16 tensor peak (SURVEY 8d FLOP counts, unpadded), Adam against HBM
         tpeak, tpeak_src = load_tensor_peak()
         extras = []
-        dy_tmf = torch.randn(nv.ops.tmh_numel(N, enc.spec.out_dim), device=dev)
-        scratch = torch.zeros_like(table)
-        us = timed_us(lambda: nv.ops.grid_backward(x, dy_tmf, enc.spec, dtable=scratch, tmf=True))
-        b_s = 12 + 16 * 2 * 4 + 16 * 8 * 2 * 4  # xyz + dL/dy (32 fp32) + 16 levels x 8 corners x 2 fp32 scattered once
-        extras.append({"kernel": "k_grid_bwd_run<16> (main hash grid scatter, fp32 reductions)", "bound": "hbm", "launch_us": us, "achieved": b_s * N / us / 1e3,
-                       "peak": peak, "unit": "GB/s", "frac": b_s * N / us / 1e3 / peak, "algorithmic_bytes_per_sample": b_s})
+        us = timed_us(lambda: nv.ops.grid_forward_jac(x, table, enc.spec))
+        b_s = 12 + 16 * 8 * 2 * 4 + 16 * 2 * 2 + 3 * 16 * 2 * 2  # xyz + 16 x 8 corner rows (fp32 pairs) + 32 fp16 features + 96 fp16 derivatives
+        extras.append({"kernel": "k_grid_fwd_tmh_jac<float2> (main hash grid forward: fp32 table -> fp16 TMH tiles + saved d feature/dx)", "bound": "hbm",
+                       "launch_us": us, "achieved": b_s * N / us / 1e3, "peak": peak, "unit": "GB/s", "frac": b_s * N / us / 1e3 / peak,
+                       "algorithmic_bytes_per_sample": b_s, "traffic": RECORDED_TRAFFIC.get("k_grid_fwd_tmh_jac")})
+        n_par = trainer.groups[0][2]
+        p2, m2, v2 = trainer.flat[:n_par].clone(), torch.zeros(n_par, device=dev), torch.zeros(n_par, device=dev)  # copies: the trainer's state is not touched
+        g2, cnt = trainer.grad[:n_par].clone(), torch.zeros(1, dtype=torch.int32, device=dev)
+        us = timed_us(lambda: nv.ops.adam_step(p2, g2, m2, v2, cnt, 1e-2, 0.9, 0.999, 1e-15))
+        extras.append({"kernel": "k_adam (fields group, 16.8 M parameters)", "bound": "hbm", "launch_us": us, "achieved": 28 * n_par / us / 1e3, "peak": peak,
+                       "unit": "GB/s", "frac": 28 * n_par / us / 1e3 / peak, "algorithmic_bytes_per_param": 28})
+        del p2, m2, v2, g2
         fld = model.field
         nets = {"mlp_base 32-64-16": (fld.mlp_base.mlp.spec, fld.mlp_base.mlp._flat_param_list(), 6144),
                 "mlp_head 63-64-64-3": (fld.mlp_head.spec, fld.mlp_head._flat_param_list(), 16640)}
@@ -306,7 +325,6 @@ def run_ours(args):
                 extras.append({"kernel": f"k_mlp_tc_{tag}: {name}", "bound": "tensor", "launch_us": t_us, "achieved": tf, "peak": tpeak, "unit": "TFLOP/s",
                                "frac": tf / tpeak, "flop_per_sample": fl, "peak_source": tpeak_src})
         roofline["others"] = extras
-        del dy_tmf, scratch
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             v, sec = cpu_port_rays_per_s(1024, 2, 1, threads)
