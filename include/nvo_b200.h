@@ -347,10 +347,11 @@ int nvo_adam_exchange_step(void* stream, int64_t n, int32_t rank, int32_t world,
 /* The same exchange restricted to the flat range [offset, offset + n) — one optimizer parameter group (NS/engine/optimizers.py:138-150
  * keeps one Adam per group; nerfacto's groups are "fields" and "proposal_networks", NS/models/nerfacto.py:244-249).  `phase`
  * (0 .. 2) selects the group's own block of flags, so the groups' exchanges of one step may be in flight concurrently; moments
- * hold nvo_exchange_slice(n, ...) floats; `step` is the group's own counter (a group that received no gradient is not stepped). */
+ * hold nvo_exchange_slice(n, ...) floats; `step` is the group's own counter (a group that received no gradient is not stepped).
+ * ctas_per_sm > 0 caps the persistent grid (0 = as many CTAs as fit): a launch that overlaps other kernels leaves them the registers. */
 int nvo_adam_exchange_group(void* stream, int64_t offset, int64_t n, int32_t phase, int32_t rank, int32_t world, const void* h_peer_params,
                             const void* h_peer_grads, const void* h_peer_flags, float* exp_avg_slice, float* exp_avg_sq_slice, int32_t* step,
-                            float lr, float beta1, float beta2, float eps, float grad_scale);
+                            float lr, float beta1, float beta2, float eps, float grad_scale, int32_t ctas_per_sm);
 /* peer-visible allocations: cudaMalloc (zero-filled) + CUDA IPC export / import; handles are 64 opaque bytes */
 int nvo_peer_alloc(int64_t bytes, void* h_ptr_out, void* h_handle64_out);
 int nvo_peer_open(const void* h_handle64, void* h_ptr_out);

@@ -159,7 +159,7 @@ extern "C" int64_t nvo_exchange_slice(int64_t n, int32_t rank, int32_t world, in
 // Exchange + Adam of the flat range [offset, offset + n) (one parameter group); `phase` selects the group's block of flags.
 extern "C" int nvo_adam_exchange_group(void* stream, int64_t offset, int64_t n, int32_t phase, int32_t rank, int32_t world, const void* h_peer_params,
                                        const void* h_peer_grads, const void* h_peer_flags, float* exp_avg_slice, float* exp_avg_sq_slice, int32_t* step,
-                                       float lr, float beta1, float beta2, float eps, float grad_scale) {
+                                       float lr, float beta1, float beta2, float eps, float grad_scale, int32_t ctas_per_sm) {
     NVO_CHECK(n > 0 && (n & 3) == 0 && offset >= 0 && (offset & 3) == 0, "adam_exchange: range [%lld, +%lld) must be float4-aligned and non-empty",
               (long long)offset, (long long)n);
     NVO_CHECK(phase >= 0 && phase < NVO_MAX_PHASES, "adam_exchange: phase %d out of range [0,%d)", phase, NVO_MAX_PHASES);
@@ -188,11 +188,13 @@ extern "C" int nvo_adam_exchange_group(void* stream, int64_t offset, int64_t n, 
     }
     cudaStream_t st = (cudaStream_t)stream;
     // persistent grid: as many 256-thread CTAs as are co-resident (measured at 2 GPUs: 151 us for the whole flat buffer against 175 us
-    // with two CTAs per SM).  NVO_EXCHANGE_CTAS_PER_SM=k caps it, for runs that overlap the exchange with other kernels.
+    // with two CTAs per SM; at 8 GPUs the kernel is NVLink-bound and ONE CTA per SM is as fast).  ctas_per_sm > 0 (or
+    // NVO_EXCHANGE_CTAS_PER_SM=k) caps it, for launches that run next to other kernels and must leave them registers.
     const int64_t items = (hi - lo) / 4;
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0);
     per_sm = max(per_sm, 1);
+    if (ctas_per_sm > 0) per_sm = min(per_sm, (int)ctas_per_sm);
     if (const char* cap = getenv("NVO_EXCHANGE_CTAS_PER_SM")) per_sm = max(1, min(per_sm, atoi(cap)));
     const unsigned int grid = (unsigned int)max((int64_t)1, min((int64_t)nvo_sm_count() * per_sm, (items + 255) / 256));
     // An SM's L1 / shared-memory split is fixed while any CTA is resident.  This kernel uses no shared memory, so by default it would
@@ -211,7 +213,7 @@ extern "C" int nvo_adam_exchange_step(void* stream, int64_t n, int32_t rank, int
                                       const void* h_peer_flags, float* exp_avg_slice, float* exp_avg_sq_slice, int32_t* step, float lr, float beta1,
                                       float beta2, float eps, float grad_scale) {
     return nvo_adam_exchange_group(stream, 0, n, 0, rank, world, h_peer_params, h_peer_grads, h_peer_flags, exp_avg_slice, exp_avg_sq_slice, step, lr,
-                                   beta1, beta2, eps, grad_scale);
+                                   beta1, beta2, eps, grad_scale, 0);
 }
 
 // ---- peer-visible allocations (CUDA IPC) ----------------------------------------------------------------------------------

@@ -119,11 +119,12 @@ class PeerBuffers:
     def group_moments(self, gid: int):
         return self._groups[gid][2], self._groups[gid][3]
 
-    def adam_exchange_group(self, gid: int, step: torch.Tensor, lr: float, beta1: float, beta2: float, eps: float) -> None:
-        """adam_exchange_step restricted to one registered group; `step` is the GROUP's device counter (incremented here)."""
+    def adam_exchange_group(self, gid: int, step: torch.Tensor, lr: float, beta1: float, beta2: float, eps: float, ctas_per_sm: int = 0) -> None:
+        """adam_exchange_step restricted to one registered group; `step` is the GROUP's device counter (incremented here).
+        ctas_per_sm > 0 caps the persistent grid (for a launch that runs next to other kernels)."""
         off, n, m, v = self._groups[gid]
         _lib.call("nvo_adam_exchange_group", off, n, gid, self.rank, self.world, ctypes.addressof(self._h_params), ctypes.addressof(self._h_grads),
-                  ctypes.addressof(self._h_flags), m, v, step, lr, beta1, beta2, eps, 1.0 / self.world)
+                  ctypes.addressof(self._h_flags), m, v, step, lr, beta1, beta2, eps, 1.0 / self.world, int(ctas_per_sm))
 
     def error_word(self) -> int:
         """0 = healthy; 1 / 2 = a peer never signalled 'gradients ready' / 'replicas written' (bounded spin timed out) in any phase."""

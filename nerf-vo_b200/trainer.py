@@ -92,6 +92,7 @@ class MappingTrainer:
         self.step_count = self.step_counts[0]
         self._opt_stream: Optional[torch.cuda.Stream] = None
         self._fields_done = False
+        self._in_backward = False
         off = 0
         self._views = []
         for p, n in zip(self.params, sizes):
@@ -196,16 +197,19 @@ class MappingTrainer:
             self.model._leaf_renders = False
         if side:
             ops.leaf_streams.join()  # the zero fill must have landed before the first backward kernel accumulates into the gradient
-        # Early launch of the fields group's optimizer / exchange next to the (deferred) proposal backward: measured on one and two B200s
-        # (profiles/r01_timeline_*s9*.csv) it does not pay — both sides want the same registers (the exchange keeps 128 B of peer loads in
-        # flight per thread), so the proposal backward crawls while the exchange runs, and the field chain loses the proposal backward
-        # that used to fill its idle issue slots.  Kept behind NVO_EARLY_FIELDS_OPT=1 for boxes with more ranks.
-        early = side and len(self.groups) == 2 and self.exchange != "nccl" and os.environ.get("NVO_EARLY_FIELDS_OPT", "0") == "1"
+        # Early launch of the fields group's exchange next to the (deferred) proposal backward.  Measured (profiles/r01_timeline_*s9*.csv,
+        # DESIGN.md section 6): on one GPU and at 2 ranks it does not pay — both sides want the same registers and the field chain loses the
+        # proposal backward that used to fill its idle issue slots; from 4 ranks on the exchange is NVLink-bound, one CTA per SM carries it, and
+        # hiding it behind the proposal backward wins (8 GPUs: 1067 -> 1030 us per step).  NVO_EARLY_FIELDS_OPT=1 / 0 forces it on / off.
+        env = os.environ.get("NVO_EARLY_FIELDS_OPT", "")
+        early = side and len(self.groups) == 2 and self.exchange != "nccl" and (env == "1" or (env != "0" and self.peer is not None and self.world_size >= 4))
         if early:
             ops.leaf_streams.after_field_backward = self._fields_optimizer_hook
+        self._in_backward = True
         try:
             total.backward()
         finally:
+            self._in_backward = False
             ops.leaf_streams.after_field_backward = None
             ops.leaf_streams.defer_event = None
         ops.clear_prepacked()
@@ -232,7 +236,9 @@ class MappingTrainer:
     def _optimizer_group(self, gi: int) -> None:
         _, off, n = self.groups[gi]
         if self.peer is not None:
-            self.peer.adam_exchange_group(self._peer_groups[gi], self.step_counts[gi], self.lr, self.betas[0], self.betas[1], self.eps)
+            # inside the backward (early launch) the exchange shares the SMs with the proposal backward: one CTA per SM
+            self.peer.adam_exchange_group(self._peer_groups[gi], self.step_counts[gi], self.lr, self.betas[0], self.betas[1], self.eps,
+                                          ctas_per_sm=1 if self._in_backward else 0)
             return
         ops.adam_step(self.flat[off:off + n], self.grad[off:off + n], self.exp_avg[off:off + n], self.exp_avg_sq[off:off + n], self.step_counts[gi],
                       self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / self.world_size)
