@@ -103,10 +103,16 @@ class MappingTrainer:
         self._attach_main_grads()
         # ---- static inputs ---------------------------------------------------------------------------------------
         B, dev = self.B, self.device
-        f = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
-        self.inputs = {"origins": f(B, 3), "directions": f(B, 3), "directions_norm": f(B, 1), "pixel_area": f(B, 1),
-                       "camera_indices": torch.zeros((B, 1), dtype=torch.int64, device=dev), "rgb": f(B, 3), "depth": f(B, 1), "normal": f(B, 3),
-                       "jitter0": f(B, 1), "jitter1": f(B, 1), "jitter2": f(B, 1)}
+        # every fp32 input is a view of ONE staging buffer, so a batch packed on the host (pack_host_batch) arrives with a single copy
+        self._float_layout = [("origins", 3), ("directions", 3), ("directions_norm", 1), ("pixel_area", 1), ("rgb", 3), ("depth", 1), ("normal", 3),
+                              ("jitter0", 1), ("jitter1", 1), ("jitter2", 1)]
+        self._float_offsets, off = {}, 0
+        for name, c in self._float_layout:  # every block starts on a 16-byte boundary (vector loads), whatever B is
+            self._float_offsets[name] = off
+            off = (off + B * c + 3) // 4 * 4
+        self._staging = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.inputs = {name: self._staging[self._float_offsets[name]:self._float_offsets[name] + B * c].view(B, c) for name, c in self._float_layout}
+        self.inputs["camera_indices"] = torch.zeros((B, 1), dtype=torch.int64, device=dev)
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
         self._terms: Dict[str, torch.Tensor] = {}
         self._term_weights: Dict[str, float] = {}
@@ -298,6 +304,26 @@ class MappingTrainer:
         ps = self.model.proposal_sampler
         seen = max(self.iteration - 1, 0)  # the sampler's _step is set by the AFTER_TRAIN_ITERATION callback of the previous iteration
         return bool(self._ssu > ps.update_sched(seen) or seen < 10)
+
+    def pack_host_batch(self, rays: Dict[str, torch.Tensor], targets: Dict[str, torch.Tensor], jitters: List[torch.Tensor]):
+        """One batch as two pinned host tensors (all fp32 inputs back to back in the staging layout, camera indices) for set_inputs_packed."""
+        src = dict(rays)
+        src.update({"rgb": targets["rgb"], "depth": targets["depth"], "normal": targets["normal"]})
+        for k in range(3):
+            src[f"jitter{k}"] = jitters[k]
+        flat = torch.zeros(self._staging.numel(), dtype=torch.float32).pin_memory()
+        for name, c in self._float_layout:
+            off = self._float_offsets[name]
+            flat[off:off + self.B * c].copy_(src[name].reshape(-1).float())
+        cam = src["camera_indices"].reshape(self.B, 1).to(torch.int64).contiguous().pin_memory()
+        return flat, cam
+
+    def set_inputs_packed(self, packed, non_blocking: bool = True) -> int:
+        """Two host-to-device copies for the whole batch; returns the bytes copied."""
+        flat, cam = packed
+        self._staging.copy_(flat, non_blocking=non_blocking)
+        self.inputs["camera_indices"].copy_(cam, non_blocking=non_blocking)
+        return flat.numel() * 4 + cam.numel() * 8
 
     def capture(self, warmup: int = 3) -> None:
         """Warm up on a side stream, then capture forward+backward (and the optimizer) into CUDA graphs: one graph for steps that update
