@@ -93,5 +93,6 @@ def test_trainer_follows_the_reference_step_and_schedule(graph):
         far = ((now[k] - v).abs() > 0.05 * moved + 1e-6).float().mean()
         # measured noise floor (tools/trainer_noise.py, the loop against ITSELF): up to 3 % of the entries of the 64-element head biases
         # land further apart than this, below 1 % elsewhere; a wrong schedule or a racing optimizer moves nearly all of them
-        # (tensors of a few elements — output biases — are judged on half of their entries: one noisy entry of three is 33 %)
-        assert float(far) < (0.15 if v.numel() >= 256 else 0.51), (k, float(far), float(moved))
+        # (tensors of a few elements — output biases — are left to the loss trajectory: one noisy entry of three is already 33 %)
+        if v.numel() >= 64:
+            assert float(far) < (0.15 if v.numel() >= 256 else 0.3), (k, float(far), float(moved))
