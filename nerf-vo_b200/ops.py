@@ -1142,9 +1142,10 @@ def mlp_tc_backward(x16, wimage, saved, y, dy, spec: MlpSpec, need_dx: bool, nee
     dx = torch.empty(tmh_numel(n, spec.in_dim), dtype=torch.float32, device=x16.device) if need_dx else None
     if need_dparams and dflat is None:
         dflat = torch.zeros(spec.n_params, dtype=torch.float32, device=x16.device)
-    scratch = _dy_absmax.pop((dy.data_ptr(), dy.numel()), None) if dy_absmax == 0.0 else None
-    if scratch is not None:
-        dy_absmax = -1.0  # `scratch` already holds max|dy|
+    hit = _dy_absmax.pop((dy.data_ptr(), dy.numel()), None) if dy_absmax == 0.0 else None
+    scratch = None
+    if hit is not None and hit[1].shape == dy.shape:
+        scratch, dy_absmax = hit[0], -1.0  # `scratch` already holds max|dy|
     else:
         scratch = torch.empty(1, dtype=torch.float32, device=x16.device)
     call("nvo_mlp_tc_backward", spec.desc, n, x16, wimage, saved, y, row_mask, dy, float(dy_absmax), scratch, dx, dflat if need_dparams else None)
@@ -1339,7 +1340,7 @@ class _FieldHeadsTC(torch.autograd.Function):
         amax = torch.zeros(1, dtype=torch.float32, device=dev)
         call("nvo_field_assemble_backward", ctx.B, ctx.S, h, selector, cam_idx, c(ddensity), dhead_in, dpn_in, 1, dh, demb if cam_idx is not None else None, amax)
         _dy_absmax.clear()
-        _dy_absmax[(dh.data_ptr(), dh.numel())] = amax
+        _dy_absmax[(dh.data_ptr(), dh.numel())] = (amax, dh)  # dh is kept alive: its address cannot be handed to another tensor meanwhile
         if demb is ctx.emb_main_grad:
             demb = None
         head_grads = [None] * ctx.n_head
