@@ -352,6 +352,12 @@ int nvo_adam_exchange_step(void* stream, int64_t n, int32_t rank, int32_t world,
 int nvo_adam_exchange_group(void* stream, int64_t offset, int64_t n, int32_t phase, int32_t rank, int32_t world, const void* h_peer_params,
                             const void* h_peer_grads, const void* h_peer_flags, float* exp_avg_slice, float* exp_avg_sq_slice, int32_t* step,
                             float lr, float beta1, float beta2, float eps, float grad_scale, int32_t ctas_per_sm);
+/* Two parameter groups stepped in the same launch (one pair of barriers instead of two; the flags of phase 0 and group A's counter as
+ * barrier epoch): what the trainer uses when both groups' gradients are complete at the same time. */
+int nvo_adam_exchange_groups2(void* stream, int64_t offset_a, int64_t n_a, float* exp_avg_a, float* exp_avg_sq_a, int32_t* step_a, int64_t offset_b,
+                              int64_t n_b, float* exp_avg_b, float* exp_avg_sq_b, int32_t* step_b, int32_t rank, int32_t world,
+                              const void* h_peer_params, const void* h_peer_grads, const void* h_peer_flags, float lr, float beta1, float beta2,
+                              float eps, float grad_scale);
 /* peer-visible allocations: cudaMalloc (zero-filled) + CUDA IPC export / import; handles are 64 opaque bytes */
 int nvo_peer_alloc(int64_t bytes, void* h_ptr_out, void* h_handle64_out);
 int nvo_peer_open(const void* h_handle64, void* h_ptr_out);

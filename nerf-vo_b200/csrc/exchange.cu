@@ -70,23 +70,22 @@ __device__ __forceinline__ bool wait_all(const int* flags, int base, int world, 
 
 // U float4 items per thread and trip: U*W independent 16-byte peer loads in flight per thread (NVLink round trips are ~2 us; the
 // kernel is latency-bound unless every SM keeps tens of KB outstanding)
+struct SliceArgs {
+    int64_t lo4, hi4;   // the rank's slice of one parameter group, in float4 units of the flat buffers
+    float* m;           // Adam moments of the slice (index 0 = element lo4)
+    float* v;
+    const int* step;    // the group's step counter
+};
+
+// reduce-scatter (peer loads) -> Adam -> all-gather (peer stores) on one slice
 template <int W, int U>
-__global__ void __launch_bounds__(256) k_exchange_adam(const __grid_constant__ PeerSet ps, int rank, int64_t lo4, int64_t hi4, float* __restrict__ m,
-                                                       float* __restrict__ v, const int* __restrict__ step_ptr, float lr, float b1, float b2, float eps,
-                                                       float grad_scale, int flag_base) {
-    int* my_flags = ps.flags[rank] + flag_base;
-    const int epoch = *step_ptr + 1;
-    // ---- 1. every rank's backward has landed -----------------------------------------------------------------------
-    if (blockIdx.x == 0 && threadIdx.x < W && threadIdx.x != rank) {
-        __threadfence_system();
-        st_release_sys(ps.flags[threadIdx.x] + flag_base + FLAG_READY + rank, epoch);
-    }
-    if (!wait_all(my_flags, FLAG_READY, W, rank, epoch)) {
-        if (threadIdx.x == 0) atomicExch(my_flags + FLAG_COUNT + 1, 1);
-    }
-    const float t = (float)epoch;
+__device__ __forceinline__ void slice_pass(const PeerSet& ps, int rank, const SliceArgs& a, float lr, float b1, float b2, float eps, float grad_scale) {
+    if (a.hi4 <= a.lo4) return;
+    const float t = (float)(*a.step + 1);
     const float step_size = lr / (1.f - powf(b1, t)), inv_bc2 = 1.f / sqrtf(1.f - powf(b2, t));
-    // ---- 2-4. reduce-scatter (peer loads) -> Adam -> all-gather (peer stores) on the own slice -------------------------
+    float* __restrict__ m = a.m;
+    float* __restrict__ v = a.v;
+    const int64_t lo4 = a.lo4, hi4 = a.hi4;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i0 = lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi4; i0 += stride * U) {
         float4 g[U][W];
@@ -124,6 +123,27 @@ __global__ void __launch_bounds__(256) k_exchange_adam(const __grid_constant__ P
             for (int k = 0; k < W; ++k) st_peer_f4(ps.params[k] + 4 * i, pp);
         }
     }
+}
+
+// One launch = barrier, the rank's slice of group A (and, when present, of group B: two parameter groups stepped together share the two
+// barriers), barrier.  The barrier epoch is group A's step counter.
+template <int W, int U>
+__global__ void __launch_bounds__(256) k_exchange_adam(const __grid_constant__ PeerSet ps, int rank, const __grid_constant__ SliceArgs sa,
+                                                       const __grid_constant__ SliceArgs sb, float lr, float b1, float b2, float eps, float grad_scale,
+                                                       int flag_base) {
+    int* my_flags = ps.flags[rank] + flag_base;
+    const int epoch = *sa.step + 1;
+    // ---- 1. every rank's backward has landed -----------------------------------------------------------------------
+    if (blockIdx.x == 0 && threadIdx.x < W && threadIdx.x != rank) {
+        __threadfence_system();
+        st_release_sys(ps.flags[threadIdx.x] + flag_base + FLAG_READY + rank, epoch);
+    }
+    if (!wait_all(my_flags, FLAG_READY, W, rank, epoch)) {
+        if (threadIdx.x == 0) atomicExch(my_flags + FLAG_COUNT + 1, 1);
+    }
+    // ---- 2-4. reduce-scatter (peer loads) -> Adam -> all-gather (peer stores) on the own slices -------------------------
+    slice_pass<W, U>(ps, rank, sa, lr, b1, b2, eps, grad_scale);
+    slice_pass<W, U>(ps, rank, sb, lr, b1, b2, eps, grad_scale);
     // ---- 5. replicas written: last CTA signals the peers and waits for theirs -----------------------------------------------
     __threadfence_system();
     __syncthreads();
@@ -139,9 +159,14 @@ __global__ void __launch_bounds__(256) k_exchange_adam(const __grid_constant__ P
     }
 }
 
+__global__ void k_tick_step2(int* a, int* b) {
+    *a += 1;
+    if (b) *b += 1;
+}
+
 __global__ void k_tick_step(int* step) { *step += 1; }
 
-typedef void (*exchange_fn)(const PeerSet, int, int64_t, int64_t, float*, float*, const int*, float, float, float, float, float, int);
+typedef void (*exchange_fn)(const PeerSet, int, const SliceArgs, const SliceArgs, float, float, float, float, float, int);
 
 extern "C" int nvo_exchange_flag_words(void) { return FLAG_WORDS; }
 
@@ -156,28 +181,30 @@ extern "C" int64_t nvo_exchange_slice(int64_t n, int32_t rank, int32_t world, in
     return (b - a) * 4;
 }
 
-// Exchange + Adam of the flat range [offset, offset + n) (one parameter group); `phase` selects the group's block of flags.
-extern "C" int nvo_adam_exchange_group(void* stream, int64_t offset, int64_t n, int32_t phase, int32_t rank, int32_t world, const void* h_peer_params,
-                                       const void* h_peer_grads, const void* h_peer_flags, float* exp_avg_slice, float* exp_avg_sq_slice, int32_t* step,
-                                       float lr, float beta1, float beta2, float eps, float grad_scale, int32_t ctas_per_sm) {
+// Exchange + Adam of the flat ranges [offset, offset + n) (group A) and, if n_b > 0, [offset_b, offset_b + n_b) (group B) in ONE launch.
+static int exchange_launch(void* stream, int64_t offset, int64_t n, float* m_a, float* v_a, int32_t* step_a, int64_t offset_b, int64_t n_b, float* m_b,
+                           float* v_b, int32_t* step_b, int32_t phase, int32_t rank, int32_t world, const void* h_peer_params, const void* h_peer_grads,
+                           const void* h_peer_flags, float lr, float beta1, float beta2, float eps, float grad_scale, int32_t ctas_per_sm) {
     NVO_CHECK(n > 0 && (n & 3) == 0 && offset >= 0 && (offset & 3) == 0, "adam_exchange: range [%lld, +%lld) must be float4-aligned and non-empty",
               (long long)offset, (long long)n);
+    NVO_CHECK(n_b >= 0 && (n_b & 3) == 0 && offset_b >= 0 && (offset_b & 3) == 0, "adam_exchange: second range [%lld, +%lld) must be float4-aligned",
+              (long long)offset_b, (long long)n_b);
     NVO_CHECK(phase >= 0 && phase < NVO_MAX_PHASES, "adam_exchange: phase %d out of range [0,%d)", phase, NVO_MAX_PHASES);
     NVO_CHECK(world >= 1 && world <= NVO_MAX_PEERS && rank >= 0 && rank < world, "adam_exchange: bad rank/world %d/%d", rank, world);
-    NVO_CHECK(h_peer_params && h_peer_grads && h_peer_flags && exp_avg_slice && exp_avg_sq_slice && step, "adam_exchange: null pointer");
+    NVO_CHECK(h_peer_params && h_peer_grads && h_peer_flags && m_a && v_a && step_a, "adam_exchange: null pointer");
+    NVO_CHECK(n_b == 0 || (m_b && v_b && step_b), "adam_exchange: null pointer (second group)");
     PeerSet ps;
     for (int k = 0; k < NVO_MAX_PEERS; ++k) {
         ps.params[k] = k < world ? ((float* const*)h_peer_params)[k] : nullptr;
         ps.grads[k] = k < world ? ((const float* const*)h_peer_grads)[k] : nullptr;
         ps.flags[k] = k < world ? ((int* const*)h_peer_flags)[k] : nullptr;
-        if (k < world) {
-            NVO_CHECK(ps.params[k] && ps.grads[k] && ps.flags[k], "adam_exchange: null peer pointer for rank %d", k);
-            ps.params[k] += offset;
-            ps.grads[k] += offset;
-        }
+        if (k < world) NVO_CHECK(ps.params[k] && ps.grads[k] && ps.flags[k], "adam_exchange: null peer pointer for rank %d", k);
     }
-    int64_t lo, hi;
+    int64_t lo, hi, lob = 0, hib = 0;
     nvo_exchange_slice(n, rank, world, &lo, &hi);
+    if (n_b > 0) nvo_exchange_slice(n_b, rank, world, &lob, &hib);
+    const SliceArgs sa = {(offset + lo) / 4, (offset + hi) / 4, m_a, v_a, step_a};
+    const SliceArgs sb = {(offset_b + lob) / 4, (offset_b + hib) / 4, m_b, v_b, n_b > 0 ? step_b : step_a};
     exchange_fn fn = nullptr;
     switch (world) {
         case 1: fn = k_exchange_adam<1, 4>; break;
@@ -190,7 +217,7 @@ extern "C" int nvo_adam_exchange_group(void* stream, int64_t offset, int64_t n, 
     // persistent grid: as many 256-thread CTAs as are co-resident (measured at 2 GPUs: 151 us for the whole flat buffer against 175 us
     // with two CTAs per SM; at 8 GPUs the kernel is NVLink-bound and ONE CTA per SM is as fast).  ctas_per_sm > 0 (or
     // NVO_EXCHANGE_CTAS_PER_SM=k) caps it, for launches that run next to other kernels and must leave them registers.
-    const int64_t items = (hi - lo) / 4;
+    const int64_t items = (hi - lo) / 4 + (hib - lob) / 4;
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0);
     per_sm = max(per_sm, 1);
@@ -202,11 +229,27 @@ extern "C" int nvo_adam_exchange_group(void* stream, int64_t offset, int64_t n, 
     // co-resident until the exchange had drained (observed: profiles/r01_timeline_n2_s9_early_no_carveout.csv).  Ask for the largest
     // carve-out instead.
     cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    fn<<<grid, 256, 0, st>>>(ps, rank, lo / 4, hi / 4, exp_avg_slice, exp_avg_sq_slice, step, lr, beta1, beta2, eps, grad_scale, phase * FLAG_PHASE_STRIDE);
+    fn<<<grid, 256, 0, st>>>(ps, rank, sa, sb, lr, beta1, beta2, eps, grad_scale, phase * FLAG_PHASE_STRIDE);
     NVO_CUDA_LAUNCH_CHECK("adam_exchange");
-    k_tick_step<<<1, 1, 0, st>>>(step);
+    k_tick_step2<<<1, 1, 0, st>>>(step_a, n_b > 0 ? step_b : nullptr);
     NVO_CUDA_LAUNCH_CHECK("adam_exchange(tick)");
     return 0;
+}
+
+extern "C" int nvo_adam_exchange_group(void* stream, int64_t offset, int64_t n, int32_t phase, int32_t rank, int32_t world, const void* h_peer_params,
+                                       const void* h_peer_grads, const void* h_peer_flags, float* exp_avg_slice, float* exp_avg_sq_slice, int32_t* step,
+                                       float lr, float beta1, float beta2, float eps, float grad_scale, int32_t ctas_per_sm) {
+    return exchange_launch(stream, offset, n, exp_avg_slice, exp_avg_sq_slice, step, 0, 0, nullptr, nullptr, nullptr, phase, rank, world, h_peer_params,
+                           h_peer_grads, h_peer_flags, lr, beta1, beta2, eps, grad_scale, ctas_per_sm);
+}
+
+extern "C" int nvo_adam_exchange_groups2(void* stream, int64_t offset_a, int64_t n_a, float* exp_avg_a, float* exp_avg_sq_a, int32_t* step_a,
+                                         int64_t offset_b, int64_t n_b, float* exp_avg_b, float* exp_avg_sq_b, int32_t* step_b, int32_t rank,
+                                         int32_t world, const void* h_peer_params, const void* h_peer_grads, const void* h_peer_flags, float lr,
+                                         float beta1, float beta2, float eps, float grad_scale) {
+    NVO_CHECK(n_b > 0, "adam_exchange_groups2: the second group is empty (use nvo_adam_exchange_group)");
+    return exchange_launch(stream, offset_a, n_a, exp_avg_a, exp_avg_sq_a, step_a, offset_b, n_b, exp_avg_b, exp_avg_sq_b, step_b, 0, rank, world,
+                           h_peer_params, h_peer_grads, h_peer_flags, lr, beta1, beta2, eps, grad_scale, 0);
 }
 
 extern "C" int nvo_adam_exchange_step(void* stream, int64_t n, int32_t rank, int32_t world, const void* h_peer_params, const void* h_peer_grads,

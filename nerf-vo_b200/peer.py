@@ -126,6 +126,13 @@ class PeerBuffers:
         _lib.call("nvo_adam_exchange_group", off, n, gid, self.rank, self.world, ctypes.addressof(self._h_params), ctypes.addressof(self._h_grads),
                   ctypes.addressof(self._h_flags), m, v, step, lr, beta1, beta2, eps, 1.0 / self.world, int(ctas_per_sm))
 
+    def adam_exchange_groups2(self, gid_a: int, step_a: torch.Tensor, gid_b: int, step_b: torch.Tensor, lr: float, beta1: float, beta2: float, eps: float) -> None:
+        """Both groups in ONE launch (one pair of barriers): for steps on which their gradients are complete at the same time."""
+        oa, na, ma, va = self._groups[gid_a]
+        ob, nb, mb, vb = self._groups[gid_b]
+        _lib.call("nvo_adam_exchange_groups2", oa, na, ma, va, step_a, ob, nb, mb, vb, step_b, self.rank, self.world, ctypes.addressof(self._h_params),
+                  ctypes.addressof(self._h_grads), ctypes.addressof(self._h_flags), lr, beta1, beta2, eps, 1.0 / self.world)
+
     def error_word(self) -> int:
         """0 = healthy; 1 / 2 = a peer never signalled 'gradients ready' / 'replicas written' (bounded spin timed out) in any phase."""
         words = int(_lib.load().nvo_exchange_flag_words())

@@ -251,6 +251,11 @@ class MappingTrainer:
 
     def _optimizer(self, updated: bool = True) -> None:
         """Steps every group that has not been stepped inside the backward; the proposal group only when it received gradients."""
+        if self.peer is not None and len(self.groups) == 2 and updated and not self._fields_done:
+            # both groups pending at the same point of the step: one exchange launch, one pair of barriers
+            self.peer.adam_exchange_groups2(self._peer_groups[0], self.step_counts[0], self._peer_groups[1], self.step_counts[1], self.lr,
+                                            self.betas[0], self.betas[1], self.eps)
+            return
         side = self.device.type == "cuda" and ops.leaf_streams.enabled and self.peer is None
         forked = False
         for gi, (name, _, _) in reversed(list(enumerate(self.groups))):  # the small group first: it slips in next to the big one's CTAs

@@ -90,11 +90,37 @@ def _two_rank_worker(rank, world, port, tmp):
     # parameter because the two kernels contract mul+add into FMA differently: tolerance 1e-6 absolute
     ok = worst < 1e-6 and hist[0] == 0.0
     ok = ok and bufs.error_word() == 0
+    # ---- two parameter groups: group A alone (its counter runs ahead), then both groups in one launch ----------------------------
+    n_a = 4 * 700_001
+    b2 = PeerBuffers(n, dev)
+    ga, gb = b2.add_group(0, n_a), b2.add_group(n_a, n - n_a)
+    b2.params.copy_(p0)
+    f2, m2, v2 = p0.clone().to(dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    ca, cb = (torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(2))
+    ra, rb = (torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(2))
+    worst2 = 0.0
+    for it, both in enumerate([True, False, True, True]):
+        gr = torch.Generator(device="cpu").manual_seed(900 + 10 * it + rank)
+        grad = torch.randn(n, generator=gr).to(dev)
+        b2.grads.copy_(grad)
+        if both:
+            b2.adam_exchange_groups2(ga, ca, gb, cb, 1e-2, 0.9, 0.999, 1e-15)
+        else:
+            b2.adam_exchange_group(ga, ca, 1e-2, 0.9, 0.999, 1e-15)
+        red = grad.clone()
+        dist.all_reduce(red)
+        ops.adam_step(f2[:n_a], red[:n_a], m2[:n_a], v2[:n_a], ra, 1e-2, 0.9, 0.999, 1e-15, 1.0 / world)
+        if both:
+            ops.adam_step(f2[n_a:], red[n_a:], m2[n_a:], v2[n_a:], rb, 1e-2, 0.9, 0.999, 1e-15, 1.0 / world)
+        torch.cuda.synchronize()
+        worst2 = max(worst2, float((b2.params - f2).abs().max()))
+    ok = ok and worst2 < 1e-6 and b2.error_word() == 0 and (int(ca), int(cb)) == (4, 3) == (int(ra), int(rb))
     lo, hi = bufs.slice
     own = float((bufs.params[lo:hi] - flat[lo:hi]).abs().max())
-    torch.save({"ok": bool(ok), "worst": worst, "per_step": hist, "own_slice_err": own, "error_word": bufs.error_word(), "steps": (int(step_a), int(step_b))},
+    torch.save({"ok": bool(ok), "worst": worst, "worst_groups": worst2, "group_steps": (int(ca), int(cb)), "per_step": hist, "own_slice_err": own, "error_word": bufs.error_word(), "steps": (int(step_a), int(step_b))},
                os.path.join(tmp, f"r{rank}.pt"))
     dist.barrier()
+    b2.close()
     bufs.close()
     dist.destroy_process_group()
 
