@@ -151,6 +151,8 @@ def load_optimizer_state(optimizers: Dict, model_state, model, trainer) -> None:
 def checkpoint_dict(step: int, model, camera_optimizer=None, trainer=None) -> Dict:
     """The dict Trainer.save_checkpoint writes (NS/engine/trainer.py:436-447), torch key layout."""
     pipeline = OrderedDict()
+    # Model.device_indicator_param (NS/models/base_model.py:81): an empty parameter the reference's strict load_state_dict expects first
+    pipeline["_model.device_indicator_param"] = torch.empty(0)
     for k, v in model.state_dict().items():
         pipeline["_model." + k] = v.detach().clone().cpu()
     if camera_optimizer is not None and hasattr(camera_optimizer, "pose_adjustment"):
