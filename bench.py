@@ -96,6 +96,16 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def cpu_model_name() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.lower().startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 def cpu_port_rays_per_s(num_rays: int, steps: int, warmup: int, threads: int):
     """Times the CPU oracle port (the reference's torch algorithm restated; oracle/nerfacto_oracle.py) on `num_rays` rays."""
@@ -107,19 +117,29 @@ def cpu_port_rays_per_s(num_rays: int, steps: int, warmup: int, threads: int):
     torch.set_num_threads(threads)
     cfg = O.ModelCfg(num_images=NUM_IMAGES)
     P = {k: v.requires_grad_(True) for k, v in O.init_params(cfg, seed=0).items()}
-    times = []
+    times, split = [], {"forward_s": 0.0, "losses_s": 0.0, "backward_s": 0.0}
     for i in range(warmup + steps):
         rays, targets = O.synthetic_rays(num_rays, num_images=NUM_IMAGES, seed=1234 + i)
         jit = O.synthetic_jitters(num_rays, seed=99 + i)
         for p in P.values():
             p.grad = None
+        # O.mapping_step, with a clock between its three phases
         t0 = time.perf_counter()
-        O.mapping_step(P, cfg, rays, targets, jit)
-        dt = time.perf_counter() - t0
+        out = O.mapping_forward(P, cfg, rays["origins"], rays["directions"], rays["camera_indices"], jit, 1.0, True, True)
+        t1 = time.perf_counter()
+        L = O.mapping_losses(cfg, out, targets["rgb"], targets.get("depth"), rays.get("directions_norm"), targets.get("normal"))
+        total_loss = sum(L.values())
+        t2 = time.perf_counter()
+        total_loss.backward()
+        t3 = time.perf_counter()
         if i >= warmup:
-            times.append(dt)
+            times.append(t3 - t0)
+            split["forward_s"] += t1 - t0
+            split["losses_s"] += t2 - t1
+            split["backward_s"] += t3 - t2
     total = sum(times)
-    return num_rays * len(times) / total, total / len(times)
+    split = {k: v / len(times) for k, v in split.items()}
+    return num_rays * len(times) / total, total / len(times), split
 
 
 def run_reference(args):
@@ -129,12 +149,12 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     n_total = args.steps + args.warmup
     rays = 512 if n_total <= 40 else (256 if n_total <= 120 else 64)
-    rps, sec = cpu_port_rays_per_s(rays, args.steps, args.warmup, threads)
+    rps, sec, split = cpu_port_rays_per_s(rays, args.steps, args.warmup, threads)
     line = {
         "metric": METRIC, "value": rps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
         "config": {"workload": WORKLOAD, "sample": f"{rays} rays per step (bounded sample of the 4096-ray batch), full-size tables"},
-        "cpu_baseline": {"value": rps, "unit": UNIT, "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": rps, "unit": UNIT, "cores": threads, "cpu_model": cpu_model_name(), "kind": "port", "phases_s_per_step": split,
                          "sample": f"{args.steps} steps x {rays} rays, full forward+losses+backward of the reference's torch algorithm (oracle port; the Python reference is not on this box)"},
         "e2e": {"value": rps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -336,8 +356,8 @@ def run_ours(args):
         roofline["others"] = extras
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, sec = cpu_port_rays_per_s(1024, 2, 1, threads)
-            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+            v, sec, split = cpu_port_rays_per_s(1024, 2, 1, threads)
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "cpu_model": cpu_model_name(), "kind": "port", "phases_s_per_step": split,
                    "sample": "2 timed steps (1 warm-up) x 1024 rays of the same workload, full-size tables, oracle port of the reference torch path"}
 
     # row f2: the same step fed by the device-resident keyframe store through the fused prologue kernel (pixel sampling +
