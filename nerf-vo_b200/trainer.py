@@ -11,9 +11,10 @@ NS/engine/trainer.py:455-494, NS/pipelines/base_pipeline.py:291-304), restated f
     gradient followed by the replicated Adam (`exchange="nccl"`); both give DDP's mean-gradient semantics
     (NS/pipelines/base_pipeline.py:281-283);
   * two optimizer parameter groups like the reference's ("fields", "proposal_networks": NS/models/nerfacto.py:244-249, one Adam each,
-    NS/engine/optimizers.py:138-150), each with its own step counter.  The fields group is stepped (and exchanged) as soon as the main
-    hash-table scatter has landed — on a high-priority stream, next to the proposal networks' backward, which is ordered behind the
-    field's backward chain; the proposal group follows.  `proposal_update="reference"` follows ProposalNetworkSampler's update schedule
+    NS/engine/optimizers.py:138-150), each with its own step counter.  On 1-2 GPUs both groups are stepped after the backward (fused arm:
+    in ONE exchange launch); from 4 ranks on the fields group is exchanged as soon as the main hash-table scatter has landed — on a
+    high-priority stream, next to the proposal networks' backward, which is then ordered behind the field's backward chain — and the
+    proposal group follows.  `proposal_update="reference"` follows ProposalNetworkSampler's update schedule
     (NS/model_components/ray_samplers.py:596-610): on steps where the proposal networks receive no gradient their backward is not run
     and their Adam group is not stepped (torch skips parameters whose .grad is None); "always" updates them every step.
 """
@@ -168,10 +169,10 @@ class MappingTrainer:
                          metadata={"directions_norm": i["directions_norm"]})
 
     def _forward_backward(self) -> None:
-        """zero-grad, forward, losses, backward.  On the fused / local arms the optimizer of the "fields" group is launched from
+        """zero-grad, forward, losses, backward.  From 4 ranks on (fused arm) the exchange + Adam of the "fields" group is launched from
         INSIDE the backward (ops.leaf_streams.after_field_backward), right behind the main hash-table scatter, on a high-priority
-        stream; the proposal networks' backward is ordered behind the field's chain, so both run side by side (one is HBM / NVLink
-        bound, the other issue / reduction bound).  _optimizer() then steps whatever has not been stepped yet."""
+        stream; the proposal networks' backward is then ordered behind the field's chain, so both run side by side (one is NVLink
+        bound, the other issue / reduction bound).  _optimizer() steps whatever has not been stepped yet."""
         i = self.inputs
         side = self.device.type == "cuda" and ops.leaf_streams.enabled
         self._fields_done = False
