@@ -87,3 +87,29 @@ def test_level_scalings_match_oracle(nv):
 
     for gc in (O.GridCfg(), O.GridCfg(5, 16, 128, 17), O.GridCfg(5, 16, 256, 17)):
         assert torch.equal(nv.ops.torch_level_scalings(gc.num_levels, gc.min_res, gc.max_res), O.level_scalings(gc))
+
+
+def test_new_entry_points_bind_and_validate_without_gpu(nv):
+    """The entry points added for the saved Jacobian, the split proposal backward and the grouped exchange: argument lists as the header
+    declares them (ctypes argtypes come from the header text, so a drifted call raises TypeError), empty batches are a no-op success and bad
+    arguments are rejected with a message before any CUDA call."""
+    lib = nv._lib.load()
+    A = ctypes.addressof
+    err = lambda: lib.nvo_last_error().decode()
+    g_tmh = nv._lib.make_grid_desc(16, 19, [16.0] * 16, torch.float32, "tmh")
+    g_f32 = nv._lib.make_grid_desc(16, 19, [16.0] * 16)
+    g_tmf = nv._lib.make_grid_desc(16, 19, [16.0] * 16, torch.float32, "tmf")
+    assert lib.nvo_grid_forward_jac(A(g_tmh), None, 0, None, None, None, None) == 0  # n = 0
+    assert lib.nvo_grid_forward_jac(A(g_f32), None, 4, None, None, None, None) != 0 and "NVO_F16_TMH" in err()
+    assert lib.nvo_grid_jac_dx(A(g_tmf), None, 0, None, None, 0.0, 1e-12, None) == 0
+    assert lib.nvo_grid_jac_dx(A(g_tmf), None, 4, None, None, 0.0, 1e-12, None) != 0 and "null pointer" in err()
+    g5 = nv._lib.make_grid_desc(5, 17, [16.0] * 5)
+    assert lib.nvo_prop_density_backward_split(A(g5), 16, 0, None, 4, 8, None, None, None, None, None, None) != 0 and "null output" in err()
+    assert lib.nvo_prop_density_backward_split(A(g5), 64, 0, None, 4, 8, None, None, None, None, 1, 1) != 0 and "hidden width" in err()
+    for off, n, phase in ((2, 8, 0), (0, 6, 0), (0, 8, 7)):  # misaligned offset, misaligned size, phase out of range
+        assert lib.nvo_adam_exchange_group(None, off, n, phase, 0, 1, None, None, None, None, None, None, 1e-2, 0.9, 0.999, 1e-15, 1.0, 0) != 0
+    assert lib.nvo_adam_exchange_groups2(None, 0, 8, None, None, None, 8, 0, None, None, None, 0, 1, None, None, None, 1e-2, 0.9, 0.999, 1e-15, 1.0) != 0
+    assert "second group is empty" in err()
+    with pytest.raises(TypeError):
+        lib.nvo_grid_jac_dx(A(g_tmf), None, 0)  # too few arguments for the declared signature
+    assert lib.nvo_exchange_flag_words() >= 3 * 40
