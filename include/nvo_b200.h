@@ -223,10 +223,12 @@ int nvo_weights_backward(void* stream, int64_t B, int32_t S, const float* starts
 
 /* PDFSampler.generate_ray_samples (ray_samplers.py:276-372) incl. the anneal pow of ProposalNetworkSampler (:602).
  * u_base[S_out+1]: linspace(0, 1-1/n, n) (+1/(2n) already added by the caller in eval); jitter[B] or NULL.
+ * anneal_dev (nullable): device float that overrides `anneal` — the trainer's CUDA graph reads the schedule value
+ * (NS/models/nerfacto.py:256-278) from it on every replay.
  * inds (nullable) int32 [B,S_out+1]: raw searchsorted(cdf,u,right) result (test hook; bit-exact contract). */
 int nvo_pdf_resample(void* stream, int64_t B, int32_t S_in, int32_t S_out, const float* weights, const float* sdist_in, const float* u_base,
-                     const float* jitter, float anneal, float histogram_padding, const float* nears, const float* fars, float* sdist_out,
-                     float* ebins_out, int32_t* inds);
+                     const float* jitter, float anneal, const float* anneal_dev, float histogram_padding, const float* nears, const float* fars,
+                     float* sdist_out, float* ebins_out, int32_t* inds);
 
 /* RGBRenderer('last_sample') + AccumulationRenderer + DepthRenderer(expected|median) + NormalsRenderer/NormalsShader
  * (NS/model_components/renderers.py:70-117,199-230,287-315,333-381,427-447; shaders.py:56-77).
@@ -282,6 +284,8 @@ int nvo_normal_loss(void* stream, int64_t B, const float* pred /*[B,3]*/, const 
  * Cameras.generate_rays perspective branch (NS/cameras/cameras.py:596-654,780-785,865-912) and
  * CameraOptimizer.apply_to_raybundle (NS/cameras/camera_optimizers.py:108-147).
  *   u[B,3]            uniform [0,1) draws (torch.rand); indices = trunc(u * [K,H,W]) in fp32, bit-exact
+ *   K / K_dev         number of active keyframes; K_dev (nullable) = device int32 read by the kernel instead of K (clamped to [1,K]):
+ *                     a captured CUDA graph then follows the keyframes the mapping thread inserts (nerfstudio_utils.py:203-241)
  *   intrinsics[*,4]   fx fy cx cy per frame; extrinsics[*,4,4] camera-to-world (row-major; only rows 0..2 are read)
  *   frames_color[K,H,W,3], frames_depth[K,H,W,1], frames_normal[K,H,W,3] (camera-frame normals; NULL = no normal target)
  *   pose_adjustment[*,6] (translation, rotation tangent) or NULL; pose_mode NVO_POSE_OFF / SO3XR3 / SE3
@@ -290,7 +294,8 @@ int nvo_normal_loss(void* stream, int64_t B, const float* pred /*[B,3]*/, const 
  *   directions_raw[B,3] (nullable): the uncorrected unit directions, the saved input of nvo_pose_correction_backward.
  * ------------------------------------------------------------------------------------------- */
 enum { NVO_POSE_OFF = 0, NVO_POSE_SO3XR3 = 1, NVO_POSE_SE3 = 2 };
-int nvo_batch_prologue(void* stream, int64_t B, int32_t K, int32_t H, int32_t W, const float* u, const float* intrinsics, const float* extrinsics,
+int nvo_batch_prologue(void* stream, int64_t B, int32_t K, const int32_t* K_dev, int32_t H, int32_t W, const float* u, const float* intrinsics,
+                       const float* extrinsics,
                        const float* frames_color, const float* frames_depth, const float* frames_normal, const float* pose_adjustment,
                        int32_t pose_mode, int64_t* indices, int64_t* camera_indices, float* origins, float* directions, float* directions_norm,
                        float* pixel_area, float* rgb, float* depth, float* normal, float* directions_raw);

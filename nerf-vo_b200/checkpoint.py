@@ -121,11 +121,15 @@ def _ordered_param_keys(model_state_keys, model, group: str) -> List[str]:
 
 
 def load_optimizer_state(optimizers: Dict, model_state, model, trainer) -> None:
-    """torch.optim.Adam.state_dict() per group -> the trainer's flat moment buffers and per-group step counters."""
-    if trainer.exp_avg is None:
-        raise NotImplementedError("optimizer state can be imported into the local / NCCL trainer arms (moments of the fused peer arm are sliced across ranks)")
+    """torch.optim.Adam.state_dict() per group -> the trainer's flat moment buffers and per-group step counters (every trainer arm: the fused
+    peer arm keeps its own slice of the assembled whole-buffer moments, MappingTrainer.load_full_moments)."""
     views = {id(p): v for p, v in zip(trainer.params, trainer._views)}
     named = dict(model.named_parameters())
+    fused = trainer.exp_avg is None
+    if fused:
+        exp_avg, exp_avg_sq = trainer.full_moments()  # collective in the fused arm: every rank loads the checkpoint
+    else:
+        exp_avg, exp_avg_sq = trainer.exp_avg, trainer.exp_avg_sq
     for gi, (gname, _, _) in enumerate(trainer.groups):
         if gname not in optimizers:
             continue
@@ -137,12 +141,14 @@ def load_optimizer_state(optimizers: Dict, model_state, model, trainer) -> None:
             if st is None or id(named[k]) not in views:  # a parameter that never received a gradient has no state (torch skips grad=None)
                 continue
             off, n = views[id(named[k])]
-            trainer.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1).to(trainer.exp_avg.device))
-            trainer.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1).to(trainer.exp_avg.device))
+            exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1).to(exp_avg.device))
+            exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1).to(exp_avg.device))
             steps.append(int(st["step"]))
         if steps:
             # torch keeps `step` per parameter; every parameter of a group that receives gradients is stepped together
             trainer.step_counts[gi].fill_(max(steps))
+    if fused:
+        trainer.load_full_moments(exp_avg, exp_avg_sq)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -157,8 +163,13 @@ def checkpoint_dict(step: int, model, camera_optimizer=None, trainer=None) -> Di
         pipeline["_model." + k] = v.detach().clone().cpu()
     if camera_optimizer is not None and hasattr(camera_optimizer, "pose_adjustment"):
         pipeline["_model.camera_optimizer.pose_adjustment"] = camera_optimizer.pose_adjustment.detach().clone().cpu()
-    out = {"step": int(step), "pipeline": pipeline, "optimizers": {}, "schedulers": {}, "scalers": {}}
-    if trainer is not None and trainer.exp_avg is not None:
+    # "scalers": NeRF-VO trains with mixed_precision=True, so the reference's GradScaler is enabled and Trainer._load_checkpoint calls
+    # grad_scaler.load_state_dict(loaded_state["scalers"]) (NS/engine/trainer.py:416), which raises on an empty dict.  These kernels scale
+    # gradients per launch on the device (csrc/mlp_tc.cu) and keep no global loss scale: a fresh GradScaler's state is written.
+    scalers = {"scale": 65536.0, "growth_factor": 2.0, "backoff_factor": 0.5, "growth_interval": 2000, "_growth_tracker": 0}
+    out = {"step": int(step), "pipeline": pipeline, "optimizers": {}, "schedulers": {}, "scalers": scalers}
+    if trainer is not None:
+        exp_avg, exp_avg_sq = trainer.full_moments()  # fused peer arm: a collective (every rank calls checkpoint_dict / save_checkpoint)
         views = {id(p): v for p, v in zip(trainer.params, trainer._views)}
         named = dict(model.named_parameters())
         keys_all = list(model.state_dict().keys())
@@ -170,8 +181,8 @@ def checkpoint_dict(step: int, model, camera_optimizer=None, trainer=None) -> Di
                 off, n = views[id(named[k])]
                 if t == 0:
                     continue
-                state[idx] = {"step": torch.tensor(float(t)), "exp_avg": trainer.exp_avg[off:off + n].view(named[k].shape).clone().cpu(),
-                              "exp_avg_sq": trainer.exp_avg_sq[off:off + n].view(named[k].shape).clone().cpu()}
+                state[idx] = {"step": torch.tensor(float(t)), "exp_avg": exp_avg[off:off + n].view(named[k].shape).clone().cpu(),
+                              "exp_avg_sq": exp_avg_sq[off:off + n].view(named[k].shape).clone().cpu()}
             group = {"lr": trainer.lr, "betas": tuple(trainer.betas), "eps": trainer.eps, "weight_decay": 0, "amsgrad": False, "maximize": False,
                      "foreach": None, "capturable": False, "differentiable": False, "fused": None, "params": list(range(len(keys)))}
             out["optimizers"][gname] = {"state": state, "param_groups": [group]}

@@ -1,5 +1,6 @@
 // Library-level entry points: error string, version, device info.
 #include <stdarg.h>
+#include <stdlib.h>
 #include "nvo_common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -18,6 +19,11 @@ int nvo_sm_count() {
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     }
     return n;
+}
+
+int nvo_env_int(const char* name, int fallback) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : fallback;
 }
 
 static long long g_launches = 0;

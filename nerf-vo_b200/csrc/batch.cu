@@ -130,7 +130,8 @@ __device__ __forceinline__ void store3(float* p, int64_t i, const float* v) {
     p[3 * i] = v[0], p[3 * i + 1] = v[1], p[3 * i + 2] = v[2];
 }
 
-__global__ void __launch_bounds__(128) k_batch_prologue(int64_t B, int K, int H, int W, const float* __restrict__ u, const float* __restrict__ intr,
+__global__ void __launch_bounds__(128) k_batch_prologue(int64_t B, int K, const int32_t* __restrict__ K_dev, int H, int W, const float* __restrict__ u,
+                                                        const float* __restrict__ intr,
                                                         const float* __restrict__ ext, const float* __restrict__ color, const float* __restrict__ depthf,
                                                         const float* __restrict__ normalf, const float* __restrict__ pose, int mode,
                                                         int64_t* __restrict__ indices, int64_t* __restrict__ cam_idx, float* __restrict__ origins,
@@ -139,6 +140,9 @@ __global__ void __launch_bounds__(128) k_batch_prologue(int64_t B, int K, int H,
                                                         float* __restrict__ draw) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
+    // the number of active keyframes as a device scalar: a captured CUDA graph keeps sampling the frames the mapping thread adds
+    // (clamped to the host-validated capacity K)
+    if (K_dev) K = max(1, min(K, __ldg(K_dev)));
     // pixel_samplers.py:103-106: (rand * [K,H,W]).long()
     // (u < 1 can still round u*K up to K in fp32: the reference then indexes out of bounds; clamped here for memory safety)
     const int64_t c = min((int64_t)__fmul_rn(__ldg(u + 3 * i), (float)K), (int64_t)K - 1);
@@ -271,7 +275,8 @@ __global__ void __launch_bounds__(128) k_pose_grad(int K, int mode, const float*
 
 }  // namespace
 
-extern "C" int nvo_batch_prologue(void* stream, int64_t B, int32_t K, int32_t H, int32_t W, const float* u, const float* intrinsics, const float* extrinsics,
+extern "C" int nvo_batch_prologue(void* stream, int64_t B, int32_t K, const int32_t* K_dev, int32_t H, int32_t W, const float* u, const float* intrinsics,
+                                  const float* extrinsics,
                                   const float* frames_color, const float* frames_depth, const float* frames_normal, const float* pose_adjustment,
                                   int32_t pose_mode, int64_t* indices, int64_t* camera_indices, float* origins, float* directions,
                                   float* directions_norm, float* pixel_area, float* rgb, float* depth, float* normal, float* directions_raw) {
@@ -284,7 +289,7 @@ extern "C" int nvo_batch_prologue(void* stream, int64_t B, int32_t K, int32_t H,
     NVO_CHECK(!frames_normal || normal, "nvo_batch_prologue: frames_normal given without a normal output");
     NVO_CHECK((((uintptr_t)intrinsics | (uintptr_t)extrinsics) & 15) == 0, "nvo_batch_prologue: intrinsics / extrinsics must be 16-byte aligned");
     if (B == 0) return 0;
-    k_batch_prologue<<<nvo_blocks(B, 128), 128, 0, (cudaStream_t)stream>>>(B, K, H, W, u, intrinsics, extrinsics, frames_color, frames_depth, frames_normal,
+    k_batch_prologue<<<nvo_blocks(B, 128), 128, 0, (cudaStream_t)stream>>>(B, K, K_dev, H, W, u, intrinsics, extrinsics, frames_color, frames_depth, frames_normal,
                                                                           pose_adjustment, pose_mode, indices, camera_indices, origins, directions,
                                                                           directions_norm, pixel_area, rgb, depth, normal, directions_raw);
     NVO_CUDA_LAUNCH_CHECK("k_batch_prologue");

@@ -222,7 +222,8 @@ static int exchange_launch(void* stream, int64_t offset, int64_t n, float* m_a, 
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0);
     per_sm = max(per_sm, 1);
     if (ctas_per_sm > 0) per_sm = min(per_sm, (int)ctas_per_sm);
-    if (const char* cap = getenv("NVO_EXCHANGE_CTAS_PER_SM")) per_sm = max(1, min(per_sm, atoi(cap)));
+    static const int cap = nvo_env_int("NVO_EXCHANGE_CTAS_PER_SM", 0);  // read once per process
+    if (cap > 0) per_sm = max(1, min(per_sm, cap));
     const unsigned int grid = (unsigned int)max((int64_t)1, min((int64_t)nvo_sm_count() * per_sm, (items + 255) / 256));
     // An SM's L1 / shared-memory split is fixed while any CTA is resident.  This kernel uses no shared memory, so by default it would
     // configure its SMs with the smallest carve-out and the proposal backward (40 KB of dynamic shared memory per CTA) could not become

@@ -462,8 +462,7 @@ extern "C" int nvo_grid_backward(const nvo_grid_desc* d, void* stream, int64_t n
     cudaStream_t st = (cudaStream_t)stream;
     if (d->out_dtype == NVO_F32_TMF && (reinterpret_cast<size_t>(dy) & 15) == 0 && (reinterpret_cast<size_t>(x) & 15) == 0) {
         // samples per thread and level: 16 (default; measured on a step's own sample positions: 146 -> 121 us), 8, or 0 = the quad kernel
-        const char* e = getenv("NVO_GRID_BWD_RUN");
-        const int run_g = e ? atoi(e) : 16;
+        static const int run_g = nvo_env_int("NVO_GRID_BWD_RUN", 16);  // read once per process
         if (run_g == 8 || run_g == 16) {
             const dim3 gr(nvo_blocks((n + run_g - 1) / run_g, 128), (unsigned int)p.L);
             if (run_g == 8)

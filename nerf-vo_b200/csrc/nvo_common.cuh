@@ -30,6 +30,9 @@ void nvo_count_launch();
 
 static inline unsigned int nvo_blocks(int64_t work, int threads) { return (unsigned int)((work + threads - 1) / threads); }
 
+// experiment switches: callers keep the result in a function-local static, i.e. one getenv per process
+int nvo_env_int(const char* name, int fallback);
+
 // 148 SMs on B200; persistent kernels size their grid from this (queried once)
 int nvo_sm_count();
 

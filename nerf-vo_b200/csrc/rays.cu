@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(32 * RAYS_PER_BLOCK) k_weights_bwd(int64_t B, 
 // smem per warp: cdf[S_in+1], bins[S_in+1]
 __global__ void __launch_bounds__(32 * RAYS_PER_BLOCK) k_pdf_resample(int64_t B, int S_in, int S_out, const float* __restrict__ weights,
                                                                       const float* __restrict__ sdist_in, const float* __restrict__ u_base,
-                                                                      const float* __restrict__ jitter, float anneal, float pad, const float* __restrict__ nears,
+                                                                      const float* __restrict__ jitter, float anneal, const float* __restrict__ anneal_dev, float pad,
+                                                                      const float* __restrict__ nears,
                                                                       const float* __restrict__ fars, float* __restrict__ sdist_out,
                                                                       float* __restrict__ ebins_out, int32_t* __restrict__ inds_out) {
     extern __shared__ float smf[];
@@ -146,6 +147,7 @@ __global__ void __launch_bounds__(32 * RAYS_PER_BLOCK) k_pdf_resample(int64_t B,
     float* cdf = smf + wid * 2 * n_in;
     float* bins = cdf + n_in;
     const float eps = 1e-5f;
+    if (anneal_dev) anneal = __ldg(anneal_dev);  // device scalar: follows the anneal schedule across CUDA-graph replays
     // pass 1: w = pow(w, anneal) + padding ; sum (ray_samplers.py:305-308, :602)
     double sum_d = 0.0;
     for (int i = lane; i < S_in; i += 32) {
@@ -455,14 +457,14 @@ extern "C" int nvo_weights_backward(void* stream, int64_t B, int32_t S, const fl
 }
 
 extern "C" int nvo_pdf_resample(void* stream, int64_t B, int32_t S_in, int32_t S_out, const float* weights, const float* sdist_in, const float* u_base,
-                                const float* jitter, float anneal, float histogram_padding, const float* nears, const float* fars, float* sdist_out,
-                                float* ebins_out, int32_t* inds) {
+                                const float* jitter, float anneal, const float* anneal_dev, float histogram_padding, const float* nears, const float* fars,
+                                float* sdist_out, float* ebins_out, int32_t* inds) {
     NVO_CHECK(B >= 0 && S_in >= 1 && S_in <= MAX_S && S_out >= 1 && S_out <= MAX_S, "pdf_resample: bad shape B=%lld S_in=%d S_out=%d", (long long)B, S_in, S_out);
     if (B == 0) return 0;
     NVO_CHECK(weights && sdist_in && u_base && nears && fars && sdist_out && ebins_out, "pdf_resample: null pointer");
     const size_t smem = sizeof(float) * 2 * (S_in + 1) * RAYS_PER_BLOCK;
     k_pdf_resample<<<ray_blocks(B), 32 * RAYS_PER_BLOCK, smem, (cudaStream_t)stream>>>(B, S_in, S_out, weights, sdist_in, u_base, jitter, anneal,
-                                                                                       histogram_padding, nears, fars, sdist_out, ebins_out, inds);
+                                                                                       anneal_dev, histogram_padding, nears, fars, sdist_out, ebins_out, inds);
     NVO_CUDA_LAUNCH_CHECK("pdf_resample");
     return 0;
 }

@@ -185,6 +185,9 @@ class DynamicDataset(torch.utils.data.Dataset):
     def __init__(self, num_frames: int, frame_height: int, frame_width: int, device=torch.device("cuda:0"), use_normals: bool = True) -> None:
         super().__init__()
         self.device, self.use_normals = torch.device(device), use_normals
+        # device copy of `num_active_frames`: the step prologue reads it, so a captured CUDA graph samples the keyframes inserted
+        # AFTER its capture as well (a by-value kernel argument would freeze the count at capture time)
+        self.num_active_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.num_frames, self.num_active_frames = num_frames, 0
         self.frame_height, self.frame_width = frame_height, frame_width
         self.normalization_matrix = None
@@ -195,6 +198,15 @@ class DynamicDataset(torch.utils.data.Dataset):
         self.frames_depth = torch.zeros((num_frames, frame_height, frame_width, 1), **f)
         self.frames_normal = torch.zeros((num_frames, frame_height, frame_width, 3), **f) if use_normals else None
         self.cameras = Cameras(None, None, None, None, frame_height, frame_width, self.camera_extrinsics[:, :3], self.camera_intrinsics, self.camera_extrinsics)
+
+    @property
+    def num_active_frames(self) -> int:
+        return self._num_active_frames
+
+    @num_active_frames.setter
+    def num_active_frames(self, n: int) -> None:
+        self._num_active_frames = int(n)
+        self.num_active_dev.fill_(int(n))
 
     def __len__(self) -> int:
         return self.num_active_frames if self.num_active_frames > 0 else self.num_frames
@@ -268,6 +280,7 @@ class DynamicDataManager:
         self.train_ray_generator = RayGenerator(self.train_dataset.cameras.to(self.device))
         self.camera_optimizer: Optional[CameraOptimizer] = None  # NerfactoModel owns it in the reference (nerfacto.py:171); attach to fuse
         self._u: Optional[torch.Tensor] = None
+        self._last_camera_indices: Optional[torch.Tensor] = None
 
     def get_train_rays_per_batch(self) -> int:
         return self.config.train_num_rays_per_batch
@@ -285,9 +298,11 @@ class DynamicDataManager:
         co = self.camera_optimizer
         pose = co.pose_adjustment if co is not None and co.config.mode != "off" else None
         out = ops.batch_prologue(u, ds.num_active_frames, ds.camera_intrinsics, ds.camera_extrinsics, ds.frames_color, ds.frames_depth,
-                                 ds.frames_normal if ds.use_normals else None, pose, co.mode_id if pose is not None else 0)
+                                 ds.frames_normal if ds.use_normals else None, pose, co.mode_id if pose is not None else 0,
+                                 num_active_dev=ds.num_active_dev)
         rb = RayBundle(origins=out["origins"], directions=out["directions"], pixel_area=out["pixel_area"], camera_indices=out["camera_indices"],
                        metadata={"directions_norm": out["directions_norm"]})
+        self._last_camera_indices = out["camera_indices"]  # under a CUDA graph: refreshed by every replay (diagnostics / tests)
         batch = {"indices": out["indices"], "image": out["image"], "depth_image": out["depth_image"]}
         if ds.use_normals:
             batch["normal_image"] = out["normal_image"]

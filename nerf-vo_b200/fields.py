@@ -242,8 +242,57 @@ class NerfactoField(Field):
         return normals.view(*c["shape"], 3)
 
     # -- colour / predicted normals -------------------------------------------------------------------------
+    def _appearance(self, ray_samples: RaySamples, B: int, device):
+        """(camera indices [B] | None, embedding table | mean vector): nerfacto_field.py:236-251."""
+        if self.training:
+            return ray_samples.camera_indices.reshape(B).long().contiguous(), self.embedding_appearance.embedding.weight
+        if self.use_average_appearance_embedding:
+            return None, self.embedding_appearance.mean(dim=0)
+        return None, torch.zeros(self.appearance_embedding_dim, device=device)
+
+    def _heads(self, h, sel, positions, dirs, cam, emb, B: int, S: int) -> Dict[FieldHeadNames, torch.Tensor]:
+        """Input assembly (SH | geo | appearance, posenc | geo) -> mlp_head -> rgb, mlp_pred_normals + head -> pred_normals, and
+        density = trunc_exp(h0) * selector, from the base network's output h [n,16] (nerfacto_field.py:225-297)."""
+        out: Dict[FieldHeadNames, torch.Tensor] = {}
+        pn_params = ()
+        if self.use_pred_normals:
+            pn_params = self.mlp_pred_normals._flat_param_list() + [self.field_head_pred_normals.net.weight, self.field_head_pred_normals.net.bias]
+            repack(pn_params)
+        if self.precision == "fp16":
+            self.mlp_head._repack()
+            density, rgb, pn = ops.field_heads_tc(h, emb, sel, dirs, positions.reshape(-1, 3), cam, B, S, self.mlp_head.spec,
+                                                  self.mlp_head._flat_param_list(), self._pn_spec if self.use_pred_normals else None, pn_params)
+            if pn is not None:
+                out[FieldHeadNames.PRED_NORMALS] = pn.view(B, S, 3)
+            out[FieldHeadNames.RGB] = rgb.view(B, S, 3)
+            out[FieldHeadNames.DENSITY] = density.view(B, S, 1)
+            return out
+        density, head_in, pn_in = ops.field_assemble(h, emb, sel, dirs, positions.reshape(-1, 3), cam, B, S, self.use_pred_normals)
+        if self.use_pred_normals:
+            pn = ops.mlp_apply(pn_in, self._pn_spec, pn_params)
+            out[FieldHeadNames.PRED_NORMALS] = ops.normalize3(pn, 1.0, 1e-12).view(B, S, 3)
+        out[FieldHeadNames.RGB] = self.mlp_head(head_in).view(B, S, 3)
+        out[FieldHeadNames.DENSITY] = density.view(B, S, 1)
+        return out
+
     def get_outputs(self, ray_samples: RaySamples, density_embedding: Optional[torch.Tensor] = None) -> Dict[FieldHeadNames, torch.Tensor]:
-        raise NotImplementedError("use forward(): density, colour and normals are evaluated by one fused pipeline")
+        """NerfactoField.get_outputs (NS/fields/nerfacto_field.py:225-297; contract NS/fields/base_field.py:104-112): colour and predicted
+        normals from the ray samples and the geometry features get_density() returned.  The base class calls it right after get_density
+        (base_field.py:114-133); forward() below runs the same kernels as one pipeline that also produces the density."""
+        assert density_embedding is not None
+        if ray_samples.camera_indices is None:
+            raise AttributeError("Camera indices are not provided.")
+        fr = ray_samples.frustums
+        B, S = fr.shape
+        n = B * S
+        geo = density_embedding.reshape(n, self.geo_feat_dim)
+        # h = [raw density | geo]: the raw-density column only feeds the density output, which this call does not return
+        h = torch.cat([torch.zeros((n, 1), dtype=geo.dtype, device=geo.device), geo], dim=1)
+        sel = torch.ones(n, dtype=torch.float32, device=geo.device)
+        cam, emb = self._appearance(ray_samples, B, geo.device)
+        out = self._heads(h, sel, fr.get_positions(), fr.directions.reshape(B, 3).contiguous(), cam, emb, B, S)
+        out.pop(FieldHeadNames.DENSITY)
+        return out
 
     def forward(self, ray_samples: RaySamples, compute_normals: bool = False) -> Dict[FieldHeadNames, torch.Tensor]:
         if ray_samples.camera_indices is None:
@@ -255,55 +304,21 @@ class NerfactoField(Field):
         h, tc = self._base(x, want_normals=compute_normals)
         self._remember(x, h, (B, S), tc)
         dirs = fr.directions.reshape(B, 3).contiguous()
-        if self.training:
-            cam = ray_samples.camera_indices.reshape(B).long().contiguous()
-            emb = self.embedding_appearance.embedding.weight
-        else:
-            cam = None
-            if self.use_average_appearance_embedding:
-                emb = self.embedding_appearance.mean(dim=0)
-            else:
-                emb = torch.zeros(self.appearance_embedding_dim, device=dirs.device)
-        out: Dict[FieldHeadNames, torch.Tensor] = {}
-        if self.precision == "fp16":
-            import os
-
-            normals = side_n = None
-            if compute_normals and ops.leaf_streams.enabled and x.is_cuda and os.environ.get("NVO_FIELD_BRANCHES", "1") == "1":
-                # density-gradient normals (base network's input-gradient chain + saved-Jacobian product) depend on the base network only:
-                # they run on their own stream next to the colour / predicted-normals heads and are joined before the renderer reads them
-                main = torch.cuda.current_stream()
-                side_n = ops.leaf_streams.branch_streams[0]
-                side_n.wait_stream(main)
-                with torch.cuda.stream(side_n):
-                    normals = self.get_normals()
-            self.mlp_head._repack()
-            pn_spec, pn_params = None, ()
-            if self.use_pred_normals:
-                pn_params = self.mlp_pred_normals._flat_param_list() + [self.field_head_pred_normals.net.weight, self.field_head_pred_normals.net.bias]
-                repack(pn_params)
-                pn_spec = self._pn_spec
-            density, rgb, pn = ops.field_heads_tc(h, emb, sel, dirs, positions.reshape(-1, 3), cam, B, S, self.mlp_head.spec,
-                                                  self.mlp_head._flat_param_list(), pn_spec, pn_params)
-            if pn is not None:
-                out[FieldHeadNames.PRED_NORMALS] = pn.view(B, S, 3)
-            out[FieldHeadNames.RGB] = rgb.view(B, S, 3)
-            out[FieldHeadNames.DENSITY] = density.view(B, S, 1)
-            if side_n is not None:
-                main.wait_stream(side_n)
-                normals.record_stream(main)
-                out[FieldHeadNames.NORMALS] = normals
-            elif compute_normals:
-                out[FieldHeadNames.NORMALS] = self.get_normals()
-            return out
-        density, head_in, pn_in = ops.field_assemble(h, emb, sel, dirs, positions.reshape(-1, 3), cam, B, S, self.use_pred_normals)
-        if self.use_pred_normals:
-            params = self.mlp_pred_normals._flat_param_list() + [self.field_head_pred_normals.net.weight, self.field_head_pred_normals.net.bias]
-            repack(params)
-            pn = ops.mlp_apply(pn_in, self._pn_spec, params)
-            out[FieldHeadNames.PRED_NORMALS] = ops.normalize3(pn, 1.0, 1e-12).view(B, S, 3)
-        out[FieldHeadNames.RGB] = self.mlp_head(head_in).view(B, S, 3)
-        out[FieldHeadNames.DENSITY] = density.view(B, S, 1)
-        if compute_normals:
+        cam, emb = self._appearance(ray_samples, B, dirs.device)
+        normals = side_n = None
+        if self.precision == "fp16" and compute_normals and ops.leaf_streams.enabled and x.is_cuda and ops.env_flag("NVO_FIELD_BRANCHES", True):
+            # density-gradient normals (base network's input-gradient chain + saved-Jacobian product) depend on the base network only:
+            # they run on their own stream next to the colour / predicted-normals heads and are joined before the renderer reads them
+            main = torch.cuda.current_stream()
+            side_n = ops.leaf_streams.branch_streams[0]
+            side_n.wait_stream(main)
+            with torch.cuda.stream(side_n):
+                normals = self.get_normals()
+        out = self._heads(h, sel, positions, dirs, cam, emb, B, S)
+        if side_n is not None:
+            main.wait_stream(side_n)
+            normals.record_stream(main)
+            out[FieldHeadNames.NORMALS] = normals
+        elif compute_normals:
             out[FieldHeadNames.NORMALS] = self.get_normals()
         return out

@@ -13,6 +13,17 @@ import torch
 from . import _lib
 from ._lib import call, check
 
+_env_cache: dict = {}
+
+
+def env_flag(name: str, default: bool) -> bool:
+    """Experiment switch read from the environment ONCE per process, not on every step."""
+    if name not in _env_cache:
+        v = os.environ.get(name)
+        _env_cache[name] = default if v is None else v == "1"
+    return _env_cache[name]
+
+
 # ------------------------------------------------------------------------------------------------
 # side streams for gradient-leaf kernels
 # ------------------------------------------------------------------------------------------------
@@ -410,7 +421,7 @@ class _PropDensity(torch.autograd.Function):
         ddensity = ddensity.contiguous()
         args = ("nvo_prop_density_backward", ctx.gspec.desc(table.dtype, torch.float32), ctx.hidden, ctx.slot, ctx.B, ctx.S, origins, directions, s, e, stride, positions,
                 flat, feat, ddensity, dtable, dflat)
-        split = need_dt and os.environ.get("NVO_PROP_BWD_SPLIT", "1") == "1"
+        split = need_dt and env_flag("NVO_PROP_BWD_SPLIT", True)
 
         def run():
             if not split:
@@ -674,9 +685,10 @@ def weights_from_density(density, iv: Intervals):
     return _Weights.apply(density, iv)
 
 
-def pdf_resample(weights, sdist_in, num_samples: int, nears, fars, jitter=None, anneal: float = 1.0, histogram_padding: float = 0.01,
+def pdf_resample(weights, sdist_in, num_samples: int, nears, fars, jitter=None, anneal=1.0, histogram_padding: float = 0.01,
                  return_inds: bool = False):
-    """-> (sdist_out [B,S_out+1], ebins_out [B,S_out+1][, inds int32 [B,S_out+1]]); no gradient (the reference detaches)."""
+    """-> (sdist_out [B,S_out+1], ebins_out [B,S_out+1][, inds int32 [B,S_out+1]]); no gradient (the reference detaches).
+    anneal: python float, or a device float32 [1] tensor the kernel reads (graph-replayable anneal schedule)."""
     B, S_in = weights.shape
     dev = weights.device
     weights = check(weights.detach().contiguous(), "weights", torch.float32, (B, S_in))
@@ -695,7 +707,11 @@ def pdf_resample(weights, sdist_in, num_samples: int, nears, fars, jitter=None, 
     sdist = torch.empty((B, n), dtype=torch.float32, device=dev)
     ebins = torch.empty_like(sdist)
     inds = torch.empty((B, n), dtype=torch.int32, device=dev) if return_inds else None
-    call("nvo_pdf_resample", B, S_in, num_samples, weights, sdist_in, u, jitter, float(anneal), float(histogram_padding), nears, fars, sdist, ebins, inds)
+    anneal_dev = None
+    if isinstance(anneal, torch.Tensor):
+        anneal_dev, anneal = check(anneal, "anneal", torch.float32, (1,)), 1.0
+    call("nvo_pdf_resample", B, S_in, num_samples, weights, sdist_in, u, jitter, float(anneal), anneal_dev, float(histogram_padding), nears, fars, sdist,
+         ebins, inds)
     return (sdist, ebins, inds) if return_inds else (sdist, ebins)
 
 
@@ -1290,7 +1306,7 @@ class _FieldHeadsTC(torch.autograd.Function):
             return flat, raw, sv, out
 
         head_flat = tc_pack_weights(_flat_of(head_params), head_spec)
-        if want_pn and leaf_streams.enabled and os.environ.get("NVO_FIELD_BRANCHES", "1") == "1":
+        if want_pn and leaf_streams.enabled and env_flag("NVO_FIELD_BRANCHES", True):
             # the predicted-normals network only shares its input assembly with the colour head: issue it on its own stream
             main = torch.cuda.current_stream()
             side = leaf_streams.branch_streams[1]
@@ -1367,9 +1383,11 @@ def _check_cameras(intrinsics, extrinsics):
 
 
 def batch_prologue(u, num_active: int, intrinsics, extrinsics, frames_color, frames_depth, frames_normal=None, pose_adjustment=None, pose_mode: int = 0,
-                   want_raw_directions: bool = False):
+                   want_raw_directions: bool = False, num_active_dev=None):
     """One launch of nvo_batch_prologue (include/nvo_b200.h): returns a dict with indices / camera_indices (int64), origins, directions,
-    directions_norm, pixel_area, image, depth_image, normal_image (when frames_normal is given) [, directions_raw]."""
+    directions_norm, pixel_area, image, depth_image, normal_image (when frames_normal is given) [, directions_raw].
+    num_active_dev: device int32 [1] holding the number of active frames; the kernel then reads the count from it (clamped to the frame
+    capacity), so a CUDA graph captured around this call keeps following keyframe insertions."""
     check(u, "uniform draws", torch.float32, (None, 3))
     _check_cameras(intrinsics, extrinsics)
     K_alloc, H, W, _ = frames_color.shape
@@ -1384,6 +1402,9 @@ def batch_prologue(u, num_active: int, intrinsics, extrinsics, frames_color, fra
         if pose_adjustment.shape[0] < num_active:
             raise RuntimeError("pose_adjustment has fewer rows than active cameras")
     B, dev = u.shape[0], u.device
+    if num_active_dev is not None:
+        check(num_active_dev, "num_active_dev", torch.int32, (1,))
+        num_active = min(K_alloc, intrinsics.shape[0], extrinsics.shape[0], pose_adjustment.shape[0] if pose_mode != 0 else K_alloc)  # capacity bound
     f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
     out = {"indices": torch.empty((B, 3), dtype=torch.int64, device=dev), "camera_indices": torch.empty((B, 1), dtype=torch.int64, device=dev),
            "origins": f(B, 3), "directions": f(B, 3), "directions_norm": f(B, 1), "pixel_area": f(B, 1), "image": f(B, 3), "depth_image": f(B, 1)}
@@ -1391,7 +1412,7 @@ def batch_prologue(u, num_active: int, intrinsics, extrinsics, frames_color, fra
         out["normal_image"] = f(B, 3)
     if want_raw_directions:
         out["directions_raw"] = f(B, 3)
-    call("nvo_batch_prologue", B, num_active, H, W, u, intrinsics, extrinsics, frames_color, frames_depth, frames_normal,
+    call("nvo_batch_prologue", B, num_active, num_active_dev, H, W, u, intrinsics, extrinsics, frames_color, frames_depth, frames_normal,
          pose_adjustment.detach() if pose_mode != 0 else None, pose_mode, out["indices"], out["camera_indices"], out["origins"], out["directions"],
          out["directions_norm"], out["pixel_area"], out["image"], out["depth_image"], out.get("normal_image"), out.get("directions_raw"))
     return out

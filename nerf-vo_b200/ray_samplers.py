@@ -105,11 +105,22 @@ class ProposalNetworkSampler(Sampler):
         self.initial_sampler = initial_sampler if initial_sampler is not None else UniformLinDispPiecewiseSampler(single_jitter=single_jitter)
         self.pdf_sampler = pdf_sampler if pdf_sampler is not None else PDFSampler(include_original=False, single_jitter=single_jitter)
         self._anneal = 1.0
+        self._anneal_dev: Optional[torch.Tensor] = None
         self._steps_since_update = 0
         self._step = 0
 
     def set_anneal(self, anneal: float) -> None:
+        changed = float(anneal) != float(self._anneal)
         self._anneal = anneal
+        if self._anneal_dev is not None and changed:  # past the anneal window the value stays 1.0: no launch
+            self._anneal_dev.fill_(float(anneal))
+
+    def use_device_anneal(self, device) -> torch.Tensor:
+        """Keeps the anneal value in a device scalar the resampling kernel reads: a CUDA graph captured around the sampler then follows
+        set_anneal() on every replay (as a by-value kernel argument it would stay frozen at its capture-time value)."""
+        if self._anneal_dev is None or self._anneal_dev.device != torch.device(device):
+            self._anneal_dev = torch.full((1,), float(self._anneal), dtype=torch.float32, device=device)
+        return self._anneal_dev
 
     def step_cb(self, step):
         self._step = step
@@ -130,7 +141,8 @@ class ProposalNetworkSampler(Sampler):
                 ray_samples = self.initial_sampler(ray_bundle, num_samples=num_samples, jitter=jit)
             else:
                 # the anneal pow (ray_samplers.py:602) is applied inside the resampling kernel
-                ray_samples = self.pdf_sampler(ray_bundle, ray_samples, weights, num_samples=num_samples, jitter=jit, anneal=self._anneal)
+                ray_samples = self.pdf_sampler(ray_bundle, ray_samples, weights, num_samples=num_samples, jitter=jit,
+                                               anneal=self._anneal_dev if self._anneal_dev is not None else self._anneal)
             if is_prop:
                 fn = density_fns[i_level]
                 owner = getattr(fn, "__self__", None)

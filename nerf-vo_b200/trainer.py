@@ -35,11 +35,14 @@ from .rays import RayBundle
 class MappingTrainer:
     def __init__(self, model: ExtendedNerfactoModel, num_rays: int, lr: float = 1e-2, eps: float = 1e-15, betas=(0.9, 0.999),
                  use_cuda_graph: bool = True, with_normals: bool = True, device: Optional[torch.device] = None, exchange: str = "fused",
-                 datamanager=None, proposal_update: str = "always"):
+                 datamanager=None, proposal_update: str = "always", external_draws: bool = False):
         self.model = model
         # optional: a DynamicDataManager (data.py). The step then starts with the fused prologue kernel (pixel sampling + gather + ray
         # generation, drawn on the device like the reference's torch.rand) instead of reading the static input buffers.
         self.datamanager = datamanager
+        # external_draws: the step's random numbers (pixel draws u [B,3], the three stratified jitters) come from the caller through
+        # set_draws_packed() instead of being drawn on the device inside the step — a reproducible run, or a host that owns the RNG
+        self.external_draws = bool(external_draws)
         self.device = device or next(model.parameters()).device
         self.B = int(num_rays)
         self.lr, self.eps, self.betas = lr, eps, betas
@@ -53,7 +56,8 @@ class MappingTrainer:
         if proposal_update not in ("always", "reference"):
             raise ValueError(f"proposal_update must be 'always' or 'reference', got {proposal_update!r}")
         self.proposal_update = proposal_update
-        self.iteration = 0  # host-side step number (drives the proposal update schedule)
+        self.iteration = 0  # host-side step number (drives the proposal update schedule and the proposal-weight annealing)
+        self._ssu = 0       # ProposalNetworkSampler._steps_since_update as the reference's callbacks would leave it
         model.train()
         # ---- flat parameter / gradient / optimizer-state buffers ---------------------------------------------
         self.params = [p for p in model.parameters() if p.requires_grad]
@@ -101,12 +105,21 @@ class MappingTrainer:
             p.data = self.flat[off:off + p.numel()].view(p.shape)
             self._views.append((off, p.numel()))
             off += n
+        if self.world_size > 1:
+            # DistributedDataParallel broadcasts rank 0's parameters at construction (NS/pipelines/base_pipeline.py:281-283): replicas must
+            # not depend on every caller seeding identically.  The draws made on the device afterwards (pixel sampling, stratified jitter)
+            # get a rank-dependent stream instead, as the reference seeds each process with seed + rank (NS/scripts/train.py:97) — with
+            # identical streams every rank would train on the same pixels.
+            dist.broadcast(self.flat, 0)
+            if self.device.type == "cuda":
+                with torch.cuda.device(self.device):
+                    torch.cuda.manual_seed(torch.initial_seed() + 7919 * dist.get_rank())
         self._attach_main_grads()
         # ---- static inputs ---------------------------------------------------------------------------------------
         B, dev = self.B, self.device
         # every fp32 input is a view of ONE staging buffer, so a batch packed on the host (pack_host_batch) arrives with a single copy
         self._float_layout = [("origins", 3), ("directions", 3), ("directions_norm", 1), ("pixel_area", 1), ("rgb", 3), ("depth", 1), ("normal", 3),
-                              ("jitter0", 1), ("jitter1", 1), ("jitter2", 1)]
+                              ("jitter0", 1), ("jitter1", 1), ("jitter2", 1), ("u", 3)]
         self._float_offsets, off = {}, 0
         for name, c in self._float_layout:  # every block starts on a 16-byte boundary (vector loads), whatever B is
             self._float_offsets[name] = off
@@ -115,6 +128,8 @@ class MappingTrainer:
         self.inputs = {name: self._staging[self._float_offsets[name]:self._float_offsets[name] + B * c].view(B, c) for name, c in self._float_layout}
         self.inputs["camera_indices"] = torch.zeros((B, 1), dtype=torch.int64, device=dev)
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        # proposal-weight annealing (NS/models/nerfacto.py:256-278): a device scalar the resampling kernel reads, set before every step
+        self._anneal_dev = model.proposal_sampler.use_device_anneal(dev) if dev.type == "cuda" else None
         self._terms: Dict[str, torch.Tensor] = {}
         self._term_weights: Dict[str, float] = {}
         if self.device.type == "cuda" and not ops.leaf_streams.enabled:
@@ -186,11 +201,13 @@ class MappingTrainer:
         else:
             self.grad.zero_()
         if self.datamanager is not None:
-            bundle, batch = self.datamanager.next_train(0)  # DynamicDataManager.next_train (nerfstudio_utils.py:295-300)
+            # DynamicDataManager.next_train (nerfstudio_utils.py:295-300): pixel draws on the device unless the caller supplies them
+            bundle, batch = self.datamanager.next_train(0, u=i["u"] if self.external_draws else None)
             if not self.with_normals:
                 batch.pop("normal_image", None)
-            for k in range(3):
-                i[f"jitter{k}"].uniform_()  # the samplers' torch.rand (ray_samplers.py:115,330), on the device
+            if not self.external_draws:
+                for k in range(3):
+                    i[f"jitter{k}"].uniform_()  # the samplers' torch.rand (ray_samplers.py:115,330), on the device
         else:
             bundle = self._bundle()
             batch = {"image": i["rgb"], "depth_image": i["depth"]}
@@ -319,10 +336,29 @@ class MappingTrainer:
             src[f"jitter{k}"] = jitters[k]
         flat = torch.zeros(self._staging.numel(), dtype=torch.float32).pin_memory()
         for name, c in self._float_layout:
+            if name not in src:
+                continue  # "u": pixel draws of the dataset-fed step (pack_host_draws)
             off = self._float_offsets[name]
             flat[off:off + self.B * c].copy_(src[name].reshape(-1).float())
         cam = src["camera_indices"].reshape(self.B, 1).to(torch.int64).contiguous().pin_memory()
         return flat, cam
+
+    def pack_host_draws(self, u: torch.Tensor, jitters: List[torch.Tensor]) -> torch.Tensor:
+        """The random numbers of one dataset-fed step (pixel draws u [B,3], three jitters [B,1]) as ONE pinned host tensor in the staging
+        layout, for set_draws_packed()."""
+        base = self._float_offsets["jitter0"]
+        flat = torch.zeros(self._staging.numel() - base, dtype=torch.float32).pin_memory()
+        src = {"u": u, "jitter0": jitters[0], "jitter1": jitters[1], "jitter2": jitters[2]}
+        for name, c in self._float_layout:
+            if name in src:
+                off = self._float_offsets[name] - base
+                flat[off:off + self.B * c].copy_(src[name].reshape(-1).float())
+        return flat
+
+    def set_draws_packed(self, packed: torch.Tensor, non_blocking: bool = True) -> int:
+        """One host-to-device copy: the draws of the next step (external_draws=True).  Returns the bytes copied."""
+        self._staging[self._float_offsets["jitter0"]:].copy_(packed, non_blocking=non_blocking)
+        return packed.numel() * 4
 
     def set_inputs_packed(self, packed, non_blocking: bool = True) -> int:
         """Two host-to-device copies for the whole batch; returns the bytes copied."""
@@ -342,8 +378,11 @@ class MappingTrainer:
         prio = -1 if os.environ.get("NVO_MAIN_PRIORITY", "1") == "1" else 0
         s = torch.cuda.Stream(priority=prio)
         s.wait_stream(torch.cuda.current_stream())
-        self._ssu = 0
         modes = [True] if self.proposal_update == "always" else [True, False]
+        # The warm-up (and the capture itself, which executes nothing) runs REAL steps on whatever sits in the input buffers: parameters,
+        # Adam moments and the device step counters are snapshotted here and restored afterwards, so capture() is free of side effects
+        # on the training state (it may be called on a fresh model or right after load_checkpoint()).
+        state = self._snapshot_state()
         with torch.cuda.stream(s):
             for _ in range(warmup):
                 for upd in modes:
@@ -353,6 +392,7 @@ class MappingTrainer:
                     self._optimizer(upd)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        self._restore_state(state)
         if not self.use_cuda_graph:
             return
         self._graphs = {}
@@ -374,9 +414,60 @@ class MappingTrainer:
                 self.launches_per_step = _lib.launch_count() - n0
         self._graph_fb, self._graph_opt = self._graphs[True]
 
+    def _moment_tensors(self) -> List[torch.Tensor]:
+        if self.peer is not None:
+            return [t for gid in self._peer_groups for t in self.peer.group_moments(gid)]
+        return [self.exp_avg, self.exp_avg_sq]
+
+    def full_moments(self):
+        """(exp_avg, exp_avg_sq) over the whole flat buffer.  Local / NCCL arms: the buffers themselves.  Fused arm: every rank holds only
+        its slice of each group, so this is a COLLECTIVE (every rank must call it) that all-gathers the slices."""
+        if self.peer is None:
+            return self.exp_avg, self.exp_avg_sq
+        from .peer import slice_range
+
+        W = self.world_size
+        outs = [torch.zeros(self.flat.numel(), dtype=torch.float32, device=self.device) for _ in range(2)]
+        for gid, (_, off, n) in zip(self._peer_groups, self.groups):
+            chunk = slice_range(n, 0, W)[1]
+            for j, t in enumerate(self.peer.group_moments(gid)):
+                full = torch.empty(chunk * W, dtype=torch.float32, device=self.device)
+                dist.all_gather_into_tensor(full, t[:chunk].contiguous())
+                outs[j][off:off + n] = full[:n]
+        return outs[0], outs[1]
+
+    def load_full_moments(self, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor) -> None:
+        """Inverse of full_moments(): every rank keeps (its slice of) the given whole-buffer Adam moments."""
+        if self.peer is None:
+            self.exp_avg.copy_(exp_avg)
+            self.exp_avg_sq.copy_(exp_avg_sq)
+            return
+        from .peer import slice_range
+
+        for gid, (_, off, n) in zip(self._peer_groups, self.groups):
+            lo, hi = slice_range(n, self.peer.rank, self.world_size)
+            for t, src in zip(self.peer.group_moments(gid), (exp_avg, exp_avg_sq)):
+                t[:hi - lo].copy_(src[off + lo:off + hi])
+
+    def _snapshot_state(self):
+        return ([t.clone() for t in [self.flat] + self._moment_tensors() + self.step_counts], self.iteration, self._ssu,
+                self.model.proposal_sampler._step, self.model.proposal_sampler._steps_since_update)
+
+    def _restore_state(self, state) -> None:
+        tensors, self.iteration, self._ssu, ps_step, ps_ssu = state
+        with torch.no_grad():
+            for dst, src in zip([self.flat] + self._moment_tensors() + self.step_counts, tensors):
+                dst.copy_(src)
+        self.model.proposal_sampler._step, self.model.proposal_sampler._steps_since_update = ps_step, ps_ssu
+        if self.world_size > 1:
+            torch.cuda.synchronize()
+            dist.barrier()  # fused arm: a peer must not start exchanging into replicas another rank is still restoring
+
     def train_step(self) -> torch.Tensor:
         """Runs one step on the current contents of the static input buffers; returns the (device) loss scalar."""
-        upd = self._updated_now() if hasattr(self, "_ssu") else True
+        upd = self._updated_now()
+        # the reference's per-iteration callbacks: set_anneal before the step (a device scalar: graph replays read it)
+        self.model.before_train_iteration(self.iteration)
         if self._graph_fb is not None:
             g_fb, g_opt = self._graphs[upd]
             g_fb.replay()
@@ -393,7 +484,6 @@ class MappingTrainer:
             self._optimizer(upd)
             self.launches_per_step = _lib.launch_count() - n0
         # ProposalNetworkSampler.step_cb + the reset in generate_ray_samples (ray_samplers.py:591-594,611-612)
-        if hasattr(self, "_ssu"):
-            self._ssu = 1 if upd else self._ssu + 1
+        self._ssu = 1 if upd else self._ssu + 1
         self.iteration += 1
         return self.loss

@@ -1,0 +1,287 @@
+"""Oracle parity at BASELINE.json's FULL sizes: the CPU oracle (oracle/nerfacto_oracle.py, pinned to the live reference by
+tests/test_oracle_vs_reference.py) runs beside the CUDA path on the same seeded inputs, through the same public model / trainer API the step uses.
+
+  * config 2 exactly: 4096 rays x (256/96 + 48) samples, 16 x 2^19 main table, 2 x (5 x 2^17) proposal tables, fp32 AND fp16 precision: rendered
+    outputs, the five losses, every parameter gradient;
+  * config 4's table: the same step with the 2^21-row main table;
+  * config 3's batch: 65 536 rays, forward + losses (the oracle's backward at this size is minutes of index_put), gradients on an 8192-ray batch;
+  * a 16-step TRAJECTORY of MappingTrainer (eager and CUDA graph; annealing + the reference's proposal update schedule) against the oracle stepped
+    by torch.optim.Adam (NS/engine/optimizers.py:138-150: one Adam per group, eps 1e-15);
+  * nvo_adam_step against torch.optim.Adam directly;
+  * the PDF-sampler searchsorted mismatch rate (fp64 vs fp32 normaliser ties, csrc/rays.cu) on a config-2 batch.
+
+Tolerances are the contract of DESIGN.md section 4 and are written next to each assert.  Every measured error is appended to
+gpurun_out/parity_fullsize.json so the numbers quoted in DESIGN.md come from the run itself."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import nerfacto_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPORT = os.path.join(ROOT, "gpurun_out", "parity_fullsize.json")
+
+
+def _record(case: str, values: dict) -> None:
+    os.makedirs(os.path.dirname(REPORT), exist_ok=True)
+    data = {}
+    if os.path.exists(REPORT):
+        try:
+            data = json.load(open(REPORT))
+        except ValueError:
+            data = {}
+    data[case] = values
+    json.dump(data, open(REPORT, "w"), indent=1, sort_keys=True)
+
+
+def _setup(nv, main_log2: int, prop_log2: int, K: int, precision: str, B: int, seed: int = 0, table_std: float = 0.1):
+    """Oracle parameters (reference keys, 'trained-like' tables N(0, 0.1): densities vary over orders of magnitude) loaded into the CUDA model."""
+    ocfg = O.ModelCfg(main_grid=O.GridCfg(log2_hashmap_size=main_log2), prop_grids=(O.GridCfg(5, 16, 128, prop_log2), O.GridCfg(5, 16, 256, prop_log2)),
+                      num_images=K)
+    P = O.init_params(ocfg, seed=seed, table_std=table_std)
+    cfg = nv.NerfactoModelConfig(log2_hashmap_size=main_log2, precision=precision)
+    for a in cfg.proposal_net_args_list:
+        a["log2_hashmap_size"] = prop_log2
+    m = nv.ExtendedNerfactoModel(cfg, num_train_data=K)
+    missing, unexpected = m.load_state_dict(P, strict=False)
+    assert not unexpected, unexpected
+    assert all(k.endswith(("aabb", "max_res", "num_levels", "log2_hashmap_size", "mlp_base.0.hash_table")) for k in missing), missing
+    m = m.to(DEV).train()
+    rays, targets = O.synthetic_rays(B, num_images=K, seed=1234)
+    jit = O.synthetic_jitters(B, seed=99)
+    rb = nv.RayBundle(origins=rays["origins"].to(DEV), directions=rays["directions"].to(DEV), pixel_area=rays["pixel_area"].to(DEV),
+                      camera_indices=rays["camera_indices"].to(DEV), metadata={"directions_norm": rays["directions_norm"].to(DEV)})
+    batch = {"image": targets["rgb"].to(DEV), "depth_image": targets["depth"].to(DEV), "normal_image": targets["normal"].to(DEV)}
+    return ocfg, P, m, rays, targets, jit, rb, batch
+
+
+def _compare_outputs(outputs, oout):
+    """max-abs errors of the rendered maps; normals as the fraction of rays further than 2e-3 (piecewise-constant per grid cell, see
+    test_gpu_parity.test_model_step_golden); median depths as the fraction of rays whose searchsorted index moved."""
+    e = {}
+    for k in ("rgb", "accumulation", "pred_normals"):
+        e[k] = float((outputs[k].detach().cpu().reshape(oout[k].shape) - oout[k].detach()).abs().max())
+    ed, od = outputs["expected_depth"].detach().cpu().reshape(-1), oout["expected_depth"].detach().reshape(-1)
+    e["expected_depth_rel"] = float(((ed - od).abs() / od.abs().clamp_min(1e-6)).max())
+    nerr = (outputs["normals"].detach().cpu() - oout["normals"].detach()).abs().max(dim=-1)[0]
+    e["normals_frac_gt_2e-3"] = float((nerr > 2e-3).float().mean())
+    for k in ("depth", "prop_depth_0", "prop_depth_1"):
+        e[k + "_frac_moved"] = float(((outputs[k].cpu().reshape(-1) - oout[k].reshape(-1)).abs() > 1e-5).float().mean())
+    for i in range(3):
+        w = outputs["weights_list"][i][..., 0].detach().cpu()
+        e[f"weights{i}"] = float((w - oout["weights_list"][i].detach()).abs().max())
+    return e
+
+
+def _compare_losses(loss_dict, oL):
+    return {k: abs(float(v) - float(oL[k])) / max(abs(float(oL[k])), 1e-12) for k, v in loss_dict.items()}
+
+
+def _compare_grads(m, Pg):
+    e = {}
+    for name, p in m.named_parameters():
+        if name not in Pg:
+            continue  # proposal_networks.k.mlp_base.0.hash_table aliases encoding.hash_table
+        ref = Pg[name].grad
+        ref = torch.zeros_like(Pg[name]) if ref is None else ref
+        got = p.grad.detach().cpu() if p.grad is not None else torch.zeros_like(ref)
+        e[name] = float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+    return e
+
+
+def _full_step(nv, main_log2, prop_log2, precision, B, K=192, backward=True):
+    ocfg, P, m, rays, targets, jit, rb, batch = _setup(nv, main_log2, prop_log2, K, precision, B)
+    outputs, loss_dict, _ = m.get_train_loss_dict(rb, batch, [j.to(DEV) for j in jit])
+    if backward:
+        sum(loss_dict.values()).backward()
+    torch.cuda.synchronize()
+    torch.set_num_threads(os.cpu_count() or 1)
+    Pg = {k: v.clone().requires_grad_(backward) for k, v in P.items()}
+    if backward:
+        oout, oL, _ = O.mapping_step(Pg, ocfg, rays, targets, jit)
+    else:
+        with torch.no_grad():
+            oout = O.mapping_forward(Pg, ocfg, rays["origins"], rays["directions"], rays["camera_indices"], jit, 1.0, True, True)
+            oL = O.mapping_losses(ocfg, oout, targets["rgb"], targets["depth"], rays["directions_norm"], targets["normal"])
+    # bit-exact integer work on the way: level-0 sample placement, PDF indices up to fp ties (reported)
+    assert torch.equal(outputs["ray_samples_list"][0].sdist().cpu(), oout["sdist_list"][0])
+    res = {"outputs": _compare_outputs(outputs, oout), "losses": _compare_losses(loss_dict, oL)}
+    if backward:
+        res["grads"] = _compare_grads(m, Pg)
+    return res
+
+
+# tolerance contracts.  fp32 = exact-arithmetic SIMT kernels; fp16 = production (tcgen05, fp16 operands / fp32 accumulate):
+# the north star's "max-abs 1e-3 for fp16 features against the reference's fp32 torch path" for rendered rgb / accumulation.
+OUT_TOL = {"fp32": {"rgb": 1e-4, "accumulation": 1e-4, "pred_normals": 2e-3, "expected_depth_rel": 1e-3},
+           "fp16": {"rgb": 1e-3, "accumulation": 1e-3, "pred_normals": 5e-3, "expected_depth_rel": 2e-3}}
+LOSS_TOL = {"fp32": 1e-4, "fp16": 1e-3}
+LOSS_TOL_LOOSE = {"fp32": 1e-3, "fp16": 5e-3}   # normal_loss / interlevel_loss: sums over cell-switching normals and near-tied searchsorted indices
+GRAD_TOL = {"fp32": 2e-3, "fp16": 2e-2}         # max-abs error / max-abs of the reference gradient, per tensor
+
+
+def _assert_step(res, precision, grads=True):
+    for k, t in OUT_TOL[precision].items():
+        assert res["outputs"][k] < t, (k, res["outputs"][k])
+    assert res["outputs"]["normals_frac_gt_2e-3"] < 0.10, res["outputs"]
+    for k in ("depth", "prop_depth_0", "prop_depth_1"):
+        assert res["outputs"][k + "_frac_moved"] <= 0.05, (k, res["outputs"])
+    for k, v in res["losses"].items():
+        tol = LOSS_TOL_LOOSE[precision] if k in ("normal_loss", "interlevel_loss") else LOSS_TOL[precision]
+        assert v <= tol, (k, v)
+    if grads:
+        for k, v in res["grads"].items():
+            assert v <= GRAD_TOL[precision], (k, v)
+
+
+@pytest.fixture(scope="module")
+def nv():
+    import nerf_vo_b200 as nv
+
+    assert torch.cuda.is_available()
+    nv._lib.load()
+    return nv
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_config2_step_vs_oracle(nv, precision):
+    """BASELINE configs[1]: 4096 rays, 2^19 / 2^17 tables — outputs, losses and EVERY parameter gradient against the CPU oracle."""
+    res = _full_step(nv, 19, 17, precision, 4096)
+    _record(f"config2_{precision}", res)
+    _assert_step(res, precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_config4_table_2pow21_step_vs_oracle(nv, precision):
+    """BASELINE configs[3]'s table: the same step on the 16 x 2^21 main table (512 MiB of table + gradient: nothing L2-resident)."""
+    res = _full_step(nv, 21, 17, precision, 4096)
+    _record(f"config4_table21_{precision}", res)
+    _assert_step(res, precision)
+
+
+def test_config3_batch_65536_forward_vs_oracle(nv):
+    """BASELINE configs[2]'s batch: 65 536 rays (3.1 M final samples), production precision, forward + all five losses."""
+    res = _full_step(nv, 19, 17, "fp16", 65536, K=512, backward=False)
+    _record("config3_65536_fp16_forward", res)
+    _assert_step(res, "fp16", grads=False)
+
+
+def test_config3_gradients_8192_vs_oracle(nv):
+    """Gradients at twice config 2's batch with config 3's 512 keyframes (the full 65 536-ray oracle backward is minutes of index_put)."""
+    res = _full_step(nv, 19, 17, "fp16", 8192, K=512)
+    _record("config3_8192_fp16_step", res)
+    _assert_step(res, "fp16")
+
+
+def test_pdf_index_mismatch_rate_config2(nv):
+    """PDFSampler's searchsorted indices on a config-2 batch (4096 rays, 256 -> 96 and 96 -> 48): bit-exact except where u ties with a cdf entry
+    to the last ulp (the kernel normalises in fp64, the reference in fp32; csrc/rays.cu).  The mismatch RATE is reported and bounded."""
+    B = 4096
+    g = torch.Generator().manual_seed(11)
+    out = {}
+    for S_in, S_out in ((256, 96), (96, 48)):
+        sd = torch.sort(torch.rand(B, S_in + 1, generator=g), dim=-1)[0]
+        sd[:, 0], sd[:, -1] = 0.0, 1.0
+        dens = torch.exp(torch.randn(B, S_in, generator=g) * 3.0)
+        w = O.get_weights((sd[:, 1:] - sd[:, :-1]) * 50.0, dens)
+        jit = torch.rand(B, 1, generator=g)
+        ref = O.pdf_resample(w, sd, S_out, jit)
+        nears, fars = torch.full((B,), 0.05, device=DEV), torch.full((B,), 1000.0, device=DEV)
+        sdist, _, inds = nv.ops.pdf_resample(w.to(DEV), sd.to(DEV), S_out, nears, fars, jitter=jit.to(DEV), return_inds=True)
+        mism = float((inds.cpu().long() != ref["inds"]).float().mean())
+        bins_err = float((sdist.cpu() - ref["bins"]).abs().max())
+        out[f"{S_in}->{S_out}"] = {"index_mismatch_rate": mism, "bins_max_abs": bins_err}
+        assert mism < 1e-4, (S_in, mism)      # < 1 index in 10 000
+        assert bins_err < 1e-5, (S_in, bins_err)  # a tied index moves the bin edge by one ulp-sized step only
+    _record("pdf_index_mismatch", out)
+
+
+def test_adam_step_vs_torch_adam(nv):
+    """nvo_adam_step (csrc/optim.cu, the N=1 optimizer of the step) against torch.optim.Adam (NS/engine/optimizers.py:138-150 configuration:
+    lr 1e-2, eps 1e-15, betas (0.9, 0.999), no weight decay) over 8 steps with fresh gradients, odd sizes, zero-gradient entries."""
+    g = torch.Generator().manual_seed(3)
+    for n in (1, 5, 1023, 262147):
+        p0 = torch.randn(n, generator=g)
+        ref = p0.clone().requires_grad_(True)
+        opt = torch.optim.Adam([ref], lr=1e-2, eps=1e-15)
+        p = p0.clone().to(DEV)
+        m, v, step = torch.zeros_like(p), torch.zeros_like(p), torch.zeros(1, dtype=torch.int32, device=DEV)
+        for it in range(8):
+            gr = torch.randn(n, generator=g) * 10.0 ** float(torch.randint(-6, 1, (1,), generator=g))
+            gr[::7] = 0.0  # untouched hash entries: exact-zero gradients must give exact-zero first-step updates
+            ref.grad = gr.clone()
+            opt.step()
+            nv.ops.adam_step(p, gr.to(DEV), m, v, step, 1e-2, 0.9, 0.999, 1e-15)
+        assert int(step) == 8
+        err = float((p.cpu() - ref.detach()).abs().max())
+        assert err < 2e-6, (n, err)
+        st = opt.state[ref]
+        assert float((m.cpu() - st["exp_avg"]).abs().max()) <= 1e-6 * float(st["exp_avg"].abs().max()) + 1e-12
+        assert float((v.cpu() - st["exp_avg_sq"]).abs().max()) <= 1e-6 * float(st["exp_avg_sq"].abs().max()) + 1e-20
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# trajectory: MappingTrainer against the oracle stepped by torch.optim.Adam
+# ---------------------------------------------------------------------------------------------------------------
+TRAJ_STEPS, TRAJ_B, TRAJ_K = 16, 1024, 8
+
+
+def _oracle_trajectory(ocfg, P0, rays, targets, jit, updated):
+    """The reference's Trainer.train_iteration on the CPU oracle: anneal set before the step (nerfacto.py:256-278), forward + losses + backward,
+    one torch.optim.Adam per parameter group (optimizers.py:138-150); the proposal group receives gradients only where `updated` says so
+    (ray_samplers.py:596-610) and is then not stepped (torch skips parameters whose .grad is None)."""
+    P = {k: v.clone().requires_grad_(True) for k, v in P0.items()}
+    fields = [v for k, v in P.items() if k.startswith("field.")]
+    props = [v for k, v in P.items() if k.startswith("proposal_networks.")]
+    opts = [torch.optim.Adam(fields, lr=1e-2, eps=1e-15), torch.optim.Adam(props, lr=1e-2, eps=1e-15)]
+    losses = []
+    for it in range(TRAJ_STEPS):
+        for o in opts:
+            o.zero_grad(set_to_none=True)
+        _, _, total = O.mapping_step(P, ocfg, rays, targets, jit, anneal=O.anneal_value(it), prop_requires_grad=updated[it])
+        for o in opts:
+            o.step()
+        losses.append(float(total))
+    return losses, {k: v.detach().clone() for k, v in P.items()}
+
+
+@pytest.mark.parametrize("graph", [False, True])
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_trainer_trajectory_vs_oracle_adam(nv, graph, precision):
+    from nerf_vo_b200.trainer import MappingTrainer
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    ocfg, P0, m, rays, targets, jit, _, _ = _setup(nv, 14, 12, TRAJ_K, precision, TRAJ_B)
+    # the reference's schedule for iterations 0..15: proposal networks updated on 0..10 (step < 10 as the sampler sees it), then every second one
+    updated = [True] * 11 + [False, True, False, True, False]
+    ref_losses, ref_state = _oracle_trajectory(ocfg, P0, rays, targets, jit, updated)
+
+    tr = MappingTrainer(m, num_rays=TRAJ_B, lr=1e-2, eps=1e-15, use_cuda_graph=graph, proposal_update="reference")
+    tr.capture(warmup=2)  # must leave parameters, moments and counters untouched (warm-up steps used to train the model)
+    for k, v in m.state_dict().items():
+        if k in P0:
+            assert torch.equal(v.cpu(), P0[k]), f"capture() moved {k}"
+    tr.set_inputs({k: v.to(DEV) for k, v in rays.items()}, {k: v.to(DEV) for k, v in targets.items()}, [j.to(DEV) for j in jit])
+    losses = [float(tr.train_step()) for _ in range(TRAJ_STEPS)]
+    torch.cuda.synchronize()
+    assert [int(c) for c in tr.step_counts] == [TRAJ_STEPS, sum(updated)]
+    rel = [abs(a - b) / abs(b) for a, b in zip(losses, ref_losses)]
+    # parameters: Adam with eps = 1e-15 turns any nonzero gradient into a step of ~lr, so an entry whose gradient is rounding noise moves by
+    # +-lr in an arbitrary direction; compare the bulk: fraction of entries further from the oracle than 5 % of the tensor's largest movement
+    now, far = m.state_dict(), {}
+    for k, v in ref_state.items():
+        moved = float((v - P0[k]).abs().max())
+        far[k] = float(((now[k].detach().cpu() - v).abs() > 0.05 * moved + 1e-7).float().mean())
+    _record(f"trajectory_{precision}_{'graph' if graph else 'eager'}", {"loss_rel_err_per_step": rel, "frac_far_per_tensor": far, "losses": losses,
+                                                                      "oracle_losses": ref_losses})
+    ltol = 2e-3 if precision == "fp32" else 1e-2
+    assert max(rel) < ltol, rel
+    ftol = 0.02 if precision == "fp32" else 0.10
+    for k, f in far.items():
+        if ref_state[k].numel() >= 64:  # 3-element output biases: one noisy entry is already 33 %
+            assert f < ftol, (k, f)

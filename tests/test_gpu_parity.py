@@ -387,6 +387,41 @@ def test_field_forward_golden(nv, golden):
     assert float(err.max()) < 1e-3, (float(err.max()), float((err > 1e-3).float().mean()))
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_field_get_density_then_get_outputs_golden(nv, golden, precision):
+    """The reference's own call order (NS/fields/base_field.py:114-133): get_density(ray_samples) -> (density, embedding), then
+    get_outputs(ray_samples, density_embedding=embedding) -> rgb / pred_normals, then get_normals(); against the reference's per-sample
+    outputs, and against forward() (the fused pipeline), with gradients reaching the head parameters and the embedding."""
+    from nerf_vo_b200.fields import FieldHeadNames as F
+
+    g = golden("model_step_small")
+    m, rb, _, _ = _build_model(nv, g, precision=precision)
+    rb = m.set_nears_and_fars(rb)
+    ebins = torch.cat([T(g["level2.starts"]), T(g["level2.ends"])[:, -1:]], -1).contiguous()
+    rs = rb.get_ray_samples(T(g["level2.sdist"]), ebins)
+    density, emb = m.field.get_density(rs)
+    assert emb.shape[-1] == 15 and density.shape[-1] == 1
+    fo = m.field.get_outputs(rs, density_embedding=emb)
+    normals = m.field.get_normals()
+    assert set(fo) == {F.RGB, F.PRED_NORMALS}
+    tol = 1e-5 if precision == "fp32" else 2e-3
+    assert rel_err(density, torch.from_numpy(g["field.density"])) < (1e-5 if precision == "fp32" else 5e-3)
+    assert float((fo[F.RGB].cpu() - torch.from_numpy(g["field.rgb"])).abs().max()) < tol
+    assert float((fo[F.PRED_NORMALS].cpu() - torch.from_numpy(g["field.pred_normals"])).abs().max()) < (1e-4 if precision == "fp32" else 5e-3)
+    nerr = (normals.cpu() - torch.from_numpy(g["field.normals"])).abs().max(dim=-1)[0]
+    assert float((nerr > 2e-3).float().mean()) < (1e-3 if precision == "fp32" else 0.05)
+    # same numbers as the fused forward()
+    ff = m.field.forward(rs, compute_normals=True)
+    assert float((ff[F.RGB] - fo[F.RGB]).abs().max()) < 1e-6
+    assert float((ff[F.PRED_NORMALS] - fo[F.PRED_NORMALS]).abs().max()) < 1e-6
+    assert rel_err(ff[F.DENSITY], density) < 1e-6
+    # gradients flow through both calls: head parameters, appearance embedding, and (through the embedding) the base network
+    (fo[F.RGB].sum() + density.sum() * 1e-3).backward()
+    assert m.field.mlp_head.layers[0].weight.grad is not None and float(m.field.mlp_head.layers[0].weight.grad.abs().max()) > 0
+    assert float(m.field.embedding_appearance.embedding.weight.grad.abs().max()) > 0
+    assert float(m.field.mlp_base.mlp.layers[0].weight.grad.abs().max()) > 0
+
+
 def test_model_step_golden(nv, golden):
     """One full mapping step (config 1/2 shape, reduced table) against the unmodified reference's outputs, losses and
     parameter gradients."""
