@@ -324,13 +324,37 @@ int nvo_frame_finalize(void* stream, int64_t n, const float* rgb, const float* d
 int nvo_depth_scale_sums(void* stream, int64_t n, const float* depth_gt, const float* depth_pred, void* sums);
 
 /* ---------------------------------------------------------------------------------------------
+ * The nerfacto field's three networks as ONE persistent tcgen05 kernel per direction (csrc/field_tc.cu): NerfactoField.get_density's
+ * mlp_base + get_outputs' mlp_head / mlp_pred_normals + PredNormalsFieldHead + Field.get_normals (NS/fields/nerfacto_field.py:199-297,
+ * NS/fields/base_field.py:80-133, NS/field_components/field_heads.py:189-204) — the tensor-core twin of tiny-cuda-nn's FullyFusedMLP
+ * chain (TCNN/src/fully_fused_mlp.cu:499-557) for NeRF-VO's fixed architecture: base 32->64->16, head 63->64->64->3 (sigmoid),
+ * pred-normals 27->64->64->64->3 (tanh, normalize); fp16 operands, fp32 accumulation.
+ *   nvo_field_pack_weights: torch-layout fp32 parameters of the three networks ([W0, b0, W1, b1, ...]; pn_params = the three
+ *     mlp_pred_normals layers followed by PredNormalsFieldHead's Linear, nullable) -> the kernels' fp16 weight image
+ *     (nvo_field_wimage_bytes() bytes); `grid` supplies the 16 level scales folded into the normals chain.
+ *   nvo_field_forward: feat16 = the main grid's TMH feature tiles (nvo_grid_forward / _jac), jac = its saved derivatives (nullable with
+ *     `normals`), positions[n,3] world sample positions (position encoding), directions[B,3], cam_idx[B] int64 or NULL (then
+ *     `embedding` is one 32-vector: eval), selector[n].  Outputs: density[n], rgb[n,3], pred_normals[n,3] (nullable: network skipped),
+ *     normals[n,3] (nullable), h0[n] raw density and pn_raw[n,3] (nullable; saved for the backward), saved = nvo_field_saved_bytes(n)
+ *     bytes of fp16 activations for the backward (nullable: inference).
+ * ------------------------------------------------------------------------------------------- */
+int64_t nvo_field_wimage_bytes(void);
+int64_t nvo_field_saved_bytes(int64_t n);
+int nvo_field_pack_weights(void* stream, const nvo_grid_desc* grid, const float* base_params, const float* head_params, const float* pn_params,
+                           void* wimage);
+int nvo_field_forward(void* stream, int64_t B, int32_t S, const void* feat16, const void* jac, const float* positions, const float* directions,
+                      const int64_t* cam_idx, const float* embedding, const float* selector, const void* wimage, float* density, float* rgb,
+                      float* pred_normals, float* normals, float* h0, float* pn_raw, void* saved);
+
+/* ---------------------------------------------------------------------------------------------
  * Fused dense Adam over a flat fp32 buffer (torch.optim.Adam semantics; NS/engine/optimizers.py:138-150,
  * nerf_vo/mapping/nerfstudio.py:84-100). step[1] is a DEVICE int32 counter (number of steps taken so far), read for the
  * bias correction and incremented by the call, so the launch is CUDA-graph replayable. grad_scale multiplies the
- * gradient first (1/world_size after a sum-allreduce).
+ * gradient first (1/world_size after a sum-allreduce).  lr / betas / eps are doubles: the scalar constants (1 - beta, bias
+ * corrections, step size) are evaluated in double precision as torch's python floats are, then rounded to fp32 once.
  * ------------------------------------------------------------------------------------------- */
-int nvo_adam_step(void* stream, int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int32_t* step, float lr,
-                  float beta1, float beta2, float eps, float grad_scale);
+int nvo_adam_step(void* stream, int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int32_t* step, double lr,
+                  double beta1, double beta2, double eps, float grad_scale);
 
 /* ---------------------------------------------------------------------------------------------
  * Data-parallel exchange fused with the optimizer over NVLink peer memory (csrc/exchange.cu) — replaces the
@@ -347,8 +371,8 @@ int nvo_adam_step(void* stream, int64_t n, float* params, const float* grads, fl
 int nvo_exchange_flag_words(void);
 int64_t nvo_exchange_slice(int64_t n, int32_t rank, int32_t world, int64_t* lo, int64_t* hi);
 int nvo_adam_exchange_step(void* stream, int64_t n, int32_t rank, int32_t world, const void* h_peer_params, const void* h_peer_grads,
-                           const void* h_peer_flags, float* exp_avg_slice, float* exp_avg_sq_slice, int32_t* step, float lr, float beta1,
-                           float beta2, float eps, float grad_scale);
+                           const void* h_peer_flags, float* exp_avg_slice, float* exp_avg_sq_slice, int32_t* step, double lr, double beta1,
+                           double beta2, double eps, float grad_scale);
 /* The same exchange restricted to the flat range [offset, offset + n) — one optimizer parameter group (NS/engine/optimizers.py:138-150
  * keeps one Adam per group; nerfacto's groups are "fields" and "proposal_networks", NS/models/nerfacto.py:244-249).  `phase`
  * (0 .. 2) selects the group's own block of flags, so the groups' exchanges of one step may be in flight concurrently; moments
@@ -356,13 +380,13 @@ int nvo_adam_exchange_step(void* stream, int64_t n, int32_t rank, int32_t world,
  * ctas_per_sm > 0 caps the persistent grid (0 = as many CTAs as fit): a launch that overlaps other kernels leaves them the registers. */
 int nvo_adam_exchange_group(void* stream, int64_t offset, int64_t n, int32_t phase, int32_t rank, int32_t world, const void* h_peer_params,
                             const void* h_peer_grads, const void* h_peer_flags, float* exp_avg_slice, float* exp_avg_sq_slice, int32_t* step,
-                            float lr, float beta1, float beta2, float eps, float grad_scale, int32_t ctas_per_sm);
+                            double lr, double beta1, double beta2, double eps, float grad_scale, int32_t ctas_per_sm);
 /* Two parameter groups stepped in the same launch (one pair of barriers instead of two; the flags of phase 0 and group A's counter as
  * barrier epoch): what the trainer uses when both groups' gradients are complete at the same time. */
 int nvo_adam_exchange_groups2(void* stream, int64_t offset_a, int64_t n_a, float* exp_avg_a, float* exp_avg_sq_a, int32_t* step_a, int64_t offset_b,
                               int64_t n_b, float* exp_avg_b, float* exp_avg_sq_b, int32_t* step_b, int32_t rank, int32_t world,
-                              const void* h_peer_params, const void* h_peer_grads, const void* h_peer_flags, float lr, float beta1, float beta2,
-                              float eps, float grad_scale);
+                              const void* h_peer_params, const void* h_peer_grads, const void* h_peer_flags, double lr, double beta1, double beta2,
+                              double eps, float grad_scale);
 /* peer-visible allocations: cudaMalloc (zero-filled) + CUDA IPC export / import; handles are 64 opaque bytes */
 int nvo_peer_alloc(int64_t bytes, void* h_ptr_out, void* h_handle64_out);
 int nvo_peer_open(const void* h_handle64, void* h_ptr_out);

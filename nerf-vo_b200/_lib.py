@@ -35,7 +35,7 @@ class MlpDesc(ctypes.Structure):
 
 _lib: Optional[ctypes.CDLL] = None
 
-# argument kinds: D descriptor pointer, S stream, p device pointer, l int64, i int32, f float.
+# argument kinds: D descriptor pointer, S stream, p device pointer, l int64, i int32, f float, d double.
 # Signatures are derived from include/nvo_b200.h itself so the binding cannot drift from the header.
 def _parse_header():
     src = open(HEADER).read()
@@ -57,6 +57,8 @@ def _parse_header():
                 sig += "l"
             elif "int32_t" in a:
                 sig += "i"
+            elif "double" in a:
+                sig += "d"
             elif "float" in a:
                 sig += "f"
             else:
@@ -66,7 +68,9 @@ def _parse_header():
 
 
 _SIGS = _parse_header()
-_CT = {"D": ctypes.c_void_p, "S": ctypes.c_void_p, "p": ctypes.c_void_p, "l": ctypes.c_int64, "i": ctypes.c_int32, "f": ctypes.c_float}
+# functions declared `int64_t name(...)` in the header
+_INT64_RETURNS = set(re.findall(r"\bint64_t\s+(nvo_[a-z0-9_]+)\s*\(", re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)))
+_CT = {"D": ctypes.c_void_p, "S": ctypes.c_void_p, "p": ctypes.c_void_p, "l": ctypes.c_int64, "i": ctypes.c_int32, "f": ctypes.c_float, "d": ctypes.c_double}
 
 
 def declared_symbols() -> list:
@@ -89,7 +93,7 @@ def load() -> ctypes.CDLL:
         fn.argtypes = [_CT[k] for k in sig]
         if name == "nvo_last_error":
             fn.restype = ctypes.c_char_p
-        elif name in ("nvo_mlp_n_params", "nvo_mlp_saved_per_sample", "nvo_launch_count", "nvo_mlp_tc_saved_bytes", "nvo_mlp_tc_wimage_bytes", "nvo_prop_density_feat_floats", "nvo_exchange_slice"):
+        elif name in _INT64_RETURNS:
             fn.restype = ctypes.c_int64
         else:
             fn.restype = ctypes.c_int
@@ -125,7 +129,7 @@ def call(name: str, *args):
             out.append(ctypes.addressof(next(it)))
         elif k == "p":
             out.append(_ptr(next(it)))
-        elif k == "f":
+        elif k in "fd":
             out.append(float(next(it)))
         else:
             out.append(int(next(it)))

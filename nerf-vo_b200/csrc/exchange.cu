@@ -18,6 +18,7 @@
 // (nvo_peer_alloc / nvo_peer_open); PyTorch wraps them as tensors.  Spin waits are bounded (~4 s): on timeout the kernel
 // raises the error word instead of hanging the GPU.
 #include "nvo_common.cuh"
+#include "adam.cuh"
 #include <stdlib.h>
 
 #define NVO_MAX_PEERS 16
@@ -79,10 +80,8 @@ struct SliceArgs {
 
 // reduce-scatter (peer loads) -> Adam -> all-gather (peer stores) on one slice
 template <int W, int U>
-__device__ __forceinline__ void slice_pass(const PeerSet& ps, int rank, const SliceArgs& a, float lr, float b1, float b2, float eps, float grad_scale) {
+__device__ __forceinline__ void slice_pass(const PeerSet& ps, int rank, const SliceArgs& a, const AdamC& c) {
     if (a.hi4 <= a.lo4) return;
-    const float t = (float)(*a.step + 1);
-    const float step_size = lr / (1.f - powf(b1, t)), inv_bc2 = 1.f / sqrtf(1.f - powf(b2, t));
     float* __restrict__ m = a.m;
     float* __restrict__ v = a.v;
     const int64_t lo4 = a.lo4, hi4 = a.hi4;
@@ -108,15 +107,10 @@ __device__ __forceinline__ void slice_pass(const PeerSet& ps, int rank, const Sl
             float4 pp = reinterpret_cast<const float4*>(ps.params[rank])[i];
             float4 mm = reinterpret_cast<float4*>(m)[j];
             float4 vv = reinterpret_cast<float4*>(v)[j];
-#define UPD(c)                                                        \
-    {                                                                 \
-        const float gr = gs.c * grad_scale;                           \
-        mm.c = b1 * mm.c + (1.f - b1) * gr;                           \
-        vv.c = b2 * vv.c + (1.f - b2) * gr * gr;                      \
-        pp.c -= step_size * mm.c / (sqrtf(vv.c) * inv_bc2 + eps);     \
-    }
-            UPD(x) UPD(y) UPD(z) UPD(w)
-#undef UPD
+            adam_update(pp.x, mm.x, vv.x, gs.x, c);
+            adam_update(pp.y, mm.y, vv.y, gs.y, c);
+            adam_update(pp.z, mm.z, vv.z, gs.z, c);
+            adam_update(pp.w, mm.w, vv.w, gs.w, c);
             reinterpret_cast<float4*>(m)[j] = mm;
             reinterpret_cast<float4*>(v)[j] = vv;
 #pragma unroll
@@ -129,8 +123,8 @@ __device__ __forceinline__ void slice_pass(const PeerSet& ps, int rank, const Sl
 // barriers), barrier.  The barrier epoch is group A's step counter.
 template <int W, int U>
 __global__ void __launch_bounds__(256) k_exchange_adam(const __grid_constant__ PeerSet ps, int rank, const __grid_constant__ SliceArgs sa,
-                                                       const __grid_constant__ SliceArgs sb, float lr, float b1, float b2, float eps, float grad_scale,
-                                                       int flag_base) {
+                                                       const __grid_constant__ SliceArgs sb, double lr, double b1, double b2, double eps,
+                                                       float grad_scale, int flag_base) {
     int* my_flags = ps.flags[rank] + flag_base;
     const int epoch = *sa.step + 1;
     // ---- 1. every rank's backward has landed -----------------------------------------------------------------------
@@ -142,8 +136,15 @@ __global__ void __launch_bounds__(256) k_exchange_adam(const __grid_constant__ P
         if (threadIdx.x == 0) atomicExch(my_flags + FLAG_COUNT + 1, 1);
     }
     // ---- 2-4. reduce-scatter (peer loads) -> Adam -> all-gather (peer stores) on the own slices -------------------------
-    slice_pass<W, U>(ps, rank, sa, lr, b1, b2, eps, grad_scale);
-    slice_pass<W, U>(ps, rank, sb, lr, b1, b2, eps, grad_scale);
+    // Adam constants per group (each has its own step counter), evaluated once per CTA in double precision
+    __shared__ AdamC s_adam[2];
+    if (threadIdx.x == 0) {
+        s_adam[0] = adam_constants(*sa.step + 1, lr, b1, b2, eps, grad_scale);
+        s_adam[1] = adam_constants(*sb.step + 1, lr, b1, b2, eps, grad_scale);
+    }
+    __syncthreads();
+    slice_pass<W, U>(ps, rank, sa, s_adam[0]);
+    slice_pass<W, U>(ps, rank, sb, s_adam[1]);
     // ---- 5. replicas written: last CTA signals the peers and waits for theirs -----------------------------------------------
     __threadfence_system();
     __syncthreads();
@@ -166,7 +167,7 @@ __global__ void k_tick_step2(int* a, int* b) {
 
 __global__ void k_tick_step(int* step) { *step += 1; }
 
-typedef void (*exchange_fn)(const PeerSet, int, const SliceArgs, const SliceArgs, float, float, float, float, float, int);
+typedef void (*exchange_fn)(const PeerSet, int, const SliceArgs, const SliceArgs, double, double, double, double, float, int);
 
 extern "C" int nvo_exchange_flag_words(void) { return FLAG_WORDS; }
 
@@ -184,7 +185,7 @@ extern "C" int64_t nvo_exchange_slice(int64_t n, int32_t rank, int32_t world, in
 // Exchange + Adam of the flat ranges [offset, offset + n) (group A) and, if n_b > 0, [offset_b, offset_b + n_b) (group B) in ONE launch.
 static int exchange_launch(void* stream, int64_t offset, int64_t n, float* m_a, float* v_a, int32_t* step_a, int64_t offset_b, int64_t n_b, float* m_b,
                            float* v_b, int32_t* step_b, int32_t phase, int32_t rank, int32_t world, const void* h_peer_params, const void* h_peer_grads,
-                           const void* h_peer_flags, float lr, float beta1, float beta2, float eps, float grad_scale, int32_t ctas_per_sm) {
+                           const void* h_peer_flags, double lr, double beta1, double beta2, double eps, float grad_scale, int32_t ctas_per_sm) {
     NVO_CHECK(n > 0 && (n & 3) == 0 && offset >= 0 && (offset & 3) == 0, "adam_exchange: range [%lld, +%lld) must be float4-aligned and non-empty",
               (long long)offset, (long long)n);
     NVO_CHECK(n_b >= 0 && (n_b & 3) == 0 && offset_b >= 0 && (offset_b & 3) == 0, "adam_exchange: second range [%lld, +%lld) must be float4-aligned",
@@ -239,23 +240,23 @@ static int exchange_launch(void* stream, int64_t offset, int64_t n, float* m_a, 
 
 extern "C" int nvo_adam_exchange_group(void* stream, int64_t offset, int64_t n, int32_t phase, int32_t rank, int32_t world, const void* h_peer_params,
                                        const void* h_peer_grads, const void* h_peer_flags, float* exp_avg_slice, float* exp_avg_sq_slice, int32_t* step,
-                                       float lr, float beta1, float beta2, float eps, float grad_scale, int32_t ctas_per_sm) {
+                                       double lr, double beta1, double beta2, double eps, float grad_scale, int32_t ctas_per_sm) {
     return exchange_launch(stream, offset, n, exp_avg_slice, exp_avg_sq_slice, step, 0, 0, nullptr, nullptr, nullptr, phase, rank, world, h_peer_params,
                            h_peer_grads, h_peer_flags, lr, beta1, beta2, eps, grad_scale, ctas_per_sm);
 }
 
 extern "C" int nvo_adam_exchange_groups2(void* stream, int64_t offset_a, int64_t n_a, float* exp_avg_a, float* exp_avg_sq_a, int32_t* step_a,
                                          int64_t offset_b, int64_t n_b, float* exp_avg_b, float* exp_avg_sq_b, int32_t* step_b, int32_t rank,
-                                         int32_t world, const void* h_peer_params, const void* h_peer_grads, const void* h_peer_flags, float lr,
-                                         float beta1, float beta2, float eps, float grad_scale) {
+                                         int32_t world, const void* h_peer_params, const void* h_peer_grads, const void* h_peer_flags, double lr,
+                                         double beta1, double beta2, double eps, float grad_scale) {
     NVO_CHECK(n_b > 0, "adam_exchange_groups2: the second group is empty (use nvo_adam_exchange_group)");
     return exchange_launch(stream, offset_a, n_a, exp_avg_a, exp_avg_sq_a, step_a, offset_b, n_b, exp_avg_b, exp_avg_sq_b, step_b, 0, rank, world,
                            h_peer_params, h_peer_grads, h_peer_flags, lr, beta1, beta2, eps, grad_scale, 0);
 }
 
 extern "C" int nvo_adam_exchange_step(void* stream, int64_t n, int32_t rank, int32_t world, const void* h_peer_params, const void* h_peer_grads,
-                                      const void* h_peer_flags, float* exp_avg_slice, float* exp_avg_sq_slice, int32_t* step, float lr, float beta1,
-                                      float beta2, float eps, float grad_scale) {
+                                      const void* h_peer_flags, float* exp_avg_slice, float* exp_avg_sq_slice, int32_t* step, double lr, double beta1,
+                                      double beta2, double eps, float grad_scale) {
     return nvo_adam_exchange_group(stream, 0, n, 0, rank, world, h_peer_params, h_peer_grads, h_peer_flags, exp_avg_slice, exp_avg_sq_slice, step, lr,
                                    beta1, beta2, eps, grad_scale, 0);
 }

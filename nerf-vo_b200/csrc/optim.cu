@@ -3,33 +3,25 @@
 // gradient pre-scale (1/world_size for the allreduce mean) folded in.  The step counter lives on the device so the
 // launch can be replayed from a CUDA graph.
 #include "nvo_common.cuh"
+#include "adam.cuh"
 
 __global__ void __launch_bounds__(256) k_adam(int64_t n4, int64_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                              float* __restrict__ v, const int* __restrict__ step_ptr, float lr, float b1, float b2, float eps,
+                                              float* __restrict__ v, const int* __restrict__ step_ptr, double lr, double b1, double b2, double eps,
                                               float grad_scale) {
-    __shared__ float s_c[2];
-    if (threadIdx.x == 0) {
-        const float t = (float)(*step_ptr + 1);
-        s_c[0] = lr / (1.f - powf(b1, t));         // step_size
-        s_c[1] = 1.f / sqrtf(1.f - powf(b2, t));   // 1/sqrt(bias_correction2)
-    }
+    __shared__ AdamC s_c;
+    if (threadIdx.x == 0) s_c = adam_constants(*step_ptr + 1, lr, b1, b2, eps, grad_scale);
     __syncthreads();
-    const float step_size = s_c[0], inv_bc2 = s_c[1];
+    const AdamC c = s_c;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n4) {
         float4 pp = reinterpret_cast<float4*>(p)[i];
         const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
         float4 mm = reinterpret_cast<float4*>(m)[i];
         float4 vv = reinterpret_cast<float4*>(v)[i];
-#define UPD(c)                                                        \
-    {                                                                 \
-        const float gr = gg.c * grad_scale;                           \
-        mm.c = b1 * mm.c + (1.f - b1) * gr;                           \
-        vv.c = b2 * vv.c + (1.f - b2) * gr * gr;                      \
-        pp.c -= step_size * mm.c / (sqrtf(vv.c) * inv_bc2 + eps);     \
-    }
-        UPD(x) UPD(y) UPD(z) UPD(w)
-#undef UPD
+        adam_update(pp.x, mm.x, vv.x, gg.x, c);
+        adam_update(pp.y, mm.y, vv.y, gg.y, c);
+        adam_update(pp.z, mm.z, vv.z, gg.z, c);
+        adam_update(pp.w, mm.w, vv.w, gg.w, c);
         reinterpret_cast<float4*>(p)[i] = pp;
         reinterpret_cast<float4*>(m)[i] = mm;
         reinterpret_cast<float4*>(v)[i] = vv;
@@ -38,20 +30,17 @@ __global__ void __launch_bounds__(256) k_adam(int64_t n4, int64_t n, float* __re
     if (blockIdx.x == 0) {
         const int64_t j = n4 * 4 + threadIdx.x;
         if (j < n) {
-            const float gr = g[j] * grad_scale;
-            const float mj = b1 * m[j] + (1.f - b1) * gr;
-            const float vj = b2 * v[j] + (1.f - b2) * gr * gr;
-            m[j] = mj;
-            v[j] = vj;
-            p[j] -= step_size * mj / (sqrtf(vj) * inv_bc2 + eps);
+            float pj = p[j], mj = m[j], vj = v[j];
+            adam_update(pj, mj, vj, g[j], c);
+            p[j] = pj, m[j] = mj, v[j] = vj;
         }
     }
 }
 
 __global__ void k_tick(int* step) { *step += 1; }
 
-extern "C" int nvo_adam_step(void* stream, int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int32_t* step, float lr,
-                             float beta1, float beta2, float eps, float grad_scale) {
+extern "C" int nvo_adam_step(void* stream, int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int32_t* step, double lr,
+                             double beta1, double beta2, double eps, float grad_scale) {
     NVO_CHECK(n >= 0, "adam_step: negative size");
     if (n == 0) return 0;
     NVO_CHECK(params && grads && exp_avg && exp_avg_sq && step, "adam_step: null pointer");

@@ -1373,6 +1373,49 @@ def field_heads_tc(h, embedding, selector, directions, positions, cam_idx, B, S,
 
 
 # ------------------------------------------------------------------------------------------------
+# fused field networks (csrc/field_tc.cu): mlp_base + normals chain + input assembly + mlp_head + mlp_pred_normals in one kernel
+# ------------------------------------------------------------------------------------------------
+
+
+def field_pack_weights(gspec: GridSpec, base_flat, head_flat, pn_flat=None):
+    """fp32 torch-layout parameters of the three field networks -> the fused kernels' fp16 weight image (uint8 tensor)."""
+    check(base_flat, "mlp_base params", torch.float32, (32 * 64 + 64 + 64 * 16 + 16,))
+    check(head_flat, "mlp_head params", torch.float32, (63 * 64 + 64 + 64 * 64 + 64 + 64 * 3 + 3,))
+    if pn_flat is not None:
+        check(pn_flat, "mlp_pred_normals (+ head) params", torch.float32, (27 * 64 + 64 + 2 * (64 * 64 + 64) + 64 * 3 + 3,))
+    img = torch.empty(int(_lib.load().nvo_field_wimage_bytes()), dtype=torch.uint8, device=base_flat.device)
+    call("nvo_field_pack_weights", gspec.desc(torch.float32, "tmh"), base_flat, head_flat, pn_flat, img)
+    return img
+
+
+def field_forward(feat16, jac, positions, directions, cam_idx, embedding, selector, wimage, B: int, S: int, want_pn: bool, save: bool):
+    """One launch: (density [n], rgb [n,3], pred_normals [n,3] | None, normals [n,3] | None, h0 [n], pn_raw [n,3] | None, saved | None).
+    jac (the grid forward's saved derivatives) enables the density-gradient normals."""
+    n = B * S
+    dev = feat16.device
+    check(feat16, "hash features (tmh)", torch.float16, (tmh_numel(n, 32),))
+    check(directions, "directions", torch.float32, (B, 3))
+    check(selector, "selector", torch.float32, (n,))
+    check(embedding, "appearance embedding", torch.float32)
+    if cam_idx is not None:
+        check(cam_idx, "camera indices", torch.int64, (B,))
+    elif embedding.numel() != 32:
+        raise RuntimeError("field_forward: without camera indices the embedding must be one 32-vector")
+    if want_pn:
+        check(positions, "positions", torch.float32, (n, 3))
+    if jac is not None:
+        check(jac, "grid jacobian", torch.float16, (3 * tmh_numel(n, 32),))
+    f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+    density, rgb, h0 = f(n), f(n, 3), f(n)
+    pn = f(n, 3) if want_pn else None
+    pn_raw = f(n, 3) if want_pn else None
+    normals = f(n, 3) if jac is not None else None
+    saved = torch.empty(int(_lib.load().nvo_field_saved_bytes(n)), dtype=torch.uint8, device=dev) if save else None
+    call("nvo_field_forward", B, S, feat16, jac, positions, directions, cam_idx, embedding, selector, wimage, density, rgb, pn, normals, h0, pn_raw, saved)
+    return density, rgb, pn, normals, h0, pn_raw, saved
+
+
+# ------------------------------------------------------------------------------------------------
 # step prologue (csrc/batch.cu): pixel sampling + gather + ray generation + camera-pose correction
 # ------------------------------------------------------------------------------------------------
 
