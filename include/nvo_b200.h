@@ -132,6 +132,11 @@ int nvo_mlp_tc_forward(const nvo_mlp_desc* d, void* stream, int64_t n, const voi
                        void* saved);
 int nvo_mlp_tc_backward(const nvo_mlp_desc* d, void* stream, int64_t n, const void* x16, const void* wimage, const void* saved, const float* y,
                         const float* row_mask, const float* dy, float dy_absmax_hint, float* scratch, float* dx, float* dparams);
+/* nvo_mlp_tc_backward on input / saved-activation tiles that are embedded in larger per-tile records (the fused field kernels' saved tiles):
+ * consecutive tiles lie x_tile_bytes / saved_tile_bytes apart. */
+int nvo_mlp_tc_backward_strided(const nvo_mlp_desc* d, void* stream, int64_t n, const void* x16, int64_t x_tile_bytes, const void* wimage,
+                                const void* saved, int64_t saved_tile_bytes, const float* y, const float* row_mask, const float* dy,
+                                float dy_absmax_hint, float* scratch, float* dx, float* dparams);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused proposal density field — replaces HashMLPDensityField.density_fn / get_density
@@ -335,16 +340,25 @@ int nvo_depth_scale_sums(void* stream, int64_t n, const float* depth_gt, const f
  *   nvo_field_forward: feat16 = the main grid's TMH feature tiles (nvo_grid_forward / _jac), jac = its saved derivatives (nullable with
  *     `normals`), positions[n,3] world sample positions (position encoding), directions[B,3], cam_idx[B] int64 or NULL (then
  *     `embedding` is one 32-vector: eval), selector[n].  Outputs: density[n], rgb[n,3], pred_normals[n,3] (nullable: network skipped),
- *     normals[n,3] (nullable), h0[n] raw density and pn_raw[n,3] (nullable; saved for the backward), saved = nvo_field_saved_bytes(n)
- *     bytes of fp16 activations for the backward (nullable: inference).
+ *     normals[n,3] (nullable), h0[n] raw density and pn_raw[n,3] (nullable; saved for the backward), saved = nvo_field_saved_bytes(n,
+ *     save_pn) bytes of fp16 activations for the backward (nullable: inference); save_pn = 0 leaves the pred-normals activations out
+ *     (512 instead of 960 B per sample): NeRF-VO trains with pred_normal_loss_mult = 0, that network receives no gradient.
  * ------------------------------------------------------------------------------------------- */
 int64_t nvo_field_wimage_bytes(void);
-int64_t nvo_field_saved_bytes(int64_t n);
+int64_t nvo_field_saved_bytes(int64_t n, int32_t save_pn);
 int nvo_field_pack_weights(void* stream, const nvo_grid_desc* grid, const float* base_params, const float* head_params, const float* pn_params,
                            void* wimage);
+/* nvo_field_backward: d loss / d(density[n], rgb[n,3]) (+ dpn_in: fp32 TMF [tiles][27][128], the gradient w.r.t. the pred-normals network's
+ * input from nvo_mlp_tc_backward_strided, nullable) -> dfeat: fp32 TMF [tiles][32][128] gradient w.r.t. the hash features (input of
+ * nvo_grid_backward), and ACCUMULATES the parameter gradients: dbase_params / dhead_params (flat, torch layout), dembedding ([K,32] rows by
+ * cam_idx, or one 32-vector when cam_idx is NULL; nullable).  rgb / h0 / saved / feat16: the forward's outputs; scratch: two device floats.
+ * Needs S >= 32 (a warp's 32 rows then span at most two rays: the embedding gradient is reduced per ray before its atomics). */
+int nvo_field_backward(void* stream, int64_t B, int32_t S, const void* feat16, const void* saved, int32_t save_pn, const void* wimage,
+                       const float* rgb, const float* h0, const float* selector, const int64_t* cam_idx, const float* ddensity, const float* drgb,
+                       const float* dpn_in, float* scratch, float* dfeat, float* dbase_params, float* dhead_params, float* dembedding);
 int nvo_field_forward(void* stream, int64_t B, int32_t S, const void* feat16, const void* jac, const float* positions, const float* directions,
                       const int64_t* cam_idx, const float* embedding, const float* selector, const void* wimage, float* density, float* rgb,
-                      float* pred_normals, float* normals, float* h0, float* pn_raw, void* saved);
+                      float* pred_normals, float* normals, float* h0, float* pn_raw, void* saved, int32_t save_pn);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused dense Adam over a flat fp32 buffer (torch.optim.Adam semantics; NS/engine/optimizers.py:138-150,

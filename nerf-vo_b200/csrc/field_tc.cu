@@ -17,6 +17,21 @@
 #include "nvo_common.cuh"
 #include "tc_common.cuh"
 
+// phase timestamps of one tile group (tools/field_timing.cu builds this file with -DNVO_FT_TIMING); compiled out of the library
+#ifdef NVO_FT_TIMING
+__device__ unsigned long long* g_ft_timing = nullptr;  // [2 threads][FT_MAX_MARKS]
+#define FT_MAX_MARKS 256
+#define FT_MARK()                                                                                              \
+    do {                                                                                                       \
+        if (blockIdx.x == 0 && g == 0 && (tid == 0 || tid == 128) && g_ft_timing && ft_mark < FT_MAX_MARKS)    \
+            g_ft_timing[(tid >> 7) * FT_MAX_MARKS + ft_mark++] = clock64();                                    \
+    } while (0)
+#else
+#define FT_MARK() \
+    do {          \
+    } while (0)
+#endif
+
 #define FT_THREADS 256       // per tile group: warp w reads TMEM lanes 32 * (w & 3) .. (rows of the tile) and the column half (w >> 2)
 #define GEO 15
 #define APP 32
@@ -39,9 +54,10 @@
 // saved-activation tile (backward): chunk offsets inside a tile of FS_CHUNKS 2 KB chunks
 #define FS_H1 0     // mlp_base hidden (64)
 #define FS_X 8      // head input (64)
-#define FS_P 16     // pred-normals input (32)
-#define FS_AH1 20
-#define FS_AH2 28
+#define FS_AH1 16
+#define FS_AH2 24
+#define FS_CHUNKS_HEAD 32   // tile size when the pred-normals network gets no gradient (NeRF-VO: pred_normal_loss_mult = 0)
+#define FS_P 32     // pred-normals input (32)
 #define FS_AP1 36
 #define FS_AP2 44
 #define FS_AP3 52
@@ -51,6 +67,7 @@ struct FieldFwdP {
     int64_t n;
     int S;
     int want_pn, want_normals;
+    int save_pn;                  // saved tiles carry the pred-normals activations too (FS_CHUNKS chunks instead of FS_CHUNKS_HEAD)
     const unsigned char* feat16;  // TMH [tiles][4][128][8] fp16
     const uint4* jac;             // [tiles][4][3][128] x 16 B
     const float* pos;             // [n,3] sample positions (world)
@@ -80,7 +97,13 @@ __device__ __forceinline__ uint32_t cvt_relu_h2(float lo, float hi) {
     return r;
 }
 __device__ __forceinline__ uint4 pack8f(const float* v) { return make_uint4(cvt_h2(v[0], v[1]), cvt_h2(v[2], v[3]), cvt_h2(v[4], v[5]), cvt_h2(v[6], v[7])); }
-__device__ __forceinline__ void group_sync(int g) {
+#define group_sync(g) \
+    do {              \
+        FT_MARK();    \
+        group_sync_(g); \
+        FT_MARK();    \
+    } while (0)
+__device__ __forceinline__ void group_sync_(int g) {
     // generic-proxy writes of the epilogue (shared memory operands) and its TMEM reads are ordered before the MMAs the group leader issues next
     tc_fence_before();
     fence_async_smem();
@@ -140,9 +163,16 @@ __device__ __forceinline__ void ft_sh16(float x, float y, float z, float* c) {
     c[14] = __fmul_rn(__fmul_rn(1.445305721320277f, z), __fsub_rn(xx, yy));
     c[15] = __fmul_rn(__fmul_rn(0.5900435899266435f, x), __fsub_rn(xx, __fmul_rn(3.f, yy)));
 }
+// sin(u) for the reference's fp32 argument u = fl(fl(2 pi x) 2^k) (+ fl(pi/2) for the cos block): two-term Cody-Waite reduction to [-pi, pi]
+// and the SFU sine (abs. error < 1e-6 there) — the value is rounded to fp16 (5e-4) right afterwards
+__device__ __forceinline__ float ft_sin_reduced(float u) {
+    const float k = rintf(u * 0.15915494309189535f);
+    const float ur = fmaf(-k, 1.7484555e-7f, fmaf(-k, 6.2831855f, u));  // 2 pi = 6.2831855 (fp32) - 1.7484555e-7
+    return __sinf(ur);
+}
 __device__ __forceinline__ float ft_posenc(float xi, int k, bool cos_block) {
     const float u = __fmul_rn(__fmul_rn(6.283185307179586f, xi), (float)(1 << k));
-    return sinf(cos_block ? __fadd_rn(u, 1.5707963267948966f) : u);
+    return ft_sin_reduced(cos_block ? __fadd_rn(u, 1.5707963267948966f) : u);
 }
 
 // ================================================================================================================================
@@ -204,16 +234,23 @@ __global__ void __launch_bounds__(G* FT_THREADS, 1) k_field_fwd(const __grid_con
     mbar_wait(mbar_w, 0);
     uint32_t ph = 0;
     int it = 0;
+#ifdef NVO_FT_TIMING
+    int ft_mark = 0;
+#endif
 #define FT_COMMIT_WAIT()                   \
+    FT_MARK();                             \
     mbar_wait(mbar_mma, ph);               \
     ph ^= 1;                               \
-    tc_fence_after();
+    tc_fence_after();                      \
+    FT_MARK();
 
     for (int64_t tile = first; tile < n_tiles; tile += stride, ++it) {
         const int64_t t = tile * TM + r;
         const bool live = t < p.n;
         const int64_t tc = live ? t : p.n - 1;  // rows past the end read the last sample's inputs (finite) and write nothing
-        uint4* sv = p.saved ? p.saved + tile * (int64_t)(FS_CHUNKS * TM) : nullptr;
+        uint4* sv = p.saved ? p.saved + tile * (int64_t)((p.save_pn ? FS_CHUNKS : FS_CHUNKS_HEAD) * TM) : nullptr;
+        uint4* svp = p.save_pn ? sv : nullptr;  // pred-normals activations
+        FT_MARK();
         mbar_wait(mbar_in, (uint32_t)(it & 1));
         // ---- S0: mlp_base layer 0 --------------------------------------------------------------------------------------------------
         if (tid == 0) {
@@ -225,6 +262,11 @@ __global__ void __launch_bounds__(G* FT_THREADS, 1) k_field_fwd(const __grid_con
         if (tid == 0 && tile + stride < n_tiles) {  // the feature tile has been consumed: fetch the next one behind the rest of the chain
             mbar_expect_tx(mbar_in, 4 * CHUNK_B);
             bulk_g2s(sFI, p.feat16 + (tile + stride) * (4 * CHUNK_B), 4 * CHUNK_B, mbar_in);
+        }
+        if (p.want_normals && hf == 1) {
+            // the saved feature derivatives are read one step later (normals epilogue): pull their 12 x 512 B per warp into L2 now
+#pragma unroll
+            for (int c = 0; c < 12; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.jac + (tile * 12 + c) * TM + r));
         }
         {
             float v[32];
@@ -299,7 +341,7 @@ __global__ void __launch_bounds__(G* FT_THREADS, 1) k_field_fwd(const __grid_con
                     *reinterpret_cast<uint4*>(sP + 1 * CHUNK_B + r * 16) = p1;
                     *reinterpret_cast<uint4*>(sP + 2 * CHUNK_B + r * 16) = p2;
                     *reinterpret_cast<uint4*>(sP + 3 * CHUNK_B + r * 16) = p3;
-                    if (sv) sv[(FS_P + 0) * TM + r] = p0, sv[(FS_P + 1) * TM + r] = p1, sv[(FS_P + 2) * TM + r] = p2, sv[(FS_P + 3) * TM + r] = p3;
+                    if (svp) svp[(FS_P + 0) * TM + r] = p0, svp[(FS_P + 1) * TM + r] = p1, svp[(FS_P + 2) * TM + r] = p2, svp[(FS_P + 3) * TM + r] = p3;
                 }
             } else {
                 // density-gradient normals first (they read accA[32,64) and the buffer the head input is about to overwrite was its operand)
@@ -382,7 +424,7 @@ __global__ void __launch_bounds__(G* FT_THREADS, 1) k_field_fwd(const __grid_con
             }
         }
         if (p.want_pn) {
-            epi_hidden<true>(trow, sH, sv ? sv + FS_AP1 * TM : nullptr, hf, r);
+            epi_hidden<true>(trow, sH, svp ? svp + FS_AP1 * TM : nullptr, hf, r);
             group_sync(g);
             // ---- S6 / S7: mlp_pred_normals layers 1, 2 (the last one has no activation, mlp.py:143-179 with out_activation None) -------------
             if (tid == 0) {
@@ -391,7 +433,7 @@ __global__ void __launch_bounds__(G* FT_THREADS, 1) k_field_fwd(const __grid_con
                 umma_commit(mbar_mma);
             }
             FT_COMMIT_WAIT();
-            epi_hidden<true>(trow, sH, sv ? sv + FS_AP2 * TM : nullptr, hf, r);
+            epi_hidden<true>(trow, sH, svp ? svp + FS_AP2 * TM : nullptr, hf, r);
             group_sync(g);
             if (tid == 0) {
                 tc_fence_after();
@@ -399,7 +441,7 @@ __global__ void __launch_bounds__(G* FT_THREADS, 1) k_field_fwd(const __grid_con
                 umma_commit(mbar_mma);
             }
             FT_COMMIT_WAIT();
-            epi_hidden<false>(trow, sH, sv ? sv + FS_AP3 * TM : nullptr, hf, r);
+            epi_hidden<false>(trow, sH, svp ? svp + FS_AP3 * TM : nullptr, hf, r);
             group_sync(g);
             // ---- S8: PredNormalsFieldHead: Linear(64, 3) + Tanh + normalize (field_heads.py:189-204) -------------------------------------------
             if (tid == 0) {
@@ -486,9 +528,11 @@ __global__ void __launch_bounds__(256) k_field_pack(const float* __restrict__ ba
     for (int o = t; o < 64; o += stride) w1[o] = __float2half_rn(__ldg(base + 64 * 32 + 64 + o));
 }
 
+__global__ void k_field_pack_bwd(const float* __restrict__ base, const float* __restrict__ head, unsigned char* __restrict__ img);
+
 // ================================================================================================================================
-extern "C" int64_t nvo_field_wimage_bytes(void) { return FI_BYTES; }
-extern "C" int64_t nvo_field_saved_bytes(int64_t n) { return ((n + TM - 1) / TM) * (int64_t)FS_CHUNKS * CHUNK_B; }
+extern "C" int64_t nvo_field_wimage_bytes(void) { return ((FI_BYTES + 127) & ~127) + 24576; }  // forward section + backward section (FB_OFF + FB_BYTES)
+extern "C" int64_t nvo_field_saved_bytes(int64_t n, int32_t save_pn) { return ((n + TM - 1) / TM) * (int64_t)(save_pn ? FS_CHUNKS : FS_CHUNKS_HEAD) * CHUNK_B; }
 
 extern "C" int nvo_field_pack_weights(void* stream, const nvo_grid_desc* grid, const float* base_params, const float* head_params, const float* pn_params,
                                       void* wimage) {
@@ -498,6 +542,8 @@ extern "C" int nvo_field_pack_weights(void* stream, const nvo_grid_desc* grid, c
     for (int i = 0; i < 16; ++i) sc.s[i] = grid->scalings[i];
     k_field_pack<<<16, 256, 0, (cudaStream_t)stream>>>(base_params, head_params, pn_params, sc, (unsigned char*)wimage);
     NVO_CUDA_LAUNCH_CHECK("field_pack_weights");
+    k_field_pack_bwd<<<8, 256, 0, (cudaStream_t)stream>>>(base_params, head_params, (unsigned char*)wimage);
+    NVO_CUDA_LAUNCH_CHECK("field_pack_weights(backward section)");
     return 0;
 }
 
@@ -508,7 +554,7 @@ static int field_groups() {
 
 extern "C" int nvo_field_forward(void* stream, int64_t B, int32_t S, const void* feat16, const void* jac, const float* positions, const float* directions,
                                  const int64_t* cam_idx, const float* embedding, const float* selector, const void* wimage, float* density, float* rgb,
-                                 float* pred_normals, float* normals, float* h0, float* pn_raw, void* saved) {
+                                 float* pred_normals, float* normals, float* h0, float* pn_raw, void* saved, int32_t save_pn) {
     NVO_CHECK(B >= 0 && S >= 1, "field_forward: bad shape B=%lld S=%d", (long long)B, S);
     if (B == 0) return 0;
     NVO_CHECK(feat16 && directions && embedding && selector && wimage && density && rgb, "field_forward: null pointer");
@@ -518,7 +564,7 @@ extern "C" int nvo_field_forward(void* stream, int64_t B, int32_t S, const void*
     p.n = B * S, p.S = S, p.want_pn = pred_normals != nullptr, p.want_normals = normals != nullptr;
     p.feat16 = (const unsigned char*)feat16, p.jac = (const uint4*)jac, p.pos = positions, p.dirs = directions, p.cam = cam_idx, p.emb = embedding;
     p.sel = selector, p.wimg = (const unsigned char*)wimage, p.density = density, p.rgb = rgb, p.pn = pred_normals, p.normals = normals, p.h0 = h0;
-    p.pn_raw = pn_raw, p.saved = (uint4*)saved;
+    p.pn_raw = pn_raw, p.saved = (uint4*)saved, p.save_pn = (saved && save_pn && pred_normals) ? 1 : 0;
     const int G = field_groups();
     const size_t smem = FT_GROUPS_OFF + (size_t)G * FT_GROUP_CHUNKS * CHUNK_B + 8 * (1 + 2 * G) + 16;
     const int64_t tiles = (p.n + TM - 1) / TM;
@@ -534,5 +580,512 @@ extern "C" int nvo_field_forward(void* stream, int64_t B, int32_t S, const void*
         k_field_fwd<3><<<grid, 3 * FT_THREADS, smem, (cudaStream_t)stream>>>(p);
     }
     NVO_CUDA_LAUNCH_CHECK("field_forward");
+    return 0;
+}
+
+// ================================================================================================================================
+// backward: mlp_head (dgrad + wgrad), input assembly backward (geometry features, appearance-embedding gradient, trunc_exp'), mlp_base
+// (dgrad + wgrad) -> d loss / d hash features (fp32 TMF tiles for the table scatter) in ONE persistent kernel.
+//
+//   * G tile groups of 256 epilogue threads + one MMA-issuing warp.  The weight gradients of all five layers stay resident in TMEM for the
+//     whole kernel (dW^T[in][out] += A_ext^T dZ, K = the tile's 128 samples, the bias as the row of a constant ones feature) and are SHARED by
+//     the groups: every tcgen05.mma of the CTA is issued by the same thread, so accumulation into the same columns is ordinary in-order
+//     accumulation.  A group signals "operands ready" on an mbarrier (one arrival per warp), the issuer polls the groups round-robin, issues
+//     the step's dgrad + wgrad MMAs and commits to the group's "done" mbarrier.
+//   * per tile 5 steps: head L2 | head L1 | head L0 | base L1 | base L0.  Saved activations arrive just in time: two 18 KB slots per group
+//     (tile + ones chunk), the issuer refills slot (q+1) & 1 with step q+1's tile by a bulk copy when step q's operands are ready (its last
+//     readers, step q-1's MMAs and epilogue, are finished by then).
+//   * gradients are scaled by powers of two before their fp16 conversion and unscaled in fp32 on the way out (tiny-cuda-nn's loss scale,
+//     TCNN/include/tiny-cuda-nn/common.h:232), with TWO scales chosen per launch by k_field_bwd_absmax: s_h for mlp_head's chain from
+//     max|d rgb sigmoid'|, s_b for mlp_base's chain from max(|d density trunc_exp'|, 4 max|d rgb sigmoid'|).  One scale for both would push
+//     the colour path's gradients into fp16 subnormals whenever the density path's are much larger.  The largest scaled entry starts in
+//     [128, 256): a chain would have to amplify it 256-fold to leave fp16's range, and the conversions saturate instead of producing inf.
+//     (kind::f16 does not take fp16 activations with bf16 gradients: mixed operand formats raise an illegal-instruction fault on B200.)
+// TMEM: [0,16) dW_head2^T | [16,32) dW_base1^T | [32,96) dW_head1^T | [96,160) dW_head0^T | [160,224) dW_base0^T | 224 + 64 g: group g's dgrad
+// ================================================================================================================================
+#define FB_OFF ((FI_BYTES + 127) & ~127)
+#define FB_H2T 0                         // N 64 (inputs), K 16 (outputs)
+#define FB_H1T (FB_H2T + 64 * 16 * 2)    // N 64, K 64
+#define FB_H0T (FB_H1T + 64 * 64 * 2)    // N 64, K 64 (input 63 = the bias column: zero row)
+#define FB_B1T (FB_H0T + 64 * 64 * 2)    // N 64, K 16
+#define FB_B0T (FB_B1T + 64 * 16 * 2)    // N 32, K 64
+#define FB_BYTES (FB_B0T + 32 * 64 * 2)
+
+#define BW_SLOT_CHUNKS 9
+#define BW_GROUP_CHUNKS (2 * BW_SLOT_CHUNKS + 8 + 2)
+#define BW_GROUPS_OFF ((FB_BYTES + 1023) & ~1023)
+#define DW_H2T 0
+#define DW_B1T 16
+#define DW_H1T 32
+#define DW_H0T 96
+#define DW_B0T 160
+#define DW_ACC 224
+
+struct FieldBwdP {
+    int64_t n;
+    int S;
+    int saved_chunks;             // chunks per saved tile (FS_CHUNKS_HEAD or FS_CHUNKS)
+    const unsigned char* feat16;  // TMH [tiles][4][128][8]
+    const unsigned char* saved;   // forward's saved tiles
+    const unsigned char* wimg;    // weight image (backward section at FB_OFF)
+    const float* rgb;             // [n,3] forward output (sigmoid')
+    const float* h0;              // [n]
+    const float* sel;             // [n]
+    const int64_t* cam;           // [B] or null
+    const float* ddensity;        // [n] or null
+    const float* drgb;            // [n,3]
+    const float* dpn_in;          // fp32 TMF [tiles][27][128] (gradient w.r.t. the pred-normals input, from its own backward) or null
+    const float* absmax;          // device float[2]: max |d rgb sigmoid'|, max |d density trunc_exp' selector|
+    float* dfeat;                 // fp32 TMF [tiles][32][128]
+    float* dbase;                 // flat fp32 gradient of mlp_base (torch layout), accumulated
+    float* dhead;                 // flat fp32 gradient of mlp_head, accumulated
+    float* demb;                  // [K,32] (cam != null) or [32], accumulated; nullable
+};
+
+__device__ __forceinline__ float ft_grad_scale(float mx) {
+    if (!(mx > 0.f) || !isfinite(mx)) return 1.f;
+    int e;
+    frexpf(mx, &e);             // mx = f * 2^e, f in [0.5, 1)
+    return ldexpf(1.f, 8 - e);  // mx * scale in [128, 256)
+}
+__device__ __forceinline__ uint32_t cvt_sat_h2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint4 pack8sat(const float* v) {
+    return make_uint4(cvt_sat_h2(v[0], v[1]), cvt_sat_h2(v[2], v[3]), cvt_sat_h2(v[4], v[5]), cvt_sat_h2(v[6], v[7]));
+}
+
+// out[0] = max |d rgb sigmoid'(rgb)|, out[1] = max |d density selector trunc_exp'(h0)| (non-negative floats order like their bit patterns)
+__global__ void __launch_bounds__(256) k_field_bwd_absmax(int64_t n, const float* __restrict__ drgb, const float* __restrict__ rgb,
+                                                          const float* __restrict__ ddensity, const float* __restrict__ sel,
+                                                          const float* __restrict__ h0, float* __restrict__ out) {
+    float m = 0.f, md = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float y = __ldg(rgb + 3 * i + j);
+            m = fmaxf(m, fabsf(__ldg(drgb + 3 * i + j) * y * (1.f - y)));
+        }
+        if (ddensity) md = fmaxf(md, fabsf(__ldg(ddensity + i) * __ldg(sel + i) * expf(fminf(fmaxf(__ldg(h0 + i), -15.f), 15.f))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        md = fmaxf(md, __shfl_xor_sync(0xffffffffu, md, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (m > 0.f) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
+        if (md > 0.f) atomicMax(reinterpret_cast<int*>(out) + 1, __float_as_int(md));
+    }
+}
+
+__device__ __forceinline__ bool mbar_test(uint64_t* mbar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done)
+                 : "r"(smem_u32(mbar)), "r"(parity)
+                 : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* mbar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mbar)) : "memory"); }
+
+// wgrad, transposed form: D[feature i (M = 128: 64 real + ones row + ignored rows)][output o (N)] += sum over the tile's 128 samples of
+// A_ext[s][i] * dZ[s][o]; both operands MN-major (the activation / dZ tiles as they lie in shared memory), 8 K-steps of 16 samples
+__device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint32_t act_base, uint32_t dz_base, int N, uint32_t accumulate) {
+    const uint32_t idesc = umma_idesc(TM, N, 1, 1);
+    for (int k = 0; k < TM / 16; ++k)
+        umma_f16(tmem_d, umma_desc(act_base + k * 256, 128, CHUNK_B), umma_desc(dz_base + k * 256, 128, CHUNK_B), idesc, k > 0 ? 1u : accumulate);
+}
+
+// dgrad epilogue of a hidden layer: 32 accumulator columns x ReLU'(saved activation) -> fp16 dZ tile
+__device__ __forceinline__ void epi_mask(uint32_t tacc, const unsigned char* __restrict__ sAct, unsigned char* __restrict__ sOut, int hf, int r) {
+    float v[32];
+    tmem_ld32(tacc + 32 * hf, v);
+    const __half2 zero = __float2half2_rn(0.f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 a = *reinterpret_cast<const uint4*>(sAct + (4 * hf + q) * CHUNK_B + r * 16);
+        uint4 u = pack8sat(v + 8 * q);
+        const __half2* a2 = reinterpret_cast<const __half2*>(&a);
+        uint32_t* u2 = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) u2[j] &= __hgt2_mask(a2[j], zero);  // 0xFFFF per half where the saved fp16 activation is positive
+        *reinterpret_cast<uint4*>(sOut + (4 * hf + q) * CHUNK_B + r * 16) = u;
+    }
+}
+
+// sum over the lanes of a warp of e[k] for every k: afterwards e[0] of lane k holds channel k's total (31 shuffles)
+__device__ __forceinline__ void warp_transpose_reduce32(float* e, int lane) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            const float send = up ? e[i] : e[i + o];
+            const float keep = up ? e[i + o] : e[i];
+            e[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __grid_constant__ FieldBwdP p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int NEPI = G * FT_THREADS;
+    const bool is_issuer_warp = threadIdx.x >= NEPI;
+    const int g = is_issuer_warp ? 0 : (int)(threadIdx.x >> 8);
+    const int tid = threadIdx.x & 255, warp = tid >> 5, hf = warp >> 2, lane = threadIdx.x & 31;
+    const int r = ((warp & 3) << 5) | lane;
+    unsigned char* sW = smem;
+    uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + BW_GROUPS_OFF + (G * BW_GROUP_CHUNKS + 2) * CHUNK_B);
+    uint64_t* mbar_w = mbars;                 // weights landed
+    uint64_t* mbar_ready = mbars + 1;         // [G] operands of the group's next step are in shared memory (8 warp arrivals)
+    uint64_t* mbar_done = mbars + 1 + G;      // [G] the step's MMAs have retired (tcgen05.commit)
+    uint64_t* mbar_load = mbars + 1 + 2 * G;  // [G][2] the slot's bulk copy has landed
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mbars + 1 + 4 * G);
+    const int64_t n_tiles = (p.n + TM - 1) >> 7;
+    const int64_t stride = (int64_t)gridDim.x * G;
+    const size_t saved_tile_bytes = (size_t)p.saved_chunks * CHUNK_B;
+
+    // zero the activation slots / dZ buffers once (padded chunks feed ignored accumulator rows, but must not hold NaN patterns that
+    // would reach real rows through the K dimension), then the constant ones chunk behind every slot
+    for (int e = threadIdx.x; e < (G * BW_GROUP_CHUNKS + 2) * CHUNK_B / 16; e += NEPI + 32)
+        reinterpret_cast<uint4*>(smem + BW_GROUPS_OFF)[e] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    if (!is_issuer_warp && tid < TM) {
+        unsigned char* sG = smem + BW_GROUPS_OFF + g * BW_GROUP_CHUNKS * CHUNK_B;
+        *reinterpret_cast<uint4*>(sG + 8 * CHUNK_B + tid * 16) = make_uint4(0x00003C00u, 0, 0, 0);
+        *reinterpret_cast<uint4*>(sG + (BW_SLOT_CHUNKS + 8) * CHUNK_B + tid * 16) = make_uint4(0x00003C00u, 0, 0, 0);
+    }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(mbar_w, 1);
+        for (int i = 0; i < G; ++i) {
+            mbar_init(mbar_ready + i, 8);
+            mbar_init(mbar_done + i, 1);
+            mbar_init(mbar_load + 2 * i, 1);
+            mbar_init(mbar_load + 2 * i + 1, 1);
+        }
+        fence_mbar_init();
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem0 = *tmem_ptr;
+    const float mx_h = __ldg(p.absmax), mx_d = __ldg(p.absmax + 1);
+    const float s_h = ft_grad_scale(mx_h), s_b = ft_grad_scale(fmaxf(mx_d, 4.f * mx_h));
+    const float inv_s_h = 1.f / s_h, inv_s_b = 1.f / s_b, s_bh = s_b * inv_s_h;
+
+    if (is_issuer_warp) {
+        // ============================================ MMA issuer + loader (one thread) ============================================
+        if (lane == 0) {
+            mbar_expect_tx(mbar_w, FB_BYTES);
+            bulk_g2s(sW, p.wimg + FB_OFF, FB_BYTES, mbar_w);
+            int64_t total_q[G];
+            int q[G];
+            uint32_t rph[G], lph[G][2];
+            int dw_started = 0;  // bit l: layer l's weight-gradient accumulator has been written once
+            int active = 0;
+            auto load = [&](int gg, int qq) {
+                const int ts = qq % 5;
+                const int64_t tile = (int64_t)blockIdx.x * G + gg + (int64_t)(qq / 5) * stride;
+                unsigned char* slot = smem + BW_GROUPS_OFF + gg * BW_GROUP_CHUNKS * CHUNK_B + (qq & 1) * BW_SLOT_CHUNKS * CHUNK_B;
+                uint64_t* mb = mbar_load + 2 * gg + (qq & 1);
+                const unsigned char* sv = p.saved + tile * saved_tile_bytes;
+                if (ts == 4) {  // base layer 0's input: the hash features (4 chunks), placed so that the ones chunk follows them
+                    mbar_expect_tx(mb, 4 * CHUNK_B);
+                    bulk_g2s(slot + 4 * CHUNK_B, p.feat16 + tile * (4 * CHUNK_B), 4 * CHUNK_B, mb);
+                } else {
+                    const int ch = ts == 0 ? FS_AH2 : ts == 1 ? FS_AH1 : ts == 2 ? FS_X : FS_H1;
+                    mbar_expect_tx(mb, 8 * CHUNK_B);
+                    bulk_g2s(slot, sv + ch * CHUNK_B, 8 * CHUNK_B, mb);
+                }
+            };
+#pragma unroll
+            for (int gg = 0; gg < G; ++gg) {
+                const int64_t first = (int64_t)blockIdx.x * G + gg;
+                const int64_t tiles_g = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+                total_q[gg] = tiles_g * 5;
+                q[gg] = 0, rph[gg] = 0, lph[gg][0] = lph[gg][1] = 0;
+                if (tiles_g > 0) {
+                    active |= 1 << gg;
+                    load(gg, 0);
+                    load(gg, 1);
+                }
+            }
+            mbar_wait(mbar_w, 0);
+            const uint32_t uW = smem_u32(sW);
+            while (active) {
+#pragma unroll
+                for (int gg = 0; gg < G; ++gg) {
+                    if (!((active >> gg) & 1)) continue;
+                    const int qq = q[gg], sl = qq & 1;
+                    if (!mbar_test(mbar_ready + gg, rph[gg]) || !mbar_test(mbar_load + 2 * gg + sl, lph[gg][sl])) continue;
+                    rph[gg] ^= 1, lph[gg][sl] ^= 1;
+                    if (qq >= 1 && qq + 1 < total_q[gg]) load(gg, qq + 1);  // slot (qq+1)&1: its readers (step qq-1) are finished
+                    tc_fence_after();
+                    const uint32_t uG = smem_u32(smem + BW_GROUPS_OFF + gg * BW_GROUP_CHUNKS * CHUNK_B);
+                    const uint32_t uSlot = uG + sl * BW_SLOT_CHUNKS * CHUNK_B, uG64 = uG + 2 * BW_SLOT_CHUNKS * CHUNK_B, uG16 = uG64 + 8 * CHUNK_B;
+                    const uint32_t acc = tmem0 + DW_ACC + 64 * gg;
+                    const int ts = qq % 5;
+                    const uint32_t started = (dw_started >> ts) & 1;
+                    switch (ts) {
+                        case 0:  // head layer 2: dA2 = dz3 W2 ; dW2^T += AH2_ext^T dz3
+                            issue_layer(acc, uG16, 1, uW + FB_H2T, 64, false, 0);
+                            issue_wgrad(tmem0 + DW_H2T, uSlot, uG16, 16, started);
+                            break;
+                        case 1:  // head layer 1
+                            issue_layer(acc, uG64, 4, uW + FB_H1T, 64, false, 0);
+                            issue_wgrad(tmem0 + DW_H1T, uSlot, uG64, 64, started);
+                            break;
+                        case 2:  // head layer 0: dX ; dW0^T += X^T dZ1 (the bias is X's constant column 63)
+                            issue_layer(acc, uG64, 4, uW + FB_H0T, 64, false, 0);
+                            issue_wgrad(tmem0 + DW_H0T, uSlot, uG64, 64, started);
+                            break;
+                        case 3:  // base layer 1
+                            issue_layer(acc, uG16, 1, uW + FB_B1T, 64, false, 0);
+                            issue_wgrad(tmem0 + DW_B1T, uSlot, uG16, 16, started);
+                            break;
+                        default:  // base layer 0: d features (32 columns); the feature tile sits in the slot's upper half
+                            issue_layer(acc, uG64, 4, uW + FB_B0T, 32, false, 0);
+                            issue_wgrad(tmem0 + DW_B0T, uSlot + 4 * CHUNK_B, uG64, 64, started);
+                            break;
+                    }
+                    dw_started |= 1 << ts;
+                    umma_commit(mbar_done + gg);
+                    q[gg] = qq + 1;
+                    if (qq + 1 == total_q[gg]) active &= ~(1 << gg);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ==================================================== tile groups ====================================================
+        unsigned char* sG = smem + BW_GROUPS_OFF + g * BW_GROUP_CHUNKS * CHUNK_B;
+        unsigned char* sG64 = sG + 2 * BW_SLOT_CHUNKS * CHUNK_B;
+        unsigned char* sG16 = sG64 + 8 * CHUNK_B;
+        const uint32_t tacc = tmem0 + DW_ACC + 64 * g + ((uint32_t)((warp & 3) * 32) << 16);
+        uint64_t* ready = mbar_ready + g;
+        uint64_t* done = mbar_done + g;
+        uint32_t dph = 0;
+        int q = 0;
+        auto arrive_ready = [&]() {
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ready);
+        };
+        auto wait_done = [&]() {
+            mbar_wait(done, dph);
+            dph ^= 1;
+            tc_fence_after();
+            mbar_wait(mbar_load + 2 * g + (q & 1), (uint32_t)((q >> 1) & 1));  // already complete (the issuer waited for it): orders the reads below
+        };
+        // dz of the colour output: drgb * sigmoid'(rgb) * scale -> G16 chunk 0 (outputs 0..2), chunk 1 = 0
+        auto write_dz3 = [&](int64_t tile) {
+            if (hf != 0) return;
+            const int64_t t = tile * TM + r;
+            float dz[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (tile < n_tiles && t < p.n) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const float y = __ldg(p.rgb + 3 * t + j);
+                    dz[j] = __ldg(p.drgb + 3 * t + j) * y * (1.f - y) * s_h;
+                }
+            }
+            *reinterpret_cast<uint4*>(sG16 + r * 16) = pack8f(dz);
+            *reinterpret_cast<uint4*>(sG16 + CHUNK_B + r * 16) = make_uint4(0, 0, 0, 0);
+        };
+        const int64_t first = (int64_t)blockIdx.x * G + g;
+        write_dz3(first);
+        for (int64_t tile = first; tile < n_tiles; tile += stride) {
+            const int64_t t = tile * TM + r;
+            const bool live = t < p.n;
+            const int64_t tc = live ? t : p.n - 1;
+            // ---- step 0: head layer 2 -> dZ2 = dA2 * ReLU'(AH2) -------------------------------------------------------------------------
+            arrive_ready();
+            wait_done();
+            epi_mask(tacc, sG + (q & 1) * BW_SLOT_CHUNKS * CHUNK_B, sG64, hf, r);
+            ++q;
+            // ---- step 1: head layer 1 -> dZ1 (in place: the step's MMAs, the buffer's readers, have retired) ---------------------------------
+            arrive_ready();
+            wait_done();
+            epi_mask(tacc, sG + (q & 1) * BW_SLOT_CHUNKS * CHUNK_B, sG64, hf, r);
+            ++q;
+            // ---- step 2: head layer 0 -> dX: geometry features -> dh, appearance embedding gradient, trunc_exp' --------------------------------
+            arrive_ready();
+            wait_done();
+            {
+                float v[32];
+                tmem_ld32(tacc + 32 * hf, v);
+                const int64_t ray = tc / p.S;
+                const int ray0 = __shfl_sync(0xffffffffu, (int)ray, 0);
+                const bool second = (int)ray != ray0;                       // the warp's 32 rows span at most two rays (S >= 32 enforced)
+                const bool split = __any_sync(0xffffffffu, second);
+                const int ray1 = __shfl_sync(0xffffffffu, (int)ray, 31);
+                if (hf == 0) {
+                    float dh[16];
+                    dh[0] = 0.f;
+                    if (live && p.ddensity)
+                        dh[0] = __ldg(p.ddensity + t) * __ldg(p.sel + t) * expf(fminf(fmaxf(__ldg(p.h0 + t), -15.f), 15.f)) * s_b;  // activations.py:38-41
+#pragma unroll
+                    for (int k = 0; k < GEO; ++k) dh[1 + k] = v[16 + k] * s_bh;  // head-chain scale -> base-chain scale
+                    if (p.dpn_in && live) {
+#pragma unroll
+                        for (int k = 0; k < GEO; ++k) dh[1 + k] += s_b * __ldg(p.dpn_in + ((tile * 27 + 12 + k) << 7) + r);
+                    }
+                    *reinterpret_cast<uint4*>(sG16 + r * 16) = pack8sat(dh);
+                    *reinterpret_cast<uint4*>(sG16 + CHUNK_B + r * 16) = pack8sat(dh + 8);
+                    if (p.demb) {  // appearance channel 0 (head input column 31)
+                        float a = second ? 0.f : v[31], b = second ? v[31] : 0.f;
+                        a = nvo_warp_sum(a);
+                        if (split) b = nvo_warp_sum(b);
+                        if (lane == 0) {
+                            atomicAdd(p.demb + (p.cam ? APP * __ldg(p.cam + ray0) : 0), a * inv_s_h);
+                            if (split) atomicAdd(p.demb + (p.cam ? APP * __ldg(p.cam + ray1) : 0), b * inv_s_h);
+                        }
+                    }
+                } else if (p.demb) {
+                    // appearance channels 1..31 = columns 32..62 (column 63 carries the bias): per-ray sums by a transpose-reduce, one
+                    // atomic per (ray, channel) instead of one per (sample, channel)
+                    float e[32];
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) e[k] = second ? 0.f : v[k];
+                    warp_transpose_reduce32(e, lane);
+                    if (lane < 31) atomicAdd(p.demb + (p.cam ? APP * __ldg(p.cam + ray0) : 0) + 1 + lane, e[0] * inv_s_h);
+                    if (split) {
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) e[k] = second ? v[k] : 0.f;
+                        warp_transpose_reduce32(e, lane);
+                        if (lane < 31) atomicAdd(p.demb + (p.cam ? APP * __ldg(p.cam + ray1) : 0) + 1 + lane, e[0] * inv_s_h);
+                    }
+                }
+            }
+            ++q;
+            // ---- step 3: base layer 1 -> dZ0 = dA * ReLU'(H1) ------------------------------------------------------------------------------
+            arrive_ready();
+            wait_done();
+            epi_mask(tacc, sG + (q & 1) * BW_SLOT_CHUNKS * CHUNK_B, sG64, hf, r);
+            ++q;
+            // ---- step 4: base layer 0 -> d features (fp32 TMF [tile][32][128]: a warp stores 128 contiguous bytes per column) ------------------
+            arrive_ready();
+            wait_done();
+            {
+                float v[16];
+                tmem_ld16(tacc + 16 * hf, v);
+                float* dst = p.dfeat + ((tile * 32 + 16 * hf) << 7) + r;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) dst[j << 7] = v[j] * inv_s_b;
+            }
+            ++q;
+            write_dz3(tile + stride);  // G16's readers (step 3's MMAs) have retired
+        }
+    }
+    // ---- flush the weight gradients: lane = input feature (64 = the ones feature = bias), column = output -----------------------------------
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (!is_issuer_warp && (int64_t)blockIdx.x * G < n_tiles) {
+        const uint32_t tlane = tmem0 + ((uint32_t)((warp & 3) * 32) << 16);
+        // (matrix, TMEM column, outputs, inputs, bias feature row, destination weight / bias offsets, destination buffer)
+        struct M {
+            int col, N, K, brow, w_off, b_off, head;
+        };
+        const M mats[5] = {
+            {DW_H1T, 64, 64, 64, 64 * 63 + 64, 64 * 63 + 64 + 64 * 64, 1},
+            {DW_H0T, 64, 63, 63, 0, 64 * 63, 1},
+            {DW_B0T, 64, 32, 32, 0, 64 * 32, 0},
+            {DW_H2T, 3, 64, 64, 64 * 63 + 64 + 64 * 64 + 64, 64 * 63 + 64 + 64 * 64 + 64 + 3 * 64, 1},
+            {DW_B1T, 16, 64, 64, 64 * 32 + 64, 64 * 32 + 64 + 16 * 64, 0},
+        };
+        for (int m = 0; m < 5; ++m) {
+            if (m % G != g) continue;
+            const M& y = mats[m];
+            float* dst = y.head ? p.dhead : p.dbase;
+            const float inv = y.head ? inv_s_h : inv_s_b;
+            if ((warp & 3) * 32 > y.brow) continue;  // this warp's lanes hold no real row
+            const int ncol = y.N < 16 ? 16 : y.N;
+            for (int c0 = hf * 16; c0 < ncol; c0 += 32) {
+                float v[16];
+                tmem_ld16(tlane + y.col + c0, v);
+                if (r < y.K) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < y.N) atomicAdd(dst + y.w_off + (c0 + j) * y.K + r, v[j] * inv);
+                } else if (r == y.brow) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < y.N) atomicAdd(dst + y.b_off + c0 + j, v[j] * inv);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem0) : "memory");
+}
+
+// backward section of the weight image: transposed tiles (N = inputs, K = outputs) for the dgrad products
+__global__ void __launch_bounds__(256) k_field_pack_bwd(const float* __restrict__ base, const float* __restrict__ head, unsigned char* __restrict__ img) {
+    struct T {
+        int head, w_off, N_in, K_in, n_out, kpad, off;  // W[o][i]: o < n_out outputs, i < K_in inputs; tile rows N_in (inputs), K = kpad outputs
+    };
+    const T L[5] = {
+        {1, 64 * 63 + 64 + 64 * 64 + 64, 64, 64, 3, 16, FB_H2T},
+        {1, 64 * 63 + 64, 64, 64, 64, 64, FB_H1T},
+        {1, 0, 64, 63, 64, 64, FB_H0T},
+        {0, 64 * 32 + 64, 64, 64, 16, 16, FB_B1T},
+        {0, 0, 32, 32, 64, 64, FB_B0T},
+    };
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (int l = 0; l < 5; ++l) {
+        const T& y = L[l];
+        const float* src = y.head ? head : base;
+        __half* iw = reinterpret_cast<__half*>(img + FB_OFF + y.off);
+        for (int e = t; e < y.N_in * y.kpad; e += stride) {
+            const int i = e / y.kpad, o = e - i * y.kpad;
+            const float w = (i < y.K_in && o < y.n_out) ? __ldg(src + y.w_off + o * y.K_in + i) : 0.f;
+            iw[((o >> 3) * y.N_in + i) * 8 + (o & 7)] = __float2half_rn(w);
+        }
+    }
+}
+
+extern "C" int nvo_field_backward(void* stream, int64_t B, int32_t S, const void* feat16, const void* saved, int32_t save_pn, const void* wimage,
+                                  const float* rgb, const float* h0, const float* selector, const int64_t* cam_idx, const float* ddensity,
+                                  const float* drgb, const float* dpn_in, float* scratch, float* dfeat, float* dbase_params, float* dhead_params,
+                                  float* dembedding) {
+    NVO_CHECK(B >= 0 && S >= 32, "field_backward: bad shape B=%lld S=%d (at least 32 samples per ray: a warp's rows span at most two rays)", (long long)B, S);
+    if (B == 0) return 0;
+    NVO_CHECK(feat16 && saved && wimage && rgb && h0 && selector && drgb && scratch && dfeat && dbase_params && dhead_params, "field_backward: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = B * S;
+    cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * sizeof(float), st);
+    NVO_CHECK(e == cudaSuccess, "field_backward: memset: %s", cudaGetErrorString(e));
+    k_field_bwd_absmax<<<(unsigned int)min((int64_t)nvo_sm_count() * 4, (n + 255) / 256), 256, 0, st>>>(n, drgb, rgb, ddensity, selector, h0, scratch);
+    NVO_CUDA_LAUNCH_CHECK("field_backward(absmax)");
+    FieldBwdP p;
+    p.n = n, p.S = S, p.saved_chunks = save_pn ? FS_CHUNKS : FS_CHUNKS_HEAD, p.feat16 = (const unsigned char*)feat16, p.saved = (const unsigned char*)saved;
+    p.wimg = (const unsigned char*)wimage, p.rgb = rgb, p.h0 = h0, p.sel = selector, p.cam = cam_idx, p.ddensity = ddensity, p.drgb = drgb, p.dpn_in = dpn_in;
+    p.absmax = scratch, p.dfeat = dfeat, p.dbase = dbase_params, p.dhead = dhead_params, p.demb = dembedding;
+    const int G = field_groups();
+    const size_t smem = BW_GROUPS_OFF + (size_t)(G * BW_GROUP_CHUNKS + 2) * CHUNK_B + 8 * (1 + 4 * G) + 16;
+    const int64_t tiles = (n + TM - 1) / TM;
+    const unsigned int grid = (unsigned int)min((int64_t)nvo_sm_count(), (tiles + G - 1) / G);
+    if (G == 2) {
+        e = cudaFuncSetAttribute(k_field_bwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        NVO_CHECK(e == cudaSuccess, "field_backward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        k_field_bwd<2><<<grid, 2 * FT_THREADS + 32, smem, st>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(k_field_bwd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        NVO_CHECK(e == cudaSuccess, "field_backward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        k_field_bwd<3><<<grid, 3 * FT_THREADS + 32, smem, st>>>(p);
+    }
+    NVO_CUDA_LAUNCH_CHECK("field_backward");
     return 0;
 }

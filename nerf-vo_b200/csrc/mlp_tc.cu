@@ -43,6 +43,7 @@ struct TcP {
     int img_bytes;
     int saved_chunk_off[TC_MAX_LAYERS];                  // chunk offset of layer l's output inside a saved tile
     int saved_chunks;                                    // chunks per saved tile
+    int64_t x_tile_bytes, saved_tile_bytes;              // backward: byte strides between consecutive tiles of the input / saved buffers
     int a_off[TC_MAX_LAYERS];                            // backward: byte offset of layer l's INPUT tile inside the stage
     int stage_bytes;                                     // backward: bytes of the activation stage (every layer's input tile + ones/zero chunks)
     int wg_t[TC_MAX_LAYERS];                             // backward: 1 = weight gradient accumulated transposed (D[in][out], N = 16 columns)
@@ -346,9 +347,9 @@ __device__ __forceinline__ void bwd_fetch(const TcP& p, unsigned char* stage, in
     const uint32_t bytes = (uint32_t)p.kpad[l] * 256u;
     mbar_expect_tx(mbar, bytes);
     if (l == 0)
-        bulk_g2s(stage + p.a_off[0], x16 + tile * ((int64_t)p.k0pad * 256), bytes, mbar);
+        bulk_g2s(stage + p.a_off[0], x16 + tile * p.x_tile_bytes, bytes, mbar);
     else
-        bulk_g2s(stage + p.a_off[l], saved + (tile * p.saved_chunks + p.saved_chunk_off[l - 1]) * (int64_t)CHUNK_B, bytes, mbar);
+        bulk_g2s(stage + p.a_off[l], saved + tile * p.saved_tile_bytes + p.saved_chunk_off[l - 1] * (int64_t)CHUNK_B, bytes, mbar);
 }
 
 // dL/dz of the last layer for one (row, output o): dy * mask * act'(y)
@@ -673,6 +674,8 @@ static int make_tc_params(const nvo_mlp_desc* d, TcP* p) {
     }
     p->n_params = off;
     p->saved_chunks = chunks;
+    p->x_tile_bytes = (int64_t)p->k0pad * 256;
+    p->saved_tile_bytes = (int64_t)chunks * CHUNK_B;
     p->img_bytes = (ioff + 15) & ~15;
     // backward: weight-gradient orientation, TMEM columns and stage layout (transposed layers first, see k_mlp_tc_bwd)
     int col = MAXW;
@@ -773,10 +776,13 @@ extern "C" int nvo_mlp_tc_forward(const nvo_mlp_desc* d, void* stream, int64_t n
     return 0;
 }
 
-extern "C" int nvo_mlp_tc_backward(const nvo_mlp_desc* d, void* stream, int64_t n, const void* x16, const void* wimage, const void* saved, const float* y,
-                                   const float* row_mask, const float* dy, float dy_absmax_hint, float* scratch, float* dx, float* dparams) {
+static int mlp_tc_backward_impl(const nvo_mlp_desc* d, void* stream, int64_t n, const void* x16, int64_t x_tile_bytes, const void* wimage, const void* saved,
+                                int64_t saved_tile_bytes, const float* y, const float* row_mask, const float* dy, float dy_absmax_hint, float* scratch, float* dx,
+                                float* dparams) {
     TcP p;
     if (int e = make_tc_params(d, &p)) return e;
+    if (x_tile_bytes > 0) p.x_tile_bytes = x_tile_bytes;
+    if (saved_tile_bytes > 0) p.saved_tile_bytes = saved_tile_bytes;
     NVO_CHECK(n >= 0, "mlp_tc_backward: negative batch");
     if (n == 0) return 0;
     NVO_CHECK(x16 && wimage && dy && scratch, "mlp_tc_backward: null pointer");
@@ -805,4 +811,18 @@ extern "C" int nvo_mlp_tc_backward(const nvo_mlp_desc* d, void* stream, int64_t 
                                          dy_absmax_hint, dx, dparams, w_off, ctrl);
     NVO_CUDA_LAUNCH_CHECK("mlp_tc_backward");
     return 0;
+}
+
+extern "C" int nvo_mlp_tc_backward(const nvo_mlp_desc* d, void* stream, int64_t n, const void* x16, const void* wimage, const void* saved, const float* y,
+                                   const float* row_mask, const float* dy, float dy_absmax_hint, float* scratch, float* dx, float* dparams) {
+    return mlp_tc_backward_impl(d, stream, n, x16, 0, wimage, saved, 0, y, row_mask, dy, dy_absmax_hint, scratch, dx, dparams);
+}
+
+// the same with the input tiles / saved-activation tiles embedded in larger per-tile records (the fused field kernel's saved tiles):
+// consecutive tiles lie x_tile_bytes / saved_tile_bytes apart
+extern "C" int nvo_mlp_tc_backward_strided(const nvo_mlp_desc* d, void* stream, int64_t n, const void* x16, int64_t x_tile_bytes, const void* wimage,
+                                           const void* saved, int64_t saved_tile_bytes, const float* y, const float* row_mask, const float* dy,
+                                           float dy_absmax_hint, float* scratch, float* dx, float* dparams) {
+    NVO_CHECK(x_tile_bytes > 0 && saved_tile_bytes > 0 && (x_tile_bytes & 15) == 0 && (saved_tile_bytes & 15) == 0, "mlp_tc_backward_strided: bad tile strides");
+    return mlp_tc_backward_impl(d, stream, n, x16, x_tile_bytes, wimage, saved, saved_tile_bytes, y, row_mask, dy, dy_absmax_hint, scratch, dx, dparams);
 }

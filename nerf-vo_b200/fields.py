@@ -132,10 +132,14 @@ class NerfactoField(Field):
                  features_per_level: int = 2, hidden_dim_color: int = 64, hidden_dim_transient: int = 64, appearance_embedding_dim: int = 32,
                  transient_embedding_dim: int = 16, use_transient_embedding: bool = False, use_semantics: bool = False, num_semantic_classes: int = 100,
                  pass_semantic_gradients: bool = False, use_pred_normals: bool = False, use_average_appearance_embedding: bool = False,
-                 spatial_distortion: Optional[nn.Module] = None, implementation: str = "nvo_b200", precision: str = "fp16") -> None:
+                 spatial_distortion: Optional[nn.Module] = None, implementation: str = "nvo_b200", precision: str = "fp16",
+                 pred_normals_trainable: bool = True) -> None:
         """precision: "fp16" = hash features and the three MLPs on the tcgen05 tensor-core path (fp16 operands, fp32 accumulate,
-        fp32 master parameters — tinycudann's operating point); "fp32" = exact-arithmetic SIMT kernels (bit-level parity runs)."""
+        fp32 master parameters — tinycudann's operating point); "fp32" = exact-arithmetic SIMT kernels (bit-level parity runs).
+        pred_normals_trainable=False: mlp_pred_normals is evaluated but its activations are not kept for a backward pass (NeRF-VO trains
+        with pred_normal_loss_mult = 0, nerf_vo/mapping/nerfstudio.py:74-75); a gradient arriving at pred_normals then raises."""
         super().__init__()
+        self.pred_normals_trainable = pred_normals_trainable
         if precision not in ("fp16", "fp32"):
             raise ValueError(f"precision must be 'fp16' or 'fp32', got {precision}")
         self.precision = precision
@@ -182,6 +186,30 @@ class NerfactoField(Field):
                          self._pn_spec))
         return nets
 
+    def _pn_params(self):
+        if not self.use_pred_normals:
+            return []
+        return self.mlp_pred_normals._flat_param_list() + [self.field_head_pred_normals.net.weight, self.field_head_pred_normals.net.bias]
+
+    def _fused(self, S: int, on_cuda: bool) -> bool:
+        """forward() as the fused kernels of csrc/field_tc.cu (one launch per direction for all three networks)?"""
+        return (self.precision == "fp16" and on_cuda and
+                ops.field_fused_supported(self.mlp_base.encoder.spec, self.mlp_base.mlp.spec, self.mlp_head.spec,
+                                          self._pn_spec if self.use_pred_normals else None, S))
+
+    def prepack(self, S: int) -> None:
+        """Trainer hook: pack this step's fp16 weight image(s) on a side stream, ahead of the forward that consumes them."""
+        if self.precision != "fp16":
+            return
+        if self._fused(S, True):
+            groups = [self.mlp_base.mlp._flat_param_list(), self.mlp_head._flat_param_list(), self._pn_params()]
+            for ps in groups:
+                if ps:
+                    repack(ps)
+            ops.prepack_field_weights(self.mlp_base.encoder.spec, groups[0], groups[1], groups[2] or None)
+        else:
+            ops.prepack_weights(self.tc_networks())
+
     def _remember(self, x, h, shape, tc=None) -> None:
         """State get_normals() needs (base_field.py:80-101 keeps _sample_locations / _density_before_activation).  Stored
         DETACHED: normals are first-order and graph-free, and holding autograd nodes across steps would pin the previous
@@ -214,6 +242,8 @@ class NerfactoField(Field):
         """-normalize(d raw_density / d x_normalised) (NS/fields/base_field.py:80-101), first order only, no graph."""
         c = self._cache
         assert c is not None, "Sample locations must be set before calling get_normals."
+        if c.get("normals") is not None:  # the fused forward evaluated them in the same kernel
+            return c["normals"].view(*c["shape"], 3)
         with torch.no_grad():
             enc, mlp = self.mlp_base.encoder, self.mlp_base.mlp
             mlp._repack()
@@ -301,10 +331,28 @@ class NerfactoField(Field):
         B, S = fr.shape
         positions = fr.get_positions()
         x, sel = ops.contract_normalize(positions)
-        h, tc = self._base(x, want_normals=compute_normals)
-        self._remember(x, h, (B, S), tc)
         dirs = fr.directions.reshape(B, 3).contiguous()
         cam, emb = self._appearance(ray_samples, B, dirs.device)
+        if self._fused(S, x.is_cuda):
+            enc = self.mlp_base.encoder
+            groups = [self.mlp_base.mlp._flat_param_list(), self.mlp_head._flat_param_list(), self._pn_params()]
+            for ps in groups:
+                if ps:
+                    repack(ps)
+            density, rgb, pn, normals, h0 = ops.field_fused(
+                x, enc.hash_table, emb, sel, positions.reshape(-1, 3), dirs, cam, B, S, enc.spec, compute_normals, groups[0], groups[1],
+                self._pn_spec if self.use_pred_normals else None, groups[2], save_pn=self.pred_normals_trainable)
+            self._cache = {"x": x.detach(), "shape": (B, S), "tc": None, "normals": normals}
+            self._sample_locations = self._cache["x"].view(B, S, 3)
+            self._density_before_activation = h0.view(B, S, 1)
+            out = {FieldHeadNames.RGB: rgb.view(B, S, 3), FieldHeadNames.DENSITY: density.view(B, S, 1)}
+            if pn is not None:
+                out[FieldHeadNames.PRED_NORMALS] = pn.view(B, S, 3)
+            if compute_normals:
+                out[FieldHeadNames.NORMALS] = normals.view(B, S, 3)
+            return out
+        h, tc = self._base(x, want_normals=compute_normals)
+        self._remember(x, h, (B, S), tc)
         normals = side_n = None
         if self.precision == "fp16" and compute_normals and ops.leaf_streams.enabled and x.is_cuda and ops.env_flag("NVO_FIELD_BRANCHES", True):
             # density-gradient normals (base network's input-gradient chain + saved-Jacobian product) depend on the base network only:

@@ -79,7 +79,8 @@ class NerfactoModel(nn.Module):
                                    features_per_level=c.features_per_level, log2_hashmap_size=c.log2_hashmap_size, hidden_dim_color=c.hidden_dim_color,
                                    hidden_dim_transient=c.hidden_dim_transient, spatial_distortion=contraction, num_images=num_train_data,
                                    use_pred_normals=c.predict_normals, use_average_appearance_embedding=c.use_average_appearance_embedding,
-                                   appearance_embedding_dim=c.appearance_embed_dim, precision=c.precision)
+                                   appearance_embedding_dim=c.appearance_embed_dim, precision=c.precision,
+                                   pred_normals_trainable=c.pred_normal_loss_mult != 0)
         self.proposal_networks = nn.ModuleList()
         for i in range(c.num_proposal_iterations):
             args = c.proposal_net_args_list[min(i, len(c.proposal_net_args_list) - 1)]

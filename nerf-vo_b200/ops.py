@@ -1130,6 +1130,7 @@ def prepack_weights(nets) -> None:
 
 def clear_prepacked() -> None:
     _prepacked.clear()
+    _field_prepacked.clear()
 
 
 def mlp_tc_forward(x16, wimage, spec: MlpSpec, n: int, save: bool, row_mask=None):
@@ -1377,18 +1378,48 @@ def field_heads_tc(h, embedding, selector, directions, positions, cam_idx, B, S,
 # ------------------------------------------------------------------------------------------------
 
 
+_field_prepacked: dict = {}  # mlp_base parameter pointer -> (weight image, ready event), see prepack_field_weights
+
+
 def field_pack_weights(gspec: GridSpec, base_flat, head_flat, pn_flat=None):
     """fp32 torch-layout parameters of the three field networks -> the fused kernels' fp16 weight image (uint8 tensor)."""
     check(base_flat, "mlp_base params", torch.float32, (32 * 64 + 64 + 64 * 16 + 16,))
     check(head_flat, "mlp_head params", torch.float32, (63 * 64 + 64 + 64 * 64 + 64 + 64 * 3 + 3,))
     if pn_flat is not None:
         check(pn_flat, "mlp_pred_normals (+ head) params", torch.float32, (27 * 64 + 64 + 2 * (64 * 64 + 64) + 64 * 3 + 3,))
+    hit = _field_prepacked.get(base_flat.data_ptr())
+    if hit is not None:
+        torch.cuda.current_stream().wait_event(hit[1])
+        return hit[0]
     img = torch.empty(int(_lib.load().nvo_field_wimage_bytes()), dtype=torch.uint8, device=base_flat.device)
     call("nvo_field_pack_weights", gspec.desc(torch.float32, "tmh"), base_flat, head_flat, pn_flat, img)
     return img
 
 
-def field_forward(feat16, jac, positions, directions, cam_idx, embedding, selector, wimage, B: int, S: int, want_pn: bool, save: bool):
+def prepack_field_weights(gspec: GridSpec, base_params, head_params, pn_params=None) -> None:
+    """The fused field kernels' weight image packed ahead of its use on a side stream (the parameters only change in the optimizer);
+    field_pack_weights() hands it out after waiting for the ready event.  Cleared by clear_prepacked()."""
+    base_flat, head_flat = _flat_of(base_params), _flat_of(head_params)
+    pn_flat = _flat_of(pn_params) if pn_params else None
+    img = torch.empty(int(_lib.load().nvo_field_wimage_bytes()), dtype=torch.uint8, device=base_flat.device)
+    with leaf_streams.fork(img):
+        call("nvo_field_pack_weights", gspec.desc(torch.float32, "tmh"), base_flat, head_flat, pn_flat, img)
+        ev = torch.cuda.Event()
+        ev.record()
+    _field_prepacked[base_flat.data_ptr()] = (img, ev)
+
+
+def field_fused_supported(gspec: GridSpec, base_spec: MlpSpec, head_spec: MlpSpec, pn_spec: Optional[MlpSpec], S: int) -> bool:
+    """The fused kernels are specialised for nerfacto's default field: 16 x 2 hash features -> 64 -> 16, head 63 -> 64 -> 64 -> 3,
+    pred-normals 27 -> 64 -> 64 -> 64 -> 3 (csrc/field_tc.cu); at least 32 samples per ray (the backward's per-ray embedding reduction)."""
+    ok = gspec.n_levels == 16 and gspec.features_per_level == 2 and base_spec.in_dim == 32 and tuple(base_spec.dims) == (64, 16)
+    ok = ok and head_spec.in_dim == 63 and tuple(head_spec.dims) == (64, 64, 3)
+    if pn_spec is not None:
+        ok = ok and pn_spec.in_dim == 27 and tuple(pn_spec.dims) == (64, 64, 64, 3)
+    return ok and S >= 32 and not env_flag("NVO_FIELD_PER_NETWORK", False)
+
+
+def field_forward(feat16, jac, positions, directions, cam_idx, embedding, selector, wimage, B: int, S: int, want_pn: bool, save: bool, save_pn: bool = False):
     """One launch: (density [n], rgb [n,3], pred_normals [n,3] | None, normals [n,3] | None, h0 [n], pn_raw [n,3] | None, saved | None).
     jac (the grid forward's saved derivatives) enables the density-gradient normals."""
     n = B * S
@@ -1410,9 +1441,133 @@ def field_forward(feat16, jac, positions, directions, cam_idx, embedding, select
     pn = f(n, 3) if want_pn else None
     pn_raw = f(n, 3) if want_pn else None
     normals = f(n, 3) if jac is not None else None
-    saved = torch.empty(int(_lib.load().nvo_field_saved_bytes(n)), dtype=torch.uint8, device=dev) if save else None
-    call("nvo_field_forward", B, S, feat16, jac, positions, directions, cam_idx, embedding, selector, wimage, density, rgb, pn, normals, h0, pn_raw, saved)
+    saved = torch.empty(int(_lib.load().nvo_field_saved_bytes(n, int(save_pn))), dtype=torch.uint8, device=dev) if save else None
+    call("nvo_field_forward", B, S, feat16, jac, positions, directions, cam_idx, embedding, selector, wimage, density, rgb, pn, normals, h0, pn_raw, saved,
+         int(save_pn))
     return density, rgb, pn, normals, h0, pn_raw, saved
+
+
+FS_CHUNKS, FS_CHUNKS_HEAD, FS_P, FS_AP1, CHUNK_B = 60, 32, 32, 36, 2048  # saved-tile layout of csrc/field_tc.cu
+
+
+def field_backward(feat16, saved, save_pn: bool, wimage, rgb, h0, selector, cam_idx, ddensity, drgb, dpn_in, B: int, S: int, dbase, dhead, demb):
+    """One launch: returns dfeat (fp32 TMF [tiles][32][128]); ACCUMULATES into dbase / dhead / demb."""
+    n = B * S
+    check(drgb, "drgb", torch.float32, (n, 3))
+    if ddensity is not None:
+        check(ddensity, "ddensity", torch.float32, (n,))
+    dfeat = torch.empty(tmh_numel(n, 32), dtype=torch.float32, device=feat16.device)
+    scratch = torch.empty(2, dtype=torch.float32, device=feat16.device)
+    call("nvo_field_backward", B, S, feat16, saved, int(save_pn), wimage, rgb, h0, selector, cam_idx, ddensity, drgb, dpn_in, scratch, dfeat, dbase, dhead, demb)
+    return dfeat
+
+
+class _FieldFused(torch.autograd.Function):
+    """NerfactoField.forward on the fused tensor-core path (csrc/field_tc.cu): hash grid (+ saved d feature / dx) -> ONE kernel for mlp_base,
+    density-gradient normals, input assembly, mlp_head and mlp_pred_normals; backward: ONE kernel for mlp_head, assembly and mlp_base
+    (+ the per-network kernel on the saved tiles for mlp_pred_normals when it receives a gradient), then the table scatter.
+    Returns density [n], rgb [n,3], pred_normals [n,3] | None, normals [n,3] | None (no gradient: base_field.py:92-97 is first order),
+    h0 [n] (raw density, no gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, table, embedding, selector, positions, directions, cam_idx, B, S, gspec, want_normals, save_pn, pn_spec, n_base, n_head, *params):
+        ctx.set_materialize_grads(False)
+        n = B * S
+        base_params, head_params, pn_params = params[:n_base], params[n_base:n_base + n_head], params[n_base + n_head:]
+        want_pn = len(pn_params) > 0
+        x = x.contiguous()
+        if want_normals:
+            feat16, jac = grid_forward_jac(x, table, gspec)
+        else:
+            feat16, jac = grid_forward(x, table, gspec, "tmh"), None
+        wimage = field_pack_weights(gspec, _flat_of(base_params), _flat_of(head_params), _flat_of(pn_params) if want_pn else None)
+        need = any(ctx.needs_input_grad)
+        embedding = check(embedding.contiguous(), "appearance embedding", torch.float32)
+        density, rgb, pn, normals, h0, pn_raw, saved = field_forward(feat16, jac, positions if want_pn else None, directions, cam_idx, embedding, selector,
+                                                                     wimage, B, S, want_pn, need, bool(save_pn and want_pn))
+        # a trainable mlp_pred_normals runs its backward through the per-network kernel (its own weight-image format)
+        pn_wimage = tc_pack_weights(_flat_of(pn_params), pn_spec) if (need and save_pn and want_pn) else None
+        ctx.save_for_backward(x, table, feat16, wimage, saved, rgb, h0, selector, cam_idx, pn_raw, pn_wimage)
+        ctx.B, ctx.S, ctx.gspec, ctx.pn_spec, ctx.save_pn, ctx.emb_shape = B, S, gspec, pn_spec, bool(save_pn and want_pn), embedding.shape
+        ctx.n_base, ctx.n_head, ctx.n_pn = n_base, n_head, len(pn_params)
+        ctx.base_spec_shapes = [tuple(p.shape) for p in base_params]
+        ctx.head_spec_shapes = [tuple(p.shape) for p in head_params]
+        ctx.pn_shapes = [tuple(p.shape) for p in pn_params]
+        ctx.table_main_grad = getattr(table, "_nvo_main_grad", None)
+        ctx.emb_main_grad = getattr(embedding, "_nvo_main_grad", None)
+        ctx.base_main_grad = getattr(base_params[0], "_nvo_main_grad", None)
+        ctx.head_main_grad = getattr(head_params[0], "_nvo_main_grad", None)
+        ctx.pn_main_grad = getattr(pn_params[0], "_nvo_main_grad", None) if want_pn else None
+        nd = [t for t in (normals, h0) if t is not None]
+        ctx.mark_non_differentiable(*nd)
+        return density, rgb, pn, normals, h0
+
+    @staticmethod
+    def backward(ctx, ddensity, drgb, dpn, _dnormals, _dh0):
+        x, table, feat16, wimage, saved, rgb, h0, selector, cam_idx, pn_raw, pn_wimage = ctx.saved_tensors
+        B, S = ctx.B, ctx.S
+        n, dev = B * S, x.device
+        c = lambda t: None if t is None else t.contiguous()
+        if drgb is None:
+            drgb = torch.zeros((n, 3), dtype=torch.float32, device=dev)
+        flat_numel = lambda shapes: sum(int(np.prod(s)) for s in shapes)
+        zeros = lambda k: torch.zeros(k, dtype=torch.float32, device=dev)
+        # mlp_pred_normals: Normalize' -> the per-network tensor-core backward reading its input / activations out of the fused saved tiles
+        dpn_in = dpn_flat = None
+        if dpn is not None and ctx.n_pn:
+            if not ctx.save_pn:
+                raise RuntimeError("fused field: pred_normals received a gradient but its activations were not saved (construct the field with "
+                                   "pred_normals_trainable=True)")
+            dpn_raw = torch.empty_like(pn_raw)
+            call("nvo_normalize3_backward", n, pn_raw, dpn.contiguous(), 1.0, 1e-12, dpn_raw)
+            spec = ctx.pn_spec
+            dpn_in = torch.empty(tmh_numel(n, spec.in_dim), dtype=torch.float32, device=dev)
+            dpn_flat = ctx.pn_main_grad if ctx.pn_main_grad is not None else zeros(spec.n_params)
+            scratch = torch.empty(1, dtype=torch.float32, device=dev)
+            tile_bytes = FS_CHUNKS * CHUNK_B
+            call("nvo_mlp_tc_backward_strided", spec.desc, n, saved[FS_P * CHUNK_B:], tile_bytes, pn_wimage, saved[FS_AP1 * CHUNK_B:], tile_bytes, pn_raw, None,
+                 dpn_raw, 0.0, scratch, dpn_in, dpn_flat)
+        dbase = ctx.base_main_grad if ctx.base_main_grad is not None else zeros(flat_numel(ctx.base_spec_shapes))
+        dhead = ctx.head_main_grad if ctx.head_main_grad is not None else zeros(flat_numel(ctx.head_spec_shapes))
+        demb = None
+        if ctx.needs_input_grad[2]:
+            demb = ctx.emb_main_grad if (ctx.emb_main_grad is not None and cam_idx is not None) else torch.zeros(ctx.emb_shape, dtype=torch.float32, device=dev)
+        dfeat = field_backward(feat16, saved, ctx.save_pn, wimage, rgb, h0, selector, cam_idx, c(ddensity), drgb.contiguous(), dpn_in, B, S, dbase, dhead, demb)
+        need_dx, need_dt = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dtable = dx = None
+        if need_dt:
+            if ctx.table_main_grad is not None and leaf_streams.enabled:
+                with leaf_streams.fork(x, dfeat):
+                    grid_backward(x, dfeat, ctx.gspec, dtable=ctx.table_main_grad, tmf=True)
+                    if leaf_streams.after_field_backward is not None and not need_dx:
+                        leaf_streams.after_field_backward()
+            elif ctx.table_main_grad is not None:
+                grid_backward(x, dfeat, ctx.gspec, dtable=ctx.table_main_grad, tmf=True)
+            else:
+                dtable = grid_backward(x, dfeat, ctx.gspec, tmf=True).view(table.shape)
+        if need_dx:
+            dx = grid_backward_input(x, table, dfeat, ctx.gspec, tmf=True)
+
+        def split(flat, shapes, main):
+            if main is not None or flat is None:
+                return [None] * len(shapes)
+            out, off = [], 0
+            for s in shapes:
+                k = int(np.prod(s))
+                out.append(flat[off:off + k].view(s))
+                off += k
+            return out
+
+        if demb is ctx.emb_main_grad:
+            demb = None
+        grads = split(dbase, ctx.base_spec_shapes, ctx.base_main_grad) + split(dhead, ctx.head_spec_shapes, ctx.head_main_grad) + split(dpn_flat, ctx.pn_shapes, ctx.pn_main_grad)
+        return (dx, dtable, demb, None, None, None, None, None, None, None, None, None, None, None, None, *grads)
+
+
+def field_fused(x, table, embedding, selector, positions, directions, cam_idx, B: int, S: int, gspec: GridSpec, want_normals: bool, base_params, head_params,
+                pn_spec: Optional[MlpSpec] = None, pn_params=(), save_pn: bool = True):
+    return _FieldFused.apply(x, table, embedding, selector, positions, directions, cam_idx, B, S, gspec, want_normals, save_pn, pn_spec, len(base_params),
+                             len(head_params), *base_params, *head_params, *pn_params)
 
 
 # ------------------------------------------------------------------------------------------------

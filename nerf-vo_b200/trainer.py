@@ -196,8 +196,7 @@ class MappingTrainer:
             # run on side streams next to the proposal sampling; both are joined before their first consumer
             with ops.leaf_streams.fork(self.grad):
                 self.grad.zero_()
-            if self.model.field.precision == "fp16":
-                ops.prepack_weights(self.model.field.tc_networks())
+            self.model.field.prepack(self.model.config.num_nerf_samples_per_ray)
         else:
             self.grad.zero_()
         if self.datamanager is not None:

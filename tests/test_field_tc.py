@@ -93,3 +93,73 @@ def test_field_forward_fused_vs_fp32_oracle():
     assert float((pn.cpu() - fo["pred_normals"].reshape(n, 3)).abs().max()) < 2e-2
     nerr = (normals.cpu() - fo["normals"].reshape(n, 3)).abs().max(dim=-1)[0]
     assert float((nerr > 2e-2).float().mean()) < 0.05
+
+
+def _loss_and_grads(nv, field, rs, B, S, with_pn, seed=5):
+    """A fixed random linear functional of (density, rgb, pred_normals) -> its gradient w.r.t. every field parameter."""
+    from nerf_vo_b200.fields import FieldHeadNames as F
+
+    g = torch.Generator().manual_seed(seed)
+    wd, wr, wp = (torch.randn(B, S, k, generator=g).to(DEV) for k in (1, 3, 3))
+    for p in field.parameters():
+        p.grad = None
+    out = field.forward(rs, compute_normals=True)
+    loss = (out[F.DENSITY].clamp(max=50.0) * wd * 1e-2).sum() + (out[F.RGB] * wr).sum()
+    if with_pn:
+        loss = loss + (out[F.PRED_NORMALS] * wp).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    grads = {k: p.grad.detach().clone() for k, p in field.named_parameters() if p.grad is not None}
+    return {k: v.detach() for k, v in out.items()}, grads
+
+
+@pytest.mark.parametrize("B,with_pn,train", [(64, False, True), (300, True, True), (37, False, True), (2048, False, True)])
+def test_field_fused_backward_vs_per_network_kernels(B, with_pn, train):
+    """Fused forward + backward (one launch per direction) against the per-network tensor-core kernels (oracle-checked in
+    tests/test_gpu_parity.py): same operand precision, so the gradients agree to fp16-rounding noise."""
+    import nerf_vo_b200 as nv
+    from nerf_vo_b200.fields import FieldHeadNames as F
+
+    S = 48
+    field = _field(nv).to(DEV).train(train)
+    _, _, rs = _samples(nv, field, B, S)
+    res = {}
+    for mode in (True, False):
+        nv.ops._env_cache["NVO_FIELD_PER_NETWORK"] = mode
+        try:
+            assert field._fused(S, True) == (not mode)
+            res[mode] = _loss_and_grads(nv, field, rs, B, S, with_pn)
+        finally:
+            nv.ops._env_cache.pop("NVO_FIELD_PER_NETWORK", None)
+    (o_ref, g_ref), (o_fus, g_fus) = res[True], res[False]
+    assert float((o_fus[F.RGB] - o_ref[F.RGB]).abs().max()) < 4e-3
+    assert set(g_ref) == set(g_fus), (sorted(set(g_ref) ^ set(g_fus)))
+    for k in sorted(g_ref):
+        a, b = g_fus[k].float(), g_ref[k].float()
+        scale = float(b.abs().max())
+        if scale == 0.0:
+            assert float(a.abs().max()) == 0.0, k
+            continue
+        rel_l2 = float((a - b).norm() / b.norm())
+        rel_max = float((a - b).abs().max()) / scale
+        if "hash_table" in k:
+            # sparse: an entry is the sum of a handful of samples, one ReLU-mask flip (fp16 bias inside the MMA) moves it by O(1) of itself
+            frac = float(((a - b).abs() > 3e-2 * scale).float().mean())
+            assert rel_l2 < 3e-2 and frac < 1e-3, (k, rel_l2, rel_max, frac)
+        else:
+            # measured: <= 1.4e-2 / 3.6e-2 (mlp_pred_normals.layers.1.weight, the end of a four-layer chain)
+            assert rel_l2 < 2e-2 and rel_max < (5e-2 if "pred_normals" in k else 3e-2), (k, rel_l2, rel_max)
+    if not with_pn:
+        assert not any("pred_normals" in k for k in g_fus)
+
+
+def test_field_fused_untrainable_pred_normals_raise():
+    import nerf_vo_b200 as nv
+    from nerf_vo_b200.fields import FieldHeadNames as F
+
+    field = _field(nv).to(DEV).train()
+    field.pred_normals_trainable = False
+    _, _, rs = _samples(nv, field, 64, 48)
+    out = field.forward(rs)
+    with pytest.raises(RuntimeError, match="pred_normals"):
+        out[F.PRED_NORMALS].sum().backward()

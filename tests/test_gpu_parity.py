@@ -411,10 +411,13 @@ def test_field_get_density_then_get_outputs_golden(nv, golden, precision):
     nerr = (normals.cpu() - torch.from_numpy(g["field.normals"])).abs().max(dim=-1)[0]
     assert float((nerr > 2e-3).float().mean()) < (1e-3 if precision == "fp32" else 0.05)
     # same numbers as the fused forward()
+    # forward(): the same arithmetic on the exact path; on the tensor-core path forward() is the fused kernel (biases ride in the MMA as
+    # fp16 operands) while get_density / get_outputs evaluate one network per launch (fp32 bias add): agreement at fp16 rounding level
     ff = m.field.forward(rs, compute_normals=True)
-    assert float((ff[F.RGB] - fo[F.RGB]).abs().max()) < 1e-6
-    assert float((ff[F.PRED_NORMALS] - fo[F.PRED_NORMALS]).abs().max()) < 1e-6
-    assert rel_err(ff[F.DENSITY], density) < 1e-6
+    t_rgb, t_pn, t_d = (1e-6, 1e-6, 1e-6) if precision == "fp32" else (4e-3, 2e-2, 2e-2)
+    assert float((ff[F.RGB] - fo[F.RGB]).abs().max()) < t_rgb
+    assert float((ff[F.PRED_NORMALS] - fo[F.PRED_NORMALS]).abs().max()) < t_pn
+    assert rel_err(ff[F.DENSITY], density) < t_d
     # gradients flow through both calls: head parameters, appearance embedding, and (through the embedding) the base network
     (fo[F.RGB].sum() + density.sum() * 1e-3).backward()
     assert m.field.mlp_head.layers[0].weight.grad is not None and float(m.field.mlp_head.layers[0].weight.grad.abs().max()) > 0
