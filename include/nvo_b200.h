@@ -280,6 +280,20 @@ int nvo_depth_loss_backward(void* stream, int64_t B, int32_t S, const float* wei
 /* MSELoss on [B,3] (NS/models/nerfacto.py:362) and monosdf_normal_loss (losses.py:327-342); d_pred is overwritten with scale*grad */
 int nvo_mse_loss(void* stream, int64_t n, const float* pred, const float* target, float scale, float* loss, float* d_pred);
 int nvo_normal_loss(void* stream, int64_t B, const float* pred /*[B,3]*/, const float* gt /*[B,3]*/, float scale, float* loss, float* d_pred);
+/* Every loss of the NeRF-VO mapping step (nerf_vo/mapping/nerfstudio.py:71-82; NS/models/nerfacto.py:354-381, depth_nerfacto.py:79-125,
+ * nerf_vo/mapping/nerfstudio_utils.py:333-350) and its gradient for grad_output == 1 in ONE launch: w_l [B,S_l] weights of proposal level 0,
+ * proposal level 1 and the field (l = 2), sdist_l [B,S_l+1] normalised bin edges, starts_l / ends_l Euclidean interval ends (row stride_l;
+ * read only with depth_gt), rgb / rgb_gt [B,3], normals / normal_gt [B,3] (nullable), depth_gt / directions_norm [B] (nullable).
+ * terms[5] (zeroed by the caller) receives the unweighted batch means [rgb, interlevel, distortion, depth summed over the levels, normal],
+ * total[1] = sum mult_i terms_i (written by the last CTA; ticket: one zero-initialised uint32 the kernel leaves zero), dw_l [B,S_l],
+ * d_rgb [B,3], d_normals [B,3] (nullable) are WRITTEN with mult * d term / d input. */
+int nvo_step_losses(void* stream, int64_t B, int32_t S0, int32_t S1, int32_t S2, const float* w0, const float* w1, const float* w2,
+                    const float* sdist0, const float* sdist1, const float* sdist2, const float* starts0, const float* ends0, int64_t stride0,
+                    const float* starts1, const float* ends1, int64_t stride1, const float* starts2, const float* ends2, int64_t stride2,
+                    const float* rgb, const float* rgb_gt, const float* normals, const float* normal_gt, const float* depth_gt,
+                    const float* directions_norm, float sigma, float mult_rgb, float mult_interlevel, float mult_distortion, float mult_depth,
+                    float mult_normal, float* terms, float* total, void* ticket, float* dw0, float* dw1, float* dw2, float* d_rgb,
+                    float* d_normals);
 
 /* ---------------------------------------------------------------------------------------------
  * Step prologue: pixel sampling + pixel gather + ray generation + camera-pose correction in ONE launch —

@@ -331,3 +331,253 @@ extern "C" int nvo_normal_loss(void* stream, int64_t B, const float* pred, const
     NVO_CUDA_LAUNCH_CHECK("normal_loss");
     return 0;
 }
+
+// ================================================================================================================================
+// The whole loss wave of one mapping step in ONE launch (the trainer's path: the step differentiates the total with grad_output == 1):
+// every term above plus its gradient w.r.t. the three weight sets, the rendered colour and the rendered normals, per ray by one warp,
+// and the weighted total by the last CTA to finish.  Same per-ray arithmetic, in the same order, as the kernels above (the two levels'
+// gradient buffers receive interlevel + depth in that order); what disappears is 14 launches spread over four streams, three zero
+// fills and the cuBLAS dot of the five terms, i.e. ~60 us of launch latency between the renderer and the backward pass.
+// ================================================================================================================================
+struct StepLossP {
+    int64_t B;
+    int S[3];                  // samples per level (proposal 0, proposal 1, final)
+    const float* w[3];         // [B,S_l]
+    const float* sdist[3];     // [B,S_l+1] normalised bin edges
+    const float* starts[3];    // Euclidean interval starts / ends (row stride `stride[l]`), depth loss
+    const float* ends[3];
+    int64_t stride[3];
+    const float *rgb, *rgb_gt;           // [B,3]
+    const float *normals, *normal_gt;    // [B,3] or null
+    const float *depth_gt, *dnorm;       // [B] or null
+    float sigma;
+    float mults[5];            // rgb, interlevel, distortion, depth (per level), normal
+    float* terms;              // [5] unweighted batch means, accumulated (zeroed by the caller)
+    float* total;              // [1] written by the last CTA
+    unsigned int* ticket;      // [1] zero before the launch; reset by the last CTA
+    float* dw[3];              // [B,S_l] written
+    float* d_rgb;              // [B,3] written
+    float* d_normals;          // [B,3] written, or null
+};
+
+__global__ void __launch_bounds__(32 * RAYS_PER_BLOCK) k_step_losses(const __grid_constant__ StepLossP p) {
+    extern __shared__ float smf[];
+    __shared__ float red[RAYS_PER_BLOCK][5];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t r = (int64_t)blockIdx.x * RAYS_PER_BLOCK + wid;
+    const bool live = r < p.B;
+    const int S = p.S[2];
+    const int npmax = max(p.S[0], p.S[1]) + 1;
+    // per warp: wf[S], cf[S+1], m[S], then cy1 / cps / E [npmax] each
+    float* wf = smf + wid * (3 * S + 1 + 3 * npmax);
+    float* cf = wf + S;
+    float* mid = cf + S + 1;
+    float* cy1 = mid + S;
+    float* cps = cy1 + npmax;
+    float* E = cps + npmax;
+    float t_rgb = 0.f, t_inter = 0.f, t_dist = 0.f, t_depth = 0.f, t_normal = 0.f;
+    if (live) {
+        const float B_f = (float)p.B;
+        const bool use_depth = p.depth_gt != nullptr;
+        const float D = use_depth ? __ldg(p.depth_gt + r) * __ldg(p.dnorm + r) : 0.f;
+        const bool dmask = D > 0.f;
+        const float two_sigma = 2.f * p.sigma;
+        const float g_depth = p.mults[3] / B_f;
+        for (int i = lane; i < S; i += 32) wf[i] = __ldg(p.w[2] + r * S + i);
+        for (int i = lane; i <= S; i += 32) cf[i] = __ldg(p.sdist[2] + r * (S + 1) + i);
+        __syncwarp();
+        // ---- proposal levels: interlevel (fwd + bwd) and depth (fwd + bwd) ------------------------------------------------------------
+        for (int l = 0; l < 2; ++l) {
+            const int Sp = p.S[l], np = Sp + 1;
+            const float* wp = p.w[l] + r * Sp;
+            double carry = 0.0;
+            for (int c0 = 0; c0 < Sp; c0 += 32) {
+                const int i = c0 + lane;
+                const float v = i < Sp ? __ldg(wp + i) : 0.f;
+                const double incl = nvo_warp_scan_incl((double)v, lane);
+                if (i < Sp) cy1[i + 1] = (float)(carry + incl);
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) cy1[0] = 0.f;
+            for (int i = lane; i < np; i += 32) {
+                cps[i] = __ldg(p.sdist[l] + r * np + i);
+                E[i] = 0.f;
+            }
+            __syncwarp();
+            const float g_scale = p.mults[1] / (B_f * (float)S);
+            float ray_loss = 0.f;
+            for (int i = lane; i < S; i += 32) {
+                const float t0s = cf[i], t0e = cf[i + 1];
+                int lo = 0, hi = Sp;
+                while (lo < hi) {
+                    const int md = (lo + hi) >> 1;
+                    if (cps[md] <= t0s) lo = md + 1; else hi = md;
+                }
+                const int idx_lo = min(max(lo - 1, 0), Sp - 1);
+                lo = 0, hi = Sp;
+                while (lo < hi) {
+                    const int md = (lo + hi) >> 1;
+                    if (cps[md + 1] <= t0e) lo = md + 1; else hi = md;
+                }
+                const int idx_hi = min(max(lo, 0), Sp - 1);
+                const float w_outer = cy1[idx_hi + 1] - cy1[idx_lo];
+                const float wi = wf[i];
+                const float d = fmaxf(wi - w_outer, 0.f);
+                ray_loss += d * d / (wi + LOSS_EPS);
+                const float g = -2.f * d / (wi + LOSS_EPS) * g_scale;
+                if (g != 0.f) {
+                    atomicAdd(E + idx_hi + 1, g);
+                    atomicAdd(E + idx_lo, -g);
+                }
+            }
+            t_inter += ray_loss;
+            __syncwarp();
+            float tot = 0.f;
+            for (int i = lane; i < np; i += 32) tot += E[i];
+            tot = nvo_warp_sum(tot);
+            float carry_f = 0.f, depth_l = 0.f;
+            const float* st = p.starts[l] + r * p.stride[l];
+            const float* en = p.ends[l] + r * p.stride[l];
+            for (int c0 = 0; c0 < Sp; c0 += 32) {
+                const int j = c0 + lane;
+                const float v = j < Sp ? E[j] : 0.f;
+                const float incl = nvo_warp_scan_incl(v, lane);
+                if (j < Sp) {
+                    float dwj = 0.f;
+                    dwj += tot - (carry_f + incl);
+                    if (use_depth) {
+                        const float s0 = __ldg(st + j), s1 = __ldg(en + j);
+                        const float t = (s0 + s1) / 2.f, len = s1 - s0;
+                        const float diff = t - D;
+                        const float e = expf(-(diff * diff) / two_sigma);
+                        const float wj = __ldg(wp + j);
+                        depth_l += -logf(wj + LOSS_EPS) * e * len;
+                        if (dmask && e != 0.f) dwj += g_depth * (-1.f / (wj + LOSS_EPS)) * e * len;
+                    }
+                    p.dw[l][r * Sp + j] = dwj;
+                }
+                carry_f += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (dmask) t_depth += depth_l;
+            __syncwarp();
+        }
+        // ---- final level: distortion (fwd + bwd) and depth (fwd + bwd) ----------------------------------------------------------------
+        for (int i = lane; i < S; i += 32) mid[i] = (cf[i + 1] + cf[i]) / 2.f;
+        __syncwarp();
+        {
+            const float g_dist = p.mults[2] / B_f;
+            const float* st = p.starts[2] + r * p.stride[2];
+            const float* en = p.ends[2] + r * p.stride[2];
+            float depth_l = 0.f;
+            for (int i = lane; i < S; i += 32) {
+                const float mi = mid[i], wi = wf[i];
+                float inner = 0.f;
+                for (int j = 0; j < S; ++j) inner += wf[j] * fabsf(mi - mid[j]);
+                const float delta = cf[i + 1] - cf[i];
+                t_dist += wi * inner + wi * wi * delta / 3.f;
+                float dwi = 0.f;
+                dwi += g_dist * (2.f * inner + 2.f * wi * delta / 3.f);
+                if (use_depth) {
+                    const float s0 = __ldg(st + i), s1 = __ldg(en + i);
+                    const float t = (s0 + s1) / 2.f, len = s1 - s0;
+                    const float diff = t - D;
+                    const float e = expf(-(diff * diff) / two_sigma);
+                    depth_l += -logf(wi + LOSS_EPS) * e * len;
+                    if (dmask && e != 0.f) dwi += g_depth * (-1.f / (wi + LOSS_EPS)) * e * len;
+                }
+                p.dw[2][r * S + i] = dwi;
+            }
+            if (dmask) t_depth += depth_l;
+        }
+        // ---- colour MSE (lanes 0..2) and MonoSDF normal loss (lane 3) -----------------------------------------------------------------
+        if (lane < 3) {
+            const float inv_n = 1.f / (3.f * B_f);
+            const float d = __ldg(p.rgb + 3 * r + lane) - __ldg(p.rgb_gt + 3 * r + lane);
+            t_rgb = d * d * inv_n;
+            p.d_rgb[3 * r + lane] = p.mults[0] * 2.f * d * inv_n;
+        }
+        if (lane == 3 && p.normals) {
+            const float inv_B = 1.f / B_f;
+            float pv[3], gv[3], np_ = 0.f, ng = 0.f;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                pv[a] = __ldg(p.normals + 3 * r + a);
+                gv[a] = __ldg(p.normal_gt + 3 * r + a);
+                np_ += pv[a] * pv[a];
+                ng += gv[a] * gv[a];
+            }
+            np_ = fmaxf(sqrtf(np_), 1e-12f);
+            ng = fmaxf(sqrtf(ng), 1e-12f);
+            float dot = 0.f, l1 = 0.f, dp[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                pv[a] /= np_;
+                gv[a] /= ng;
+                dot += pv[a] * gv[a];
+                const float d = pv[a] - gv[a];
+                l1 += fabsf(d);
+                dp[a] = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) - gv[a];
+            }
+            t_normal = (l1 + 1.f - dot) * inv_B;
+            if (p.d_normals) {
+                const float pd = pv[0] * dp[0] + pv[1] * dp[1] + pv[2] * dp[2];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) p.d_normals[3 * r + a] = p.mults[4] * inv_B * (dp[a] - pv[a] * pd) / np_;
+            }
+        }
+        t_inter *= 1.f / (B_f * (float)S);
+        t_dist *= 1.f / B_f;
+        t_depth *= 1.f / B_f;
+    }
+    t_rgb = nvo_warp_sum(t_rgb), t_inter = nvo_warp_sum(t_inter), t_dist = nvo_warp_sum(t_dist), t_depth = nvo_warp_sum(t_depth), t_normal = nvo_warp_sum(t_normal);
+    if (lane == 0) red[wid][0] = t_rgb, red[wid][1] = t_inter, red[wid][2] = t_dist, red[wid][3] = t_depth, red[wid][4] = t_normal;
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x < 5) {
+        float s = 0.f;
+        for (int i = 0; i < RAYS_PER_BLOCK; ++i) s += red[i][threadIdx.x];
+        atomicAdd(p.terms + threadIdx.x, s);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        float tot = 0.f;
+        for (int i = 0; i < 5; ++i) tot += p.mults[i] * __ldcg(p.terms + i);
+        *p.total = tot;
+        *p.ticket = 0u;
+    }
+}
+
+extern "C" int nvo_step_losses(void* stream, int64_t B, int32_t S0, int32_t S1, int32_t S2, const float* w0, const float* w1, const float* w2,
+                               const float* sdist0, const float* sdist1, const float* sdist2, const float* starts0, const float* ends0, int64_t stride0,
+                               const float* starts1, const float* ends1, int64_t stride1, const float* starts2, const float* ends2, int64_t stride2,
+                               const float* rgb, const float* rgb_gt, const float* normals, const float* normal_gt, const float* depth_gt,
+                               const float* directions_norm, float sigma, float mult_rgb, float mult_interlevel, float mult_distortion, float mult_depth,
+                               float mult_normal, float* terms, float* total, void* ticket, float* dw0, float* dw1, float* dw2, float* d_rgb,
+                               float* d_normals) {
+    NVO_CHECK(B >= 0 && S0 >= 1 && S1 >= 1 && S2 >= 1 && S0 <= MAX_S && S1 <= MAX_S && S2 <= MAX_S, "step_losses: bad shape");
+    if (B == 0) return 0;
+    NVO_CHECK(w0 && w1 && w2 && sdist0 && sdist1 && sdist2 && rgb && rgb_gt && terms && total && ticket && dw0 && dw1 && dw2 && d_rgb, "step_losses: null pointer");
+    NVO_CHECK(!depth_gt || (directions_norm && starts0 && ends0 && starts1 && ends1 && starts2 && ends2), "step_losses: depth loss needs the sample intervals");
+    NVO_CHECK(!normals || normal_gt, "step_losses: normal target missing");
+    StepLossP p;
+    p.B = B;
+    p.S[0] = S0, p.S[1] = S1, p.S[2] = S2;
+    p.w[0] = w0, p.w[1] = w1, p.w[2] = w2;
+    p.sdist[0] = sdist0, p.sdist[1] = sdist1, p.sdist[2] = sdist2;
+    p.starts[0] = starts0, p.starts[1] = starts1, p.starts[2] = starts2;
+    p.ends[0] = ends0, p.ends[1] = ends1, p.ends[2] = ends2;
+    p.stride[0] = stride0, p.stride[1] = stride1, p.stride[2] = stride2;
+    p.rgb = rgb, p.rgb_gt = rgb_gt, p.normals = normals, p.normal_gt = normal_gt, p.depth_gt = depth_gt, p.dnorm = directions_norm, p.sigma = sigma;
+    p.mults[0] = mult_rgb, p.mults[1] = mult_interlevel, p.mults[2] = mult_distortion, p.mults[3] = mult_depth, p.mults[4] = mult_normal;
+    p.terms = terms, p.total = total, p.ticket = (unsigned int*)ticket;
+    p.dw[0] = dw0, p.dw[1] = dw1, p.dw[2] = dw2, p.d_rgb = d_rgb, p.d_normals = d_normals;
+    const size_t smem = sizeof(float) * RAYS_PER_BLOCK * (3 * (size_t)S2 + 1 + 3 * (size_t)(max(S0, S1) + 1));
+    NVO_CHECK(smem <= 48 * 1024, "step_losses: %zu bytes of shared memory per CTA exceed 48 KB", smem);
+    k_step_losses<<<ray_blocks(B), 32 * RAYS_PER_BLOCK, smem, (cudaStream_t)stream>>>(p);
+    NVO_CUDA_LAUNCH_CHECK("step_losses");
+    return 0;
+}

@@ -62,16 +62,21 @@ class _LeafStreams:
         # independent branches of the field's forward (density-gradient normals, predicted-normals network) next to the colour head:
         # each is a chain of latency-bound launches that leaves most of the SMs idle
         self.branch_streams = [torch.cuda.Stream(priority=-1) for _ in range(2)]
+        # the main hash-table scatter is the tail of the step's critical path (the optimizer waits for it): its own high-priority stream, so
+        # its CTAs are placed ahead of the proposal networks' backward and scatters that are pending at the same time
+        self.critical_stream = torch.cuda.Stream(priority=-1) if os.environ.get("NVO_SCATTER_PRIORITY", "1") == "1" else None
         self.enabled = True
 
     def on_level_stream(self) -> bool:
         cur = torch.cuda.current_stream()
         return any(cur == st for st in getattr(self, "level_streams", []))
 
-    def fork(self, *keepalive, aux: bool = False):
+    def fork(self, *keepalive, aux: bool = False, critical: bool = False):
         """Returns a context manager running its body on the next side stream, ordered after the current stream."""
         cur = torch.cuda.current_stream()
-        if aux:
+        if critical and getattr(self, "critical_stream", None) is not None:
+            st = self.critical_stream
+        elif aux:
             st = self.aux_streams[self.next_aux % len(self.aux_streams)]
             self.next_aux += 1
         else:
@@ -942,7 +947,6 @@ class _FusedStepLosses(torch.autograd.Function):
         B = ws[0].shape[0]
         dev = ws[0].device
         rgb = check(rgb.contiguous(), "rgb", torch.float32, (B, 3))
-        terms = torch.zeros(5, dtype=torch.float32, device=dev)
         d_rgb = torch.empty_like(rgb)
         d_n = None
         if spec["normal_gt"] is not None and normals_img is not None:
@@ -957,39 +961,44 @@ class _FusedStepLosses(torch.autograd.Function):
         dws = None
         if eager:
             sizes = [w.shape[1] for w in ws]
-            flat = torch.zeros(B * sum(sizes), dtype=torch.float32, device=dev)
+            # one launch for the whole wave (csrc/losses.cu: k_step_losses): terms, weighted total and every gradient
+            flat = torch.empty(B * sum(sizes), dtype=torch.float32, device=dev)
             dws, off = [], 0
             for n_s in sizes:
                 dws.append(flat[off:off + B * n_s].view(B, n_s))
                 off += B * n_s
-            one = _cached_linspace(("unit_grad",), lambda: torch.ones(1, dtype=torch.float32), dev)
-        m = spec["mults"]
+            state = torch.zeros(8, dtype=torch.float32, device=dev)  # terms[5], total, ticket (uint32 zero), pad
+            m = spec["mults"]
+            use_d = spec["depth_gt"] is not None
+            ivs = [spec["iv"][i].triple() if use_d else (None, None, 0) for i in range(3)]
+            call("nvo_step_losses", B, sizes[0], sizes[1], sizes[2], ws[0], ws[1], ws[2], spec["sdist"][0], spec["sdist"][1], spec["sdist"][2],
+                 ivs[0][0], ivs[0][1], ivs[0][2], ivs[1][0], ivs[1][1], ivs[1][2], ivs[2][0], ivs[2][1], ivs[2][2], rgb, spec["rgb_gt"],
+                 normals_img if d_n is not None else None, spec["normal_gt"] if d_n is not None else None, spec["depth_gt"], spec["dnorm"], spec["sigma"],
+                 m[0], m[1], m[2], m[3] if use_d else 0.0, m[4] if d_n is not None else 0.0, state, state[5:], state[6:], dws[0], dws[1], dws[2], d_rgb, d_n)
+            terms, total = state[:5], state[5]
+            ctx.save_for_backward(dws[0], dws[1], dws[2], d_rgb, d_n)
+            ctx.eager = True
+            ctx.spec = spec
+            ctx.mark_non_differentiable(terms)
+            return total, terms
+        terms = torch.zeros(5, dtype=torch.float32, device=dev)
 
         def level(i):  # everything that reads weight set i: the kernels are tiny (4096 warps), so the three levels run side by side
             if i < 2:
                 call("nvo_interlevel_loss_forward", B, wf.shape[1], ws[i].shape[1], wf, cf, ws[i], spec["sdist"][i], terms[1:], None, None)
-                if eager:
-                    call("nvo_interlevel_loss_backward", B, wf.shape[1], sizes[i], wf, cf, ws[i], spec["sdist"][i], one, m[1], dws[i])
             else:
                 call("nvo_mse_loss", rgb.numel(), rgb, spec["rgb_gt"], spec["mults"][0], terms, d_rgb)
                 call("nvo_distortion_loss_forward", B, wf.shape[1], wf, cf, terms[2:])
-                if eager:
-                    call("nvo_distortion_loss_backward", B, wf.shape[1], wf, cf, one, m[2], dws[2])
                 if d_n is not None:
                     call("nvo_normal_loss", B, normals_img, spec["normal_gt"], spec["mults"][4], terms[4:], d_n)
             if spec["depth_gt"] is not None:
                 s, e, stride = spec["iv"][i].triple()
                 call("nvo_depth_loss_forward", B, ws[i].shape[1], ws[i], s, e, stride, spec["depth_gt"], spec["dnorm"], spec["sigma"], terms[3:])
-                if eager:
-                    call("nvo_depth_loss_backward", B, sizes[i], ws[i], s, e, stride, spec["depth_gt"], spec["dnorm"], spec["sigma"], one, m[3], dws[i])
 
         _run_levels(level)
         total = torch.dot(terms, spec["mults_dev"])
-        if eager:
-            ctx.save_for_backward(dws[0], dws[1], dws[2], d_rgb, d_n)
-        else:
-            ctx.save_for_backward(*ws, d_rgb, d_n)
-        ctx.eager = eager
+        ctx.save_for_backward(*ws, d_rgb, d_n)
+        ctx.eager = False
         ctx.spec = spec
         ctx.mark_non_differentiable(terms)
         return total, terms
@@ -1537,7 +1546,7 @@ class _FieldFused(torch.autograd.Function):
         dtable = dx = None
         if need_dt:
             if ctx.table_main_grad is not None and leaf_streams.enabled:
-                with leaf_streams.fork(x, dfeat):
+                with leaf_streams.fork(x, dfeat, critical=True):
                     grid_backward(x, dfeat, ctx.gspec, dtable=ctx.table_main_grad, tmf=True)
                     if leaf_streams.after_field_backward is not None and not need_dx:
                         leaf_streams.after_field_backward()

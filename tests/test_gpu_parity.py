@@ -652,16 +652,18 @@ def test_fused_proposal_density_vs_oracle(nv, S, B):
         assert torch.equal(field.density_from_ray_samples(rs), dens)
 
 
-def test_fused_step_losses_match_unfused(nv, golden):
-    """The single-node loss evaluation the trainer uses (ops.fused_step_losses) against the per-loss path that the golden
-    test pins to the reference: total and every weighted term 1e-6 relative, every parameter gradient 1e-5 of max-abs."""
+@pytest.mark.parametrize("eager", [False, True])
+def test_fused_step_losses_match_unfused(nv, golden, eager):
+    """The single-node loss evaluation the trainer uses (ops.fused_step_losses; eager: the whole wave, gradients included, as ONE launch of
+    k_step_losses) against the per-loss path that the golden test pins to the reference: total and every weighted term 1e-6 relative,
+    every parameter gradient 1e-5 of max-abs."""
     g = golden("model_step_small")
     res = []
     for fused in (False, True):
         m, rb, batch, jit = _build_model(nv, g)
         m.proposal_sampler.set_anneal(float(g["anneal"]))
         if fused:
-            _, total, terms, weights = m.get_train_loss_fused(rb, batch, jit)
+            _, total, terms, weights = m.get_train_loss_fused(rb, batch, jit, eager_grads=eager)
             ld = {k: v * weights[k] for k, v in terms.items()}
         else:
             _, ld, _ = m.get_train_loss_dict(rb, batch, jit)
