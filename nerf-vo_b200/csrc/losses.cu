@@ -364,7 +364,11 @@ __global__ void __launch_bounds__(32 * RAYS_PER_BLOCK) k_step_losses(const __gri
     extern __shared__ float smf[];
     __shared__ float red[RAYS_PER_BLOCK][5];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int64_t r = (int64_t)blockIdx.x * RAYS_PER_BLOCK + wid;
+    // three warps per ray: role 0 / 1 = that proposal level's interlevel + depth terms, role 2 = the field level's distortion + depth terms,
+    // colour and normal losses (the levels' gradient buffers are disjoint, the five sums meet in the block reduction)
+    const int64_t gw = (int64_t)blockIdx.x * RAYS_PER_BLOCK + wid;
+    const int64_t r = gw / 3;
+    const int role = (int)(gw - 3 * r);
     const bool live = r < p.B;
     const int S = p.S[2];
     const int npmax = max(p.S[0], p.S[1]) + 1;
@@ -388,6 +392,7 @@ __global__ void __launch_bounds__(32 * RAYS_PER_BLOCK) k_step_losses(const __gri
         __syncwarp();
         // ---- proposal levels: interlevel (fwd + bwd) and depth (fwd + bwd) ------------------------------------------------------------
         for (int l = 0; l < 2; ++l) {
+            if (l != role) continue;
             const int Sp = p.S[l], np = Sp + 1;
             const float* wp = p.w[l] + r * Sp;
             double carry = 0.0;
@@ -464,7 +469,7 @@ __global__ void __launch_bounds__(32 * RAYS_PER_BLOCK) k_step_losses(const __gri
         // ---- final level: distortion (fwd + bwd) and depth (fwd + bwd) ----------------------------------------------------------------
         for (int i = lane; i < S; i += 32) mid[i] = (cf[i + 1] + cf[i]) / 2.f;
         __syncwarp();
-        {
+        if (role == 2) {
             const float g_dist = p.mults[2] / B_f;
             const float* st = p.starts[2] + r * p.stride[2];
             const float* en = p.ends[2] + r * p.stride[2];
@@ -490,13 +495,13 @@ __global__ void __launch_bounds__(32 * RAYS_PER_BLOCK) k_step_losses(const __gri
             if (dmask) t_depth += depth_l;
         }
         // ---- colour MSE (lanes 0..2) and MonoSDF normal loss (lane 3) -----------------------------------------------------------------
-        if (lane < 3) {
+        if (role == 2 && lane < 3) {
             const float inv_n = 1.f / (3.f * B_f);
             const float d = __ldg(p.rgb + 3 * r + lane) - __ldg(p.rgb_gt + 3 * r + lane);
             t_rgb = d * d * inv_n;
             p.d_rgb[3 * r + lane] = p.mults[0] * 2.f * d * inv_n;
         }
-        if (lane == 3 && p.normals) {
+        if (role == 2 && lane == 3 && p.normals) {
             const float inv_B = 1.f / B_f;
             float pv[3], gv[3], np_ = 0.f, ng = 0.f;
 #pragma unroll
@@ -577,7 +582,7 @@ extern "C" int nvo_step_losses(void* stream, int64_t B, int32_t S0, int32_t S1, 
     p.dw[0] = dw0, p.dw[1] = dw1, p.dw[2] = dw2, p.d_rgb = d_rgb, p.d_normals = d_normals;
     const size_t smem = sizeof(float) * RAYS_PER_BLOCK * (3 * (size_t)S2 + 1 + 3 * (size_t)(max(S0, S1) + 1));
     NVO_CHECK(smem <= 48 * 1024, "step_losses: %zu bytes of shared memory per CTA exceed 48 KB", smem);
-    k_step_losses<<<ray_blocks(B), 32 * RAYS_PER_BLOCK, smem, (cudaStream_t)stream>>>(p);
+    k_step_losses<<<ray_blocks(3 * B), 32 * RAYS_PER_BLOCK, smem, (cudaStream_t)stream>>>(p);
     NVO_CUDA_LAUNCH_CHECK("step_losses");
     return 0;
 }

@@ -225,7 +225,12 @@ class MappingTrainer:
         # proposal backward that used to fill its idle issue slots; from 4 ranks on the exchange is NVLink-bound, one CTA per SM carries it, and
         # hiding it behind the proposal backward wins (8 GPUs: 1067 -> 1030 us per step).  NVO_EARLY_FIELDS_OPT=1 / 0 forces it on / off.
         env = os.environ.get("NVO_EARLY_FIELDS_OPT", "")
-        early = side and len(self.groups) == 2 and self.exchange != "nccl" and (env == "1" or (env != "0" and self.peer is not None and self.world_size >= 4))
+        multi = self.peer is not None and self.world_size >= 4
+        early = side and len(self.groups) == 2 and self.exchange != "nccl" and (env in ("1", "2") or (env != "0" and (multi or self.peer is None)))
+        # one GPU (and NVO_EARLY_FIELDS_OPT=2): the fields group's Adam (HBM-bound) starts right behind the main table scatter, which runs on
+        # the high-priority critical stream, while the proposal networks' backward and scatters (issue / reduction bound) are still running
+        # and stay where they are; from 4 ranks on the exchange takes that place and the proposal backward is deferred behind the field chain
+        self._defer_proposal = env == "1" or (env != "2" and multi)
         if early:
             ops.leaf_streams.after_field_backward = self._fields_optimizer_hook
         self._in_backward = True
@@ -248,7 +253,8 @@ class MappingTrainer:
         cur = torch.cuda.current_stream()
         ev = torch.cuda.Event()
         ev.record(cur)
-        ops.leaf_streams.defer_event = ev  # the proposal networks' backward starts here, not next to the field's backward chain
+        if self._defer_proposal:
+            ops.leaf_streams.defer_event = ev  # the proposal networks' backward starts here, not next to the field's backward chain
         if self._opt_stream is None:
             self._opt_stream = torch.cuda.Stream(priority=-1)
         self._opt_stream.wait_event(ev)
