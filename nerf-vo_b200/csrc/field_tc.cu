@@ -117,6 +117,16 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
     for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // one layer's MMAs: D[128 x N] (tmem_d) = A (ksteps x 16 columns from a_base) x W^T (+ bias step against the ones tile)
 __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_base, int ksteps, uint32_t w_base, int N, bool bias, uint32_t ones_base) {
     const uint32_t idesc = umma_idesc(TM, N, 0, 0);
@@ -178,12 +188,61 @@ __device__ __forceinline__ float ft_posenc(float xi, int k, bool cos_block) {
 // ================================================================================================================================
 // forward
 // shared memory: [weight image FI_BYTES][ones tile 2 chunks][per group: FI 4 | H 8 | X 8 | P 4 chunks][mbarriers][tmem ptr]
-// TMEM per group: accA = columns [0,64) (wide layers; normals chain in [32,64) next to the 16-wide base output), accB = [64,80) (the
-// narrow output layers issued together with the next wide one)
+// TMEM: the CTA owns all 512 columns (base 0); group g uses [128 g, 128 g + 128): accA = +[0,64) wide layers, accB = +[64,80) the narrow
+// output layers (issued together with the next wide one), accN = +[96,128) the normals chain's input-gradient product
 // ================================================================================================================================
 #define FT_GROUP_CHUNKS 24
 #define FT_ONES_OFF ((FI_BYTES + 1023) & ~1023)
 #define FT_GROUPS_OFF (FT_ONES_OFF + 2 * CHUNK_B)
+#define FT_MBAR_OFF(G) (FT_GROUPS_OFF + (G) * FT_GROUP_CHUNKS * CHUNK_B)
+
+__device__ __forceinline__ void umma_commit_u32(uint32_t mbar_saddr) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar_saddr) : "memory");
+}
+
+// Shared-memory descriptor of the canonical no-swizzle layout at byte offset `off` (compile-time) from the CTA's shared-memory base, whose
+// 16-byte index `base16` = (address & 0x3FFFF) >> 4 is the only run-time input: low word = base16 + constant (no carry into the LBO field:
+// shared-memory addresses stay below 2^18), high word constant.  One uniform add per descriptor instead of a shift / mask / or chain.
+__device__ __forceinline__ uint64_t umma_desc_rel(uint32_t base16, uint32_t off, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    const uint32_t lo = base16 + ((off >> 4) + ((lbo_bytes >> 4) << 16));
+    const uint32_t hi = (sbo_bytes >> 4) | (1u << 14);
+    return ((uint64_t)hi << 32) | lo;
+}
+__device__ __forceinline__ void issue_layer_rel(uint32_t tmem_d, uint32_t base16, uint32_t a_off, int ksteps, uint32_t w_off, int N, bool bias) {
+    const uint32_t idesc = umma_idesc(TM, N, 0, 0);
+#pragma unroll
+    for (int k = 0; k < ksteps; ++k)
+        umma_f16(tmem_d, umma_desc_rel(base16, a_off + k * 2 * CHUNK_B, CHUNK_B, 128), umma_desc_rel(base16, w_off + k * 2 * N * 16, N * 16, 128), idesc, k > 0);
+    if (bias) umma_f16(tmem_d, umma_desc_rel(base16, FT_ONES_OFF, CHUNK_B, 128), umma_desc_rel(base16, w_off + ksteps * 2 * N * 16, N * 16, 128), idesc, 1);
+}
+
+// One step's MMAs of tile group GI.  Every operand is derived from the CTA's shared-memory base and compile-time constants (the group
+// index included, TMEM base 0), so the descriptors live in uniform registers, one add each; with a run-time group index ptxas wraps every
+// MMA in an elect / R2UR.BROADCAST loop behind a dependent shift / mask chain (~110 cycles per MMA instead of the pipe's 46).
+template <int G, int GI>
+__device__ __forceinline__ void ft_issue(int step, uint32_t uBase, int want_normals, int want_pn) {
+    const uint32_t b16 = (uBase & 0x3FFFFu) >> 4;
+    constexpr uint32_t oG = FT_GROUPS_OFF + GI * FT_GROUP_CHUNKS * CHUNK_B;
+    constexpr uint32_t oFI = oG, oH = oG + 4 * CHUNK_B, oX = oG + 12 * CHUNK_B, oP = oG + 20 * CHUNK_B;
+    constexpr uint32_t accA = GI * 128, accB = GI * 128 + 64, accN = GI * 128 + 96;
+    switch (step) {
+        case 0: issue_layer_rel(accA, b16, oFI, 2, FI_B0, 64, true); break;
+        case 1:
+            issue_layer_rel(accA, b16, oH, 4, FI_B1, 16, true);
+            if (want_normals) issue_layer_rel(accN, b16, oX, 4, FI_NS, 32, false);
+            break;
+        case 2: issue_layer_rel(accA, b16, oX, 4, FI_H0, 64, false); break;
+        case 3: issue_layer_rel(accA, b16, oH, 4, FI_H1, 64, true); break;
+        case 4:
+            issue_layer_rel(accB, b16, oH, 4, FI_H2, 16, true);
+            if (want_pn) issue_layer_rel(accA, b16, oP, 2, FI_P0, 64, false);
+            break;
+        case 5: issue_layer_rel(accA, b16, oH, 4, FI_P1, 64, true); break;
+        case 6: issue_layer_rel(accA, b16, oH, 4, FI_P2, 64, true); break;
+        default: issue_layer_rel(accB, b16, oH, 4, FI_P3, 16, true); break;
+    }
+    umma_commit_u32(uBase + FT_MBAR_OFF(G) + 8 * (1 + GI));
+}
 
 template <int G>
 __global__ void __launch_bounds__(G* FT_THREADS, 1) k_field_fwd(const __grid_constant__ FieldFwdP p) {
@@ -194,21 +253,21 @@ __global__ void __launch_bounds__(G* FT_THREADS, 1) k_field_fwd(const __grid_con
     unsigned char* sOnes = smem + FT_ONES_OFF;
     unsigned char* sG = smem + FT_GROUPS_OFF + g * FT_GROUP_CHUNKS * CHUNK_B;
     unsigned char *sFI = sG, *sH = sG + 4 * CHUNK_B, *sX = sG + 12 * CHUNK_B, *sP = sG + 20 * CHUNK_B;
-    uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + FT_GROUPS_OFF + G * FT_GROUP_CHUNKS * CHUNK_B);
+    uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + FT_MBAR_OFF(G));
     uint64_t* mbar_w = mbars;
     uint64_t* mbar_mma = mbars + 1 + g;
     uint64_t* mbar_in = mbars + 1 + G + g;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mbars + 1 + 2 * G);
-    constexpr int TMEM_COLS = G * 128 <= 256 ? 256 : 512;
     const int64_t n_tiles = (p.n + TM - 1) >> 7;
     const int64_t stride = (int64_t)gridDim.x * G;
     const int64_t first = (int64_t)blockIdx.x * G + g;
+    const uint32_t uBase = smem_u32(smem);
 
     // ones tile: chunk 0 = feature 0 is 1.0 for every row, chunk 1 = zeros
     for (int e = threadIdx.x; e < 2 * CHUNK_B / 16; e += G * FT_THREADS)
         reinterpret_cast<uint4*>(sOnes)[e] = e < TM ? make_uint4(0x00003C00u, 0, 0, 0) : make_uint4(0, 0, 0, 0);
     if (threadIdx.x < 32) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (threadIdx.x == 0) {
@@ -219,6 +278,7 @@ __global__ void __launch_bounds__(G* FT_THREADS, 1) k_field_fwd(const __grid_con
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (*tmem_ptr != 0u) __trap();  // all 512 columns: the allocation can only start at column 0 (ft_issue relies on it)
     if (threadIdx.x == 0) {
         mbar_expect_tx(mbar_w, FI_BYTES);
         bulk_g2s(sW, p.wimg, FI_BYTES, mbar_w);
@@ -227,16 +287,24 @@ __global__ void __launch_bounds__(G* FT_THREADS, 1) k_field_fwd(const __grid_con
         mbar_expect_tx(mbar_in, 4 * CHUNK_B);
         bulk_g2s(sFI, p.feat16 + first * (4 * CHUNK_B), 4 * CHUNK_B, mbar_in);
     }
-    const uint32_t tmem = *tmem_ptr + (uint32_t)(g * 128);
-    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's lanes
-    const uint32_t accA = tmem, accB = tmem + 64;
-    const uint32_t uW = smem_u32(sW), uOnes = smem_u32(sOnes), uFI = smem_u32(sFI), uH = smem_u32(sH), uX = smem_u32(sX), uP = smem_u32(sP);
+    const uint32_t trow = (uint32_t)(g * 128) + ((uint32_t)((warp & 3) * 32) << 16);  // this group's columns, this warp's lanes
     mbar_wait(mbar_w, 0);
     uint32_t ph = 0;
     int it = 0;
 #ifdef NVO_FT_TIMING
     int ft_mark = 0;
 #endif
+#define FT_ISSUE(step)                                                       \
+    if (tid == 0) {                                                          \
+        tc_fence_after();                                                    \
+        if (g == 0)                                                          \
+            ft_issue<G, 0>(step, uBase, p.want_normals, p.want_pn);          \
+        else if (G > 1 && g == 1)                                            \
+            ft_issue<G, (G > 1 ? 1 : 0)>(step, uBase, p.want_normals, p.want_pn); \
+        else if (G > 2)                                                      \
+            ft_issue<G, (G > 2 ? 2 : 0)>(step, uBase, p.want_normals, p.want_pn); \
+    }                                                                        \
+    __syncwarp();
 #define FT_COMMIT_WAIT()                   \
     FT_MARK();                             \
     mbar_wait(mbar_mma, ph);               \
@@ -253,18 +321,30 @@ __global__ void __launch_bounds__(G* FT_THREADS, 1) k_field_fwd(const __grid_con
         FT_MARK();
         mbar_wait(mbar_in, (uint32_t)(it & 1));
         // ---- S0: mlp_base layer 0 --------------------------------------------------------------------------------------------------
-        if (tid == 0) {
-            tc_fence_after();
-            issue_layer(accA, uFI, 2, uW + FI_B0, 64, true, uOnes);
-            umma_commit(mbar_mma);
+        FT_ISSUE(0);
+        // per-ray inputs of the head's input tile: requested now, consumed two steps later (their latency hides behind S0 and S1)
+        const int ray = (int)((uint32_t)tc / (uint32_t)p.S);
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, e0 = 0.f, selv = 0.f;
+        uint4 x4, x5, x6, x7;
+        if (hf == 0) {
+            d0 = __ldg(p.dirs + 3 * ray), d1 = __ldg(p.dirs + 3 * ray + 1), d2 = __ldg(p.dirs + 3 * ray + 2);
+            e0 = __ldg((p.cam ? p.emb + APP * __ldg(p.cam + ray) : p.emb));
+            selv = __ldg(p.sel + tc);
+        } else {
+            // head input columns 32..63: appearance embedding 1..31, then the constant 1 that carries the first layer's bias
+            const float* e = p.cam ? p.emb + APP * __ldg(p.cam + ray) : p.emb;
+            float ev[32];
+#pragma unroll
+            for (int k = 0; k < APP; k += 4) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(e + k));
+                ev[k] = q.x, ev[k + 1] = q.y, ev[k + 2] = q.z, ev[k + 3] = q.w;
+            }
+            x4 = pack8f(ev + 1), x5 = pack8f(ev + 9), x6 = pack8f(ev + 17);
+            x7 = make_uint4(cvt_h2(ev[25], ev[26]), cvt_h2(ev[27], ev[28]), cvt_h2(ev[29], ev[30]), cvt_h2(ev[31], 1.f));
         }
         FT_COMMIT_WAIT();
-        if (tid == 0 && tile + stride < n_tiles) {  // the feature tile has been consumed: fetch the next one behind the rest of the chain
-            mbar_expect_tx(mbar_in, 4 * CHUNK_B);
-            bulk_g2s(sFI, p.feat16 + (tile + stride) * (4 * CHUNK_B), 4 * CHUNK_B, mbar_in);
-        }
         if (p.want_normals && hf == 1) {
-            // the saved feature derivatives are read one step later (normals epilogue): pull their 12 x 512 B per warp into L2 now
+            // the saved feature derivatives are read two steps later (normals): pull their 12 x 512 B per warp into L2 now
 #pragma unroll
             for (int c = 0; c < 12; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.jac + (tile * 12 + c) * TM + r));
         }
@@ -284,136 +364,111 @@ __global__ void __launch_bounds__(G* FT_THREADS, 1) k_field_fwd(const __grid_con
                     const __half2 zero = __float2half2_rn(0.f);
                     uint4 d;
                     const __half2* a2 = reinterpret_cast<const __half2*>(&u);
-                    const __half2* w2 = reinterpret_cast<const __half2*>(&w);
-                    __half2* d2 = reinterpret_cast<__half2*>(&d);
+                    const uint32_t* w2 = reinterpret_cast<const uint32_t*>(&w);
+                    uint32_t* dd = reinterpret_cast<uint32_t*>(&d);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) d2[j] = __hmul2(__hgt2(a2[j], zero), w2[j]);
+                    for (int j = 0; j < 4; ++j) dd[j] = w2[j] & __hgt2_mask(a2[j], zero);
                     *reinterpret_cast<uint4*>(sX + (4 * hf + q) * CHUNK_B + r * 16) = d;
                 }
             }
         }
         group_sync(g);
-        // ---- S1: mlp_base layer 1 (16 outputs) + the normals chain's input-gradient product (32 feature columns) -------------------------
-        if (tid == 0) {
-            tc_fence_after();
-            issue_layer(accA, uH, 4, uW + FI_B1, 16, true, uOnes);
-            if (p.want_normals) issue_layer(accA + 32, uX, 4, uW + FI_NS, 32, false, uOnes);
-            umma_commit(mbar_mma);
+        // the feature tile has been consumed (S0's MMA retired) and every thread of the group is past this tile's wait on mbar_in (the barrier
+        // above) — only now may the barrier's next phase start: a thread still to make that wait would otherwise see the parity wrap around
+        if (tid == 0 && tile + stride < n_tiles) {
+            mbar_expect_tx(mbar_in, 4 * CHUNK_B);
+            bulk_g2s(sFI, p.feat16 + (tile + stride) * (4 * CHUNK_B), 4 * CHUNK_B, mbar_in);
         }
+        // ---- S1: mlp_base layer 1 (16 outputs) + the normals chain's input-gradient product (32 feature columns, accN) ----------------------
+        FT_ISSUE(1);
         FT_COMMIT_WAIT();
-        {
-            const int64_t ray = tc / p.S;
-            float hv[16];
-            tmem_ld16(trow, hv);  // both halves need the geometry features
-            if (hf == 0) {
-                // density = trunc_exp(h0) * selector (nerfacto_field.py:216-221), head input columns 0..31, pred-normals input
-                if (live) {
-                    p.density[t] = __fmul_rn(expf(hv[0]), __ldg(p.sel + t));
-                    if (p.h0) p.h0[t] = hv[0];
-                }
-                float c[16];
-                ft_sh16(__fmul_rn(__fadd_rn(__ldg(p.dirs + 3 * ray), 1.f), 0.5f), __fmul_rn(__fadd_rn(__ldg(p.dirs + 3 * ray + 1), 1.f), 0.5f),
-                        __fmul_rn(__fadd_rn(__ldg(p.dirs + 3 * ray + 2), 1.f), 0.5f), c);
-                const float e0 = __ldg((p.cam ? p.emb + APP * __ldg(p.cam + ray) : p.emb));
-                uint4 x0 = pack8f(c), x1 = pack8f(c + 8), x2 = pack8f(hv + 1);
-                uint4 x3 = make_uint4(cvt_h2(hv[9], hv[10]), cvt_h2(hv[11], hv[12]), cvt_h2(hv[13], hv[14]), cvt_h2(hv[15], e0));
-                *reinterpret_cast<uint4*>(sX + 0 * CHUNK_B + r * 16) = x0;
-                *reinterpret_cast<uint4*>(sX + 1 * CHUNK_B + r * 16) = x1;
-                *reinterpret_cast<uint4*>(sX + 2 * CHUNK_B + r * 16) = x2;
-                *reinterpret_cast<uint4*>(sX + 3 * CHUNK_B + r * 16) = x3;
-                if (sv) sv[(FS_X + 0) * TM + r] = x0, sv[(FS_X + 1) * TM + r] = x1, sv[(FS_X + 2) * TM + r] = x2, sv[(FS_X + 3) * TM + r] = x3;
-                if (p.want_pn) {
-                    float pe[12];
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        const float xi = __ldg(p.pos + 3 * tc + i);
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            pe[i * 2 + k] = ft_posenc(xi, k, false);
-                            pe[6 + i * 2 + k] = ft_posenc(xi, k, true);
-                        }
-                    }
-                    const uint4 p0 = pack8f(pe);
-                    const uint4 p1 = make_uint4(cvt_h2(pe[8], pe[9]), cvt_h2(pe[10], pe[11]), cvt_h2(hv[1], hv[2]), cvt_h2(hv[3], hv[4]));
-                    const uint4 p2 = pack8f(hv + 5);
-                    const uint4 p3 = make_uint4(cvt_h2(hv[13], hv[14]), cvt_h2(hv[15], 1.f), 0u, 0u);  // column 27 = 1: carries the first layer's bias
-                    *reinterpret_cast<uint4*>(sP + 0 * CHUNK_B + r * 16) = p0;
-                    *reinterpret_cast<uint4*>(sP + 1 * CHUNK_B + r * 16) = p1;
-                    *reinterpret_cast<uint4*>(sP + 2 * CHUNK_B + r * 16) = p2;
-                    *reinterpret_cast<uint4*>(sP + 3 * CHUNK_B + r * 16) = p3;
-                    if (svp) svp[(FS_P + 0) * TM + r] = p0, svp[(FS_P + 1) * TM + r] = p1, svp[(FS_P + 2) * TM + r] = p2, svp[(FS_P + 3) * TM + r] = p3;
-                }
-            } else {
-                // density-gradient normals first (they read accA[32,64) and the buffer the head input is about to overwrite was its operand)
-                if (p.want_normals) {
-                    float v[32];
-                    tmem_ld32(trow + 32, v);
-                    float acc[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const uint4* jb = p.jac + ((tile * 4 + c) * 3) * TM + r;
-                        const uint4 J[3] = {__ldg(jb), __ldg(jb + TM), __ldg(jb + 2 * TM)};
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float g0 = v[8 * c + 2 * q], g1 = v[8 * c + 2 * q + 1];  // already x level scale (folded into the weights)
-#pragma unroll
-                            for (int a = 0; a < 3; ++a) {
-                                const uint32_t w = q == 0 ? J[a].x : q == 1 ? J[a].y : q == 2 ? J[a].z : J[a].w;
-                                const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&w));
-                                acc[a] = fmaf(d.x, g0, fmaf(d.y, g1, acc[a]));
-                            }
-                        }
-                    }
-                    const float nrm = fmaxf(sqrtf(acc[0] * acc[0] + acc[1] * acc[1] + acc[2] * acc[2]), 1e-12f);
-                    if (live) {
-                        p.normals[3 * t] = -(acc[0] / nrm);
-                        p.normals[3 * t + 1] = -(acc[1] / nrm);
-                        p.normals[3 * t + 2] = -(acc[2] / nrm);
-                    }
-                }
-                // head input columns 32..63: appearance embedding 1..31, then the constant 1 that carries the first layer's bias
-                const float* e = p.cam ? p.emb + APP * __ldg(p.cam + ray) : p.emb;
-                float ev[32];
-#pragma unroll
-                for (int k = 0; k < APP; k += 4) {
-                    const float4 q = __ldg(reinterpret_cast<const float4*>(e + k));
-                    ev[k] = q.x, ev[k + 1] = q.y, ev[k + 2] = q.z, ev[k + 3] = q.w;
-                }
-                const uint4 x4 = pack8f(ev + 1), x5 = pack8f(ev + 9), x6 = pack8f(ev + 17);
-                const uint4 x7 = make_uint4(cvt_h2(ev[25], ev[26]), cvt_h2(ev[27], ev[28]), cvt_h2(ev[29], ev[30]), cvt_h2(ev[31], 1.f));
-                // (the normals MMA read sX as its operand: it retired before the commit this epilogue waited for)
-                *reinterpret_cast<uint4*>(sX + 4 * CHUNK_B + r * 16) = x4;
-                *reinterpret_cast<uint4*>(sX + 5 * CHUNK_B + r * 16) = x5;
-                *reinterpret_cast<uint4*>(sX + 6 * CHUNK_B + r * 16) = x6;
-                *reinterpret_cast<uint4*>(sX + 7 * CHUNK_B + r * 16) = x7;
-                if (sv) sv[(FS_X + 4) * TM + r] = x4, sv[(FS_X + 5) * TM + r] = x5, sv[(FS_X + 6) * TM + r] = x6, sv[(FS_X + 7) * TM + r] = x7;
-            }
+        float hv[16];
+        tmem_ld16(trow, hv);  // raw density + geometry features (both halves need them)
+        if (hf == 0) {
+            // head input columns 0..31: SH16 | geo15 | appearance channel 0 (nerfacto_field.py:253-262)
+            float c[16];
+            ft_sh16(__fmul_rn(__fadd_rn(d0, 1.f), 0.5f), __fmul_rn(__fadd_rn(d1, 1.f), 0.5f), __fmul_rn(__fadd_rn(d2, 1.f), 0.5f), c);
+            const uint4 x0 = pack8f(c), x1 = pack8f(c + 8), x2 = pack8f(hv + 1);
+            const uint4 x3 = make_uint4(cvt_h2(hv[9], hv[10]), cvt_h2(hv[11], hv[12]), cvt_h2(hv[13], hv[14]), cvt_h2(hv[15], e0));
+            // (the normals MMA read sX as its operand: it retired before the commit this epilogue waited for)
+            *reinterpret_cast<uint4*>(sX + 0 * CHUNK_B + r * 16) = x0;
+            *reinterpret_cast<uint4*>(sX + 1 * CHUNK_B + r * 16) = x1;
+            *reinterpret_cast<uint4*>(sX + 2 * CHUNK_B + r * 16) = x2;
+            *reinterpret_cast<uint4*>(sX + 3 * CHUNK_B + r * 16) = x3;
+            if (sv) sv[(FS_X + 0) * TM + r] = x0, sv[(FS_X + 1) * TM + r] = x1, sv[(FS_X + 2) * TM + r] = x2, sv[(FS_X + 3) * TM + r] = x3;
+        } else {
+            *reinterpret_cast<uint4*>(sX + 4 * CHUNK_B + r * 16) = x4;
+            *reinterpret_cast<uint4*>(sX + 5 * CHUNK_B + r * 16) = x5;
+            *reinterpret_cast<uint4*>(sX + 6 * CHUNK_B + r * 16) = x6;
+            *reinterpret_cast<uint4*>(sX + 7 * CHUNK_B + r * 16) = x7;
+            if (sv) sv[(FS_X + 4) * TM + r] = x4, sv[(FS_X + 5) * TM + r] = x5, sv[(FS_X + 6) * TM + r] = x6, sv[(FS_X + 7) * TM + r] = x7;
         }
         group_sync(g);
-        // ---- S2 / S3: mlp_head hidden layers ------------------------------------------------------------------------------------------
-        if (tid == 0) {
-            tc_fence_after();
-            issue_layer(accA, uX, 4, uW + FI_H0, 64, false, uOnes);
-            umma_commit(mbar_mma);
+        // ---- S2: mlp_head layer 0; behind its issue, off the chain: density, the pred-normals input tile, the density-gradient normals -----
+        FT_ISSUE(2);
+        if (hf == 0) {
+            // density = trunc_exp(h0) * selector (nerfacto_field.py:216-221)
+            if (live) {
+                p.density[t] = __fmul_rn(expf(hv[0]), selv);
+                if (p.h0) p.h0[t] = hv[0];
+            }
+            if (p.want_pn) {
+                float pe[12];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const float xi = __ldg(p.pos + 3 * tc + i);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        pe[i * 2 + k] = ft_posenc(xi, k, false);
+                        pe[6 + i * 2 + k] = ft_posenc(xi, k, true);
+                    }
+                }
+                const uint4 p0 = pack8f(pe);
+                const uint4 p1 = make_uint4(cvt_h2(pe[8], pe[9]), cvt_h2(pe[10], pe[11]), cvt_h2(hv[1], hv[2]), cvt_h2(hv[3], hv[4]));
+                const uint4 p2 = pack8f(hv + 5);
+                const uint4 p3 = make_uint4(cvt_h2(hv[13], hv[14]), cvt_h2(hv[15], 1.f), 0u, 0u);  // column 27 = 1: carries the first layer's bias
+                *reinterpret_cast<uint4*>(sP + 0 * CHUNK_B + r * 16) = p0;
+                *reinterpret_cast<uint4*>(sP + 1 * CHUNK_B + r * 16) = p1;
+                *reinterpret_cast<uint4*>(sP + 2 * CHUNK_B + r * 16) = p2;
+                *reinterpret_cast<uint4*>(sP + 3 * CHUNK_B + r * 16) = p3;
+                if (svp) svp[(FS_P + 0) * TM + r] = p0, svp[(FS_P + 1) * TM + r] = p1, svp[(FS_P + 2) * TM + r] = p2, svp[(FS_P + 3) * TM + r] = p3;
+            }
+        } else if (p.want_normals) {
+            float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint4* jb = p.jac + ((tile * 4 + c) * 3) * TM + r;
+                const uint4 J[3] = {__ldg(jb), __ldg(jb + TM), __ldg(jb + 2 * TM)};
+                float v[8];
+                tmem_ld8(trow + 96 + 8 * c, v);  // already x level scale (folded into the weights)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float g0 = v[2 * q], g1 = v[2 * q + 1];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const uint32_t w = q == 0 ? J[a].x : q == 1 ? J[a].y : q == 2 ? J[a].z : J[a].w;
+                        const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&w));
+                        acc[a] = fmaf(d.x, g0, fmaf(d.y, g1, acc[a]));
+                    }
+                }
+            }
+            const float nrm = fmaxf(sqrtf(acc[0] * acc[0] + acc[1] * acc[1] + acc[2] * acc[2]), 1e-12f);
+            if (live) {
+                p.normals[3 * t] = -(acc[0] / nrm);
+                p.normals[3 * t + 1] = -(acc[1] / nrm);
+                p.normals[3 * t + 2] = -(acc[2] / nrm);
+            }
         }
         FT_COMMIT_WAIT();
         epi_hidden<true>(trow, sH, sv ? sv + FS_AH1 * TM : nullptr, hf, r);
         group_sync(g);
-        if (tid == 0) {
-            tc_fence_after();
-            issue_layer(accA, uH, 4, uW + FI_H1, 64, true, uOnes);
-            umma_commit(mbar_mma);
-        }
+        // ---- S3: mlp_head layer 1 ---------------------------------------------------------------------------------------------------------
+        FT_ISSUE(3);
         FT_COMMIT_WAIT();
         epi_hidden<true>(trow, sH, sv ? sv + FS_AH2 * TM : nullptr, hf, r);
         group_sync(g);
         // ---- S4 (+ S5): colour output layer, issued together with the pred-normals input layer ---------------------------------------------
-        if (tid == 0) {
-            tc_fence_after();
-            issue_layer(accB, uH, 4, uW + FI_H2, 16, true, uOnes);
-            if (p.want_pn) issue_layer(accA, uP, 2, uW + FI_P0, 64, false, uOnes);
-            umma_commit(mbar_mma);
-        }
+        FT_ISSUE(4);
         FT_COMMIT_WAIT();
         if (hf == 0) {
             float v[4];
@@ -427,28 +482,16 @@ __global__ void __launch_bounds__(G* FT_THREADS, 1) k_field_fwd(const __grid_con
             epi_hidden<true>(trow, sH, svp ? svp + FS_AP1 * TM : nullptr, hf, r);
             group_sync(g);
             // ---- S6 / S7: mlp_pred_normals layers 1, 2 (the last one has no activation, mlp.py:143-179 with out_activation None) -------------
-            if (tid == 0) {
-                tc_fence_after();
-                issue_layer(accA, uH, 4, uW + FI_P1, 64, true, uOnes);
-                umma_commit(mbar_mma);
-            }
+            FT_ISSUE(5);
             FT_COMMIT_WAIT();
             epi_hidden<true>(trow, sH, svp ? svp + FS_AP2 * TM : nullptr, hf, r);
             group_sync(g);
-            if (tid == 0) {
-                tc_fence_after();
-                issue_layer(accA, uH, 4, uW + FI_P2, 64, true, uOnes);
-                umma_commit(mbar_mma);
-            }
+            FT_ISSUE(6);
             FT_COMMIT_WAIT();
             epi_hidden<false>(trow, sH, svp ? svp + FS_AP3 * TM : nullptr, hf, r);
             group_sync(g);
             // ---- S8: PredNormalsFieldHead: Linear(64, 3) + Tanh + normalize (field_heads.py:189-204) -------------------------------------------
-            if (tid == 0) {
-                tc_fence_after();
-                issue_layer(accB, uH, 4, uW + FI_P3, 16, true, uOnes);
-                umma_commit(mbar_mma);
-            }
+            FT_ISSUE(7);
             FT_COMMIT_WAIT();
             if (hf == 0) {
                 float v[4];
@@ -464,9 +507,10 @@ __global__ void __launch_bounds__(G* FT_THREADS, 1) k_field_fwd(const __grid_con
         group_sync(g);  // the next tile's first MMA overwrites accA and (after its epilogue) sH
     }
 #undef FT_COMMIT_WAIT
+#undef FT_ISSUE
     tc_fence_before();
     __syncthreads();
-    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_ptr), "n"(TMEM_COLS) : "memory");
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(0u) : "memory");
 }
 
 // ================================================================================================================================
@@ -549,7 +593,7 @@ extern "C" int nvo_field_pack_weights(void* stream, const nvo_grid_desc* grid, c
 
 static int field_groups() {
     static const int g = nvo_env_int("NVO_FIELD_GROUPS", 3);
-    return g == 2 ? 2 : 3;
+    return g >= 1 && g <= 3 ? g : 3;
 }
 
 extern "C" int nvo_field_forward(void* stream, int64_t B, int32_t S, const void* feat16, const void* jac, const float* positions, const float* directions,
@@ -570,7 +614,11 @@ extern "C" int nvo_field_forward(void* stream, int64_t B, int32_t S, const void*
     const int64_t tiles = (p.n + TM - 1) / TM;
     const unsigned int grid = (unsigned int)min((int64_t)nvo_sm_count(), (tiles + G - 1) / G);
     cudaError_t e;
-    if (G == 2) {
+    if (G == 1) {
+        e = cudaFuncSetAttribute(k_field_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        NVO_CHECK(e == cudaSuccess, "field_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        k_field_fwd<1><<<grid, FT_THREADS, smem, (cudaStream_t)stream>>>(p);
+    } else if (G == 2) {
         e = cudaFuncSetAttribute(k_field_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         NVO_CHECK(e == cudaSuccess, "field_forward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         k_field_fwd<2><<<grid, 2 * FT_THREADS, smem, (cudaStream_t)stream>>>(p);

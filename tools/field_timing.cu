@@ -23,6 +23,7 @@ __global__ void fill_float(float* p, size_t n, float scale, float offset, unsign
 }
 
 int main(int argc, char** argv) {
+    setvbuf(stdout, nullptr, _IOLBF, 0);
     const int64_t B = argc > 1 ? atoll(argv[1]) : 4096;
     const int S = 48;
     const int save = argc > 2 ? atoi(argv[2]) : 1;
