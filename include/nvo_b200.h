@@ -366,13 +366,29 @@ int nvo_field_pack_weights(void* stream, const nvo_grid_desc* grid, const float*
  * input from nvo_mlp_tc_backward_strided, nullable) -> dfeat: fp32 TMF [tiles][32][128] gradient w.r.t. the hash features (input of
  * nvo_grid_backward), and ACCUMULATES the parameter gradients: dbase_params / dhead_params (flat, torch layout), dembedding ([K,32] rows by
  * cam_idx, or one 32-vector when cam_idx is NULL; nullable).  rgb / h0 / saved / feat16: the forward's outputs; scratch: two device floats.
+ * ddirections[B,3] (nullable, with directions[B,3]): accumulates d loss / d ray direction through the SH encoding (camera-pose optimisation).
  * Needs S >= 32 (a warp's 32 rows then span at most two rays: the embedding gradient is reduced per ray before its atomics). */
 int nvo_field_backward(void* stream, int64_t B, int32_t S, const void* feat16, const void* saved, int32_t save_pn, const void* wimage,
                        const float* rgb, const float* h0, const float* selector, const int64_t* cam_idx, const float* ddensity, const float* drgb,
-                       const float* dpn_in, float* scratch, float* dfeat, float* dbase_params, float* dhead_params, float* dembedding);
+                       const float* dpn_in, float* scratch, float* dfeat, float* dbase_params, float* dhead_params, float* dembedding,
+                       const float* directions, float* ddirections);
 int nvo_field_forward(void* stream, int64_t B, int32_t S, const void* feat16, const void* jac, const float* positions, const float* directions,
                       const int64_t* cam_idx, const float* embedding, const float* selector, const void* wimage, float* density, float* rgb,
                       float* pred_normals, float* normals, float* h0, float* pn_raw, void* saved, int32_t save_pn);
+
+/* d loss / d (ray origins, ray directions)[B,3] (accumulated with atomics; either nullable) from dx[B*S,3] = d loss / d x, x = the normalised,
+ * selector-masked contracted sample positions the hash grids read (NS/cameras/rays.py:49-58, spatial_distortions.py:67-69,
+ * nerfacto_field.py:204-209): the path the reference's autograd takes from the field back to CameraOptimizer.apply_to_raybundle. */
+int nvo_position_backward(void* stream, int64_t B, int32_t S, const float* origins, const float* directions, const float* starts,
+                          const float* ends, int64_t stride, const float* dx, float* d_origins, float* d_directions);
+/* CameraOptimizer.get_loss_dict (NS/cameras/camera_optimizers.py:149-155): loss += mean_k ||t_k|| trans_l2_penalty + mean_k ||r_k|| rot_l2_penalty;
+ * d_pose[K,6] (nullable) += scale * its gradient (zero at a zero vector, like torch's norm backward). */
+int nvo_pose_regularizer(void* stream, int32_t K, const float* pose_adjustment, float trans_l2_penalty, float rot_l2_penalty, float scale,
+                         float* loss, float* d_pose);
+/* nvo_adam_step with ExponentialDecayScheduler's learning rate (no warm-up; NS/engine/schedulers.py:122-138) evaluated on the device from
+ * the step counter: lr = exp(log(lr_init) (1 - t) + log(lr_final) t), t = min(step / max_steps, 1) — the "camera_opt" group. */
+int nvo_adam_step_decay(void* stream, int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int32_t* step,
+                        double lr_init, double lr_final, int32_t max_steps, double beta1, double beta2, double eps, float grad_scale);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused dense Adam over a flat fp32 buffer (torch.optim.Adam semantics; NS/engine/optimizers.py:138-150,
@@ -411,6 +427,12 @@ int nvo_adam_exchange_group(void* stream, int64_t offset, int64_t n, int32_t pha
                             double lr, double beta1, double beta2, double eps, float grad_scale, int32_t ctas_per_sm);
 /* Two parameter groups stepped in the same launch (one pair of barriers instead of two; the flags of phase 0 and group A's counter as
  * barrier epoch): what the trainer uses when both groups' gradients are complete at the same time. */
+/* nvo_adam_exchange_group under ExponentialDecayScheduler (lr_init -> lr_final over max_steps, evaluated on the device from the group's step
+ * counter): the "camera_opt" group of a data-parallel run. */
+int nvo_adam_exchange_group_decay(void* stream, int64_t offset, int64_t n, int32_t phase, int32_t rank, int32_t world, const void* h_peer_params,
+                                  const void* h_peer_grads, const void* h_peer_flags, float* exp_avg_slice, float* exp_avg_sq_slice, int32_t* step,
+                                  double lr_init, double lr_final, int32_t max_steps, double beta1, double beta2, double eps, float grad_scale,
+                                  int32_t ctas_per_sm);
 int nvo_adam_exchange_groups2(void* stream, int64_t offset_a, int64_t n_a, float* exp_avg_a, float* exp_avg_sq_a, int32_t* step_a, int64_t offset_b,
                               int64_t n_b, float* exp_avg_b, float* exp_avg_sq_b, int32_t* step_b, int32_t rank, int32_t world,
                               const void* h_peer_params, const void* h_peer_grads, const void* h_peer_flags, double lr, double beta1, double beta2,

@@ -124,7 +124,7 @@ __device__ __forceinline__ void slice_pass(const PeerSet& ps, int rank, const Sl
 template <int W, int U>
 __global__ void __launch_bounds__(256) k_exchange_adam(const __grid_constant__ PeerSet ps, int rank, const __grid_constant__ SliceArgs sa,
                                                        const __grid_constant__ SliceArgs sb, double lr, double b1, double b2, double eps,
-                                                       float grad_scale, int flag_base) {
+                                                       float grad_scale, int flag_base, double lr_final, int max_steps) {
     int* my_flags = ps.flags[rank] + flag_base;
     const int epoch = *sa.step + 1;
     // ---- 1. every rank's backward has landed -----------------------------------------------------------------------
@@ -139,7 +139,12 @@ __global__ void __launch_bounds__(256) k_exchange_adam(const __grid_constant__ P
     // Adam constants per group (each has its own step counter), evaluated once per CTA in double precision
     __shared__ AdamC s_adam[2];
     if (threadIdx.x == 0) {
-        s_adam[0] = adam_constants(*sa.step + 1, lr, b1, b2, eps, grad_scale);
+        double lr_a = lr;
+        if (lr_final > 0.0) {  // group A under ExponentialDecayScheduler (the "camera_opt" group), see k_adam
+            const double t = fmin(fmax((double)*sa.step / (double)max_steps, 0.0), 1.0);
+            lr_a = exp(log(lr) * (1.0 - t) + log(lr_final) * t);
+        }
+        s_adam[0] = adam_constants(*sa.step + 1, lr_a, b1, b2, eps, grad_scale);
         s_adam[1] = adam_constants(*sb.step + 1, lr, b1, b2, eps, grad_scale);
     }
     __syncthreads();
@@ -167,7 +172,7 @@ __global__ void k_tick_step2(int* a, int* b) {
 
 __global__ void k_tick_step(int* step) { *step += 1; }
 
-typedef void (*exchange_fn)(const PeerSet, int, const SliceArgs, const SliceArgs, double, double, double, double, float, int);
+typedef void (*exchange_fn)(const PeerSet, int, const SliceArgs, const SliceArgs, double, double, double, double, float, int, double, int);
 
 extern "C" int nvo_exchange_flag_words(void) { return FLAG_WORDS; }
 
@@ -185,7 +190,8 @@ extern "C" int64_t nvo_exchange_slice(int64_t n, int32_t rank, int32_t world, in
 // Exchange + Adam of the flat ranges [offset, offset + n) (group A) and, if n_b > 0, [offset_b, offset_b + n_b) (group B) in ONE launch.
 static int exchange_launch(void* stream, int64_t offset, int64_t n, float* m_a, float* v_a, int32_t* step_a, int64_t offset_b, int64_t n_b, float* m_b,
                            float* v_b, int32_t* step_b, int32_t phase, int32_t rank, int32_t world, const void* h_peer_params, const void* h_peer_grads,
-                           const void* h_peer_flags, double lr, double beta1, double beta2, double eps, float grad_scale, int32_t ctas_per_sm) {
+                           const void* h_peer_flags, double lr, double beta1, double beta2, double eps, float grad_scale, int32_t ctas_per_sm,
+                           double lr_final = 0.0, int max_steps = 1) {
     NVO_CHECK(n > 0 && (n & 3) == 0 && offset >= 0 && (offset & 3) == 0, "adam_exchange: range [%lld, +%lld) must be float4-aligned and non-empty",
               (long long)offset, (long long)n);
     NVO_CHECK(n_b >= 0 && (n_b & 3) == 0 && offset_b >= 0 && (offset_b & 3) == 0, "adam_exchange: second range [%lld, +%lld) must be float4-aligned",
@@ -231,7 +237,7 @@ static int exchange_launch(void* stream, int64_t offset, int64_t n, float* m_a, 
     // co-resident until the exchange had drained (observed: profiles/r01_timeline_n2_s9_early_no_carveout.csv).  Ask for the largest
     // carve-out instead.
     cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    fn<<<grid, 256, 0, st>>>(ps, rank, sa, sb, lr, beta1, beta2, eps, grad_scale, phase * FLAG_PHASE_STRIDE);
+    fn<<<grid, 256, 0, st>>>(ps, rank, sa, sb, lr, beta1, beta2, eps, grad_scale, phase * FLAG_PHASE_STRIDE, lr_final, max_steps);
     NVO_CUDA_LAUNCH_CHECK("adam_exchange");
     k_tick_step2<<<1, 1, 0, st>>>(step_a, n_b > 0 ? step_b : nullptr);
     NVO_CUDA_LAUNCH_CHECK("adam_exchange(tick)");
@@ -243,6 +249,16 @@ extern "C" int nvo_adam_exchange_group(void* stream, int64_t offset, int64_t n, 
                                        double lr, double beta1, double beta2, double eps, float grad_scale, int32_t ctas_per_sm) {
     return exchange_launch(stream, offset, n, exp_avg_slice, exp_avg_sq_slice, step, 0, 0, nullptr, nullptr, nullptr, phase, rank, world, h_peer_params,
                            h_peer_grads, h_peer_flags, lr, beta1, beta2, eps, grad_scale, ctas_per_sm);
+}
+
+// one group under ExponentialDecayScheduler (lr_init -> lr_final over max_steps, evaluated on the device from the group's step counter)
+extern "C" int nvo_adam_exchange_group_decay(void* stream, int64_t offset, int64_t n, int32_t phase, int32_t rank, int32_t world,
+                                             const void* h_peer_params, const void* h_peer_grads, const void* h_peer_flags, float* exp_avg_slice,
+                                             float* exp_avg_sq_slice, int32_t* step, double lr_init, double lr_final, int32_t max_steps, double beta1,
+                                             double beta2, double eps, float grad_scale, int32_t ctas_per_sm) {
+    NVO_CHECK(lr_init > 0.0 && lr_final > 0.0 && max_steps >= 1, "adam_exchange_group_decay: bad schedule");
+    return exchange_launch(stream, offset, n, exp_avg_slice, exp_avg_sq_slice, step, 0, 0, nullptr, nullptr, nullptr, phase, rank, world, h_peer_params,
+                           h_peer_grads, h_peer_flags, lr_init, beta1, beta2, eps, grad_scale, ctas_per_sm, lr_final, max_steps);
 }
 
 extern "C" int nvo_adam_exchange_groups2(void* stream, int64_t offset_a, int64_t n_a, float* exp_avg_a, float* exp_avg_sq_a, int32_t* step_a,

@@ -688,6 +688,8 @@ struct FieldBwdP {
     float* dbase;                 // flat fp32 gradient of mlp_base (torch layout), accumulated
     float* dhead;                 // flat fp32 gradient of mlp_head, accumulated
     float* demb;                  // [K,32] (cam != null) or [32], accumulated; nullable
+    const float* dirs;            // [B,3] ray directions (with ddirs)
+    float* ddirs;                 // [B,3] d loss / d ray direction through the SH encoding, accumulated (atomics); nullable
 };
 
 __device__ __forceinline__ float ft_grad_scale(float mx) {
@@ -990,6 +992,33 @@ __global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __gri
                     }
                     *reinterpret_cast<uint4*>(sG16 + r * 16) = pack8sat(dh);
                     *reinterpret_cast<uint4*>(sG16 + CHUNK_B + r * 16) = pack8sat(dh + 8);
+                    if (p.ddirs) {
+                        // head input columns 0..15 = SH16((d + 1) / 2): d loss / d d = 0.5 J_SH^T dSH (NS/utils/math.py:45-78), summed per ray
+                        const float x = __fmul_rn(__fadd_rn(__ldg(p.dirs + 3 * ray), 1.f), 0.5f), y = __fmul_rn(__fadd_rn(__ldg(p.dirs + 3 * ray + 1), 1.f), 0.5f),
+                                    z = __fmul_rn(__fadd_rn(__ldg(p.dirs + 3 * ray + 2), 1.f), 0.5f);
+                        const float xx = x * x, yy = y * y, zz = z * z;
+                        const float a1 = 0.4886025119029199f, b = 1.0925484305920792f, c6 = 0.9461746957575601f, e8 = 0.5462742152960396f,
+                                    f9 = 0.5900435899266435f, g10 = 2.890611442640554f, h11 = 0.4570457994644658f, i12 = 0.3731763325901154f,
+                                    j14 = 1.445305721320277f;
+                        const float* G = v;  // G[k] = d loss / d SH_k (x head-chain scale)
+                        float gd[3];
+                        gd[0] = a1 * G[3] + b * y * G[4] + b * z * G[7] + 2.f * e8 * x * G[8] + 6.f * f9 * x * y * G[9] + g10 * y * z * G[10] +
+                                h11 * (5.f * zz - 1.f) * G[13] + 2.f * j14 * z * x * G[14] + f9 * (3.f * xx - 3.f * yy) * G[15];
+                        gd[1] = a1 * G[1] + b * x * G[4] + b * z * G[5] - 2.f * e8 * y * G[8] + f9 * (3.f * xx - 3.f * yy) * G[9] + g10 * x * z * G[10] +
+                                h11 * (5.f * zz - 1.f) * G[11] - 2.f * j14 * z * y * G[14] - 6.f * f9 * x * y * G[15];
+                        gd[2] = a1 * G[2] + b * y * G[5] + 2.f * c6 * z * G[6] + b * x * G[7] + g10 * x * y * G[10] + 10.f * h11 * y * z * G[11] +
+                                i12 * (15.f * zz - 3.f) * G[12] + 10.f * h11 * x * z * G[13] + j14 * (xx - yy) * G[14];
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) {
+                            const float val = live ? gd[a] * (0.5f * inv_s_h) : 0.f;
+                            const float s0 = nvo_warp_sum(second ? 0.f : val);
+                            const float s1 = split ? nvo_warp_sum(second ? val : 0.f) : 0.f;
+                            if (lane == 0) {
+                                atomicAdd(p.ddirs + 3 * ray0 + a, s0);
+                                if (split) atomicAdd(p.ddirs + 3 * ray1 + a, s1);
+                            }
+                        }
+                    }
                     if (p.demb) {  // appearance channel 0 (head input column 31)
                         float a = second ? 0.f : v[31], b = second ? v[31] : 0.f;
                         a = nvo_warp_sum(a);
@@ -1107,7 +1136,7 @@ __global__ void __launch_bounds__(256) k_field_pack_bwd(const float* __restrict_
 extern "C" int nvo_field_backward(void* stream, int64_t B, int32_t S, const void* feat16, const void* saved, int32_t save_pn, const void* wimage,
                                   const float* rgb, const float* h0, const float* selector, const int64_t* cam_idx, const float* ddensity,
                                   const float* drgb, const float* dpn_in, float* scratch, float* dfeat, float* dbase_params, float* dhead_params,
-                                  float* dembedding) {
+                                  float* dembedding, const float* directions, float* ddirections) {
     NVO_CHECK(B >= 0 && S >= 32, "field_backward: bad shape B=%lld S=%d (at least 32 samples per ray: a warp's rows span at most two rays)", (long long)B, S);
     if (B == 0) return 0;
     NVO_CHECK(feat16 && saved && wimage && rgb && h0 && selector && drgb && scratch && dfeat && dbase_params && dhead_params, "field_backward: null pointer");
@@ -1121,6 +1150,8 @@ extern "C" int nvo_field_backward(void* stream, int64_t B, int32_t S, const void
     p.n = n, p.S = S, p.saved_chunks = save_pn ? FS_CHUNKS : FS_CHUNKS_HEAD, p.feat16 = (const unsigned char*)feat16, p.saved = (const unsigned char*)saved;
     p.wimg = (const unsigned char*)wimage, p.rgb = rgb, p.h0 = h0, p.sel = selector, p.cam = cam_idx, p.ddensity = ddensity, p.drgb = drgb, p.dpn_in = dpn_in;
     p.absmax = scratch, p.dfeat = dfeat, p.dbase = dbase_params, p.dhead = dhead_params, p.demb = dembedding;
+    NVO_CHECK(!ddirections || directions, "field_backward: directions required for their gradient");
+    p.dirs = directions, p.ddirs = ddirections;
     const int G = field_groups();
     const size_t smem = BW_GROUPS_OFF + (size_t)(G * BW_GROUP_CHUNKS + 2) * CHUNK_B + 8 * (1 + 4 * G) + 16;
     const int64_t tiles = (n + TM - 1) / TM;

@@ -7,9 +7,17 @@
 
 __global__ void __launch_bounds__(256) k_adam(int64_t n4, int64_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                               float* __restrict__ v, const int* __restrict__ step_ptr, double lr, double b1, double b2, double eps,
-                                              float grad_scale) {
+                                              float grad_scale, double lr_final, int max_steps) {
     __shared__ AdamC s_c;
-    if (threadIdx.x == 0) s_c = adam_constants(*step_ptr + 1, lr, b1, b2, eps, grad_scale);
+    if (threadIdx.x == 0) {
+        const int done = *step_ptr;  // optimizer steps taken so far == the epoch the LambdaLR scheduler is in
+        if (lr_final > 0.0) {
+            // ExponentialDecayScheduler without warm-up (NS/engine/schedulers.py:122-138): exp(log(lr_init) (1 - t) + log(lr_final) t)
+            const double t = fmin(fmax((double)done / (double)max_steps, 0.0), 1.0);
+            lr = exp(log(lr) * (1.0 - t) + log(lr_final) * t);
+        }
+        s_c = adam_constants(done + 1, lr, b1, b2, eps, grad_scale);
+    }
     __syncthreads();
     const AdamC c = s_c;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -39,8 +47,8 @@ __global__ void __launch_bounds__(256) k_adam(int64_t n4, int64_t n, float* __re
 
 __global__ void k_tick(int* step) { *step += 1; }
 
-extern "C" int nvo_adam_step(void* stream, int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int32_t* step, double lr,
-                             double beta1, double beta2, double eps, float grad_scale) {
+static int adam_step_impl(void* stream, int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int32_t* step, double lr,
+                          double beta1, double beta2, double eps, float grad_scale, double lr_final, int max_steps) {
     NVO_CHECK(n >= 0, "adam_step: negative size");
     if (n == 0) return 0;
     NVO_CHECK(params && grads && exp_avg && exp_avg_sq && step, "adam_step: null pointer");
@@ -51,9 +59,59 @@ extern "C" int nvo_adam_step(void* stream, int64_t n, float* params, const float
     // largest shared-memory carve-out: kernels with dynamic shared memory (proposal backward) can then share an SM with this one
     // (the L1 / shared split of an SM cannot change while CTAs are resident); Adam streams and has no use for L1
     cudaFuncSetAttribute(k_adam, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    k_adam<<<nvo_blocks(n4 > 0 ? n4 : 1, 256), 256, 0, st>>>(n4, n, params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, grad_scale);
+    k_adam<<<nvo_blocks(n4 > 0 ? n4 : 1, 256), 256, 0, st>>>(n4, n, params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, grad_scale, lr_final,
+                                                             max_steps);
     NVO_CUDA_LAUNCH_CHECK("adam_step");
     k_tick<<<1, 1, 0, st>>>(step);
     NVO_CUDA_LAUNCH_CHECK("adam_step(tick)");
+    return 0;
+}
+
+extern "C" int nvo_adam_step(void* stream, int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int32_t* step, double lr,
+                             double beta1, double beta2, double eps, float grad_scale) {
+    return adam_step_impl(stream, n, params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, grad_scale, 0.0, 1);
+}
+
+// the same with the learning rate of ExponentialDecayScheduler (no warm-up) evaluated on the device from the step counter, so a captured
+// CUDA graph follows the schedule (the "camera_opt" group: lr 1e-4 -> 1e-5 over the mapping iterations, nerf_vo/mapping/nerfstudio.py:93-100)
+extern "C" int nvo_adam_step_decay(void* stream, int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int32_t* step,
+                                   double lr_init, double lr_final, int32_t max_steps, double beta1, double beta2, double eps, float grad_scale) {
+    NVO_CHECK(lr_init > 0.0 && lr_final > 0.0 && max_steps >= 1, "adam_step_decay: bad schedule");
+    return adam_step_impl(stream, n, params, grads, exp_avg, exp_avg_sq, step, lr_init, beta1, beta2, eps, grad_scale, lr_final, max_steps);
+}
+
+// ---- CameraOptimizer.get_loss_dict (NS/cameras/camera_optimizers.py:149-155): mean ||t_k|| trans_l2_penalty + mean ||r_k|| rot_l2_penalty and
+// its gradient (torch's norm backward: x / ||x||, zero at x = 0) accumulated into d_pose[K,6] scaled by `scale` ---------------------------------
+__global__ void __launch_bounds__(256) k_pose_regularizer(int K, const float* __restrict__ pose, float trans_pen, float rot_pen, float scale,
+                                                          float* __restrict__ loss, float* __restrict__ d_pose) {
+    __shared__ float red[8];
+    float v = 0.f;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
+        const float* q = pose + 6 * k;
+        const float nt = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]), nr = sqrtf(q[3] * q[3] + q[4] * q[4] + q[5] * q[5]);
+        v += (nt * trans_pen + nr * rot_pen) / (float)K;
+        if (d_pose) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                if (nt > 0.f) d_pose[6 * k + a] += scale * trans_pen / (float)K * q[a] / nt;
+                if (nr > 0.f) d_pose[6 * k + 3 + a] += scale * rot_pen / (float)K * q[3 + a] / nr;
+            }
+        }
+    }
+    v = nvo_warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0 && loss) {
+        float s = 0.f;
+        for (int i = 0; i < 8; ++i) s += red[i];
+        atomicAdd(loss, s);
+    }
+}
+
+extern "C" int nvo_pose_regularizer(void* stream, int32_t K, const float* pose_adjustment, float trans_l2_penalty, float rot_l2_penalty, float scale,
+                                    float* loss, float* d_pose) {
+    NVO_CHECK(K >= 1 && pose_adjustment, "pose_regularizer: bad arguments");
+    k_pose_regularizer<<<1, 256, 0, (cudaStream_t)stream>>>(K, pose_adjustment, trans_l2_penalty, rot_l2_penalty, scale, loss, d_pose);
+    NVO_CUDA_LAUNCH_CHECK("pose_regularizer");
     return 0;
 }

@@ -507,3 +507,78 @@ extern "C" int nvo_render_backward(void* stream, int64_t B, int32_t S, const flo
     NVO_CUDA_LAUNCH_CHECK("render_backward");
     return 0;
 }
+
+// ================================================================================================================================
+// d loss / d (ray origin, ray direction) from d loss / d x, x = the normalised contracted sample positions the hash grids read:
+// x = selector * (contract_Linf(o + d (start + end) / 2) + 2) / 4  (rays.py:49-58, spatial_distortions.py:67-69, nerfacto_field.py:204-209).
+// One warp per ray: every lane back-propagates its samples through the selector mask, the normalisation and the contraction Jacobian, the
+// warp sums dL/dp (origin) and t dL/dp (direction) and adds them to the ray's rows with six atomics (the three sampling levels and the
+// field's direction encoding accumulate into the same buffers, possibly from different streams).
+// ================================================================================================================================
+__global__ void __launch_bounds__(32 * RAYS_PER_BLOCK) k_position_backward(int64_t B, int S, const float* __restrict__ o, const float* __restrict__ d,
+                                                                           const float* __restrict__ starts, const float* __restrict__ ends, int64_t stride,
+                                                                           const float* __restrict__ dx, float* __restrict__ d_o, float* __restrict__ d_d) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t r = (int64_t)blockIdx.x * RAYS_PER_BLOCK + wid;
+    if (r >= B) return;
+    const float ox = __ldg(o + 3 * r), oy = __ldg(o + 3 * r + 1), oz = __ldg(o + 3 * r + 2);
+    const float dxr = __ldg(d + 3 * r), dyr = __ldg(d + 3 * r + 1), dzr = __ldg(d + 3 * r + 2);
+    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = lane; k < S; k += 32) {
+        const float se = __fadd_rn(__ldg(starts + r * stride + k), __ldg(ends + r * stride + k));
+        const float t = se * 0.5f;
+        const float p[3] = {__fadd_rn(ox, __fmul_rn(__fmul_rn(dxr, se), 0.5f)), __fadd_rn(oy, __fmul_rn(__fmul_rn(dyr, se), 0.5f)),
+                            __fadd_rn(oz, __fmul_rn(__fmul_rn(dzr, se), 0.5f))};
+        const float a[3] = {fabsf(p[0]), fabsf(p[1]), fabsf(p[2])};
+        const float mag = fmaxf(a[0], fmaxf(a[1], a[2]));
+        const bool inside = mag < 1.f;
+        // forward values again (selector)
+        bool sel = true;
+        float sfac = 1.f;
+        if (!inside) sfac = (2.f - 1.f / mag) / mag;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float q = __fmul_rn(__fadd_rn(inside ? p[i] : __fmul_rn(__fsub_rn(2.f, __fdiv_rn(1.f, mag)), __fdiv_rn(p[i], mag)), 2.f), 0.25f);
+            sel = sel && (q > 0.f) && (q < 1.f);
+        }
+        if (!sel) continue;
+        const int64_t smp = r * S + k;
+        const float g[3] = {0.25f * __ldg(dx + 3 * smp), 0.25f * __ldg(dx + 3 * smp + 1), 0.25f * __ldg(dx + 3 * smp + 2)};  // d loss / d contracted
+        float dp[3];
+        if (inside) {
+            dp[0] = g[0], dp[1] = g[1], dp[2] = g[2];
+        } else {
+            // c = s(m) p with s = 2/m - 1/m^2, m = |p_k| the largest component: dL/dp_j = s g_j + [j == k] sign(p_k) s'(m) (g . p)
+            const int kmax = (a[0] >= a[1] && a[0] >= a[2]) ? 0 : (a[1] >= a[2] ? 1 : 2);
+            const float ds = -2.f / (mag * mag) + 2.f / (mag * mag * mag);
+            const float gp = g[0] * p[0] + g[1] * p[1] + g[2] * p[2];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) dp[i] = sfac * g[i] + (i == kmax ? (p[i] < 0.f ? -1.f : 1.f) * ds * gp : 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            acc[i] += dp[i];
+            acc[3 + i] += t * dp[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) acc[i] = nvo_warp_sum(acc[i]);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (d_o && acc[i] != 0.f) atomicAdd(d_o + 3 * r + i, acc[i]);
+            if (d_d && acc[3 + i] != 0.f) atomicAdd(d_d + 3 * r + i, acc[3 + i]);
+        }
+    }
+}
+
+extern "C" int nvo_position_backward(void* stream, int64_t B, int32_t S, const float* origins, const float* directions, const float* starts,
+                                     const float* ends, int64_t stride, const float* dx, float* d_origins, float* d_directions) {
+    NVO_CHECK(B >= 0 && S >= 1, "position_backward: bad shape");
+    if (B == 0) return 0;
+    NVO_CHECK(origins && directions && starts && ends && dx && (d_origins || d_directions), "position_backward: null pointer");
+    k_position_backward<<<ray_blocks(B), 32 * RAYS_PER_BLOCK, 0, (cudaStream_t)stream>>>(B, S, origins, directions, starts, ends, stride, dx, d_origins,
+                                                                                          d_directions);
+    NVO_CUDA_LAUNCH_CHECK("position_backward");
+    return 0;
+}

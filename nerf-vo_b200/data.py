@@ -132,7 +132,11 @@ class PixelSampler:
 
 @dataclass
 class CameraOptimizerConfig:
+    """NS/cameras/camera_optimizers.py:39-56."""
+
     mode: str = "off"
+    trans_l2_penalty: float = 1e-2
+    rot_l2_penalty: float = 1e-3
 
     def setup(self, num_cameras: int, device) -> "CameraOptimizer":
         return CameraOptimizer(self, num_cameras, device)
@@ -170,6 +174,17 @@ class CameraOptimizer(nn.Module):
         o, d = ops.pose_correction(raybundle.origins.contiguous(), raybundle.directions.contiguous(), raybundle.camera_indices.reshape(-1).contiguous(),
                                    self.pose_adjustment, self.mode_id)
         raybundle.origins, raybundle.directions = o, d
+
+    def get_loss_dict(self, loss_dict: dict) -> None:
+        """Regulariser on the pose deltas (camera_optimizers.py:149-155)."""
+        if self.config.mode != "off":
+            loss_dict["camera_opt_regularizer"] = (self.pose_adjustment[:, :3].norm(dim=-1).mean() * self.config.trans_l2_penalty
+                                                   + self.pose_adjustment[:, 3:].norm(dim=-1).mean() * self.config.rot_l2_penalty)
+
+    def get_metrics_dict(self, metrics_dict: dict) -> None:
+        if self.config.mode != "off":
+            metrics_dict["camera_opt_translation"] = self.pose_adjustment[:, :3].norm()
+            metrics_dict["camera_opt_rotation"] = self.pose_adjustment[:, 3:].norm()
 
     def get_param_groups(self, param_groups: dict) -> None:
         ps = list(self.parameters())
@@ -299,9 +314,10 @@ class DynamicDataManager:
         pose = co.pose_adjustment if co is not None and co.config.mode != "off" else None
         out = ops.batch_prologue(u, ds.num_active_frames, ds.camera_intrinsics, ds.camera_extrinsics, ds.frames_color, ds.frames_depth,
                                  ds.frames_normal if ds.use_normals else None, pose, co.mode_id if pose is not None else 0,
-                                 num_active_dev=ds.num_active_dev)
+                                 num_active_dev=ds.num_active_dev, want_raw_directions=pose is not None)
         rb = RayBundle(origins=out["origins"], directions=out["directions"], pixel_area=out["pixel_area"], camera_indices=out["camera_indices"],
-                       metadata={"directions_norm": out["directions_norm"]})
+                       metadata={"directions_norm": out["directions_norm"]}, pose_corrected=pose is not None)
+        self._last_directions_raw = out.get("directions_raw")  # saved input of the pose correction's backward
         self._last_camera_indices = out["camera_indices"]  # under a CUDA graph: refreshed by every replay (diagnostics / tests)
         batch = {"indices": out["indices"], "image": out["image"], "depth_image": out["depth_image"]}
         if ds.use_normals:

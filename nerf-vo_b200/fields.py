@@ -329,21 +329,20 @@ class NerfactoField(Field):
             raise AttributeError("Camera indices are not provided.")
         fr = ray_samples.frustums
         B, S = fr.shape
-        positions = fr.get_positions()
-        x, sel = ops.contract_normalize(positions)
-        dirs = fr.directions.reshape(B, 3).contiguous()
-        cam, emb = self._appearance(ray_samples, B, dirs.device)
-        if self._fused(S, x.is_cuda):
+        per_ray = fr.offsets is None and fr.origins.dim() == 3 and fr.origins.shape[-2] == 1
+        if per_ray and self._fused(S, fr.origins.is_cuda):
             enc = self.mlp_base.encoder
             groups = [self.mlp_base.mlp._flat_param_list(), self.mlp_head._flat_param_list(), self._pn_params()]
             for ps in groups:
                 if ps:
                     repack(ps)
-            density, rgb, pn, normals, h0 = ops.field_fused(
-                x, enc.hash_table, emb, sel, positions.reshape(-1, 3), dirs, cam, B, S, enc.spec, compute_normals, groups[0], groups[1],
+            o, dirs = fr.origins.reshape(B, 3), fr.directions.reshape(B, 3)
+            cam, emb = self._appearance(ray_samples, B, dirs.device)
+            density, rgb, pn, normals, h0, x = ops.field_fused(
+                o, dirs, fr.intervals(), enc.hash_table, emb, cam, B, S, enc.spec, compute_normals, groups[0], groups[1],
                 self._pn_spec if self.use_pred_normals else None, groups[2], save_pn=self.pred_normals_trainable)
-            self._cache = {"x": x.detach(), "shape": (B, S), "tc": None, "normals": normals}
-            self._sample_locations = self._cache["x"].view(B, S, 3)
+            self._cache = {"x": x, "shape": (B, S), "tc": None, "normals": normals}
+            self._sample_locations = x.view(B, S, 3)
             self._density_before_activation = h0.view(B, S, 1)
             out = {FieldHeadNames.RGB: rgb.view(B, S, 3), FieldHeadNames.DENSITY: density.view(B, S, 1)}
             if pn is not None:
@@ -351,6 +350,10 @@ class NerfactoField(Field):
             if compute_normals:
                 out[FieldHeadNames.NORMALS] = normals.view(B, S, 3)
             return out
+        positions = fr.get_positions()
+        x, sel = ops.contract_normalize(positions)
+        dirs = fr.directions.reshape(B, 3).contiguous()
+        cam, emb = self._appearance(ray_samples, B, dirs.device)
         h, tc = self._base(x, want_normals=compute_normals)
         self._remember(x, h, (B, S), tc)
         normals = side_n = None

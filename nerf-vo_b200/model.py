@@ -63,6 +63,10 @@ class NerfactoModelConfig:
     normal_loss_mult: float = 0.000005
     # "fp16": field MLPs + hash features on the tcgen05 tensor-core path; "fp32": exact SIMT kernels (parity runs)
     precision: str = "fp16"
+    # CameraOptimizerConfig.mode of the model's camera optimizer (NS/models/nerfacto.py:130 defaults to "SO3xR3", which is what NeRF-VO's
+    # mapping step trains with, group "camera_opt", nerf_vo/mapping/nerfstudio.py:93-100).  "off" here: every golden vector of the parity
+    # tests was generated with the optimizer off; MappingTrainer(camera_opt=True) and bench.py switch it on.
+    camera_optimizer_mode: str = "off"
 
 
 class NerfactoModel(nn.Module):
@@ -86,6 +90,9 @@ class NerfactoModel(nn.Module):
             args = c.proposal_net_args_list[min(i, len(c.proposal_net_args_list) - 1)]
             self.proposal_networks.append(HashMLPDensityField(aabb, spatial_distortion=contraction, **args))
         self.density_fns = [net.density_fn for net in self.proposal_networks]
+        from .data import CameraOptimizerConfig
+
+        self.camera_optimizer = CameraOptimizerConfig(mode=c.camera_optimizer_mode).setup(num_cameras=num_train_data, device="cpu")
 
         def update_schedule(step):
             return np.clip(np.interp(step, [0, c.proposal_warmup], [0, c.proposal_update_every]), 1, c.proposal_update_every)
@@ -99,7 +106,9 @@ class NerfactoModel(nn.Module):
 
     # ---- bookkeeping the reference does through training callbacks (nerfacto.py:244-286) ------------------
     def get_param_groups(self) -> Dict[str, List[nn.Parameter]]:
-        return {"proposal_networks": list(self.proposal_networks.parameters()), "fields": list(self.field.parameters())}
+        groups = {"proposal_networks": list(self.proposal_networks.parameters()), "fields": list(self.field.parameters())}
+        self.camera_optimizer.get_param_groups(groups)
+        return groups
 
     def before_train_iteration(self, step: int) -> None:
         self.step = step
@@ -129,6 +138,9 @@ class NerfactoModel(nn.Module):
         return self.get_outputs(self.set_nears_and_fars(ray_bundle), jitters)
 
     def get_outputs(self, ray_bundle: RayBundle, jitters: Optional[List[torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        # apply the camera optimizer pose tweaks (NS/models/nerfacto.py:288-291) unless the step prologue already did
+        if self.training and not ray_bundle.pose_corrected:
+            self.camera_optimizer.apply_to_raybundle(ray_bundle)
         ray_samples, weights_list, ray_samples_list = self.proposal_sampler(ray_bundle, density_fns=self.density_fns, jitters=jitters)
         fo = self.field.forward(ray_samples, compute_normals=self.config.predict_normals)
         weights = ray_samples.get_weights(fo[FieldHeadNames.DENSITY])
@@ -185,6 +197,7 @@ class NerfactoModel(nn.Module):
                     loss["orientation_loss"] = c.orientation_loss_mult * torch.mean(outputs["rendered_orientation_loss"])
                 if "rendered_pred_normal_loss" in outputs:
                     loss["pred_normal_loss"] = c.pred_normal_loss_mult * torch.mean(outputs["rendered_pred_normal_loss"])
+            self.camera_optimizer.get_loss_dict(loss)  # nerfacto.py:379-380
         return loss
 
     # ---- evaluation (NS/models/base_model.py:164-192) ----------------------------------------------------------------
@@ -267,6 +280,10 @@ class ExtendedNerfactoModel(DepthNerfactoModel):
             normals_img=outputs["normals"] if use_n else None, normal_gt=batch["normal_image"] if use_n else None,
             depth_gt=batch["depth_image"] if use_d else None, directions_norm=dnorm if use_d else None, sigma=c.depth_sigma, mults=mults,
             eager_grads=eager_grads)
+        if self.camera_optimizer.config.mode != "off" and ops.ray_grad_sink is None:
+            reg: Dict[str, torch.Tensor] = {}
+            self.camera_optimizer.get_loss_dict(reg)  # under MappingTrainer (ray_grad_sink set) the trainer adds value and gradient itself
+            total = total + reg["camera_opt_regularizer"]
         names = ("rgb_loss", "interlevel_loss", "distortion_loss", "depth_loss", "normal_loss")
         # depth: `terms` holds the SUM over the weight sets, its weight the multiplier / number of sets (depth_nerfacto.py:93-103)
         return outputs, total, {n: terms[i] for i, n in enumerate(names) if mults[i] != 0.0}, {n: mults[i] for i, n in enumerate(names) if mults[i] != 0.0}

@@ -406,12 +406,16 @@ class _PropDensity(torch.autograd.Function):
         ctx.table_main_grad = getattr(table, "_nvo_main_grad", None)
         ctx.mlp_main_grad = getattr(params[0], "_nvo_main_grad", None)
         ctx.mspec_shapes = [tuple(p.shape) for p in params]
+        ctx.sink = ray_grad_sink if (positions is None and any(ctx.needs_input_grad)) else None
         return density
 
     @staticmethod
     def backward(ctx, ddensity):
         table, flat, feat, origins, directions, positions = ctx.saved_tensors
         need_dt, need_dp = ctx.needs_input_grad[0], any(ctx.needs_input_grad[10:])
+        # camera-pose optimisation: d loss / d (origins, directions) through this level's sample positions
+        need_rays = positions is None and (ctx.needs_input_grad[4] or ctx.needs_input_grad[5] or ctx.sink is not None)
+        d_o = d_d = None
         dev = table.device
         dtable = dflat = None
         if need_dt:
@@ -426,7 +430,10 @@ class _PropDensity(torch.autograd.Function):
         ddensity = ddensity.contiguous()
         args = ("nvo_prop_density_backward", ctx.gspec.desc(table.dtype, torch.float32), ctx.hidden, ctx.slot, ctx.B, ctx.S, origins, directions, s, e, stride, positions,
                 flat, feat, ddensity, dtable, dflat)
-        split = need_dt and env_flag("NVO_PROP_BWD_SPLIT", True)
+        split = (need_dt and env_flag("NVO_PROP_BWD_SPLIT", True)) or need_rays
+        if need_rays:
+            d_o, d_d = ctx.sink if ctx.sink is not None else (torch.zeros((ctx.B, 3), dtype=torch.float32, device=dev),
+                                                              torch.zeros((ctx.B, 3), dtype=torch.float32, device=dev))
 
         def run():
             if not split:
@@ -438,12 +445,16 @@ class _PropDensity(torch.autograd.Function):
             xq = torch.empty(((n + 127) // 128 * 128, 3), dtype=torch.float32, device=dev)
             call("nvo_prop_density_backward_split", ctx.gspec.desc(table.dtype, torch.float32), ctx.hidden, ctx.slot, ctx.B, ctx.S, flat, feat, ddensity, dflat,
                  dft, xq)
-            grid_backward(xq[:n], dft, ctx.gspec, dtable=dtable.view(-1, 2), tmf=True)
+            if need_dt:
+                grid_backward(xq[:n], dft, ctx.gspec, dtable=dtable.view(-1, 2), tmf=True)
+            if need_rays:
+                dxn = grid_backward_input(xq[:n], table, dft, ctx.gspec, tmf=True)
+                position_backward(origins, directions, ctx.iv, dxn, d_o, d_d)
 
         if leaf_streams.defer_event is not None:
             torch.cuda.current_stream().wait_event(leaf_streams.defer_event)
         if (leaf_streams.enabled and not leaf_streams.on_level_stream() and (not need_dt or dtable is ctx.table_main_grad)
-                and (not need_dp or dflat is ctx.mlp_main_grad)):
+                and (not need_dp or dflat is ctx.mlp_main_grad) and (not need_rays or ctx.sink is not None)):
             with leaf_streams.fork(table, flat, feat, origins, directions, positions, ddensity, ctx.iv):
                 run()
         else:
@@ -460,7 +471,9 @@ class _PropDensity(torch.autograd.Function):
                 k = int(np.prod(shp))
                 grads.append(dflat[off:off + k].view(shp))
                 off += k
-        return (dtable, None, None, None, None, None, None, None, None, None, *grads)
+        if ctx.sink is not None:
+            d_o = d_d = None
+        return (dtable, None, None, None, d_o if ctx.needs_input_grad[4] else None, d_d if ctx.needs_input_grad[5] else None, None, None, None, None, *grads)
 
 
 def prop_density(table, gspec: GridSpec, mspec: MlpSpec, params, B: int, S: int, origins=None, directions=None, iv=None, positions=None, slot: int = 0):
@@ -1064,6 +1077,24 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr: float, beta1: float 
     call("nvo_adam_step", n, params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, grad_scale)
 
 
+def adam_step_decay(params, grads, exp_avg, exp_avg_sq, step, lr_init: float, lr_final: float, max_steps: int, beta1: float = 0.9, beta2: float = 0.999,
+                    eps: float = 1e-8, grad_scale: float = 1.0):
+    """adam_step under ExponentialDecayScheduler (NS/engine/schedulers.py:109-141, no warm-up): the learning rate is evaluated on the device
+    from `step`, so a captured CUDA graph follows the schedule."""
+    n = params.numel()
+    for t, name in ((params, "params"), (grads, "grads"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        check(t, name, torch.float32, (n,))
+    check(step, "step", torch.int32, (1,))
+    call("nvo_adam_step_decay", n, params, grads, exp_avg, exp_avg_sq, step, lr_init, lr_final, int(max_steps), beta1, beta2, eps, grad_scale)
+
+
+def pose_regularizer(pose_adjustment, trans_l2_penalty: float, rot_l2_penalty: float, loss=None, d_pose=None, scale: float = 1.0):
+    """CameraOptimizer.get_loss_dict (camera_optimizers.py:149-155): adds the regulariser to `loss` (device scalar) and scale * its gradient
+    to d_pose [K,6]."""
+    check(pose_adjustment, "pose_adjustment", torch.float32, (None, 6))
+    call("nvo_pose_regularizer", pose_adjustment.shape[0], pose_adjustment, trans_l2_penalty, rot_l2_penalty, scale, loss, d_pose)
+
+
 # ------------------------------------------------------------------------------------------------
 # tensor-core (tcgen05) MLP path: fp16 operands, fp32 accumulate, for widths <= 64 and depth <= 4
 # ------------------------------------------------------------------------------------------------
@@ -1459,45 +1490,68 @@ def field_forward(feat16, jac, positions, directions, cam_idx, embedding, select
 FS_CHUNKS, FS_CHUNKS_HEAD, FS_P, FS_AP1, CHUNK_B = 60, 32, 32, 36, 2048  # saved-tile layout of csrc/field_tc.cu
 
 
-def field_backward(feat16, saved, save_pn: bool, wimage, rgb, h0, selector, cam_idx, ddensity, drgb, dpn_in, B: int, S: int, dbase, dhead, demb):
-    """One launch: returns dfeat (fp32 TMF [tiles][32][128]); ACCUMULATES into dbase / dhead / demb."""
+def field_backward(feat16, saved, save_pn: bool, wimage, rgb, h0, selector, cam_idx, ddensity, drgb, dpn_in, B: int, S: int, dbase, dhead, demb,
+                   directions=None, ddirections=None):
+    """One launch: returns dfeat (fp32 TMF [tiles][32][128]); ACCUMULATES into dbase / dhead / demb (and ddirections [B,3])."""
     n = B * S
     check(drgb, "drgb", torch.float32, (n, 3))
     if ddensity is not None:
         check(ddensity, "ddensity", torch.float32, (n,))
     dfeat = torch.empty(tmh_numel(n, 32), dtype=torch.float32, device=feat16.device)
     scratch = torch.empty(2, dtype=torch.float32, device=feat16.device)
-    call("nvo_field_backward", B, S, feat16, saved, int(save_pn), wimage, rgb, h0, selector, cam_idx, ddensity, drgb, dpn_in, scratch, dfeat, dbase, dhead, demb)
+    call("nvo_field_backward", B, S, feat16, saved, int(save_pn), wimage, rgb, h0, selector, cam_idx, ddensity, drgb, dpn_in, scratch, dfeat, dbase, dhead, demb,
+         directions, ddirections)
     return dfeat
 
 
+# d loss / d (ray origins, ray directions) of the step in flight: (d_origins [B,3], d_directions [B,3]) zeroed by the trainer, or None.  While
+# set, the field / proposal-density backward passes ACCUMULATE their contributions there (on whatever side stream they run on) instead of
+# returning them through autograd; the trainer turns the sums into d loss / d pose_adjustment after joining the streams
+# (CameraOptimizer.apply_to_raybundle's backward, NS/cameras/camera_optimizers.py:142-147).
+ray_grad_sink = None
+
+
+def position_backward(origins, directions, iv: "Intervals", dx, d_origins, d_directions) -> None:
+    """Accumulates d loss / d (origins, directions) [B,3] from dx [B*S,3] = d loss / d (normalised contracted sample positions)."""
+    s, e, stride = iv.triple()
+    check(dx, "dx", torch.float32, (iv.B * iv.S, 3))
+    call("nvo_position_backward", iv.B, iv.S, origins, directions, s, e, stride, dx, d_origins, d_directions)
+
+
 class _FieldFused(torch.autograd.Function):
-    """NerfactoField.forward on the fused tensor-core path (csrc/field_tc.cu): hash grid (+ saved d feature / dx) -> ONE kernel for mlp_base,
-    density-gradient normals, input assembly, mlp_head and mlp_pred_normals; backward: ONE kernel for mlp_head, assembly and mlp_base
-    (+ the per-network kernel on the saved tiles for mlp_pred_normals when it receives a gradient), then the table scatter.
+    """NerfactoField.forward on the fused tensor-core path (csrc/field_tc.cu): sample positions -> contraction -> hash grid (+ saved d feature / dx)
+    -> ONE kernel for mlp_base, density-gradient normals, input assembly, mlp_head and mlp_pred_normals; backward: ONE kernel for mlp_head,
+    assembly and mlp_base (+ the per-network kernel on the saved tiles for mlp_pred_normals when it receives a gradient), then the table
+    scatter and, for camera-pose optimisation, d loss / d (origins, directions).
     Returns density [n], rgb [n,3], pred_normals [n,3] | None, normals [n,3] | None (no gradient: base_field.py:92-97 is first order),
-    h0 [n] (raw density, no gradient)."""
+    h0 [n] (raw density, no gradient), x [n,3] (normalised sample locations, no gradient)."""
 
     @staticmethod
-    def forward(ctx, x, table, embedding, selector, positions, directions, cam_idx, B, S, gspec, want_normals, save_pn, pn_spec, n_base, n_head, *params):
+    def forward(ctx, origins, directions, table, embedding, cam_idx, iv, B, S, gspec, want_normals, save_pn, pn_spec, n_base, n_head, *params):
         ctx.set_materialize_grads(False)
         n = B * S
         base_params, head_params, pn_params = params[:n_base], params[n_base:n_base + n_head], params[n_base + n_head:]
         want_pn = len(pn_params) > 0
-        x = x.contiguous()
-        if want_normals:
+        origins = check(origins.contiguous(), "origins", torch.float32, (B, 3))
+        directions = check(directions.contiguous(), "directions", torch.float32, (B, 3))
+        positions = sample_positions(origins, directions, iv).reshape(-1, 3)
+        x, selector = contract_normalize(positions)
+        need = any(ctx.needs_input_grad)
+        want_ray_grads = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or (ray_grad_sink is not None and need)
+        if want_normals or want_ray_grads:
             feat16, jac = grid_forward_jac(x, table, gspec)
         else:
             feat16, jac = grid_forward(x, table, gspec, "tmh"), None
         wimage = field_pack_weights(gspec, _flat_of(base_params), _flat_of(head_params), _flat_of(pn_params) if want_pn else None)
-        need = any(ctx.needs_input_grad)
         embedding = check(embedding.contiguous(), "appearance embedding", torch.float32)
-        density, rgb, pn, normals, h0, pn_raw, saved = field_forward(feat16, jac, positions if want_pn else None, directions, cam_idx, embedding, selector,
-                                                                     wimage, B, S, want_pn, need, bool(save_pn and want_pn))
+        density, rgb, pn, normals, h0, pn_raw, saved = field_forward(feat16, jac if want_normals else None, positions if want_pn else None, directions, cam_idx,
+                                                                     embedding, selector, wimage, B, S, want_pn, need, bool(save_pn and want_pn))
         # a trainable mlp_pred_normals runs its backward through the per-network kernel (its own weight-image format)
         pn_wimage = tc_pack_weights(_flat_of(pn_params), pn_spec) if (need and save_pn and want_pn) else None
-        ctx.save_for_backward(x, table, feat16, wimage, saved, rgb, h0, selector, cam_idx, pn_raw, pn_wimage)
+        ctx.save_for_backward(x, table, feat16, wimage, saved, rgb, h0, selector, cam_idx, pn_raw, pn_wimage, origins, directions,
+                              jac if want_ray_grads else None)
         ctx.B, ctx.S, ctx.gspec, ctx.pn_spec, ctx.save_pn, ctx.emb_shape = B, S, gspec, pn_spec, bool(save_pn and want_pn), embedding.shape
+        ctx.iv, ctx.sink = iv, ray_grad_sink if want_ray_grads else None
         ctx.n_base, ctx.n_head, ctx.n_pn = n_base, n_head, len(pn_params)
         ctx.base_spec_shapes = [tuple(p.shape) for p in base_params]
         ctx.head_spec_shapes = [tuple(p.shape) for p in head_params]
@@ -1507,13 +1561,13 @@ class _FieldFused(torch.autograd.Function):
         ctx.base_main_grad = getattr(base_params[0], "_nvo_main_grad", None)
         ctx.head_main_grad = getattr(head_params[0], "_nvo_main_grad", None)
         ctx.pn_main_grad = getattr(pn_params[0], "_nvo_main_grad", None) if want_pn else None
-        nd = [t for t in (normals, h0) if t is not None]
+        nd = [t for t in (normals, h0, x) if t is not None]
         ctx.mark_non_differentiable(*nd)
-        return density, rgb, pn, normals, h0
+        return density, rgb, pn, normals, h0, x
 
     @staticmethod
-    def backward(ctx, ddensity, drgb, dpn, _dnormals, _dh0):
-        x, table, feat16, wimage, saved, rgb, h0, selector, cam_idx, pn_raw, pn_wimage = ctx.saved_tensors
+    def backward(ctx, ddensity, drgb, dpn, _dnormals, _dh0, _dx):
+        x, table, feat16, wimage, saved, rgb, h0, selector, cam_idx, pn_raw, pn_wimage, origins, directions, jac = ctx.saved_tensors
         B, S = ctx.B, ctx.S
         n, dev = B * S, x.device
         c = lambda t: None if t is None else t.contiguous()
@@ -1539,23 +1593,39 @@ class _FieldFused(torch.autograd.Function):
         dbase = ctx.base_main_grad if ctx.base_main_grad is not None else zeros(flat_numel(ctx.base_spec_shapes))
         dhead = ctx.head_main_grad if ctx.head_main_grad is not None else zeros(flat_numel(ctx.head_spec_shapes))
         demb = None
-        if ctx.needs_input_grad[2]:
+        if ctx.needs_input_grad[3]:
             demb = ctx.emb_main_grad if (ctx.emb_main_grad is not None and cam_idx is not None) else torch.zeros(ctx.emb_shape, dtype=torch.float32, device=dev)
-        dfeat = field_backward(feat16, saved, ctx.save_pn, wimage, rgb, h0, selector, cam_idx, c(ddensity), drgb.contiguous(), dpn_in, B, S, dbase, dhead, demb)
-        need_dx, need_dt = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        dtable = dx = None
+        # camera-pose optimisation: d loss / d (origins, directions), into the trainer's sink or back through autograd
+        need_rays = jac is not None
+        d_o = d_d = None
+        if need_rays:
+            d_o, d_d = ctx.sink if ctx.sink is not None else (torch.zeros((B, 3), dtype=torch.float32, device=dev), torch.zeros((B, 3), dtype=torch.float32, device=dev))
+        dfeat = field_backward(feat16, saved, ctx.save_pn, wimage, rgb, h0, selector, cam_idx, c(ddensity), drgb.contiguous(), dpn_in, B, S, dbase, dhead, demb,
+                               directions if need_rays else None, d_d)
+        need_dt = ctx.needs_input_grad[2]
+        dtable = None
         if need_dt:
             if ctx.table_main_grad is not None and leaf_streams.enabled:
                 with leaf_streams.fork(x, dfeat, critical=True):
                     grid_backward(x, dfeat, ctx.gspec, dtable=ctx.table_main_grad, tmf=True)
-                    if leaf_streams.after_field_backward is not None and not need_dx:
+                    if leaf_streams.after_field_backward is not None:
                         leaf_streams.after_field_backward()
             elif ctx.table_main_grad is not None:
                 grid_backward(x, dfeat, ctx.gspec, dtable=ctx.table_main_grad, tmf=True)
             else:
                 dtable = grid_backward(x, dfeat, ctx.gspec, tmf=True).view(table.shape)
-        if need_dx:
-            dx = grid_backward_input(x, table, dfeat, ctx.gspec, tmf=True)
+        if need_rays:
+            # d x through the saved feature derivatives (one streaming pass instead of a second gather over the table), then the contraction
+            # Jacobian and the per-ray sums; positions feed mlp_pred_normals' encoding too, but that path carries no gradient here
+            def rays():
+                dxn = grid_jac_dx(jac, dfeat, ctx.gspec, n)
+                position_backward(origins, directions, ctx.iv, dxn, d_o, d_d)
+
+            if ctx.sink is not None and leaf_streams.enabled:
+                with leaf_streams.fork(jac, dfeat, origins, directions, ctx.iv):
+                    rays()
+            else:
+                rays()
 
         def split(flat, shapes, main):
             if main is not None or flat is None:
@@ -1569,13 +1639,17 @@ class _FieldFused(torch.autograd.Function):
 
         if demb is ctx.emb_main_grad:
             demb = None
+        if ctx.sink is not None:
+            d_o = d_d = None
         grads = split(dbase, ctx.base_spec_shapes, ctx.base_main_grad) + split(dhead, ctx.head_spec_shapes, ctx.head_main_grad) + split(dpn_flat, ctx.pn_shapes, ctx.pn_main_grad)
-        return (dx, dtable, demb, None, None, None, None, None, None, None, None, None, None, None, None, *grads)
+        return (d_o if ctx.needs_input_grad[0] else None, d_d if ctx.needs_input_grad[1] else None, dtable, demb, None, None, None, None, None, None, None, None,
+                None, None, *grads)
 
 
-def field_fused(x, table, embedding, selector, positions, directions, cam_idx, B: int, S: int, gspec: GridSpec, want_normals: bool, base_params, head_params,
+def field_fused(origins, directions, iv, table, embedding, cam_idx, B: int, S: int, gspec: GridSpec, want_normals: bool, base_params, head_params,
                 pn_spec: Optional[MlpSpec] = None, pn_params=(), save_pn: bool = True):
-    return _FieldFused.apply(x, table, embedding, selector, positions, directions, cam_idx, B, S, gspec, want_normals, save_pn, pn_spec, len(base_params),
+    """origins / directions [B,3] per ray, iv = the samples' Euclidean intervals; see _FieldFused."""
+    return _FieldFused.apply(origins, directions, table, embedding, cam_idx, iv, B, S, gspec, want_normals, save_pn, pn_spec, len(base_params),
                              len(head_params), *base_params, *head_params, *pn_params)
 
 

@@ -126,6 +126,13 @@ class PeerBuffers:
         _lib.call("nvo_adam_exchange_group", off, n, gid, self.rank, self.world, ctypes.addressof(self._h_params), ctypes.addressof(self._h_grads),
                   ctypes.addressof(self._h_flags), m, v, step, lr, beta1, beta2, eps, 1.0 / self.world, int(ctas_per_sm))
 
+    def adam_exchange_group_decay(self, gid: int, step: torch.Tensor, lr_init: float, lr_final: float, max_steps: int, beta1: float, beta2: float,
+                                  eps: float, ctas_per_sm: int = 0) -> None:
+        """adam_exchange_group with ExponentialDecayScheduler's learning rate evaluated on the device (the "camera_opt" group)."""
+        off, n, m, v = self._groups[gid]
+        _lib.call("nvo_adam_exchange_group_decay", off, n, gid, self.rank, self.world, ctypes.addressof(self._h_params), ctypes.addressof(self._h_grads),
+                  ctypes.addressof(self._h_flags), m, v, step, lr_init, lr_final, int(max_steps), beta1, beta2, eps, 1.0 / self.world, int(ctas_per_sm))
+
     def adam_exchange_groups2(self, gid_a: int, step_a: torch.Tensor, gid_b: int, step_b: torch.Tensor, lr: float, beta1: float, beta2: float, eps: float) -> None:
         """Both groups in ONE launch (one pair of barriers): for steps on which their gradients are complete at the same time."""
         oa, na, ma, va = self._groups[gid_a]

@@ -108,6 +108,7 @@ class RayBundle:
     fars: Optional[torch.Tensor] = None
     metadata: Dict[str, torch.Tensor] = field(default_factory=dict)
     times: Optional[torch.Tensor] = None
+    pose_corrected: bool = False  # the camera optimizer's correction is already applied (fused step prologue, data.py)
 
     def __len__(self) -> int:
         return self.origins.numel() // self.origins.shape[-1]
@@ -115,7 +116,7 @@ class RayBundle:
     def _map(self, fn) -> "RayBundle":
         f = lambda t: None if t is None else fn(t)
         return RayBundle(f(self.origins), f(self.directions), f(self.pixel_area), f(self.camera_indices), f(self.nears), f(self.fars),
-                         {k: fn(v) for k, v in self.metadata.items()}, f(self.times))
+                         {k: fn(v) for k, v in self.metadata.items()}, f(self.times), self.pose_corrected)
 
     def flatten(self) -> "RayBundle":
         return self._map(lambda t: t.reshape(-1, t.shape[-1]))

@@ -35,7 +35,10 @@ from .rays import RayBundle
 class MappingTrainer:
     def __init__(self, model: ExtendedNerfactoModel, num_rays: int, lr: float = 1e-2, eps: float = 1e-15, betas=(0.9, 0.999),
                  use_cuda_graph: bool = True, with_normals: bool = True, device: Optional[torch.device] = None, exchange: str = "fused",
-                 datamanager=None, proposal_update: str = "always", external_draws: bool = False):
+                 datamanager=None, proposal_update: str = "always", external_draws: bool = False, camera_opt_lr: float = 1e-4,
+                 camera_opt_lr_final: float = 1e-5, max_num_iterations: int = 8192):
+        """camera_opt_lr / camera_opt_lr_final / max_num_iterations: the "camera_opt" group (Adam, ExponentialDecayScheduler over the mapping
+        iterations, nerf_vo/mapping/nerfstudio.py:93-100), trained when the model's camera optimizer is on (config.camera_optimizer_mode)."""
         self.model = model
         # optional: a DynamicDataManager (data.py). The step then starts with the fused prologue kernel (pixel sampling + gather + ray
         # generation, drawn on the device like the reference's torch.rand) instead of reading the static input buffers.
@@ -51,6 +54,7 @@ class MappingTrainer:
             raise ValueError(f"exchange must be 'fused' (peer-memory reduce-scatter + Adam + all-gather kernel) or 'nccl', got {exchange!r}")
         self.exchange = exchange if self.world_size > 1 else "local"
         self.peer = None
+        self._peer_cam = None
         self.use_cuda_graph = use_cuda_graph
         self.with_normals = with_normals
         if proposal_update not in ("always", "reference"):
@@ -72,13 +76,21 @@ class MappingTrainer:
         total = sum(sizes)
         # parameter groups = contiguous ranges of the flat buffer: "fields" first, "proposal_networks" behind it (registration order)
         names = {id(p): n for n, p in model.named_parameters()}
+        # the camera optimizer's pose deltas ("camera_opt": own learning rate and schedule) sit behind both groups, registered last
+        is_cam = [names[id(p)].startswith("camera_optimizer.") for p in self.params]
+        n_cam = sum(sz for sz, cm in zip(sizes, is_cam) if cm)
+        if n_cam and not all(is_cam[is_cam.index(True):]):
+            raise RuntimeError("internal: camera optimizer parameters must be registered last")
         is_prop = [names[id(p)].startswith("proposal_networks.") for p in self.params]
-        n_fields = sum(sz for sz, pr in zip(sizes, is_prop) if not pr)
-        contiguous = all(not pr for pr in is_prop[:is_prop.index(True)]) and all(is_prop[is_prop.index(True):]) if any(is_prop) else True
-        if any(is_prop) and contiguous and 0 < n_fields < total:
-            self.groups = [("fields", 0, n_fields), ("proposal_networks", n_fields, total - n_fields)]
+        n_fields = sum(sz for sz, pr, cm in zip(sizes, is_prop, is_cam) if not pr and not cm)
+        n_main = total - n_cam
+        contiguous = all(not pr for pr in is_prop[:is_prop.index(True)]) and all(pr or cm for pr, cm in zip(is_prop[is_prop.index(True):], is_cam[is_prop.index(True):])) if any(is_prop) else True
+        if any(is_prop) and contiguous and 0 < n_fields < n_main:
+            self.groups = [("fields", 0, n_fields), ("proposal_networks", n_fields, n_main - n_fields)]
         else:
-            self.groups = [("fields", 0, total)]
+            self.groups = [("fields", 0, n_main)]
+        self.cam_group = ("camera_opt", n_main, n_cam) if n_cam else None
+        self.cam_lr, self.cam_lr_final, self.max_num_iterations = float(camera_opt_lr), float(camera_opt_lr_final), int(max_num_iterations)
         if self.exchange == "fused":
             # parameters and gradients live in peer-mapped (CUDA IPC) allocations; Adam moments only for the slices this rank owns
             from .peer import PeerBuffers
@@ -86,6 +98,7 @@ class MappingTrainer:
             self.peer = PeerBuffers(total, self.device)
             self.flat, self.grad = self.peer.params, self.peer.grads
             self._peer_groups = [self.peer.add_group(off, n) for _, off, n in self.groups]
+            self._peer_cam = self.peer.add_group(self.cam_group[1], self.cam_group[2]) if self.cam_group else None
             self.exp_avg = self.exp_avg_sq = None
         else:
             self.flat = torch.zeros(total, dtype=torch.float32, device=self.device)
@@ -95,6 +108,11 @@ class MappingTrainer:
         # one device step counter per group (torch keeps `step` per parameter; a group that got no gradient is not stepped)
         self.step_counts = [torch.zeros(1, dtype=torch.int32, device=self.device) for _ in self.groups]
         self.step_count = self.step_counts[0]
+        self.cam_step = torch.zeros(1, dtype=torch.int32, device=self.device) if self.cam_group else None
+        # d loss / d (ray origins, ray directions) of the step in flight (ops.ray_grad_sink) and the pose backward's per-camera scratch
+        self._ray_grads = torch.zeros((2, self.B, 3), dtype=torch.float32, device=self.device) if self.cam_group else None
+        if self.cam_group and datamanager is not None:
+            datamanager.camera_optimizer = model.camera_optimizer  # the step prologue applies the pose correction itself
         self._opt_stream: Optional[torch.cuda.Stream] = None
         self._fields_done = False
         self._in_backward = False
@@ -196,9 +214,13 @@ class MappingTrainer:
             # run on side streams next to the proposal sampling; both are joined before their first consumer
             with ops.leaf_streams.fork(self.grad):
                 self.grad.zero_()
+                if self._ray_grads is not None:
+                    self._ray_grads.zero_()
             self.model.field.prepack(self.model.config.num_nerf_samples_per_ray)
         else:
             self.grad.zero_()
+            if self._ray_grads is not None:
+                self._ray_grads.zero_()
         if self.datamanager is not None:
             # DynamicDataManager.next_train (nerfstudio_utils.py:295-300): pixel draws on the device unless the caller supplies them
             bundle, batch = self.datamanager.next_train(0, u=i["u"] if self.external_draws else None)
@@ -213,6 +235,8 @@ class MappingTrainer:
             if self.with_normals:
                 batch["normal_image"] = i["normal"]
         self.model._leaf_renders = side  # proposal depth maps rendered on side streams (joined below), only inside this step
+        if self._ray_grads is not None:
+            ops.ray_grad_sink = (self._ray_grads[0], self._ray_grads[1])
         try:
             # eager_grads: this step differentiates `total` with total.backward() below, i.e. with grad_output == 1
             _, total, terms, weights = self.model.get_train_loss_fused(bundle, batch, [i["jitter0"], i["jitter1"], i["jitter2"]], eager_grads=True)
@@ -240,11 +264,24 @@ class MappingTrainer:
             self._in_backward = False
             ops.leaf_streams.after_field_backward = None
             ops.leaf_streams.defer_event = None
+            ops.ray_grad_sink = None
         ops.clear_prepacked()
         ops.leaf_streams.join()  # scatter kernels running on side streams must land before the all-reduce / optimizer
         if self._fields_done:
             torch.cuda.current_stream().wait_stream(self._opt_stream)
         self.loss.copy_(total.detach())
+        if self.cam_group is not None:
+            # CameraOptimizer.apply_to_raybundle's backward on the summed ray gradients (every level's sample positions + the field's direction
+            # encoding), and the pose regulariser (value into the loss, gradient into the group's range of the flat gradient)
+            co = self.model.camera_optimizer
+            _, off, n = self.cam_group
+            d_pose = self.grad[off:off + co.pose_adjustment.numel()].view(co.pose_adjustment.shape)
+            if self.datamanager is not None:
+                cam_idx, raw = self.datamanager._last_camera_indices, self.datamanager._last_directions_raw
+            else:
+                cam_idx, raw = i["camera_indices"], i["directions"]
+            ops.pose_correction_backward(cam_idx.reshape(-1), raw, self._ray_grads[0], self._ray_grads[1], co.pose_adjustment.detach(), co.mode_id, d_pose=d_pose)
+            ops.pose_regularizer(co.pose_adjustment.detach(), co.config.trans_l2_penalty, co.config.rot_l2_penalty, loss=self.loss, d_pose=d_pose)
         self._terms, self._term_weights = terms, weights
 
     def _fields_optimizer_hook(self) -> None:
@@ -278,6 +315,7 @@ class MappingTrainer:
             # both groups pending at the same point of the step: one exchange launch, one pair of barriers
             self.peer.adam_exchange_groups2(self._peer_groups[0], self.step_counts[0], self._peer_groups[1], self.step_counts[1], self.lr,
                                             self.betas[0], self.betas[1], self.eps)
+            self._optimizer_camera()
             return
         side = self.device.type == "cuda" and ops.leaf_streams.enabled and self.peer is None
         forked = False
@@ -295,6 +333,19 @@ class MappingTrainer:
         if forked:
             ops.leaf_streams.join()
         self._fields_done = False
+        self._optimizer_camera()
+
+    def _optimizer_camera(self) -> None:
+        """The "camera_opt" group: Adam under ExponentialDecayScheduler, every step (the pose deltas receive gradients through all three levels)."""
+        if self.cam_group is None:
+            return
+        _, off, n = self.cam_group
+        if self.peer is not None:
+            self.peer.adam_exchange_group_decay(self._peer_cam, self.cam_step, self.cam_lr, self.cam_lr_final, self.max_num_iterations, self.betas[0],
+                                                self.betas[1], self.eps, ctas_per_sm=1)
+            return
+        ops.adam_step_decay(self.flat[off:off + n], self.grad[off:off + n], self.exp_avg[off:off + n], self.exp_avg_sq[off:off + n], self.cam_step,
+                            self.cam_lr, self.cam_lr_final, self.max_num_iterations, self.betas[0], self.betas[1], self.eps, 1.0 / self.world_size)
 
     def _exchange(self) -> None:
         """NCCL arm: sum-all-reduce of the flat gradient (the fused arm exchanges inside the optimizer kernel)."""
@@ -421,7 +472,8 @@ class MappingTrainer:
 
     def _moment_tensors(self) -> List[torch.Tensor]:
         if self.peer is not None:
-            return [t for gid in self._peer_groups for t in self.peer.group_moments(gid)]
+            gids = self._peer_groups + ([self._peer_cam] if self._peer_cam is not None else [])
+            return [t for gid in gids for t in self.peer.group_moments(gid)]
         return [self.exp_avg, self.exp_avg_sq]
 
     def full_moments(self):
@@ -454,14 +506,17 @@ class MappingTrainer:
             for t, src in zip(self.peer.group_moments(gid), (exp_avg, exp_avg_sq)):
                 t[:hi - lo].copy_(src[off + lo:off + hi])
 
+    def _counters(self) -> List[torch.Tensor]:
+        return self.step_counts + ([self.cam_step] if self.cam_step is not None else [])
+
     def _snapshot_state(self):
-        return ([t.clone() for t in [self.flat] + self._moment_tensors() + self.step_counts], self.iteration, self._ssu,
+        return ([t.clone() for t in [self.flat] + self._moment_tensors() + self._counters()], self.iteration, self._ssu,
                 self.model.proposal_sampler._step, self.model.proposal_sampler._steps_since_update)
 
     def _restore_state(self, state) -> None:
         tensors, self.iteration, self._ssu, ps_step, ps_ssu = state
         with torch.no_grad():
-            for dst, src in zip([self.flat] + self._moment_tensors() + self.step_counts, tensors):
+            for dst, src in zip([self.flat] + self._moment_tensors() + self._counters(), tensors):
                 dst.copy_(src)
         self.model.proposal_sampler._step, self.model.proposal_sampler._steps_since_update = ps_step, ps_ssu
         if self.world_size > 1:

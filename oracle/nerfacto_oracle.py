@@ -326,7 +326,8 @@ def nerfacto_field(
     pos = sample_positions(origins, directions, starts, ends)
     with torch.enable_grad():
         x, sel = normalized_positions(pos)
-        x = x.detach().requires_grad_(True)  # nerfacto_field.py:210-212 (leaf w.r.t. normals)
+        if not x.requires_grad:  # nerfacto_field.py:210-212: a leaf for the normals unless the rays already carry a graph (camera optimizer on:
+            x = x.detach().requires_grad_(True)  # then the sample locations stay differentiable w.r.t. the pose deltas)
         feat = hash_encode(x.reshape(-1, 3), P["field.mlp_base.model.0.hash_table"], level_scalings(gc), gc.log2_hashmap_size)
         ws, bs = _layers(P, "field.mlp_base.model.1")
         h = mlp_forward(feat, ws, bs).reshape(B, S, -1)

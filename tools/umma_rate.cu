@@ -29,6 +29,8 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_
 
 // mode 0: fwd (A K-major lbo 2048/sbo 128, B K-major lbo N*16/sbo 128); 1: dgrad (B MN-major lbo 128/sbo N*16); 2: wgrad (both MN-major lbo 128/sbo 2048)
 // mode 3: fwd with 128B-swizzle descriptors (K-major, sbo 1024) — data is garbage, only the rate matters
+// mode 4 / 5: as mode 0 (no swizzle) / mode 3 (128B swizzle) but every MMA reads DIFFERENT operand tiles (four A tiles and four B tiles in
+// rotation, as the K steps of a layer do): the same-descriptor loops above may be served from an operand cache
 __global__ void __launch_bounds__(128) rate(int mode, int N, int R, int two_acc, long long* out) {
     extern __shared__ __align__(1024) unsigned char dyn[];
     __shared__ __align__(8) uint64_t mbar;
@@ -53,8 +55,19 @@ __global__ void __launch_bounds__(128) rate(int mode, int N, int R, int two_acc,
         if (mode == 0) { idesc = make_idesc(128, N, 0, 0); ad = make_desc(a0, 2048, 128, 0); bd = make_desc(b0, N * 16, 128, 0); }
         else if (mode == 1) { idesc = make_idesc(128, N, 0, 1); ad = make_desc(a0, 2048, 128, 0); bd = make_desc(b0, 128, N * 16, 0); }
         else if (mode == 2) { idesc = make_idesc(128, N, 1, 1); ad = make_desc(a0, 128, 2048, 0); bd = make_desc(b0, 128, 2048, 0); }
-        else { idesc = make_idesc(128, N, 0, 0); ad = make_desc(a0, 16, 1024, 2); bd = make_desc(b0, 16, 1024, 2); }
+        else if (mode == 3 || mode == 5) { idesc = make_idesc(128, N, 0, 0); ad = make_desc(a0, 16, 1024, 2); bd = make_desc(b0, 16, 1024, 2); }
+        else { idesc = make_idesc(128, N, 0, 0); ad = make_desc(a0, 2048, 128, 0); bd = make_desc(b0, N * 16, 128, 0); }
         t0 = clock64();
+        if (mode >= 4) {
+            // operand tiles 4 KB (A: 128 rows x 16 columns) / N * 32 B (B) apart: descriptor start address field += bytes >> 4
+            const uint64_t a_step = 4096 >> 4, b_step = (uint64_t)(N * 32) >> 4;
+            for (int r = 0; r < R; r += 4) {
+                mma_f16(tmem, ad, bd, idesc, r > 1);
+                mma_f16(tmem, ad + a_step, bd + b_step, idesc, 1);
+                mma_f16(tmem, ad + 2 * a_step, bd + 2 * b_step, idesc, 1);
+                mma_f16(tmem, ad + 3 * a_step, bd + 3 * b_step, idesc, 1);
+            }
+        } else
         for (int r = 0; r < R; ++r) mma_f16(tmem + (two_acc ? (r & 1) * 256 : 0), ad, bd, idesc, r > 1);
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
     }
@@ -76,11 +89,13 @@ int main() {
     long long h[148];
     cudaFuncSetAttribute(rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
     const int R = 4096;
-    const char* names[] = {"fwd  K/K  no-swizzle", "dgrad K/MN no-swizzle", "wgrad MN/MN no-swizzle", "fwd  K/K  128B-swizzle"};
-    for (int mode = 0; mode < 4; ++mode)
-        for (int N : {16, 32, 64, 80, 128, 256})
+    const char* names[] = {"fwd  K/K  no-swizzle", "dgrad K/MN no-swizzle", "wgrad MN/MN no-swizzle", "fwd  K/K  128B-swizzle",
+                           "fwd no-swizzle, rotating tiles", "fwd 128B-swizzle, rotating tiles"};
+    for (int mode = 0; mode < 6; ++mode)
+        for (int N : {16, 32, 64, 128, 256})
             for (int two = 0; two < 2; ++two) {
-                if (mode == 2 && N > 128) continue;
+                if ((mode == 1 || mode == 2) && N > 128) continue;
+                if (mode >= 4 && (two || N > 128)) continue;
                 rate<<<148, 128, 65536>>>(mode, N, R, two, d);
                 cudaError_t e = cudaDeviceSynchronize();
                 if (e != cudaSuccess) { printf("%s N=%d: %s\n", names[mode], N, cudaGetErrorString(e)); return 1; }
