@@ -325,6 +325,10 @@ int nvo_generate_rays(void* stream, int64_t n, int32_t cam, int32_t W, const int
                       int64_t* camera_indices, float* origins, float* directions, float* directions_norm, float* pixel_area);
 /* exp_map_SO3xR3 / exp_map_SE3 (NS/cameras/lie_groups.py:25-60,63-120): tangent[n,6] -> matrices[n,3,4] (CameraOptimizer.forward) */
 int nvo_pose_exp_map(void* stream, int64_t n, int32_t pose_mode, const float* tangent, float* matrices);
+/* CameraOptimizer.apply_to_raybundle (NS/cameras/camera_optimizers.py:142-147): origins_out = origins + t(camera), directions_out =
+ * R(camera) directions, with [R|t] = exp map of pose_adjustment[camera_indices[i]]. */
+int nvo_pose_apply(void* stream, int64_t B, int32_t pose_mode, const int64_t* camera_indices, const float* pose_adjustment, const float* origins,
+                   const float* directions, float* origins_out, float* directions_out);
 /* backward of the pose correction: d_pose[K,6] += d(origins, directions)/d(pose_adjustment) applied to (d_origins, d_directions)[B,3].
  * scratch[K,12] must be zero on entry (per-camera cotangent of [R|t], accumulated by reductions). */
 int nvo_pose_correction_backward(void* stream, int64_t B, int32_t K, int32_t pose_mode, const int64_t* camera_indices, const float* directions_raw,

@@ -317,6 +317,37 @@ extern "C" int nvo_pose_exp_map(void* stream, int64_t n, int32_t pose_mode, cons
     return 0;
 }
 
+// CameraOptimizer.apply_to_raybundle on an existing bundle (NS/cameras/camera_optimizers.py:142-147) in one launch: every ray evaluates its
+// camera's exp map (a few dozen flops) instead of the gather / add / bmm chain over a [K,3,4] matrix table
+__global__ void __launch_bounds__(128) k_pose_apply(int64_t B, int mode, const int64_t* __restrict__ cam_idx, const float* __restrict__ pose,
+                                                    const float* __restrict__ o, const float* __restrict__ d, float* __restrict__ oo, float* __restrict__ od) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const float* tp = pose + 6 * __ldg(cam_idx + i);
+    float t[6], M[3][4];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) t[k] = __ldg(tp + k);
+    exp_map<float>(mode, t, M);
+    const float dv[3] = {__ldg(d + 3 * i), __ldg(d + 3 * i + 1), __ldg(d + 3 * i + 2)};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        oo[3 * i + a] = __ldg(o + 3 * i + a) + M[a][3];
+        od[3 * i + a] = M[a][0] * dv[0] + M[a][1] * dv[1] + M[a][2] * dv[2];
+    }
+}
+
+extern "C" int nvo_pose_apply(void* stream, int64_t B, int32_t pose_mode, const int64_t* camera_indices, const float* pose_adjustment, const float* origins,
+                              const float* directions, float* origins_out, float* directions_out) {
+    NVO_CHECK(pose_mode == NVO_POSE_SO3XR3 || pose_mode == NVO_POSE_SE3, "nvo_pose_apply: pose_mode must be SO3xR3 (1) or SE3 (2), got %d", pose_mode);
+    NVO_CHECK(B >= 0, "nvo_pose_apply: negative size");
+    if (B == 0) return 0;
+    NVO_CHECK(camera_indices && pose_adjustment && origins && directions && origins_out && directions_out, "nvo_pose_apply: null pointer");
+    k_pose_apply<<<nvo_blocks(B, 128), 128, 0, (cudaStream_t)stream>>>(B, pose_mode, camera_indices, pose_adjustment, origins, directions, origins_out,
+                                                                        directions_out);
+    NVO_CUDA_LAUNCH_CHECK("k_pose_apply");
+    return 0;
+}
+
 extern "C" int nvo_pose_correction_backward(void* stream, int64_t B, int32_t K, int32_t pose_mode, const int64_t* camera_indices, const float* directions_raw,
                                             const float* d_origins, const float* d_directions, const float* pose_adjustment, float* scratch,
                                             float* d_pose) {

@@ -367,6 +367,42 @@ __global__ void __launch_bounds__(256) k_grid_bwd_input(const __grid_constant__ 
     }
 }
 
+// dL/dx, one thread per SAMPLE walking all LL levels (the proposal grids' L = 5 does not divide a warp: the (sample, level) kernel above
+// then needs a zero fill and three atomics per thread): 8 LL gathers in flight per thread, one 12-byte store.
+template <int LL>
+__global__ void __launch_bounds__(256) k_grid_bwd_input_sample(const __grid_constant__ GridP p, int64_t n, const float* __restrict__ x,
+                                                               const float2* __restrict__ table, const float* __restrict__ dy, float* __restrict__ dx, int tmf) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const float px = __ldg(x + 3 * s), py = __ldg(x + 3 * s + 1), pz = __ldg(x + 3 * s + 2);
+    const uint32_t mask = (1u << p.log2T) - 1u;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+    for (int l = 0; l < LL; ++l) {
+        const float scale = p.scale[l];
+        const Corner c = make_corner(px, py, pz, scale);
+        float2 f[8];
+        gather_level(table + ((size_t)l << p.log2T), c, mask, f);
+        const float2 g = load_dy(dy, s, l, LL, tmf);
+        const float mx = 1.f - c.ox, my = 1.f - c.oy, mz = 1.f - c.oz;
+        float ax = 0.f, ay = 0.f, az = 0.f;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+#define FJ(k) (j == 0 ? f[k].x : f[k].y)
+            const float gj = j == 0 ? g.x : g.y;
+            const float f03 = FJ(0) * c.ox + FJ(3) * mx, f12 = FJ(1) * c.ox + FJ(2) * mx;
+            const float f56 = FJ(5) * c.ox + FJ(6) * mx, f47 = FJ(4) * c.ox + FJ(7) * mx;
+            const float f0312 = f03 * c.oy + f12 * my, f4756 = f47 * c.oy + f56 * my;
+            az += gj * (f0312 - f4756);
+            ay += gj * (c.oz * (f03 - f12) + mz * (f47 - f56));
+            ax += gj * (c.oz * (c.oy * (FJ(0) - FJ(3)) + my * (FJ(1) - FJ(2))) + mz * (c.oy * (FJ(4) - FJ(7)) + my * (FJ(5) - FJ(6))));
+#undef FJ
+        }
+        gx += ax * scale, gy += ay * scale, gz += az * scale;
+    }
+    dx[3 * s] = gx, dx[3 * s + 1] = gy, dx[3 * s + 2] = gz;
+}
+
 __global__ void __launch_bounds__(256) k_grid_indices(const __grid_constant__ GridP p, int64_t total, const float* __restrict__ x, int64_t* __restrict__ idx) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
@@ -492,6 +528,11 @@ extern "C" int nvo_grid_backward_input(const nvo_grid_desc* d, void* stream, int
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned int g = nvo_blocks(total, 256);
     const int shuffle = (p.L <= 32 && (p.L & (p.L - 1)) == 0) ? 1 : 0;
+    if (p.L == 5 && d->table_dtype == NVO_F32 && (d->out_dtype == NVO_F32 || d->out_dtype == NVO_F32_TMF)) {
+        k_grid_bwd_input_sample<5><<<nvo_blocks(n, 256), 256, 0, st>>>(p, n, x, (const float2*)table, (const float*)dy, dx, d->out_dtype == NVO_F32_TMF);
+        NVO_CUDA_LAUNCH_CHECK("grid_backward_input(sample)");
+        return 0;
+    }
     if (!shuffle) {
         cudaError_t e = cudaMemsetAsync(dx, 0, sizeof(float) * 3 * n, st);
         NVO_CHECK(e == cudaSuccess, "grid_backward_input: memset failed: %s", cudaGetErrorString(e));

@@ -445,11 +445,19 @@ class _PropDensity(torch.autograd.Function):
             xq = torch.empty(((n + 127) // 128 * 128, 3), dtype=torch.float32, device=dev)
             call("nvo_prop_density_backward_split", ctx.gspec.desc(table.dtype, torch.float32), ctx.hidden, ctx.slot, ctx.B, ctx.S, flat, feat, ddensity, dflat,
                  dft, xq)
-            if need_dt:
-                grid_backward(xq[:n], dft, ctx.gspec, dtable=dtable.view(-1, 2), tmf=True)
-            if need_rays:
+            def ray_part():
                 dxn = grid_backward_input(xq[:n], table, dft, ctx.gspec, tmf=True)
                 position_backward(origins, directions, ctx.iv, dxn, d_o, d_d)
+
+            if need_rays and ctx.sink is not None and leaf_streams.enabled:
+                # the gather pass for d loss / d positions (L2-read bound) next to the table scatter (reduction bound), both reading dft;
+                # joined with the other leaf streams before the optimizer touches the table
+                with leaf_streams.fork(xq, dft, table, origins, directions, ctx.iv):
+                    ray_part()
+            if need_dt:
+                grid_backward(xq[:n], dft, ctx.gspec, dtable=dtable.view(-1, 2), tmf=True)
+            if need_rays and not (ctx.sink is not None and leaf_streams.enabled):
+                ray_part()
 
         if leaf_streams.defer_event is not None:
             torch.cuda.current_stream().wait_event(leaf_streams.defer_event)
@@ -1745,25 +1753,31 @@ def pose_exp_map(tangent, mode: int):
 class _PoseCorrection(torch.autograd.Function):
     @staticmethod
     def forward(ctx, origins, directions, cam_idx, pose, mode):
-        B = origins.shape[0]
-        M = torch.empty((pose.shape[0], 3, 4), dtype=torch.float32, device=pose.device)
-        call("nvo_pose_exp_map", pose.shape[0], mode, pose, M)
-        Mi = M[cam_idx]
-        o = origins + Mi[:, :, 3]
-        d = torch.bmm(Mi[:, :, :3], directions[..., None]).squeeze(-1)
-        ctx.save_for_backward(directions, cam_idx, pose, Mi)
+        # no materialised zero gradients: under MappingTrainer's gradient sink nothing flows back through autograd, and the engine would
+        # otherwise run this node's backward on zeros
+        ctx.set_materialize_grads(False)
+        o, d = torch.empty_like(origins), torch.empty_like(directions)
+        call("nvo_pose_apply", origins.shape[0], mode, cam_idx, pose, origins, directions, o, d)
+        ctx.save_for_backward(directions, cam_idx, pose)
         ctx.mode = mode
         return o, d
 
     @staticmethod
     def backward(ctx, do, dd):
-        directions, cam_idx, pose, Mi = ctx.saved_tensors
-        K = pose.shape[0]
+        if do is None and dd is None:
+            return None, None, None, None, None
+        directions, cam_idx, pose = ctx.saved_tensors
+        K, B = pose.shape[0], directions.shape[0]
         dpose = torch.zeros_like(pose)
         scratch = torch.zeros((K, 12), dtype=torch.float32, device=pose.device)
-        do, dd = do.contiguous(), dd.contiguous()
-        call("nvo_pose_correction_backward", directions.shape[0], K, ctx.mode, cam_idx, directions, do, dd, pose, scratch, dpose)
-        d_dir = torch.bmm(Mi[:, :, :3].transpose(1, 2), dd[..., None]).squeeze(-1) if ctx.needs_input_grad[1] else None
+        do = torch.zeros_like(directions) if do is None else do.contiguous()
+        dd = torch.zeros_like(directions) if dd is None else dd.contiguous()
+        call("nvo_pose_correction_backward", B, K, ctx.mode, cam_idx, directions, do, dd, pose, scratch, dpose)
+        d_dir = None
+        if ctx.needs_input_grad[1]:  # R^T dd
+            M = torch.empty((K, 3, 4), dtype=torch.float32, device=pose.device)
+            call("nvo_pose_exp_map", K, ctx.mode, pose, M)
+            d_dir = torch.bmm(M[cam_idx][:, :, :3].transpose(1, 2), dd[..., None]).squeeze(-1)
         return (do if ctx.needs_input_grad[0] else None), d_dir, None, dpose, None
 
 

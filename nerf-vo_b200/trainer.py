@@ -222,6 +222,8 @@ class MappingTrainer:
             if self._ray_grads is not None:
                 self._ray_grads.zero_()
         if self.datamanager is not None:
+            if self.cam_group is not None and self.datamanager.camera_optimizer is None:
+                self.datamanager.camera_optimizer = self.model.camera_optimizer  # the step prologue applies the pose correction itself
             # DynamicDataManager.next_train (nerfstudio_utils.py:295-300): pixel draws on the device unless the caller supplies them
             bundle, batch = self.datamanager.next_train(0, u=i["u"] if self.external_draws else None)
             if not self.with_normals:

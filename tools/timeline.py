@@ -13,6 +13,7 @@ from nerf_vo_b200.trainer import MappingTrainer
 ap = argparse.ArgumentParser()
 ap.add_argument("--rays", type=int, default=4096)
 ap.add_argument("--tag", default="step")
+ap.add_argument("--pose", default="SO3xR3")
 a = ap.parse_args()
 world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
 dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
@@ -21,7 +22,7 @@ if world > 1:  # under torchrun: every rank steps (fused exchange), rank 0 write
     import torch.distributed as dist
     dist.init_process_group("nccl", device_id=dev)
 torch.manual_seed(0)
-model = nv.ExtendedNerfactoModel(nv.NerfactoModelConfig(), num_train_data=192).to(dev)
+model = nv.ExtendedNerfactoModel(nv.NerfactoModelConfig(camera_optimizer_mode=a.pose), num_train_data=192).to(dev)
 tr = MappingTrainer(model, num_rays=a.rays)
 rays, targets = synthetic_rays(a.rays, num_images=192, seed=1234 + 1000 * rank)
 jit = synthetic_jitters(a.rays, seed=99 + 1000 * rank)
