@@ -186,6 +186,24 @@ def checkpoint_dict(step: int, model, camera_optimizer=None, trainer=None) -> Di
             group = {"lr": trainer.lr, "betas": tuple(trainer.betas), "eps": trainer.eps, "weight_decay": 0, "amsgrad": False, "maximize": False,
                      "foreach": None, "capturable": False, "differentiable": False, "fused": None, "params": list(range(len(keys)))}
             out["optimizers"][gname] = {"state": state, "param_groups": [group]}
+        if getattr(trainer, "cam_group", None) is not None:
+            # the "camera_opt" group (Adam 1e-4, ExponentialDecayScheduler; nerf_vo/mapping/nerfstudio.py:93-100) and its LambdaLR state
+            import math
+
+            _, off, _ = trainer.cam_group
+            pose = model.camera_optimizer.pose_adjustment
+            t = int(trainer.cam_step)
+            frac = min(max(t / trainer.max_num_iterations, 0.0), 1.0)
+            lr_t = math.exp(math.log(trainer.cam_lr) * (1 - frac) + math.log(trainer.cam_lr_final) * frac)
+            state = {}
+            if t > 0:
+                state[0] = {"step": torch.tensor(float(t)), "exp_avg": exp_avg[off:off + pose.numel()].view(pose.shape).clone().cpu(),
+                            "exp_avg_sq": exp_avg_sq[off:off + pose.numel()].view(pose.shape).clone().cpu()}
+            group = {"lr": lr_t, "initial_lr": trainer.cam_lr, "betas": tuple(trainer.betas), "eps": trainer.eps, "weight_decay": 0, "amsgrad": False,
+                     "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None, "params": [0]}
+            out["optimizers"]["camera_opt"] = {"state": state, "param_groups": [group]}
+            out["schedulers"]["camera_opt"] = {"base_lrs": [trainer.cam_lr], "last_epoch": t, "verbose": False, "_step_count": t + 1,
+                                               "_get_lr_called_within_step": False, "_last_lr": [lr_t], "lr_lambdas": [None]}
     return out
 
 

@@ -5,10 +5,28 @@
 #include "nvo_common.cuh"
 #include "adam.cuh"
 
+// Persistent grid (a few CTAs per SM, grid-stride over float4 items): the Adam constants cost a double-precision pow() per CTA, which a
+// one-item-per-thread launch pays once per WAVE (16 k CTAs = 14 waves of ~3 us of exposed latency each: measured 124 us = 58 % of the HBM
+// peak for the 16.8 M-parameter group); here it is paid once, behind the first batch of loads, and every thread keeps 4 x 4 float4 loads in flight.
+#define ADAM_UNROLL 4
 __global__ void __launch_bounds__(256) k_adam(int64_t n4, int64_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                               float* __restrict__ v, const int* __restrict__ step_ptr, double lr, double b1, double b2, double eps,
                                               float grad_scale, double lr_final, int max_steps) {
     __shared__ AdamC s_c;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // first batch of loads in flight before the constants are needed
+    float4 pp[ADAM_UNROLL], gg[ADAM_UNROLL], mm[ADAM_UNROLL], vv[ADAM_UNROLL];
+#pragma unroll
+    for (int u = 0; u < ADAM_UNROLL; ++u) {
+        const int64_t j = i + u * stride;
+        if (j < n4) {
+            pp[u] = reinterpret_cast<float4*>(p)[j];
+            gg[u] = __ldg(reinterpret_cast<const float4*>(g) + j);
+            mm[u] = reinterpret_cast<float4*>(m)[j];
+            vv[u] = reinterpret_cast<float4*>(v)[j];
+        }
+    }
     if (threadIdx.x == 0) {
         const int done = *step_ptr;  // optimizer steps taken so far == the epoch the LambdaLR scheduler is in
         if (lr_final > 0.0) {
@@ -17,6 +35,63 @@ __global__ void __launch_bounds__(256) k_adam(int64_t n4, int64_t n, float* __re
             lr = exp(log(lr) * (1.0 - t) + log(lr_final) * t);
         }
         s_c = adam_constants(done + 1, lr, b1, b2, eps, grad_scale);
+    }
+    __syncthreads();
+    const AdamC c = s_c;
+    while (i < n4) {
+#pragma unroll
+        for (int u = 0; u < ADAM_UNROLL; ++u) {
+            const int64_t j = i + u * stride;
+            if (j < n4) {
+                adam_update(pp[u].x, mm[u].x, vv[u].x, gg[u].x, c);
+                adam_update(pp[u].y, mm[u].y, vv[u].y, gg[u].y, c);
+                adam_update(pp[u].z, mm[u].z, vv[u].z, gg[u].z, c);
+                adam_update(pp[u].w, mm[u].w, vv[u].w, gg[u].w, c);
+                reinterpret_cast<float4*>(p)[j] = pp[u];
+                reinterpret_cast<float4*>(m)[j] = mm[u];
+                reinterpret_cast<float4*>(v)[j] = vv[u];
+            }
+        }
+        i += ADAM_UNROLL * stride;
+#pragma unroll
+        for (int u = 0; u < ADAM_UNROLL; ++u) {
+            const int64_t j = i + u * stride;
+            if (j < n4) {
+                pp[u] = reinterpret_cast<float4*>(p)[j];
+                gg[u] = __ldg(reinterpret_cast<const float4*>(g) + j);
+                mm[u] = reinterpret_cast<float4*>(m)[j];
+                vv[u] = reinterpret_cast<float4*>(v)[j];
+            }
+        }
+    }
+    // tail (n not a multiple of 4)
+    if (blockIdx.x == 0) {
+        const int64_t j = n4 * 4 + threadIdx.x;
+        if (j < n) {
+            float pj = p[j], mj = m[j], vj = v[j];
+            adam_update(pj, mj, vj, g[j], c);
+            p[j] = pj, m[j] = mj, v[j] = vj;
+        }
+    }
+}
+
+// one float4 per thread, constants evaluated by thread 0 of every CTA (the round-1 kernel; NVO_ADAM_MODE=0) or read from `consts` when
+// a one-thread pre-kernel evaluated them (NVO_ADAM_MODE=2)
+__global__ void __launch_bounds__(256) k_adam_flat(int64_t n4, int64_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, const int* __restrict__ step_ptr, double lr, double b1, double b2, double eps,
+                                                   float grad_scale, double lr_final, int max_steps, const AdamC* __restrict__ consts) {
+    __shared__ AdamC s_c;
+    if (threadIdx.x == 0) {
+        if (consts) {
+            s_c = *consts;
+        } else {
+            const int done = *step_ptr;
+            if (lr_final > 0.0) {
+                const double t = fmin(fmax((double)done / (double)max_steps, 0.0), 1.0);
+                lr = exp(log(lr) * (1.0 - t) + log(lr_final) * t);
+            }
+            s_c = adam_constants(done + 1, lr, b1, b2, eps, grad_scale);
+        }
     }
     __syncthreads();
     const AdamC c = s_c;
@@ -34,7 +109,6 @@ __global__ void __launch_bounds__(256) k_adam(int64_t n4, int64_t n, float* __re
         reinterpret_cast<float4*>(m)[i] = mm;
         reinterpret_cast<float4*>(v)[i] = vv;
     }
-    // tail (n not a multiple of 4)
     if (blockIdx.x == 0) {
         const int64_t j = n4 * 4 + threadIdx.x;
         if (j < n) {
@@ -43,6 +117,16 @@ __global__ void __launch_bounds__(256) k_adam(int64_t n4, int64_t n, float* __re
             p[j] = pj, m[j] = mj, v[j] = vj;
         }
     }
+}
+__device__ AdamC g_adam_consts[64];
+__global__ void k_adam_consts(const int* __restrict__ step_ptr, double lr, double b1, double b2, double eps, float grad_scale, double lr_final, int max_steps,
+                              AdamC* __restrict__ out) {
+    const int done = *step_ptr;
+    if (lr_final > 0.0) {
+        const double t = fmin(fmax((double)done / (double)max_steps, 0.0), 1.0);
+        lr = exp(log(lr) * (1.0 - t) + log(lr_final) * t);
+    }
+    *out = adam_constants(done + 1, lr, b1, b2, eps, grad_scale);
 }
 
 __global__ void k_tick(int* step) { *step += 1; }
@@ -59,8 +143,28 @@ static int adam_step_impl(void* stream, int64_t n, float* params, const float* g
     // largest shared-memory carve-out: kernels with dynamic shared memory (proposal backward) can then share an SM with this one
     // (the L1 / shared split of an SM cannot change while CTAs are resident); Adam streams and has no use for L1
     cudaFuncSetAttribute(k_adam, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    k_adam<<<nvo_blocks(n4 > 0 ? n4 : 1, 256), 256, 0, st>>>(n4, n, params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, grad_scale, lr_final,
-                                                             max_steps);
+    static const int mode = nvo_env_int("NVO_ADAM_MODE", 2);  // 0: constants per CTA, 1: persistent grid, 2: pre-kernel constants (default)
+    if (mode == 1) {
+        const int64_t want = (n4 + 256 * ADAM_UNROLL - 1) / (256 * ADAM_UNROLL);
+        const unsigned int grid = (unsigned int)max((int64_t)1, min((int64_t)nvo_sm_count() * 2, want));
+        k_adam<<<grid, 256, 0, st>>>(n4, n, params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, grad_scale, lr_final, max_steps);
+    } else {
+        // the constants (a double-precision pow per launch) come from a one-thread pre-kernel: evaluated by thread 0 of every CTA they cost
+        // every WAVE of the 16 k-CTA launch a few microseconds of exposed latency (measured: step 0.812 -> 0.800 ms).  64 device slots used
+        // round-robin, so launches in flight on different streams (the two parameter groups) never share one.
+        AdamC* consts = nullptr;
+        if (mode == 2) {
+            static int next = 0;
+            AdamC* slots = nullptr;
+            cudaGetSymbolAddress((void**)&slots, g_adam_consts);
+            consts = slots + (next++ & 63);
+            k_adam_consts<<<1, 1, 0, st>>>(step, lr, beta1, beta2, eps, grad_scale, lr_final, max_steps, consts);
+            NVO_CUDA_LAUNCH_CHECK("adam_step(consts)");
+        }
+        cudaFuncSetAttribute(k_adam_flat, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        k_adam_flat<<<nvo_blocks(n4 > 0 ? n4 : 1, 256), 256, 0, st>>>(n4, n, params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, grad_scale,
+                                                                      lr_final, max_steps, consts);
+    }
     NVO_CUDA_LAUNCH_CHECK("adam_step");
     k_tick<<<1, 1, 0, st>>>(step);
     NVO_CUDA_LAUNCH_CHECK("adam_step(tick)");

@@ -487,7 +487,11 @@ class MappingTrainer:
 
         W = self.world_size
         outs = [torch.zeros(self.flat.numel(), dtype=torch.float32, device=self.device) for _ in range(2)]
-        for gid, (_, off, n) in zip(self._peer_groups, self.groups):
+        gids, groups = list(self._peer_groups), list(self.groups)
+        if self._peer_cam is not None:
+            gids.append(self._peer_cam)
+            groups.append(self.cam_group)
+        for gid, (_, off, n) in zip(gids, groups):
             chunk = slice_range(n, 0, W)[1]
             for j, t in enumerate(self.peer.group_moments(gid)):
                 full = torch.empty(chunk * W, dtype=torch.float32, device=self.device)
@@ -503,7 +507,11 @@ class MappingTrainer:
             return
         from .peer import slice_range
 
-        for gid, (_, off, n) in zip(self._peer_groups, self.groups):
+        gids, groups = list(self._peer_groups), list(self.groups)
+        if self._peer_cam is not None:
+            gids.append(self._peer_cam)
+            groups.append(self.cam_group)
+        for gid, (_, off, n) in zip(gids, groups):
             lo, hi = slice_range(n, self.peer.rank, self.world_size)
             for t, src in zip(self.peer.group_moments(gid), (exp_avg, exp_avg_sq)):
                 t[:hi - lo].copy_(src[off + lo:off + hi])
