@@ -533,14 +533,50 @@ def measure_roofline(torch, nv, model, trainer, dev, B):
     extras.append({"kernel": f"k_adam (fields group, {n_par / 1e6:.1f} M parameters)", "bound": "hbm", "launch_us": us, "achieved": 28 * n_par / us / 1e3, "peak": peak,
                    "unit": "GB/s", "frac": 28 * n_par / us / 1e3 / peak, "algorithmic_bytes_per_param": 28})
     del p2, m2, v2, g2
-    extras.extend(field_mlp_roofline(torch, nv, model.field, N, dev, timed_us, tpeak, tpeak_src))
+    extras.extend(field_mlp_roofline(torch, nv, model.field, N, dev, timed_us, tpeak, tpeak_src, x=x, S=model.config.num_nerf_samples_per_ray))
     roofline["others"] = extras
     return roofline
 
 
-def field_mlp_roofline(torch, nv, fld, N, dev, timed_us, tpeak, tpeak_src):
-    """The field networks' tensor-core kernels on N samples against the dense fp16/bf16 tensor peak (SURVEY 8d FLOP counts, unpadded)."""
+def field_mlp_roofline(torch, nv, fld, N, dev, timed_us, tpeak, tpeak_src, x=None, S=48):
+    """The field networks' tensor-core kernels on N samples against the dense fp16/bf16 tensor peak (SURVEY 8d FLOP counts, unpadded).
+    First the two fused launches the mapping step runs (csrc/field_tc.cu: mlp_base + normals chain + assembly + mlp_head + mlp_pred_normals
+    forward; mlp_head + assembly + mlp_base backward with dgrad and wgrad), then the per-network kernels behind the tcnn-style modules."""
     out = []
+    ops = nv.ops
+    if x is not None and N % S == 0:
+        B = N // S
+        enc = fld.mlp_base.encoder
+        flat = lambda ps: ops._flat_of([p.detach() for p in ps])
+        with torch.no_grad():
+            feat16, jac = ops.grid_forward_jac(x, enc.hash_table.detach(), enc.spec)
+            pn_params = fld.mlp_pred_normals._flat_param_list() + [fld.field_head_pred_normals.net.weight, fld.field_head_pred_normals.net.bias]
+            img = ops.field_pack_weights(enc.spec, flat(fld.mlp_base.mlp._flat_param_list()), flat(fld.mlp_head._flat_param_list()), flat(pn_params))
+            g = torch.Generator(device=dev).manual_seed(5)
+            dirs = torch.nn.functional.normalize(torch.randn(B, 3, device=dev, generator=g), dim=-1)
+            pos = (x * 4 - 2).contiguous()
+            cam = torch.zeros(B, dtype=torch.int64, device=dev)
+            emb = fld.embedding_appearance.embedding.weight.detach()
+            sel = torch.ones(N, device=dev)
+            fwd = lambda: ops.field_forward(feat16, jac, pos, dirs, cam, emb, sel, img, B, S, True, True)
+            density, rgb, pn, normals, h0, pn_raw, saved = fwd()
+            us_f = timed_us(fwd)
+            dbase = torch.zeros(sum(p.numel() for p in fld.mlp_base.mlp._flat_param_list()), device=dev)
+            dhead = torch.zeros(sum(p.numel() for p in fld.mlp_head._flat_param_list()), device=dev)
+            demb = torch.zeros_like(emb)
+            dden = torch.randn(N, device=dev, generator=g) * 1e-3
+            drgb = torch.randn(N, 3, device=dev, generator=g) * 1e-3
+            us_b = timed_us(lambda: ops.field_backward(feat16, saved, False, img, rgb, h0, sel, cam, dden, drgb, None, B, S, dbase, dhead, demb))
+        # forward: the three networks (43 008 FLOP) + the normals chain's input-gradient product (2 x 64 x 32); backward: dgrad + wgrad of
+        # mlp_head and mlp_base = 2 x (16 640 + 6 144) (mlp_pred_normals receives no gradient in NeRF-VO: pred_normal_loss_mult = 0)
+        for tag, t_us, fl, note in (("k_field_fwd (mlp_base + normals chain + assembly + mlp_head + mlp_pred_normals, activations saved)", us_f, 43008 + 4096,
+                                     "HBM per sample: 64 B features + 192 B feature derivatives read, 512 B activations + 44 B outputs written"),
+                                    ("k_field_bwd (mlp_head + assembly + mlp_base: dgrad + wgrad)", us_b, 2 * (16640 + 6144),
+                                     "HBM per sample: 512 B saved activations + 64 B features read, 128 B fp32 feature gradient written")):
+            tf = fl * N / t_us / 1e6
+            out.append({"kernel": tag, "bound": "tensor", "launch_us": t_us, "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+                        "flop_per_sample": fl, "peak_source": tpeak_src, "note": note})
+        del feat16, jac, saved
     nets = {"mlp_base 32-64-16": (fld.mlp_base.mlp.spec, fld.mlp_base.mlp._flat_param_list(), 6144),
             "mlp_head 63-64-64-3": (fld.mlp_head.spec, fld.mlp_head._flat_param_list(), 16640)}
     for name, (spec, params, flop) in nets.items():
@@ -555,8 +591,8 @@ def field_mlp_roofline(torch, nv, fld, N, dev, timed_us, tpeak, tpeak_src):
             us_b = timed_us(lambda: nv.ops.mlp_tc_backward(x16, wimg, saved, y, dy, spec, True, True, dflat, dy_absmax=8.0))
         for tag, t_us, fl in (("fwd", us_f, flop), ("bwd (dgrad + wgrad)", us_b, 2 * flop)):
             tf = fl * N / t_us / 1e6
-            out.append({"kernel": f"k_mlp_tc_{tag}: {name}", "bound": "tensor", "launch_us": t_us, "achieved": tf, "peak": tpeak, "unit": "TFLOP/s",
-                        "frac": tf / tpeak, "flop_per_sample": fl, "peak_source": tpeak_src})
+            out.append({"kernel": f"k_mlp_tc_{tag}: {name} (per-network kernel behind tcnn_api.Network; not in the fused step)", "bound": "tensor", "launch_us": t_us,
+                        "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak, "flop_per_sample": fl, "peak_source": tpeak_src})
     return out
 
 

@@ -345,6 +345,13 @@ int nvo_frame_finalize(void* stream, int64_t n, const float* rgb, const float* d
 /* sums[3] (double, accumulate; caller zero-fills) += { sum depth_gt, sum depth_pred, count } over pixels with
  * 0 < depth_gt < 5 and 0 < depth_pred < 5 (evaluation/renderer.py:88-93: the per-keyframe depth-scale alignment). */
 int nvo_depth_scale_sums(void* stream, int64_t n, const float* depth_gt, const float* depth_pred, void* sums);
+/* Point-cloud export for Poisson meshing (evaluation/nerf_renderer.py:170-209 calling NS/exporter/exporter_utils.py:78-231, lines 130-180 and
+ * 222-226): points[n,3] = origins + directions * depth; keep[n] (uint8) = accumulation > 0.5 and, when box_min / box_max (HOST float[3],
+ * both or neither) are given, box_min < point < box_max on every axis; normals[n,3] = normals_coded * 2 - 1 (nullable pair), negated where
+ * reorient != 0 and dot(direction, normal) > 0.  The caller compacts by `keep`. */
+int nvo_point_cloud(void* stream, int64_t n, const float* origins, const float* directions, const float* depth, const float* accumulation,
+                    const float* normals_coded, const float* box_min, const float* box_max, int32_t reorient, float* points, float* normals,
+                    void* keep);
 
 /* ---------------------------------------------------------------------------------------------
  * The nerfacto field's three networks as ONE persistent tcgen05 kernel per direction (csrc/field_tc.cu): NerfactoField.get_density's

@@ -3,6 +3,7 @@ API (tinycudann modules; nerfstudio fields / samplers / renderers / losses).  Se
 from . import _lib, ops, sharding  # noqa: F401
 from . import tcnn_api  # noqa: F401
 from . import checkpoint  # noqa: F401
+from . import exporter  # noqa: F401
 from .data import (CameraOptimizer, CameraOptimizerConfig, Cameras, DynamicDataManager, DynamicDataManagerConfig, DynamicDataset, PixelSampler,  # noqa: F401
                    PixelSamplerConfig, RayGenerator)
 from .field_components import MLP, Embedding, HashEncoding, MLPWithHashEncoding, NeRFEncoding, SceneContraction, SHEncoding, trunc_exp  # noqa: F401

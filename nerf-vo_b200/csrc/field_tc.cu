@@ -690,6 +690,7 @@ struct FieldBwdP {
     float* demb;                  // [K,32] (cam != null) or [32], accumulated; nullable
     const float* dirs;            // [B,3] ray directions (with ddirs)
     float* ddirs;                 // [B,3] d loss / d ray direction through the SH encoding, accumulated (atomics); nullable
+    int l2_prefetch;              // prefetch the next tile's saved activations into L2 (NVO_FIELD_BWD_PREFETCH, default 1)
 };
 
 __device__ __forceinline__ float ft_grad_scale(float mx) {
@@ -780,6 +781,64 @@ __device__ __forceinline__ void warp_transpose_reduce32(float* e, int lane) {
     }
 }
 
+// The backward's MMA issue with every operand address derived from the CTA's shared-memory base + compile-time constants (group, slot and
+// step are template / switch constants, TMEM base 0): descriptors stay in uniform registers, one add each.  With run-time addresses ptxas
+// wraps every tcgen05.mma of the single issuing thread in an elect / R2UR.BROADCAST loop behind a shift / mask chain (~110 cycles per MMA
+// against the pipe's 32-46), and that one thread issues the 54 MMAs per tile of all groups: it was the CTA's serial bottleneck.
+__device__ __forceinline__ void issue_wgrad_rel(uint32_t tmem_d, uint32_t base16, uint32_t act_off, uint32_t dz_off, int N, uint32_t accumulate) {
+    const uint32_t idesc = umma_idesc(TM, N, 1, 1);
+#pragma unroll
+    for (int k = 0; k < TM / 16; ++k)
+        umma_f16(tmem_d, umma_desc_rel(base16, act_off + k * 256, 128, CHUNK_B), umma_desc_rel(base16, dz_off + k * 256, 128, CHUNK_B), idesc, k > 0 ? 1u : accumulate);
+}
+#define BW_MBAR_OFF(G) (BW_GROUPS_OFF + ((G) * BW_GROUP_CHUNKS + 2) * CHUNK_B)
+template <int G, int GI, int SL>
+__device__ __forceinline__ void fb_issue(int ts, uint32_t uBase, uint32_t started, int lane) {
+    const uint32_t b16 = (uBase & 0x3FFFFu) >> 4;
+    constexpr uint32_t oG = BW_GROUPS_OFF + GI * BW_GROUP_CHUNKS * CHUNK_B, oSlot = oG + SL * BW_SLOT_CHUNKS * CHUNK_B;
+    constexpr uint32_t oG64 = oG + 2 * BW_SLOT_CHUNKS * CHUNK_B, oG16 = oG64 + 8 * CHUNK_B;
+    constexpr uint32_t acc = DW_ACC + 64 * GI;
+    // `ts` is warp-uniform: a uniform switch, then lane 0 alone issues the step's MMAs and the commit
+    switch (ts) {
+        case 0:  // head layer 2: dA2 = dz3 W2 ; dW2^T += AH2_ext^T dz3
+            if (lane == 0) {
+                issue_layer_rel(acc, b16, oG16, 1, FB_H2T, 64, false);
+                issue_wgrad_rel(DW_H2T, b16, oSlot, oG16, 16, started);
+                umma_commit_u32(uBase + BW_MBAR_OFF(G) + 8 * (1 + G + GI));
+            }
+            break;
+        case 1:  // head layer 1
+            if (lane == 0) {
+                issue_layer_rel(acc, b16, oG64, 4, FB_H1T, 64, false);
+                issue_wgrad_rel(DW_H1T, b16, oSlot, oG64, 64, started);
+                umma_commit_u32(uBase + BW_MBAR_OFF(G) + 8 * (1 + G + GI));
+            }
+            break;
+        case 2:  // head layer 0: dX ; dW0^T += X^T dZ1 (the bias is X's constant column 63)
+            if (lane == 0) {
+                issue_layer_rel(acc, b16, oG64, 4, FB_H0T, 64, false);
+                issue_wgrad_rel(DW_H0T, b16, oSlot, oG64, 64, started);
+                umma_commit_u32(uBase + BW_MBAR_OFF(G) + 8 * (1 + G + GI));
+            }
+            break;
+        case 3:  // base layer 1
+            if (lane == 0) {
+                issue_layer_rel(acc, b16, oG16, 1, FB_B1T, 64, false);
+                issue_wgrad_rel(DW_B1T, b16, oSlot, oG16, 16, started);
+                umma_commit_u32(uBase + BW_MBAR_OFF(G) + 8 * (1 + G + GI));
+            }
+            break;
+        default:  // base layer 0: d features (32 columns); the feature tile sits in the slot's upper half
+            if (lane == 0) {
+                issue_layer_rel(acc, b16, oG64, 4, FB_B0T, 32, false);
+                issue_wgrad_rel(DW_B0T, b16, oSlot + 4 * CHUNK_B, oG64, 64, started);
+                umma_commit_u32(uBase + BW_MBAR_OFF(G) + 8 * (1 + G + GI));
+            }
+            break;
+    }
+    __syncwarp();
+}
+
 template <int G>
 __global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __grid_constant__ FieldBwdP p) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -789,7 +848,8 @@ __global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __gri
     const int tid = threadIdx.x & 255, warp = tid >> 5, hf = warp >> 2, lane = threadIdx.x & 31;
     const int r = ((warp & 3) << 5) | lane;
     unsigned char* sW = smem;
-    uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + BW_GROUPS_OFF + (G * BW_GROUP_CHUNKS + 2) * CHUNK_B);
+    const uint32_t uBase = smem_u32(smem);  // defined in converged code: the issuer's descriptors derive from it in uniform registers
+    uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + BW_MBAR_OFF(G));
     uint64_t* mbar_w = mbars;                 // weights landed
     uint64_t* mbar_ready = mbars + 1;         // [G] operands of the group's next step are in shared memory (8 warp arrivals)
     uint64_t* mbar_done = mbars + 1 + G;      // [G] the step's MMAs have retired (tcgen05.commit)
@@ -828,90 +888,91 @@ __global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem0 = *tmem_ptr;
+    if (tmem0 != 0u) __trap();  // all 512 columns: the allocation can only start at column 0 (fb_issue relies on it)
     const float mx_h = __ldg(p.absmax), mx_d = __ldg(p.absmax + 1);
     const float s_h = ft_grad_scale(mx_h), s_b = ft_grad_scale(fmaxf(mx_d, 4.f * mx_h));
     const float inv_s_h = 1.f / s_h, inv_s_b = 1.f / s_b, s_bh = s_b * inv_s_h;
 
     if (is_issuer_warp) {
-        // ============================================ MMA issuer + loader (one thread) ============================================
+        // ===================================== MMA issuer + loader (one warp, lane 0 acts) =====================================
+        // The whole warp walks the polling loop with warp-uniform state (the mbarrier tests are combined with a vote), so the step's descriptor
+        // arithmetic lives in uniform registers; the single-thread actions — bulk copies, tcgen05.mma, tcgen05.commit — are lane 0's.
         if (lane == 0) {
             mbar_expect_tx(mbar_w, FB_BYTES);
             bulk_g2s(sW, p.wimg + FB_OFF, FB_BYTES, mbar_w);
-            int64_t total_q[G];
-            int q[G];
-            uint32_t rph[G], lph[G][2];
-            int dw_started = 0;  // bit l: layer l's weight-gradient accumulator has been written once
-            int active = 0;
-            auto load = [&](int gg, int qq) {
-                const int ts = qq % 5;
-                const int64_t tile = (int64_t)blockIdx.x * G + gg + (int64_t)(qq / 5) * stride;
-                unsigned char* slot = smem + BW_GROUPS_OFF + gg * BW_GROUP_CHUNKS * CHUNK_B + (qq & 1) * BW_SLOT_CHUNKS * CHUNK_B;
-                uint64_t* mb = mbar_load + 2 * gg + (qq & 1);
-                const unsigned char* sv = p.saved + tile * saved_tile_bytes;
-                if (ts == 4) {  // base layer 0's input: the hash features (4 chunks), placed so that the ones chunk follows them
-                    mbar_expect_tx(mb, 4 * CHUNK_B);
-                    bulk_g2s(slot + 4 * CHUNK_B, p.feat16 + tile * (4 * CHUNK_B), 4 * CHUNK_B, mb);
-                } else {
-                    const int ch = ts == 0 ? FS_AH2 : ts == 1 ? FS_AH1 : ts == 2 ? FS_X : FS_H1;
-                    mbar_expect_tx(mb, 8 * CHUNK_B);
-                    bulk_g2s(slot, sv + ch * CHUNK_B, 8 * CHUNK_B, mb);
-                }
-            };
+        }
+        int64_t total_q[G];
+        int q[G];
+        uint32_t rph[G], lph[G][2];
+        int dw_started = 0;  // bit l: layer l's weight-gradient accumulator has been written once
+        int active = 0;
+        const bool l2_prefetch = p.l2_prefetch != 0;
+        auto load = [&](int gg, int qq) {  // lane 0 only
+            const int ts = qq % 5;
+            const int64_t tile = (int64_t)blockIdx.x * G + gg + (int64_t)(qq / 5) * stride;
+            unsigned char* slot = smem + BW_GROUPS_OFF + gg * BW_GROUP_CHUNKS * CHUNK_B + (qq & 1) * BW_SLOT_CHUNKS * CHUNK_B;
+            uint64_t* mb = mbar_load + 2 * gg + (qq & 1);
+            const unsigned char* sv = p.saved + tile * saved_tile_bytes;
+            if (ts == 0 && tile + stride < n_tiles && l2_prefetch) {
+                // the group's NEXT tile (five steps ahead): its 64 KB of saved activations and 8 KB of features start towards L2 now, so the
+                // just-in-time slot copies below find them there instead of waiting on HBM inside the step chain
+                bulk_prefetch_l2(p.saved + (tile + stride) * saved_tile_bytes, FS_CHUNKS_HEAD * CHUNK_B);
+                bulk_prefetch_l2(p.feat16 + (tile + stride) * (4 * CHUNK_B), 4 * CHUNK_B);
+            }
+            if (ts == 4) {  // base layer 0's input: the hash features (4 chunks), placed so that the ones chunk follows them
+                mbar_expect_tx(mb, 4 * CHUNK_B);
+                bulk_g2s(slot + 4 * CHUNK_B, p.feat16 + tile * (4 * CHUNK_B), 4 * CHUNK_B, mb);
+            } else {
+                const int ch = ts == 0 ? FS_AH2 : ts == 1 ? FS_AH1 : ts == 2 ? FS_X : FS_H1;
+                mbar_expect_tx(mb, 8 * CHUNK_B);
+                bulk_g2s(slot, sv + ch * CHUNK_B, 8 * CHUNK_B, mb);
+            }
+        };
 #pragma unroll
-            for (int gg = 0; gg < G; ++gg) {
-                const int64_t first = (int64_t)blockIdx.x * G + gg;
-                const int64_t tiles_g = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
-                total_q[gg] = tiles_g * 5;
-                q[gg] = 0, rph[gg] = 0, lph[gg][0] = lph[gg][1] = 0;
-                if (tiles_g > 0) {
-                    active |= 1 << gg;
+        for (int gg = 0; gg < G; ++gg) {
+            const int64_t first = (int64_t)blockIdx.x * G + gg;
+            const int64_t tiles_g = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+            total_q[gg] = tiles_g * 5;
+            q[gg] = 0, rph[gg] = 0, lph[gg][0] = lph[gg][1] = 0;
+            if (tiles_g > 0) {
+                active |= 1 << gg;
+                if (lane == 0) {
                     load(gg, 0);
                     load(gg, 1);
                 }
             }
-            mbar_wait(mbar_w, 0);
-            const uint32_t uW = smem_u32(sW);
-            while (active) {
+        }
+        mbar_wait(mbar_w, 0);
+        while (active) {
 #pragma unroll
-                for (int gg = 0; gg < G; ++gg) {
-                    if (!((active >> gg) & 1)) continue;
-                    const int qq = q[gg], sl = qq & 1;
-                    if (!mbar_test(mbar_ready + gg, rph[gg]) || !mbar_test(mbar_load + 2 * gg + sl, lph[gg][sl])) continue;
-                    rph[gg] ^= 1, lph[gg][sl] ^= 1;
-                    if (qq >= 1 && qq + 1 < total_q[gg]) load(gg, qq + 1);  // slot (qq+1)&1: its readers (step qq-1) are finished
-                    tc_fence_after();
-                    const uint32_t uG = smem_u32(smem + BW_GROUPS_OFF + gg * BW_GROUP_CHUNKS * CHUNK_B);
-                    const uint32_t uSlot = uG + sl * BW_SLOT_CHUNKS * CHUNK_B, uG64 = uG + 2 * BW_SLOT_CHUNKS * CHUNK_B, uG16 = uG64 + 8 * CHUNK_B;
-                    const uint32_t acc = tmem0 + DW_ACC + 64 * gg;
-                    const int ts = qq % 5;
-                    const uint32_t started = (dw_started >> ts) & 1;
-                    switch (ts) {
-                        case 0:  // head layer 2: dA2 = dz3 W2 ; dW2^T += AH2_ext^T dz3
-                            issue_layer(acc, uG16, 1, uW + FB_H2T, 64, false, 0);
-                            issue_wgrad(tmem0 + DW_H2T, uSlot, uG16, 16, started);
-                            break;
-                        case 1:  // head layer 1
-                            issue_layer(acc, uG64, 4, uW + FB_H1T, 64, false, 0);
-                            issue_wgrad(tmem0 + DW_H1T, uSlot, uG64, 64, started);
-                            break;
-                        case 2:  // head layer 0: dX ; dW0^T += X^T dZ1 (the bias is X's constant column 63)
-                            issue_layer(acc, uG64, 4, uW + FB_H0T, 64, false, 0);
-                            issue_wgrad(tmem0 + DW_H0T, uSlot, uG64, 64, started);
-                            break;
-                        case 3:  // base layer 1
-                            issue_layer(acc, uG16, 1, uW + FB_B1T, 64, false, 0);
-                            issue_wgrad(tmem0 + DW_B1T, uSlot, uG16, 16, started);
-                            break;
-                        default:  // base layer 0: d features (32 columns); the feature tile sits in the slot's upper half
-                            issue_layer(acc, uG64, 4, uW + FB_B0T, 32, false, 0);
-                            issue_wgrad(tmem0 + DW_B0T, uSlot + 4 * CHUNK_B, uG64, 64, started);
-                            break;
-                    }
-                    dw_started |= 1 << ts;
-                    umma_commit(mbar_done + gg);
-                    q[gg] = qq + 1;
-                    if (qq + 1 == total_q[gg]) active &= ~(1 << gg);
-                }
+            for (int gg = 0; gg < G; ++gg) {
+                if (!((active >> gg) & 1)) continue;
+                const int qq = q[gg], sl = qq & 1;
+                // every lane tests; the vote makes the decision (and everything derived from it) warp-uniform
+                const bool go = mbar_test(mbar_ready + gg, rph[gg]) && mbar_test(mbar_load + 2 * gg + sl, lph[gg][sl]);
+                if (!__all_sync(0xffffffffu, go)) continue;
+                rph[gg] ^= 1, lph[gg][sl] ^= 1;
+                if (lane == 0 && qq >= 1 && qq + 1 < total_q[gg]) load(gg, qq + 1);  // slot (qq+1)&1: its readers (step qq-1) are finished
+                tc_fence_after();
+                const int ts = qq % 5;
+                const uint32_t started = (dw_started >> ts) & 1;
+#define FB_ISSUE(GI)                                        \
+    do {                                                    \
+        if (sl)                                             \
+            fb_issue<G, GI, 1>(ts, uBase, started, lane);   \
+        else                                                \
+            fb_issue<G, GI, 0>(ts, uBase, started, lane);   \
+    } while (0)
+                if (gg == 0)
+                    FB_ISSUE(0);
+                else if (G > 1 && gg == 1)
+                    FB_ISSUE((G > 1 ? 1 : 0));
+                else if (G > 2)
+                    FB_ISSUE((G > 2 ? 2 : 0));
+#undef FB_ISSUE
+                dw_started |= 1 << ts;
+                q[gg] = qq + 1;
+                if (qq + 1 == total_q[gg]) active &= ~(1 << gg);
             }
         }
         __syncwarp();
@@ -1152,6 +1213,8 @@ extern "C" int nvo_field_backward(void* stream, int64_t B, int32_t S, const void
     p.absmax = scratch, p.dfeat = dfeat, p.dbase = dbase_params, p.dhead = dhead_params, p.demb = dembedding;
     NVO_CHECK(!ddirections || directions, "field_backward: directions required for their gradient");
     p.dirs = directions, p.ddirs = ddirections;
+    static const int l2_prefetch = nvo_env_int("NVO_FIELD_BWD_PREFETCH", 1);
+    p.l2_prefetch = l2_prefetch;
     const int G = field_groups();
     const size_t smem = BW_GROUPS_OFF + (size_t)(G * BW_GROUP_CHUNKS + 2) * CHUNK_B + 8 * (1 + 4 * G) + 16;
     const int64_t tiles = (n + TM - 1) / TM;

@@ -68,6 +68,39 @@ __global__ void __launch_bounds__(256) k_depth_scale_sums(int64_t n, const float
     }
 }
 
+// Point-cloud export (evaluation/nerf_renderer.py:170-209 -> NS/exporter/exporter_utils.py:130-180): per ray the surface point
+// origin + direction * depth, the opacity (> 0.5) and axis-aligned box tests, the decoded normal n * 2 - 1 and its re-orientation against
+// the view direction (exporter_utils.py:222-226: flipped where dot(view, n) > 0).  keep[i] = 1 for the rays the reference's two masks keep.
+__global__ void __launch_bounds__(256) k_point_cloud(int64_t n, const float* __restrict__ origins, const float* __restrict__ directions,
+                                                     const float* __restrict__ depth, const float* __restrict__ accumulation,
+                                                     const float* __restrict__ normals_coded, float3 lo, float3 hi, int use_box, int reorient,
+                                                     float* __restrict__ points, float* __restrict__ normals, uint8_t* __restrict__ keep) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float d = __ldg(depth + i);
+    float pt[3], v[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        v[a] = __ldg(directions + 3 * i + a);
+        pt[a] = __fadd_rn(__ldg(origins + 3 * i + a), __fmul_rn(v[a], d));  // torch: origins + directions * depth
+        points[3 * i + a] = pt[a];
+    }
+    bool k = __ldg(accumulation + i) > 0.5f;
+    if (use_box) k = k && pt[0] > lo.x && pt[1] > lo.y && pt[2] > lo.z && pt[0] < hi.x && pt[1] < hi.y && pt[2] < hi.z;
+    keep[i] = k ? 1 : 0;
+    if (normals_coded) {
+        float nn[3], dot = 0.f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            nn[a] = __fsub_rn(__fmul_rn(__ldg(normals_coded + 3 * i + a), 2.f), 1.f);
+            dot = __fadd_rn(dot, __fmul_rn(v[a], nn[a]));
+        }
+        const float sgn = (reorient && dot > 0.f) ? -1.f : 1.f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) normals[3 * i + a] = nn[a] * sgn;
+    }
+}
+
 }  // namespace
 
 extern "C" int nvo_frame_finalize(void* stream, int64_t n, const float* rgb, const float* depth, const float* directions_norm, float scale_a, float scale_b,
@@ -92,5 +125,25 @@ extern "C" int nvo_depth_scale_sums(void* stream, int64_t n, const float* depth_
     const unsigned blocks = (unsigned)(want < 4 * nvo_sm_count() ? want : 4 * nvo_sm_count());
     k_depth_scale_sums<<<blocks, 256, 0, (cudaStream_t)stream>>>(n, depth_gt, depth_pred, (double*)sums);
     NVO_CUDA_LAUNCH_CHECK("k_depth_scale_sums");
+    return 0;
+}
+
+extern "C" int nvo_point_cloud(void* stream, int64_t n, const float* origins, const float* directions, const float* depth, const float* accumulation,
+                               const float* normals_coded, const float* box_min, const float* box_max, int32_t reorient, float* points, float* normals,
+                               void* keep) {
+    NVO_CHECK(n >= 0, "nvo_point_cloud: negative n");
+    if (n == 0) return 0;
+    NVO_CHECK(origins && directions && depth && accumulation && points && keep, "nvo_point_cloud: null pointer");
+    NVO_CHECK(!normals_coded || normals, "nvo_point_cloud: normals output missing");
+    NVO_CHECK((box_min == nullptr) == (box_max == nullptr), "nvo_point_cloud: box_min and box_max go together");
+    float3 lo = make_float3(0.f, 0.f, 0.f), hi = lo;
+    if (box_min) {  // HOST pointers: three floats each
+        lo = make_float3(box_min[0], box_min[1], box_min[2]);
+        hi = make_float3(box_max[0], box_max[1], box_max[2]);
+        NVO_CHECK(lo.x < hi.x && lo.y < hi.y && lo.z < hi.z, "nvo_point_cloud: bounding box min must be smaller than max");
+    }
+    k_point_cloud<<<nvo_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(n, origins, directions, depth, accumulation, normals_coded, lo, hi, box_min != nullptr,
+                                                                       reorient, points, normals, (uint8_t*)keep);
+    NVO_CUDA_LAUNCH_CHECK("k_point_cloud");
     return 0;
 }

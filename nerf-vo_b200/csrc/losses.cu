@@ -360,6 +360,123 @@ struct StepLossP {
     float* d_normals;          // [B,3] written, or null
 };
 
+// One proposal level's interlevel + depth terms for one ray, by one warp — the lane-blocked variant: lane j owns the C CONSECUTIVE samples
+// [C j, C j + C) (C = ceil(S_l / 32)), so the weight cumsum and the gradient's suffix sum are C serial adds + ONE warp scan of the lane totals
+// instead of one warp scan per 32-sample chunk (8 dependent shuffle chains at 256 samples), the depth term's expf / logf run as C independent
+// chains per lane, and the two bin searches of a query advance in the same loop.  Same terms as the chunked path below; the cumsum is
+// still accumulated in double and rounded to fp32 per entry.  Shared rows indexed by sample are padded (PI) so that the lane-blocked
+// accesses of an even C hit 32 different banks.
+template <int C>
+__device__ __forceinline__ int sl_pi(int i) { return (C % 2 == 0) ? i + i / C : i; }
+template <int C>
+__device__ __forceinline__ void sl_level_fast(const StepLossP& p, const int l, const int64_t r, const int lane, const float* __restrict__ wf, const float* __restrict__ cf,
+                                              float* __restrict__ cy1, float* __restrict__ cps, float* __restrict__ E, const float D, const bool use_depth,
+                                              const bool dmask, const float two_sigma, const float g_depth, const float B_f, float& t_inter, float& t_depth) {
+    const int Sp = p.S[l], np = Sp + 1, S = p.S[2];
+    const float* wp = p.w[l] + r * Sp;
+    const int j0 = C * lane;
+    float v[C];
+    if (C % 4 == 0 && j0 + C <= Sp && (reinterpret_cast<uintptr_t>(wp) & 15) == 0) {
+#pragma unroll
+        for (int k = 0; k < C; k += 4) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(wp + j0 + k));
+            v[k] = q.x, v[k + 1] = q.y, v[k + 2] = q.z, v[k + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < C; ++k) v[k] = j0 + k < Sp ? __ldg(wp + j0 + k) : 0.f;
+    }
+    // interval geometry of the lane's samples (depth term): requested now, consumed at the end
+    float s0[C], s1[C];
+    if (use_depth) {
+        const float* st = p.starts[l] + r * p.stride[l];
+        const float* en = p.ends[l] + r * p.stride[l];
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const bool in = j0 + k < Sp;
+            s0[k] = in ? __ldg(st + j0 + k) : 0.f;
+            s1[k] = in ? __ldg(en + j0 + k) : 0.f;
+        }
+    }
+    double loc[C], s = 0.0;
+#pragma unroll
+    for (int k = 0; k < C; ++k) s += (double)v[k], loc[k] = s;
+    const double incl = nvo_warp_scan_incl(s, lane);
+    double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 0.0;
+#pragma unroll
+    for (int k = 0; k < C; ++k)
+        if (j0 + k < Sp) cy1[sl_pi<C>(j0 + k + 1)] = (float)(excl + loc[k]);
+    if (lane == 0) cy1[0] = 0.f;
+    for (int i = lane; i < np; i += 32) cps[i] = __ldg(p.sdist[l] + r * np + i);
+    const int np_pad = sl_pi<C>(np) + 1;
+    for (int i = lane; i < np_pad; i += 32) E[i] = 0.f;
+    __syncwarp();
+    const float g_scale = p.mults[1] / (B_f * (float)S);
+    float ray_loss = 0.f;
+    for (int i = lane; i < S; i += 32) {
+        const float t0s = cf[i], t0e = cf[i + 1];
+        int lo = 0, hi = Sp, lo2 = 0, hi2 = Sp;
+        while (lo < hi || lo2 < hi2) {
+            if (lo < hi) {
+                const int md = (lo + hi) >> 1;
+                if (cps[md] <= t0s) lo = md + 1; else hi = md;
+            }
+            if (lo2 < hi2) {
+                const int md = (lo2 + hi2) >> 1;
+                if (cps[md + 1] <= t0e) lo2 = md + 1; else hi2 = md;
+            }
+        }
+        const int idx_lo = min(max(lo - 1, 0), Sp - 1);
+        const int idx_hi = min(max(lo2, 0), Sp - 1);
+        const float w_outer = cy1[sl_pi<C>(idx_hi + 1)] - cy1[sl_pi<C>(idx_lo)];
+        const float wi = wf[i];
+        const float d = fmaxf(wi - w_outer, 0.f);
+        ray_loss += d * d / (wi + LOSS_EPS);
+        const float g = -2.f * d / (wi + LOSS_EPS) * g_scale;
+        if (g != 0.f) {
+            atomicAdd(E + sl_pi<C>(idx_hi + 1), g);
+            atomicAdd(E + sl_pi<C>(idx_lo), -g);
+        }
+    }
+    t_inter += ray_loss;
+    __syncwarp();
+    // d loss / d w_j = sum of E over the entries behind j
+    float e[C], sl = 0.f;
+#pragma unroll
+    for (int k = 0; k < C; ++k) sl += j0 + k < Sp ? E[sl_pi<C>(j0 + k)] : 0.f, e[k] = sl;
+    const float incl_f = nvo_warp_scan_incl(sl, lane);
+    float excl_f = __shfl_up_sync(0xffffffffu, incl_f, 1);
+    if (lane == 0) excl_f = 0.f;
+    const float tot = __shfl_sync(0xffffffffu, incl_f, 31) + E[sl_pi<C>(Sp)];
+    float depth_l = 0.f, dwv[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        float dwj = tot - (excl_f + e[k]);
+        if (use_depth && j0 + k < Sp) {
+            const float t = (s0[k] + s1[k]) / 2.f, len = s1[k] - s0[k];
+            const float diff = t - D;
+            const float ex = expf(-(diff * diff) / two_sigma);
+            depth_l += -logf(v[k] + LOSS_EPS) * ex * len;
+            if (dmask && ex != 0.f) dwj += g_depth * (-1.f / (v[k] + LOSS_EPS)) * ex * len;
+        }
+        dwv[k] = dwj;
+    }
+    float* dwp = p.dw[l] + r * Sp;
+    if (C % 4 == 0 && j0 + C <= Sp && (reinterpret_cast<uintptr_t>(dwp) & 15) == 0) {
+#pragma unroll
+        for (int k = 0; k < C; k += 4) *reinterpret_cast<float4*>(dwp + j0 + k) = make_float4(dwv[k], dwv[k + 1], dwv[k + 2], dwv[k + 3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < C; ++k)
+            if (j0 + k < Sp) dwp[j0 + k] = dwv[k];
+    }
+    if (dmask) t_depth += depth_l;
+    __syncwarp();
+}
+
+// C0 / C1 > 0: the lane-blocked level path above with C = ceil(S_l / 32) samples per lane (the host picks the instantiation); 0: the chunked path
+template <int C0, int C1>
 __global__ void __launch_bounds__(32 * RAYS_PER_BLOCK) k_step_losses(const __grid_constant__ StepLossP p) {
     extern __shared__ float smf[];
     __shared__ float red[RAYS_PER_BLOCK][5];
@@ -371,7 +488,7 @@ __global__ void __launch_bounds__(32 * RAYS_PER_BLOCK) k_step_losses(const __gri
     const int role = (int)(gw - 3 * r);
     const bool live = r < p.B;
     const int S = p.S[2];
-    const int npmax = max(p.S[0], p.S[1]) + 1;
+    const int npmax = 2 * (max(p.S[0], p.S[1]) + 1);  // rows indexed by sample carry the lane-blocked path's padding (< 2x)
     // per warp: wf[S], cf[S+1], m[S], then cy1 / cps / E [npmax] each
     float* wf = smf + wid * (3 * S + 1 + 3 * npmax);
     float* cf = wf + S;
@@ -391,8 +508,10 @@ __global__ void __launch_bounds__(32 * RAYS_PER_BLOCK) k_step_losses(const __gri
         for (int i = lane; i <= S; i += 32) cf[i] = __ldg(p.sdist[2] + r * (S + 1) + i);
         __syncwarp();
         // ---- proposal levels: interlevel (fwd + bwd) and depth (fwd + bwd) ------------------------------------------------------------
+        if (C0 > 0 && role == 0) sl_level_fast<(C0 > 0 ? C0 : 1)>(p, 0, r, lane, wf, cf, cy1, cps, E, D, use_depth, dmask, two_sigma, g_depth, B_f, t_inter, t_depth);
+        if (C1 > 0 && role == 1) sl_level_fast<(C1 > 0 ? C1 : 1)>(p, 1, r, lane, wf, cf, cy1, cps, E, D, use_depth, dmask, two_sigma, g_depth, B_f, t_inter, t_depth);
         for (int l = 0; l < 2; ++l) {
-            if (l != role) continue;
+            if (l != role || (l == 0 ? C0 : C1) > 0) continue;
             const int Sp = p.S[l], np = Sp + 1;
             const float* wp = p.w[l] + r * Sp;
             double carry = 0.0;
@@ -580,9 +699,22 @@ extern "C" int nvo_step_losses(void* stream, int64_t B, int32_t S0, int32_t S1, 
     p.mults[0] = mult_rgb, p.mults[1] = mult_interlevel, p.mults[2] = mult_distortion, p.mults[3] = mult_depth, p.mults[4] = mult_normal;
     p.terms = terms, p.total = total, p.ticket = (unsigned int*)ticket;
     p.dw[0] = dw0, p.dw[1] = dw1, p.dw[2] = dw2, p.d_rgb = d_rgb, p.d_normals = d_normals;
-    const size_t smem = sizeof(float) * RAYS_PER_BLOCK * (3 * (size_t)S2 + 1 + 3 * (size_t)(max(S0, S1) + 1));
-    NVO_CHECK(smem <= 48 * 1024, "step_losses: %zu bytes of shared memory per CTA exceed 48 KB", smem);
-    k_step_losses<<<ray_blocks(3 * B), 32 * RAYS_PER_BLOCK, smem, (cudaStream_t)stream>>>(p);
+    const size_t smem = sizeof(float) * RAYS_PER_BLOCK * (3 * (size_t)S2 + 1 + 3 * 2 * (size_t)(max(S0, S1) + 1));
+    const int c0 = (S0 + 31) / 32, c1 = (S1 + 31) / 32;
+    static const int fast = nvo_env_int("NVO_LOSS_FAST", 1);
+    if (fast && c0 == 8 && c1 == 3) {  // NeRF-VO's 256 / 96 proposal samples
+        NVO_CHECK(smem <= 48 * 1024, "step_losses: %zu bytes of shared memory per CTA exceed 48 KB", smem);
+        k_step_losses<8, 3><<<ray_blocks(3 * B), 32 * RAYS_PER_BLOCK, smem, (cudaStream_t)stream>>>(p);
+    } else if (fast && c0 == 2 && c1 == 1) {  // 64 / 32 samples: the small shapes of the parity tests walk the same code
+        NVO_CHECK(smem <= 48 * 1024, "step_losses: %zu bytes of shared memory per CTA exceed 48 KB", smem);
+        k_step_losses<2, 1><<<ray_blocks(3 * B), 32 * RAYS_PER_BLOCK, smem, (cudaStream_t)stream>>>(p);
+    } else {
+        if (smem > 48 * 1024) {
+            NVO_CHECK(smem <= 200 * 1024, "step_losses: %zu bytes of shared memory per CTA exceed 200 KB", smem);
+            cudaFuncSetAttribute(k_step_losses<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }
+        k_step_losses<0, 0><<<ray_blocks(3 * B), 32 * RAYS_PER_BLOCK, smem, (cudaStream_t)stream>>>(p);
+    }
     NVO_CUDA_LAUNCH_CHECK("step_losses");
     return 0;
 }

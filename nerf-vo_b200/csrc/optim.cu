@@ -162,7 +162,10 @@ static int adam_step_impl(void* stream, int64_t n, float* params, const float* g
             NVO_CUDA_LAUNCH_CHECK("adam_step(consts)");
         }
         cudaFuncSetAttribute(k_adam_flat, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        k_adam_flat<<<nvo_blocks(n4 > 0 ? n4 : 1, 256), 256, 0, st>>>(n4, n, params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, grad_scale,
+        // NVO_ADAM_SMEM bytes of (unused) dynamic shared memory per CTA cap the CTAs per SM, leaving thread slots to kernels running next to it
+        static const int pad_smem = nvo_env_int("NVO_ADAM_SMEM", 0);
+        if (pad_smem > 0) cudaFuncSetAttribute(k_adam_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_smem);
+        k_adam_flat<<<nvo_blocks(n4 > 0 ? n4 : 1, 256), 256, pad_smem > 0 ? pad_smem : 0, st>>>(n4, n, params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, grad_scale,
                                                                       lr_final, max_steps, consts);
     }
     NVO_CUDA_LAUNCH_CHECK("adam_step");

@@ -850,3 +850,30 @@ def render_frame(P: Dict[str, Tensor], cfg: ModelCfg, intrinsics: Tensor, extrin
             depth.append(o["depth"])
     color, d = finalize_frame(torch.cat(rgb), torch.cat(depth), rays["directions_norm"])
     return color.reshape(height, width, 3), d.reshape(height, width)
+
+
+def point_cloud_batch(origins: Tensor, directions: Tensor, depth: Tensor, accumulation: Tensor, normals_coded: Optional[Tensor] = None,
+                      bounding_box_min=None, bounding_box_max=None, reorient_normals: bool = False):
+    """One iteration of generate_point_cloud's loop plus its final re-orientation (NS/exporter/exporter_utils.py:130-180, 222-226), the way
+    NerfstudioRenderer.render_mesh drives it (evaluation/nerf_renderer.py:188-203): returns the COMPACTED (points, rgb-mask indices, normals)."""
+    point = origins + directions * depth
+    view = directions
+    mask = accumulation[..., 0] > 0.5 if accumulation.dim() == 2 else accumulation > 0.5  # get_rgba_image: alpha = accumulation
+    idx = torch.nonzero(mask)[:, 0]
+    point, view = point[mask], view[mask]
+    normal = None
+    if normals_coded is not None:
+        normal = (normals_coded * 2.0) - 1.0
+        normal = normal[mask]
+    if bounding_box_min is not None:
+        comp_l, comp_m = torch.tensor(bounding_box_min), torch.tensor(bounding_box_max)
+        assert torch.all(comp_l < comp_m)
+        m2 = torch.all(torch.concat([point > comp_l, point < comp_m], dim=-1), dim=-1)
+        point, view, idx = point[m2], view[m2], idx[m2]
+        if normal is not None:
+            normal = normal[m2]
+    if reorient_normals and normal is not None:
+        normal = normal.clone()
+        flip = torch.sum(view * normal, dim=-1) > 0
+        normal[flip] *= -1
+    return point, idx, normal

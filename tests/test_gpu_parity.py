@@ -678,3 +678,37 @@ def test_fused_step_losses_match_unfused(nv, golden, eager):
     assert set(g0) == set(g1)
     for k in g0:
         assert rel_err(g1[k], g0[k]) < 1e-5, (k, rel_err(g1[k], g0[k]))
+
+
+@pytest.mark.parametrize("sizes", [(256, 96, 48), (64, 32, 16), (40, 20, 10)])
+def test_step_losses_lane_blocked_levels_match_per_loss_kernels(nv, sizes):
+    """k_step_losses' lane-blocked proposal-level path (256 / 96 and 64 / 32 samples; 40 / 20 takes the chunked path) against the per-loss kernels
+    the goldens pin to the reference, on nested sorted bins with ties: terms 2e-6 relative, every weight gradient 1e-5 of max-abs."""
+    B = 515
+    g = torch.Generator().manual_seed(sum(sizes))
+    ws, sd, ivs = [], [], []
+    for S in sizes:
+        e = torch.sort(torch.rand(B, S + 1, generator=g), dim=-1).values
+        e[:, 0], e[:, -1] = 0.0, 1.0
+        e[::7, S // 2] = e[::7, S // 2 - 1]  # zero-width bins (tied edges)
+        w = torch.rand(B, S, generator=g) ** 4
+        w = w / w.sum(-1, keepdim=True) * torch.rand(B, 1, generator=g)
+        ws.append(w.to(DEV)), sd.append(e.to(DEV).contiguous()), ivs.append(nv.ops.Intervals(ebins=(0.05 + 3.0 * e).to(DEV).contiguous()))
+    rgb, rgb_gt = torch.rand(B, 3, generator=g).to(DEV), torch.rand(B, 3, generator=g).to(DEV)
+    n_img, n_gt = torch.rand(B, 3, generator=g).to(DEV), torch.nn.functional.normalize(torch.randn(B, 3, generator=g), dim=-1).to(DEV)
+    depth_gt = (0.5 + 2.0 * torch.rand(B, generator=g)).to(DEV)
+    depth_gt[::5] = 0.0  # masked rays
+    dnorm = (1.0 + 0.2 * torch.rand(B, generator=g)).to(DEV)
+    out = []
+    for eager in (False, True):
+        wl = [w.clone().requires_grad_(True) for w in ws]
+        r, n = rgb.clone().requires_grad_(True), n_img.clone().requires_grad_(True)
+        total, terms = nv.ops.fused_step_losses(wl, sd, ivs, r, rgb_gt, n, n_gt, depth_gt, dnorm, sigma=0.01, mults=(1.0, 1.0, 0.002, 0.001 / 3, 5e-6),
+                                                eager_grads=eager)
+        total.backward()
+        out.append((float(total), terms.detach().cpu(), [w.grad.detach().cpu() for w in wl] + [r.grad.cpu(), n.grad.cpu()]))
+    (t0, te0, g0), (t1, te1, g1) = out
+    assert abs(t0 - t1) <= 2e-6 * abs(t0), (t0, t1)
+    assert torch.allclose(te0, te1, rtol=2e-6, atol=1e-12), (te0, te1)
+    for a, b in zip(g0, g1):
+        assert rel_err(b, a) < 1e-5, rel_err(b, a)

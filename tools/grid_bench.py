@@ -71,3 +71,11 @@ for run in ("0", "8", "16"):
         print(f"  run={run}: max |d - d_ref| / max|d_ref| = {float((dtable - ref).abs().max() / ref.abs().max()):.2e}")
     timed(f"grid_backward (scatter) NVO_GRID_BWD_RUN={run}", lambda: nv.ops.grid_backward(x, dy, spec, dtable=dtable, tmf=True), alg_bytes=n * (12 + 128 + 16 * 64))
 os.environ.pop("NVO_GRID_BWD_RUN")
+# per-level cost of the scatter (one-level grids with the level's resolution): where the time goes between coarse (many samples per vertex,
+# same-address reductions) and fine (every sample its own 8 vertices) levels
+tot = 0.0
+for l in range(L):
+    sp = nv.ops.GridSpec(1, a.log2, (spec.scalings[l],))
+    dyl = torch.randn(nv.ops.tmh_numel(n, 2), device=dev)
+    dtl = torch.zeros((1 << a.log2, 2), device=dev)
+    timed(f"  scatter level {l:2d} alone (scale {spec.scalings[l]:7.1f})", lambda: nv.ops.grid_backward(x, dyl, sp, dtable=dtl, tmf=True), reps=10)
