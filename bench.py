@@ -56,6 +56,25 @@ PRESETS = {
 }
 
 
+_JSON_OUT = None
+
+
+def claim_stdout() -> None:
+    """stdout carries ONE JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its version banner there at
+    communicator creation): fd 1 is pointed at stderr for the lifetime of the process and the JSON line goes to a private duplicate."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def workload_string(cfg: dict, B: int, world: int) -> str:
     return (f"{cfg['name']}: {B} rays/GPU x {world} GPU, proposal 256/96 + 48 samples, hash 16x2^{cfg['log2']}x2 + 2x(5x2^17x2), "
             "rgb+interlevel+distortion+depth+normal losses")
@@ -217,7 +236,7 @@ def run_reference(args, cfg):
                                    "(pinned to the live reference in the build container; the Python reference is not on this box)"},
         "e2e": {"value": rps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -269,7 +288,8 @@ def run_ours(args, cfg):
     # poses either); the `pose_opt` leg below reports the step with it
     pose_mode = "SO3xR3" if args.pose_opt else "off"
     model = nv.ExtendedNerfactoModel(nv.NerfactoModelConfig(log2_hashmap_size=log2, camera_optimizer_mode=pose_mode), num_train_data=K_IMG).to(dev)
-    trainer = MappingTrainer(model, num_rays=B, lr=1e-2, eps=1e-15, use_cuda_graph=not args.no_graph, exchange=args.exchange)
+    defer = args.defer_fields == "on" or (args.defer_fields == "auto" and world > 1)
+    trainer = MappingTrainer(model, num_rays=B, lr=1e-2, eps=1e-15, use_cuda_graph=not args.no_graph, exchange=args.exchange, defer_fields_update=defer)
     trainer.iteration = 2000  # past the proposal-weight anneal window (first 1000 of NeRF-VO's 8192 iterations): steady-state step
 
     n_pool = 8 if B <= 65536 else 3
@@ -297,6 +317,7 @@ def run_ours(args, cfg):
             loss = trainer.train_step()
             if read_loss:
                 loss_host = float(loss)  # D2H of the step's result
+        trainer.flush()  # defer_fields_update: the last step's pending fields-group update belongs to the timed steps
         ev1.record()
         barrier()
         ms = ev0.elapsed_time(ev1)
@@ -308,9 +329,23 @@ def run_ours(args, cfg):
 
     # ---- value: inputs resident in HBM (one device-to-device copy of the packed batch per step) -----------------------------------------
     packed_dev = [tuple(t.to(dev) for t in trainer.pack_host_batch(*hb)) for hb in host_batches]
-    for s in range(max(3, args.warmup)):
+    def settle(step_fn):
+        """Warm-up: max(3, W) untimed steps, extended to ~150 ms of stepping (a count fixed by the batch size, identical on every rank: the
+        steps contain collectives).  A 4096-ray step is under a millisecond, so W steps alone end before the clocks of all ranks have ramped up
+        and the ranks' launch queues have filled — the first timed steps of a short window then carry that ramp (r02: 8 GPUs, 40 timed
+        steps read 0.96 ms per step, 100 steps 0.87 ms)."""
+        n = max(3, args.warmup, min(200, int(0.15 / (B * 2e-7))))
+        for s in range(n):
+            step_fn(s)
+            if s % 16 == 15:
+                torch.cuda.synchronize()
+        return n
+
+    def warm_value(s):
         trainer.set_inputs_packed(packed_dev[s % n_pool])
         trainer.train_step()
+
+    settle(warm_value)
     with ClockSampler(local) as clk:
         ms, _ = timed(lambda s: trainer.set_inputs_packed(packed_dev[s % n_pool]), False, args.steps)
     launches_per_step = trainer.launches_per_step
@@ -375,9 +410,11 @@ def run_ours(args, cfg):
     trainer.capture(warmup=3)
     g = torch.Generator().manual_seed(555 + rank)
     draws = [trainer.pack_host_draws(torch.rand(B, 3, generator=g), [torch.rand(B, 1, generator=g) for _ in range(3)]) for _ in range(n_pool)]
-    for s in range(max(3, args.warmup)):
+    def warm_e2e(s):
         trainer.set_draws_packed(draws[s % n_pool])
         float(trainer.train_step())
+
+    settle(warm_e2e)
     ms_e2e, h2d = timed(lambda s: trainer.set_draws_packed(draws[s % n_pool]), True, args.steps)
     e2e_rays_per_s = world * B * args.steps / (ms_e2e * 1e-3)
     e2e_loss = float(trainer.loss)
@@ -454,7 +491,10 @@ def run_ours(args, cfg):
                        "step": "zero-grad + forward + losses + backward + fused Adam, proposal networks updated every step, camera poses optimised ("
                                + pose_mode + ": ray gradients of all three levels -> pose deltas, Adam under the exponential schedule)",
                        "l2": f"no explicit flush: main table + gradient + Adam moments = {4 * table_mb:.0f} MiB streamed per step exceed the 126 MB L2",
-                       "cuda_graph": not args.no_graph},
+                       "cuda_graph": not args.no_graph,
+                       "defer_fields_update": bool(trainer.defer_fields),
+                       "defer_note": ("the fields group's exchange + Adam of step k is launched at the start of step k+1 next to its proposal sampling; "
+                                      "the timed region ends with flush(), so K steps contain K fields updates") if trainer.defer_fields else None},
             "e2e": {"value": e2e_rays_per_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
                     "path": "MappingTrainer(datamanager=DynamicDataManager, external_draws=True): set_draws_packed (pinned host -> device) + train_step "
                             "(prologue kernel: pixel sampling + rgb/depth/normal gather + ray generation from the resident keyframe store; forward; losses; "
@@ -470,7 +510,7 @@ def run_ours(args, cfg):
             "reference_schedule": ref_sched, "pose_opt": pose_leg,
             "final_loss": final_loss,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -693,7 +733,7 @@ def run_eval_frame(args, cfg):
             "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu,
             "frame_checksum": int(out["c"].astype(np.int64).sum()),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -716,9 +756,13 @@ def main():
     ap.add_argument("--pose-opt", action="store_true", help="headline step with the model's camera optimizer on (default: reported as the `pose_opt` leg)")
     ap.add_argument("--no-roofline", action="store_true", help="skip the isolated-kernel roofline legs")
     ap.add_argument("--no-schedule-leg", action="store_true", help="skip the extra leg that follows the reference's proposal update schedule")
+    ap.add_argument("--defer-fields", default="auto", choices=["auto", "on", "off"],
+                    help="MappingTrainer(defer_fields_update=...): the fields group's optimizer / exchange of step k runs next to step k+1's proposal "
+                         "sampling (auto = on for N > 1, where it hides the NVLink exchange)")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="N>1 gradient exchange: 'fused' = peer-memory reduce-scatter+Adam+all-gather kernel, 'nccl' = all-reduce + replicated Adam")
     args = ap.parse_args()
+    claim_stdout()
     if args.mode == "eval-frame":
         args.config = 5
     cfg = PRESETS[args.config]

@@ -80,6 +80,8 @@ def load_checkpoint(ckpt, model, camera_optimizer=None, trainer=None, strict: bo
     datamanager state) are reported in "unexpected" and ignored, as the reference's strict=False fallback does."""
     if not isinstance(ckpt, dict):
         ckpt = torch.load(ckpt, map_location=map_location, weights_only=False)
+    if trainer is not None and hasattr(trainer, "_pending_fields"):
+        trainer._pending_fields = False  # a deferred update of the state being replaced is dropped with it
     pipeline_state = ckpt["pipeline"] if "pipeline" in ckpt else ckpt
     model_state, other = split_pipeline_state(pipeline_state)
     layout = layout_of(model_state)
@@ -156,6 +158,8 @@ def load_optimizer_state(optimizers: Dict, model_state, model, trainer) -> None:
 # ---------------------------------------------------------------------------------------------------------------------
 def checkpoint_dict(step: int, model, camera_optimizer=None, trainer=None) -> Dict:
     """The dict Trainer.save_checkpoint writes (NS/engine/trainer.py:436-447), torch key layout."""
+    if trainer is not None and hasattr(trainer, "flush"):
+        trainer.flush()  # defer_fields_update: the last step's fields-group update is applied before the state is read
     pipeline = OrderedDict()
     # Model.device_indicator_param (NS/models/base_model.py:81): an empty parameter the reference's strict load_state_dict expects first
     pipeline["_model.device_indicator_param"] = torch.empty(0)

@@ -142,6 +142,9 @@ class NerfactoModel(nn.Module):
         if self.training and not ray_bundle.pose_corrected:
             self.camera_optimizer.apply_to_raybundle(ray_bundle)
         ray_samples, weights_list, ray_samples_list = self.proposal_sampler(ray_bundle, density_fns=self.density_fns, jitters=jitters)
+        hook = getattr(self, "_before_field_forward", None)
+        if hook is not None:
+            hook()  # MappingTrainer(defer_fields_update=True): the previous step's fields update lands here, behind the proposal sampling
         fo = self.field.forward(ray_samples, compute_normals=self.config.predict_normals)
         weights = ray_samples.get_weights(fo[FieldHeadNames.DENSITY])
         weights_list.append(weights)

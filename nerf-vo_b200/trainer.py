@@ -36,10 +36,16 @@ class MappingTrainer:
     def __init__(self, model: ExtendedNerfactoModel, num_rays: int, lr: float = 1e-2, eps: float = 1e-15, betas=(0.9, 0.999),
                  use_cuda_graph: bool = True, with_normals: bool = True, device: Optional[torch.device] = None, exchange: str = "fused",
                  datamanager=None, proposal_update: str = "always", external_draws: bool = False, camera_opt_lr: float = 1e-4,
-                 camera_opt_lr_final: float = 1e-5, max_num_iterations: int = 8192):
+                 camera_opt_lr_final: float = 1e-5, max_num_iterations: int = 8192, defer_fields_update: bool = False):
         """camera_opt_lr / camera_opt_lr_final / max_num_iterations: the "camera_opt" group (Adam, ExponentialDecayScheduler over the mapping
         iterations, nerf_vo/mapping/nerfstudio.py:93-100), trained when the model's camera optimizer is on (config.camera_optimizer_mode)."""
         self.model = model
+        # defer_fields_update: the "fields" group's optimizer (at N > 1: its NVLink exchange) of step k runs at the START of step k+1, next to that
+        # step's proposal sampling — which reads the proposal networks only — and is joined before the field forward.  Same arithmetic, same
+        # order of updates; what changes is when the fields parameters become current: after train_step() they lag by the last update until
+        # the next step or flush() (checkpointing / rendering / reading parameters go through flush()).
+        self._defer_requested = bool(defer_fields_update)
+        self._pending_fields = False
         # optional: a DynamicDataManager (data.py). The step then starts with the fused prologue kernel (pixel sampling + gather + ray
         # generation, drawn on the device like the reference's torch.rand) instead of reading the static input buffers.
         self.datamanager = datamanager
@@ -114,6 +120,7 @@ class MappingTrainer:
         if self.cam_group and datamanager is not None:
             datamanager.camera_optimizer = model.camera_optimizer  # the step prologue applies the pose correction itself
         self._opt_stream: Optional[torch.cuda.Stream] = None
+        self.defer_fields = self._defer_requested and len(self.groups) == 2 and self.exchange != "nccl" and self.device.type == "cuda"
         self._fields_done = False
         self._in_backward = False
         off = 0
@@ -201,7 +208,7 @@ class MappingTrainer:
         return RayBundle(origins=i["origins"], directions=i["directions"], pixel_area=i["pixel_area"], camera_indices=i["camera_indices"],
                          metadata={"directions_norm": i["directions_norm"]})
 
-    def _forward_backward(self) -> None:
+    def _forward_backward(self, pending: bool = False) -> None:
         """zero-grad, forward, losses, backward.  From 4 ranks on (fused arm) the exchange + Adam of the "fields" group is launched from
         INSIDE the backward (ops.leaf_streams.after_field_backward), right behind the main hash-table scatter, on a high-priority
         stream; the proposal networks' backward is then ordered behind the field's chain, so both run side by side (one is NVLink
@@ -209,7 +216,32 @@ class MappingTrainer:
         i = self.inputs
         side = self.device.type == "cuda" and ops.leaf_streams.enabled
         self._fields_done = False
-        if side:
+        self.model._before_field_forward = None
+        if side and self.defer_fields and pending:
+            # the previous step's fields-group update next to this step's proposal sampling: optimizer (exchange) -> zero fill of the group's
+            # gradient range -> this step's fp16 weight images, on the optimizer stream; the main stream joins before the field forward
+            n_f = self.groups[0][2]
+            if self._opt_stream is None:
+                # high priority: the exchange's one CTA per SM is placed ahead of the proposal kernels pending at the same time, which fill the rest
+                self._opt_stream = torch.cuda.Stream(priority=-1)
+            cur = torch.cuda.current_stream()
+            self._opt_stream.wait_stream(cur)
+            with torch.cuda.stream(self._opt_stream):
+                self._narrow_exchange = True
+                try:
+                    self._optimizer_group(0)
+                finally:
+                    self._narrow_exchange = False
+                self.grad[:n_f].zero_()
+                self.model.field.prepack(self.model.config.num_nerf_samples_per_ray)
+                ev = torch.cuda.Event()
+                ev.record(self._opt_stream)
+            self.model._before_field_forward = lambda: torch.cuda.current_stream().wait_event(ev)
+            with ops.leaf_streams.fork(self.grad):
+                self.grad[n_f:].zero_()
+                if self._ray_grads is not None:
+                    self._ray_grads.zero_()
+        elif side:
             # off the critical chain: the 74 MB zero fill of the flat gradient and the fp16 weight images of the three field networks
             # run on side streams next to the proposal sampling; both are joined before their first consumer
             with ops.leaf_streams.fork(self.grad):
@@ -244,6 +276,7 @@ class MappingTrainer:
             _, total, terms, weights = self.model.get_train_loss_fused(bundle, batch, [i["jitter0"], i["jitter1"], i["jitter2"]], eager_grads=True)
         finally:
             self.model._leaf_renders = False
+            self.model._before_field_forward = None
         if side:
             ops.leaf_streams.join()  # the zero fill must have landed before the first backward kernel accumulates into the gradient
         # Early launch of the fields group's exchange next to the (deferred) proposal backward.  Measured (profiles/r01_timeline_*s9*.csv,
@@ -252,7 +285,8 @@ class MappingTrainer:
         # hiding it behind the proposal backward wins (8 GPUs: 1067 -> 1030 us per step).  NVO_EARLY_FIELDS_OPT=1 / 0 forces it on / off.
         env = os.environ.get("NVO_EARLY_FIELDS_OPT", "")
         multi = self.peer is not None and self.world_size >= 4
-        early = side and len(self.groups) == 2 and self.exchange != "nccl" and (env in ("1", "2") or (env != "0" and (multi or self.peer is None)))
+        early = (side and len(self.groups) == 2 and self.exchange != "nccl" and (env in ("1", "2") or (env != "0" and (multi or self.peer is None)))
+                 and not self.defer_fields)
         # one GPU (and NVO_EARLY_FIELDS_OPT=2): the fields group's Adam (HBM-bound) starts right behind the main table scatter, which runs on
         # the high-priority critical stream, while the proposal networks' backward and scatters (issue / reduction bound) are still running
         # and stay where they are; from 4 ranks on the exchange takes that place and the proposal backward is deferred behind the field chain
@@ -271,6 +305,8 @@ class MappingTrainer:
         ops.leaf_streams.join()  # scatter kernels running on side streams must land before the all-reduce / optimizer
         if self._fields_done:
             torch.cuda.current_stream().wait_stream(self._opt_stream)
+        if self.defer_fields:
+            self._fields_done = True  # _optimizer() leaves the fields group alone: its update opens the next step (or flush())
         self.loss.copy_(total.detach())
         if self.cam_group is not None:
             # CameraOptimizer.apply_to_raybundle's backward on the summed ray gradients (every level's sample positions + the field's direction
@@ -306,7 +342,8 @@ class MappingTrainer:
         if self.peer is not None:
             # inside the backward (early launch) the exchange shares the SMs with the proposal backward: one CTA per SM
             self.peer.adam_exchange_group(self._peer_groups[gi], self.step_counts[gi], self.lr, self.betas[0], self.betas[1], self.eps,
-                                          ctas_per_sm=1 if self._in_backward else 0)
+                                          ctas_per_sm=(int(os.environ.get("NVO_DEFER_CTAS", "1")) if getattr(self, "_narrow_exchange", False) else
+                                                       1 if self._in_backward else 0))
             return
         ops.adam_step(self.flat[off:off + n], self.grad[off:off + n], self.exp_avg[off:off + n], self.exp_avg_sq[off:off + n], self.step_counts[gi],
                       self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / self.world_size)
@@ -441,36 +478,42 @@ class MappingTrainer:
         # Adam moments and the device step counters are snapshotted here and restored afterwards, so capture() is free of side effects
         # on the training state (it may be called on a fresh model or right after load_checkpoint()).
         state = self._snapshot_state()
+        pendings = [False, True] if self.defer_fields else [False]
         with torch.cuda.stream(s):
             for _ in range(warmup):
                 for upd in modes:
-                    self._set_sampler_state(upd)
-                    self._forward_backward()
-                    self._exchange()
-                    self._optimizer(upd)
+                    for pend in pendings:
+                        self._set_sampler_state(upd)
+                        self._forward_backward(pend)
+                        self._exchange()
+                        self._optimizer(upd)
+            if self.defer_fields:
+                self._optimizer_group(0)  # every rank leaves the warm-up with the same number of fields-group exchanges behind it
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self._restore_state(state)
+        self._pending_fields = False
         if not self.use_cuda_graph:
             return
         self._graphs = {}
         for upd in modes:
-            self._set_sampler_state(upd)
-            n0 = _lib.launch_count()
-            g_fb = torch.cuda.CUDAGraph()
-            g_opt = None
-            with torch.cuda.graph(g_fb, stream=s):
-                self._forward_backward()
-                if self.exchange != "nccl":
-                    self._optimizer(upd)
-            if self.exchange == "nccl":
-                g_opt = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g_opt, stream=s):
-                    self._optimizer(upd)
-            self._graphs[upd] = (g_fb, g_opt)
-            if upd:
-                self.launches_per_step = _lib.launch_count() - n0
-        self._graph_fb, self._graph_opt = self._graphs[True]
+            for pend in pendings:
+                self._set_sampler_state(upd)
+                n0 = _lib.launch_count()
+                g_fb = torch.cuda.CUDAGraph()
+                g_opt = None
+                with torch.cuda.graph(g_fb, stream=s):
+                    self._forward_backward(pend)
+                    if self.exchange != "nccl":
+                        self._optimizer(upd)
+                if self.exchange == "nccl":
+                    g_opt = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g_opt, stream=s):
+                        self._optimizer(upd)
+                self._graphs[(upd, pend)] = (g_fb, g_opt)
+                if upd and pend == pendings[-1]:
+                    self.launches_per_step = _lib.launch_count() - n0
+        self._graph_fb, self._graph_opt = self._graphs[(True, False)]
 
     def _moment_tensors(self) -> List[torch.Tensor]:
         if self.peer is not None:
@@ -481,6 +524,7 @@ class MappingTrainer:
     def full_moments(self):
         """(exp_avg, exp_avg_sq) over the whole flat buffer.  Local / NCCL arms: the buffers themselves.  Fused arm: every rank holds only
         its slice of each group, so this is a COLLECTIVE (every rank must call it) that all-gathers the slices."""
+        self.flush()
         if self.peer is None:
             return self.exp_avg, self.exp_avg_sq
         from .peer import slice_range
@@ -533,13 +577,21 @@ class MappingTrainer:
             torch.cuda.synchronize()
             dist.barrier()  # fused arm: a peer must not start exchanging into replicas another rank is still restoring
 
+    def flush(self) -> None:
+        """Applies the deferred fields-group update of the last step (defer_fields_update=True); afterwards parameters, moments and step counters
+        are exactly what the undeferred trainer holds after the same steps.  Collective at N > 1 (every rank calls it).  No-op otherwise."""
+        if self._pending_fields:
+            self._optimizer_group(0)
+            self._pending_fields = False
+
     def train_step(self) -> torch.Tensor:
         """Runs one step on the current contents of the static input buffers; returns the (device) loss scalar."""
         upd = self._updated_now()
         # the reference's per-iteration callbacks: set_anneal before the step (a device scalar: graph replays read it)
         self.model.before_train_iteration(self.iteration)
+        pend = self.defer_fields and self._pending_fields
         if self._graph_fb is not None:
-            g_fb, g_opt = self._graphs[upd]
+            g_fb, g_opt = self._graphs[(upd, pend)]
             g_fb.replay()
             if self.exchange == "nccl":
                 sharding.allreduce_gradient_(self.grad)
@@ -549,10 +601,12 @@ class MappingTrainer:
 
             n0 = _lib.launch_count()
             self._set_sampler_state(upd)
-            self._forward_backward()
+            self._forward_backward(pend)
             self._exchange()
             self._optimizer(upd)
             self.launches_per_step = _lib.launch_count() - n0
+        if self.defer_fields:
+            self._pending_fields = True
         # ProposalNetworkSampler.step_cb + the reset in generate_ray_samples (ray_samplers.py:591-594,611-612)
         self._ssu = 1 if upd else self._ssu + 1
         self.iteration += 1

@@ -113,3 +113,39 @@ def test_graph_replay_samples_keyframes_inserted_after_capture():
         tr.train_step()
         seen |= set(dm._last_camera_indices.reshape(-1).tolist())
     assert seen == set(range(K)), seen
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_deferred_fields_update_matches_undeferred(graph):
+    """defer_fields_update=True runs the fields group's Adam of step k at the start of step k+1 (next to the proposal sampling): after flush()
+    parameters, moments and step counters equal the undeferred trainer's after the same steps (both walk the same kernels; the hash-table
+    scatter's atomic order is the only difference between two runs), the loss trajectory is the same, and without flush() the fields
+    group lags by exactly one update."""
+    import nerf_vo_b200 as nv
+    from nerf_vo_b200.trainer import MappingTrainer
+
+    rays, targets, jit = _inputs()
+    out = []
+    for defer in (False, True):
+        model = _small_model(nv).to(DEV)
+        tr = MappingTrainer(model, num_rays=B, lr=1e-2, eps=1e-15, use_cuda_graph=graph, proposal_update="reference", defer_fields_update=defer)
+        assert tr.defer_fields == defer
+        tr.capture(warmup=2)
+        tr.set_inputs({k: v.to(DEV) for k, v in rays.items()}, {k: v.to(DEV) for k, v in targets.items()}, [j.to(DEV) for j in jit])
+        losses = [float(tr.train_step()) for _ in range(STEPS)]
+        if defer:
+            assert [int(c) for c in tr.step_counts] == [STEPS - 1, 13]  # the last fields update is pending
+            tr.flush()
+            tr.flush()  # idempotent
+        torch.cuda.synchronize()
+        assert [int(c) for c in tr.step_counts] == [STEPS, 13]
+        out.append((losses, tr.flat.detach().clone(), [m.detach().clone() for m in tr._moment_tensors()]))
+    (l0, p0, m0), (l1, p1, m1) = out
+    assert l1 == pytest.approx(l0, rel=1e-3), (l0, l1)
+    init = torch.cat([torch.cat([p.detach().reshape(-1), p.new_zeros((-p.numel()) % 4)]) for p in _small_model(nv).to(DEV).parameters() if p.requires_grad])
+    d0, d1 = (p0 - init).double(), (p1 - init).double()  # what 16 steps moved (Adam at lr 1e-2 amplifies the scatter's atomic-order noise on
+    cos = float((d0 * d1).sum() / (d0.norm() * d1.norm()))  # entries with tiny gradients: judged by the movement as a whole, as the oracle test does)
+    assert cos > 0.995, cos
+    assert abs(float(d0.norm()) - float(d1.norm())) < 2e-2 * float(d0.norm())
+    for a, b in zip(m0, m1):
+        assert float((a - b).norm()) <= 1e-1 * float(a.norm()) + 1e-12  # same chaos-amplified noise, seen through the moments

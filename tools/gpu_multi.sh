@@ -18,6 +18,6 @@ for c in $CONFIGS; do
   echo "config $c rc=$? bytes=$(wc -c < gpurun_out/${tag}_config$c.json)"
   python -c "
 import json
-d=json.load(open('gpurun_out/${tag}_config$c.json')); print('config$c', d['n_gpus'], d['value'], d['unit'], d['ms_per_step'], d.get('exchange'))"
+d=json.loads([l for l in open('gpurun_out/${tag}_config$c.json') if l.startswith('{')][-1]); print('config$c', d['n_gpus'], d['value'], d['unit'], d['ms_per_step'], d.get('exchange'))"
   tail -n 3 gpurun_out/${tag}_config$c.err
 done
