@@ -310,6 +310,51 @@ __global__ void __launch_bounds__(128) k_grid_bwd_run(const __grid_constant__ Gr
     run.flush(slab);
 }
 
+// Rolled variant of k_grid_bwd_run: the same walk (G consecutive samples of a ray, one level, run merging in registers), but the G / 4 sample
+// quads are a real loop with the next quad's positions and gradients requested before the current one is processed.  The fully unrolled
+// kernel keeps all 2 G gradient values live and expands CellRun's flush G + 1 times (3 584 instructions, 92 registers: 5 CTAs per SM,
+// instruction-cache misses on the 5-level proposal launches); this one is a quarter of the code and fits 6 CTAs per SM.
+template <int G>
+__global__ void __launch_bounds__(128, 6) k_grid_bwd_run_rolled(const __grid_constant__ GridP p, int64_t n, const float* __restrict__ x,
+                                                                const float* __restrict__ dy, float* __restrict__ dtable) {
+    const int64_t t0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * G;
+    if (t0 >= n) return;
+    const int l = blockIdx.y;
+    float* slab = dtable + (((size_t)l << p.log2T) << 1);
+    const float scale = p.scale[l];
+    const uint32_t mask = (1u << p.log2T) - 1u;
+    const float* b = dy + (((t0 >> 7) * (2 * p.L) + 2 * l) << 7) + (t0 & 127);
+    const bool full = t0 + G <= n;
+    CellRun run;
+    run.reset();
+    if (!full) {  // ragged tail of the batch: scalar walk
+        for (int k = 0; k < G && t0 + k < n; ++k) {
+            const float g0 = __ldg(b + k), g1 = __ldg(b + 128 + k);
+            if (g0 == 0.f && g1 == 0.f) continue;
+            const int64_t t = t0 + k;
+            run.add(slab, __ldg(x + 3 * t), __ldg(x + 3 * t + 1), __ldg(x + 3 * t + 2), scale, mask, g0, g1);
+        }
+        run.flush(slab);
+        return;
+    }
+    const float4* xv = reinterpret_cast<const float4*>(x + 3 * t0);  // 16-byte aligned: t0 is a multiple of 4 and the caller checked the base
+    float4 na = __ldg(reinterpret_cast<const float4*>(b)), nc = __ldg(reinterpret_cast<const float4*>(b + 128));
+    float4 nx0 = __ldg(xv), nx1 = __ldg(xv + 1), nx2 = __ldg(xv + 2);
+#pragma unroll 1
+    for (int k = 0; k < G; k += 4) {
+        const float4 a = na, c = nc, x0 = nx0, x1 = nx1, x2 = nx2;
+        if (k + 4 < G) {
+            na = __ldg(reinterpret_cast<const float4*>(b + k + 4)), nc = __ldg(reinterpret_cast<const float4*>(b + 128 + k + 4));
+            nx0 = __ldg(xv + 3 * (k / 4 + 1)), nx1 = __ldg(xv + 3 * (k / 4 + 1) + 1), nx2 = __ldg(xv + 3 * (k / 4 + 1) + 2);
+        }
+        if (!(a.x == 0.f && c.x == 0.f)) run.add(slab, x0.x, x0.y, x0.z, scale, mask, a.x, c.x);
+        if (!(a.y == 0.f && c.y == 0.f)) run.add(slab, x0.w, x1.x, x1.y, scale, mask, a.y, c.y);
+        if (!(a.z == 0.f && c.z == 0.f)) run.add(slab, x1.z, x1.w, x2.x, scale, mask, a.z, c.z);
+        if (!(a.w == 0.f && c.w == 0.f)) run.add(slab, x2.y, x2.z, x2.w, scale, mask, a.w, c.w);
+    }
+    run.flush(slab);
+}
+
 // dL/dx: one thread per (sample, level) computes its level's contribution, then the L lanes of a sample are
 // summed with warp shuffles when L divides 32 (main grid, L=16), else with atomics (L=5 proposals).
 template <typename RowT, typename OutT>
@@ -499,6 +544,21 @@ extern "C" int nvo_grid_backward(const nvo_grid_desc* d, void* stream, int64_t n
     if (d->out_dtype == NVO_F32_TMF && (reinterpret_cast<size_t>(dy) & 15) == 0 && (reinterpret_cast<size_t>(x) & 15) == 0) {
         // samples per thread and level: 16 (default; measured on a step's own sample positions: 146 -> 121 us), 8, or 0 = the quad kernel
         static const int run_g = nvo_env_int("NVO_GRID_BWD_RUN", 16);  // read once per process
+        // rolled walk (k_grid_bwd_run_rolled): 0 = off, 1 = grids of up to 8 levels (the proposal networks'), 2 = every grid
+        static const int rolled = nvo_env_int("NVO_GRID_BWD_ROLLED", 0);
+        static const int rolled_g = nvo_env_int("NVO_GRID_BWD_ROLLED_G", 16);
+        if (rolled == 2 || (rolled == 1 && p.L <= 8)) {
+            const int g = rolled_g == 8 ? 8 : rolled_g == 32 ? 32 : 16;
+            const dim3 gr(nvo_blocks((n + g - 1) / g, 128), (unsigned int)p.L);
+            if (g == 8)
+                k_grid_bwd_run_rolled<8><<<gr, 128, 0, st>>>(p, n, x, (const float*)dy, dtable);
+            else if (g == 32)
+                k_grid_bwd_run_rolled<32><<<gr, 128, 0, st>>>(p, n, x, (const float*)dy, dtable);
+            else
+                k_grid_bwd_run_rolled<16><<<gr, 128, 0, st>>>(p, n, x, (const float*)dy, dtable);
+            NVO_CUDA_LAUNCH_CHECK("grid_backward(rolled)");
+            return 0;
+        }
         if (run_g == 8 || run_g == 16) {
             const dim3 gr(nvo_blocks((n + run_g - 1) / run_g, 128), (unsigned int)p.L);
             if (run_g == 8)
