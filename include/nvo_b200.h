@@ -174,6 +174,11 @@ int nvo_prop_density_backward_split(const nvo_grid_desc* g, int32_t hidden, int3
  * NS/fields/nerfacto_field.py:201-209): pos[n,3] -> x[n,3] (zeroed where outside (0,1)), selector[n] (0/1 as float).
  * contract=0 skips the contraction and maps through the aabb instead: x = (pos - aabb_min)/(aabb_max-aabb_min). */
 int nvo_contract_forward(void* stream, int64_t n, const float* pos, float* x, float* selector);
+/* nvo_sample_positions followed by nvo_contract_forward in one pass (Frustums.get_positions, NS/cameras/rays.py:49-58, then
+ * SceneContraction + normalisation + selector, spatial_distortions.py:67-69, nerfacto_field.py:201-209): positions[B*S,3] (world),
+ * x[B*S,3] (normalised, selector-masked), selector[B*S].  starts / ends: Euclidean interval edges with row stride `stride`. */
+int nvo_sample_positions_contract(void* stream, int64_t B, int32_t S, const float* origins, const float* directions, const float* starts,
+                                  const float* ends, int64_t stride, float* positions, float* x, float* selector);
 /* SHEncoding degree 4 on the vector as given (NS/utils/math.py:29-93): d[n,3] -> out[n,16] */
 int nvo_sh4_forward(void* stream, int64_t n, const float* d, float* out);
 /* NeRFEncoding torch path (NS/field_components/encodings.py:170-176): sin(cat[u, u+pi/2]), u = 2*pi*x_i*2^k;

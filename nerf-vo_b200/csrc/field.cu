@@ -24,6 +24,38 @@ __global__ void __launch_bounds__(256) k_contract(int64_t n, const float* __rest
     selector[t] = m;
 }
 
+// sample positions (rays.py:55: origins + directions * (starts + ends) / 2) and their contraction in one pass: the fused field forward needs
+// both (world positions feed the predicted-normals encoding, contracted ones the hash grid); same arithmetic as k_sample_positions + k_contract
+__global__ void __launch_bounds__(256) k_positions_contract(int64_t B, int S, const float* __restrict__ o, const float* __restrict__ d,
+                                                            const float* __restrict__ starts, const float* __restrict__ ends, int64_t stride,
+                                                            float* __restrict__ pos, float* __restrict__ x, float* __restrict__ selector) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * S) return;
+    const int64_t r = t / S;
+    const int k = (int)(t - r * S);
+    const float se = __fadd_rn(__ldg(starts + r * stride + k), __ldg(ends + r * stride + k));
+    float p[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        p[a] = __fadd_rn(__ldg(o + 3 * r + a), __fmul_rn(__fmul_rn(__ldg(d + 3 * r + a), se), 0.5f));
+        pos[3 * t + a] = p[a];
+    }
+    const float mag = fmaxf(fabsf(p[0]), fmaxf(fabsf(p[1]), fabsf(p[2])));
+    bool sel = true;
+    float q[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float c = p[a];
+        if (!(mag < 1.f)) c = __fmul_rn(__fsub_rn(2.f, __fdiv_rn(1.f, mag)), __fdiv_rn(p[a], mag));
+        q[a] = __fmul_rn(__fadd_rn(c, 2.f), 0.25f);
+        sel = sel && (q[a] > 0.f) && (q[a] < 1.f);
+    }
+    const float m = sel ? 1.f : 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) x[3 * t + a] = __fmul_rn(q[a], m);
+    selector[t] = m;
+}
+
 // ---- SH degree 4 (NS/utils/math.py:45-78), constants rounded to fp32 as torch does for python-float * tensor ----
 __device__ __forceinline__ void sh16(float x, float y, float z, float* c) {
     const float xx = __fmul_rn(x, x), yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
@@ -283,6 +315,15 @@ extern "C" int nvo_contract_forward(void* stream, int64_t n, const float* pos, f
     NVO_CHECK(pos && x && selector, "contract_forward: null pointer");
     k_contract<<<nvo_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(n, pos, x, selector);
     NVO_CUDA_LAUNCH_CHECK("contract_forward");
+    return 0;
+}
+extern "C" int nvo_sample_positions_contract(void* stream, int64_t B, int32_t S, const float* origins, const float* directions, const float* starts,
+                                             const float* ends, int64_t stride, float* positions, float* x, float* selector) {
+    NVO_CHECK(B >= 0 && S >= 1, "sample_positions_contract: bad shape");
+    if (B == 0) return 0;
+    NVO_CHECK(origins && directions && starts && ends && positions && x && selector, "sample_positions_contract: null pointer");
+    k_positions_contract<<<nvo_blocks(B * S, 256), 256, 0, (cudaStream_t)stream>>>(B, S, origins, directions, starts, ends, stride, positions, x, selector);
+    NVO_CUDA_LAUNCH_CHECK("sample_positions_contract");
     return 0;
 }
 extern "C" int nvo_sh4_forward(void* stream, int64_t n, const float* d, float* out) {

@@ -726,7 +726,13 @@ __global__ void __launch_bounds__(256) k_field_bwd_absmax(int64_t n, const float
         m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         md = fmaxf(md, __shfl_xor_sync(0xffffffffu, md, o));
     }
-    if ((threadIdx.x & 31) == 0) {
+    // one pair of atomics per CTA (same-address atomics from every warp of the grid serialise in L2: 4736 x 2 of them cost more than the pass itself)
+    __shared__ float sm[8], smd[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m, smd[threadIdx.x >> 5] = md;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, sm[w]), md = fmaxf(md, smd[w]);
         if (m > 0.f) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
         if (md > 0.f) atomicMax(reinterpret_cast<int*>(out) + 1, __float_as_int(md));
     }

@@ -414,29 +414,45 @@ __device__ __forceinline__ void sl_level_fast(const StepLossP& p, const int l, c
     __syncwarp();
     const float g_scale = p.mults[1] / (B_f * (float)S);
     float ray_loss = 0.f;
-    for (int i = lane; i < S; i += 32) {
-        const float t0s = cf[i], t0e = cf[i + 1];
-        int lo = 0, hi = Sp, lo2 = 0, hi2 = Sp;
-        while (lo < hi || lo2 < hi2) {
-            if (lo < hi) {
-                const int md = (lo + hi) >> 1;
-                if (cps[md] <= t0s) lo = md + 1; else hi = md;
-            }
-            if (lo2 < hi2) {
-                const int md = (lo2 + hi2) >> 1;
-                if (cps[md + 1] <= t0e) lo2 = md + 1; else hi2 = md;
+    // two field samples per lane and trip (S = 48: one trip), four bin searches advancing together
+    for (int i0 = lane; i0 < S; i0 += 64) {
+        float ts[2], te[2];
+        int lo[2], hi[2], lo2[2], hi2[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int i = i0 + 32 * q;
+            const bool act = i < S;
+            ts[q] = act ? cf[i] : 0.f, te[q] = act ? cf[i + 1] : 0.f;
+            lo[q] = lo2[q] = 0, hi[q] = hi2[q] = act ? Sp : 0;
+        }
+        while (lo[0] < hi[0] || lo2[0] < hi2[0] || lo[1] < hi[1] || lo2[1] < hi2[1]) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (lo[q] < hi[q]) {
+                    const int md = (lo[q] + hi[q]) >> 1;
+                    if (cps[md] <= ts[q]) lo[q] = md + 1; else hi[q] = md;
+                }
+                if (lo2[q] < hi2[q]) {
+                    const int md = (lo2[q] + hi2[q]) >> 1;
+                    if (cps[md + 1] <= te[q]) lo2[q] = md + 1; else hi2[q] = md;
+                }
             }
         }
-        const int idx_lo = min(max(lo - 1, 0), Sp - 1);
-        const int idx_hi = min(max(lo2, 0), Sp - 1);
-        const float w_outer = cy1[sl_pi<C>(idx_hi + 1)] - cy1[sl_pi<C>(idx_lo)];
-        const float wi = wf[i];
-        const float d = fmaxf(wi - w_outer, 0.f);
-        ray_loss += d * d / (wi + LOSS_EPS);
-        const float g = -2.f * d / (wi + LOSS_EPS) * g_scale;
-        if (g != 0.f) {
-            atomicAdd(E + sl_pi<C>(idx_hi + 1), g);
-            atomicAdd(E + sl_pi<C>(idx_lo), -g);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int i = i0 + 32 * q;
+            if (i >= S) continue;
+            const int idx_lo = min(max(lo[q] - 1, 0), Sp - 1);
+            const int idx_hi = min(max(lo2[q], 0), Sp - 1);
+            const float w_outer = cy1[sl_pi<C>(idx_hi + 1)] - cy1[sl_pi<C>(idx_lo)];
+            const float wi = wf[i];
+            const float d = fmaxf(wi - w_outer, 0.f);
+            ray_loss += d * d / (wi + LOSS_EPS);
+            const float g = -2.f * d / (wi + LOSS_EPS) * g_scale;
+            if (g != 0.f) {
+                atomicAdd(E + sl_pi<C>(idx_hi + 1), g);
+                atomicAdd(E + sl_pi<C>(idx_lo), -g);
+            }
         }
     }
     t_inter += ray_loss;

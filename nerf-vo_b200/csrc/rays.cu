@@ -131,8 +131,112 @@ __global__ void __launch_bounds__(32 * RAYS_PER_BLOCK) k_weights_bwd(int64_t B, 
     }
 }
 
+// ---- lane-blocked variants ------------------------------------------------------------------------------------
+// Lane j owns the C CONSECUTIVE samples [C j, C j + C) of its ray (C = ceil(S / 32)): a prefix sum is then C serial fp64 adds, ONE warp scan of
+// the lane totals and C adds, instead of one 5-step warp scan per 32-sample chunk (8 dependent shuffle chains at 256 samples).  Same fp64
+// accumulation and per-entry fp32 rounding as the chunked kernels above, which stay as the path for other sample counts.
+template <int C>
+__device__ __forceinline__ void lane_block_scan(const double (&x)[C], int lane, double (&incl)[C], double& excl_lane, double& total) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < C; ++k) s += x[k], incl[k] = s;
+    const double sc = nvo_warp_scan_incl(s, lane);
+    excl_lane = __shfl_up_sync(0xffffffffu, sc, 1);
+    if (lane == 0) excl_lane = 0.0;
+    total = __shfl_sync(0xffffffffu, sc, 31);
+}
+
+template <int C>
+__global__ void __launch_bounds__(32 * RAYS_PER_BLOCK) k_weights_fwd_lb(int64_t B, int S, const float* __restrict__ starts, const float* __restrict__ ends,
+                                                                        int64_t stride, const float* __restrict__ density, float* __restrict__ weights) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * RAYS_PER_BLOCK + (threadIdx.x >> 5);
+    if (r >= B) return;
+    const float* st = starts + r * stride;
+    const float* en = ends + r * stride;
+    const int j0 = C * lane;
+    float dd[C];
+    double x[C], incl[C], excl_lane, total;
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        const int i = j0 + k;
+        dd[k] = i < S ? __fmul_rn(__fsub_rn(__ldg(en + i), __ldg(st + i)), __ldg(density + r * S + i)) : 0.f;
+        x[k] = (double)dd[k];
+    }
+    lane_block_scan<C>(x, lane, incl, excl_lane, total);
+    float w[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        const float excl = (float)(excl_lane + incl[k] - x[k]);
+        w[k] = nan_to_num(__fmul_rn(__fsub_rn(1.f, expf(-dd[k])), expf(-excl)));
+    }
+    float* wp = weights + r * S;
+    if (C % 4 == 0 && j0 + C <= S && (reinterpret_cast<uintptr_t>(wp) & 15) == 0) {
+#pragma unroll
+        for (int k = 0; k < C; k += 4) *reinterpret_cast<float4*>(wp + j0 + k) = make_float4(w[k], w[k + 1], w[k + 2], w[k + 3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < C; ++k)
+            if (j0 + k < S) wp[j0 + k] = w[k];
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(32 * RAYS_PER_BLOCK) k_weights_bwd_lb(int64_t B, int S, const float* __restrict__ starts, const float* __restrict__ ends,
+                                                                        int64_t stride, const float* __restrict__ density, const float* __restrict__ dweights,
+                                                                        float* __restrict__ ddensity) {
+    // w_i = (1-e^{-a_i}) T_i, T_i = e^{-sum_{j<i} a_j}:  dL/da_i = g_i T_i e^{-a_i} - sum_{k>i} g_k w_k ; dL/dsigma_i = delta_i dL/da_i
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * RAYS_PER_BLOCK + (threadIdx.x >> 5);
+    if (r >= B) return;
+    const float* st = starts + r * stride;
+    const float* en = ends + r * stride;
+    const int j0 = C * lane;
+    float delta[C], g[C], dd[C];
+    double x[C], incl[C], excl_lane, total;
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        const int i = j0 + k;
+        const bool in = i < S;
+        delta[k] = in ? __fsub_rn(__ldg(en + i), __ldg(st + i)) : 0.f;
+        dd[k] = in ? __fmul_rn(delta[k], __ldg(density + r * S + i)) : 0.f;
+        g[k] = in ? __ldg(dweights + r * S + i) : 0.f;
+        x[k] = (double)dd[k];
+    }
+    lane_block_scan<C>(x, lane, incl, excl_lane, total);
+    float first[C];  // g_i T_i e^{-a_i} where the weight is finite
+    double gw[C], incl_gw[C], excl_gw, tot_gw;
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        const float excl = (float)(excl_lane + incl[k] - x[k]);
+        const float T = expf(-excl), e = expf(-dd[k]);
+        float w = __fmul_rn(__fsub_rn(1.f, e), T);
+        const bool ok = isfinite(w);
+        if (!ok) w = 0.f;  // nan_to_num zeroes the gradient path of non-finite weights
+        gw[k] = j0 + k < S ? (double)(g[k] * w) : 0.0;
+        first[k] = ok ? g[k] * T * e : 0.f;
+    }
+    lane_block_scan<C>(gw, lane, incl_gw, excl_gw, tot_gw);
+    float out[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        const double suffix = tot_gw - (excl_gw + incl_gw[k]);  // sum_{k' > i} g_k' w_k'
+        out[k] = delta[k] * (first[k] - (float)suffix);
+    }
+    float* dp = ddensity + r * S;
+    if (C % 4 == 0 && j0 + C <= S && (reinterpret_cast<uintptr_t>(dp) & 15) == 0) {
+#pragma unroll
+        for (int k = 0; k < C; k += 4) *reinterpret_cast<float4*>(dp + j0 + k) = make_float4(out[k], out[k + 1], out[k + 2], out[k + 3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < C; ++k)
+            if (j0 + k < S) dp[j0 + k] = out[k];
+    }
+}
+
 // ---- PDF resampling -------------------------------------------------------------------------------------------
 // smem per warp: cdf[S_in+1], bins[S_in+1]
+template <int C>
 __global__ void __launch_bounds__(32 * RAYS_PER_BLOCK) k_pdf_resample(int64_t B, int S_in, int S_out, const float* __restrict__ weights,
                                                                       const float* __restrict__ sdist_in, const float* __restrict__ u_base,
                                                                       const float* __restrict__ jitter, float anneal, const float* __restrict__ anneal_dev, float pad,
@@ -164,40 +268,77 @@ __global__ void __launch_bounds__(32 * RAYS_PER_BLOCK) k_pdf_resample(int64_t B,
     w_sum = __fadd_rn(w_sum, padding);
     __syncwarp();
     // pass 2: pdf = w / sum ; cdf = min(1, cumsum(pdf)) ; cdf = [0, cdf]
-    double carry = 0.0;
-    for (int c0 = 0; c0 < S_in; c0 += 32) {
-        const int i = c0 + lane;
-        float pdf = 0.f;
-        if (i < S_in) pdf = __fdiv_rn(__fadd_rn(cdf[i + 1], pad_each), w_sum);
-        const double incl = nvo_warp_scan_incl((double)pdf, lane);
-        if (i < S_in) cdf[i + 1] = fminf(1.f, (float)(carry + incl));
-        carry += __shfl_sync(0xffffffffu, incl, 31);
+    if (C > 0) {  // lane-blocked cumsum (C = ceil(S_in / 32) samples per lane), see lane_block_scan
+        constexpr int CC = C > 0 ? C : 1;
+        double x[CC], incl[CC], excl_lane, total;
+#pragma unroll
+        for (int k = 0; k < CC; ++k) {
+            const int i = CC * lane + k;
+            x[k] = i < S_in ? (double)__fdiv_rn(__fadd_rn(cdf[i + 1], pad_each), w_sum) : 0.0;
+        }
+        __syncwarp();
+        lane_block_scan<CC>(x, lane, incl, excl_lane, total);
+#pragma unroll
+        for (int k = 0; k < CC; ++k) {
+            const int i = CC * lane + k;
+            if (i < S_in) cdf[i + 1] = fminf(1.f, (float)(excl_lane + incl[k]));
+        }
+    } else {
+        double carry = 0.0;
+        for (int c0 = 0; c0 < S_in; c0 += 32) {
+            const int i = c0 + lane;
+            float pdf = 0.f;
+            if (i < S_in) pdf = __fdiv_rn(__fadd_rn(cdf[i + 1], pad_each), w_sum);
+            const double incl = nvo_warp_scan_incl((double)pdf, lane);
+            if (i < S_in) cdf[i + 1] = fminf(1.f, (float)(carry + incl));
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
     }
     if (lane == 0) cdf[0] = 0.f;
     __syncwarp();
     const float s_near = spacing_fn(__ldg(nears + r)), s_far = spacing_fn(__ldg(fars + r));
     const float jit = jitter ? __fdiv_rn(__ldg(jitter + r), (float)n_out) : 0.f;
-    for (int k = lane; k < n_out; k += 32) {
-        const float u = jitter ? __fadd_rn(__ldg(u_base + k), jit) : __ldg(u_base + k);
-        // searchsorted(cdf, u, side="right"): number of entries <= u
-        int lo = 0, hi = n_in;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (cdf[mid] <= u)
-                lo = mid + 1;
-            else
-                hi = mid;
+    // four output samples per lane and trip: their binary searches advance together (independent chains hide the shared-memory latency)
+    int iters = 0;
+    while ((1 << iters) < n_in + 1) ++iters;
+    for (int k0 = lane; k0 < n_out; k0 += 128) {
+        float u[4];
+        int lo[4], hi[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = k0 + 32 * q;
+            const bool act = k < n_out;
+            u[q] = act ? (jitter ? __fadd_rn(__ldg(u_base + k), jit) : __ldg(u_base + k)) : 0.f;
+            lo[q] = 0, hi[q] = act ? n_in : 0;
         }
-        const int ind = lo;
-        if (inds_out) inds_out[r * n_out + k] = ind;
-        const int below = min(max(ind - 1, 0), S_in), above = min(max(ind, 0), S_in);
-        const float c0 = cdf[below], c1 = cdf[above], b0 = bins[below], b1 = bins[above];
-        float t = __fdiv_rn(__fsub_rn(u, c0), __fsub_rn(c1, c0));
-        t = nan_to_num(t);
-        t = fminf(fmaxf(t, 0.f), 1.f);
-        const float b = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
-        sdist_out[r * n_out + k] = b;
-        ebins_out[r * n_out + k] = to_euclid(b, s_near, s_far);
+        // searchsorted(cdf, u, side="right"): number of entries <= u
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (lo[q] < hi[q]) {
+                    const int mid = (lo[q] + hi[q]) >> 1;
+                    if (cdf[mid] <= u[q])
+                        lo[q] = mid + 1;
+                    else
+                        hi[q] = mid;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = k0 + 32 * q;
+            if (k >= n_out) continue;
+            const int ind = lo[q];
+            if (inds_out) inds_out[r * n_out + k] = ind;
+            const int below = min(max(ind - 1, 0), S_in), above = min(max(ind, 0), S_in);
+            const float c0 = cdf[below], c1 = cdf[above], b0 = bins[below], b1 = bins[above];
+            float t = __fdiv_rn(__fsub_rn(u[q], c0), __fsub_rn(c1, c0));
+            t = nan_to_num(t);
+            t = fminf(fmaxf(t, 0.f), 1.f);
+            const float b = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+            sdist_out[r * n_out + k] = b;
+            ebins_out[r * n_out + k] = to_euclid(b, s_near, s_far);
+        }
     }
 }
 
@@ -441,7 +582,14 @@ extern "C" int nvo_weights_forward(void* stream, int64_t B, int32_t S, const flo
     NVO_CHECK(B >= 0 && S >= 1, "weights_forward: bad shape");
     if (B == 0) return 0;
     NVO_CHECK(starts && ends && density && weights, "weights_forward: null pointer");
-    k_weights_fwd<<<ray_blocks(B), 32 * RAYS_PER_BLOCK, 0, (cudaStream_t)stream>>>(B, S, starts, ends, stride, density, weights);
+    static const int lb = nvo_env_int("NVO_RAYS_LANE_BLOCKED", 1);
+    const int c = lb ? (S + 31) / 32 : 0;
+    if (c == 8)
+        k_weights_fwd_lb<8><<<ray_blocks(B), 32 * RAYS_PER_BLOCK, 0, (cudaStream_t)stream>>>(B, S, starts, ends, stride, density, weights);
+    else if (c == 3)
+        k_weights_fwd_lb<3><<<ray_blocks(B), 32 * RAYS_PER_BLOCK, 0, (cudaStream_t)stream>>>(B, S, starts, ends, stride, density, weights);
+    else
+        k_weights_fwd<<<ray_blocks(B), 32 * RAYS_PER_BLOCK, 0, (cudaStream_t)stream>>>(B, S, starts, ends, stride, density, weights);
     NVO_CUDA_LAUNCH_CHECK("weights_forward");
     return 0;
 }
@@ -451,7 +599,14 @@ extern "C" int nvo_weights_backward(void* stream, int64_t B, int32_t S, const fl
     NVO_CHECK(B >= 0 && S >= 1, "weights_backward: bad shape");
     if (B == 0) return 0;
     NVO_CHECK(starts && ends && density && dweights && ddensity, "weights_backward: null pointer");
-    k_weights_bwd<<<ray_blocks(B), 32 * RAYS_PER_BLOCK, 0, (cudaStream_t)stream>>>(B, S, starts, ends, stride, density, dweights, ddensity);
+    static const int lb = nvo_env_int("NVO_RAYS_LANE_BLOCKED", 1);
+    const int c = lb ? (S + 31) / 32 : 0;
+    if (c == 8)
+        k_weights_bwd_lb<8><<<ray_blocks(B), 32 * RAYS_PER_BLOCK, 0, (cudaStream_t)stream>>>(B, S, starts, ends, stride, density, dweights, ddensity);
+    else if (c == 3)
+        k_weights_bwd_lb<3><<<ray_blocks(B), 32 * RAYS_PER_BLOCK, 0, (cudaStream_t)stream>>>(B, S, starts, ends, stride, density, dweights, ddensity);
+    else
+        k_weights_bwd<<<ray_blocks(B), 32 * RAYS_PER_BLOCK, 0, (cudaStream_t)stream>>>(B, S, starts, ends, stride, density, dweights, ddensity);
     NVO_CUDA_LAUNCH_CHECK("weights_backward");
     return 0;
 }
@@ -463,8 +618,17 @@ extern "C" int nvo_pdf_resample(void* stream, int64_t B, int32_t S_in, int32_t S
     if (B == 0) return 0;
     NVO_CHECK(weights && sdist_in && u_base && nears && fars && sdist_out && ebins_out, "pdf_resample: null pointer");
     const size_t smem = sizeof(float) * 2 * (S_in + 1) * RAYS_PER_BLOCK;
-    k_pdf_resample<<<ray_blocks(B), 32 * RAYS_PER_BLOCK, smem, (cudaStream_t)stream>>>(B, S_in, S_out, weights, sdist_in, u_base, jitter, anneal,
-                                                                                       anneal_dev, histogram_padding, nears, fars, sdist_out, ebins_out, inds);
+    static const int lb = nvo_env_int("NVO_RAYS_LANE_BLOCKED", 1);
+    const int c = lb ? (S_in + 31) / 32 : 0;
+    if (c == 8)
+        k_pdf_resample<8><<<ray_blocks(B), 32 * RAYS_PER_BLOCK, smem, (cudaStream_t)stream>>>(B, S_in, S_out, weights, sdist_in, u_base, jitter, anneal, anneal_dev,
+                                                                                              histogram_padding, nears, fars, sdist_out, ebins_out, inds);
+    else if (c == 3)
+        k_pdf_resample<3><<<ray_blocks(B), 32 * RAYS_PER_BLOCK, smem, (cudaStream_t)stream>>>(B, S_in, S_out, weights, sdist_in, u_base, jitter, anneal, anneal_dev,
+                                                                                              histogram_padding, nears, fars, sdist_out, ebins_out, inds);
+    else
+        k_pdf_resample<0><<<ray_blocks(B), 32 * RAYS_PER_BLOCK, smem, (cudaStream_t)stream>>>(B, S_in, S_out, weights, sdist_in, u_base, jitter, anneal, anneal_dev,
+                                                                                              histogram_padding, nears, fars, sdist_out, ebins_out, inds);
     NVO_CUDA_LAUNCH_CHECK("pdf_resample");
     return 0;
 }

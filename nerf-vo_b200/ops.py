@@ -1542,8 +1542,10 @@ class _FieldFused(torch.autograd.Function):
         want_pn = len(pn_params) > 0
         origins = check(origins.contiguous(), "origins", torch.float32, (B, 3))
         directions = check(directions.contiguous(), "directions", torch.float32, (B, 3))
-        positions = sample_positions(origins, directions, iv).reshape(-1, 3)
-        x, selector = contract_normalize(positions)
+        positions = torch.empty((n, 3), dtype=torch.float32, device=origins.device)
+        x, selector = torch.empty_like(positions), torch.empty(n, dtype=torch.float32, device=origins.device)
+        s_, e_, stride_ = iv.triple()
+        call("nvo_sample_positions_contract", B, S, origins, directions, s_, e_, stride_, positions, x, selector)
         need = any(ctx.needs_input_grad)
         want_ray_grads = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or (ray_grad_sink is not None and need)
         if want_normals or want_ray_grads:

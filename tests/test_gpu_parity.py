@@ -712,3 +712,23 @@ def test_step_losses_lane_blocked_levels_match_per_loss_kernels(nv, sizes):
     assert torch.allclose(te0, te1, rtol=2e-6, atol=1e-12), (te0, te1)
     for a, b in zip(g0, g1):
         assert rel_err(b, a) < 1e-5, rel_err(b, a)
+
+
+def test_sample_positions_contract_equals_the_two_kernels(nv):
+    """nvo_sample_positions_contract (the fused field forward's first launch) is bit-identical to nvo_sample_positions + nvo_contract_forward,
+    inside and outside the unit box, ragged size."""
+    from nerf_vo_b200._lib import call
+
+    B, S = 1031, 48
+    g = torch.Generator().manual_seed(3)
+    o = (torch.randn(B, 3, generator=g) * 0.7).to(DEV)
+    d = torch.nn.functional.normalize(torch.randn(B, 3, generator=g), dim=-1).to(DEV)
+    e = (0.05 + torch.sort(torch.rand(B, S + 1, generator=g) * 6.0, dim=-1).values).to(DEV).contiguous()
+    iv = nv.ops.Intervals(ebins=e)
+    pos_ref = nv.ops.sample_positions(o, d, iv).reshape(-1, 3)
+    x_ref, sel_ref = nv.ops.contract_normalize(pos_ref)
+    pos, x, sel = torch.empty_like(pos_ref), torch.empty_like(x_ref), torch.empty_like(sel_ref)
+    s_, e_, stride = iv.triple()
+    call("nvo_sample_positions_contract", B, S, o, d, s_, e_, stride, pos, x, sel)
+    assert torch.equal(pos, pos_ref) and torch.equal(x, x_ref) and torch.equal(sel, sel_ref)
+    assert 0 < float(sel.mean()) <= 1 and float((pos_ref.abs().amax(-1) > 1).float().mean()) > 0.1  # both branches of the contraction ran
