@@ -26,10 +26,24 @@ __device__ unsigned long long* g_ft_timing = nullptr;  // [2 threads][FT_MAX_MAR
         if (blockIdx.x == 0 && g == 0 && (tid == 0 || tid == 128) && g_ft_timing && ft_mark < FT_MAX_MARKS)    \
             g_ft_timing[(tid >> 7) * FT_MAX_MARKS + ft_mark++] = clock64();                                    \
     } while (0)
+// backward: [0] = group 0's thread 0, [1] = the issuer's lane 0 (events of group 0), CTA 0
+__device__ unsigned long long* g_fb_timing = nullptr;  // [2][FT_MAX_MARKS]
+__device__ int g_fb_skip = 0;  // timing experiments only (results are wrong): bit 0 = no wgrad MMAs, bit 1 = no dgrad MMAs, bit 2 = no slot copies after the first two
+#define FB_SKIP(bit) ((g_fb_skip >> (bit)) & 1)
+// `fbt` = g_fb_timing read ONCE at kernel start: a mark is a clock read and a fire-and-forget store (re-reading the pointer from global memory
+// at every mark put an L2 round trip, 500+ cycles, into the issuer's serial path and into the numbers)
+#define FB_MARK(who, idx)                                                                \
+    do {                                                                                 \
+        if (fbt && (idx) < FT_MAX_MARKS) fbt[(who) * FT_MAX_MARKS + (idx)++] = clock64(); \
+    } while (0)
 #else
 #define FT_MARK() \
     do {          \
     } while (0)
+#define FB_MARK(who, idx) \
+    do {                  \
+    } while (0)
+#define FB_SKIP(bit) 0
 #endif
 
 #define FT_THREADS 256       // per tile group: warp w reads TMEM lanes 32 * (w & 3) .. (rows of the tile) and the column half (w >> 2)
@@ -294,17 +308,18 @@ __global__ void __launch_bounds__(G* FT_THREADS, 1) k_field_fwd(const __grid_con
 #ifdef NVO_FT_TIMING
     int ft_mark = 0;
 #endif
-#define FT_ISSUE(step)                                                       \
-    if (tid == 0) {                                                          \
-        tc_fence_after();                                                    \
-        if (g == 0)                                                          \
-            ft_issue<G, 0>(step, uBase, p.want_normals, p.want_pn);          \
-        else if (G > 1 && g == 1)                                            \
-            ft_issue<G, (G > 1 ? 1 : 0)>(step, uBase, p.want_normals, p.want_pn); \
-        else if (G > 2)                                                      \
-            ft_issue<G, (G > 2 ? 2 : 0)>(step, uBase, p.want_normals, p.want_pn); \
-    }                                                                        \
-    __syncwarp();
+#define FT_ISSUE(step)                                                           \
+    if (warp == 0) { /* warp-uniform; the group's first warp is converged here */ \
+        tc_fence_after();                                                        \
+        if (g == 0) {                                                            \
+            if (elect_one()) ft_issue<G, 0>(step, uBase, p.want_normals, p.want_pn); \
+        } else if (G > 1 && g == 1) {                                            \
+            if (elect_one()) ft_issue<G, (G > 1 ? 1 : 0)>(step, uBase, p.want_normals, p.want_pn); \
+        } else if (G > 2) {                                                      \
+            if (elect_one()) ft_issue<G, (G > 2 ? 2 : 0)>(step, uBase, p.want_normals, p.want_pn); \
+        }                                                                        \
+        __syncwarp();                                                            \
+    }
 #define FT_COMMIT_WAIT()                   \
     FT_MARK();                             \
     mbar_wait(mbar_mma, ph);               \
@@ -375,9 +390,12 @@ __global__ void __launch_bounds__(G* FT_THREADS, 1) k_field_fwd(const __grid_con
         group_sync(g);
         // the feature tile has been consumed (S0's MMA retired) and every thread of the group is past this tile's wait on mbar_in (the barrier
         // above) — only now may the barrier's next phase start: a thread still to make that wait would otherwise see the parity wrap around
-        if (tid == 0 && tile + stride < n_tiles) {
-            mbar_expect_tx(mbar_in, 4 * CHUNK_B);
-            bulk_g2s(sFI, p.feat16 + (tile + stride) * (4 * CHUNK_B), 4 * CHUNK_B, mbar_in);
+        if (warp == 0 && tile + stride < n_tiles) {
+            if (elect_one()) {
+                mbar_expect_tx(mbar_in, 4 * CHUNK_B);
+                bulk_g2s(sFI, p.feat16 + (tile + stride) * (4 * CHUNK_B), 4 * CHUNK_B, mbar_in);
+            }
+            __syncwarp();
         }
         // ---- S1: mlp_base layer 1 (16 outputs) + the normals chain's input-gradient product (32 feature columns, accN) ----------------------
         FT_ISSUE(1);
@@ -691,6 +709,7 @@ struct FieldBwdP {
     const float* dirs;            // [B,3] ray directions (with ddirs)
     float* ddirs;                 // [B,3] d loss / d ray direction through the SH encoding, accumulated (atomics); nullable
     int l2_prefetch;              // prefetch the next tile's saved activations into L2 (NVO_FIELD_BWD_PREFETCH, default 1)
+    int wait_hint_ns;             // suspend-time hint of the groups' wait for their MMAs (NVO_FIELD_BWD_WAIT_NS; 0 = plain try_wait loop)
 };
 
 __device__ __forceinline__ float ft_grad_scale(float mx) {
@@ -798,46 +817,76 @@ __device__ __forceinline__ void issue_wgrad_rel(uint32_t tmem_d, uint32_t base16
         umma_f16(tmem_d, umma_desc_rel(base16, act_off + k * 256, 128, CHUNK_B), umma_desc_rel(base16, dz_off + k * 256, 128, CHUNK_B), idesc, k > 0 ? 1u : accumulate);
 }
 #define BW_MBAR_OFF(G) (BW_GROUPS_OFF + ((G) * BW_GROUP_CHUNKS + 2) * CHUNK_B)
+// One step's MMAs + commit with the step TS a compile-time constant as well (the static issue schedule of k_field_bwd): no switch, the
+// elected lane's instruction stream is the uniform-register descriptor adds and the tcgen05.mma themselves.
+template <int G, int GI, int SL, int TS>
+__device__ __forceinline__ void fb_issue_s(uint32_t uBase, uint32_t started) {
+    const uint32_t b16 = (uBase & 0x3FFFFu) >> 4;
+    constexpr uint32_t oG = BW_GROUPS_OFF + GI * BW_GROUP_CHUNKS * CHUNK_B, oSlot = oG + SL * BW_SLOT_CHUNKS * CHUNK_B;
+    constexpr uint32_t oG64 = oG + 2 * BW_SLOT_CHUNKS * CHUNK_B, oG16 = oG64 + 8 * CHUNK_B;
+    constexpr uint32_t acc = DW_ACC + 64 * GI;
+    if (elect_one()) {
+        if constexpr (TS == 0) {  // head layer 2: dA2 = dz3 W2 ; dW2^T += AH2_ext^T dz3
+            if (!FB_SKIP(1)) issue_layer_rel(acc, b16, oG16, 1, FB_H2T, 64, false);
+            if (!FB_SKIP(0)) issue_wgrad_rel(DW_H2T, b16, oSlot, oG16, 16, started);
+        } else if constexpr (TS == 1) {  // head layer 1
+            if (!FB_SKIP(1)) issue_layer_rel(acc, b16, oG64, 4, FB_H1T, 64, false);
+            if (!FB_SKIP(0)) issue_wgrad_rel(DW_H1T, b16, oSlot, oG64, 64, started);
+        } else if constexpr (TS == 2) {  // head layer 0: dX ; dW0^T += X^T dZ1 (the bias is X's constant column 63)
+            if (!FB_SKIP(1)) issue_layer_rel(acc, b16, oG64, 4, FB_H0T, 64, false);
+            if (!FB_SKIP(0)) issue_wgrad_rel(DW_H0T, b16, oSlot, oG64, 64, started);
+        } else if constexpr (TS == 3) {  // base layer 1
+            if (!FB_SKIP(1)) issue_layer_rel(acc, b16, oG16, 1, FB_B1T, 64, false);
+            if (!FB_SKIP(0)) issue_wgrad_rel(DW_B1T, b16, oSlot, oG16, 16, started);
+        } else {  // base layer 0: d features (32 columns); the feature tile sits in the slot's upper half
+            if (!FB_SKIP(1)) issue_layer_rel(acc, b16, oG64, 4, FB_B0T, 32, false);
+            if (!FB_SKIP(0)) issue_wgrad_rel(DW_B0T, b16, oSlot + 4 * CHUNK_B, oG64, 64, started);
+        }
+        umma_commit_u32(uBase + BW_MBAR_OFF(G) + 8 * (1 + G + GI));
+    }
+    __syncwarp();
+}
+
 template <int G, int GI, int SL>
 __device__ __forceinline__ void fb_issue(int ts, uint32_t uBase, uint32_t started, int lane) {
     const uint32_t b16 = (uBase & 0x3FFFFu) >> 4;
     constexpr uint32_t oG = BW_GROUPS_OFF + GI * BW_GROUP_CHUNKS * CHUNK_B, oSlot = oG + SL * BW_SLOT_CHUNKS * CHUNK_B;
     constexpr uint32_t oG64 = oG + 2 * BW_SLOT_CHUNKS * CHUNK_B, oG16 = oG64 + 8 * CHUNK_B;
     constexpr uint32_t acc = DW_ACC + 64 * GI;
-    // `ts` is warp-uniform: a uniform switch, then lane 0 alone issues the step's MMAs and the commit
+    // `ts` is warp-uniform: a uniform switch, then the elected lane alone issues the step's MMAs and the commit
     switch (ts) {
         case 0:  // head layer 2: dA2 = dz3 W2 ; dW2^T += AH2_ext^T dz3
-            if (lane == 0) {
-                issue_layer_rel(acc, b16, oG16, 1, FB_H2T, 64, false);
-                issue_wgrad_rel(DW_H2T, b16, oSlot, oG16, 16, started);
+            if (elect_one()) {
+                if (!FB_SKIP(1)) issue_layer_rel(acc, b16, oG16, 1, FB_H2T, 64, false);
+                if (!FB_SKIP(0)) issue_wgrad_rel(DW_H2T, b16, oSlot, oG16, 16, started);
                 umma_commit_u32(uBase + BW_MBAR_OFF(G) + 8 * (1 + G + GI));
             }
             break;
         case 1:  // head layer 1
-            if (lane == 0) {
-                issue_layer_rel(acc, b16, oG64, 4, FB_H1T, 64, false);
-                issue_wgrad_rel(DW_H1T, b16, oSlot, oG64, 64, started);
+            if (elect_one()) {
+                if (!FB_SKIP(1)) issue_layer_rel(acc, b16, oG64, 4, FB_H1T, 64, false);
+                if (!FB_SKIP(0)) issue_wgrad_rel(DW_H1T, b16, oSlot, oG64, 64, started);
                 umma_commit_u32(uBase + BW_MBAR_OFF(G) + 8 * (1 + G + GI));
             }
             break;
         case 2:  // head layer 0: dX ; dW0^T += X^T dZ1 (the bias is X's constant column 63)
-            if (lane == 0) {
-                issue_layer_rel(acc, b16, oG64, 4, FB_H0T, 64, false);
-                issue_wgrad_rel(DW_H0T, b16, oSlot, oG64, 64, started);
+            if (elect_one()) {
+                if (!FB_SKIP(1)) issue_layer_rel(acc, b16, oG64, 4, FB_H0T, 64, false);
+                if (!FB_SKIP(0)) issue_wgrad_rel(DW_H0T, b16, oSlot, oG64, 64, started);
                 umma_commit_u32(uBase + BW_MBAR_OFF(G) + 8 * (1 + G + GI));
             }
             break;
         case 3:  // base layer 1
-            if (lane == 0) {
-                issue_layer_rel(acc, b16, oG16, 1, FB_B1T, 64, false);
-                issue_wgrad_rel(DW_B1T, b16, oSlot, oG16, 16, started);
+            if (elect_one()) {
+                if (!FB_SKIP(1)) issue_layer_rel(acc, b16, oG16, 1, FB_B1T, 64, false);
+                if (!FB_SKIP(0)) issue_wgrad_rel(DW_B1T, b16, oSlot, oG16, 16, started);
                 umma_commit_u32(uBase + BW_MBAR_OFF(G) + 8 * (1 + G + GI));
             }
             break;
         default:  // base layer 0: d features (32 columns); the feature tile sits in the slot's upper half
-            if (lane == 0) {
-                issue_layer_rel(acc, b16, oG64, 4, FB_B0T, 32, false);
-                issue_wgrad_rel(DW_B0T, b16, oSlot + 4 * CHUNK_B, oG64, 64, started);
+            if (elect_one()) {
+                if (!FB_SKIP(1)) issue_layer_rel(acc, b16, oG64, 4, FB_B0T, 32, false);
+                if (!FB_SKIP(0)) issue_wgrad_rel(DW_B0T, b16, oSlot + 4 * CHUNK_B, oG64, 64, started);
                 umma_commit_u32(uBase + BW_MBAR_OFF(G) + 8 * (1 + G + GI));
             }
             break;
@@ -845,7 +894,7 @@ __device__ __forceinline__ void fb_issue(int ts, uint32_t uBase, uint32_t starte
     __syncwarp();
 }
 
-template <int G>
+template <int G, bool STATIC>
 __global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __grid_constant__ FieldBwdP p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int NEPI = G * FT_THREADS;
@@ -895,6 +944,9 @@ __global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __gri
     tc_fence_after();
     const uint32_t tmem0 = *tmem_ptr;
     if (tmem0 != 0u) __trap();  // all 512 columns: the allocation can only start at column 0 (fb_issue relies on it)
+#ifdef NVO_FT_TIMING
+    unsigned long long* const fbt = blockIdx.x == 0 ? g_fb_timing : nullptr;
+#endif
     const float mx_h = __ldg(p.absmax), mx_d = __ldg(p.absmax + 1);
     const float s_h = ft_grad_scale(mx_h), s_b = ft_grad_scale(fmaxf(mx_d, 4.f * mx_h));
     const float inv_s_h = 1.f / s_h, inv_s_b = 1.f / s_b, s_bh = s_b * inv_s_h;
@@ -912,8 +964,29 @@ __global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __gri
         uint32_t rph[G], lph[G][2];
         int dw_started = 0;  // bit l: layer l's weight-gradient accumulator has been written once
         int active = 0;
+#ifdef NVO_FT_TIMING
+        int fb_mi = 0;
+#endif
         const bool l2_prefetch = p.l2_prefetch != 0;
-        auto load = [&](int gg, int qq) {  // lane 0 only
+        auto load_s = [&](int gg, int ts, int sl, int64_t tile_local) {  // the elected lane only; gg, ts, sl are constants at the call sites
+            const int64_t tile = (int64_t)blockIdx.x * G + gg + tile_local * stride;
+            unsigned char* slot = smem + BW_GROUPS_OFF + gg * BW_GROUP_CHUNKS * CHUNK_B + sl * BW_SLOT_CHUNKS * CHUNK_B;
+            uint64_t* mb = mbar_load + 2 * gg + sl;
+            const unsigned char* sv = p.saved + tile * saved_tile_bytes;
+            if (ts == 0 && tile + stride < n_tiles && l2_prefetch) {
+                bulk_prefetch_l2(p.saved + (tile + stride) * saved_tile_bytes, FS_CHUNKS_HEAD * CHUNK_B);
+                bulk_prefetch_l2(p.feat16 + (tile + stride) * (4 * CHUNK_B), 4 * CHUNK_B);
+            }
+            if (ts == 4) {
+                mbar_expect_tx(mb, 4 * CHUNK_B);
+                bulk_g2s(slot + 4 * CHUNK_B, p.feat16 + tile * (4 * CHUNK_B), 4 * CHUNK_B, mb);
+            } else {
+                const int ch = ts == 0 ? FS_AH2 : ts == 1 ? FS_AH1 : ts == 2 ? FS_X : FS_H1;
+                mbar_expect_tx(mb, 8 * CHUNK_B);
+                bulk_g2s(slot, sv + ch * CHUNK_B, 8 * CHUNK_B, mb);
+            }
+        };
+        auto load = [&](int gg, int qq) {  // the elected lane only
             const int ts = qq % 5;
             const int64_t tile = (int64_t)blockIdx.x * G + gg + (int64_t)(qq / 5) * stride;
             unsigned char* slot = smem + BW_GROUPS_OFF + gg * BW_GROUP_CHUNKS * CHUNK_B + (qq & 1) * BW_SLOT_CHUNKS * CHUNK_B;
@@ -949,6 +1022,41 @@ __global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __gri
             }
         }
         mbar_wait(mbar_w, 0);
+        if constexpr (STATIC) {
+            // ---- static schedule (default): the groups are served round-robin in a fixed order, one step each — two tiles (10 steps) per
+            // iteration, so the step, the slot and the `ready` parity of every block below are compile-time constants and a block is: two
+            // mbarrier waits, one bulk-copy request, the MMAs, the commit.  The polling loop of the dynamic schedule (any ready group, run-time
+            // step) cost the issuing warp 150-200 scalar instructions per step next to 24 epilogue warps — 900-1300 cycles against 450 for the
+            // step's MMAs (tools/field_timing.cu, profiles/r02_field_bwd_phase_timing.log) — and that warp serialises the three groups.
+            int64_t tiles_g[G];
+            int64_t tiles_max = 0;
+#pragma unroll
+            for (int gg = 0; gg < G; ++gg) tiles_g[gg] = total_q[gg] / 5, tiles_max = tiles_g[gg] > tiles_max ? tiles_g[gg] : tiles_max;
+            uint32_t lbits = 0;  // bit 2 gg + sl: phase parity of the slot's load barrier
+            for (int64_t it = 0; it < tiles_max; it += 2) {
+#define FB_BLOCK(GI, U)                                                                                                              \
+    if (GI < G && it + ((U) >= 5) < tiles_g[GI < G ? GI : 0]) {                                                                          \
+        constexpr int gi = GI < G ? GI : 0, sl = (U) & 1, ts = (U) % 5;                                                                \
+        mbar_wait(mbar_ready + gi, (uint32_t)sl);                                                                                     \
+        mbar_wait(mbar_load + 2 * gi + sl, (lbits >> (2 * gi + sl)) & 1u);                                                            \
+        lbits ^= 1u << (2 * gi + sl);                                                                                                 \
+        if (gi == 0 && lane == 0) FB_MARK(1, fb_mi);                                                                                  \
+        const int64_t tl = it + ((U) >= 5);                                /* this step's tile of the group */                         \
+        if ((it > 0 || (U) > 0) && (ts < 4 || tl + 1 < tiles_g[gi])) {     /* step q + 1 exists, and is not one of the two preloaded */ \
+            if (elect_one()) load_s(gi, (ts + 1) % 5, sl ^ 1, tl + (ts == 4));                                                        \
+            __syncwarp();                                                                                                             \
+        }                                                                                                                             \
+        if (gi == 0 && lane == 0) FB_MARK(1, fb_mi);                                                                                  \
+        tc_fence_after();                                                                                                             \
+        fb_issue_s<G, gi, sl, ts>(uBase, (it > 0 || (U) >= 5 || gi > 0) ? 1u : 0u);                                                    \
+        if (gi == 0 && lane == 0) FB_MARK(1, fb_mi);                                                                                  \
+    }
+#define FB_ROUND(U) FB_BLOCK(0, U) FB_BLOCK(1, U) FB_BLOCK(2, U)
+                FB_ROUND(0) FB_ROUND(1) FB_ROUND(2) FB_ROUND(3) FB_ROUND(4) FB_ROUND(5) FB_ROUND(6) FB_ROUND(7) FB_ROUND(8) FB_ROUND(9)
+#undef FB_ROUND
+#undef FB_BLOCK
+            }
+        } else
         while (active) {
 #pragma unroll
             for (int gg = 0; gg < G; ++gg) {
@@ -958,7 +1066,12 @@ __global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __gri
                 const bool go = mbar_test(mbar_ready + gg, rph[gg]) && mbar_test(mbar_load + 2 * gg + sl, lph[gg][sl]);
                 if (!__all_sync(0xffffffffu, go)) continue;
                 rph[gg] ^= 1, lph[gg][sl] ^= 1;
-                if (lane == 0 && qq >= 1 && qq + 1 < total_q[gg]) load(gg, qq + 1);  // slot (qq+1)&1: its readers (step qq-1) are finished
+                if (gg == 0 && lane == 0) FB_MARK(1, fb_mi);
+                if (qq >= 1 && qq + 1 < total_q[gg]) {  // slot (qq+1)&1: its readers (step qq-1) are finished
+                    if (elect_one()) load(gg, qq + 1);
+                    __syncwarp();
+                }
+                if (gg == 0 && lane == 0) FB_MARK(1, fb_mi);
                 tc_fence_after();
                 const int ts = qq % 5;
                 const uint32_t started = (dw_started >> ts) & 1;
@@ -976,6 +1089,7 @@ __global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __gri
                 else if (G > 2)
                     FB_ISSUE((G > 2 ? 2 : 0));
 #undef FB_ISSUE
+                if (gg == 0 && lane == 0) FB_MARK(1, fb_mi);
                 dw_started |= 1 << ts;
                 q[gg] = qq + 1;
                 if (qq + 1 == total_q[gg]) active &= ~(1 << gg);
@@ -992,16 +1106,32 @@ __global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __gri
         uint64_t* done = mbar_done + g;
         uint32_t dph = 0;
         int q = 0;
+#ifdef NVO_FT_TIMING
+        int fb_mg = 0;
+        const bool fb_me = g == 0 && tid == 0;
+#endif
         auto arrive_ready = [&]() {
+#ifdef NVO_FT_TIMING
+            if (fb_me) FB_MARK(0, fb_mg);  // epilogue of the previous step done
+#endif
             fence_async_smem();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(ready);
+#ifdef NVO_FT_TIMING
+            if (fb_me) FB_MARK(0, fb_mg);  // arrived
+#endif
         };
         auto wait_done = [&]() {
-            mbar_wait(done, dph);
+            if (p.wait_hint_ns > 0)
+                mbar_wait_hint(done, dph, (uint32_t)p.wait_hint_ns);
+            else
+                mbar_wait(done, dph);
             dph ^= 1;
             tc_fence_after();
+#ifdef NVO_FT_TIMING
+            if (fb_me) FB_MARK(0, fb_mg);  // MMAs retired
+#endif
             mbar_wait(mbar_load + 2 * g + (q & 1), (uint32_t)((q >> 1) & 1));  // already complete (the issuer waited for it): orders the reads below
         };
         // dz of the colour output: drgb * sigmoid'(rgb) * scale -> G16 chunk 0 (outputs 0..2), chunk 1 = 0
@@ -1221,18 +1351,25 @@ extern "C" int nvo_field_backward(void* stream, int64_t B, int32_t S, const void
     p.dirs = directions, p.ddirs = ddirections;
     static const int l2_prefetch = nvo_env_int("NVO_FIELD_BWD_PREFETCH", 1);
     p.l2_prefetch = l2_prefetch;
+    static const int wait_ns = nvo_env_int("NVO_FIELD_BWD_WAIT_NS", 0);
+    p.wait_hint_ns = wait_ns;
     const int G = field_groups();
+    static const int static_issue = nvo_env_int("NVO_FIELD_BWD_STATIC", 1);  // 0 = the dynamic (poll any ready group) issue schedule, G = 3 only
     const size_t smem = BW_GROUPS_OFF + (size_t)(G * BW_GROUP_CHUNKS + 2) * CHUNK_B + 8 * (1 + 4 * G) + 16;
     const int64_t tiles = (n + TM - 1) / TM;
     const unsigned int grid = (unsigned int)min((int64_t)nvo_sm_count(), (tiles + G - 1) / G);
     if (G == 2) {
-        e = cudaFuncSetAttribute(k_field_bwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(k_field_bwd<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         NVO_CHECK(e == cudaSuccess, "field_backward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        k_field_bwd<2><<<grid, 2 * FT_THREADS + 32, smem, st>>>(p);
+        k_field_bwd<2, true><<<grid, 2 * FT_THREADS + 32, smem, st>>>(p);
+    } else if (static_issue) {
+        e = cudaFuncSetAttribute(k_field_bwd<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        NVO_CHECK(e == cudaSuccess, "field_backward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        k_field_bwd<3, true><<<grid, 3 * FT_THREADS + 32, smem, st>>>(p);
     } else {
-        e = cudaFuncSetAttribute(k_field_bwd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(k_field_bwd<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         NVO_CHECK(e == cudaSuccess, "field_backward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        k_field_bwd<3><<<grid, 3 * FT_THREADS + 32, smem, st>>>(p);
+        k_field_bwd<3, false><<<grid, 3 * FT_THREADS + 32, smem, st>>>(p);
     }
     NVO_CUDA_LAUNCH_CHECK("field_backward");
     return 0;

@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(NT) k_mlp_tc_fwd(const __grid_constant__ TcP p
         mbar_wait(mbar_in + buf, (uint32_t)((it >> 1) & 1));
         for (int l = 0; l < p.n_layers; ++l) {
             const int kp = p.kpad[l], np = p.npad[l];
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {  // elect.sync, not `tid == 0`: see elect_one() in tc_common.cuh
                 tc_fence_after();
                 const uint32_t idesc = umma_idesc(TM, np, 0, 0);
                 const uint32_t a0 = smem_u32(l == 0 ? sIn : sAct), b0 = smem_u32(sW + p.iw_off[l]);
@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(NT) k_mlp_tc_bwd(const __grid_constant__ TcP p
             unsigned char* sA = stage + p.a_off[l];                    // input activations of layer l (+ ones / zero chunks)
             const bool need_dgrad = l > 0 || dx != nullptr;
             mbar_wait(mbar_a + l, a_parity);  // this tile's input activations of layer l have landed (read by the wgrad MMAs and by the epilogue)
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 const uint32_t g0 = smem_u32(sG), a0 = smem_u32(sA), w0 = smem_u32(sW + p.iw_off[l]);
                 if (need_dgrad) {

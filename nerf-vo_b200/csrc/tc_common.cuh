@@ -27,6 +27,16 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Leader election for the single-thread instructions (tcgen05.mma / commit, bulk copies).  Call it from a CONVERGED warp, right at the use:
+// `if (elect_one()) { ... }`.  With `if (lane == 0)` ptxas cannot prove that one thread is active and wraps EVERY tcgen05.mma in an
+// ELECT / BRA.U.ANY loop behind R2UR moves (12 instructions, 125-165 cycles per MMA measured by tools/field_timing.cu); behind elect.sync
+// the MMAs are emitted back to back from uniform registers.  The same lane is elected every time for a given mask, so the MMAs of one
+// warp stay in issue order.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* mbar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
 }
@@ -40,6 +50,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
             : "=r"(done)
             : "r"(smem_u32(mbar)), "r"(parity)
+            : "memory");
+    }
+}
+// same wait with a suspend-time hint (ns): the thread sleeps in hardware until the phase completes or the hint elapses instead of re-issuing
+// try_wait back to back — the spinning of 24 epilogue warps otherwise takes issue slots from the one warp that issues the MMAs
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* mbar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(smem_u32(mbar)), "r"(parity), "r"(hint_ns)
             : "memory");
     }
 }

@@ -5,9 +5,12 @@ when the box has two GPUs — two ranks exchanging through NVLink peer memory ag
 import ctypes
 import os
 import socket
+import sys
 
 import pytest
 import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_slice_ranges_cover_the_flat_buffer_cpu():
@@ -139,3 +142,70 @@ def test_exchange_two_ranks_matches_nccl_arm(tmp_path):
     for r in range(2):
         out = torch.load(os.path.join(str(tmp_path), f"r{r}.pt"))
         assert out["ok"], (r, out)
+
+
+def _two_rank_trainer_worker(rank, world, port, tmp):
+    """16 steps of the mapping trainer on two ranks (fused peer-memory arm), undeferred and with defer_fields_update: replicas stay bit-identical,
+    the deferred run reproduces the undeferred loss trajectory and, after flush(), its parameter movement."""
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import nerfacto_oracle as O
+    import nerf_vo_b200 as nv
+    from nerf_vo_b200.trainer import MappingTrainer
+
+    K, B, STEPS = 8, 256, 16
+    rays, targets = O.synthetic_rays(B, num_images=K, seed=3 + rank)
+    jit = O.synthetic_jitters(B)
+    res = {}
+    for defer in (False, True):
+        torch.manual_seed(0)
+        cfg = nv.NerfactoModelConfig(log2_hashmap_size=14)
+        for a in cfg.proposal_net_args_list:
+            a["log2_hashmap_size"] = 12
+        model = nv.ExtendedNerfactoModel(cfg, num_train_data=K).to(dev)
+        tr = MappingTrainer(model, num_rays=B, lr=1e-2, eps=1e-15, use_cuda_graph=True, exchange="fused", defer_fields_update=defer)
+        init = tr.flat.detach().clone()
+        tr.capture(warmup=2)
+        tr.set_inputs({k: v.to(dev) for k, v in rays.items()}, {k: v.to(dev) for k, v in targets.items()}, [j.to(dev) for j in jit])
+        losses = [float(tr.train_step()) for _ in range(STEPS)]
+        tr.flush()
+        torch.cuda.synchronize()
+        dist.barrier()
+        flat = tr.flat.detach().clone()
+        other = flat.clone()
+        dist.broadcast(other, 0)
+        res[defer] = {"losses": losses, "move": (flat - init).double().cpu(), "replicas_equal": bool(torch.equal(other, flat)), "steps": [int(c) for c in tr.step_counts],
+                      "error_word": tr.peer.error_word()}
+        dist.barrier()
+    d0, d1 = res[False]["move"], res[True]["move"]
+    out = {"cos": float((d0 * d1).sum() / (d0.norm() * d1.norm())), "norm_rel": abs(float(d0.norm()) - float(d1.norm())) / float(d0.norm()),
+           "losses": (res[False]["losses"], res[True]["losses"]), "replicas_equal": (res[False]["replicas_equal"], res[True]["replicas_equal"]),
+           "steps": (res[False]["steps"], res[True]["steps"]), "error_words": (res[False]["error_word"], res[True]["error_word"])}
+    torch.save(out, os.path.join(tmp, f"t{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_two_rank_trainer_deferred_fields_update(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_two_rank_trainer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        out = torch.load(os.path.join(str(tmp_path), f"t{r}.pt"))
+        assert out["replicas_equal"] == (True, True), out["replicas_equal"]
+        assert out["error_words"] == (0, 0)
+        assert out["steps"][0] == out["steps"][1] == [16, 16], out["steps"]
+        assert out["losses"][1] == pytest.approx(out["losses"][0], rel=2e-3), out["losses"]
+        assert out["cos"] > 0.995 and out["norm_rel"] < 2e-2, (out["cos"], out["norm_rel"])

@@ -73,6 +73,50 @@ int main(int argc, char** argv) {
         cudaEventElapsedTime(&ms, e0, e1);
         printf("rep %d: %.1f us (B=%lld save=%d)\n", rep, ms * 1e3, (long long)B, save);
     }
+    // ---- backward: phase timestamps of group 0 and of the issuer's view of group 0 (needs the saved tiles of a forward with save=1) ----
+    if (save && argc > 3 && atoi(argv[3])) {
+        float *ddensity, *drgb, *scratch, *dfeat, *dbase, *dhead, *demb;
+        cudaMalloc(&ddensity, n * 4); cudaMalloc(&drgb, n * 12); cudaMalloc(&scratch, 8); cudaMalloc(&dfeat, tiles * 128 * 32 * 4);
+        cudaMalloc(&dbase, 4096 * 4); cudaMalloc(&dhead, 16384 * 4); cudaMalloc(&demb, 64 * 32 * 4);
+        fill_float<<<1024, 256>>>(ddensity, n, 1e-3f, 0.f, 11);
+        fill_float<<<1024, 256>>>(drgb, n * 3, 1e-3f, 0.f, 12);
+        cudaMemset(dbase, 0, 4096 * 4); cudaMemset(dhead, 0, 16384 * 4); cudaMemset(demb, 0, 64 * 32 * 4);
+        unsigned long long* tb;
+        cudaMalloc(&tb, 2 * FT_MAX_MARKS * 8);
+        cudaMemset(tb, 0, 2 * FT_MAX_MARKS * 8);
+        const int skip = argc > 4 ? atoi(argv[4]) : 0;
+        cudaMemcpyToSymbol(g_fb_skip, &skip, sizeof(skip));
+        if (skip) printf("TIMING EXPERIMENT: skip bits %d (results invalid)\n", skip);
+        for (int rep = 0; rep < 3; ++rep) {
+            unsigned long long* arg = rep == 2 ? tb : nullptr;
+            cudaMemcpyToSymbol(g_fb_timing, &arg, sizeof(arg));
+            cudaEventRecord(e0);
+            if (nvo_field_backward(0, B, S, feat, saved, 0, wimg, rgb, h0, sel, cam, ddensity, drgb, nullptr, scratch, dfeat, dbase, dhead, demb, nullptr, nullptr)) {
+                printf("backward: %s\n", nvo_last_error());
+                return 1;
+            }
+            cudaEventRecord(e1);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("sync: %s\n", cudaGetErrorString(e)); return 1; }
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            printf("backward rep %d: %.1f us (absmax pass included)\n", rep, ms * 1e3);
+        }
+        std::vector<unsigned long long> hb(2 * FT_MAX_MARKS);
+        cudaMemcpy(hb.data(), tb, hb.size() * 8, cudaMemcpyDeviceToHost);
+        const unsigned long long *gm = hb.data(), *im = hb.data() + FT_MAX_MARKS;
+        // group marks per step: epilogue-done, arrived, MMAs-retired; issuer marks per step: ready+load observed, slot copy requested, issued
+        const char* bs[5] = {"head L2", "head L1", "head L0", "base L1", "base L0"};
+        printf("---- backward, CTA 0 group 0: cycles per step\n");
+        for (int q = 0; q < 40 && gm[3 * q + 2] && im[3 * q + 2]; ++q) {
+            const unsigned long long epi_done = gm[3 * q], arrived = gm[3 * q + 1], retired = gm[3 * q + 2], seen = im[3 * q], loaded = im[3 * q + 1], issued = im[3 * q + 2];
+            const unsigned long long next = gm[3 * (q + 1)];
+            printf("  tile %d %-8s fence+arrive %5llu | issuer sees ready+load %6lld | copy req %5llu | issue %5llu | MMA + commit %5llu | epilogue %5llu | step total %6llu\n", q / 5,
+                   bs[q % 5], arrived - epi_done, (long long)(seen - arrived), loaded - seen, issued - loaded, retired - issued, next ? next - retired : 0ULL,
+                   next ? next - epi_done : 0ULL);
+        }
+        return 0;
+    }
     std::vector<unsigned long long> h(2 * FT_MAX_MARKS);
     cudaMemcpy(h.data(), tim, h.size() * 8, cudaMemcpyDeviceToHost);
     // marks per tile: [in-wait pre] then per step: commit-wait pre, post, sync pre, sync post

@@ -1,0 +1,14 @@
+#!/bin/bash
+# elect.sync MMA issue: phase timing of the backward, the field tests, the bench
+cd "$GRAFT_REPO_ROOT"
+mkdir -p gpurun_out
+timeout 120 tools/field_timing 4096 1 1 > gpurun_out/c31_bwd_timing.log 2>&1; grep "rep" gpurun_out/c31_bwd_timing.log; sed -n '/tile 1 head L2/,/tile 1 base L0/p' gpurun_out/c31_bwd_timing.log | cut -c1-200
+timeout 120 tools/field_timing 4096 1 0 > gpurun_out/c31_fwd_timing.log 2>&1; grep "rep" gpurun_out/c31_fwd_timing.log
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/c31_pytest.log 2>&1
+echo "rc=$?" >> gpurun_out/c31_pytest.log
+tail -4 gpurun_out/c31_pytest.log
+timeout 300 python bench.py --steps 200 --warmup 10 --no-cpu-baseline --no-schedule-leg > gpurun_out/c31_bench.json 2> gpurun_out/c31_bench.err
+python -c "
+import json
+d=json.load(open('gpurun_out/c31_bench.json')); print('bench', d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches_per_step'])
+for o in d['roofline']['others'][:4]: print('  ', o['kernel'][:60], round(o['launch_us'],1), round(o.get('frac'),4))"

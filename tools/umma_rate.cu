@@ -33,7 +33,8 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_
 // rotation, as the K steps of a layer do): the same-descriptor loops above may be served from an operand cache
 __global__ void __launch_bounds__(128) rate(int mode, int N, int R, int two_acc, long long* out) {
     extern __shared__ __align__(1024) unsigned char dyn[];
-    __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) uint64_t mbar, mbar2;
+    __shared__ volatile int stop;
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < 65536 / 4; i += 128) reinterpret_cast<uint32_t*>(dyn)[i] = 0x3C003C00u;
@@ -41,7 +42,11 @@ __global__ void __launch_bounds__(128) rate(int mode, int N, int R, int two_acc,
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)) : "memory");
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar2)) : "memory");
+        stop = 0;
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -54,11 +59,30 @@ __global__ void __launch_bounds__(128) rate(int mode, int N, int R, int two_acc,
         uint64_t ad, bd;
         if (mode == 0) { idesc = make_idesc(128, N, 0, 0); ad = make_desc(a0, 2048, 128, 0); bd = make_desc(b0, N * 16, 128, 0); }
         else if (mode == 1) { idesc = make_idesc(128, N, 0, 1); ad = make_desc(a0, 2048, 128, 0); bd = make_desc(b0, 128, N * 16, 0); }
-        else if (mode == 2) { idesc = make_idesc(128, N, 1, 1); ad = make_desc(a0, 128, 2048, 0); bd = make_desc(b0, 128, 2048, 0); }
+        else if (mode == 2 || mode == 6 || mode == 7) { idesc = make_idesc(128, N, 1, 1); ad = make_desc(a0, 128, 2048, 0); bd = make_desc(b0, 128, 2048, 0); }
         else if (mode == 3 || mode == 5) { idesc = make_idesc(128, N, 0, 0); ad = make_desc(a0, 16, 1024, 2); bd = make_desc(b0, 16, 1024, 2); }
         else { idesc = make_idesc(128, N, 0, 0); ad = make_desc(a0, 2048, 128, 0); bd = make_desc(b0, N * 16, 128, 0); }
         t0 = clock64();
-        if (mode >= 4) {
+        if (mode == 6 || mode == 7) {
+            // wgrad as the field backward issues it: 8 K-steps of 16 samples, A and B slabs 256 B apart, four different tile pairs in rotation
+            for (int r = 0; r < R; r += 8) {
+                const uint64_t o = (uint64_t)(((r >> 3) & 3) * 2048) >> 4;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) mma_f16(tmem, ad + o + (uint64_t)k * 16, bd + o + (uint64_t)k * 16, idesc, (r | k) > 0);
+            }
+        } else if (mode == 8) {
+            // the forward's pattern: a burst of `two_acc ? 5 : 12` MMAs, commit, wait — latency of a small batch, not throughput
+            const int burst = two_acc ? 5 : 12;
+            uint32_t ph = 0;
+            for (int r = 0; r < R; r += burst) {
+                for (int k = 0; k < burst; ++k) mma_f16(tmem, ad + (uint64_t)(k & 3) * 256, bd + (uint64_t)(k & 3) * (N * 2), idesc, k > 0);
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar2)) : "memory");
+                uint32_t dn = 0;
+                while (!dn)
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(dn) : "r"(smem_u32(&mbar2)), "r"(ph) : "memory");
+                ph ^= 1;
+            }
+        } else if (mode >= 4) {
             // operand tiles 4 KB (A: 128 rows x 16 columns) / N * 32 B (B) apart: descriptor start address field += bytes >> 4
             const uint64_t a_step = 4096 >> 4, b_step = (uint64_t)(N * 32) >> 4;
             for (int r = 0; r < R; r += 4) {
@@ -71,12 +95,26 @@ __global__ void __launch_bounds__(128) rate(int mode, int N, int R, int two_acc,
         for (int r = 0; r < R; ++r) mma_f16(tmem + (two_acc ? (r & 1) * 256 : 0), ad, bd, idesc, r > 1);
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
     }
+    if (mode == 7 && warp >= 1) {
+        uint4* z = reinterpret_cast<uint4*>(dyn + 49152) + (tid - 32);  // a region no MMA reads
+        uint4 v = make_uint4(tid, 0, 0, 0);
+        while (!stop) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                z[(i & 3) * 256] = v;
+                v.x += z[((i + 1) & 3) * 256].y;
+            }
+        }
+        if (v.x == 0x12345678u) out[0] = 0;
+    }
     uint32_t done = 0;
+    if (!(mode == 7 && warp >= 1))
     while (!done)
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0) : "memory");
     if (tid == 0) {
         t1 = clock64();
         out[blockIdx.x] = t1 - t0;
+        stop = 1;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -88,14 +126,17 @@ int main() {
     cudaMalloc(&d, 148 * 8);
     long long h[148];
     cudaFuncSetAttribute(rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-    const int R = 4096;
+    const int R = 4080;  // a multiple of 8, 12 and 5
     const char* names[] = {"fwd  K/K  no-swizzle", "dgrad K/MN no-swizzle", "wgrad MN/MN no-swizzle", "fwd  K/K  128B-swizzle",
-                           "fwd no-swizzle, rotating tiles", "fwd 128B-swizzle, rotating tiles"};
-    for (int mode = 0; mode < 6; ++mode)
+                           "fwd no-swizzle, rotating tiles", "fwd 128B-swizzle, rotating tiles", "wgrad MN/MN rotating slabs", "wgrad rotating + smem noise",
+                           "fwd bursts (acc=1: 12, acc=2: 5 MMAs) + commit + wait"};
+    const int first_mode = getenv("UMMA_RATE_FIRST") ? atoi(getenv("UMMA_RATE_FIRST")) : 0;
+    for (int mode = first_mode; mode < 9; ++mode)
         for (int N : {16, 32, 64, 128, 256})
             for (int two = 0; two < 2; ++two) {
                 if ((mode == 1 || mode == 2) && N > 128) continue;
-                if (mode >= 4 && (two || N > 128)) continue;
+                if (mode >= 4 && mode != 8 && (two || N > 128)) continue;
+                if (mode >= 6 && N > 64) continue;
                 rate<<<148, 128, 65536>>>(mode, N, R, two, d);
                 cudaError_t e = cudaDeviceSynchronize();
                 if (e != cudaSuccess) { printf("%s N=%d: %s\n", names[mode], N, cudaGetErrorString(e)); return 1; }
