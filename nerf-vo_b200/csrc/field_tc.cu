@@ -28,6 +28,16 @@ __device__ unsigned long long* g_ft_timing = nullptr;  // [2 threads][FT_MAX_MAR
     } while (0)
 // backward: [0] = group 0's thread 0, [1] = the issuer's lane 0 (events of group 0), CTA 0
 __device__ unsigned long long* g_fb_timing = nullptr;  // [2][FT_MAX_MARKS]
+__device__ unsigned long long* g_fb_cta = nullptr;  // [gridDim.x][8] %globaltimer (ns): kernel entry, setup done, tile loop done, weight gradients flushed, then thread 0's flush: first TMEM read done, first stores issued, last stores issued
+__device__ __forceinline__ unsigned long long fb_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define FB_CTA_MARK(i)                                                                     \
+    do {                                                                                   \
+        if (threadIdx.x == 0 && g_fb_cta) g_fb_cta[8 * blockIdx.x + (i)] = fb_gtime();     \
+    } while (0)
 __device__ int g_fb_skip = 0;  // timing experiments only (results are wrong): bit 0 = no wgrad MMAs, bit 1 = no dgrad MMAs, bit 2 = no slot copies after the first two
 #define FB_SKIP(bit) ((g_fb_skip >> (bit)) & 1)
 // `fbt` = g_fb_timing read ONCE at kernel start: a mark is a clock read and a fire-and-forget store (re-reading the pointer from global memory
@@ -44,6 +54,9 @@ __device__ int g_fb_skip = 0;  // timing experiments only (results are wrong): b
     do {                  \
     } while (0)
 #define FB_SKIP(bit) 0
+#define FB_CTA_MARK(i) \
+    do {               \
+    } while (0)
 #endif
 
 #define FT_THREADS 256       // per tile group: warp w reads TMEM lanes 32 * (w & 3) .. (rows of the tile) and the column half (w >> 2)
@@ -709,7 +722,6 @@ struct FieldBwdP {
     const float* dirs;            // [B,3] ray directions (with ddirs)
     float* ddirs;                 // [B,3] d loss / d ray direction through the SH encoding, accumulated (atomics); nullable
     int l2_prefetch;              // prefetch the next tile's saved activations into L2 (NVO_FIELD_BWD_PREFETCH, default 1)
-    int wait_hint_ns;             // suspend-time hint of the groups' wait for their MMAs (NVO_FIELD_BWD_WAIT_NS; 0 = plain try_wait loop)
 };
 
 __device__ __forceinline__ float ft_grad_scale(float mx) {
@@ -757,14 +769,6 @@ __global__ void __launch_bounds__(256) k_field_bwd_absmax(int64_t n, const float
     }
 }
 
-__device__ __forceinline__ bool mbar_test(uint64_t* mbar, uint32_t parity) {
-    uint32_t done;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                 : "=r"(done)
-                 : "r"(smem_u32(mbar)), "r"(parity)
-                 : "memory");
-    return done != 0;
-}
 __device__ __forceinline__ void mbar_arrive(uint64_t* mbar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mbar)) : "memory"); }
 
 // wgrad, transposed form: D[feature i (M = 128: 64 real + ones row + ignored rows)][output o (N)] += sum over the tile's 128 samples of
@@ -820,12 +824,13 @@ __device__ __forceinline__ void issue_wgrad_rel(uint32_t tmem_d, uint32_t base16
 // One step's MMAs + commit with the step TS a compile-time constant as well (the static issue schedule of k_field_bwd): no switch, the
 // elected lane's instruction stream is the uniform-register descriptor adds and the tcgen05.mma themselves.
 template <int G, int GI, int SL, int TS>
-__device__ __forceinline__ void fb_issue_s(uint32_t uBase, uint32_t started) {
+__device__ __forceinline__ void fb_issue_s(uint32_t uBase, uint32_t started, uint32_t signal_go) {
     const uint32_t b16 = (uBase & 0x3FFFFu) >> 4;
     constexpr uint32_t oG = BW_GROUPS_OFF + GI * BW_GROUP_CHUNKS * CHUNK_B, oSlot = oG + SL * BW_SLOT_CHUNKS * CHUNK_B;
     constexpr uint32_t oG64 = oG + 2 * BW_SLOT_CHUNKS * CHUNK_B, oG16 = oG64 + 8 * CHUNK_B;
     constexpr uint32_t acc = DW_ACC + 64 * GI;
     if (elect_one()) {
+        if (signal_go) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(uBase + BW_MBAR_OFF(G) + 8 * (1 + 4 * G + GI)) : "memory");
         if constexpr (TS == 0) {  // head layer 2: dA2 = dz3 W2 ; dW2^T += AH2_ext^T dz3
             if (!FB_SKIP(1)) issue_layer_rel(acc, b16, oG16, 1, FB_H2T, 64, false);
             if (!FB_SKIP(0)) issue_wgrad_rel(DW_H2T, b16, oSlot, oG16, 16, started);
@@ -847,59 +852,13 @@ __device__ __forceinline__ void fb_issue_s(uint32_t uBase, uint32_t started) {
     __syncwarp();
 }
 
-template <int G, int GI, int SL>
-__device__ __forceinline__ void fb_issue(int ts, uint32_t uBase, uint32_t started, int lane) {
-    const uint32_t b16 = (uBase & 0x3FFFFu) >> 4;
-    constexpr uint32_t oG = BW_GROUPS_OFF + GI * BW_GROUP_CHUNKS * CHUNK_B, oSlot = oG + SL * BW_SLOT_CHUNKS * CHUNK_B;
-    constexpr uint32_t oG64 = oG + 2 * BW_SLOT_CHUNKS * CHUNK_B, oG16 = oG64 + 8 * CHUNK_B;
-    constexpr uint32_t acc = DW_ACC + 64 * GI;
-    // `ts` is warp-uniform: a uniform switch, then the elected lane alone issues the step's MMAs and the commit
-    switch (ts) {
-        case 0:  // head layer 2: dA2 = dz3 W2 ; dW2^T += AH2_ext^T dz3
-            if (elect_one()) {
-                if (!FB_SKIP(1)) issue_layer_rel(acc, b16, oG16, 1, FB_H2T, 64, false);
-                if (!FB_SKIP(0)) issue_wgrad_rel(DW_H2T, b16, oSlot, oG16, 16, started);
-                umma_commit_u32(uBase + BW_MBAR_OFF(G) + 8 * (1 + G + GI));
-            }
-            break;
-        case 1:  // head layer 1
-            if (elect_one()) {
-                if (!FB_SKIP(1)) issue_layer_rel(acc, b16, oG64, 4, FB_H1T, 64, false);
-                if (!FB_SKIP(0)) issue_wgrad_rel(DW_H1T, b16, oSlot, oG64, 64, started);
-                umma_commit_u32(uBase + BW_MBAR_OFF(G) + 8 * (1 + G + GI));
-            }
-            break;
-        case 2:  // head layer 0: dX ; dW0^T += X^T dZ1 (the bias is X's constant column 63)
-            if (elect_one()) {
-                if (!FB_SKIP(1)) issue_layer_rel(acc, b16, oG64, 4, FB_H0T, 64, false);
-                if (!FB_SKIP(0)) issue_wgrad_rel(DW_H0T, b16, oSlot, oG64, 64, started);
-                umma_commit_u32(uBase + BW_MBAR_OFF(G) + 8 * (1 + G + GI));
-            }
-            break;
-        case 3:  // base layer 1
-            if (elect_one()) {
-                if (!FB_SKIP(1)) issue_layer_rel(acc, b16, oG16, 1, FB_B1T, 64, false);
-                if (!FB_SKIP(0)) issue_wgrad_rel(DW_B1T, b16, oSlot, oG16, 16, started);
-                umma_commit_u32(uBase + BW_MBAR_OFF(G) + 8 * (1 + G + GI));
-            }
-            break;
-        default:  // base layer 0: d features (32 columns); the feature tile sits in the slot's upper half
-            if (elect_one()) {
-                if (!FB_SKIP(1)) issue_layer_rel(acc, b16, oG64, 4, FB_B0T, 32, false);
-                if (!FB_SKIP(0)) issue_wgrad_rel(DW_B0T, b16, oSlot + 4 * CHUNK_B, oG64, 64, started);
-                umma_commit_u32(uBase + BW_MBAR_OFF(G) + 8 * (1 + G + GI));
-            }
-            break;
-    }
-    __syncwarp();
-}
-
-template <int G, bool STATIC>
-__global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __grid_constant__ FieldBwdP p) {
+template <int G>
+__global__ void __launch_bounds__(G* FT_THREADS + 64, 1) k_field_bwd(const __grid_constant__ FieldBwdP p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int NEPI = G * FT_THREADS;
-    const bool is_issuer_warp = threadIdx.x >= NEPI;
-    const int g = is_issuer_warp ? 0 : (int)(threadIdx.x >> 8);
+    const bool is_issuer_warp = threadIdx.x >= NEPI && threadIdx.x < NEPI + 32, is_loader_warp = threadIdx.x >= NEPI + 32;
+    const bool is_group_thread = threadIdx.x < NEPI;
+    const int g = is_group_thread ? (int)(threadIdx.x >> 8) : 0;
     const int tid = threadIdx.x & 255, warp = tid >> 5, hf = warp >> 2, lane = threadIdx.x & 31;
     const int r = ((warp & 3) << 5) | lane;
     unsigned char* sW = smem;
@@ -909,17 +868,19 @@ __global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __gri
     uint64_t* mbar_ready = mbars + 1;         // [G] operands of the group's next step are in shared memory (8 warp arrivals)
     uint64_t* mbar_done = mbars + 1 + G;      // [G] the step's MMAs have retired (tcgen05.commit)
     uint64_t* mbar_load = mbars + 1 + 2 * G;  // [G][2] the slot's bulk copy has landed
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mbars + 1 + 4 * G);
+    uint64_t* mbar_go = mbars + 1 + 4 * G;    // [G] issuer -> loader: step q's operands are ready, the other slot may be refilled
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mbars + 1 + 5 * G);
     const int64_t n_tiles = (p.n + TM - 1) >> 7;
     const int64_t stride = (int64_t)gridDim.x * G;
     const size_t saved_tile_bytes = (size_t)p.saved_chunks * CHUNK_B;
+    FB_CTA_MARK(0);
 
     // zero the activation slots / dZ buffers once (padded chunks feed ignored accumulator rows, but must not hold NaN patterns that
     // would reach real rows through the K dimension), then the constant ones chunk behind every slot
-    for (int e = threadIdx.x; e < (G * BW_GROUP_CHUNKS + 2) * CHUNK_B / 16; e += NEPI + 32)
+    for (int e = threadIdx.x; e < (G * BW_GROUP_CHUNKS + 2) * CHUNK_B / 16; e += NEPI + 64)
         reinterpret_cast<uint4*>(smem + BW_GROUPS_OFF)[e] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    if (!is_issuer_warp && tid < TM) {
+    if (is_group_thread && tid < TM) {
         unsigned char* sG = smem + BW_GROUPS_OFF + g * BW_GROUP_CHUNKS * CHUNK_B;
         *reinterpret_cast<uint4*>(sG + 8 * CHUNK_B + tid * 16) = make_uint4(0x00003C00u, 0, 0, 0);
         *reinterpret_cast<uint4*>(sG + (BW_SLOT_CHUNKS + 8) * CHUNK_B + tid * 16) = make_uint4(0x00003C00u, 0, 0, 0);
@@ -935,6 +896,7 @@ __global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __gri
             mbar_init(mbar_done + i, 1);
             mbar_init(mbar_load + 2 * i, 1);
             mbar_init(mbar_load + 2 * i + 1, 1);
+            mbar_init(mbar_go + i, 1);
         }
         fence_mbar_init();
     }
@@ -944,6 +906,7 @@ __global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __gri
     tc_fence_after();
     const uint32_t tmem0 = *tmem_ptr;
     if (tmem0 != 0u) __trap();  // all 512 columns: the allocation can only start at column 0 (fb_issue relies on it)
+    FB_CTA_MARK(1);
 #ifdef NVO_FT_TIMING
     unsigned long long* const fbt = blockIdx.x == 0 ? g_fb_timing : nullptr;
 #endif
@@ -951,148 +914,105 @@ __global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __gri
     const float s_h = ft_grad_scale(mx_h), s_b = ft_grad_scale(fmaxf(mx_d, 4.f * mx_h));
     const float inv_s_h = 1.f / s_h, inv_s_b = 1.f / s_b, s_bh = s_b * inv_s_h;
 
-    if (is_issuer_warp) {
-        // ===================================== MMA issuer + loader (one warp, lane 0 acts) =====================================
-        // The whole warp walks the polling loop with warp-uniform state (the mbarrier tests are combined with a vote), so the step's descriptor
-        // arithmetic lives in uniform registers; the single-thread actions — bulk copies, tcgen05.mma, tcgen05.commit — are lane 0's.
-        if (lane == 0) {
-            mbar_expect_tx(mbar_w, FB_BYTES);
-            bulk_g2s(sW, p.wimg + FB_OFF, FB_BYTES, mbar_w);
-        }
-        int64_t total_q[G];
-        int q[G];
-        uint32_t rph[G], lph[G][2];
-        int dw_started = 0;  // bit l: layer l's weight-gradient accumulator has been written once
-        int active = 0;
-#ifdef NVO_FT_TIMING
-        int fb_mi = 0;
-#endif
-        const bool l2_prefetch = p.l2_prefetch != 0;
-        auto load_s = [&](int gg, int ts, int sl, int64_t tile_local) {  // the elected lane only; gg, ts, sl are constants at the call sites
-            const int64_t tile = (int64_t)blockIdx.x * G + gg + tile_local * stride;
-            unsigned char* slot = smem + BW_GROUPS_OFF + gg * BW_GROUP_CHUNKS * CHUNK_B + sl * BW_SLOT_CHUNKS * CHUNK_B;
-            uint64_t* mb = mbar_load + 2 * gg + sl;
-            const unsigned char* sv = p.saved + tile * saved_tile_bytes;
-            if (ts == 0 && tile + stride < n_tiles && l2_prefetch) {
-                bulk_prefetch_l2(p.saved + (tile + stride) * saved_tile_bytes, FS_CHUNKS_HEAD * CHUNK_B);
-                bulk_prefetch_l2(p.feat16 + (tile + stride) * (4 * CHUNK_B), 4 * CHUNK_B);
-            }
-            if (ts == 4) {
-                mbar_expect_tx(mb, 4 * CHUNK_B);
-                bulk_g2s(slot + 4 * CHUNK_B, p.feat16 + tile * (4 * CHUNK_B), 4 * CHUNK_B, mb);
-            } else {
-                const int ch = ts == 0 ? FS_AH2 : ts == 1 ? FS_AH1 : ts == 2 ? FS_X : FS_H1;
-                mbar_expect_tx(mb, 8 * CHUNK_B);
-                bulk_g2s(slot, sv + ch * CHUNK_B, 8 * CHUNK_B, mb);
-            }
-        };
-        auto load = [&](int gg, int qq) {  // the elected lane only
-            const int ts = qq % 5;
-            const int64_t tile = (int64_t)blockIdx.x * G + gg + (int64_t)(qq / 5) * stride;
-            unsigned char* slot = smem + BW_GROUPS_OFF + gg * BW_GROUP_CHUNKS * CHUNK_B + (qq & 1) * BW_SLOT_CHUNKS * CHUNK_B;
-            uint64_t* mb = mbar_load + 2 * gg + (qq & 1);
-            const unsigned char* sv = p.saved + tile * saved_tile_bytes;
-            if (ts == 0 && tile + stride < n_tiles && l2_prefetch) {
-                // the group's NEXT tile (five steps ahead): its 64 KB of saved activations and 8 KB of features start towards L2 now, so the
-                // just-in-time slot copies below find them there instead of waiting on HBM inside the step chain
-                bulk_prefetch_l2(p.saved + (tile + stride) * saved_tile_bytes, FS_CHUNKS_HEAD * CHUNK_B);
-                bulk_prefetch_l2(p.feat16 + (tile + stride) * (4 * CHUNK_B), 4 * CHUNK_B);
-            }
-            if (ts == 4) {  // base layer 0's input: the hash features (4 chunks), placed so that the ones chunk follows them
-                mbar_expect_tx(mb, 4 * CHUNK_B);
-                bulk_g2s(slot + 4 * CHUNK_B, p.feat16 + tile * (4 * CHUNK_B), 4 * CHUNK_B, mb);
-            } else {
-                const int ch = ts == 0 ? FS_AH2 : ts == 1 ? FS_AH1 : ts == 2 ? FS_X : FS_H1;
-                mbar_expect_tx(mb, 8 * CHUNK_B);
-                bulk_g2s(slot, sv + ch * CHUNK_B, 8 * CHUNK_B, mb);
-            }
-        };
+    if (is_issuer_warp || is_loader_warp) {
+        // ===================================== MMA issuer warp and loader warp =====================================
+        // Both walk the SAME static schedule: the groups are served round-robin in a fixed order, one step each — two tiles (10 steps) per loop
+        // iteration, so the step, the slot and the barrier parities of every block below are compile-time constants.
+        //   issuer, per block: wait `ready` (operands written) and `load` (the slot's copy landed) -> arrive on `go` -> the step's MMAs -> commit.
+        //   loader, per block: wait `go` -> request the bulk copy of step q + 1 into the other slot (its readers, step q - 1's MMAs and epilogue,
+        //     are finished once step q's operands are ready) and the L2 prefetch of a piece of the group's next tile.
+        // History (tools/field_timing.cu, profiles/r02_field_bwd_phase_timing*.log): a polling issuer (any ready group, run-time step) spent
+        // 150-200 scalar instructions = 900-1300 cycles per step next to 24 epilogue warps, against 550-720 for the step's MMAs, and that one
+        // warp serialises the groups; with the copy requests (64-bit address arithmetic, ~250 cycles) in a second warp the issuer's block is
+        // the MMAs themselves.  `go` phases cannot run ahead of the loader: the issuer arrives on go(q + 1) only after load(q + 1) has landed,
+        // which the loader requests after it has seen go(q) (q = 0 has no `go`: steps 0 and 1 are preloaded; the last step requests nothing).
+        int64_t tiles_g[G];
+        int64_t tiles_max = 0;
 #pragma unroll
         for (int gg = 0; gg < G; ++gg) {
             const int64_t first = (int64_t)blockIdx.x * G + gg;
-            const int64_t tiles_g = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
-            total_q[gg] = tiles_g * 5;
-            q[gg] = 0, rph[gg] = 0, lph[gg][0] = lph[gg][1] = 0;
-            if (tiles_g > 0) {
-                active |= 1 << gg;
-                if (lane == 0) {
-                    load(gg, 0);
-                    load(gg, 1);
-                }
-            }
+            tiles_g[gg] = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+            tiles_max = tiles_g[gg] > tiles_max ? tiles_g[gg] : tiles_max;
         }
-        mbar_wait(mbar_w, 0);
-        if constexpr (STATIC) {
-            // ---- static schedule (default): the groups are served round-robin in a fixed order, one step each — two tiles (10 steps) per
-            // iteration, so the step, the slot and the `ready` parity of every block below are compile-time constants and a block is: two
-            // mbarrier waits, one bulk-copy request, the MMAs, the commit.  The polling loop of the dynamic schedule (any ready group, run-time
-            // step) cost the issuing warp 150-200 scalar instructions per step next to 24 epilogue warps — 900-1300 cycles against 450 for the
-            // step's MMAs (tools/field_timing.cu, profiles/r02_field_bwd_phase_timing.log) — and that warp serialises the three groups.
-            int64_t tiles_g[G];
-            int64_t tiles_max = 0;
+#ifdef NVO_FT_TIMING
+        int fb_mi = 0;
+#endif
+        if (is_loader_warp) {
+            const bool l2_prefetch = p.l2_prefetch != 0;
+            auto load_s = [&](int gg, int ts, int sl, int64_t tile_local) {  // the elected lane only; gg, ts, sl are constants at the call sites
+                const int64_t tile = (int64_t)blockIdx.x * G + gg + tile_local * stride;
+                unsigned char* slot = smem + BW_GROUPS_OFF + gg * BW_GROUP_CHUNKS * CHUNK_B + sl * BW_SLOT_CHUNKS * CHUNK_B;
+                uint64_t* mb = mbar_load + 2 * gg + sl;
+                const unsigned char* sv = p.saved + tile * saved_tile_bytes;
+                if (ts == 4) {  // base layer 0's input: the hash features (4 chunks), placed so that the ones chunk follows them
+                    mbar_expect_tx(mb, 4 * CHUNK_B);
+                    bulk_g2s(slot + 4 * CHUNK_B, p.feat16 + tile * (4 * CHUNK_B), 4 * CHUNK_B, mb);
+                } else {
+                    const int ch = ts == 0 ? FS_AH2 : ts == 1 ? FS_AH1 : ts == 2 ? FS_X : FS_H1;
+                    mbar_expect_tx(mb, 8 * CHUNK_B);
+                    bulk_g2s(slot, sv + ch * CHUNK_B, 8 * CHUNK_B, mb);
+                }
+                // the group's NEXT tile starts towards L2 in four pieces, each behind a slot copy (the TMA engine serves its requests in order:
+                // one 72 KB prefetch ahead of a copy delayed that copy past the step that needed it)
+                if (tile + stride < n_tiles && l2_prefetch) {
+                    const unsigned char* nx = p.saved + (tile + stride) * saved_tile_bytes;
+                    if (ts == 1) bulk_prefetch_l2(nx + FS_AH2 * CHUNK_B, 8 * CHUNK_B);
+                    if (ts == 2) bulk_prefetch_l2(nx + FS_AH1 * CHUNK_B, 8 * CHUNK_B);
+                    if (ts == 3) bulk_prefetch_l2(nx + FS_X * CHUNK_B, 8 * CHUNK_B);
+                    if (ts == 4) {
+                        bulk_prefetch_l2(nx + FS_H1 * CHUNK_B, 8 * CHUNK_B);
+                        bulk_prefetch_l2(p.feat16 + (tile + stride) * (4 * CHUNK_B), 4 * CHUNK_B);
+                    }
+                }
+            };
+            if (elect_one()) {
+                mbar_expect_tx(mbar_w, FB_BYTES);
+                bulk_g2s(sW, p.wimg + FB_OFF, FB_BYTES, mbar_w);
 #pragma unroll
-            for (int gg = 0; gg < G; ++gg) tiles_g[gg] = total_q[gg] / 5, tiles_max = tiles_g[gg] > tiles_max ? tiles_g[gg] : tiles_max;
+                for (int gg = 0; gg < G; ++gg)
+                    if (tiles_g[gg] > 0) {
+                        load_s(gg, 0, 0, 0);
+                        load_s(gg, 1, 1, 0);
+                    }
+            }
+            __syncwarp();
+            for (int64_t it = 0; it < tiles_max; it += 2) {
+#define FB_LBLOCK(GI, U)                                                                                                   \
+    if (GI < G && it + ((U) >= 5) < tiles_g[GI < G ? GI : 0] && (it > 0 || (U) > 0)) {                                      \
+        constexpr int gi = GI < G ? GI : 0, sl = (U) & 1, ts = (U) % 5;                                                    \
+        mbar_wait(mbar_go + gi, (uint32_t)(((U) + 1) & 1));                                                                \
+        const int64_t tl = it + ((U) >= 5);                /* this step's tile of the group */                             \
+        if (ts < 4 || tl + 1 < tiles_g[gi]) {              /* step q + 1 exists */                                         \
+            if (elect_one()) load_s(gi, (ts + 1) % 5, sl ^ 1, tl + (ts == 4));                                            \
+            __syncwarp();                                                                                                 \
+        }                                                                                                                 \
+    }
+#define FB_LROUND(U) FB_LBLOCK(0, U) FB_LBLOCK(1, U) FB_LBLOCK(2, U)
+                FB_LROUND(0) FB_LROUND(1) FB_LROUND(2) FB_LROUND(3) FB_LROUND(4) FB_LROUND(5) FB_LROUND(6) FB_LROUND(7) FB_LROUND(8) FB_LROUND(9)
+#undef FB_LROUND
+#undef FB_LBLOCK
+            }
+        } else {
+            mbar_wait(mbar_w, 0);
             uint32_t lbits = 0;  // bit 2 gg + sl: phase parity of the slot's load barrier
             for (int64_t it = 0; it < tiles_max; it += 2) {
-#define FB_BLOCK(GI, U)                                                                                                              \
-    if (GI < G && it + ((U) >= 5) < tiles_g[GI < G ? GI : 0]) {                                                                          \
-        constexpr int gi = GI < G ? GI : 0, sl = (U) & 1, ts = (U) % 5;                                                                \
-        mbar_wait(mbar_ready + gi, (uint32_t)sl);                                                                                     \
-        mbar_wait(mbar_load + 2 * gi + sl, (lbits >> (2 * gi + sl)) & 1u);                                                            \
-        lbits ^= 1u << (2 * gi + sl);                                                                                                 \
-        if (gi == 0 && lane == 0) FB_MARK(1, fb_mi);                                                                                  \
-        const int64_t tl = it + ((U) >= 5);                                /* this step's tile of the group */                         \
-        if ((it > 0 || (U) > 0) && (ts < 4 || tl + 1 < tiles_g[gi])) {     /* step q + 1 exists, and is not one of the two preloaded */ \
-            if (elect_one()) load_s(gi, (ts + 1) % 5, sl ^ 1, tl + (ts == 4));                                                        \
-            __syncwarp();                                                                                                             \
-        }                                                                                                                             \
-        if (gi == 0 && lane == 0) FB_MARK(1, fb_mi);                                                                                  \
-        tc_fence_after();                                                                                                             \
-        fb_issue_s<G, gi, sl, ts>(uBase, (it > 0 || (U) >= 5 || gi > 0) ? 1u : 0u);                                                    \
-        if (gi == 0 && lane == 0) FB_MARK(1, fb_mi);                                                                                  \
+#define FB_BLOCK(GI, U)                                                                                                   \
+    if (GI < G && it + ((U) >= 5) < tiles_g[GI < G ? GI : 0]) {                                                            \
+        constexpr int gi = GI < G ? GI : 0, sl = (U) & 1, ts = (U) % 5;                                                    \
+        if (gi == 0 && lane == 0) FB_MARK(1, fb_mi);                                                                      \
+        mbar_wait(mbar_ready + gi, (uint32_t)sl);                                                                         \
+        if (gi == 0 && lane == 0) FB_MARK(1, fb_mi);                                                                      \
+        mbar_wait(mbar_load + 2 * gi + sl, (lbits >> (2 * gi + sl)) & 1u);                                                \
+        lbits ^= 1u << (2 * gi + sl);                                                                                     \
+        if (gi == 0 && lane == 0) FB_MARK(1, fb_mi);                                                                      \
+        tc_fence_after();                                                                                                 \
+        fb_issue_s<G, gi, sl, ts>(uBase, (it > 0 || (U) >= 5 || gi > 0) ? 1u : 0u, (it > 0 || (U) > 0) ? 1u : 0u);         \
+        if (gi == 0 && lane == 0) FB_MARK(1, fb_mi);                                                                      \
     }
 #define FB_ROUND(U) FB_BLOCK(0, U) FB_BLOCK(1, U) FB_BLOCK(2, U)
                 FB_ROUND(0) FB_ROUND(1) FB_ROUND(2) FB_ROUND(3) FB_ROUND(4) FB_ROUND(5) FB_ROUND(6) FB_ROUND(7) FB_ROUND(8) FB_ROUND(9)
 #undef FB_ROUND
 #undef FB_BLOCK
-            }
-        } else
-        while (active) {
-#pragma unroll
-            for (int gg = 0; gg < G; ++gg) {
-                if (!((active >> gg) & 1)) continue;
-                const int qq = q[gg], sl = qq & 1;
-                // every lane tests; the vote makes the decision (and everything derived from it) warp-uniform
-                const bool go = mbar_test(mbar_ready + gg, rph[gg]) && mbar_test(mbar_load + 2 * gg + sl, lph[gg][sl]);
-                if (!__all_sync(0xffffffffu, go)) continue;
-                rph[gg] ^= 1, lph[gg][sl] ^= 1;
-                if (gg == 0 && lane == 0) FB_MARK(1, fb_mi);
-                if (qq >= 1 && qq + 1 < total_q[gg]) {  // slot (qq+1)&1: its readers (step qq-1) are finished
-                    if (elect_one()) load(gg, qq + 1);
-                    __syncwarp();
-                }
-                if (gg == 0 && lane == 0) FB_MARK(1, fb_mi);
-                tc_fence_after();
-                const int ts = qq % 5;
-                const uint32_t started = (dw_started >> ts) & 1;
-#define FB_ISSUE(GI)                                        \
-    do {                                                    \
-        if (sl)                                             \
-            fb_issue<G, GI, 1>(ts, uBase, started, lane);   \
-        else                                                \
-            fb_issue<G, GI, 0>(ts, uBase, started, lane);   \
-    } while (0)
-                if (gg == 0)
-                    FB_ISSUE(0);
-                else if (G > 1 && gg == 1)
-                    FB_ISSUE((G > 1 ? 1 : 0));
-                else if (G > 2)
-                    FB_ISSUE((G > 2 ? 2 : 0));
-#undef FB_ISSUE
-                if (gg == 0 && lane == 0) FB_MARK(1, fb_mi);
-                dw_started |= 1 << ts;
-                q[gg] = qq + 1;
-                if (qq + 1 == total_q[gg]) active &= ~(1 << gg);
             }
         }
         __syncwarp();
@@ -1123,10 +1043,7 @@ __global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __gri
 #endif
         };
         auto wait_done = [&]() {
-            if (p.wait_hint_ns > 0)
-                mbar_wait_hint(done, dph, (uint32_t)p.wait_hint_ns);
-            else
-                mbar_wait(done, dph);
+            mbar_wait(done, dph);
             dph ^= 1;
             tc_fence_after();
 #ifdef NVO_FT_TIMING
@@ -1134,11 +1051,12 @@ __global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __gri
 #endif
             mbar_wait(mbar_load + 2 * g + (q & 1), (uint32_t)((q >> 1) & 1));  // already complete (the issuer waited for it): orders the reads below
         };
-        // dz of the colour output: drgb * sigmoid'(rgb) * scale -> G16 chunk 0 (outputs 0..2), chunk 1 = 0
-        auto write_dz3 = [&](int64_t tile) {
+        // dz of the colour output: drgb * sigmoid'(rgb) * scale -> G16 chunk 0 (outputs 0..2), chunk 1 = 0.  Two halves: the global loads are
+        // requested a step early (their latency hides behind the wait for the MMAs), the shared-memory write follows once G16's readers retired.
+        auto load_dz3 = [&](int64_t tile, float* dz) {
+            dz[0] = dz[1] = dz[2] = 0.f;
             if (hf != 0) return;
             const int64_t t = tile * TM + r;
-            float dz[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (tile < n_tiles && t < p.n) {
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
@@ -1146,11 +1064,19 @@ __global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __gri
                     dz[j] = __ldg(p.drgb + 3 * t + j) * y * (1.f - y) * s_h;
                 }
             }
+        };
+        auto store_dz3 = [&](const float* dz3) {
+            if (hf != 0) return;
+            const float dz[8] = {dz3[0], dz3[1], dz3[2], 0.f, 0.f, 0.f, 0.f, 0.f};
             *reinterpret_cast<uint4*>(sG16 + r * 16) = pack8f(dz);
             *reinterpret_cast<uint4*>(sG16 + CHUNK_B + r * 16) = make_uint4(0, 0, 0, 0);
         };
         const int64_t first = (int64_t)blockIdx.x * G + g;
-        write_dz3(first);
+        {
+            float dz0[3];
+            load_dz3(first, dz0);
+            store_dz3(dz0);
+        }
         for (int64_t tile = first; tile < n_tiles; tile += stride) {
             const int64_t t = tile * TM + r;
             const bool live = t < p.n;
@@ -1167,6 +1093,10 @@ __global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __gri
             ++q;
             // ---- step 2: head layer 0 -> dX: geometry features -> dh, appearance embedding gradient, trunc_exp' --------------------------------
             arrive_ready();
+            // d loss / d raw density (global loads: requested before the wait for the MMAs)
+            float dh0 = 0.f;
+            if (hf == 0 && live && p.ddensity)
+                dh0 = __ldg(p.ddensity + t) * __ldg(p.sel + t) * expf(fminf(fmaxf(__ldg(p.h0 + t), -15.f), 15.f)) * s_b;  // activations.py:38-41
             wait_done();
             {
                 float v[32];
@@ -1178,9 +1108,7 @@ __global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __gri
                 const int ray1 = __shfl_sync(0xffffffffu, (int)ray, 31);
                 if (hf == 0) {
                     float dh[16];
-                    dh[0] = 0.f;
-                    if (live && p.ddensity)
-                        dh[0] = __ldg(p.ddensity + t) * __ldg(p.sel + t) * expf(fminf(fmaxf(__ldg(p.h0 + t), -15.f), 15.f)) * s_b;  // activations.py:38-41
+                    dh[0] = dh0;
 #pragma unroll
                     for (int k = 0; k < GEO; ++k) dh[1 + k] = v[16 + k] * s_bh;  // head-chain scale -> base-chain scale
                     if (p.dpn_in && live) {
@@ -1189,6 +1117,12 @@ __global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __gri
                     }
                     *reinterpret_cast<uint4*>(sG16 + r * 16) = pack8sat(dh);
                     *reinterpret_cast<uint4*>(sG16 + CHUNK_B + r * 16) = pack8sat(dh + 8);
+                }
+                // step 3's operands (dh in G16) are complete and this step's accumulator is in registers: hand over to the issuer NOW, the per-ray
+                // reductions below (direction / appearance-embedding gradients: shuffles and global atomics) run while base layer 1's MMAs do
+                ++q;
+                arrive_ready();
+                if (hf == 0) {
                     if (p.ddirs) {
                         // head input columns 0..15 = SH16((d + 1) / 2): d loss / d d = 0.5 J_SH^T dSH (NS/utils/math.py:45-78), summed per ray
                         const float x = __fmul_rn(__fadd_rn(__ldg(p.dirs + 3 * ray), 1.f), 0.5f), y = __fmul_rn(__fadd_rn(__ldg(p.dirs + 3 * ray + 1), 1.f), 0.5f),
@@ -1241,15 +1175,16 @@ __global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __gri
                     }
                 }
             }
-            ++q;
-            // ---- step 3: base layer 1 -> dZ0 = dA * ReLU'(H1) ------------------------------------------------------------------------------
-            arrive_ready();
+            // ---- step 3: base layer 1 -> dZ0 = dA * ReLU'(H1) (arrival: above) ---------------------------------------------------------------
             wait_done();
             epi_mask(tacc, sG + (q & 1) * BW_SLOT_CHUNKS * CHUNK_B, sG64, hf, r);
             ++q;
             // ---- step 4: base layer 0 -> d features (fp32 TMF [tile][32][128]: a warp stores 128 contiguous bytes per column) ------------------
             arrive_ready();
+            float dz_next[3];
+            load_dz3(tile + stride, dz_next);  // the next tile's colour gradient: in flight during the wait
             wait_done();
+            store_dz3(dz_next);  // G16's readers (step 3's MMAs) have retired; written first, so the next tile's arrival only waits for the TMEM read
             {
                 float v[16];
                 tmem_ld16(tacc + 16 * hf, v);
@@ -1258,29 +1193,31 @@ __global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __gri
                 for (int j = 0; j < 16; ++j) dst[j << 7] = v[j] * inv_s_b;
             }
             ++q;
-            write_dz3(tile + stride);  // G16's readers (step 3's MMAs) have retired
         }
     }
     // ---- flush the weight gradients: lane = input feature (64 = the ones feature = bias), column = output -----------------------------------
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (!is_issuer_warp && (int64_t)blockIdx.x * G < n_tiles) {
+    FB_CTA_MARK(2);
+    if (is_group_thread && (int64_t)blockIdx.x * G < n_tiles) {
         const uint32_t tlane = tmem0 + ((uint32_t)((warp & 3) * 32) << 16);
         // (matrix, TMEM column, outputs, inputs, bias feature row, destination weight / bias offsets, destination buffer)
         struct M {
             int col, N, K, brow, w_off, b_off, head;
         };
-        const M mats[5] = {
+        constexpr M mats[5] = {
             {DW_H1T, 64, 64, 64, 64 * 63 + 64, 64 * 63 + 64 + 64 * 64, 1},
             {DW_H0T, 64, 63, 63, 0, 64 * 63, 1},
             {DW_B0T, 64, 32, 32, 0, 64 * 32, 0},
             {DW_H2T, 3, 64, 64, 64 * 63 + 64 + 64 * 64 + 64, 64 * 63 + 64 + 64 * 64 + 64 + 3 * 64, 1},
             {DW_B1T, 16, 64, 64, 64 * 32 + 64, 64 * 32 + 64 + 16 * 64, 0},
         };
-        for (int m = 0; m < 5; ++m) {
+#pragma unroll
+        for (int m = 0; m < 5; ++m) {  // unrolled: the table above folds into immediates (as a run-time array it lived in local memory)
             if (m % G != g) continue;
-            const M& y = mats[m];
+            constexpr M zero = {0, 0, 0, 0, 0, 0, 0};
+            const M y = m < 5 ? mats[m] : zero;
             float* dst = y.head ? p.dhead : p.dbase;
             const float inv = y.head ? inv_s_h : inv_s_b;
             if ((warp & 3) * 32 > y.brow) continue;  // this warp's lanes hold no real row
@@ -1302,6 +1239,7 @@ __global__ void __launch_bounds__(G* FT_THREADS + 32, 1) k_field_bwd(const __gri
     }
     tc_fence_before();
     __syncthreads();
+    FB_CTA_MARK(3);
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem0) : "memory");
 }
 
@@ -1351,25 +1289,18 @@ extern "C" int nvo_field_backward(void* stream, int64_t B, int32_t S, const void
     p.dirs = directions, p.ddirs = ddirections;
     static const int l2_prefetch = nvo_env_int("NVO_FIELD_BWD_PREFETCH", 1);
     p.l2_prefetch = l2_prefetch;
-    static const int wait_ns = nvo_env_int("NVO_FIELD_BWD_WAIT_NS", 0);
-    p.wait_hint_ns = wait_ns;
     const int G = field_groups();
-    static const int static_issue = nvo_env_int("NVO_FIELD_BWD_STATIC", 1);  // 0 = the dynamic (poll any ready group) issue schedule, G = 3 only
-    const size_t smem = BW_GROUPS_OFF + (size_t)(G * BW_GROUP_CHUNKS + 2) * CHUNK_B + 8 * (1 + 4 * G) + 16;
+    const size_t smem = BW_GROUPS_OFF + (size_t)(G * BW_GROUP_CHUNKS + 2) * CHUNK_B + 8 * (1 + 5 * G) + 16;
     const int64_t tiles = (n + TM - 1) / TM;
     const unsigned int grid = (unsigned int)min((int64_t)nvo_sm_count(), (tiles + G - 1) / G);
     if (G == 2) {
-        e = cudaFuncSetAttribute(k_field_bwd<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(k_field_bwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         NVO_CHECK(e == cudaSuccess, "field_backward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        k_field_bwd<2, true><<<grid, 2 * FT_THREADS + 32, smem, st>>>(p);
-    } else if (static_issue) {
-        e = cudaFuncSetAttribute(k_field_bwd<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        NVO_CHECK(e == cudaSuccess, "field_backward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        k_field_bwd<3, true><<<grid, 3 * FT_THREADS + 32, smem, st>>>(p);
+        k_field_bwd<2><<<grid, 2 * FT_THREADS + 64, smem, st>>>(p);
     } else {
-        e = cudaFuncSetAttribute(k_field_bwd<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(k_field_bwd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         NVO_CHECK(e == cudaSuccess, "field_backward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        k_field_bwd<3, false><<<grid, 3 * FT_THREADS + 32, smem, st>>>(p);
+        k_field_bwd<3><<<grid, 3 * FT_THREADS + 64, smem, st>>>(p);
     }
     NVO_CUDA_LAUNCH_CHECK("field_backward");
     return 0;

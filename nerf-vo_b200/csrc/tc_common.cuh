@@ -53,18 +53,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
             : "memory");
     }
 }
-// same wait with a suspend-time hint (ns): the thread sleeps in hardware until the phase completes or the hint elapses instead of re-issuing
-// try_wait back to back — the spinning of 24 epilogue warps otherwise takes issue slots from the one warp that issues the MMAs
-__device__ __forceinline__ void mbar_wait_hint(uint64_t* mbar, uint32_t parity, uint32_t hint_ns) {
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(done)
-            : "r"(smem_u32(mbar)), "r"(parity), "r"(hint_ns)
-            : "memory");
-    }
-}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* mbar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
 }

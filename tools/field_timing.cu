@@ -102,17 +102,46 @@ int main(int argc, char** argv) {
             cudaEventElapsedTime(&ms, e0, e1);
             printf("backward rep %d: %.1f us (absmax pass included)\n", rep, ms * 1e3);
         }
+        {
+            // per-CTA wall-clock phases (%globaltimer) of one more launch
+            unsigned long long* ct;
+            cudaMalloc(&ct, 148 * 8 * 8);
+            cudaMemset(ct, 0, 148 * 8 * 8);
+            cudaMemcpyToSymbol(g_fb_cta, &ct, sizeof(ct));
+            unsigned long long* none = nullptr;
+            cudaMemcpyToSymbol(g_fb_timing, &none, sizeof(none));
+            nvo_field_backward(0, B, S, feat, saved, 0, wimg, rgb, h0, sel, cam, ddensity, drgb, nullptr, scratch, dfeat, dbase, dhead, demb, nullptr, nullptr);
+            cudaDeviceSynchronize();
+            std::vector<unsigned long long> hc(148 * 8);
+            cudaMemcpy(hc.data(), ct, hc.size() * 8, cudaMemcpyDeviceToHost);
+            unsigned long long t0 = ~0ULL;
+            for (int c = 0; c < 148; ++c) if (hc[8 * c] && hc[8 * c] < t0) t0 = hc[8 * c];
+            printf("---- per CTA, ns since the first CTA's entry: entry | setup done | tile loop done | flushed\n");
+            double s1 = 0, s2 = 0, s3 = 0, mx2 = 0, mx3 = 0, mn2 = 1e18;
+            int nc = 0;
+            for (int c = 0; c < 148; ++c) {
+                if (!hc[8 * c]) continue;
+                ++nc;
+                const double a = hc[8 * c] - t0, b = hc[8 * c + 1] - t0, d = hc[8 * c + 2] - t0, e = hc[8 * c + 3] - t0;
+                if (c < 6 || c % 37 == 0) printf("  CTA %3d: %7.0f %7.0f %7.0f %7.0f\n", c, a, b, d, e);
+                s1 += b, s2 += d, s3 += e;
+                if (d > mx2) mx2 = d;
+                if (d < mn2) mn2 = d;
+                if (e > mx3) mx3 = e;
+            }
+            printf("  mean setup done %.0f, tile loop done mean %.0f min %.0f max %.0f, flushed mean %.0f max %.0f ns (%d CTAs)\n", s1 / nc, s2 / nc, mn2, mx2, s3 / nc, mx3, nc);
+        }
         std::vector<unsigned long long> hb(2 * FT_MAX_MARKS);
         cudaMemcpy(hb.data(), tb, hb.size() * 8, cudaMemcpyDeviceToHost);
         const unsigned long long *gm = hb.data(), *im = hb.data() + FT_MAX_MARKS;
-        // group marks per step: epilogue-done, arrived, MMAs-retired; issuer marks per step: ready+load observed, slot copy requested, issued
+        // group marks per step: epilogue-done, arrived, MMAs-retired; issuer marks per step: block reached, ready observed, load observed, issued
         const char* bs[5] = {"head L2", "head L1", "head L0", "base L1", "base L0"};
         printf("---- backward, CTA 0 group 0: cycles per step\n");
-        for (int q = 0; q < 40 && gm[3 * q + 2] && im[3 * q + 2]; ++q) {
-            const unsigned long long epi_done = gm[3 * q], arrived = gm[3 * q + 1], retired = gm[3 * q + 2], seen = im[3 * q], loaded = im[3 * q + 1], issued = im[3 * q + 2];
+        for (int q = 0; q < 40 && gm[3 * q + 2] && im[4 * q + 3]; ++q) {
+            const unsigned long long epi_done = gm[3 * q], arrived = gm[3 * q + 1], retired = gm[3 * q + 2], at_block = im[4 * q], ready_seen = im[4 * q + 1], seen = im[4 * q + 2], issued = im[4 * q + 3];
             const unsigned long long next = gm[3 * (q + 1)];
-            printf("  tile %d %-8s fence+arrive %5llu | issuer sees ready+load %6lld | copy req %5llu | issue %5llu | MMA + commit %5llu | epilogue %5llu | step total %6llu\n", q / 5,
-                   bs[q % 5], arrived - epi_done, (long long)(seen - arrived), loaded - seen, issued - loaded, retired - issued, next ? next - retired : 0ULL,
+            printf("  tile %d %-8s fence+arrive %5llu | issuer reaches block %6lld | waits ready %5llu | waits load %5llu | issue %5llu | MMA + commit %5llu | epilogue %5llu | step total %6llu\n", q / 5,
+                   bs[q % 5], arrived - epi_done, (long long)(at_block - arrived), ready_seen - at_block, seen - ready_seen, issued - seen, retired - issued, next ? next - retired : 0ULL,
                    next ? next - epi_done : 0ULL);
         }
         return 0;

@@ -1,0 +1,12 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT"
+mkdir -p gpurun_out
+timeout 120 tools/field_timing 4096 1 1 > gpurun_out/c39_bwd_timing.log 2>&1; grep "backward rep" gpurun_out/c39_bwd_timing.log; sed -n '/per CTA, ns/,/mean setup/p' gpurun_out/c39_bwd_timing.log | tail -2
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/c39_pytest.log 2>&1
+echo "rc=$?" >> gpurun_out/c39_pytest.log
+tail -4 gpurun_out/c39_pytest.log
+timeout 300 python bench.py --steps 200 --warmup 10 --no-cpu-baseline --no-schedule-leg > gpurun_out/c39_bench.json 2> gpurun_out/c39_bench.err
+python -c "
+import json
+d=json.load(open('gpurun_out/c39_bench.json')); print('bench', d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches_per_step'])
+for o in d['roofline']['others'][:4]: print('  ', o['kernel'][:60], round(o['launch_us'],1), round(o.get('frac'),4))"
