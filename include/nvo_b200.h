@@ -154,7 +154,12 @@ int nvo_prop_density_supported(int32_t n_levels, int32_t hidden, int32_t n_layer
 /* floats of the saved-feature buffer for n samples (level-major, padded to 128-sample blocks, permuted inside a block) */
 int64_t nvo_prop_density_feat_floats(int32_t n_levels, int64_t n);
 /* slot in [0,4): which constant-memory bank holds this network's MLP parameters while its kernels run (the call copies
- * `params` there first, device to device, on `stream`); networks evaluated concurrently on different streams need distinct slots. */
+ * `params` there first, device to device, on `stream`); networks evaluated concurrently on different streams need distinct slots.
+ * params == NULL in the forward / backward calls: the bank already holds the network — the caller has run nvo_prop_density_upload(stream',
+ * slot, params) (the forward's and the backward's copy), ordered the call behind it, and nothing else has used the slot since.  The
+ * mapping step uploads both proposal networks at its start, next to the first sampling kernel, instead of in front of each of the four
+ * launches that use them. */
+int nvo_prop_density_upload(void* stream, int32_t slot, const float* params);
 int nvo_prop_density_forward(const nvo_grid_desc* g, int32_t hidden, int32_t slot, void* stream, int64_t B, int32_t S, const float* origins,
                              const float* directions, const float* starts, const float* ends, int64_t stride, const float* positions, const void* table,
                              const float* params, float* density, float* feat);

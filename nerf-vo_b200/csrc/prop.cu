@@ -325,14 +325,21 @@ extern "C" int nvo_prop_density_supported(int32_t n_levels, int32_t hidden, int3
 
 extern "C" int64_t nvo_prop_density_feat_floats(int32_t n_levels, int64_t n) { return ((int64_t)n_levels * 2 + 4) * ((n + 127) / 128 * 128); }
 
+// params == NULL: the caller has uploaded the network into `slot` with nvo_prop_density_upload and nothing else has used the slot since
 static int upload_params(int slot, const float* params, cudaStream_t st, bool backward_copy = false) {
     NVO_CHECK(slot >= 0 && slot < PROP_SLOTS, "prop_density: slot %d out of range [0,%d)", slot, PROP_SLOTS);
+    if (!params) return 0;
     cudaError_t e = cudaMemcpyToSymbolAsync(c_prop, params, sizeof(float) * PropLayout<5>::NP, sizeof(float) * PROP_SLOT_FLOATS * slot,
                                             cudaMemcpyDeviceToDevice, st);
     if (e == cudaSuccess && backward_copy)
         e = cudaMemcpyToSymbolAsync(c_propb, params, sizeof(float) * PropLayout<5>::NP, sizeof(float) * PROP_SLOT_FLOATS * slot, cudaMemcpyDeviceToDevice, st);
     NVO_CHECK(e == cudaSuccess, "prop_density: parameter upload failed: %s", cudaGetErrorString(e));
     return 0;
+}
+
+extern "C" int nvo_prop_density_upload(void* stream, int32_t slot, const float* params) {
+    NVO_CHECK(params, "prop_density_upload: null pointer");
+    return upload_params(slot, params, (cudaStream_t)stream, true);
 }
 
 template <int SLOT>
@@ -352,7 +359,7 @@ extern "C" int nvo_prop_density_forward(const nvo_grid_desc* g, int32_t hidden, 
     if (int e = prop_params(g, hidden, &p)) return e;
     NVO_CHECK(B >= 0 && S >= 1, "prop_density_forward: bad shape");
     if (B == 0) return 0;
-    NVO_CHECK(table && params && density, "prop_density_forward: null pointer");
+    NVO_CHECK(table && density, "prop_density_forward: null pointer");
     NVO_CHECK(positions || (origins && directions && starts && ends), "prop_density_forward: need positions or rays + intervals");
     const int64_t N = B * S, Npad = (N + 127) / 128 * 128;
     cudaStream_t st = (cudaStream_t)stream;
@@ -413,7 +420,7 @@ static int prop_backward_impl(const nvo_grid_desc* g, int32_t hidden, int32_t sl
     if (int e = prop_params(g, hidden, &p)) return e;
     NVO_CHECK(B >= 0 && S >= 1, "prop_density_backward: bad shape");
     if (B == 0) return 0;
-    NVO_CHECK(params && feat && ddensity, "prop_density_backward: null pointer");
+    NVO_CHECK(feat && ddensity, "prop_density_backward: null pointer");
     NVO_CHECK(positions || (origins && directions && starts && ends), "prop_density_backward: need positions or rays + intervals");
     const int64_t N = B * S, Npad = (N + 127) / 128 * 128;
     cudaStream_t st = (cudaStream_t)stream;

@@ -93,6 +93,14 @@ class HashMLPDensityField(Field):
             self._fused_ok = (not self.use_linear) and ops.prop_density_supported(self.encoding.spec, self._net().spec)
         return self._fused_ok
 
+    def preload(self) -> None:
+        """Trainer hook at the start of a step: the MLP goes to its constant-memory bank on a side stream, once, instead of in front of each
+        of the step's launches that use it (density forward, backward)."""
+        if self._fused():
+            net = self._net()
+            net._repack()
+            ops.prop_density_preload(self._slot, net._flat_param_list())
+
     def _density_from_positions(self, positions: torch.Tensor) -> Tuple[torch.Tensor, None]:
         net = self._net()
         if self._fused():

@@ -146,6 +146,9 @@ class NerfactoModel(nn.Module):
         if hook is not None:
             hook()  # MappingTrainer(defer_fields_update=True): the previous step's fields update lands here, behind the proposal sampling
         fo = self.field.forward(ray_samples, compute_normals=self.config.predict_normals)
+        hook = getattr(self, "_after_field_forward", None)
+        if hook is not None:
+            hook()  # MappingTrainer: the zero fill of the fields group's gradient range starts here, next to the render / loss kernels
         weights = ray_samples.get_weights(fo[FieldHeadNames.DENSITY])
         weights_list.append(weights)
         ray_samples_list.append(ray_samples)

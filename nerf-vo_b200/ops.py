@@ -380,6 +380,37 @@ def prop_density_supported(gspec: GridSpec, mspec: MlpSpec) -> bool:
     return bool(_lib.load().nvo_prop_density_supported(gspec.n_levels, mspec.dims[0], 2))
 
 
+# constant-memory banks of the fused proposal field that hold their network for the step in flight: slot -> (event recorded behind the
+# upload, data_ptr of the parameters uploaded).  Set by prop_density_preload (the trainer, at the start of a step), cleared by clear_prepacked().
+_prop_resident: dict = {}
+
+
+def prop_density_preload(slot: int, params) -> None:
+    """Uploads the proposal network `params` into constant-memory bank `slot` on a side stream (next to whatever the current stream does
+    next); _PropDensity's forward / backward of that slot then wait for the upload's event instead of copying the parameters themselves."""
+    flat = _flat_of(params)
+    slot = int(slot) % 4
+    if leaf_streams.enabled:
+        with leaf_streams.fork(flat):
+            call("nvo_prop_density_upload", slot, flat)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+    else:
+        call("nvo_prop_density_upload", slot, flat)
+        ev = None
+    _prop_resident[slot] = (ev, flat.data_ptr())
+
+
+def _prop_params_arg(slot: int, flat):
+    """None (after ordering the current stream behind the upload) when bank `slot` already holds `flat`, else `flat`."""
+    hit = _prop_resident.get(slot)
+    if hit is None or hit[1] != flat.data_ptr():
+        return flat
+    if hit[0] is not None:
+        torch.cuda.current_stream().wait_event(hit[0])
+    return None
+
+
 class _PropDensity(torch.autograd.Function):
     """density [B,S] at the samples of `iv` on rays (origins, directions), or at explicit `positions` [B*S,3]."""
 
@@ -399,8 +430,8 @@ class _PropDensity(torch.autograd.Function):
             check(origins, "origins", torch.float32, (B, 3))
             check(directions, "directions", torch.float32, (B, 3))
             s, e, stride = iv.triple()
-        call("nvo_prop_density_forward", gspec.desc(table.dtype, torch.float32), hidden, slot, B, S, origins, directions, s, e, stride, positions, table, flat,
-             density, feat)
+        call("nvo_prop_density_forward", gspec.desc(table.dtype, torch.float32), hidden, slot, B, S, origins, directions, s, e, stride, positions, table,
+             _prop_params_arg(slot, flat), density, feat)
         ctx.save_for_backward(table, flat, feat, origins, directions, positions)
         ctx.iv, ctx.gspec, ctx.hidden, ctx.slot, ctx.B, ctx.S, ctx.n_tensors = iv, gspec, hidden, slot, B, S, len(params)
         ctx.table_main_grad = getattr(table, "_nvo_main_grad", None)
@@ -428,8 +459,9 @@ class _PropDensity(torch.autograd.Function):
         else:
             s, e, stride = ctx.iv.triple()
         ddensity = ddensity.contiguous()
+        params_arg = _prop_params_arg(ctx.slot, flat)
         args = ("nvo_prop_density_backward", ctx.gspec.desc(table.dtype, torch.float32), ctx.hidden, ctx.slot, ctx.B, ctx.S, origins, directions, s, e, stride, positions,
-                flat, feat, ddensity, dtable, dflat)
+                params_arg, feat, ddensity, dtable, dflat)
         split = (need_dt and env_flag("NVO_PROP_BWD_SPLIT", True)) or need_rays
         if need_rays:
             d_o, d_d = ctx.sink if ctx.sink is not None else (torch.zeros((ctx.B, 3), dtype=torch.float32, device=dev),
@@ -443,7 +475,7 @@ class _PropDensity(torch.autograd.Function):
             n = ctx.B * ctx.S
             dft = torch.empty(tmh_numel(n, ctx.gspec.out_dim), dtype=torch.float32, device=dev)
             xq = torch.empty(((n + 127) // 128 * 128, 3), dtype=torch.float32, device=dev)
-            call("nvo_prop_density_backward_split", ctx.gspec.desc(table.dtype, torch.float32), ctx.hidden, ctx.slot, ctx.B, ctx.S, flat, feat, ddensity, dflat,
+            call("nvo_prop_density_backward_split", ctx.gspec.desc(table.dtype, torch.float32), ctx.hidden, ctx.slot, ctx.B, ctx.S, params_arg, feat, ddensity, dflat,
                  dft, xq)
             def ray_part():
                 dxn = grid_backward_input(xq[:n], table, dft, ctx.gspec, tmf=True)
@@ -1179,6 +1211,7 @@ def prepack_weights(nets) -> None:
 def clear_prepacked() -> None:
     _prepacked.clear()
     _field_prepacked.clear()
+    _prop_resident.clear()
 
 
 def mlp_tc_forward(x16, wimage, spec: MlpSpec, n: int, save: bool, row_mask=None):

@@ -217,6 +217,7 @@ class MappingTrainer:
         side = self.device.type == "cuda" and ops.leaf_streams.enabled
         self._fields_done = False
         self.model._before_field_forward = None
+        self.model._after_field_forward = None
         if side and self.defer_fields and pending:
             # the previous step's fields-group update next to this step's proposal sampling: optimizer (exchange) -> zero fill of the group's
             # gradient range -> this step's fp16 weight images, on the optimizer stream; the main stream joins before the field forward
@@ -242,17 +243,29 @@ class MappingTrainer:
                 if self._ray_grads is not None:
                     self._ray_grads.zero_()
         elif side:
-            # off the critical chain: the 74 MB zero fill of the flat gradient and the fp16 weight images of the three field networks
-            # run on side streams next to the proposal sampling; both are joined before their first consumer
+            # off the critical chain: the zero fill of the flat gradient and the fp16 weight images of the three field networks run on side
+            # streams; both are joined before their first consumer.  The fill is split: the proposal networks' range (11 MB) next to the first
+            # sampling kernel, the fields group's range (67 MB) behind the field forward, next to the render / loss kernels, which leave the
+            # HBM idle — at the start of the step its CTAs sat in front of the first proposal forward's (launched later at the same priority)
+            # and held the sampling chain back by the 18 us the fill takes (profiles/r02_timeline_final.csv vs r02_timeline_split_fill.csv)
+            n_f = self.groups[0][2] if (len(self.groups) >= 2 and os.environ.get("NVO_SPLIT_FILL", "1") == "1") else 0
             with ops.leaf_streams.fork(self.grad):
-                self.grad.zero_()
+                self.grad[n_f:].zero_()
                 if self._ray_grads is not None:
                     self._ray_grads.zero_()
+            if n_f > 0:
+                def _fill_fields(n_f=n_f):
+                    with ops.leaf_streams.fork(self.grad):
+                        self.grad[:n_f].zero_()
+                self.model._after_field_forward = _fill_fields
             self.model.field.prepack(self.model.config.num_nerf_samples_per_ray)
         else:
             self.grad.zero_()
             if self._ray_grads is not None:
                 self._ray_grads.zero_()
+        if side:
+            for pn in self.model.proposal_networks:
+                pn.preload()  # constant-memory banks of the fused proposal fields, filled next to the step's first kernels
         if self.datamanager is not None:
             if self.cam_group is not None and self.datamanager.camera_optimizer is None:
                 self.datamanager.camera_optimizer = self.model.camera_optimizer  # the step prologue applies the pose correction itself
@@ -277,6 +290,7 @@ class MappingTrainer:
         finally:
             self.model._leaf_renders = False
             self.model._before_field_forward = None
+            self.model._after_field_forward = None
         if side:
             ops.leaf_streams.join()  # the zero fill must have landed before the first backward kernel accumulates into the gradient
         # Early launch of the fields group's exchange next to the (deferred) proposal backward.  Measured (profiles/r01_timeline_*s9*.csv,
