@@ -151,6 +151,7 @@ def load_optimizer_state(optimizers: Dict, model_state, model, trainer) -> None:
             trainer.step_counts[gi].fill_(max(steps))
     if fused:
         trainer.load_full_moments(exp_avg, exp_avg_sq)
+        trainer.peer.reset_epochs()  # the step counters may have gone back: the exchange barriers' epoch flags follow (collective)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

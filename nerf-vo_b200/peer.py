@@ -140,6 +140,17 @@ class PeerBuffers:
         _lib.call("nvo_adam_exchange_groups2", oa, na, ma, va, step_a, ob, nb, mb, vb, step_b, self.rank, self.world, ctypes.addressof(self._h_params),
                   ctypes.addressof(self._h_grads), ctypes.addressof(self._h_flags), lr, beta1, beta2, eps, 1.0 / self.world)
 
+    def reset_epochs(self) -> None:
+        """COLLECTIVE.  Zeroes this rank's flag pads.  The exchange kernels' barriers wait for `flag >= epoch` with the epoch taken from the
+        group's device step counter, so whenever a counter is set BACK (the state restore behind MappingTrainer.capture()'s warm-up steps, a
+        checkpoint load) flags left at a later epoch would let the next barriers pass before the peers have arrived: reduce-scatter over
+        gradients that are still being written, identical replicas, wrong parameters.  Call it with no exchange in flight."""
+        torch.cuda.synchronize(self.device)
+        dist.barrier()
+        self.flags.zero_()
+        torch.cuda.synchronize(self.device)
+        dist.barrier()
+
     def error_word(self) -> int:
         """0 = healthy; 1 / 2 = a peer never signalled 'gradients ready' / 'replicas written' (bounded spin timed out) in any phase."""
         words = int(_lib.load().nvo_exchange_flag_words())

@@ -587,9 +587,13 @@ class MappingTrainer:
             for dst, src in zip([self.flat] + self._moment_tensors() + self._counters(), tensors):
                 dst.copy_(src)
         self.model.proposal_sampler._step, self.model.proposal_sampler._steps_since_update = ps_step, ps_ssu
-        if self.world_size > 1:
+        if self.peer is not None:
+            # the step counters went back: the exchange barriers' epoch flags must follow (PeerBuffers.reset_epochs; without it the first
+            # `warmup x variants` steps after capture() ran unsynchronised — tests/test_exchange.py::test_two_rank_trainer_deferred_fields_update)
+            self.peer.reset_epochs()
+        elif self.world_size > 1:
             torch.cuda.synchronize()
-            dist.barrier()  # fused arm: a peer must not start exchanging into replicas another rank is still restoring
+            dist.barrier()
 
     def flush(self) -> None:
         """Applies the deferred fields-group update of the last step (defer_fields_update=True); afterwards parameters, moments and step counters
