@@ -218,6 +218,7 @@ class MappingTrainer:
         self._fields_done = False
         self.model._before_field_forward = None
         self.model._after_field_forward = None
+        ev_fill = None
         if side and self.defer_fields and pending:
             # the previous step's fields-group update next to this step's proposal sampling: optimizer (exchange) -> zero fill of the group's
             # gradient range -> this step's fp16 weight images, on the optimizer stream; the main stream joins before the field forward
@@ -233,10 +234,14 @@ class MappingTrainer:
                     self._optimizer_group(0)
                 finally:
                     self._narrow_exchange = False
-                self.grad[:n_f].zero_()
                 self.model.field.prepack(self.model.config.num_nerf_samples_per_ray)
                 ev = torch.cuda.Event()
                 ev.record(self._opt_stream)
+                # the zero fill of the group's gradient range follows the exchange (peers read the gradients until its last barrier) but is
+                # not in front of the field forward: the main stream joins it before the backward
+                self.grad[:n_f].zero_()
+                ev_fill = torch.cuda.Event()
+                ev_fill.record(self._opt_stream)
             self.model._before_field_forward = lambda: torch.cuda.current_stream().wait_event(ev)
             with ops.leaf_streams.fork(self.grad):
                 self.grad[n_f:].zero_()
@@ -293,6 +298,8 @@ class MappingTrainer:
             self.model._after_field_forward = None
         if side:
             ops.leaf_streams.join()  # the zero fill must have landed before the first backward kernel accumulates into the gradient
+            if ev_fill is not None:
+                torch.cuda.current_stream().wait_event(ev_fill)
         # Early launch of the fields group's exchange next to the (deferred) proposal backward.  Measured (profiles/r01_timeline_*s9*.csv,
         # DESIGN.md section 6): on one GPU and at 2 ranks it does not pay — both sides want the same registers and the field chain loses the
         # proposal backward that used to fill its idle issue slots; from 4 ranks on the exchange is NVLink-bound, one CTA per SM carries it, and
