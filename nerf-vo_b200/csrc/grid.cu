@@ -113,7 +113,7 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
-template <typename RowT>
+template <typename RowT, bool PAIR>
 __global__ void __launch_bounds__(256, 2) k_grid_fwd_tmh_jac(const __grid_constant__ GridP p, int64_t n, int nch, const float* __restrict__ x,
                                                           const RowT* __restrict__ table, uint4* __restrict__ y, uint4* __restrict__ jac) {
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256, 2) k_grid_fwd_tmh_jac(const __grid_consta
             const int l = c * 4 + q;
             if (l < p.L) {
                 cs[q] = make_corner(px, py, pz, p.scale[l]);
-                gather_level(table + ((size_t)l << p.log2T), cs[q], mask, f[q]);
+                gather_level<RowT, PAIR>(table + ((size_t)l << p.log2T), cs[q], mask, f[q]);
             }
         }
 #pragma unroll
@@ -513,10 +513,14 @@ extern "C" int nvo_grid_forward_jac(const nvo_grid_desc* d, void* stream, int64_
     const int nch = ((2 * p.L + 15) & ~15) >> 3;
     const dim3 grid((unsigned int)(((n + 127) / 128 * 128 + 255) / 256), (unsigned int)nch);
     cudaStream_t st = (cudaStream_t)stream;
-    if (d->table_dtype == NVO_F32)
-        k_grid_fwd_tmh_jac<float2><<<grid, 256, 0, st>>>(p, n, nch, x, (const float2*)table, (uint4*)y, (uint4*)jac);
-    else
-        k_grid_fwd_tmh_jac<__half2><<<grid, 256, 0, st>>>(p, n, nch, x, (const __half2*)table, (uint4*)y, (uint4*)jac);
+    static const int pair = nvo_env_int("NVO_GRID_FWD_PAIR", 1);  // 0: eight plain gathers per level instead of paired 16-byte loads behind a branch
+    if (d->table_dtype == NVO_F32) {
+        if (pair)
+            k_grid_fwd_tmh_jac<float2, true><<<grid, 256, 0, st>>>(p, n, nch, x, (const float2*)table, (uint4*)y, (uint4*)jac);
+        else
+            k_grid_fwd_tmh_jac<float2, false><<<grid, 256, 0, st>>>(p, n, nch, x, (const float2*)table, (uint4*)y, (uint4*)jac);
+    } else
+        k_grid_fwd_tmh_jac<__half2, true><<<grid, 256, 0, st>>>(p, n, nch, x, (const __half2*)table, (uint4*)y, (uint4*)jac);
     NVO_CUDA_LAUNCH_CHECK("grid_forward_jac");
     return 0;
 }

@@ -87,7 +87,9 @@ __device__ __forceinline__ void load_row_pair(const __half2* t, uint32_t lo, flo
     a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
     b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
 }
-template <typename RowT>
+// PAIR = false: eight plain loads, no divergent branch — for kernels that are issue-bound rather than bound by the gathers (the fused proposal
+// forward: selectable with NVO_PROP_FWD_PAIR); the values are the same either way.
+template <typename RowT, bool PAIR = true>
 __device__ __forceinline__ void gather_level(const RowT* __restrict__ slab, const Corner& c, uint32_t mask, float2* f) {
     // reference corner k -> (x,y,z): 0=ccc 1=cfc 2=ffc 3=fcc 4=ccf 5=cff 6=fff 7=fcf.  For the (y,z) combination j = sy + 2*sz the
     // x-ceil member is corner kc[j] and the x-floor member corner kf[j]:  (f,f): 5,6   (c,f): 4,7   (f,c): 1,2   (c,c): 0,3
@@ -97,7 +99,7 @@ __device__ __forceinline__ void gather_level(const RowT* __restrict__ slab, cons
         const int sy = j & 1, sz = j >> 1;
         const uint32_t hyz = c.hy[sy] ^ c.hz[sz];
         const uint32_t idf = (c.hx[0] ^ hyz) & mask, idc = (c.hx[1] ^ hyz) & mask;
-        if ((idf ^ idc) == 1u) {
+        if (PAIR && (idf ^ idc) == 1u) {
             float2 lo, hi;
             load_row_pair(slab, idf & idc, lo, hi);  // idf & idc == min(idf, idc): the even row of the pair
             f[kf[j]] = (idf & 1u) ? hi : lo;
@@ -110,10 +112,10 @@ __device__ __forceinline__ void gather_level(const RowT* __restrict__ slab, cons
 }
 
 // one level of the encoding for one sample: all gathers issued back to back, then the interpolation
-template <typename RowT>
+template <typename RowT, bool PAIR = true>
 __device__ __forceinline__ float2 grid_level_forward(const RowT* __restrict__ slab, const Corner& c, uint32_t mask) {
     float2 f[8];
-    gather_level(slab, c, mask, f);
+    gather_level<RowT, PAIR>(slab, c, mask, f);
     return trilerp_ref(f, c);
 }
 

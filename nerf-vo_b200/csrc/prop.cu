@@ -79,7 +79,7 @@ __device__ __forceinline__ float prop_mlp(const float* f, float* h) {
 // consecutive samples) reads 256 / 512 contiguous bytes per warp while the forward (one thread = one sample) still writes whole sectors.
 __device__ __forceinline__ int64_t feat_slot(int64_t t) { return (t & ~(int64_t)127) + ((t & 3) << 5) + ((t & 127) >> 2); }
 
-template <int L, int SLOT, typename RowT>
+template <int L, int SLOT, typename RowT, bool PAIR>
 __global__ void __launch_bounds__(256) k_prop_fwd(const __grid_constant__ GridP p, int64_t N, int64_t Npad, int S, const float* __restrict__ o,
                                                   const float* __restrict__ d, const float* __restrict__ starts, const float* __restrict__ ends,
                                                   int64_t stride, const float* __restrict__ positions, const RowT* __restrict__ table,
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256) k_prop_fwd(const __grid_constant__ GridP 
 #pragma unroll
     for (int l = 0; l < L; ++l) {
         const Corner c = make_corner(q[0], q[1], q[2], p.scale[l]);
-        const float2 v = grid_level_forward(table + ((size_t)l << p.log2T), c, mask);
+        const float2 v = grid_level_forward<RowT, PAIR>(table + ((size_t)l << p.log2T), c, mask);
         f[2 * l] = v.x;
         f[2 * l + 1] = v.y;
         if (feat) feat[(int64_t)l * Npad + slot] = v;
@@ -346,10 +346,14 @@ template <int SLOT>
 static void launch_fwd(const nvo_grid_desc* g, const GridP& p, cudaStream_t st, int64_t N, int64_t Npad, int S, const float* o, const float* d, const float* s,
                        const float* e, int64_t stride, const float* positions, const void* table, float* density, float* feat) {
     const unsigned int grid = nvo_blocks(N, 256);
-    if (g->table_dtype == NVO_F32)
-        k_prop_fwd<5, SLOT, float2><<<grid, 256, 0, st>>>(p, N, Npad, S, o, d, s, e, stride, positions, (const float2*)table, density, (float2*)feat);
-    else
-        k_prop_fwd<5, SLOT, __half2><<<grid, 256, 0, st>>>(p, N, Npad, S, o, d, s, e, stride, positions, (const __half2*)table, density, (float2*)feat);
+    static const int pair = nvo_env_int("NVO_PROP_FWD_PAIR", 0);  // 0 (default): eight plain gathers per level; 1: paired 16-byte loads behind a divergent branch (54 vs 41 us: the kernel is issue-bound)
+    if (g->table_dtype == NVO_F32) {
+        if (pair)
+            k_prop_fwd<5, SLOT, float2, true><<<grid, 256, 0, st>>>(p, N, Npad, S, o, d, s, e, stride, positions, (const float2*)table, density, (float2*)feat);
+        else
+            k_prop_fwd<5, SLOT, float2, false><<<grid, 256, 0, st>>>(p, N, Npad, S, o, d, s, e, stride, positions, (const float2*)table, density, (float2*)feat);
+    } else
+        k_prop_fwd<5, SLOT, __half2, true><<<grid, 256, 0, st>>>(p, N, Npad, S, o, d, s, e, stride, positions, (const __half2*)table, density, (float2*)feat);
 }
 
 extern "C" int nvo_prop_density_forward(const nvo_grid_desc* g, int32_t hidden, int32_t slot, void* stream, int64_t B, int32_t S, const float* origins,
