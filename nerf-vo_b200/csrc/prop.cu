@@ -57,21 +57,31 @@ __device__ __forceinline__ void sample_point(int64_t t, int S, const float* __re
 __constant__ float c_prop[PROP_SLOTS][PROP_SLOT_FLOATS];
 __constant__ float c_propb[PROP_SLOTS][PROP_SLOT_FLOATS];
 
-// hidden layer + output pre-activation, accumulation order of the SIMT reference kernel (bias first, inputs ascending)
+// Packed fp32 FMAs (sm_100 FFMA2: two IEEE fmas per instruction, each rounded like fmaf).  These kernels are issue-bound, not FMA-pipe-bound, and
+// half of their instructions are the MLP's multiply-adds: pairing them frees issue slots for the hashing / address / interpolation work.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 cw2(const float* w) { return *reinterpret_cast<const float2*>(w); }  // two adjacent weights (8-byte aligned)
+
+// hidden layer + output pre-activation.  Each output accumulates its even and its odd inputs in the two halves of one packed accumulator
+// (bias in the even half, inputs ascending in each half), summed at the end; forward and the backward's recomputation share this function.
 template <int L, int SLOT>
 __device__ __forceinline__ float prop_mlp(const float* f, float* h) {
     using PL = PropLayout<L>;
-    float z = c_prop[SLOT][PL::B1];
+    static_assert(PL::IN % 2 == 0 && PH % 2 == 0, "packed FMAs pair adjacent inputs / hidden units");
+    float2 f2[PL::IN / 2];
+#pragma unroll
+    for (int i = 0; i < PL::IN / 2; ++i) f2[i] = make_float2(f[2 * i], f[2 * i + 1]);
 #pragma unroll
     for (int j = 0; j < PH; ++j) {
-        float acc = c_prop[SLOT][PL::B0 + j];
+        float2 acc = make_float2(c_prop[SLOT][PL::B0 + j], 0.f);
 #pragma unroll
-        for (int i = 0; i < PL::IN; ++i) acc = fmaf(c_prop[SLOT][PL::W0 + j * PL::IN + i], f[i], acc);
-        h[j] = fmaxf(acc, 0.f);
+        for (int i = 0; i < PL::IN / 2; ++i) acc = ffma2(cw2(&c_prop[SLOT][PL::W0 + j * PL::IN + 2 * i]), f2[i], acc);
+        h[j] = fmaxf(acc.x + acc.y, 0.f);
     }
+    float2 z = make_float2(c_prop[SLOT][PL::B1], 0.f);
 #pragma unroll
-    for (int j = 0; j < PH; ++j) z = fmaf(c_prop[SLOT][PL::W1 + j], h[j], z);
-    return z;
+    for (int j = 0; j < PH / 2; ++j) z = ffma2(cw2(&c_prop[SLOT][PL::W1 + 2 * j]), make_float2(h[2 * j], h[2 * j + 1]), z);
+    return z.x + z.y;
 }
 
 // Saved-for-backward layout (opaque `feat` buffer): features level-major [L][Npad] float2, then [Npad] float4 = (normalised position,
@@ -194,20 +204,30 @@ __global__ void __launch_bounds__(PROP_BWD_THREADS, SPLIT ? 5 : 4) k_prop_bwd(co
 #pragma unroll
             for (int j = 0; j < PH; ++j) dh[j] = h[j] > 0.f ? dz * c_propb[SLOT][PL::W1 + j] : 0.f;
             {
-                float df[PL::IN];
+                float2 df[PL::IN / 2];  // df[i] = sum_j W0[j][i] dh[j], hidden units ascending: two adjacent inputs per packed FMA
 #pragma unroll
-                for (int i = 0; i < PL::IN; ++i) df[i] = 0.f;
+                for (int i = 0; i < PL::IN / 2; ++i) df[i] = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int j = 0; j < PH; ++j) {
+                    const float2 d2 = make_float2(dh[j], dh[j]);
 #pragma unroll
-                    for (int i = 0; i < PL::IN; ++i) df[i] = fmaf(c_propb[SLOT][PL::W0 + j * PL::IN + i], dh[j], df[i]);
+                    for (int i = 0; i < PL::IN / 2; ++i) df[i] = ffma2(cw2(&c_propb[SLOT][PL::W0 + j * PL::IN + 2 * i]), d2, df[i]);
                 }
 #pragma unroll
-                for (int i = 0; i < PL::IN; ++i) dfs[(g * PL::IN + i) * 32 + lane] = df[i];
+                for (int i = 0; i < PL::IN / 2; ++i) {
+                    dfs[(g * PL::IN + 2 * i) * 32 + lane] = df[i].x;
+                    dfs[(g * PL::IN + 2 * i + 1) * 32 + lane] = df[i].y;
+                }
             }
             if (dparams && nz != 0u) {
+                {
+                    const float2 dz2 = make_float2(dz, dz);
 #pragma unroll
-                for (int j = 0; j < PH; ++j) accw1[j] = fmaf(dz, h[j], accw1[j]);
+                    for (int j = 0; j < PH / 2; ++j) {
+                        const float2 a = ffma2(dz2, make_float2(h[2 * j], h[2 * j + 1]), make_float2(accw1[2 * j], accw1[2 * j + 1]));
+                        accw1[2 * j] = a.x, accw1[2 * j + 1] = a.y;
+                    }
+                }
                 accb1 += dz;
                 float4* row = reinterpret_cast<float4*>(stage + lane * SM::RS);
 #pragma unroll
@@ -221,13 +241,14 @@ __global__ void __launch_bounds__(PROP_BWD_THREADS, SPLIT ? 5 : 4) k_prop_bwd(co
                     const float* r = stage + ((k >> 2) * 8 + hw * 4 + (k & 3)) * SM::RS;
                     const float2 gj = *reinterpret_cast<const float2*>(r + SM::S_DH + 2 * jp);
                     const float2* fe = reinterpret_cast<const float2*>(r + SM::S_F + 6 * ch);
+                    const float2 gx = make_float2(gj.x, gj.x), gy = make_float2(gj.y, gj.y);
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         const float2 v = fe[c];
-                        acc0[0][2 * c] = fmaf(gj.x, v.x, acc0[0][2 * c]);
-                        acc0[0][2 * c + 1] = fmaf(gj.x, v.y, acc0[0][2 * c + 1]);
-                        acc0[1][2 * c] = fmaf(gj.y, v.x, acc0[1][2 * c]);
-                        acc0[1][2 * c + 1] = fmaf(gj.y, v.y, acc0[1][2 * c + 1]);
+                        const float2 a = ffma2(gx, v, make_float2(acc0[0][2 * c], acc0[0][2 * c + 1]));
+                        const float2 b = ffma2(gy, v, make_float2(acc0[1][2 * c], acc0[1][2 * c + 1]));
+                        acc0[0][2 * c] = a.x, acc0[0][2 * c + 1] = a.y;
+                        acc0[1][2 * c] = b.x, acc0[1][2 * c + 1] = b.y;
                     }
                 }
                 __syncwarp();
