@@ -54,23 +54,21 @@ __device__ __forceinline__ float2 load_row(const __half2* t, size_t i) { return 
 // a*w + b*(1-w) with the reference's rounding sequence (mul, mul, add)
 __device__ __forceinline__ float lerp_ref(float a, float b, float w, float omw) { return __fadd_rn(__fmul_rn(a, w), __fmul_rn(b, omw)); }
 
-// trilinear interpolation of the 8 gathered rows in the reference's order (encodings.py:453-463)
+// trilinear interpolation of the 8 gathered rows in the reference's order (encodings.py:453-463).  Both features of a row go through one packed
+// instruction (sm_100 FMUL2 / FADD2: each half rounded like the scalar op, no contraction): 21 instead of 42 instructions per level, same bits.
+// (The same packing in the scatter's CellRun measured neutral to slightly slower — 94 registers, extra moves — and was not kept.)
+__device__ __forceinline__ float2 lerp_ref2(float2 a, float2 b, float2 w, float2 omw) { return __fadd2_rn(__fmul2_rn(a, w), __fmul2_rn(b, omw)); }
 __device__ __forceinline__ float2 trilerp_ref(const float2* f, const Corner& c) {
     const float mx = __fsub_rn(1.f, c.ox), my = __fsub_rn(1.f, c.oy), mz = __fsub_rn(1.f, c.oz);
-    float out[2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-#define FJ(k) (j == 0 ? f[k].x : f[k].y)
-        const float f03 = lerp_ref(FJ(0), FJ(3), c.ox, mx);
-        const float f12 = lerp_ref(FJ(1), FJ(2), c.ox, mx);
-        const float f56 = lerp_ref(FJ(5), FJ(6), c.ox, mx);
-        const float f47 = lerp_ref(FJ(4), FJ(7), c.ox, mx);
-        const float f0312 = lerp_ref(f03, f12, c.oy, my);
-        const float f4756 = lerp_ref(f47, f56, c.oy, my);
-        out[j] = lerp_ref(f0312, f4756, c.oz, mz);
-#undef FJ
-    }
-    return make_float2(out[0], out[1]);
+    const float2 ox2 = make_float2(c.ox, c.ox), mx2 = make_float2(mx, mx), oy2 = make_float2(c.oy, c.oy), my2 = make_float2(my, my);
+    const float2 oz2 = make_float2(c.oz, c.oz), mz2 = make_float2(mz, mz);
+    const float2 f03 = lerp_ref2(f[0], f[3], ox2, mx2);
+    const float2 f12 = lerp_ref2(f[1], f[2], ox2, mx2);
+    const float2 f56 = lerp_ref2(f[5], f[6], ox2, mx2);
+    const float2 f47 = lerp_ref2(f[4], f[7], ox2, mx2);
+    const float2 f0312 = lerp_ref2(f03, f12, oy2, my2);
+    const float2 f4756 = lerp_ref2(f47, f56, oy2, my2);
+    return lerp_ref2(f0312, f4756, oz2, mz2);
 }
 
 // Gather of the 8 corner rows of one (sample, level) into f[k] (reference corner numbering).  The hash is linear in x
