@@ -407,7 +407,8 @@ static int launch_bwd(const GridP& p, cudaStream_t st, int64_t N, int64_t Npad, 
     if (df_tmf) {
         cudaError_t err = cudaFuncSetAttribute(k_prop_bwd<5, SLOT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         NVO_CHECK(err == cudaSuccess, "prop_density_backward: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
-        const unsigned int grid = (unsigned int)min(blocks, (int64_t)nvo_sm_count() * 10);
+        static const int ctas_per_sm = nvo_env_int("NVO_PROP_BWD_CTAS", 10);  // grid cap in CTAs per SM (5 fit at once: 40 KB of shared memory each)
+        const unsigned int grid = (unsigned int)min(blocks, (int64_t)nvo_sm_count() * ctas_per_sm);
         k_prop_bwd<5, SLOT, true><<<grid, PROP_BWD_THREADS, smem, st>>>(p, N, Npad, S, (const float2*)feat, ddensity, nullptr, dparams, df_tmf, xq);
         return 0;
     }
